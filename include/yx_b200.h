@@ -1,0 +1,237 @@
+/*
+ * yx_b200.h — C-ABI of the B200-native (sm_100a) YOLOX detection hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a
+ * `cudaStream_t` passed as `void*`, returns 0 on success or a negative
+ * `yx_status` code, never throws and never synchronises the host (all work is
+ * enqueued on `stream`, so the calls are CUDA-graph capturable).  There are no
+ * torch types in any signature; PyTorch only owns the memory the pointers refer
+ * to.  All activations are NHWC ("channels-last"), 16-bit (bf16/fp16) on the
+ * tensor-core path or fp32 on the verification path; channel counts and channel
+ * offsets are multiples of 8 elements so that every pixel row is 16-byte aligned.
+ *
+ * The reference (yhenon/pixeltable-yolox, a pure-PyTorch library) has no FFI of
+ * its own; each entry point below names the reference function (file:line under
+ * /root/reference) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ */
+#ifndef YX_B200_H_
+#define YX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YX_VERSION 100 /* 0.1.0 */
+
+typedef enum yx_status {
+  YX_OK = 0,
+  YX_ERR_INVALID_ARG = -1,   /* bad shape / alignment / null pointer              */
+  YX_ERR_UNSUPPORTED = -2,   /* shape outside what the sm_100a kernels implement  */
+  YX_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed (see yx_last_error) */
+  YX_ERR_NO_DEVICE = -4,     /* no sm_100 device visible: there is NO CPU fallback */
+  YX_ERR_CAPACITY = -5       /* a caller-provided workspace/output is too small   */
+} yx_status;
+
+typedef enum yx_dtype { YX_BF16 = 0, YX_FP16 = 1, YX_FP32 = 2, YX_U8 = 3 } yx_dtype;
+typedef enum yx_act { YX_ACT_NONE = 0, YX_ACT_SILU = 1, YX_ACT_RELU = 2, YX_ACT_LRELU = 3 } yx_act;
+
+/* Epilogue of the implicit-GEMM conv. */
+typedef enum yx_epilogue {
+  YX_EPI_STORE = 0, /* y = act(acc + bias) (+ residual) -> NHWC activation, dtype of the input */
+  YX_EPI_HEAD = 1   /* YOLOX head: acc+bias -> [B, A, 5+nc] fp32 with decode/sigmoid fused
+                       (yolox/models/yolo_head.py:185-187,205-207,233-251)                     */
+} yx_epilogue;
+
+const char* yx_strerror(int code);
+/* Last error message of the calling thread (CUDA error string, failed check ...). */
+const char* yx_last_error(void);
+int yx_version(void);
+/* 0 when device `dev` is an sm_100 part and the kernels can run, else YX_ERR_NO_DEVICE. */
+int yx_device_check(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense conv + folded BN + activation as one implicit GEMM
+ *   replaces BaseConv.forward  (yolox/models/network_blocks.py:27-52, act(bn(conv(x))))
+ *   and the biased 1x1 prediction convs of YoloxHead (yolox/models/yolo_head.py:94-120).
+ *   BN folding follows fuse_conv_and_bn (yolox/utils/model_utils.py:33-75).
+ *
+ * GEMM view: M = batch*out_h*out_w pixels, N = out_c, K = ksize*ksize*in_c.
+ *   in  : NHWC, `in_c` channels read starting at `in` with a per-pixel stride of `in_ld`
+ *         elements (so a channel slice of a wider concat buffer is a valid input);
+ *   w   : [out_c][ksize*ksize][in_c] (K-major), BN scale folded in, same dtype as `in`;
+ *   bias: [out_c] fp32 (folded BN shift, or the pred-conv bias);
+ *   out : NHWC slice, per-pixel stride `out_ld`; `res` (optional) is added AFTER the
+ *         activation (Bottleneck shortcut, network_blocks.py:95-99);
+ *   ups : optional second destination that receives the result replicated 2x2
+ *         (nn.Upsample(scale_factor=2, "nearest") fused into the producer:
+ *         yolox/models/yolo_pafpn.py:97-99,102-104); its spatial size is 2*out_h x 2*out_w.
+ * Constraints: ksize in {1,3}; stride in {1,2}; pad = (ksize-1)/2; in_c % 16 == 0;
+ *   out_c % 16 == 0; all *_ld % 8 == 0; pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yx_conv_desc {
+  int32_t batch, in_h, in_w, in_c;
+  int32_t out_h, out_w, out_c;
+  int32_t ksize, stride;
+  int32_t dtype;    /* yx_dtype of in/w/out/res: YX_BF16 | YX_FP16 (tcgen05) | YX_FP32 (SIMT) */
+  int32_t act;      /* yx_act */
+  int32_t epilogue; /* yx_epilogue */
+  const void* in;   int64_t in_ld;
+  const void* w;
+  const float* bias;
+  void* out;        int64_t out_ld;
+  const void* res;  int64_t res_ld;
+  void* ups;        int64_t ups_ld;
+  /* YX_EPI_HEAD only: out_c (>= 5+nc, padded) accumulators per pixel are written as fp32 rows
+   * head_out[(b*head_anchors + head_anchor_off + y*out_w + x)*(5+head_nc) + c], c < 5+nc.
+   * head_decode is a bit set:  bit0 = box decode: c<2 -> (v + grid)*head_stride,
+   * c in {2,3} -> exp(v)*head_stride;  bit1 = sigmoid on c >= 4 (obj, cls).
+   *   3 = eval with decode_in_inference (yolo_head.py:185-187, 233-251)
+   *   2 = eval with decode_in_inference=False (yolo_head.py:208-211)
+   *   1 = training branch: decoded boxes, raw logits (yolo_head.py:161-166, 213-231)
+   *   0 = raw prediction-conv outputs */
+  float* head_out;
+  int32_t head_anchors, head_anchor_off, head_nc, head_decode;
+  float head_stride;
+} yx_conv_desc;
+
+/* tcgen05/TMEM/TMA implicit GEMM for bf16/fp16; routes YX_FP32 to the SIMT kernel. */
+int yx_conv_bn_act_fwd(const yx_conv_desc* d, void* stream);
+/* CUDA-core (FFMA, fp32 accumulate in K order) implementation of the same contract for every
+ * dtype: the fp32 verification mode and the on-device cross-check of the tensor-core kernel. */
+int yx_conv_bn_act_fwd_simt(const yx_conv_desc* d, void* stream);
+
+/* Depthwise 3x3 conv + folded BN + act (DWConv.dconv, network_blocks.py:55-67), NHWC.
+ *   w: [9][c] (tap-major) in `dtype`, bias [c] fp32. stride in {1,2}, pad 1. */
+int yx_dwconv3x3_bn_act_fwd(const void* in, int64_t in_ld, const void* w, const float* bias,
+                            void* out, int64_t out_ld, int32_t batch, int32_t in_h, int32_t in_w,
+                            int32_t c, int32_t stride, int32_t act, int32_t dtype, void* stream);
+
+/* SPP max pools (SPPBottleneck, network_blocks.py:120-142): reads c channels at `buf`
+ * (pixel stride ld) and writes maxpool5/9/13 (stride 1, -inf padding) to channel offsets
+ * c, 2c, 3c of the same buffer, i.e. completes cat[x, m5(x), m9(x), m13(x)] in place. */
+int yx_spp_maxpool(void* buf, int64_t ld, int32_t batch, int32_t h, int32_t w, int32_t c,
+                   int32_t dtype, void* stream);
+
+/* Focus space-to-depth (network_blocks.py:193-208): NCHW image [B,3,H,W] (fp32 or uint8,
+ * raw 0..255) -> NHWC [B,H/2,W/2,out_ld] with channels (TL,BL,TR,BR) x (c0,c1,c2) = 12 real
+ * channels, the rest zero. */
+int yx_focus_s2d(const void* img, int32_t img_dtype, void* out, int64_t out_ld, int32_t out_dtype,
+                 int32_t batch, int32_t h, int32_t w, void* stream);
+
+/* Fold BN into a conv and repack it for yx_conv_bn_act_fwd (model_utils.py:33-75):
+ *   src    : [o][i][kh][kw] fp32 (nn.Conv2d.weight); gamma/beta/mean/var [o] fp32 or NULL
+ *            (plain conv); conv_bias [o] fp32 or NULL;
+ *   dst_w  : packed [dst_o_total][kh*kw][dst_i_total]; rows o land at dst_o_off + o, columns i
+ *            at dst_i_off + i (everything else is left untouched: zero the buffer first);
+ *   dst_b  : fp32 [dst_o_total], written at dst_o_off + o.
+ * depthwise != 0 packs [c][1][3][3] -> [9][dst_i_total] (tap-major) instead. */
+int yx_pack_weights(const float* src, const float* gamma, const float* beta, const float* mean,
+                    const float* var, const float* conv_bias, float eps, int32_t o, int32_t i,
+                    int32_t kh, int32_t kw, void* dst_w, int32_t dst_dtype, int32_t dst_o_off,
+                    int32_t dst_i_off, int32_t dst_i_total, float* dst_b, int32_t depthwise,
+                    void* stream);
+
+/* Standalone decode of an undecoded [B, A, 5+nc] fp32 tensor in place
+ * (YoloxHead.decode_outputs, yolo_head.py:233-251). hw: 2*n_levels ints (h,w per level). */
+int yx_head_decode(float* pred, int32_t batch, int32_t anchors, int32_t nc, const int32_t* hw,
+                   const int32_t* strides, int32_t n_levels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * postprocess: score filter + class-aware NMS  (yolox/utils/boxes.py:31-75 and the
+ * third-party torchvision.ops.batched_nms it calls, boxes.py:62-67).
+ *   pred      : [B, A, 5+nc] fp32 (cx,cy,w,h,obj,cls...). When `inplace_xyxy` != 0 the first
+ *               four columns are overwritten with (x1,y1,x2,y2) exactly like boxes.py:32-37.
+ *   dets      : [B, max_det, 7] fp32 rows (x1,y1,x2,y2,obj,class_conf,class_pred) in
+ *               descending-score order; det_idx [B, max_det] int64 anchor index of each kept
+ *               row; det_count [B] int32.
+ *   nms_variant: 0 = coordinate-offset trick (torchvision CUDA path for <= 100k coordinates),
+ *               1 = per-class ("vanilla", torchvision CPU path above 4000 coordinates),
+ *               2 = class-agnostic (boxes.py:55-60),
+ *               3 / 4 = what torchvision itself picks per image on CUDA / on CPU:
+ *               the offset trick unless 4*n_candidates > 100000 (CUDA) / 4000 (CPU), else per-class.
+ *   workspace : yx_postprocess_workspace_bytes(B, A) bytes of device scratch.
+ * ------------------------------------------------------------------------------------------ */
+int64_t yx_postprocess_workspace_bytes(int32_t batch, int32_t anchors);
+int yx_postprocess(float* pred, int32_t batch, int32_t anchors, int32_t nc, float conf_thre,
+                   double nms_thre, int32_t nms_variant, int32_t inplace_xyxy, float* dets,
+                   int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* The two stages of yx_postprocess on their own (parity tests, SURVEY 8b export list); both use
+ * a workspace of yx_postprocess_workspace_bytes(batch, anchors | n_max) bytes.
+ * conf_thre is compared in fp32 (torch casts the Python scalar to the tensor dtype, boxes.py:48);
+ * nms_thre is a double because torchvision's CPU kernel compares the fp32 IoU with a double.
+ * yx_score_filter_compact: candidates in ascending anchor order: cand [B, A, 8] fp32 rows
+ *   (x1,y1,x2,y2,obj,class_conf,class_pred,score), cand_idx [B, A] int32, cand_count [B].
+ * yx_batched_nms: boxes [B, n_max, 4] xyxy, scores [B, n_max], cls [B, n_max] (int32),
+ *   counts [B]; keep [B, n_max] int32 indices (into the per-image candidate list) in
+ *   descending score order, keep_count [B]. */
+int yx_score_filter_compact(const float* pred, int32_t batch, int32_t anchors, int32_t nc,
+                            float conf_thre, float* cand, int32_t* cand_idx, int32_t* cand_count,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+int yx_batched_nms(const float* boxes, const float* scores, const int32_t* cls,
+                   const int32_t* counts, int32_t batch, int32_t n_max, double nms_thre,
+                   int32_t nms_variant, int32_t* keep, int32_t* keep_count, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* Pairwise IoU (yolox/utils/boxes.py:78-101): a [n,4], b [m,4] fp32 -> out [n,m]. */
+int yx_bboxes_iou(const float* a, int32_t n, const float* b, int32_t m, int32_t xyxy, float* out,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SimOTA label assignment (YoloxHead.get_assignments / get_geometry_constraint /
+ * simota_matching, yolox/models/yolo_head.py:420-574), batched over images, no host sync.
+ *   pred   : [B, A, 5+nc] fp32 training-branch head output (decoded boxes, raw obj/cls logits)
+ *   labels : [B, max_gt, 5] fp32 rows (cls, cx, cy, w, h), zero padded (data_augment.py:200-208)
+ *   anchor grid: x_shift[A], y_shift[A], stride[A] fp32 (yolo_head.py:213-231)
+ * outputs (dense over anchors):
+ *   fg_mask [B, A] uint8, matched_gt [B, A] int32 (-1 when not foreground),
+ *   matched_iou [B, A] fp32, matched_cls [B, A] int32, num_fg [B] int32, num_gt [B] int32.
+ *   workspace: yx_simota_workspace_bytes(B, A, max_gt) bytes.
+ * ------------------------------------------------------------------------------------------ */
+int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt);
+int yx_simota_assign(const float* pred, const float* labels, const float* x_shift,
+                     const float* y_shift, const float* stride_per_anchor, int32_t batch,
+                     int32_t anchors, int32_t nc, int32_t max_gt, uint8_t* fg_mask,
+                     int32_t* matched_gt, float* matched_iou, int32_t* matched_cls,
+                     int32_t* num_fg, int32_t* num_gt, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+/* simota_matching alone (yolo_head.py:542-574) on a given cost / IoU matrix [G, n] fp32
+ * (row stride ld): match_gt [n] int32 (-1 = not matched), match_iou [n] fp32, num_fg[1]. */
+int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int32_t n,
+                       int64_t ld, int32_t* match_gt, float* match_iou, int32_t* num_fg,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Plan: the native runtime.  A plan is an ordered list of the launches of one forward pass
+ * (YoloxModule.forward eval branch, yolox/models/yolox.py:72-92) over pre-allocated buffers.
+ * Tensor maps are encoded once at add time; yx_plan_run enqueues every launch on `stream`
+ * from C++ (one FFI call per forward) and can replay them as one CUDA graph.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yx_plan yx_plan;
+yx_plan* yx_plan_create(void);
+void yx_plan_destroy(yx_plan* p);
+int yx_plan_add_conv(yx_plan* p, const yx_conv_desc* d);
+int yx_plan_add_dwconv(yx_plan* p, const void* in, int64_t in_ld, const void* w, const float* bias,
+                       void* out, int64_t out_ld, int32_t batch, int32_t in_h, int32_t in_w,
+                       int32_t c, int32_t stride, int32_t act, int32_t dtype);
+int yx_plan_add_spp(yx_plan* p, void* buf, int64_t ld, int32_t batch, int32_t h, int32_t w,
+                    int32_t c, int32_t dtype);
+int yx_plan_add_focus(yx_plan* p, const void* img, int32_t img_dtype, void* out, int64_t out_ld,
+                      int32_t out_dtype, int32_t batch, int32_t h, int32_t w);
+int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anchors, int32_t nc,
+                            float conf_thre, double nms_thre, int32_t nms_variant,
+                            int32_t inplace_xyxy, float* dets, int64_t* det_idx,
+                            int32_t* det_count, int32_t max_det, void* workspace,
+                            int64_t workspace_bytes);
+int yx_plan_num_launches(const yx_plan* p);
+/* use_graph != 0: capture on first use, replay afterwards. */
+int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YX_B200_H_ */

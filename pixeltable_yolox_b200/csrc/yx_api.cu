@@ -1,0 +1,418 @@
+// C-ABI (include/yx_b200.h) and the plan runtime: an ordered list of pre-encoded launches for
+// one YoloxModule.forward (yolox/models/yolox.py:72-92) + postprocess (utils/boxes.py:31-75),
+// enqueued from C++ in one FFI call and replayable as a CUDA graph.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "yx_epilogue.cuh"
+
+namespace yx {
+
+// ---- implemented in the kernel translation units ----
+struct ConvTcParams;
+struct ConvTcLaunch;
+int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L);
+int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream);
+int conv_simt_launch(const yx_conv_desc* d, cudaStream_t stream);
+int focus_launch(const void* img, int img_dtype, void* out, long long out_ld, int out_dtype, int batch, int h, int w, cudaStream_t s);
+int spp_launch(void* buf, long long ld, int batch, int h, int w, int c, int dtype, cudaStream_t s);
+int dwconv_launch(const void* in, long long in_ld, const void* w, const float* bias, void* out, long long out_ld,
+                  int batch, int in_h, int in_w, int c, int stride, int act, int dtype, cudaStream_t s);
+int pack_launch(const float* src, const float* gamma, const float* beta, const float* mean, const float* var,
+                const float* conv_bias, float eps, int o, int i, int kh, int kw, void* dst_w, int dst_dtype,
+                int dst_o_off, int dst_i_off, int dst_i_total, float* dst_b, int depthwise, cudaStream_t s);
+int decode_launch(float* pred, int batch, int anchors, int nc, const int* hw, const int* strides, int n_levels, cudaStream_t s);
+int iou_launch(const float* a, int n, const float* b, int m, int xyxy, float* out, cudaStream_t s);
+long long postprocess_ws_bytes(int batch, int anchors);
+int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_thre, double nms_thre, int nms_variant,
+                       int inplace_xyxy, float* dets, long long* det_idx, int* det_count, int max_det, void* ws,
+                       long long ws_bytes, cudaStream_t s);
+int filter_compact_launch(const float* pred, int batch, int anchors, int nc, float conf_thre, float* cand,
+                          int* cand_idx, int* cand_count, void* ws, long long ws_bytes, cudaStream_t s);
+int batched_nms_launch(const float* boxes, const float* scores, const int* cls, const int* counts, int batch,
+                       int n_max, double nms_thre, int nms_variant, int* keep, int* keep_count, void* ws,
+                       long long ws_bytes, cudaStream_t s);
+long long simota_ws_bytes(int batch, int anchors, int max_gt);
+int simota_assign_launch(const float* pred, const float* labels, const float* xs, const float* ys, const float* st,
+                         int batch, int anchors, int nc, int max_gt, unsigned char* fg_mask, int* matched_gt,
+                         float* matched_iou, int* matched_cls, int* num_fg, int* num_gt, void* ws, long long ws_bytes,
+                         cudaStream_t s);
+int simota_matching_launch(const float* cost, const float* ious, int G, int n, long long ld, int* match_gt,
+                           float* match_iou, int* num_fg, cudaStream_t s);
+size_t conv_tc_launch_size();
+ConvTcLaunch* conv_tc_alloc();
+void conv_tc_free(ConvTcLaunch*);
+
+// ---- error plumbing ----
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return YX_ERR_NO_DEVICE;
+  return YX_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+static int require_device() {
+  static int ok = 0;
+  if (ok) return YX_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute", __FILE__, __LINE__);
+  YX_REQUIRE(major == 10, YX_ERR_NO_DEVICE,
+             "device %d has compute capability %d.x; these kernels are built for sm_100a only (no fallback)", dev, major);
+  ok = 1;
+  return YX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST };
+
+struct Op {
+  OpKind kind;
+  ConvTcLaunch* tc;  // OP_CONV_TC
+  yx_conv_desc conv;  // OP_CONV_SIMT
+  struct { const void* in; long long in_ld; const void* w; const float* bias; void* out; long long out_ld;
+           int batch, in_h, in_w, c, stride, act, dtype; } dw;
+  struct { void* buf; long long ld; int batch, h, w, c, dtype; } spp;
+  struct { const void* img; int img_dtype; void* out; long long out_ld; int out_dtype, batch, h, w; } focus;
+  struct { float* pred; int batch, anchors, nc; float conf; double nms; int variant, inplace; float* dets;
+           long long* det_idx; int* det_count; int max_det; void* ws; long long ws_bytes; } post;
+};
+
+}  // namespace yx
+
+struct yx_plan {
+  std::vector<yx::Op> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+
+namespace yx {
+
+static int run_op(const Op& o, cudaStream_t s) {
+  switch (o.kind) {
+    case OP_CONV_TC: return conv_tc_launch(o.tc, s);
+    case OP_CONV_SIMT: return conv_simt_launch(&o.conv, s);
+    case OP_DWCONV: return dwconv_launch(o.dw.in, o.dw.in_ld, o.dw.w, o.dw.bias, o.dw.out, o.dw.out_ld, o.dw.batch,
+                                         o.dw.in_h, o.dw.in_w, o.dw.c, o.dw.stride, o.dw.act, o.dw.dtype, s);
+    case OP_SPP: return spp_launch(o.spp.buf, o.spp.ld, o.spp.batch, o.spp.h, o.spp.w, o.spp.c, o.spp.dtype, s);
+    case OP_FOCUS: return focus_launch(o.focus.img, o.focus.img_dtype, o.focus.out, o.focus.out_ld, o.focus.out_dtype,
+                                       o.focus.batch, o.focus.h, o.focus.w, s);
+    case OP_POST: return postprocess_launch(o.post.pred, o.post.batch, o.post.anchors, o.post.nc, o.post.conf, o.post.nms,
+                                            o.post.variant, o.post.inplace, o.post.dets, o.post.det_idx, o.post.det_count,
+                                            o.post.max_det, o.post.ws, o.post.ws_bytes, s);
+  }
+  return YX_ERR_INVALID_ARG;
+}
+
+}  // namespace yx
+
+using namespace yx;
+
+extern "C" {
+
+const char* yx_strerror(int code) {
+  switch (code) {
+    case YX_OK: return "ok";
+    case YX_ERR_INVALID_ARG: return "invalid argument";
+    case YX_ERR_UNSUPPORTED: return "unsupported shape";
+    case YX_ERR_CUDA: return "CUDA error";
+    case YX_ERR_NO_DEVICE: return "no sm_100 device (there is no CPU fallback)";
+    case YX_ERR_CAPACITY: return "workspace or output too small";
+    default: return "unknown error";
+  }
+}
+const char* yx_last_error(void) { return g_err; }
+int yx_version(void) { return YX_VERSION; }
+
+int yx_device_check(int dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device visible (%s)", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return YX_ERR_NO_DEVICE;
+  }
+  YX_REQUIRE(dev >= 0 && dev < count, YX_ERR_INVALID_ARG, "device %d out of range (0..%d)", dev, count - 1);
+  int major = 0;
+  YX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  YX_REQUIRE(major == 10, YX_ERR_NO_DEVICE, "device %d is sm_%d0, need sm_100", dev, major);
+  return YX_OK;
+}
+
+int yx_conv_bn_act_fwd(const yx_conv_desc* d, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  YX_REQUIRE(d != nullptr, YX_ERR_INVALID_ARG, "conv: null descriptor");
+  if (d->dtype == YX_FP32) return conv_simt_launch(d, (cudaStream_t)stream);
+  ConvTcLaunch* L = conv_tc_alloc();
+  rc = conv_tc_prepare(d, L);
+  if (rc == YX_OK) rc = conv_tc_launch(L, (cudaStream_t)stream);
+  conv_tc_free(L);
+  return rc;
+}
+
+int yx_conv_bn_act_fwd_simt(const yx_conv_desc* d, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return conv_simt_launch(d, (cudaStream_t)stream);
+}
+
+int yx_dwconv3x3_bn_act_fwd(const void* in, int64_t in_ld, const void* w, const float* bias, void* out,
+                            int64_t out_ld, int32_t batch, int32_t in_h, int32_t in_w, int32_t c, int32_t stride,
+                            int32_t act, int32_t dtype, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return dwconv_launch(in, in_ld, w, bias, out, out_ld, batch, in_h, in_w, c, stride, act, dtype, (cudaStream_t)stream);
+}
+
+int yx_spp_maxpool(void* buf, int64_t ld, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return spp_launch(buf, ld, batch, h, w, c, dtype, (cudaStream_t)stream);
+}
+
+int yx_focus_s2d(const void* img, int32_t img_dtype, void* out, int64_t out_ld, int32_t out_dtype, int32_t batch,
+                 int32_t h, int32_t w, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return focus_launch(img, img_dtype, out, out_ld, out_dtype, batch, h, w, (cudaStream_t)stream);
+}
+
+int yx_pack_weights(const float* src, const float* gamma, const float* beta, const float* mean, const float* var,
+                    const float* conv_bias, float eps, int32_t o, int32_t i, int32_t kh, int32_t kw, void* dst_w,
+                    int32_t dst_dtype, int32_t dst_o_off, int32_t dst_i_off, int32_t dst_i_total, float* dst_b,
+                    int32_t depthwise, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return pack_launch(src, gamma, beta, mean, var, conv_bias, eps, o, i, kh, kw, dst_w, dst_dtype, dst_o_off, dst_i_off,
+                     dst_i_total, dst_b, depthwise, (cudaStream_t)stream);
+}
+
+int yx_head_decode(float* pred, int32_t batch, int32_t anchors, int32_t nc, const int32_t* hw, const int32_t* strides,
+                   int32_t n_levels, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return decode_launch(pred, batch, anchors, nc, hw, strides, n_levels, (cudaStream_t)stream);
+}
+
+int64_t yx_postprocess_workspace_bytes(int32_t batch, int32_t anchors) { return postprocess_ws_bytes(batch, anchors); }
+
+int yx_postprocess(float* pred, int32_t batch, int32_t anchors, int32_t nc, float conf_thre, double nms_thre,
+                   int32_t nms_variant, int32_t inplace_xyxy, float* dets, int64_t* det_idx, int32_t* det_count,
+                   int32_t max_det, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return postprocess_launch(pred, batch, anchors, nc, conf_thre, nms_thre, nms_variant, inplace_xyxy, dets,
+                            (long long*)det_idx, det_count, max_det, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int yx_score_filter_compact(const float* pred, int32_t batch, int32_t anchors, int32_t nc, float conf_thre,
+                            float* cand, int32_t* cand_idx, int32_t* cand_count, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return filter_compact_launch(pred, batch, anchors, nc, conf_thre, cand, cand_idx, cand_count, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
+}
+
+int yx_batched_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts, int32_t batch,
+                   int32_t n_max, double nms_thre, int32_t nms_variant, int32_t* keep, int32_t* keep_count,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return batched_nms_launch(boxes, scores, cls, counts, batch, n_max, nms_thre, nms_variant, keep, keep_count,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int yx_bboxes_iou(const float* a, int32_t n, const float* b, int32_t m, int32_t xyxy, float* out, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return iou_launch(a, n, b, m, xyxy, out, (cudaStream_t)stream);
+}
+
+int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt) {
+  return simota_ws_bytes(batch, anchors, max_gt);
+}
+
+int yx_simota_assign(const float* pred, const float* labels, const float* x_shift, const float* y_shift,
+                     const float* stride_per_anchor, int32_t batch, int32_t anchors, int32_t nc, int32_t max_gt,
+                     uint8_t* fg_mask, int32_t* matched_gt, float* matched_iou, int32_t* matched_cls, int32_t* num_fg,
+                     int32_t* num_gt, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return simota_assign_launch(pred, labels, x_shift, y_shift, stride_per_anchor, batch, anchors, nc, max_gt, fg_mask,
+                              matched_gt, matched_iou, matched_cls, num_fg, num_gt, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
+int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int32_t n, int64_t ld,
+                       int32_t* match_gt, float* match_iou, int32_t* num_fg, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return simota_matching_launch(cost, ious, num_gt, n, ld, match_gt, match_iou, num_fg, (cudaStream_t)stream);
+}
+
+// ---- plan ----
+yx_plan* yx_plan_create(void) { return new (std::nothrow) yx_plan(); }
+
+void yx_plan_destroy(yx_plan* p) {
+  if (!p) return;
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->graph) cudaGraphDestroy(p->graph);
+  for (auto& o : p->ops)
+    if (o.tc) conv_tc_free(o.tc);
+  delete p;
+}
+
+static void plan_invalidate(yx_plan* p) {
+  if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+  if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
+}
+
+int yx_plan_add_conv(yx_plan* p, const yx_conv_desc* d) {
+  YX_REQUIRE(p && d, YX_ERR_INVALID_ARG, "plan_add_conv: null");
+  int rc = require_device();
+  if (rc) return rc;
+  Op o;
+  memset(&o, 0, sizeof(o));
+  if (d->dtype == YX_FP32) {
+    o.kind = OP_CONV_SIMT;
+    o.conv = *d;
+    EpiParams e;
+    rc = fill_epi_params(d, &e);
+    if (rc) return rc;
+  } else {
+    o.kind = OP_CONV_TC;
+    o.tc = conv_tc_alloc();
+    rc = conv_tc_prepare(d, o.tc);
+    if (rc) { conv_tc_free(o.tc); return rc; }
+  }
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_dwconv(yx_plan* p, const void* in, int64_t in_ld, const void* w, const float* bias, void* out,
+                       int64_t out_ld, int32_t batch, int32_t in_h, int32_t in_w, int32_t c, int32_t stride,
+                       int32_t act, int32_t dtype) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_dwconv: null plan");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_DWCONV;
+  o.dw = {in, in_ld, w, bias, out, out_ld, batch, in_h, in_w, c, stride, act, dtype};
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_spp(yx_plan* p, void* buf, int64_t ld, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_spp: null plan");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_SPP;
+  o.spp = {buf, ld, batch, h, w, c, dtype};
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_focus(yx_plan* p, const void* img, int32_t img_dtype, void* out, int64_t out_ld, int32_t out_dtype,
+                      int32_t batch, int32_t h, int32_t w) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_focus: null plan");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_FOCUS;
+  o.focus = {img, img_dtype, out, out_ld, out_dtype, batch, h, w};
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anchors, int32_t nc, float conf_thre,
+                            double nms_thre, int32_t nms_variant, int32_t inplace_xyxy, float* dets,
+                            int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
+                            int64_t workspace_bytes) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_postprocess: null plan");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_POST;
+  o.post = {pred, batch, anchors, nc, conf_thre, nms_thre, nms_variant, inplace_xyxy, dets, (long long*)det_idx,
+            det_count, max_det, workspace, workspace_bytes};
+  p->ops.push_back(o);
+  p->launches += 2;  // filter + sort/NMS kernels (plus one memset node)
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_num_launches(const yx_plan* p) { return p ? p->launches : 0; }
+
+int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_run: null plan");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!use_graph) {
+    for (const auto& o : p->ops) {
+      rc = run_op(o, s);
+      if (rc) return rc;
+    }
+    return YX_OK;
+  }
+  if (!p->exec) {
+    // warm every kernel once outside capture (cudaFuncSetAttribute etc. are not capturable)
+    for (const auto& o : p->ops) {
+      rc = run_op(o, s);
+      if (rc) return rc;
+    }
+    YX_CUDA(cudaStreamSynchronize(s));
+    YX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (const auto& o : p->ops) {
+      rc = run_op(o, s);
+      if (rc) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+    }
+    YX_CUDA(cudaStreamEndCapture(s, &p->graph));
+    YX_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
+  }
+  YX_CUDA(cudaGraphLaunch(p->exec, s));
+  return YX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// tcgen05/TMEM/TMA implicit-GEMM convolution for sm_100a.
+//
+// Replaces BaseConv.forward (yolox/models/network_blocks.py:27-52: conv -> BN -> SiLU) and the
+// biased 1x1 prediction convs of YoloxHead (yolox/models/yolo_head.py:94-120, 140-211).
+//
+// GEMM view   D[M=pixels, N=out_c] = A[M, K] * W[N, K]^T,   K = taps * in_c
+//   A is never materialised: for every filter tap (r, s) a TMA *tiled* 4-D load of the NHWC
+//   activation tensor [C, W, H, B] with box [KC, tw, th, 1] starting at
+//   (c, w0*stride + s - pad, h0*stride + r - pad, b) lands a [128 pixel rows x KC channels]
+//   K-major, hardware-swizzled operand tile in shared memory. TMA zero-fills out-of-bounds
+//   elements, which is exactly Conv2d's zero padding; stride-2 convs use elementStrides = 2.
+//   1x1 convs use the same code with the tensor viewed as [C, M, 1, 1] (flat 128-pixel tiles).
+//   W is a plain 2-D tensor [K, N] (K contiguous) loaded with box [KC, BN].
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0      TMA producer (one elected lane): fills a ring of `stages` {A,B} slots
+//   warp 1      TMEM allocator + MMA issuer (one lane): tcgen05.mma 128 x BN x 16, fp32
+//               accumulators in TMEM, `acc_stages`-deep so tile i+1 is multiplied while
+//               tile i is drained
+//   warps 2..5  epilogue: tcgen05.ld (each warp owns the 32 TMEM lanes of its quarter),
+//               bias + activation (+ residual, + 2x upsample copy, or head decode), 16-byte stores
+// Synchronisation is mbarrier-only: full/empty per smem slot, tmem_full/tmem_empty per
+// accumulator stage; tcgen05.commit releases slots and publishes accumulators.
+#include <stdlib.h>
+#include <string.h>
+
+#include "yx_epilogue.cuh"
+
+namespace yx {
+
+struct ConvTcParams {
+  int tw, th;            // spatial tile; tw*th <= 128 (flat mode: tw = 128, th = 1)
+  int tiles_w, tiles_h;  // tiles per image (flat mode: tiles_w = ceil(M/128), tiles_h = 1)
+  int n_tiles;           // out_c / BN
+  int num_tiles;         // total work items
+  int BN, BNpad;         // N tile and its TMEM column pitch
+  int KC;                // channels per pipeline stage (16 / 32 / 64)
+  int kchunks;           // in_c / KC
+  int ksize, stride, pad;
+  int in_c;
+  int batch;
+  int flat;
+  long long M;           // batch*out_h*out_w
+  int stages, acc_stages;
+  unsigned a_stage_bytes, stage_bytes, tx_bytes;
+  unsigned desc_hi;      // upper 32 bits of the UMMA smem descriptor (SBO, version, layout)
+  unsigned idesc;
+  unsigned tmem_cols;
+  EpiParams epi;
+};
+
+static constexpr int kMaxStages = 8;
+static constexpr int kMaxAcc = 4;
+static constexpr int kThreads = 192;
+
+struct __align__(8) TcShared {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[kMaxAcc];
+  uint64_t tmem_empty[kMaxAcc];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // operand tiles need 1024-byte alignment for the 128-byte swizzle atom
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcShared* sh = reinterpret_cast<TcShared*>(smem);
+  uint8_t* tiles = smem + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&sh->full[i], 1);
+      mbar_init(&sh->empty[i], 1);
+    }
+    for (int i = 0; i < p.acc_stages; ++i) {
+      mbar_init(&sh->tmem_full[i], 1);
+      mbar_init(&sh->tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh->tmem_base, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  const int num_k = p.ksize * p.ksize * p.kchunks;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n_tile = t % p.n_tiles;
+        const int m_tile = t / p.n_tiles;
+        int b, x0, y0;
+        if (p.flat) {
+          b = 0; y0 = 0; x0 = m_tile * 128;
+        } else {
+          b = m_tile / tiles_per_img;
+          const int r = m_tile - b * tiles_per_img;
+          const int ty = r / p.tiles_w;
+          const int tx = r - ty * p.tiles_w;
+          x0 = tx * p.tw * p.stride - p.pad;
+          y0 = ty * p.th * p.stride - p.pad;
+        }
+        for (int kt = 0; kt < num_k; ++kt) {
+          const int tap = kt / p.kchunks;
+          const int cc = kt - tap * p.kchunks;
+          const int fr = tap / p.ksize;
+          const int fs = tap - fr * p.ksize;
+          mbar_wait(&sh->empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sh->full[stage], p.tx_bytes);
+          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_stage_bytes;
+          tma_load_4d(&map_a, &sh->full[stage], sa, cc * p.KC, x0 + fs, y0 + fr, b);
+          tma_load_2d(&map_b, &sh->full[stage], sb, tap * p.in_c + cc * p.KC, n_tile * p.BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      const int ksteps = p.KC / 16;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        mbar_wait(&sh->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BNpad);
+        for (int kt = 0; kt < num_k; ++kt) {
+          mbar_wait(&sh->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + p.a_stage_bytes;
+          const uint64_t hi = (uint64_t)p.desc_hi << 32;
+          // lower word: start address >> 4 | LBO(=1) << 16
+          uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFF) | (1u << 16));
+          uint64_t bdesc = hi | (uint64_t)(((sb >> 4) & 0x3FFF) | (1u << 16));
+          for (int j = 0; j < ksteps; ++j) {
+            umma_f16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kt | j) != 0));
+            adesc += 2;  // +32 bytes = 16 elements along K inside the swizzled row
+            bdesc += 2;
+          }
+          umma_commit(&sh->empty[stage]);  // slot is free once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&sh->tmem_full[as]);   // accumulator complete -> epilogue
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = quarter * 32 + lane;     // accumulator row = pixel inside the tile
+    int as = 0;
+    uint32_t aphase = 0;
+    const int out_hw = p.epi.out_h * p.epi.out_w;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int n_tile = t % p.n_tiles;
+      const int m_tile = t / p.n_tiles;
+      int b, ho, wo;
+      bool valid;
+      if (p.flat) {
+        const long long m = (long long)m_tile * 128 + row;
+        valid = m < p.M;
+        const long long mm = valid ? m : 0;
+        b = (int)(mm / out_hw);
+        const int r = (int)(mm - (long long)b * out_hw);
+        ho = r / p.epi.out_w;
+        wo = r - ho * p.epi.out_w;
+      } else {
+        b = m_tile / tiles_per_img;
+        const int r = m_tile - b * tiles_per_img;
+        const int ty = r / p.tiles_w;
+        const int tx = r - ty * p.tiles_w;
+        const int hl = row / p.tw;
+        const int wl = row - hl * p.tw;
+        ho = ty * p.th + hl;
+        wo = tx * p.tw + wl;
+        valid = (hl < p.th) && (ho < p.epi.out_h) && (wo < p.epi.out_w);
+      }
+      mbar_wait(&sh->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t raw[16];
+        tmem_ld_x16(taddr + (uint32_t)c, raw);
+        tmem_ld_wait();
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          epi_store16<false>(p.epi, b, ho, wo, n_tile * p.BN + c, v);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->tmem_empty[as]);
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct ConvTcLaunch {
+  CUtensorMap map_a, map_b;
+  ConvTcParams p;
+  int grid;
+  size_t smem;
+};
+
+int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
+  YX_REQUIRE(d->out_c % 16 == 0, YX_ERR_INVALID_ARG, "conv: out_c=%d must be a multiple of 16", d->out_c);
+  e->out_h = d->out_h; e->out_w = d->out_w; e->out_c = d->out_c;
+  e->act = d->act; e->dtype = d->dtype; e->epilogue = d->epilogue;
+  e->bias = d->bias;
+  YX_REQUIRE(d->bias != nullptr, YX_ERR_INVALID_ARG, "conv: bias is null");
+  YX_REQUIRE(((uintptr_t)d->bias & 15) == 0, YX_ERR_INVALID_ARG, "conv: bias must be 16-byte aligned");
+  e->out = d->out; e->out_ld = d->out_ld;
+  e->res = d->res; e->res_ld = d->res_ld;
+  e->ups = d->ups; e->ups_ld = d->ups_ld;
+  e->head_out = d->head_out;
+  e->head_anchors = d->head_anchors; e->head_anchor_off = d->head_anchor_off;
+  e->head_nc = d->head_nc; e->head_decode = d->head_decode; e->head_stride = d->head_stride;
+  if (d->epilogue == YX_EPI_HEAD) {
+    YX_REQUIRE(d->head_out != nullptr, YX_ERR_INVALID_ARG, "conv(head): head_out is null");
+    YX_REQUIRE(5 + d->head_nc <= d->out_c, YX_ERR_INVALID_ARG, "conv(head): out_c=%d < 5+nc=%d", d->out_c, 5 + d->head_nc);
+  } else {
+    YX_REQUIRE(d->epilogue == YX_EPI_STORE, YX_ERR_INVALID_ARG, "conv: unknown epilogue %d", d->epilogue);
+    YX_REQUIRE(d->out != nullptr, YX_ERR_INVALID_ARG, "conv: out is null");
+    const int al = d->dtype == YX_FP32 ? 4 : 8;
+    YX_REQUIRE(d->out_ld % al == 0 && ((uintptr_t)d->out & 15) == 0, YX_ERR_INVALID_ARG,
+               "conv: out must be 16-byte aligned with out_ld %% %d == 0", al);
+    YX_REQUIRE(d->out_ld >= d->out_c, YX_ERR_INVALID_ARG, "conv: out_ld < out_c");
+    if (d->res) YX_REQUIRE(d->res_ld % al == 0 && ((uintptr_t)d->res & 15) == 0, YX_ERR_INVALID_ARG, "conv: res misaligned");
+    if (d->ups) YX_REQUIRE(d->ups_ld % al == 0 && ((uintptr_t)d->ups & 15) == 0, YX_ERR_INVALID_ARG, "conv: ups misaligned");
+  }
+  return YX_OK;
+}
+
+int validate_conv_geometry(const yx_conv_desc* d) {
+  YX_REQUIRE(d != nullptr, YX_ERR_INVALID_ARG, "conv: null descriptor");
+  YX_REQUIRE(d->ksize == 1 || d->ksize == 3, YX_ERR_UNSUPPORTED, "conv: ksize=%d (only 1 and 3)", d->ksize);
+  YX_REQUIRE(d->stride == 1 || d->stride == 2, YX_ERR_UNSUPPORTED, "conv: stride=%d (only 1 and 2)", d->stride);
+  YX_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0, YX_ERR_INVALID_ARG, "conv: empty input");
+  const int pad = (d->ksize - 1) / 2;
+  const int oh = (d->in_h + 2 * pad - d->ksize) / d->stride + 1;
+  const int ow = (d->in_w + 2 * pad - d->ksize) / d->stride + 1;
+  YX_REQUIRE(oh == d->out_h && ow == d->out_w, YX_ERR_INVALID_ARG,
+             "conv: out %dx%d inconsistent with in %dx%d k%d s%d (expected %dx%d)", d->out_h, d->out_w,
+             d->in_h, d->in_w, d->ksize, d->stride, oh, ow);
+  YX_REQUIRE(d->in_c % 16 == 0 && d->in_c > 0, YX_ERR_INVALID_ARG, "conv: in_c=%d must be a multiple of 16", d->in_c);
+  YX_REQUIRE(d->in != nullptr && d->w != nullptr, YX_ERR_INVALID_ARG, "conv: null in/w");
+  YX_REQUIRE(d->in_ld >= d->in_c, YX_ERR_INVALID_ARG, "conv: in_ld < in_c");
+  return YX_OK;
+}
+
+static int largest_divisor_tile(int n, int cap) {
+  // largest multiple-of-16 divisor of n that is <= cap
+  for (int t = cap - cap % 16; t >= 16; t -= 16)
+    if (n % t == 0) return t;
+  return 16;
+}
+
+int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
+  int rc = validate_conv_geometry(d);
+  if (rc) return rc;
+  YX_REQUIRE(d->dtype == YX_BF16 || d->dtype == YX_FP16, YX_ERR_INVALID_ARG, "conv_tc: dtype must be bf16/fp16");
+  YX_REQUIRE(d->in_ld % 8 == 0 && ((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
+             YX_ERR_INVALID_ARG, "conv_tc: in/w must be 16-byte aligned, in_ld %% 8 == 0");
+  ConvTcParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  rc = fill_epi_params(d, &p.epi);
+  if (rc) return rc;
+  EncodeTiledFn encode = get_encode_fn();
+  YX_REQUIRE(encode != nullptr, YX_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+
+  p.ksize = d->ksize; p.stride = d->stride; p.pad = (d->ksize - 1) / 2;
+  p.in_c = d->in_c; p.batch = d->batch;
+  p.M = (long long)d->batch * d->out_h * d->out_w;
+  p.KC = (d->in_c % 64 == 0) ? 64 : (d->in_c % 32 == 0 ? 32 : 16);
+  p.kchunks = d->in_c / p.KC;
+  p.BN = largest_divisor_tile(d->out_c, 256);
+  p.n_tiles = d->out_c / p.BN;
+  p.BNpad = 32;
+  while (p.BNpad < p.BN) p.BNpad <<= 1;
+  p.acc_stages = 512 / p.BNpad;
+  if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
+  p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);  // power of two >= 32 by construction
+
+  p.flat = (d->ksize == 1 && d->stride == 1) ? 1 : 0;
+  if (p.flat) {
+    p.tw = 128; p.th = 1;
+    p.tiles_w = (int)ceil_div64(p.M, 128); p.tiles_h = 1;
+    p.num_tiles = p.tiles_w * p.n_tiles;
+  } else {
+    // choose the spatial tile (tw x th <= 128 pixels) that wastes the fewest accumulator rows
+    long long best_cost = -1; int btw = 1, bth = 1;
+    const int max_tw = d->stride == 2 ? 128 : 128;
+    for (int tw = 1; tw <= d->out_w && tw <= max_tw; ++tw) {
+      int th = 128 / tw;
+      if (th > d->out_h) th = d->out_h;
+      if (th < 1) continue;
+      if (th * d->stride > 256 || tw * d->stride > 256) continue;
+      const long long tiles = ceil_div64(d->out_w, tw) * ceil_div64(d->out_h, th);
+      // cost: number of tiles; tie -> wider rows (longer contiguous runs for TMA)
+      const long long cost = tiles * 1024 - tw;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; btw = tw; bth = th; }
+    }
+    p.tw = btw; p.th = bth;
+    p.tiles_w = (int)ceil_div64(d->out_w, p.tw);
+    p.tiles_h = (int)ceil_div64(d->out_h, p.th);
+    p.num_tiles = d->batch * p.tiles_w * p.tiles_h * p.n_tiles;
+  }
+
+  const unsigned row_bytes = (unsigned)p.KC * 2;             // 128 / 64 / 32 = swizzle span
+  const unsigned a_bytes = 128u * row_bytes;
+  const unsigned b_bytes = (unsigned)p.BN * row_bytes;
+  p.a_stage_bytes = (a_bytes + 1023u) & ~1023u;
+  p.stage_bytes = p.a_stage_bytes + ((b_bytes + 1023u) & ~1023u);
+  p.tx_bytes = (unsigned)(p.tw * p.th) * row_bytes + b_bytes;  // bytes TMA actually delivers
+  int dev = 0, max_smem = 0;
+  YX_CUDA(cudaGetDevice(&dev));
+  YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int num_k = d->ksize * d->ksize * p.kchunks;
+  int stages = (int)((max_smem - 2048) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  YX_REQUIRE(stages >= 2, YX_ERR_UNSUPPORTED, "conv_tc: stage of %u bytes does not fit shared memory", p.stage_bytes);
+  (void)num_k;
+  p.stages = stages;
+  L->smem = 2048 + (size_t)stages * p.stage_bytes;
+
+  // UMMA shared-memory descriptor, upper word: SBO = 8 rows * row_bytes, version 1, layout type
+  const unsigned layout = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);  // SW128 / SW64 / SW32
+  const unsigned sbo = (8u * row_bytes) >> 4;
+  p.desc_hi = (sbo & 0x3FFFu) | (1u << 14) | (layout << 29);
+  const unsigned fmt = d->dtype == YX_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+
+  const CUtensorMapDataType tdt = d->dtype == YX_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = p.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (p.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4];
+    if (p.flat) {
+      dims[0] = (cuuint64_t)d->in_c; dims[1] = (cuuint64_t)p.M; dims[2] = 1; dims[3] = 1;
+      strides[0] = (cuuint64_t)d->in_ld * 2;
+      strides[1] = strides[0] * (cuuint64_t)p.M;
+      strides[2] = strides[1];
+      box[0] = (cuuint32_t)p.KC; box[1] = 128; box[2] = 1; box[3] = 1;
+      estr[0] = estr[1] = estr[2] = estr[3] = 1;
+    } else {
+      dims[0] = (cuuint64_t)d->in_c; dims[1] = (cuuint64_t)d->in_w; dims[2] = (cuuint64_t)d->in_h; dims[3] = (cuuint64_t)d->batch;
+      strides[0] = (cuuint64_t)d->in_ld * 2;
+      strides[1] = strides[0] * (cuuint64_t)d->in_w;
+      strides[2] = strides[1] * (cuuint64_t)d->in_h;
+      box[0] = (cuuint32_t)p.KC; box[1] = (cuuint32_t)(p.tw * d->stride); box[2] = (cuuint32_t)(p.th * d->stride); box[3] = 1;
+      estr[0] = 1; estr[1] = (cuuint32_t)d->stride; estr[2] = (cuuint32_t)d->stride; estr[3] = 1;
+    }
+    CUresult r = encode(&L->map_a, tdt, 4, const_cast<void*>(d->in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d (in_c=%d ld=%lld box=%u,%u,%u)",
+               (int)r, d->in_c, (long long)d->in_ld, box[0], box[1], box[2]);
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)d->ksize * d->ksize * d->in_c;
+    cuuint64_t dims[2] = {K, (cuuint64_t)d->out_c};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&L->map_b, tdt, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+  }
+  const int sms = num_sms();
+  L->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  return YX_OK;
+}
+
+ConvTcLaunch* conv_tc_alloc() {
+  void* p = nullptr;
+  if (posix_memalign(&p, 64, sizeof(ConvTcLaunch)) != 0) return nullptr;  // CUtensorMap wants 64-byte alignment
+  memset(p, 0, sizeof(ConvTcLaunch));
+  return reinterpret_cast<ConvTcLaunch*>(p);
+}
+void conv_tc_free(ConvTcLaunch* p) { free(p); }
+
+int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int dev = 0, max_smem = 0;
+    YX_CUDA(cudaGetDevice(&dev));
+    YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<L->grid, kThreads, L->smem, stream>>>(L->map_a, L->map_b, L->p);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+}  // namespace yx

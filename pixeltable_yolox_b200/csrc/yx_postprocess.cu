@@ -1,0 +1,515 @@
+// postprocess = score filter + class-aware NMS, batched over images, no host synchronisation.
+//   reference: yolox/utils/boxes.py:31-75 (postprocess) and the third-party
+//   torchvision.ops.batched_nms / nms it calls at boxes.py:56-67 (torchvision 0.17.2 pinned in
+//   poetry.lock:2084-2085; semantics restated in oracle/postprocess_oracle.py and pinned against
+//   the installed torchvision by tests/golden/make_golden.py).
+//
+// Stage 1  filter_kernel      warp per anchor: coalesced read of the 5+nc floats, warp arg-max over
+//                             the classes (first index wins ties, like torch.max), score =
+//                             obj*class_conf (one fp32 multiply), cxcywh->xyxy exactly as
+//                             boxes.py:32-37, dense candidate row + 64-bit sort key for anchors with
+//                             score >= conf_thre (warp-aggregated append).
+// Stage 2  sort_nms_kernel    one CTA per image: bitonic sort of the keys (descending score,
+//                             ascending anchor = torch's stable descending sort) in shared memory,
+//                             then greedy NMS in chunks of 512 sorted candidates: a chunk is first
+//                             tested against the boxes already kept (they sit in L1/L2), then the
+//                             512x512 suppression bitmask of the chunk is built in shared memory
+//                             and scanned by one warp that hops from kept box to kept box with
+//                             ffs. The O(n^2/64) mask never touches HBM.
+// IoU arithmetic follows torchvision's nms kernel operation by operation in fp32 (round-to-nearest
+// intrinsics so that nvcc cannot contract multiplies and adds into FMAs):
+//   inter = max(0, min(x2) - max(x1)) * max(0, min(y2) - max(y1));
+//   suppressed iff inter / (area_i + area_j - inter) > thr.
+#include <string.h>
+#include <math.h>
+
+#include "yx_common.cuh"
+
+namespace yx {
+
+static constexpr int kChunk = 512;
+static constexpr int kChunkWords = kChunk / 32;
+static constexpr int kNmsThreads = 512;
+static constexpr int kMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
+
+__device__ __forceinline__ uint32_t orderable(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 1
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+filter_kernel(float* __restrict__ pred, int batch, int anchors, int nc, float conf_thre, int inplace_xyxy,
+              float* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warps_per_img = gridDim.x * (blockDim.x >> 5) / batch;  // grid is a multiple of batch
+  const int b = warp_global / warps_per_img;
+  const int wi = warp_global - b * warps_per_img;
+  if (b >= batch) return;
+  const int nch = 5 + nc;
+  for (int a = wi; a < anchors; a += warps_per_img) {
+    float* row = pred + ((long long)b * anchors + a) * nch;
+    // arg-max over the class columns: lane handles classes lane, lane+32, ...
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int c = lane; c < nc; c += 32) {
+      const float v = row[5 + c];
+      // torch.max semantics: first occurrence of the maximum; NaN propagates as the maximum
+      const bool take = (best_i == 0x7fffffff) || (!(best != best) && ((v != v) || v > best));
+      if (take) { best = v; best_i = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      const bool other_nan = (ov != ov), mine_nan = (best != best);
+      bool take;
+      if (oi == 0x7fffffff) take = false;
+      else if (best_i == 0x7fffffff) take = true;
+      else if (other_nan != mine_nan) take = other_nan;
+      else if (other_nan) take = oi < best_i;
+      else take = (ov > best) || (ov == best && oi < best_i);
+      if (take) { best = ov; best_i = oi; }
+    }
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float obj = 0.f;
+    if (lane == 0) {
+      const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+      obj = row[4];
+      const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+      box.x = __fsub_rn(cx, hw); box.y = __fsub_rn(cy, hh);
+      box.z = __fadd_rn(cx, hw); box.w = __fadd_rn(cy, hh);
+      const float score = __fmul_rn(obj, best);
+      if (inplace_xyxy) { row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; }
+      float4* crow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + a) * 8);
+      crow[0] = box;
+      crow[1] = make_float4(obj, best, (float)best_i, score);
+      if (score >= conf_thre) {
+        const int slot = atomicAdd(&counts[b], 1);
+        const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
+        keys[(long long)b * anchors + slot] =
+            ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)a;
+      }
+    }
+  }
+}
+
+// Ordered compaction for yx_score_filter_compact: one CTA per image walks the dense candidate
+// rows in anchor order with a block-wide exclusive scan of the pass flags.
+__global__ void __launch_bounds__(1024)
+compact_kernel(const float* __restrict__ cand_dense, int anchors, float conf_thre, float* __restrict__ cand,
+               int* __restrict__ cand_idx, int* __restrict__ cand_count) {
+  __shared__ int warp_sums[32];
+  __shared__ int base;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int a0 = 0; a0 < anchors; a0 += blockDim.x) {
+    const int a = a0 + threadIdx.x;
+    const float4* row = reinterpret_cast<const float4*>(cand_dense + ((long long)b * anchors + a) * 8);
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 0, -INFINITY);
+    bool pass = false;
+    if (a < anchors) { r0 = row[0]; r1 = row[1]; pass = r1.w >= conf_thre; }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    const int wprefix = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      int v = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+      }
+      warp_sums[lane] = v;  // inclusive
+    }
+    __syncthreads();
+    const int woff = warp == 0 ? 0 : warp_sums[warp - 1];
+    if (pass) {
+      const int dst = base + woff + wprefix;
+      float4* orow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + dst) * 8);
+      orow[0] = r0; orow[1] = r1;
+      cand_idx[(long long)b * anchors + dst] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cand_count[b] = base;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 2
+// ------------------------------------------------------------------------------------------
+struct NmsSource {
+  const float* boxes; int box_stride;      // xyxy, floats per candidate
+  const float* scores; int score_stride;
+  const void* cls; int cls_stride; int cls_is_float;
+  long long per_image;                      // candidates per image in the dense arrays
+};
+
+struct NmsArgs {
+  NmsSource src;
+  const unsigned long long* keys;  // [B, per_image] (filter path) or null (build from scores)
+  const int* counts;               // [B]
+  float thr;                       // largest float f with (double)f <= nms_thre: x > f <=> x > nms_thre
+  int variant;                     // 0 offset trick, 1 per-class, 2 class-agnostic,
+                                   // 3/4: torchvision's own choice on CUDA / CPU (by candidate count)
+  // scratch [B, per_image]
+  unsigned long long* gkeys;       // used when the key list does not fit shared memory
+  long long gkeys_stride;          // keys per image in gkeys (next_pow2(per_image))
+  int smem_keys_cap;               // number of 64-bit keys the dynamic shared memory can hold
+  float4* sorted_box;              // boxes as NMS sees them (offset applied for variant 0)
+  int* sorted_cls;
+  int* sorted_idx;
+  int* kept_pos;                   // positions (in sorted order) of the kept candidates
+  // outputs
+  int* keep; int* keep_count;      // yx_batched_nms
+  float* dets; long long* det_idx; int* det_count; int max_det;  // yx_postprocess (from cand rows)
+};
+
+__device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+  const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return ovr > thr;
+}
+__device__ __forceinline__ float box_area(const float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs g) {
+  extern __shared__ __align__(16) uint8_t nsm[];
+  __shared__ float red[kNmsThreads / 32];
+  __shared__ int s_nkept;
+  __shared__ unsigned s_removed[kChunkWords];
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)b * g.src.per_image;
+  int n = g.counts[b];
+  if (n > g.src.per_image) n = (int)g.src.per_image;
+
+  float4* sbox = g.sorted_box + base;
+  int* scls = g.sorted_cls + base;
+  int* sidx = g.sorted_idx + base;
+  int* kept = g.kept_pos + base;
+
+  if (tid == 0) s_nkept = 0;
+  // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA) / 4000 (CPU)
+  int variant = g.variant;
+  if (variant == 3) variant = (4LL * n > 100000) ? 1 : 0;
+  if (variant == 4) variant = (4LL * n > 4000) ? 1 : 0;
+
+  if (n > 0) {
+    // ---------------- sort ----------------
+    int P = 1;
+    while (P < n) P <<= 1;
+    unsigned long long* keys = (P <= g.smem_keys_cap) ? reinterpret_cast<unsigned long long*>(nsm)
+                                                      : (g.gkeys + (long long)b * g.gkeys_stride);
+    for (int i = tid; i < P; i += kNmsThreads) {
+      unsigned long long k = ~0ull;
+      if (i < n) {
+        if (g.keys) k = g.keys[base + i];
+        else {
+          float sc = g.src.scores[(base + i) * g.src.score_stride];
+          if (sc == 0.0f) sc = 0.0f;
+          k = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)i;
+        }
+      }
+      keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < (P >> 1); i += kNmsThreads) {
+          const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+          const int hi = lo | stride;
+          const bool up = ((lo & size) == 0);
+          const unsigned long long a = keys[lo], c = keys[hi];
+          if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
+    float mx = -INFINITY;
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
+      const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
+      const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+      int c;
+      if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+      else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+      sbox[i] = bx; scls[i] = c; sidx[i] = idx;
+      mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+    }
+    if (variant == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) red[warp] = mx;
+      __syncthreads();
+      mx = red[0];
+      for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, red[i]);
+      // boxes_for_nms = boxes + idxs.to(boxes) * (max_coordinate + 1)   (torchvision boxes.py)
+      const float step = __fadd_rn(mx, 1.0f);
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const float off = __fmul_rn((float)scls[i], step);
+        float4 bx = sbox[i];
+        bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
+        bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+        sbox[i] = bx;
+      }
+    }
+    __syncthreads();
+
+    // ---------------- greedy NMS, chunk by chunk ----------------
+    float4* cbox = reinterpret_cast<float4*>(nsm);                          // [kChunk]
+    float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
+    int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
+    unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kChunkWords]
+    const bool gate_cls = (variant == 1);
+
+    for (int c0 = 0; c0 < n; c0 += kChunk) {
+      const int cn = min(kChunk, n - c0);
+      __syncthreads();
+      const int nk = s_nkept;
+      // this kernel uses kNmsThreads == kChunk: thread t owns candidate c0 + t
+      float4 me = make_float4(0, 0, 0, 0);
+      float my_area = 0.f;
+      int my_cls = -1;
+      bool dead = (tid >= cn);
+      if (!dead) {
+        me = sbox[c0 + tid]; my_cls = scls[c0 + tid]; my_area = box_area(me);
+      }
+      cbox[tid] = me; carea[tid] = my_area; ccls[tid] = my_cls;
+      // phase A: against the boxes kept in earlier chunks (uniform, L1-resident loads)
+      if (!dead) {
+        for (int k = 0; k < nk; ++k) {
+          const int kp = kept[k];
+          const float4 kb = sbox[kp];
+          if (gate_cls && scls[kp] != my_cls) continue;
+          if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+        }
+      }
+      __syncthreads();
+      {
+        const unsigned bal = __ballot_sync(0xffffffffu, dead);
+        if (lane == 0) s_removed[warp] = bal;
+      }
+      // phase B: suppression bitmask inside the chunk (row i, bits j > i)
+      for (int w = 0; w < kChunkWords; ++w) {
+        unsigned bits = 0u;
+        if (!dead && (w * 32 + 31) > tid) {
+#pragma unroll 4
+          for (int jb = 0; jb < 32; ++jb) {
+            const int j = w * 32 + jb;
+            if (j > tid && j < cn) {
+              if (!gate_cls || ccls[j] == my_cls) {
+                if (suppresses(me, my_area, cbox[j], carea[j], g.thr)) bits |= (1u << jb);
+              }
+            }
+          }
+        }
+        cmask[tid * kChunkWords + w] = bits;
+      }
+      __syncthreads();
+      // phase C: one warp walks the chunk; lane w owns word w of the removed set
+      if (warp == 0) {
+        unsigned removed = lane < kChunkWords ? s_removed[lane] : 0xffffffffu;
+        int nkept = nk;
+        int pos = 0;
+        while (true) {
+          // next alive candidate at or after pos
+          unsigned alive = (lane < kChunkWords) ? ~removed : 0u;
+          const int wpos = pos >> 5;
+          if (lane < wpos) alive = 0u;
+          else if (lane == wpos) alive &= (0xffffffffu << (pos & 31));
+          const unsigned has = __ballot_sync(0xffffffffu, alive != 0u);
+          if (has == 0u) break;
+          const int wsel = __ffs(has) - 1;
+          const unsigned aw = __shfl_sync(0xffffffffu, alive, wsel);
+          const int i = wsel * 32 + (__ffs(aw) - 1);
+          if (i >= cn) break;
+          if (lane == 0) kept[nkept] = c0 + i;
+          ++nkept;
+          if (lane < kChunkWords) removed |= cmask[i * kChunkWords + lane];
+          pos = i + 1;
+          if (pos >= cn) break;
+        }
+        if (lane == 0) s_nkept = nkept;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // ---------------- outputs ----------------
+  const int nk = s_nkept;
+  if (g.keep) {
+    for (int k = tid; k < nk; k += kNmsThreads) g.keep[base + k] = sidx[kept[k]];
+    if (tid == 0) g.keep_count[b] = nk;
+  }
+  if (g.dets) {
+    const int m = min(nk, g.max_det);
+    for (int k = tid; k < m; k += kNmsThreads) {
+      const int idx = sidx[kept[k]];
+      const float4* crow = reinterpret_cast<const float4*>(g.src.boxes + (base + idx) * 8);
+      const float4 r0 = crow[0], r1 = crow[1];
+      float* d = g.dets + ((long long)b * g.max_det + k) * 7;
+      d[0] = r0.x; d[1] = r0.y; d[2] = r0.z; d[3] = r0.w; d[4] = r1.x; d[5] = r1.y; d[6] = r1.z;
+      if (g.det_idx) g.det_idx[(long long)b * g.max_det + k] = idx;
+    }
+    if (tid == 0) g.det_count[b] = nk;  // true number kept; rows beyond max_det are dropped
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline long long next_pow2_ll(long long v) { long long p = 1; while (p < v) p <<= 1; return p; }
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct PostWs {
+  float* cand; unsigned long long* keys; unsigned long long* gkeys; float4* sbox;
+  int* scls; int* sidx; int* kept; int* counts;
+  size_t total;
+};
+
+static PostWs carve_ws(void* ws, int batch, long long per_image) {
+  PostWs w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  const long long padded = per_image > kMaxSmemKeys ? next_pow2_ll(per_image) : per_image;
+  w.counts = reinterpret_cast<int*>(p + off); off += align256((size_t)batch * 4);
+  w.cand = reinterpret_cast<float*>(p + off); off += align256((size_t)batch * per_image * 32);
+  w.keys = reinterpret_cast<unsigned long long*>(p + off); off += align256((size_t)batch * per_image * 8);
+  w.gkeys = reinterpret_cast<unsigned long long*>(p + off);
+  off += align256(per_image > kMaxSmemKeys ? (size_t)batch * padded * 8 : 256);
+  w.sbox = reinterpret_cast<float4*>(p + off); off += align256((size_t)batch * per_image * 16);
+  w.scls = reinterpret_cast<int*>(p + off); off += align256((size_t)batch * per_image * 4);
+  w.sidx = reinterpret_cast<int*>(p + off); off += align256((size_t)batch * per_image * 4);
+  w.kept = reinterpret_cast<int*>(p + off); off += align256((size_t)batch * per_image * 4);
+  w.total = off;
+  return w;
+}
+
+long long postprocess_ws_bytes(int batch, int anchors) {
+  if (batch <= 0 || anchors <= 0) return 256;
+  return (long long)carve_ws(nullptr, batch, anchors).total;
+}
+
+static float thr_for_strict_gt(double nms_thre) {
+  // torchvision's CPU kernel compares the fp32 IoU with the double threshold:
+  // x > thr  <=>  x > f, where f is the largest float that is <= thr
+  float f = (float)nms_thre;
+  if ((double)f > nms_thre) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+static int smem_keys_cap(long long per_image) {
+  const long long p = next_pow2_ll(per_image);
+  return (int)(p > kMaxSmemKeys ? kMaxSmemKeys : p);
+}
+static size_t nms_smem_bytes(long long per_image) {
+  const size_t sort_bytes = (size_t)smem_keys_cap(per_image) * 8;
+  const size_t chunk_bytes = (size_t)kChunk * 24 + (size_t)kChunk * kChunkWords * 4;
+  return sort_bytes > chunk_bytes ? sort_bytes : chunk_bytes;
+}
+
+static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
+  g.smem_keys_cap = smem_keys_cap(g.src.per_image);
+  g.gkeys_stride = next_pow2_ll(g.src.per_image);
+  const size_t smem = nms_smem_bytes(g.src.per_image);
+  static size_t configured = 0;
+  if (smem > configured) {
+    YX_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  sort_nms_kernel<<<batch, kNmsThreads, smem, s>>>(g);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+int filter_launch(float* pred, int batch, int anchors, int nc, float conf_thre, int inplace_xyxy, const PostWs& w,
+                  cudaStream_t s) {
+  YX_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * 4, s));
+  // 8 warps per block; blocks per image chosen so that each warp handles ~8 anchors
+  int blocks_per_img = (anchors + 63) / 64;
+  if (blocks_per_img < 1) blocks_per_img = 1;
+  filter_kernel<<<batch * blocks_per_img, 256, 0, s>>>(pred, batch, anchors, nc, conf_thre, inplace_xyxy, w.cand,
+                                                       w.keys, w.counts);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_thre, double nms_thre, int nms_variant,
+                       int inplace_xyxy, float* dets, long long* det_idx, int* det_count, int max_det, void* ws,
+                       long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(pred && dets && det_count && ws, YX_ERR_INVALID_ARG, "postprocess: null pointer");
+  YX_REQUIRE(batch > 0 && anchors > 0 && nc > 0 && max_det > 0, YX_ERR_INVALID_ARG, "postprocess: bad sizes");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "postprocess: nms_variant must be 0..4");
+  YX_REQUIRE(((uintptr_t)ws & 255) == 0, YX_ERR_INVALID_ARG, "postprocess: workspace must be 256-byte aligned");
+  PostWs w = carve_ws(ws, batch, anchors);
+  YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "postprocess: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
+  int rc = filter_launch(pred, batch, anchors, nc, conf_thre, inplace_xyxy, w, s);
+  if (rc) return rc;
+  NmsArgs g;
+  memset(&g, 0, sizeof(g));
+  g.src.boxes = w.cand; g.src.box_stride = 8;
+  g.src.scores = w.cand + 7; g.src.score_stride = 8;
+  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1;
+  g.src.per_image = anchors;
+  g.keys = w.keys; g.counts = w.counts;
+  g.thr = thr_for_strict_gt(nms_thre);
+  g.variant = nms_variant;
+  g.gkeys = w.gkeys; g.sorted_box = w.sbox; g.sorted_cls = w.scls; g.sorted_idx = w.sidx; g.kept_pos = w.kept;
+  g.dets = dets; g.det_idx = det_idx; g.det_count = det_count; g.max_det = max_det;
+  return launch_sort_nms(g, batch, s);
+}
+
+int filter_compact_launch(const float* pred, int batch, int anchors, int nc, float conf_thre, float* cand,
+                          int* cand_idx, int* cand_count, void* ws, long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(pred && cand && cand_idx && cand_count && ws, YX_ERR_INVALID_ARG, "filter: null pointer");
+  YX_REQUIRE(batch > 0 && anchors > 0 && nc > 0, YX_ERR_INVALID_ARG, "filter: bad sizes");
+  PostWs w = carve_ws(ws, batch, anchors);
+  YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "filter: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
+  int rc = filter_launch(const_cast<float*>(pred), batch, anchors, nc, conf_thre, 0, w, s);
+  if (rc) return rc;
+  compact_kernel<<<batch, 1024, 0, s>>>(w.cand, anchors, conf_thre, cand, cand_idx, cand_count);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+int batched_nms_launch(const float* boxes, const float* scores, const int* cls, const int* counts, int batch,
+                       int n_max, double nms_thre, int nms_variant, int* keep, int* keep_count, void* ws,
+                       long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(boxes && scores && cls && counts && keep && keep_count && ws, YX_ERR_INVALID_ARG, "nms: null pointer");
+  YX_REQUIRE(batch > 0 && n_max > 0, YX_ERR_INVALID_ARG, "nms: bad sizes");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "nms: nms_variant must be 0..4");
+  PostWs w = carve_ws(ws, batch, n_max);
+  YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "nms: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
+  NmsArgs g;
+  memset(&g, 0, sizeof(g));
+  g.src.boxes = boxes; g.src.box_stride = 4;
+  g.src.scores = scores; g.src.score_stride = 1;
+  g.src.cls = cls; g.src.cls_stride = 1; g.src.cls_is_float = 0;
+  g.src.per_image = n_max;
+  g.keys = nullptr; g.counts = counts;
+  g.thr = thr_for_strict_gt(nms_thre);
+  g.variant = nms_variant;
+  g.gkeys = w.gkeys; g.sorted_box = w.sbox; g.sorted_cls = w.scls; g.sorted_idx = w.sidx; g.kept_pos = w.kept;
+  g.keep = keep; g.keep_count = keep_count;
+  return launch_sort_nms(g, batch, s);
+}
+
+}  // namespace yx

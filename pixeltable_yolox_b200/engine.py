@@ -1,0 +1,417 @@
+"""Host-side lowering of the reference's eval forward onto the native plan runtime.
+
+`Builder` turns a module tree (network_blocks / darknet / yolo_pafpn / yolo_head) into an ordered
+list of launches over pre-allocated NHWC buffers: BN is folded and weights repacked once by a
+CUDA kernel (yx_pack_weights), tensor maps are encoded once (yx_plan_add_conv), and a forward is a
+single FFI call (yx_plan_run) that can replay one CUDA graph.
+
+Data layout in HBM
+  activations : NHWC, bf16/fp16 (tensor-core path) or fp32 (verification path); a logical tensor
+                with c channels occupies pad16(c) channel slots (extra slots are exact zeros);
+                concatenations (CSP, PAFPN, SPP, head towers) are *segments* of one buffer that
+                the producers write directly, so no concat/upsample kernels exist.
+  weights     : [out_c][taps][in_c] K-major in the activation dtype; bias fp32.
+  head output : [B, A, 5+nc] fp32, written by the prediction-GEMM epilogue.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import ACT_CODES, check, dtype_code, lib, stream_ptr
+from .ops import View
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+@dataclass
+class Feat:
+    """NHWC buffer slice made of channel segments; segment i has segs[i] real channels and
+    occupies pad16(segs[i]) slots."""
+
+    t: torch.Tensor          # [B, H, W, Ctot]
+    c_off: int
+    segs: List[int]
+
+    @property
+    def B(self): return self.t.shape[0]
+    @property
+    def H(self): return self.t.shape[1]
+    @property
+    def W(self): return self.t.shape[2]
+    @property
+    def c_slots(self): return sum(pad16(s) for s in self.segs)
+    @property
+    def c_real(self): return sum(self.segs)
+
+    def seg_off(self, i: int) -> int:
+        return sum(pad16(s) for s in self.segs[:i])
+
+    def seg(self, i: int) -> "Feat":
+        return Feat(self.t, self.c_off + self.seg_off(i), [self.segs[i]])
+
+    def view(self) -> View:
+        return View(self.t, self.c_off, self.c_slots)
+
+    def to_nchw(self) -> torch.Tensor:
+        """Logical NCHW tensor (drops the padding slots); for module-level forward only."""
+        chunks = []
+        for i, s in enumerate(self.segs):
+            o = self.c_off + self.seg_off(i)
+            chunks.append(self.t[..., o:o + s])
+        x = chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=-1)
+        return x.permute(0, 3, 1, 2).contiguous()
+
+
+@dataclass
+class Part:
+    """One source conv of a (possibly merged) GEMM: rows [o_off, o_off+o) of the packed weight;
+    its logical input channels map, in order, onto the listed input segments."""
+
+    weight: torch.Tensor
+    bn: Optional[nn.BatchNorm2d]
+    bias: Optional[torch.Tensor]
+    o_off: Optional[int] = None
+    in_segs: Optional[List[int]] = None
+
+
+class Builder:
+    def __init__(self, device: torch.device, dtype: torch.dtype, use_plan: bool = True):
+        if device.type != "cuda":
+            raise RuntimeError(
+                f"eval forward requested on {device}: the B200 path runs hand-written sm_100a CUDA only; "
+                "there is no CPU fallback (put the module in train() mode for the autograd path)")
+        self.dev = device
+        self.dtype = dtype
+        self.plan = lib().yx_plan_create() if use_plan else None
+        self.keep: List[torch.Tensor] = []   # buffers and packed weights referenced by the plan
+        self.weight_cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.n_ops = 0
+        self.flops = 0.0
+        self.input_ops: List[tuple] = []
+
+    def close(self):
+        if self.plan is not None:
+            lib().yx_plan_destroy(self.plan)
+            self.plan = None
+
+    # ---------------------------------------------------------------- buffers
+    def new_feat(self, B, H, W, segs: Sequence[int]) -> Feat:
+        slots = sum(pad16(s) for s in segs)
+        needs_zero = any(pad16(s) != s for s in segs)
+        alloc = torch.zeros if needs_zero else torch.empty
+        t = alloc((B, H, W, slots), dtype=self.dtype, device=self.dev)
+        self.keep.append(t)
+        return Feat(t, 0, list(segs))
+
+    def from_nchw(self, x: torch.Tensor) -> Feat:
+        B, Cc, H, W = x.shape
+        f = self.new_feat(B, H, W, [Cc])
+        if pad16(Cc) != Cc:
+            f.t.zero_()
+        f.t[..., :Cc] = x.permute(0, 2, 3, 1).to(self.dtype)
+        return f
+
+    # ---------------------------------------------------------------- weights
+    def part(self, m, o_off=None, in_segs=None) -> Part:
+        if isinstance(m, nn.Conv2d):
+            return Part(m.weight, None, m.bias, o_off, in_segs)
+        return Part(m.conv.weight, m.bn, m.conv.bias, o_off, in_segs)
+
+    def _pack(self, parts: List[Part], x: Feat, ksize: int, o_total: Optional[int]):
+        key = tuple((p.weight.data_ptr(), p.weight._version, p.o_off, tuple(p.in_segs or ())) for p in parts) + (
+            tuple(x.segs), self.dtype, o_total)
+        hit = self.weight_cache.get(key)
+        if hit is not None:
+            return hit
+        # output rows: explicit offsets (head) or one padded segment per part
+        out_segs = []
+        if all(p.o_off is None for p in parts):
+            off = 0
+            for p in parts:
+                p.o_off = off
+                out_segs.append(p.weight.shape[0])
+                off += pad16(p.weight.shape[0])
+            O = off
+        else:
+            O = pad16(o_total)
+            out_segs = [o_total]
+        I = x.c_slots
+        w = torch.zeros((O, ksize * ksize, I), dtype=self.dtype, device=self.dev)
+        bias = torch.zeros((O,), dtype=torch.float32, device=self.dev)
+        for p in parts:
+            segs = p.in_segs if p.in_segs is not None else list(range(len(x.segs)))
+            lo = 0
+            bn = None
+            eps = 0.0
+            if p.bn is not None:
+                bn = (p.bn.weight, p.bn.bias, p.bn.running_mean, p.bn.running_var)
+                eps = p.bn.eps
+            assert sum(x.segs[s] for s in segs) == p.weight.shape[1], (
+                f"conv expects {p.weight.shape[1]} input channels, segments give {[x.segs[s] for s in segs]}")
+            for s in segs:
+                n = x.segs[s]
+                ops.pack_weights(p.weight[:, lo:lo + n], bn, p.bias, eps, w, bias, o_off=p.o_off, i_off=x.seg_off(s))
+                lo += n
+        self.keep += [w, bias]
+        self.weight_cache[key] = (w, bias, out_segs)
+        return w, bias, out_segs
+
+    # ---------------------------------------------------------------- ops
+    def conv(self, x: Feat, parts: List[Part], out: Optional[Feat] = None, res: Optional[Feat] = None,
+             ups: Optional[Feat] = None, act: Optional[str] = "silu", ksize: int = 1, stride: int = 1,
+             o_total: Optional[int] = None, head: Optional[dict] = None) -> Optional[Feat]:
+        w, bias, out_segs = self._pack(parts, x, ksize, o_total)
+        pad = (ksize - 1) // 2
+        oh = (x.H + 2 * pad - ksize) // stride + 1
+        ow = (x.W + 2 * pad - ksize) // stride + 1
+        head_arg = None
+        if head is not None:
+            ho = head["out"]
+            head_arg = dict(out_ptr=ho.data_ptr(), anchors=head["anchors"], anchor_off=head["anchor_off"],
+                            nc=head["nc"], decode=head["decode"], stride=head["stride"])
+            out_view = None
+        else:
+            if out is None:
+                out = self.new_feat(x.B, oh, ow, out_segs)
+            assert out.c_slots == w.shape[0], (out.segs, w.shape)
+            out_view = out.view()
+        d = ops.make_conv_desc(x.view(), w, bias, out_view, ksize, stride, ACT_CODES[act],
+                               res.view() if res is not None else None,
+                               ups.view() if ups is not None else None, head_arg)
+        self._emit_conv(d)
+        self.flops += 2.0 * x.B * oh * ow * sum(p.weight.shape[0] * p.weight.shape[1] for p in parts) * ksize * ksize
+        return out
+
+    def _emit_conv(self, d):
+        if self.plan is not None:
+            check(lib().yx_plan_add_conv(self.plan, C.byref(d)), "plan_add_conv")
+        else:
+            check(lib().yx_conv_bn_act_fwd(C.byref(d), stream_ptr(self.dev)), "conv")
+        self.n_ops += 1
+
+    def dwconv(self, x: Feat, m, out: Optional[Feat] = None) -> Feat:
+        """Depthwise 3x3 BaseConv (groups == channels)."""
+        conv, bn = m.conv, m.bn
+        c = conv.weight.shape[0]
+        assert len(x.segs) == 1 and x.segs[0] == c and conv.kernel_size == (3, 3)
+        key = (conv.weight.data_ptr(), conv.weight._version, "dw", self.dtype)
+        hit = self.weight_cache.get(key)
+        if hit is None:
+            w = torch.zeros((9, pad16(c)), dtype=self.dtype, device=self.dev)
+            bias = torch.zeros((pad16(c),), dtype=torch.float32, device=self.dev)
+            ops.pack_weights(conv.weight, (bn.weight, bn.bias, bn.running_mean, bn.running_var), conv.bias, bn.eps,
+                             w, bias, depthwise=True)
+            self.keep += [w, bias]
+            hit = (w, bias)
+            self.weight_cache[key] = hit
+        w, bias = hit
+        stride = conv.stride[0]
+        oh = (x.H + 2 - 3) // stride + 1
+        ow = (x.W + 2 - 3) // stride + 1
+        if out is None:
+            out = self.new_feat(x.B, oh, ow, [c])
+        from .network_blocks import act_name
+
+        act = ACT_CODES[act_name(m.act)]
+        xv, ov = x.view(), out.view()
+        if self.plan is not None:
+            check(lib().yx_plan_add_dwconv(self.plan, xv.ptr, xv.ld, w.data_ptr(), bias.data_ptr(), ov.ptr, ov.ld,
+                                           x.B, x.H, x.W, xv.c, stride, act, dtype_code(self.dtype)), "plan_add_dwconv")
+        else:
+            ops.dwconv3x3(xv, w, bias, ov, stride, act)
+        self.n_ops += 1
+        self.flops += 2.0 * x.B * oh * ow * c * 9
+        return out
+
+    def spp(self, cat: Feat, c: int) -> None:
+        v = cat.view()
+        if pad16(c) != c:
+            raise NotImplementedError("SPP with a hidden width that is not a multiple of 16")
+        if self.plan is not None:
+            check(lib().yx_plan_add_spp(self.plan, v.ptr, v.ld, v.B, v.H, v.W, c, dtype_code(self.dtype)), "plan_add_spp")
+        else:
+            ops.spp_maxpool(v, c)
+        self.n_ops += 1
+
+    def focus(self, img: torch.Tensor) -> Feat:
+        B, _, H, W = img.shape
+        f = self.new_feat(B, H // 2, W // 2, [12])
+        v = f.view()
+        if self.plan is not None:
+            check(lib().yx_plan_add_focus(self.plan, img.data_ptr(), dtype_code(img.dtype), v.ptr, v.ld,
+                                          dtype_code(self.dtype), B, H, W), "plan_add_focus")
+        else:
+            ops.focus_s2d(img, v)
+        self.n_ops += 1
+        return f
+
+    def postprocess(self, pred, nc, conf, nms, variant, inplace, dets, det_idx, det_count, max_det, ws):
+        check(lib().yx_plan_add_postprocess(self.plan, pred.data_ptr(), pred.shape[0], pred.shape[1], nc, float(conf),
+                                            float(nms), int(variant), 1 if inplace else 0, dets.data_ptr(),
+                                            det_idx.data_ptr(), det_count.data_ptr(), max_det, ws.data_ptr(),
+                                            ws.numel()), "plan_add_postprocess")
+        self.keep += [pred, dets, det_idx, det_count, ws]
+
+    def run(self, use_graph: bool = False) -> None:
+        check(lib().yx_plan_run(self.plan, stream_ptr(self.dev), 1 if use_graph else 0), "plan_run")
+
+    @property
+    def launches(self) -> int:
+        return lib().yx_plan_num_launches(self.plan) if self.plan is not None else self.n_ops
+
+
+# ---------------------------------------------------------------------------------------------
+# module-level eval forward (NCHW in / NCHW out like the reference; eager launches)
+# ---------------------------------------------------------------------------------------------
+def _module_dtype(m: nn.Module, x: torch.Tensor) -> torch.dtype:
+    for p in m.parameters():
+        return p.dtype
+    return x.dtype
+
+
+def _check_dtype(dt: torch.dtype) -> None:
+    if dt not in (torch.bfloat16, torch.float16, torch.float32):
+        raise TypeError(f"unsupported module dtype {dt}")
+
+
+@torch.no_grad()
+def run_block(block: nn.Module, x: torch.Tensor):
+    """Eval forward of a single block through eager C-ABI launches."""
+    from .darknet import CspDarknet
+    from .network_blocks import Focus
+    from .yolo_pafpn import YoloPafpn
+
+    dt = _module_dtype(block, x)
+    _check_dtype(dt)
+    b = Builder(x.device, dt, use_plan=False)
+    if isinstance(block, Focus):
+        return block.lower_image(b, x.contiguous()).to_nchw()
+    if isinstance(block, CspDarknet):
+        feats = block.lower_image(b, x.contiguous())
+        return {k: v.to_nchw() for k, v in feats.items() if k in block.out_features}
+    if isinstance(block, YoloPafpn):
+        return tuple(f.to_nchw() for f in block.lower_image(b, x.contiguous()))
+    return block.lower(b, b.from_nchw(x)).to_nchw()
+
+
+@torch.no_grad()
+def run_head(head: nn.Module, xin: Sequence[torch.Tensor]) -> torch.Tensor:
+    dt = _module_dtype(head, xin[0])
+    _check_dtype(dt)
+    b = Builder(xin[0].device, dt, use_plan=False)
+    feats = [b.from_nchw(x) for x in xin]
+    A = sum(f.H * f.W for f in feats)
+    out = torch.empty((xin[0].shape[0], A, 5 + head.num_classes), dtype=torch.float32, device=xin[0].device)
+    head.lower(b, feats, out)
+    return out if head.output_dtype is None else out.to(head.output_dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-model engine
+# ---------------------------------------------------------------------------------------------
+class InferenceEngine:
+    """One captured plan per (batch, H, W, input dtype, thresholds): YoloxModule.forward (eval) and,
+    optionally, postprocess in the same CUDA graph. The batch is walked in micro-batches that
+    share every intermediate buffer, so a micro-batch's activations stay resident in the 126 MB L2
+    between producer and consumer layers."""
+
+    def __init__(self, module: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype,
+                 device: torch.device, micro_batch: Optional[int] = None, use_graph: bool = True,
+                 post: Optional[dict] = None):
+        from .yolox import YoloxModule
+
+        assert isinstance(module, YoloxModule)
+        if height % 32 or width % 32:
+            raise ValueError(f"input size must be a multiple of 32, got {height}x{width}")
+        self.module = module
+        self.dtype = _module_dtype(module, torch.empty(0))
+        _check_dtype(self.dtype)
+        self.use_graph = use_graph
+        self.batch = batch
+        self.mb = min(batch, micro_batch or batch)
+        self.builder = Builder(device, self.dtype, use_plan=True)
+        b = self.builder
+        head = module.head
+        strides = head.strides
+        self.anchors = sum((height // s) * (width // s) for s in strides)
+        self.nc = head.num_classes
+        # persistent input staging buffer: the plan's pointers are fixed at build time
+        self.input = torch.empty((batch, 3, height, width), dtype=in_dtype, device=device)
+        self.pred = torch.empty((batch, self.anchors, 5 + self.nc), dtype=torch.float32, device=device)
+        # intermediate buffers are allocated while lowering the first micro-batch and reused after
+        first_keep = None
+        for b0 in range(0, batch, self.mb):
+            b1 = min(batch, b0 + self.mb)
+            if b1 - b0 != self.mb:
+                self._replay_alloc = None       # ragged tail: allocate fresh (smaller) buffers
+            img = self.input[b0:b1]
+            if first_keep is None or b1 - b0 != self.mb:
+                mark = len(b.keep)
+                self._lower(img, self.pred[b0:b1])
+                if first_keep is None:
+                    first_keep = (mark, len(b.keep))
+                    self._record = [t for t in b.keep[mark:]]
+            else:
+                self._lower_reusing(img, self.pred[b0:b1])
+        self.post = None
+        if post is not None:
+            max_det = post.get("max_det") or self.anchors
+            dev = device
+            self.dets = torch.zeros((batch, max_det, 7), dtype=torch.float32, device=dev)
+            self.det_idx = torch.zeros((batch, max_det), dtype=torch.int64, device=dev)
+            self.det_count = torch.zeros((batch,), dtype=torch.int32, device=dev)
+            ws = torch.empty((lib().yx_postprocess_workspace_bytes(batch, self.anchors),), dtype=torch.uint8, device=dev)
+            b.postprocess(self.pred, self.nc, post["conf_thre"], post["nms_thre"], post["nms_variant"], True,
+                          self.dets, self.det_idx, self.det_count, max_det, ws)
+            self.post = dict(post, max_det=max_det)
+        self.flops_per_image = b.flops / batch
+
+    # buffer reuse across micro-batches: new_feat hands back the tensors of the first lowering
+    def _lower(self, img, pred_slice):
+        m = self.module
+        feats = m.backbone.lower_image(self.builder, img)
+        m.head.lower(self.builder, list(feats), pred_slice)
+
+    def _lower_reusing(self, img, pred_slice):
+        b = self.builder
+        pool = list(self._record)
+        orig_new_feat = b.new_feat
+
+        def reuse_feat(B, H, W, segs):
+            slots = sum(pad16(s) for s in segs)
+            while pool:
+                t = pool.pop(0)
+                if t.dim() == 4:
+                    assert tuple(t.shape) == (B, H, W, slots), (tuple(t.shape), (B, H, W, slots))
+                    return Feat(t, 0, list(segs))
+            raise RuntimeError("buffer replay ran out of tensors")
+
+        b.new_feat = reuse_feat
+        try:
+            self._lower(img, pred_slice)
+        finally:
+            b.new_feat = orig_new_feat
+
+    @property
+    def launches(self) -> int:
+        return self.builder.launches
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [B,3,H,W] on any device (a host tensor is copied H2D here). Returns the engine's
+        own prediction buffer [B, A, 5+nc] fp32 (valid until the next call)."""
+        if tuple(x.shape) != tuple(self.input.shape):
+            raise ValueError(f"engine built for {tuple(self.input.shape)}, got {tuple(x.shape)}")
+        self.input.copy_(x, non_blocking=True)
+        self.builder.run(self.use_graph)
+        return self.pred
+
+    def close(self):
+        self.builder.close()

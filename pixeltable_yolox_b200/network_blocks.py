@@ -1,0 +1,206 @@
+"""Building blocks with the reference's names, constructor signatures and state_dict layout
+(yolox/models/network_blocks.py:27-208), so reference checkpoints load unchanged.
+
+Execution model
+  * eval + CUDA : every block lowers itself onto an ``engine.Builder`` (``lower`` methods); the
+    launches are hand-written sm_100a kernels called through the C-ABI. ``forward`` on a block
+    builds a tiny plan for just that block (NCHW in / NCHW out, like the reference).
+  * training    : plain PyTorch ops so that autograd can differentiate the step (SURVEY 8a row 6:
+    the SimOTA assignment is the B200-native part of the training step).
+  * eval + CPU  : raises. There is deliberately no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def get_activation(name="silu", inplace=True):
+    # yolox/models/network_blocks.py:14-24
+    table = {"silu": lambda: nn.SiLU(inplace=inplace), "relu": lambda: nn.ReLU(inplace=inplace),
+             "lrelu": lambda: nn.LeakyReLU(0.1, inplace=inplace)}
+    if name not in table:
+        raise AttributeError("Unsupported act type: {}".format(name))
+    return table[name]()
+
+
+def act_name(module: nn.Module) -> str:
+    if isinstance(module, nn.SiLU):
+        return "silu"
+    if isinstance(module, nn.LeakyReLU):
+        return "lrelu"
+    if isinstance(module, nn.ReLU):
+        return "relu"
+    raise AttributeError(f"Unsupported activation module {type(module).__name__}")
+
+
+class _B200Block(nn.Module):
+    """Shared forward dispatch: training -> torch autograd ops, eval -> B200 plan."""
+
+    def _train_forward(self, x):  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    def lower(self, b, x):  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    def forward(self, x):
+        if self.training:
+            return self._train_forward(x)
+        from .engine import run_block
+
+        return run_block(self, x)
+
+
+class BaseConv(_B200Block):
+    """Conv2d(bias=False, pad=(k-1)//2) -> BatchNorm2d -> act (network_blocks.py:27-52)."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="silu"):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=ksize, stride=stride,
+                              padding=(ksize - 1) // 2, groups=groups, bias=bias)
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.act = get_activation(act, inplace=True)
+
+    def _train_forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+    def fuseforward(self, x):
+        return self.act(self.conv(x))
+
+    def lower(self, b, x, out=None, res=None, ups=None):
+        if self.conv.groups != 1:
+            return b.dwconv(x, self, out=out)
+        return b.conv(x, [b.part(self)], out=out, res=res, ups=ups, act=act_name(self.act),
+                      ksize=self.conv.kernel_size[0], stride=self.conv.stride[0])
+
+
+class DWConv(_B200Block):
+    """Depthwise 3x3 BaseConv followed by a 1x1 BaseConv (network_blocks.py:55-74)."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride=1, act="silu"):
+        super().__init__()
+        self.dconv = BaseConv(in_channels, in_channels, ksize=ksize, stride=stride, groups=in_channels, act=act)
+        self.pconv = BaseConv(in_channels, out_channels, ksize=1, stride=1, groups=1, act=act)
+
+    def _train_forward(self, x):
+        return self.pconv._train_forward(self.dconv._train_forward(x))
+
+    def lower(self, b, x, out=None, res=None, ups=None):
+        return self.pconv.lower(b, self.dconv.lower(b, x), out=out, res=res, ups=ups)
+
+
+class Bottleneck(_B200Block):
+    """1x1 -> 3x3 (+ x when shortcut and channels match) (network_blocks.py:77-99)."""
+
+    def __init__(self, in_channels, out_channels, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
+        super().__init__()
+        hidden_channels = int(out_channels * expansion)
+        Conv = DWConv if depthwise else BaseConv
+        self.conv1 = BaseConv(in_channels, hidden_channels, 1, stride=1, act=act)
+        self.conv2 = Conv(hidden_channels, out_channels, 3, stride=1, act=act)
+        self.use_add = shortcut and in_channels == out_channels
+
+    def _train_forward(self, x):
+        y = self.conv2._train_forward(self.conv1._train_forward(x))
+        return y + x if self.use_add else y
+
+    def lower(self, b, x, out=None):
+        # the residual is added in the epilogue of conv2; writing in place over x is safe because
+        # conv2 reads only conv1's output and each thread reads x[p] before it writes out[p]
+        t = self.conv1.lower(b, x)
+        return self.conv2.lower(b, t, out=out, res=x if self.use_add else None)
+
+
+class ResLayer(_B200Block):
+    "Residual layer with `in_channels` inputs (Darknet-53 only; network_blocks.py:102-117)."
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        mid_channels = in_channels // 2
+        self.layer1 = BaseConv(in_channels, mid_channels, ksize=1, stride=1, act="lrelu")
+        self.layer2 = BaseConv(mid_channels, in_channels, ksize=3, stride=1, act="lrelu")
+
+    def _train_forward(self, x):
+        return x + self.layer2._train_forward(self.layer1._train_forward(x))
+
+    def lower(self, b, x, out=None):
+        return self.layer2.lower(b, self.layer1.lower(b, x), out=out, res=x)
+
+
+class SPPBottleneck(_B200Block):
+    """1x1 -> cat[x, maxpool5, maxpool9, maxpool13] -> 1x1 (network_blocks.py:120-142)."""
+
+    def __init__(self, in_channels, out_channels, kernel_sizes=(5, 9, 13), activation="silu"):
+        super().__init__()
+        hidden_channels = in_channels // 2
+        self.conv1 = BaseConv(in_channels, hidden_channels, 1, stride=1, act=activation)
+        self.m = nn.ModuleList([nn.MaxPool2d(kernel_size=ks, stride=1, padding=ks // 2) for ks in kernel_sizes])
+        conv2_channels = hidden_channels * (len(kernel_sizes) + 1)
+        self.conv2 = BaseConv(conv2_channels, out_channels, 1, stride=1, act=activation)
+
+    def _train_forward(self, x):
+        x = self.conv1._train_forward(x)
+        x = torch.cat([x] + [m(x) for m in self.m], dim=1)
+        return self.conv2._train_forward(x)
+
+    def lower(self, b, x, out=None):
+        ks = tuple(m.kernel_size for m in self.m)
+        if ks != (5, 9, 13):
+            raise NotImplementedError(f"SPP kernel sizes {ks}: the B200 kernel implements the 5/9/13 cascade")
+        hidden = self.conv1.conv.out_channels
+        cat = b.new_feat(x.B, x.H, x.W, [hidden] * 4)   # conv1 writes segment 0, the pool kernel 1..3
+        self.conv1.lower(b, x, out=cat.seg(0))
+        b.spp(cat, hidden)
+        return self.conv2.lower(b, cat, out=out)
+
+
+class CspLayer(_B200Block):
+    """C3: conv3(cat(m(conv1(x)), conv2(x))) (network_blocks.py:145-183)."""
+
+    def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
+        super().__init__()
+        hidden_channels = int(out_channels * expansion)
+        self.conv1 = BaseConv(in_channels, hidden_channels, 1, stride=1, act=act)
+        self.conv2 = BaseConv(in_channels, hidden_channels, 1, stride=1, act=act)
+        self.conv3 = BaseConv(2 * hidden_channels, out_channels, 1, stride=1, act=act)
+        self.m = nn.Sequential(*[
+            Bottleneck(hidden_channels, hidden_channels, shortcut, 1.0, depthwise, act=act) for _ in range(n)
+        ])
+
+    def _train_forward(self, x):
+        x_1 = self.conv1._train_forward(x)
+        x_2 = self.conv2._train_forward(x)
+        for blk in self.m:
+            x_1 = blk._train_forward(x_1)
+        return self.conv3._train_forward(torch.cat((x_1, x_2), dim=1))
+
+    def lower(self, b, x, out=None):
+        # conv1 and conv2 read the same tensor: one GEMM with stacked weights writes the concat
+        # buffer [x_1 | x_2]; the bottleneck chain then updates the x_1 half in place, so the
+        # torch.cat of the reference (network_blocks.py:182) never happens.
+        hidden = self.conv1.conv.out_channels
+        cat = b.conv(x, [b.part(self.conv1), b.part(self.conv2)], act=act_name(self.conv1.act), ksize=1, stride=1)
+        x1 = cat.seg(0)
+        for blk in self.m:
+            blk.lower(b, x1, out=x1)
+        return self.conv3.lower(b, cat, out=out)
+
+
+class Focus(_B200Block):
+    """Space-to-depth (TL, BL, TR, BR) then a conv (network_blocks.py:186-208)."""
+
+    def __init__(self, in_channels, out_channels, ksize=1, stride=1, act="silu"):
+        super().__init__()
+        self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act)
+
+    def _train_forward(self, x):
+        tl, tr = x[..., ::2, ::2], x[..., ::2, 1::2]
+        bl, br = x[..., 1::2, ::2], x[..., 1::2, 1::2]
+        return self.conv._train_forward(torch.cat((tl, bl, tr, br), dim=1))
+
+    def lower_image(self, b, img, out=None):
+        """img: NCHW fp32/uint8 image batch (raw 0..255)."""
+        if img.shape[1] != 3:
+            raise NotImplementedError("Focus on the B200 path expects a 3-channel image")
+        return self.conv.lower(b, b.focus(img), out=out)

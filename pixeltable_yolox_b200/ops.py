@@ -1,0 +1,304 @@
+"""Torch-tensor front end of the C-ABI ops (pointers in, pointers out; no compute in Python).
+
+PyTorch is used for device memory and streams only. Every function here requires CUDA tensors
+and raises otherwise: the hot path is hand-written sm_100a CUDA with no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, dtype_code, lib, require_cuda, stream_ptr
+
+
+@dataclass
+class View:
+    """A channel slice [c_off, c_off + c) of an NHWC buffer ``t`` of shape [B, H, W, Ctot]."""
+
+    t: torch.Tensor
+    c_off: int = 0
+    c: Optional[int] = None
+
+    def __post_init__(self):
+        assert self.t.dim() == 4 and self.t.is_contiguous()
+        if self.c is None:
+            self.c = self.t.shape[3] - self.c_off
+        assert 0 <= self.c_off and self.c_off + self.c <= self.t.shape[3]
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.c_off * self.t.element_size()
+
+    @property
+    def ld(self) -> int:
+        return self.t.shape[3]
+
+    @property
+    def B(self) -> int:
+        return self.t.shape[0]
+
+    @property
+    def H(self) -> int:
+        return self.t.shape[1]
+
+    @property
+    def W(self) -> int:
+        return self.t.shape[2]
+
+    def sub(self, off: int, c: int) -> "View":
+        return View(self.t, self.c_off + off, c)
+
+    def batch_slice(self, b0: int, b1: int) -> "View":
+        return View(self.t[b0:b1], self.c_off, self.c)
+
+    def torch(self) -> torch.Tensor:
+        return self.t[..., self.c_off:self.c_off + self.c]
+
+
+def make_conv_desc(
+    x: View, w: torch.Tensor, bias: torch.Tensor, out: Optional[View], ksize: int, stride: int, act: int,
+    res: Optional[View] = None, ups: Optional[View] = None, head: Optional[dict] = None,
+) -> ConvDesc:
+    pad = (ksize - 1) // 2
+    oh = (x.H + 2 * pad - ksize) // stride + 1
+    ow = (x.W + 2 * pad - ksize) // stride + 1
+    d = ConvDesc()
+    d.batch, d.in_h, d.in_w, d.in_c = x.B, x.H, x.W, x.c
+    d.out_h, d.out_w = oh, ow
+    d.out_c = w.shape[0]
+    d.ksize, d.stride = ksize, stride
+    d.dtype = dtype_code(x.t.dtype)
+    d.act = act
+    d.in_, d.in_ld = x.ptr, x.ld
+    assert w.dtype == x.t.dtype and w.is_contiguous() and w.shape[1] == ksize * ksize and w.shape[2] == x.c, (
+        w.shape, x.c, ksize)
+    assert bias.dtype == torch.float32 and bias.numel() == w.shape[0]
+    d.w = w.data_ptr()
+    d.bias = bias.data_ptr()
+    if head is None:
+        assert out is not None and out.c == d.out_c and out.t.dtype == x.t.dtype
+        assert (out.B, out.H, out.W) == (x.B, oh, ow), ((out.B, out.H, out.W), (x.B, oh, ow))
+        d.epilogue = _lib.YX_EPI_STORE
+        d.out, d.out_ld = out.ptr, out.ld
+        if res is not None:
+            assert (res.B, res.H, res.W, res.c) == (out.B, out.H, out.W, out.c)
+            d.res, d.res_ld = res.ptr, res.ld
+        if ups is not None:
+            assert (ups.B, ups.H, ups.W, ups.c) == (out.B, 2 * out.H, 2 * out.W, out.c)
+            d.ups, d.ups_ld = ups.ptr, ups.ld
+    else:
+        d.epilogue = _lib.YX_EPI_HEAD
+        d.head_out = head["out_ptr"]
+        d.head_anchors = head["anchors"]
+        d.head_anchor_off = head["anchor_off"]
+        d.head_nc = head["nc"]
+        d.head_decode = head["decode"]
+        d.head_stride = float(head["stride"])
+    return d
+
+
+def conv_bn_act(x: View, w, bias, out, ksize, stride, act, res=None, ups=None, head=None, simt=False) -> None:
+    require_cuda(x.t, "conv_bn_act")
+    d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head)
+    fn = lib().yx_conv_bn_act_fwd_simt if simt else lib().yx_conv_bn_act_fwd
+    check(fn(C.byref(d), stream_ptr(x.t.device)), "conv_bn_act")
+
+
+def pack_weights(
+    src: torch.Tensor, bn: Optional[Sequence[torch.Tensor]], conv_bias: Optional[torch.Tensor], eps: float,
+    dst_w: torch.Tensor, dst_b: Optional[torch.Tensor], o_off: int = 0, i_off: int = 0, depthwise: bool = False,
+) -> None:
+    """BN-fold + repack one nn.Conv2d weight [o,i,kh,kw] into dst_w [O,kh*kw,I] at (o_off, i_off)."""
+    require_cuda(dst_w, "pack_weights")
+    dev = dst_w.device
+    src = src.detach().to(device=dev, dtype=torch.float32).contiguous()
+    o, i, kh, kw = src.shape
+    ptrs = [0, 0, 0, 0]
+    keep = [src]
+    if bn is not None:
+        for k, t in enumerate(bn):
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            ptrs[k] = t.data_ptr()
+    cb = 0
+    if conv_bias is not None:
+        conv_bias = conv_bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        keep.append(conv_bias)
+        cb = conv_bias.data_ptr()
+    i_total = dst_w.shape[-1]
+    if depthwise:
+        assert dst_w.dim() == 2 and dst_w.shape[0] == kh * kw
+    else:
+        assert dst_w.dim() == 3 and dst_w.shape[1] == kh * kw and o_off + o <= dst_w.shape[0] and i_off + i <= i_total
+    check(
+        lib().yx_pack_weights(
+            src.data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3], cb, float(eps), o, i, kh, kw, dst_w.data_ptr(),
+            dtype_code(dst_w.dtype), o_off, i_off, i_total, dst_b.data_ptr() if dst_b is not None else 0,
+            1 if depthwise else 0, stream_ptr(dev)),
+        "pack_weights")
+    # the source temporaries must outlive the asynchronous kernel
+    torch.cuda.current_stream(dev).synchronize()
+    del keep
+
+
+def dwconv3x3(x: View, w: torch.Tensor, bias: torch.Tensor, out: View, stride: int, act: int) -> None:
+    require_cuda(x.t, "dwconv3x3")
+    assert w.shape == (9, x.c) and out.c == x.c
+    check(
+        lib().yx_dwconv3x3_bn_act_fwd(x.ptr, x.ld, w.data_ptr(), bias.data_ptr(), out.ptr, out.ld, x.B, x.H, x.W, x.c,
+                                      stride, act, dtype_code(x.t.dtype), stream_ptr(x.t.device)),
+        "dwconv3x3")
+
+
+def spp_maxpool(buf: View, c: int) -> None:
+    require_cuda(buf.t, "spp_maxpool")
+    assert buf.c >= 4 * c
+    check(lib().yx_spp_maxpool(buf.ptr, buf.ld, buf.B, buf.H, buf.W, c, dtype_code(buf.t.dtype),
+                               stream_ptr(buf.t.device)), "spp_maxpool")
+
+
+def focus_s2d(img: torch.Tensor, out: View) -> None:
+    require_cuda(img, "focus_s2d")
+    assert img.dim() == 4 and img.shape[1] == 3 and img.is_contiguous()
+    assert out.c_off == 0 and out.ld >= 16
+    check(lib().yx_focus_s2d(img.data_ptr(), dtype_code(img.dtype), out.ptr, out.ld, dtype_code(out.t.dtype),
+                             img.shape[0], img.shape[2], img.shape[3], stream_ptr(img.device)), "focus_s2d")
+
+
+def head_decode_(pred: torch.Tensor, hw: Sequence[Sequence[int]], strides: Sequence[int]) -> torch.Tensor:
+    require_cuda(pred, "head_decode")
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    n = len(strides)
+    hw_arr = (C.c_int32 * (2 * n))(*[int(v) for pair in hw for v in pair])
+    st_arr = (C.c_int32 * n)(*[int(s) for s in strides])
+    check(lib().yx_head_decode(pred.data_ptr(), pred.shape[0], pred.shape[1], pred.shape[2] - 5, hw_arr, st_arr, n,
+                               stream_ptr(pred.device)), "head_decode")
+    return pred
+
+
+# ---------------------------------------------------------------------------------------------
+# postprocess / NMS
+# ---------------------------------------------------------------------------------------------
+_ws_cache: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+    key = (dev.index, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def postprocess_device(pred: torch.Tensor, num_classes: int, conf_thre: float, nms_thre: float, nms_variant: int,
+                       inplace_xyxy: bool = True, max_det: Optional[int] = None):
+    """Returns (dets [B,max_det,7] fp32, det_idx [B,max_det] int64, det_count [B] int32) on device."""
+    require_cuda(pred, "postprocess")
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    B, A, nch = pred.shape
+    assert nch == 5 + num_classes
+    dev = pred.device
+    if max_det is None:
+        max_det = A
+    dets = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
+    det_idx = torch.empty((B, max_det), dtype=torch.int64, device=dev)
+    det_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    if B == 0:
+        return dets, det_idx, det_count
+    nbytes = lib().yx_postprocess_workspace_bytes(B, A)
+    ws = _workspace(dev, nbytes, "post")
+    check(lib().yx_postprocess(pred.data_ptr(), B, A, num_classes, float(conf_thre), float(nms_thre), int(nms_variant),
+                               1 if inplace_xyxy else 0, dets.data_ptr(), det_idx.data_ptr(), det_count.data_ptr(),
+                               max_det, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "postprocess")
+    return dets, det_idx, det_count
+
+
+def score_filter_compact(pred: torch.Tensor, num_classes: int, conf_thre: float):
+    require_cuda(pred, "score_filter_compact")
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    B, A, _ = pred.shape
+    dev = pred.device
+    cand = torch.zeros((B, A, 8), dtype=torch.float32, device=dev)
+    idx = torch.zeros((B, A), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ws = _workspace(dev, lib().yx_postprocess_workspace_bytes(B, A), "post")
+    check(lib().yx_score_filter_compact(pred.data_ptr(), B, A, num_classes, float(conf_thre), cand.data_ptr(),
+                                        idx.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+          "score_filter_compact")
+    return cand, idx, cnt
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, cls: torch.Tensor, counts: torch.Tensor, nms_thre: float,
+                nms_variant: int):
+    """boxes [B,n,4] fp32 xyxy, scores [B,n] fp32, cls [B,n] int32, counts [B] int32 -> keep [B,n], keep_count [B]."""
+    require_cuda(boxes, "batched_nms")
+    B, n, _ = boxes.shape
+    dev = boxes.device
+    boxes = boxes.contiguous().float(); scores = scores.contiguous().float()
+    cls = cls.contiguous().to(torch.int32); counts = counts.contiguous().to(torch.int32)
+    keep = torch.full((B, n), -1, dtype=torch.int32, device=dev)
+    keep_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ws = _workspace(dev, lib().yx_postprocess_workspace_bytes(B, n), "post")
+    check(lib().yx_batched_nms(boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), counts.data_ptr(), B, n,
+                               float(nms_thre), int(nms_variant), keep.data_ptr(), keep_count.data_ptr(),
+                               ws.data_ptr(), ws.numel(), stream_ptr(dev)), "batched_nms")
+    return keep, keep_count
+
+
+def bboxes_iou_device(a: torch.Tensor, b: torch.Tensor, xyxy: bool) -> torch.Tensor:
+    require_cuda(a, "bboxes_iou")
+    a = a.contiguous().float(); b = b.contiguous().float()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().yx_bboxes_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], 1 if xyxy else 0, out.data_ptr(),
+                              stream_ptr(a.device)), "bboxes_iou")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SimOTA
+# ---------------------------------------------------------------------------------------------
+def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tensor, y_shifts: torch.Tensor,
+                  strides: torch.Tensor, num_classes: int):
+    """Batched get_assignments. Returns dict of dense per-anchor tensors (see include/yx_b200.h)."""
+    require_cuda(pred, "simota_assign")
+    pred = pred.contiguous().float(); labels = labels.contiguous().float()
+    B, A, nch = pred.shape
+    assert nch == 5 + num_classes and labels.shape[0] == B and labels.shape[2] == 5
+    max_gt = labels.shape[1]
+    dev = pred.device
+    xs = x_shifts.reshape(-1).contiguous().float(); ys = y_shifts.reshape(-1).contiguous().float()
+    st = strides.reshape(-1).contiguous().float()
+    assert xs.numel() == A and ys.numel() == A and st.numel() == A
+    out = {
+        "fg_mask": torch.empty((B, A), dtype=torch.uint8, device=dev),
+        "matched_gt": torch.empty((B, A), dtype=torch.int32, device=dev),
+        "matched_iou": torch.empty((B, A), dtype=torch.float32, device=dev),
+        "matched_cls": torch.empty((B, A), dtype=torch.int32, device=dev),
+        "num_fg": torch.empty((B,), dtype=torch.int32, device=dev),
+        "num_gt": torch.empty((B,), dtype=torch.int32, device=dev),
+    }
+    ws = _workspace(dev, lib().yx_simota_workspace_bytes(B, A, max_gt), "simota")
+    check(lib().yx_simota_assign(pred.data_ptr(), labels.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), B, A,
+                                 num_classes, max_gt, out["fg_mask"].data_ptr(), out["matched_gt"].data_ptr(),
+                                 out["matched_iou"].data_ptr(), out["matched_cls"].data_ptr(), out["num_fg"].data_ptr(),
+                                 out["num_gt"].data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "simota_assign")
+    return out
+
+
+def simota_matching_device(cost: torch.Tensor, ious: torch.Tensor):
+    """simota_matching on a [G, n] cost / IoU pair. Returns (match_gt [n] int32, match_iou [n], num_fg [1])."""
+    require_cuda(cost, "simota_matching")
+    cost = cost.contiguous().float(); ious = ious.contiguous().float()
+    G, n = cost.shape
+    dev = cost.device
+    mg = torch.empty((n,), dtype=torch.int32, device=dev)
+    mi = torch.empty((n,), dtype=torch.float32, device=dev)
+    nf = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib().yx_simota_matching(cost.data_ptr(), ious.data_ptr(), G, n, n, mg.data_ptr(), mi.data_ptr(),
+                                   nf.data_ptr(), stream_ptr(dev)), "simota_matching")
+    return mg, mi, nf

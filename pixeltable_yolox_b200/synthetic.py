@@ -1,0 +1,123 @@
+"""Seeded synthetic inputs (there is no dataset offline): structured images, decoded head tensors
+for the NMS stress case, labels and SimOTA cost matrices. numpy PCG64 only, so the
+same seed gives the same bytes on every box. Used by bench.py, the tests and the oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def images(batch: int, h: int, w: int, seed: int = 7) -> np.ndarray:
+    """[B,3,H,W] float32 with integer values 0..255 (exactly representable in bf16/fp16): random
+    colour rectangles over smooth gradients plus pixel noise, so that features vary at every
+    pyramid level (white noise collapses to a constant after a few stride-2 stages)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, h, dtype=np.float32), np.linspace(0, 1, w, dtype=np.float32), indexing="ij")
+    out = np.empty((batch, 3, h, w), dtype=np.float32)
+    for b in range(batch):
+        img = np.empty((3, h, w), dtype=np.float32)
+        for c in range(3):
+            fx, fy, ph = rng.uniform(0.5, 3.0), rng.uniform(0.5, 3.0), rng.uniform(0, 6.28)
+            img[c] = 128 + 90 * np.sin(6.28 * (fx * xx + fy * yy) + ph)
+        for _ in range(int(rng.integers(6, 16))):
+            x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+            bw, bh = int(rng.integers(max(4, w // 16), max(8, w // 2))), int(rng.integers(max(4, h // 16), max(8, h // 2)))
+            col = rng.uniform(0, 255, size=(3, 1, 1)).astype(np.float32)
+            img[:, y0:y0 + bh, x0:x0 + bw] = col
+        img += rng.normal(0, 12, size=img.shape).astype(np.float32)
+        out[b] = np.floor(np.clip(img, 0, 255))
+    return out
+
+
+def dense_scene(batch: int, anchors: int = 8400, nc: int = 80, seed: int = 11, clusters: int = 60,
+                size: float = 640.0) -> np.ndarray:
+    """Decoded head tensor [B, A, 5+nc] fp32 for the NMS stress case: boxes
+    jittered around `clusters` centres, obj~U(0.1,1), one dominant class per cluster."""
+    out = np.empty((batch, anchors, 5 + nc), dtype=np.float32)
+    for b in range(batch):
+        rng = np.random.default_rng(seed * 1000 + b)
+        centres = rng.uniform(40, size - 40, size=(clusters, 2))
+        which = rng.integers(0, clusters, size=anchors)
+        xy = centres[which] + rng.normal(0, 6, size=(anchors, 2))
+        wh = np.exp(rng.normal(0, 0.15, size=(anchors, 2))) * np.array([120.0, 90.0])
+        obj = rng.uniform(0.1, 1.0, size=(anchors, 1))
+        cls = rng.uniform(0, 0.3, size=(anchors, nc))
+        cls[np.arange(anchors), which % nc] = rng.uniform(0.5, 1.0, size=anchors)
+        out[b] = np.concatenate([xy, wh, obj, cls], axis=1).astype(np.float32)
+    return out
+
+
+def sparse_scene(batch: int, anchors: int, nc: int = 80, seed: int = 5, objects: int = 12,
+                 size: float = 640.0) -> np.ndarray:
+    """Mostly-background head tensor with a few strong, overlapping detections per object."""
+    out = np.empty((batch, anchors, 5 + nc), dtype=np.float32)
+    for b in range(batch):
+        rng = np.random.default_rng(seed * 1000 + b)
+        xy = rng.uniform(0, size, size=(anchors, 2)); wh = rng.uniform(8, 64, size=(anchors, 2))
+        obj = rng.uniform(0.0, 0.05, size=(anchors, 1)); cls = rng.uniform(0, 0.2, size=(anchors, nc))
+        n_obj = int(rng.integers(0, objects + 1))
+        for o in range(n_obj):
+            k = int(rng.integers(3, 12))
+            idx = rng.integers(0, anchors, size=k)
+            c = rng.uniform(60, size - 60, size=2); s = rng.uniform(40, 200, size=2)
+            xy[idx] = c + rng.normal(0, 3, size=(k, 2)); wh[idx] = s * np.exp(rng.normal(0, 0.05, size=(k, 2)))
+            obj[idx, 0] = rng.uniform(0.6, 1.0, size=k)
+            cls[idx, int(rng.integers(0, nc))] = rng.uniform(0.6, 1.0, size=k)
+        out[b] = np.concatenate([xy, wh, obj, cls], axis=1).astype(np.float32)
+    return out
+
+
+def labels(batch: int, max_gt: int = 120, nc: int = 80, seed: int = 3, size: float = 640.0,
+           counts=None) -> np.ndarray:
+    """[B, max_gt, 5] (cls, cx, cy, w, h), zero padded. Centres stay >= 40 px inside the image so that
+    every GT has in-centre anchors on all levels (SURVEY 8a row 13 parity hazard (i))."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, max_gt, 5), dtype=np.float32)
+    for b in range(batch):
+        g = int(rng.integers(0, 50)) if counts is None else int(counts[b])
+        g = min(g, max_gt)
+        out[b, :g, 0] = rng.integers(0, nc, size=g)
+        out[b, :g, 1:3] = rng.uniform(40, size - 40, size=(g, 2))
+        out[b, :g, 3:5] = rng.uniform(8, 208, size=(g, 2))
+    return out
+
+
+def train_head_output(batch: int, hw, strides, lab: np.ndarray, nc: int = 80, seed: int = 9) -> np.ndarray:
+    """Training-branch head tensor [B, A, 5+nc]: decoded boxes, raw obj/cls logits. Anchors near a GT
+    centre predict that GT's box with jitter so that dynamic_k spans 1..10."""
+    rng = np.random.default_rng(seed)
+    xs, ys, st = [], [], []
+    for (h, w), s in zip(hw, strides):
+        yv, xv = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        xs.append(xv.reshape(-1)); ys.append(yv.reshape(-1)); st.append(np.full(h * w, s))
+    xs, ys, st = (np.concatenate(v).astype(np.float32) for v in (xs, ys, st))
+    A = xs.size
+    out = np.empty((batch, A, 5 + nc), dtype=np.float32)
+    for b in range(batch):
+        cx = (xs + 0.5) * st + rng.normal(0, 4, size=A); cy = (ys + 0.5) * st + rng.normal(0, 4, size=A)
+        wh = np.exp(rng.normal(0, 0.5, size=(A, 2))) * st[:, None] * 4
+        box = np.stack([cx, cy, wh[:, 0], wh[:, 1]], 1)
+        logits = rng.normal(-3.0, 1.5, size=(A, 1 + nc))
+        gts = lab[b][lab[b].sum(1) > 0]
+        for g in gts:
+            d = np.abs((xs + 0.5) * st - g[1]) / st + np.abs((ys + 0.5) * st - g[2]) / st
+            near = np.where(d < 2.5)[0]
+            near = near[rng.random(near.size) < 0.7]
+            box[near] = g[1:5] * np.exp(rng.normal(0, 0.08, size=(near.size, 4)))
+            logits[near, 0] = rng.normal(1.0, 1.0, size=near.size)
+            logits[near, 1 + int(g[0])] = rng.normal(1.5, 1.0, size=near.size)
+        out[b] = np.concatenate([box, logits], 1).astype(np.float32)
+    return out
+
+
+def simota_case(num_gt: int, seed: int = 21):
+    """Synthetic cost / IoU matrices [G, 27*G] (SURVEY 8d config 4 direct matcher test)."""
+    rng = np.random.default_rng(seed)
+    n = 27 * num_gt
+    ious = rng.beta(2, 5, size=(num_gt, n)).astype(np.float32) * 0.6
+    for g in range(num_gt):
+        k = int(rng.integers(0, 14))
+        ious[g, rng.integers(0, n, size=k)] = rng.uniform(0.7, 0.99, size=k)
+    geom = rng.random((num_gt, n)) < 0.4
+    cost = (rng.uniform(0.5, 8.0, size=(num_gt, n)) + 3.0 * -np.log(ious + 1e-8)).astype(np.float32)
+    cost = (cost + np.float32(1e6) * (~geom)).astype(np.float32)
+    return cost, ious

@@ -1,0 +1,230 @@
+"""Decoupled YOLOX head with the reference's interface (yolox/models/yolo_head.py:17-574).
+
+eval  : lowered onto the B200 plan; the three prediction convs of a level are one implicit GEMM
+        with block-diagonal weights whose epilogue applies sigmoid/decode and writes the final
+        fp32 [B, A, 5+nc] tensor directly (yolo_head.py:185-187, 203-211, 233-251).
+train : the network runs through PyTorch autograd; the SimOTA assignment of the whole batch is a
+        single launch of the sm_100a kernel (no per-image Python loop, no host sync), and the
+        losses are assembled from its dense per-anchor outputs (yolo_head.py:253-411).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .losses import IouLoss
+from .network_blocks import BaseConv, DWConv, _B200Block, act_name
+
+
+class YoloxHead(_B200Block):
+    def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
+                 depthwise=False):
+        super().__init__()
+        self.num_classes = num_classes
+        self.decode_in_inference = True  # for deploy, set to False
+        self.cls_convs = nn.ModuleList()
+        self.reg_convs = nn.ModuleList()
+        self.cls_preds = nn.ModuleList()
+        self.reg_preds = nn.ModuleList()
+        self.obj_preds = nn.ModuleList()
+        self.stems = nn.ModuleList()
+        Conv = DWConv if depthwise else BaseConv
+        hid = int(256 * width)
+        for cin in in_channels:
+            self.stems.append(BaseConv(int(cin * width), hid, ksize=1, stride=1, act=act))
+            self.cls_convs.append(nn.Sequential(Conv(hid, hid, 3, 1, act=act), Conv(hid, hid, 3, 1, act=act)))
+            self.reg_convs.append(nn.Sequential(Conv(hid, hid, 3, 1, act=act), Conv(hid, hid, 3, 1, act=act)))
+            self.cls_preds.append(nn.Conv2d(hid, self.num_classes, 1, 1, 0))
+            self.reg_preds.append(nn.Conv2d(hid, 4, 1, 1, 0))
+            self.obj_preds.append(nn.Conv2d(hid, 1, 1, 1, 0))
+        self.use_l1 = False
+        self.l1_loss = nn.L1Loss(reduction="none")
+        self.bcewithlog_loss = nn.BCEWithLogitsLoss(reduction="none")
+        self.iou_loss = IouLoss(reduction="none")
+        self.strides = strides
+        self.grids = [torch.zeros(1)] * len(in_channels)
+        self.hw = None
+        # "auto" follows torchvision.ops.batched_nms on CUDA; see boxes.postprocess
+        self.output_dtype = None
+
+    def initialize_biases(self, prior_prob):
+        # yolo_head.py:129-138
+        v = -math.log((1 - prior_prob) / prior_prob)
+        for conv in list(self.cls_preds) + list(self.obj_preds):
+            conv.bias = nn.Parameter(torch.full_like(conv.bias.data, v), requires_grad=True)
+
+    # ------------------------------------------------------------------ eval lowering
+    def decode_flags(self) -> int:
+        return 3 if self.decode_in_inference else 2
+
+    def lower(self, b, feats, head_out, decode=None):
+        """feats: 3 Feats (strides 8/16/32); head_out: fp32 tensor [B, A, 5+nc]."""
+        decode = self.decode_flags() if decode is None else decode
+        hw = []
+        off = 0
+        total = sum(f.H * f.W for f in feats)
+        assert head_out.shape[1] == total and head_out.shape[2] == 5 + self.num_classes
+        for k, x in enumerate(feats):
+            stem = self.stems[k].lower(b, x)
+            hid = stem.c_real
+            c0, c1 = self.cls_convs[k][0], self.cls_convs[k][1]
+            r0, r1 = self.reg_convs[k][0], self.reg_convs[k][1]
+            if isinstance(c0, BaseConv):
+                # first tower convs share their input -> one 3x3 GEMM with N = 2*hid
+                t0 = b.conv(stem, [b.part(c0), b.part(r0)], act=act_name(c0.act), ksize=3, stride=1)
+                t1 = b.new_feat(stem.B, stem.H, stem.W, [hid, hid])
+                c1.lower(b, t0.seg(0), out=t1.seg(0))
+                r1.lower(b, t0.seg(1), out=t1.seg(1))
+            else:
+                t1 = b.new_feat(stem.B, stem.H, stem.W, [hid, hid])
+                c1.lower(b, c0.lower(b, stem), out=t1.seg(0))
+                r1.lower(b, r0.lower(b, stem), out=t1.seg(1))
+            # [reg(4) | obj(1) | cls(nc)] rows; reg/obj read the reg tower (segment 1), cls segment 0
+            parts = [
+                b.part(self.reg_preds[k], o_off=0, in_segs=[1]),
+                b.part(self.obj_preds[k], o_off=4, in_segs=[1]),
+                b.part(self.cls_preds[k], o_off=5, in_segs=[0]),
+            ]
+            b.conv(t1, parts, act=None, ksize=1, stride=1, o_total=5 + self.num_classes,
+                   head=dict(out=head_out, anchors=total, anchor_off=off, nc=self.num_classes, decode=decode,
+                             stride=self.strides[k]))
+            hw.append((x.H, x.W))
+            off += x.H * x.W
+        self.hw = [torch.Size(v) for v in hw]
+        return head_out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, xin, labels=None, imgs=None):
+        if not self.training:
+            from .engine import run_head
+
+            return run_head(self, xin)
+        outputs, origin_preds, x_shifts, y_shifts, expanded_strides = [], [], [], [], []
+        for k, x in enumerate(xin):
+            x = self.stems[k]._train_forward(x)
+            cls_feat = x
+            for blk in self.cls_convs[k]:
+                cls_feat = blk._train_forward(cls_feat)
+            reg_feat = x
+            for blk in self.reg_convs[k]:
+                reg_feat = blk._train_forward(reg_feat)
+            cls_output = self.cls_preds[k](cls_feat)
+            reg_output = self.reg_preds[k](reg_feat)
+            obj_output = self.obj_preds[k](reg_feat)
+            output = torch.cat([reg_output, obj_output, cls_output], 1)
+            output, grid = self.get_output_and_grid(output, k, self.strides[k], xin[0].type())
+            x_shifts.append(grid[:, :, 0])
+            y_shifts.append(grid[:, :, 1])
+            expanded_strides.append(torch.zeros(1, grid.shape[1]).fill_(self.strides[k]).type_as(xin[0]))
+            if self.use_l1:
+                bsz, _, hs, ws = reg_output.shape
+                origin_preds.append(reg_output.view(bsz, 1, 4, hs, ws).permute(0, 1, 3, 4, 2).reshape(bsz, -1, 4).clone())
+            outputs.append(output)
+        return self.get_losses(imgs, x_shifts, y_shifts, expanded_strides, labels, torch.cat(outputs, 1),
+                               origin_preds, dtype=xin[0].dtype)
+
+    def get_output_and_grid(self, output, k, stride, dtype):
+        # yolo_head.py:213-231
+        grid = self.grids[k]
+        batch_size = output.shape[0]
+        n_ch = 5 + self.num_classes
+        hsize, wsize = output.shape[-2:]
+        if grid.shape[2:4] != output.shape[2:4]:
+            yv, xv = torch.meshgrid([torch.arange(hsize), torch.arange(wsize)], indexing="ij")
+            grid = torch.stack((xv, yv), 2).view(1, 1, hsize, wsize, 2).type(dtype)
+            self.grids[k] = grid
+        output = output.view(batch_size, 1, n_ch, hsize, wsize).permute(0, 1, 3, 4, 2).reshape(batch_size, hsize * wsize, -1)
+        grid = grid.view(1, -1, 2)
+        xy = (output[..., :2] + grid) * stride
+        wh = torch.exp(output[..., 2:4]) * stride
+        return torch.cat([xy, wh, output[..., 4:]], dim=-1), grid
+
+    def decode_outputs(self, outputs, dtype=None):
+        """yolo_head.py:233-251 as one in-place kernel (grids are never materialised)."""
+        ops.require_cuda(outputs, "decode_outputs")
+        out = outputs.float().contiguous()
+        if out.data_ptr() == outputs.data_ptr():
+            out = out.clone()
+        ops.head_decode_(out, [tuple(hw) for hw in self.hw], self.strides)
+        return out if outputs.dtype == torch.float32 else out.to(outputs.dtype)
+
+    # ------------------------------------------------------------------ training: losses
+    def get_losses(self, imgs, x_shifts, y_shifts, expanded_strides, labels, outputs, origin_preds, dtype):
+        bbox_preds = outputs[:, :, :4]
+        obj_preds = outputs[:, :, 4:5]
+        cls_preds = outputs[:, :, 5:]
+        x_shifts = torch.cat(x_shifts, 1)
+        y_shifts = torch.cat(y_shifts, 1)
+        expanded_strides = torch.cat(expanded_strides, 1)
+        if self.use_l1:
+            origin_preds = torch.cat(origin_preds, 1)
+        B, A = outputs.shape[:2]
+
+        with torch.no_grad():
+            asg = ops.simota_assign(outputs.detach(), labels, x_shifts, y_shifts, expanded_strides, self.num_classes)
+        fg = asg["fg_mask"].bool()                               # [B, A]
+        num_fg = asg["num_fg"].sum().clamp(min=1).to(outputs.dtype)
+        num_gts = asg["num_gt"].sum().clamp(min=1).to(outputs.dtype)
+        b_idx, a_idx = fg.nonzero(as_tuple=True)                 # image-major, anchor order (yolo_head.py:368-378)
+        g_idx = asg["matched_gt"][b_idx, a_idx].long()
+        reg_targets = labels[b_idx, g_idx, 1:5].to(outputs.dtype)
+        cls_targets = F.one_hot(asg["matched_cls"][b_idx, a_idx].long(), self.num_classes).to(outputs.dtype) \
+            * asg["matched_iou"][b_idx, a_idx].unsqueeze(-1).to(outputs.dtype)
+        obj_targets = fg.reshape(-1, 1).to(dtype)
+
+        loss_iou = self.iou_loss(bbox_preds.reshape(-1, 4)[fg.reshape(-1)], reg_targets).sum() / num_fg
+        loss_obj = self.bcewithlog_loss(obj_preds.reshape(-1, 1), obj_targets).sum() / num_fg
+        loss_cls = self.bcewithlog_loss(cls_preds.reshape(-1, self.num_classes)[fg.reshape(-1)], cls_targets).sum() / num_fg
+        if self.use_l1:
+            l1_targets = self.get_l1_target(outputs.new_zeros((b_idx.numel(), 4)), reg_targets,
+                                            expanded_strides[0][a_idx], x_shifts[0][a_idx], y_shifts[0][a_idx])
+            loss_l1 = self.l1_loss(origin_preds.reshape(-1, 4)[fg.reshape(-1)], l1_targets).sum() / num_fg
+        else:
+            loss_l1 = 0.0
+        reg_weight = 5.0
+        loss = reg_weight * loss_iou + loss_obj + loss_cls + loss_l1
+        return (loss, reg_weight * loss_iou, loss_obj, loss_cls, loss_l1, num_fg / num_gts)
+
+    def get_l1_target(self, l1_target, gt, stride, x_shifts, y_shifts, eps=1e-8):
+        l1_target[:, 0] = gt[:, 0] / stride - x_shifts
+        l1_target[:, 1] = gt[:, 1] / stride - y_shifts
+        l1_target[:, 2] = torch.log(gt[:, 2] / stride + eps)
+        l1_target[:, 3] = torch.log(gt[:, 3] / stride + eps)
+        return l1_target
+
+    # ------------------------------------------------------------------ reference-shaped SimOTA API
+    @torch.no_grad()
+    def get_assignments(self, batch_idx, num_gt, gt_bboxes_per_image, gt_classes, bboxes_preds_per_image,
+                        expanded_strides, x_shifts, y_shifts, cls_preds, obj_preds, mode="gpu"):
+        """Same arguments and return tuple as yolo_head.py:420-509, computed by one kernel launch.
+        ``mode="cpu"`` (the reference's OOM escape hatch) is rejected: the kernel never
+        materialises the [G, A', nc] tensor that made it necessary."""
+        if mode != "gpu":
+            raise RuntimeError("get_assignments(mode='cpu') is not available: the B200 path has no CPU fallback")
+        A = bboxes_preds_per_image.shape[0]
+        pred = torch.cat([bboxes_preds_per_image.float(), obj_preds[batch_idx].float().reshape(A, 1),
+                          cls_preds[batch_idx].float()], dim=1).unsqueeze(0)
+        labels = torch.cat([gt_classes.float().reshape(-1, 1), gt_bboxes_per_image.float()], dim=1)[:num_gt]
+        pad = max(num_gt, 1)
+        lab = torch.zeros((1, pad, 5), dtype=torch.float32, device=pred.device)
+        lab[0, :num_gt] = labels
+        asg = ops.simota_assign(pred, lab, x_shifts, y_shifts, expanded_strides, self.num_classes)
+        fg_mask = asg["fg_mask"][0].bool()
+        matched_gt_inds = asg["matched_gt"][0][fg_mask].long()
+        gt_matched_classes = gt_classes[matched_gt_inds]
+        pred_ious = asg["matched_iou"][0][fg_mask]
+        return gt_matched_classes, fg_mask, pred_ious, matched_gt_inds, int(asg["num_fg"][0].item())
+
+    def simota_matching(self, cost, pair_wise_ious, gt_classes, num_gt, fg_mask):
+        """yolo_head.py:542-574 (mutates fg_mask in place like the reference)."""
+        mg, mi, nf = ops.simota_matching_device(cost[:num_gt], pair_wise_ious[:num_gt])
+        fg_inboxes = mg >= 0
+        num_fg = int(nf.item())
+        fg_mask[fg_mask.clone()] = fg_inboxes
+        matched_gt_inds = mg[fg_inboxes].long()
+        gt_matched_classes = gt_classes[matched_gt_inds]
+        return num_fg, gt_matched_classes, mi[fg_inboxes], matched_gt_inds

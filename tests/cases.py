@@ -1,0 +1,58 @@
+"""Seeded test cases shared by tests/golden/make_golden.py (which runs the reference on them in the
+build container) and by the tests (which run the oracle and the CUDA path on them)."""
+from __future__ import annotations
+
+import numpy as np
+
+from pixeltable_yolox_b200 import synthetic as syn
+
+# name -> (generator, kwargs, conf_thre, nms_thre)
+POST_CASES = {
+    "dense_a2100_t001": (syn.dense_scene, dict(batch=2, anchors=2100, seed=11, clusters=25, size=320.0), 0.001, 0.65),
+    "dense_a2100_t25": (syn.dense_scene, dict(batch=2, anchors=2100, seed=12, clusters=25, size=320.0), 0.25, 0.65),
+    "dense_a8400_t001": (syn.dense_scene, dict(batch=2, anchors=8400, seed=13), 0.001, 0.65),
+    "dense_a8400_t5": (syn.dense_scene, dict(batch=3, anchors=8400, seed=14), 0.5, 0.65),
+    "dense_a8400_nms45": (syn.dense_scene, dict(batch=2, anchors=8400, seed=15), 0.3, 0.45),
+    "sparse_a8400": (syn.sparse_scene, dict(batch=6, anchors=8400, seed=5), 0.5, 0.65),
+    "sparse_a3549": (syn.sparse_scene, dict(batch=4, anchors=3549, seed=6, size=416.0), 0.25, 0.65),
+    "sparse_small": (syn.sparse_scene, dict(batch=3, anchors=300, seed=7, objects=4, size=160.0), 0.3, 0.65),
+    "empty": (syn.sparse_scene, dict(batch=2, anchors=500, seed=8, objects=0), 0.9, 0.65),
+}
+
+SIMOTA_MATCH_CASES = {"g1": (1, 21), "g3": (3, 22), "g17": (17, 23), "g50": (50, 24), "g120": (120, 25)}
+
+# get_assignments end to end: (image size, label counts per image, seed)
+SIMOTA_ASSIGN_CASES = {
+    "s640": dict(size=640, counts=[0, 1, 7, 23, 50, 120], seed=31),
+    "s416": dict(size=416, counts=[3, 12], seed=32),
+}
+STRIDES = (8, 16, 32)
+
+
+def post_case(name):
+    gen, kw, conf, nms = POST_CASES[name]
+    return gen(**kw), conf, nms
+
+
+def assign_case(name):
+    c = SIMOTA_ASSIGN_CASES[name]
+    size = c["size"]
+    hw = [(size // s, size // s) for s in STRIDES]
+    lab = syn.labels(len(c["counts"]), max_gt=120, seed=c["seed"], size=float(size), counts=c["counts"])
+    pred = syn.train_head_output(len(c["counts"]), hw, STRIDES, lab, seed=c["seed"] + 1)
+    return pred, lab, hw
+
+
+# small networks for the forward golden: (depth, width, depthwise, H, W, batch, seed)
+NET_CASES = {
+    "w25_d33_64": dict(depth=0.33, width=0.25, depthwise=False, h=64, w=64, batch=2, seed=0),
+    "w25_d33_dw_96": dict(depth=0.33, width=0.25, depthwise=True, h=96, w=64, batch=2, seed=1),
+    "w50_d33_96x128": dict(depth=0.33, width=0.50, depthwise=False, h=96, w=128, batch=1, seed=2),
+    "w375_d33_64": dict(depth=0.33, width=0.375, depthwise=False, h=64, w=64, batch=2, seed=3),
+}
+
+
+def checksum(a: np.ndarray) -> str:
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]

@@ -1,0 +1,149 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) and the
+torchvision build it calls on the seeded cases of tests/cases.py. Build-container only:
+    python tests/golden/make_golden.py
+The committed .npz files are what pins the oracle (tests/test_oracle_golden.py) and, through it,
+the CUDA path; the GPU box never sees /root/reference."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torchvision
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from golden._ref_shim import import_reference  # noqa: E402
+
+import cases  # noqa: E402
+from oracle import yolox_oracle as yo  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+ref = import_reference()
+torch.set_num_threads(8)
+
+
+def pack_list(prefix, arrays, out):
+    out[prefix + "_n"] = np.array([-1 if a is None else len(a) for a in arrays], dtype=np.int64)
+    for i, a in enumerate(arrays):
+        if a is not None:
+            out[f"{prefix}_{i}"] = np.asarray(a)
+
+
+def gen_postprocess():
+    from torchvision.ops import boxes as tvb
+
+    out = {"torchvision": np.array(torchvision.__version__), "torch": np.array(torch.__version__)}
+    for name in cases.POST_CASES:
+        pred, conf, nms = cases.post_case(name)
+        out[f"{name}/in_sha"] = np.array(cases.checksum(pred))
+        # (1) the reference's own postprocess on CPU (torchvision picks the variant by candidate count)
+        t = torch.from_numpy(pred.copy())
+        res = ref["boxes"].postprocess(t, 80, conf, nms, class_agnostic=False)
+        pack_list(f"{name}/ref_dets", [None if r is None else r.numpy() for r in res], out)
+        out[f"{name}/xyxy_sha"] = np.array(cases.checksum(t[:, :, :4].numpy()))
+        res_ag = ref["boxes"].postprocess(torch.from_numpy(pred.copy()), 80, conf, nms, class_agnostic=True)
+        pack_list(f"{name}/ref_agnostic", [None if r is None else r.numpy() for r in res_ag], out)
+        # (2) both torchvision variants explicitly, as kept ANCHOR indices
+        t = torch.from_numpy(pred.copy())
+        box = torch.stack([t[..., 0] - t[..., 2] / 2, t[..., 1] - t[..., 3] / 2, t[..., 0] + t[..., 2] / 2,
+                           t[..., 1] + t[..., 3] / 2], -1)
+        for variant, fn in (("offset", tvb._batched_nms_coordinate_trick), ("per_class", tvb._batched_nms_vanilla)):
+            kept = []
+            for b in range(t.shape[0]):
+                conf_c, cls_c = torch.max(t[b, :, 5:85], 1)
+                score = t[b, :, 4] * conf_c
+                m = score >= conf
+                idx = torch.nonzero(m).flatten()
+                if idx.numel() == 0:
+                    kept.append(None)
+                    continue
+                k = fn(box[b][idx], score[idx], cls_c[idx].float(), nms)
+                kept.append(idx[k].numpy())
+            pack_list(f"{name}/{variant}_idx", kept, out)
+    np.savez_compressed(OUT / "postprocess.npz", **out)
+    print("postprocess.npz", len(out))
+
+
+def gen_simota():
+    out = {}
+    head = ref["YoloxHead"](80)
+    for name, (g, seed) in cases.SIMOTA_MATCH_CASES.items():
+        from pixeltable_yolox_b200.synthetic import simota_case
+
+        cost, ious = simota_case(g, seed)
+        n = cost.shape[1]
+        fg_mask = torch.ones(n, dtype=torch.bool)
+        num_fg, cls, pious, minds = head.simota_matching(torch.from_numpy(cost), torch.from_numpy(ious),
+                                                         torch.arange(g).float(), g, fg_mask)
+        out[f"{name}/in_sha"] = np.array(cases.checksum(cost) + cases.checksum(ious))
+        out[f"{name}/fg"] = fg_mask.numpy()
+        out[f"{name}/matched"] = minds.numpy()
+        out[f"{name}/ious"] = pious.numpy()
+        out[f"{name}/num_fg"] = np.array(num_fg)
+    for name in cases.SIMOTA_ASSIGN_CASES:
+        pred, lab, hw = cases.assign_case(name)
+        from oracle.simota_oracle import anchor_grid
+
+        xs, ys, st = anchor_grid(hw, cases.STRIDES)
+        out[f"{name}/in_sha"] = np.array(cases.checksum(pred) + cases.checksum(lab))
+        tp = torch.from_numpy(pred)
+        for b in range(pred.shape[0]):
+            gts = lab[b][lab[b].sum(1) > 0]
+            G = len(gts)
+            if G == 0:
+                continue
+            r = head.get_assignments(b, G, torch.from_numpy(gts[:, 1:5]), torch.from_numpy(gts[:, 0]), tp[b, :, :4],
+                                     torch.from_numpy(st)[None], torch.from_numpy(xs)[None], torch.from_numpy(ys)[None],
+                                     tp[:, :, 5:], tp[:, :, 4:5])
+            gcls, fg, pious, minds, num_fg = r
+            out[f"{name}/{b}/fg"] = fg.numpy()
+            out[f"{name}/{b}/matched"] = minds.numpy()
+            out[f"{name}/{b}/ious"] = pious.numpy()
+            out[f"{name}/{b}/cls"] = gcls.numpy()
+            out[f"{name}/{b}/num_fg"] = np.array(num_fg)
+    # bboxes_iou
+    rng = np.random.default_rng(77)
+    a = rng.uniform(0, 300, size=(40, 4)).astype(np.float32); b = rng.uniform(0, 300, size=(55, 4)).astype(np.float32)
+    a[:, 2:] += a[:, :2]; b[:, 2:] += b[:, :2]
+    out["iou/xyxy"] = ref["boxes"].bboxes_iou(torch.from_numpy(a), torch.from_numpy(b), True).numpy()
+    out["iou/cxcywh"] = ref["boxes"].bboxes_iou(torch.from_numpy(a), torch.from_numpy(b), False).numpy()
+    out["iou/a"], out["iou/b"] = a, b
+    np.savez_compressed(OUT / "simota.npz", **out)
+    print("simota.npz", len(out))
+
+
+def gen_network():
+    from pixeltable_yolox_b200.synthetic import images
+
+    out = {}
+    for name, c in cases.NET_CASES.items():
+        m = ref["YoloxModule"](
+            ref["YoloPafpn"](c["depth"], c["width"], depthwise=c["depthwise"]),
+            ref["YoloxHead"](80, c["width"], depthwise=c["depthwise"]))
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.eps = 1e-3
+        sd = yo.seeded_state_dict(m.state_dict(), c["seed"], (c["h"], c["w"]))
+        m.load_state_dict(sd)
+        m.eval()
+        x = torch.from_numpy(images(c["batch"], c["h"], c["w"], seed=c["seed"] + 500))
+        with torch.no_grad():
+            y = m(x)
+            feats = m.backbone(x)
+        out[f"{name}/out"] = y.numpy()
+        out[f"{name}/pan2_sha"] = np.array(cases.checksum(feats[0].numpy()))
+        out[f"{name}/keys"] = np.array(len(sd))
+        out[f"{name}/sd_sha"] = np.array(cases.checksum(np.concatenate([v.float().reshape(-1).numpy() for v in sd.values()])))
+        # training-branch head tensor (decoded boxes, raw logits) for the SimOTA path
+        m.head.decode_in_inference = False
+        with torch.no_grad():
+            out[f"{name}/undecoded"] = m(x).numpy()
+    np.savez_compressed(OUT / "network.npz", **out)
+    print("network.npz", len(out))
+
+
+if __name__ == "__main__":
+    gen_postprocess()
+    gen_simota()
+    gen_network()
