@@ -115,8 +115,8 @@ def decode_outputs(outputs, hw, strides):
         g = torch.stack((xv, yv), 2).view(1, -1, 2)
         grids.append(g)
         st.append(torch.full((1, g.shape[1], 1), s))
-    grids = torch.cat(grids, 1).to(outputs.dtype)
-    st = torch.cat(st, 1).to(outputs.dtype)
+    grids = torch.cat(grids, 1).to(outputs.dtype).to(outputs.device)
+    st = torch.cat(st, 1).to(outputs.dtype).to(outputs.device)
     return torch.cat([(outputs[..., 0:2] + grids) * st, torch.exp(outputs[..., 2:4]) * st, outputs[..., 4:]], -1)
 
 
@@ -135,7 +135,8 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, act: str = "silu", dec
 # statistics calibrated layer by layer on U[0,255] images so that activations neither die nor blow up.
 # ------------------------------------------------------------------------------------------------
 def seeded_state_dict(template: Dict[str, torch.Tensor], seed: int, image_hw: Tuple[int, int] = (64, 64),
-                      calib_batch: int = 8, act: str = "silu", big_boxes: bool = False) -> Dict[str, torch.Tensor]:
+                      calib_batch: int = 8, act: str = "silu", big_boxes: bool = False,
+                      calib_x: torch.Tensor = None) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for k, v in template.items():
@@ -166,7 +167,20 @@ def seeded_state_dict(template: Dict[str, torch.Tensor], seed: int, image_hw: Tu
     from pixeltable_yolox_b200.synthetic import images
 
     x = torch.from_numpy(images(calib_batch, image_hw[0], image_hw[1], seed=seed + 100))
+    if calib_x is not None:      # include the evaluation images: tiny maps give too few BN samples otherwise
+        x = torch.cat([calib_x.float(), x], 0)
     _calibrate(sd, x, ACTS[act])
+    # keep the raw box regressions in a sane range (|v| <= 2.5) so that exp(wh) stays well conditioned
+    with torch.no_grad():
+        a = ACTS[act]
+        raw, hw = head(sd, pafpn(sd, x, a), a, decode=False, sigmoid=False)
+        off = 0
+        for k, (h, w) in enumerate(hw):
+            m = raw[:, off:off + h * w, :4].abs().max().item()
+            off += h * w
+            if m > 2.5:
+                sd[f"head.reg_preds.{k}.weight"] = sd[f"head.reg_preds.{k}.weight"] * (2.5 / m)
+                sd[f"head.reg_preds.{k}.bias"] = sd[f"head.reg_preds.{k}.bias"] * (2.5 / m)
     return sd
 
 

@@ -112,6 +112,7 @@ struct yx_plan {
   std::vector<yx::Op> ops;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
   int launches = 0;
 };
 
@@ -288,6 +289,7 @@ void yx_plan_destroy(yx_plan* p) {
   if (!p) return;
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
   for (auto& o : p->ops)
     if (o.tc) conv_tc_free(o.tc);
   delete p;
@@ -398,17 +400,19 @@ int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph) {
       if (rc) return rc;
     }
     YX_CUDA(cudaStreamSynchronize(s));
-    YX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    if (!p->capture_stream) YX_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = p->capture_stream;
+    YX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     for (const auto& o : p->ops) {
-      rc = run_op(o, s);
+      rc = run_op(o, cs);
       if (rc) {
         cudaGraph_t g = nullptr;
-        cudaStreamEndCapture(s, &g);
+        cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);
         return rc;
       }
     }
-    YX_CUDA(cudaStreamEndCapture(s, &p->graph));
+    YX_CUDA(cudaStreamEndCapture(cs, &p->graph));
     YX_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
   }
   YX_CUDA(cudaGraphLaunch(p->exec, s));

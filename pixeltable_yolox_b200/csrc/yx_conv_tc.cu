@@ -46,6 +46,8 @@ struct ConvTcParams {
   unsigned desc_hi;      // upper 32 bits of the UMMA smem descriptor (SBO, version, layout)
   unsigned idesc;
   unsigned tmem_cols;
+  unsigned bias_bytes;   // shared-memory copy of the bias vector (out_c floats, rounded to 1 KB)
+  unsigned head_bytes;   // YX_EPI_HEAD: per-warp [32][5+nc] fp32 staging for coalesced row stores
   EpiParams epi;
 };
 
@@ -61,6 +63,69 @@ struct __align__(8) TcShared {
   uint32_t tmem_base;
 };
 
+
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// SiLU with one MUFU: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32: ~2^-11 relative,
+// below the bf16/fp16 output rounding)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// 16 accumulator columns of one pixel: bias (smem) + act (+ residual) -> 16-bit, one 32-byte store
+__device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
+                                             const uint32_t* res, bool fp16, uint16_t* dst, int b, int ho, int wo,
+                                             int c0) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+    v[j + 0] = __uint_as_float(raw[j + 0]) + bb.x;
+    v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
+    v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z;
+    v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
+  }
+  if (e.act == YX_ACT_SILU && !fp16) {
+    // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_tanh(v[j]);
+  } else if (e.act != YX_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_f<false>(v[j], e.act);
+  }
+  if (res) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a, c;
+      unpack16(res[j], fp16, a, c);
+      v[2 * j] += a; v[2 * j + 1] += c;
+    }
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = pack16(v[2 * j], v[2 * j + 1], fp16);
+  st_global_256(dst, w);
+  if (e.ups) {
+    const int uw = 2 * e.out_w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long up = ((long long)b * 2 * e.out_h + 2 * ho + (q >> 1)) * uw + 2 * wo + (q & 1);
+      st_global_256((uint16_t*)e.ups + up * e.ups_ld + c0, w);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
@@ -68,7 +133,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // operand tiles need 1024-byte alignment for the 128-byte swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcShared* sh = reinterpret_cast<TcShared*>(smem);
-  uint8_t* tiles = smem + 1024;
+  float* sbias = reinterpret_cast<float*>(smem + 1024);
+  float* shead = reinterpret_cast<float*>(smem + 1024 + p.bias_bytes);
+  uint8_t* tiles = smem + 1024 + p.bias_bytes + p.head_bytes;
+  // bias lives in shared memory: with ~200 KB of operand stages the L1 carve-out is ~0, so a
+  // global bias load in the epilogue would be an L2 round trip per 16 columns
+  for (int i = threadIdx.x; i < p.epi.out_c; i += kThreads) sbias[i] = p.epi.bias[i];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -197,15 +267,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&sh->tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t raw[16];
-        tmem_ld_x16(taddr + (uint32_t)c, raw);
+      const float* tbias = sbias + n_tile * p.BN;
+      if (p.epi.epilogue == YX_EPI_HEAD) {
+        // ---- head: decode/sigmoid in registers, stage the warp's 32 rows in shared memory, then
+        //      write each [5+nc] fp32 row with coalesced 128-byte stores
+        const int nch = 5 + p.epi.head_nc;
+        float* wstage = shead + (size_t)(warp - 2) * 32 * nch;
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t raw[16];
+          tmem_ld_x16(taddr + (uint32_t)c, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = c + j;
+            if (ch < nch) {
+              float x = __uint_as_float(raw[j]) + tbias[ch];
+              if (ch < 2) {
+                if (p.epi.head_decode & 1) x = (x + (ch == 0 ? (float)wo : (float)ho)) * p.epi.head_stride;
+              } else if (ch < 4) {
+                if (p.epi.head_decode & 1) x = expf(x) * p.epi.head_stride;
+              } else if (p.epi.head_decode & 2) {
+                x = 1.0f / (1.0f + expf(-x));
+              }
+              wstage[lane * nch + ch] = x;
+            }
+          }
+        }
+        // accumulators are in registers/smem now: hand the TMEM stage back before the slow stores
+        tc_fence_before();
+        mbar_arrive(&sh->tmem_empty[as]);
+        const long long arow = valid ? ((long long)b * p.epi.head_anchors + p.epi.head_anchor_off +
+                                        (long long)ho * p.epi.out_w + wo) : -1;
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+          const long long ar = __shfl_sync(0xffffffffu, arow, r);
+          if (ar < 0) continue;
+          float* dst = p.epi.head_out + ar * nch;
+          const float* src = wstage + r * nch;
+          for (int ch = lane; ch < nch; ch += 32) dst[ch] = src[ch];
+        }
+        __syncwarp();
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+        continue;
+      }
+      // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
+      //      wait, one 256-bit store per thread per 16 columns (a full 32-byte sector)
+      const bool fp16 = (p.epi.dtype == YX_FP16);
+      const long long pix = ((long long)b * p.epi.out_h + ho) * p.epi.out_w + wo;
+      uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld + n_tile * p.BN;
+      const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld + n_tile * p.BN : nullptr;
+      for (int c = 0; c < p.BN; c += 32) {
+        const bool two = (c + 16 < p.BN);
+        uint32_t ra[16], rb[16];
+        tmem_ld_x16(taddr + (uint32_t)c, ra);
+        if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
+        uint32_t qa[8], qb[8];
+        if (rrow && valid) {
+          ld_global_256(rrow + c, qa);
+          if (two) ld_global_256(rrow + c + 16, qb);
+        }
         tmem_ld_wait();
         if (valid) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          epi_store16<false>(p.epi, b, ho, wo, n_tile * p.BN + c, v);
+          epi_tc_chunk(p.epi, ra, tbias + c, rrow ? qa : nullptr, fp16, orow + c, b, ho, wo, n_tile * p.BN + c);
+          if (two)
+            epi_tc_chunk(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, fp16, orow + c + 16, b, ho, wo,
+                         n_tile * p.BN + c + 16);
         }
       }
       tc_fence_before();
@@ -310,6 +436,13 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   YX_REQUIRE(d->dtype == YX_BF16 || d->dtype == YX_FP16, YX_ERR_INVALID_ARG, "conv_tc: dtype must be bf16/fp16");
   YX_REQUIRE(d->in_ld % 8 == 0 && ((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->w & 15) == 0,
              YX_ERR_INVALID_ARG, "conv_tc: in/w must be 16-byte aligned, in_ld %% 8 == 0");
+  if (d->epilogue == YX_EPI_STORE) {
+    // the epilogue moves 16 channels (32 bytes) per instruction
+    YX_REQUIRE(d->out_ld % 16 == 0 && ((uintptr_t)d->out & 31) == 0, YX_ERR_INVALID_ARG,
+               "conv_tc: out must be 32-byte aligned with out_ld %% 16 == 0");
+    if (d->res) YX_REQUIRE(d->res_ld % 16 == 0 && ((uintptr_t)d->res & 31) == 0, YX_ERR_INVALID_ARG, "conv_tc: res must be 32-byte aligned");
+    if (d->ups) YX_REQUIRE(d->ups_ld % 16 == 0 && ((uintptr_t)d->ups & 31) == 0, YX_ERR_INVALID_ARG, "conv_tc: ups must be 32-byte aligned");
+  }
   ConvTcParams& p = L->p;
   memset(&p, 0, sizeof(p));
   rc = fill_epi_params(d, &p.epi);
@@ -365,12 +498,15 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   YX_CUDA(cudaGetDevice(&dev));
   YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_k = d->ksize * d->ksize * p.kchunks;
-  int stages = (int)((max_smem - 2048) / p.stage_bytes);
+  p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
+  p.head_bytes = d->epilogue == YX_EPI_HEAD ? ((4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
+  const unsigned fixed_bytes = 2048u + p.bias_bytes + p.head_bytes;
+  int stages = (int)((max_smem - (int)fixed_bytes) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   YX_REQUIRE(stages >= 2, YX_ERR_UNSUPPORTED, "conv_tc: stage of %u bytes does not fit shared memory", p.stage_bytes);
   (void)num_k;
   p.stages = stages;
-  L->smem = 2048 + (size_t)stages * p.stage_bytes;
+  L->smem = fixed_bytes + (size_t)stages * p.stage_bytes;
 
   // UMMA shared-memory descriptor, upper word: SBO = 8 rows * row_bytes, version 1, layout type
   const unsigned layout = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);  // SW128 / SW64 / SW32

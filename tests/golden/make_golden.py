@@ -124,10 +124,10 @@ def gen_network():
         for mod in m.modules():
             if isinstance(mod, torch.nn.BatchNorm2d):
                 mod.eps = 1e-3
-        sd = yo.seeded_state_dict(m.state_dict(), c["seed"], (c["h"], c["w"]))
+        x = torch.from_numpy(images(c["batch"], c["h"], c["w"], seed=c["seed"] + 500))
+        sd = yo.seeded_state_dict(m.state_dict(), c["seed"], (c["h"], c["w"]), calib_x=x)
         m.load_state_dict(sd)
         m.eval()
-        x = torch.from_numpy(images(c["batch"], c["h"], c["w"], seed=c["seed"] + 500))
         with torch.no_grad():
             y = m(x)
             feats = m.backbone(x)

@@ -1,0 +1,136 @@
+"""-m gpu: score filter + NMS through the C-ABI; kept rows must be BIT-EXACT against the committed
+reference goldens and the oracle (integer/index work and fp32 compares)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import unpack_list
+
+pytestmark = pytest.mark.gpu
+
+import pixeltable_yolox_b200 as yx  # noqa: E402
+from oracle import postprocess_oracle as po  # noqa: E402
+from pixeltable_yolox_b200 import ops  # noqa: E402
+from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
+
+
+def _check_lists(got, want):
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert (g is None) == (w is None), f"image {i}"
+        if g is not None:
+            np.testing.assert_array_equal(g.cpu().numpy(), w, err_msg=f"image {i}")
+
+
+@pytest.mark.parametrize("name", list(cases.POST_CASES))
+def test_postprocess_matches_reference_golden(cuda, name, golden_post):
+    pred, conf, nms = cases.post_case(name)
+    t = torch.from_numpy(pred).to(cuda)
+    got = yx.postprocess(t, 80, conf, nms, nms_variant="auto_cpu")       # the variant the CPU reference took
+    _check_lists(got, unpack_list(golden_post, f"{name}/ref_dets"))
+    assert cases.checksum(t[:, :, :4].cpu().numpy()) == str(golden_post[f"{name}/xyxy_sha"])   # in-place xyxy
+    got = yx.postprocess(torch.from_numpy(pred).to(cuda), 80, conf, nms, class_agnostic=True)
+    _check_lists(got, unpack_list(golden_post, f"{name}/ref_agnostic"))
+
+
+@pytest.mark.parametrize("name", list(cases.POST_CASES))
+@pytest.mark.parametrize("variant", ["offset", "per_class"])
+def test_nms_variants_kept_indices(cuda, name, variant, golden_post):
+    pred, conf, nms = cases.post_case(name)
+    t = torch.from_numpy(pred).to(cuda)
+    _, idx, cnt = ops.postprocess_device(t, 80, conf, nms, yx.boxes.NMS_VARIANTS[variant])
+    cnt = cnt.cpu().tolist()
+    for b, want in enumerate(unpack_list(golden_post, f"{name}/{variant}_idx")):
+        if want is None:
+            assert cnt[b] == 0
+        else:
+            np.testing.assert_array_equal(idx[b, :cnt[b]].cpu().numpy(), want)
+
+
+def test_auto_variant_follows_torchvision_cuda_rule(cuda):
+    pred = syn.dense_scene(2, anchors=8400, seed=41)
+    want, _ = po.postprocess(pred.copy(), 80, 0.3, 0.65, variant="offset", return_indices=True)
+    _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.3, 0.65), want)
+
+
+def test_large_anchor_count_takes_global_sort_path(cuda):
+    """A > 16384 candidates: keys no longer fit shared memory."""
+    pred = syn.dense_scene(1, anchors=20000, seed=42, clusters=150, size=1280.0)
+    for variant in ("offset", "per_class"):
+        want, _ = po.postprocess(pred.copy(), 80, 0.001, 0.65, variant=variant, return_indices=True)
+        _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.001, 0.65, nms_variant=variant), want)
+
+
+def test_ties_and_degenerate_boxes(cuda):
+    """identical scores (stable order), zero-area boxes (0/0 -> NaN -> kept), IoU exactly at threshold."""
+    A = 64
+    pred = np.zeros((1, A, 85), dtype=np.float32)
+    pred[0, :, 0:2] = 100.0
+    pred[0, :, 2:4] = 20.0
+    pred[0, :, 4] = 0.9
+    pred[0, :, 5] = 0.5                      # every score identical
+    pred[0, 10:20, 2:4] = 0.0                # zero-area boxes
+    pred[0, 30:40, 0] += np.arange(10, dtype=np.float32) * 7.0
+    pred[0, 40:, 5 + 3] = 0.8                # another class, higher score
+    for variant in ("offset", "per_class"):
+        want, _ = po.postprocess(pred.copy(), 80, 0.1, 0.5, variant=variant, return_indices=True)
+        _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.1, 0.5, nms_variant=variant), want)
+
+
+def test_empty_batch_and_no_candidates(cuda):
+    assert yx.postprocess(torch.zeros(0, 100, 85, device=cuda), 80) == []
+    out = yx.postprocess(torch.zeros(3, 100, 85, device=cuda), 80, 0.5, 0.65)
+    assert out == [None, None, None]
+
+
+def test_score_filter_compact_is_ordered(cuda):
+    pred = syn.dense_scene(2, anchors=3000, seed=43)
+    cand, idx, cnt = ops.score_filter_compact(torch.from_numpy(pred).to(cuda), 80, 0.3)
+    p = pred.copy()
+    cls = p[:, :, 5:]
+    for b in range(2):
+        conf = cls[b].max(1); lab = cls[b].argmax(1)
+        score = p[b, :, 4] * conf
+        keep = np.where(score >= np.float32(0.3))[0]
+        n = int(cnt[b])
+        assert n == len(keep)
+        np.testing.assert_array_equal(idx[b, :n].cpu().numpy(), keep)
+        got = cand[b, :n].cpu().numpy()
+        np.testing.assert_array_equal(got[:, 4], p[b, keep, 4]); np.testing.assert_array_equal(got[:, 5], conf[keep])
+        np.testing.assert_array_equal(got[:, 6], lab[keep].astype(np.float32)); np.testing.assert_array_equal(got[:, 7], score[keep])
+
+
+def test_batched_nms_standalone(cuda):
+    rng = np.random.default_rng(44)
+    B, n = 3, 700
+    boxes = rng.uniform(0, 200, size=(B, n, 4)).astype(np.float32); boxes[..., 2:] += boxes[..., :2]
+    scores = rng.uniform(0, 1, size=(B, n)).astype(np.float32)
+    cls = rng.integers(0, 5, size=(B, n)).astype(np.int32)
+    counts = np.array([700, 0, 333], dtype=np.int32)
+    for variant, name in ((0, "offset"), (1, "per_class")):
+        keep, kc = ops.batched_nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(scores).to(cuda),
+                                   torch.from_numpy(cls).to(cuda), torch.from_numpy(counts).to(cuda), 0.5, variant)
+        for b in range(B):
+            c = counts[b]
+            want = po.batched_nms(boxes[b, :c], scores[b, :c], cls[b, :c].astype(np.int64), 0.5, name) if c else np.empty(0, np.int64)
+            assert int(kc[b]) == len(want)
+            np.testing.assert_array_equal(keep[b, :len(want)].cpu().numpy(), want)
+
+
+def test_processor_postprocess_matches_oracle(cuda):
+    from PIL import Image
+
+    proc = yx.YoloxProcessor("yolox_s")
+    pred = syn.sparse_scene(2, anchors=8400, seed=45)
+    images = [Image.new("RGB", (640, 480)), Image.new("RGB", (480, 640))]
+    res = proc.postprocess(images, torch.from_numpy(pred).to(cuda), threshold=0.5)
+    want = po.postprocess(pred.copy(), 80, 0.5, 0.65, variant="offset")
+    for im, r, w in zip(images, res, want):
+        ratio = min(640 / im.height, 640 / im.width)
+        if w is None:
+            assert r["bboxes"] == []
+            continue
+        assert r["labels"] == [int(v) for v in w[:, 6]]
+        np.testing.assert_allclose(np.array(r["bboxes"], dtype=np.float32), w[:, :4] / np.float32(ratio), rtol=1e-6)
+        np.testing.assert_allclose(r["scores"], [float(a) * float(b) for a, b in zip(w[:, 4], w[:, 5])], rtol=0)

@@ -1,0 +1,93 @@
+"""-m gpu: SimOTA. simota_matching is bit-exact on a given cost/IoU matrix (reference goldens);
+the fused assignment is checked against the oracle/goldens with a near-tie allowance because its
+cost matrix is floating point."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+import pixeltable_yolox_b200 as yx  # noqa: E402
+from oracle import simota_oracle as so  # noqa: E402
+from pixeltable_yolox_b200 import ops  # noqa: E402
+from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(cases.SIMOTA_MATCH_CASES))
+def test_simota_matching_bit_exact(cuda, name, golden_simota):
+    g, seed = cases.SIMOTA_MATCH_CASES[name]
+    cost, ious = syn.simota_case(g, seed)
+    mg, mi, nf = ops.simota_matching_device(torch.from_numpy(cost).to(cuda), torch.from_numpy(ious).to(cuda))
+    mg, mi = mg.cpu().numpy(), mi.cpu().numpy()
+    fg = mg >= 0
+    np.testing.assert_array_equal(fg, golden_simota[f"{name}/fg"])
+    np.testing.assert_array_equal(mg[fg], golden_simota[f"{name}/matched"])
+    np.testing.assert_array_equal(mi[fg], golden_simota[f"{name}/ious"])
+    assert int(nf) == int(golden_simota[f"{name}/num_fg"])
+
+
+def test_simota_matching_head_api_mutates_fg_mask(cuda):
+    cost, ious = syn.simota_case(17, 23)
+    head = yx.YoloxHead(80)
+    n = cost.shape[1]
+    fg_mask = torch.ones(n + 5, dtype=torch.bool, device=cuda)
+    fg_mask[::(n + 5) // 5][:5] = False
+    assert int(fg_mask.sum()) == n
+    num_fg, cls, pious, minds = head.simota_matching(torch.from_numpy(cost).to(cuda), torch.from_numpy(ious).to(cuda),
+                                                     torch.arange(17, device=cuda).float(), 17, fg_mask)
+    want_mg, want_mi, want_nf = so.simota_matching(cost, ious)
+    assert num_fg == want_nf == int(fg_mask.sum())
+    np.testing.assert_array_equal(minds.cpu().numpy(), want_mg[want_mg >= 0])
+    np.testing.assert_array_equal(cls.cpu().numpy(), want_mg[want_mg >= 0].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", list(cases.SIMOTA_ASSIGN_CASES))
+def test_simota_assign_vs_reference(cuda, name, golden_simota):
+    pred, lab, hw = cases.assign_case(name)
+    xs, ys, st = so.anchor_grid(hw, cases.STRIDES)
+    out = ops.simota_assign(torch.from_numpy(pred).to(cuda), torch.from_numpy(lab).to(cuda), torch.from_numpy(xs).to(cuda),
+                            torch.from_numpy(ys).to(cuda), torch.from_numpy(st).to(cuda), 80)
+    fg_all = out["fg_mask"].cpu().numpy().astype(bool)
+    mgt_all = out["matched_gt"].cpu().numpy()
+    miou_all = out["matched_iou"].cpu().numpy()
+    for b in range(pred.shape[0]):
+        G = int((lab[b].sum(1) > 0).sum())
+        assert int(out["num_gt"][b]) == G
+        if G == 0:
+            assert not fg_all[b].any() and int(out["num_fg"][b]) == 0
+            continue
+        ref_fg = golden_simota[f"{name}/{b}/fg"]
+        theirs = np.full(ref_fg.shape, -1, dtype=np.int64); theirs[ref_fg] = golden_simota[f"{name}/{b}/matched"]
+        their_iou = np.zeros(ref_fg.shape, dtype=np.float32); their_iou[ref_fg] = golden_simota[f"{name}/{b}/ious"]
+        agree = (fg_all[b] == ref_fg).mean()
+        assert agree >= 0.999, (b, agree)
+        both = fg_all[b] & ref_fg
+        assert (mgt_all[b][both] == theirs[both]).mean() >= 0.995
+        same = both & (mgt_all[b] == theirs)
+        np.testing.assert_allclose(miou_all[b][same], their_iou[same], rtol=1e-5, atol=1e-6)
+        assert abs(int(out["num_fg"][b]) - int(golden_simota[f"{name}/{b}/num_fg"])) <= max(2, 0.01 * ref_fg.sum())
+        assert int(out["num_fg"][b]) == int(fg_all[b].sum())
+        # the oracle (same summation structure is not guaranteed either) must agree at least as well
+        o_fg, o_mgt, _, _ = so.get_assignments(pred[b], lab[b][:G], 80, st, xs, ys)
+        assert (o_fg == fg_all[b]).mean() >= 0.999
+
+
+def test_get_assignments_reference_signature(cuda):
+    pred, lab, hw = cases.assign_case("s416")
+    xs, ys, st = so.anchor_grid(hw, cases.STRIDES)
+    head = yx.YoloxHead(80)
+    tp = torch.from_numpy(pred).to(cuda)
+    b = 1
+    gts = lab[b][lab[b].sum(1) > 0]
+    G = len(gts)
+    r = head.get_assignments(b, G, torch.from_numpy(gts[:, 1:5]).to(cuda), torch.from_numpy(gts[:, 0]).to(cuda), tp[b, :, :4],
+                             torch.from_numpy(st)[None].to(cuda), torch.from_numpy(xs)[None].to(cuda),
+                             torch.from_numpy(ys)[None].to(cuda), tp[:, :, 5:], tp[:, :, 4:5])
+    gcls, fg, pious, minds, num_fg = r
+    assert fg.dtype == torch.bool and fg.shape == (pred.shape[1],)
+    assert num_fg == int(fg.sum()) == minds.numel() == pious.numel() == gcls.numel()
+    assert minds.dtype == torch.int64
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        head.get_assignments(b, G, None, None, None, None, None, None, None, None, mode="cpu")
