@@ -1,0 +1,344 @@
+"""bench.py — YOLOX-s 640^2 images/s (fwd + decode + NMS) on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (YoloxModule.forward eval + postprocess, i.e. focus -> convs ->
+head decode -> score filter -> NMS, one CUDA graph) over one batch of 64 synthetic 640x640 images
+per GPU (weak scaling: the batch is sharded by image, no data-path collective).
+  value     : whole-job images/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       : the same metric through the public API with HOST (pinned) fp32 images: H2D of the batch
+              and D2H of the detections inside the timed region, double-buffered over two streams
+  roofline  : the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs / its device
+              time, measured live with CUDA events around every launch of an eager pass
+  cpu_baseline / --impl reference : the CPU restatement of the reference path (oracle/, torch CPU ops +
+              numpy/C NMS) on the host cores, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GFLOP_PER_IMAGE = {"yolox_s": 26.686, "yolox_m": 73.530, "yolox_l": 155.293, "yolox_x": 281.410,
+                   "yolox_tiny": 6.413, "yolox_nano": 1.045}   # BASELINE.md section 2 (conv 2*MAC)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="yolox_s")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--conf", type=float, default=0.5)
+    ap.add_argument("--nms", type=float, default=0.65)
+    ap.add_argument("--max-det", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=16)
+    ap.add_argument("--profile-ops", action="store_true", help="print the per-op table of the eager pass")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_model(args, device):
+    import torch
+
+    import pixeltable_yolox_b200 as yx
+    from pixeltable_yolox_b200 import synthetic as syn
+
+    cfg = yx.YoloxConfig.get_named_config(args.model)
+    cfg.model = None
+    torch.manual_seed(0)
+    model = cfg.get_model().to(device)
+    calib = syn.images(4, args.size, args.size, seed=1234)
+    syn.randomize_and_calibrate(model, calib, seed=0)       # non-degenerate random-init weights
+    return cfg, model
+
+
+def cpu_reference_rate(args, sd, images_np, seconds_cap=25.0):
+    """The reference path restated on CPU (oracle/): torch CPU fp32 forward + numpy/C postprocess."""
+    import numpy as np
+    import torch
+
+    from oracle import postprocess_oracle as po
+    from oracle import yolox_oracle as yo
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    x = torch.from_numpy(images_np)
+    done, t_used = 0, 0.0
+    chunk = 4
+    yo.forward(sd, x[:1])   # warm-up (thread pool, allocator)
+    while done < x.shape[0] and t_used < seconds_cap:
+        t0 = time.perf_counter()
+        out = yo.forward(sd, x[done:done + chunk]).numpy()
+        po.postprocess(np.ascontiguousarray(out), 80, args.conf, args.nms, variant="auto_cpu")
+        t_used += time.perf_counter() - t0
+        done += min(chunk, x.shape[0] - done)
+    return done / t_used, threads, done
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pixeltable_yolox_b200 import synthetic as syn
+
+    _, model = build_model(args, torch.device("cpu"))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    per_step = max(1, min(args.cpu_images, 8))
+    imgs = syn.images(per_step, args.size, args.size, seed=7)
+    import numpy as np
+
+    from oracle import postprocess_oracle as po
+    from oracle import yolox_oracle as yo
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    x = torch.from_numpy(imgs)
+
+    def step():
+        out = yo.forward(sd, x).numpy()
+        po.postprocess(np.ascontiguousarray(out), 80, args.conf, args.nms, variant="auto_cpu")
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    steps = min(args.steps, 10)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = per_step * steps / dt
+    line = {
+        "metric": "images_per_second", "impl": "reference", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} {args.size}x{args.size} fwd+decode+NMS, CPU sample of {per_step} images/step",
+                   "conf_thre": args.conf, "nms_thre": args.nms},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps x {per_step} images, oracle/ torch-CPU fp32 forward + numpy/C NMS"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pixeltable_yolox_b200 import synthetic as syn
+    from pixeltable_yolox_b200.boxes import NMS_VARIANTS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    cfg, model = build_model(args, dev)
+    sd_cpu = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model = model.to(dtype).eval()
+    model.micro_batch = args.micro_batch
+    B, S = args.batch, args.size
+    # two distinct synthetic batches per rank, alternated, each 315 MB fp32 (> 126 MB L2)
+    host = [torch.from_numpy(syn.images(B, S, S, seed=7 + 100 * rank + i)).pin_memory() for i in range(2)]
+    dev_in = [h.to(dev) for h in host]
+    post = dict(conf_thre=args.conf, nms_thre=args.nms, nms_variant=NMS_VARIANTS["auto"], max_det=args.max_det)
+    eng = [model.engine_for(dev_in[0], post, slot=i) for i in range(2)]
+    launches_per_step = eng[0].launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM ----------------
+    for i in range(args.warmup):
+        eng[0].forward(dev_in[i % 2])
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng[0].forward(dev_in[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+    value = world * B * args.steps / (ms / 1e3)
+    kept = int(eng[0].det_count.clamp(max=args.max_det).sum().item())
+    kept_true_mean = float(eng[0].det_count.float().mean().item())
+    scores = eng[0].pred[..., 4] * eng[0].pred[..., 5:].max(-1).values
+    cand_mean = float((scores >= args.conf).float().sum(1).mean().item())
+
+    # ---------------- e2e: host buffers in, detections out, every step ----------------
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    out_host = [torch.empty((B, args.max_det, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
+    cnt_host = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def e2e_step(i):
+        s = i % 2
+        with torch.cuda.stream(streams[s]):
+            eng[s].forward(host[s])                       # H2D copy + graph on this stream
+            out_host[s].copy_(eng[s].dets, non_blocking=True)
+            cnt_host[s].copy_(eng[s].det_count, non_blocking=True)
+
+    for i in range(max(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+        if i >= 1:
+            streams[(i - 1) % 2].synchronize()            # consume step i-1's detections while step i runs
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = host[0].numel() * host[0].element_size()
+    d2h = out_host[0].numel() * 4 + cnt_host[0].numel() * 4
+
+    # ---------------- roofline of the dominant kernel (rank 0, eager pass with per-op events) ----------------
+    line = None
+    if rank == 0:
+        pk = peaks()
+        prof = eng[0].builder.profile()
+        prof = eng[0].builder.profile()
+        tc = [p for p in prof if p["kind"] == 0]
+        tc_ms = sum(p["ms"] for p in tc)
+        tc_flops = sum(p["flops"] for p in tc)
+        all_ms = sum(p["ms"] for p in prof)
+        achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        if args.profile_ops:
+            for p in prof:
+                print(f"# {p['name']:44s} {p['ms']*1e3:9.1f} us  {p['flops']/max(p['ms'],1e-9)/1e9:8.1f} TFLOP/s  "
+                      f"{p['bytes']/max(p['ms'],1e-9)/1e6:8.1f} GB/s", file=sys.stderr)
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                "launches": len(tc), "avg_launch_us": 1e3 * tc_ms / max(len(tc), 1), "share_of_step": tc_ms / all_ms,
+                "whole_step_frac_of_peak": GFLOP_PER_IMAGE.get(args.model, 0) * 1e9 * (value / world) / (pk["tf_sustained"] * 1e12)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            imgs = host[0][:args.cpu_images].numpy()
+            rate, threads, n = cpu_reference_rate(args, sd_cpu, imgs)
+            cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"{n} of the step's images, oracle/ torch-CPU fp32 forward + numpy/C NMS"}
+        vs = None
+        line = {
+            "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": vs, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{args.model} {S}x{S} batch-{B}/GPU {args.dtype} inference (fwd+decode+NMS), config[1] of BASELINE.json",
+                       "per_gpu_batch": B, "global_batch": B * world, "micro_batch": args.micro_batch,
+                       "conf_thre": args.conf, "nms_thre": args.nms, "nms_variant": "auto (torchvision CUDA rule)",
+                       "weights": "random init, BN calibrated (synthetic.randomize_and_calibrate)",
+                       "l2": "two alternating input batches of 315 MB each (> 126 MB L2)",
+                       "detections_kept_last_step": kept, "kept_per_image_mean": kept_true_mean,
+                       "candidates_per_image_mean": cand_mean},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "input": "pinned host fp32 [B,3,H,W], double-buffered over 2 streams"},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

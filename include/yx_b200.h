@@ -228,6 +228,11 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
                             int32_t* det_count, int32_t max_det, void* workspace,
                             int64_t workspace_bytes);
 int yx_plan_num_launches(const yx_plan* p);
+int yx_plan_num_ops(const yx_plan* p);
+/* Measurement aid: runs the ops one by one (no graph) with a CUDA event between consecutive ops on
+ * `stream` and returns each op's device time in milliseconds (ms[i], i < yx_plan_num_ops) and its
+ * kind (0 tcgen05 conv, 1 SIMT conv, 2 depthwise, 3 SPP, 4 focus, 5 postprocess). Synchronises. */
+int yx_plan_profile(yx_plan* p, void* stream, float* ms, int32_t* kinds, int32_t capacity);
 /* use_graph != 0: capture on first use, replay afterwards. */
 int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph);
 

@@ -380,6 +380,34 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
 }
 
 int yx_plan_num_launches(const yx_plan* p) { return p ? p->launches : 0; }
+int yx_plan_num_ops(const yx_plan* p) { return p ? (int)p->ops.size() : 0; }
+
+int yx_plan_profile(yx_plan* p, void* stream, float* ms, int32_t* kinds, int32_t capacity) {
+  YX_REQUIRE(p && ms && kinds, YX_ERR_INVALID_ARG, "plan_profile: null");
+  const int n = (int)p->ops.size();
+  YX_REQUIRE(capacity >= n, YX_ERR_CAPACITY, "plan_profile: capacity %d < %d ops", capacity, n);
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) YX_CUDA(cudaEventCreate(&e));
+  YX_CUDA(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n; ++i) {
+    rc = run_op(p->ops[i], s);
+    if (rc) break;
+    cudaEventRecord(ev[i + 1], s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == YX_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  if (rc == YX_OK) {
+    for (int i = 0; i < n; ++i) {
+      cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+      kinds[i] = (int32_t)p->ops[i].kind;
+    }
+  }
+  for (auto& ee : ev) cudaEventDestroy(ee);
+  return rc;
+}
 
 int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph) {
   YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_run: null plan");

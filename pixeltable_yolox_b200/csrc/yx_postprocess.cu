@@ -31,6 +31,11 @@ static constexpr int kChunk = 512;
 static constexpr int kChunkWords = kChunk / 32;
 static constexpr int kNmsThreads = 512;
 static constexpr int kMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
+static constexpr int kChunkBytes = kChunk * 24 + kChunk * kChunkWords * 4;
+static constexpr int kClassCap = 1024;      // class ids below this get a linked list of kept boxes
+static constexpr int kTriItems = 32 * (kChunkWords * (kChunkWords + 1) / 2);  // (row, word) items of the upper triangle
+static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassCap * 4;
+static constexpr int kKeptEntryBytes = 28;  // box 16 + area 4 + class 4 + next 4
 
 __device__ __forceinline__ uint32_t orderable(float f) {
   uint32_t u = __float_as_uint(f);
@@ -163,6 +168,7 @@ struct NmsArgs {
   unsigned long long* gkeys;       // used when the key list does not fit shared memory
   long long gkeys_stride;          // keys per image in gkeys (next_pow2(per_image))
   int smem_keys_cap;               // number of 64-bit keys the dynamic shared memory can hold
+  int kept_cap;                    // kept boxes that fit the shared-memory kept list
   float4* sorted_box;              // boxes as NMS sees them (offset applied for variant 0)
   int* sorted_cls;
   int* sorted_idx;
@@ -187,8 +193,9 @@ __device__ __forceinline__ float box_area(const float4 b) {
 
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs g) {
   extern __shared__ __align__(16) uint8_t nsm[];
-  __shared__ float red[kNmsThreads / 32];
-  __shared__ int s_nkept;
+  __shared__ float red[kNmsThreads / 32], red_mn[kNmsThreads / 32];
+  __shared__ int red_cmax[kNmsThreads / 32], red_cmin[kNmsThreads / 32];
+  __shared__ int s_nkept, s_ck;
   __shared__ unsigned s_removed[kChunkWords];
 
   const int b = blockIdx.x;
@@ -242,7 +249,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     }
 
     // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
-    float mx = -INFINITY;
+    float mx = -INFINITY, mn = INFINITY;
+    int cmax = 0, cmin = 0;
     for (int i = tid; i < n; i += kNmsThreads) {
       const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
       const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
@@ -252,14 +260,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
       sbox[i] = bx; scls[i] = c; sidx[i] = idx;
       mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+      mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
+      cmax = max(cmax, c); cmin = min(cmin, c);
+    }
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      }
+      if (lane == 0) { red[warp] = mx; red_mn[warp] = mn; red_cmax[warp] = cmax; red_cmin[warp] = cmin; }
+      __syncthreads();
+      mx = red[0]; mn = red_mn[0]; cmax = red_cmax[0]; cmin = red_cmin[0];
+      for (int i = 1; i < kNmsThreads / 32; ++i) {
+        mx = fmaxf(mx, red[i]); mn = fminf(mn, red_mn[i]);
+        cmax = max(cmax, red_cmax[i]); cmin = min(cmin, red_cmin[i]);
+      }
     }
     if (variant == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) red[warp] = mx;
-      __syncthreads();
-      mx = red[0];
-      for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, red[i]);
       // boxes_for_nms = boxes + idxs.to(boxes) * (max_coordinate + 1)   (torchvision boxes.py)
       const float step = __fadd_rn(mx, 1.0f);
       for (int i = tid; i < n; i += kNmsThreads) {
@@ -273,17 +293,48 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     __syncthreads();
 
     // ---------------- greedy NMS, chunk by chunk ----------------
+    // Which pairs can interact?  per-class variant: equal classes only.  Offset variant: class c lives in
+    // [c*s + min, c*s + max] with s = max+1, so classes a < b can only overlap when (b-a)*s < max-min+1,
+    // i.e. |a-b| <= J with J = ceil((max-min+1)/s) - 1 (J = 0 when no coordinate is negative; J = 1 for
+    // ordinary scenes with boxes sticking out of the image).  Pairs outside the window have IoU == 0 in
+    // torchvision's own arithmetic, so skipping them is exact.  Class-agnostic: everything interacts.
+    //
+    // shared memory (the sort buffer is dead now):
+    //   chunk : box/area/class of the 512 candidates in flight, their 512x512 suppression bitmask, and a
+    //           linked list of chunk members per class
+    //   kept  : boxes already kept (box, area, class) with a linked list per class
     float4* cbox = reinterpret_cast<float4*>(nsm);                          // [kChunk]
     float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
     int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
     unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kChunkWords]
-    const bool gate_cls = (variant == 1);
+    int* cnext = reinterpret_cast<int*>(nsm + kChunkBytes);                  // [kChunk]
+    int* ck = cnext + kChunk;                                                // [kChunk] kept members of the chunk
+    int* chead = ck + kChunk;                                                // [kClassCap]
+    int* khead = chead + kClassCap;                                          // [kClassCap]
+    uint8_t* kbase = reinterpret_cast<uint8_t*>(khead + kClassCap);
+    const int KC = g.kept_cap;
+    float4* kbox = reinterpret_cast<float4*>(kbase);                          // [KC]
+    float* karea = reinterpret_cast<float*>(kbase + (size_t)KC * 16);         // [KC]
+    int* kcls = reinterpret_cast<int*>(kbase + (size_t)KC * 20);              // [KC]
+    int* knext = reinterpret_cast<int*>(kbase + (size_t)KC * 24);             // [KC]
+
+    int J = 0x3fffffff;                                   // class window; "infinite" = ungated
+    if (variant == 1) J = 0;
+    else if (variant == 0) {
+      const float sft = mx + 1.0f;
+      if (sft > 0.0f) {
+        const float ratio = (mx - mn + 1.0f) / sft + 1e-3f;
+        if (ratio < 64.0f) J = max(0, (int)ceilf(ratio) - 1);
+      }
+    }
+    const bool use_lists = (J <= 4) && cmin >= 0 && cmax < kClassCap;
+    for (int i = tid; i < kClassCap; i += kNmsThreads) { khead[i] = -1; chead[i] = -1; }
 
     for (int c0 = 0; c0 < n; c0 += kChunk) {
       const int cn = min(kChunk, n - c0);
       __syncthreads();
       const int nk = s_nkept;
-      // this kernel uses kNmsThreads == kChunk: thread t owns candidate c0 + t
+      // kNmsThreads == kChunk: thread t owns candidate c0 + t
       float4 me = make_float4(0, 0, 0, 0);
       float my_area = 0.f;
       int my_cls = -1;
@@ -292,44 +343,80 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         me = sbox[c0 + tid]; my_cls = scls[c0 + tid]; my_area = box_area(me);
       }
       cbox[tid] = me; carea[tid] = my_area; ccls[tid] = my_cls;
-      // phase A: against the boxes kept in earlier chunks (uniform, L1-resident loads)
+      if (tid == 0) s_ck = 0;
+      // ---- phase A: against the boxes kept in earlier chunks
       if (!dead) {
-        for (int k = 0; k < nk; ++k) {
+        const int nks = min(nk, KC);
+        if (use_lists) {
+          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2)
+            for (int k = khead[c2]; k >= 0; k = knext[k])
+              if (suppresses(kbox[k], karea[k], me, my_area, g.thr)) { dead = true; break; }
+        } else {
+          for (int k = 0; k < nks; ++k) {
+            if (abs(kcls[k] - my_cls) > J) continue;
+            if (suppresses(kbox[k], karea[k], me, my_area, g.thr)) { dead = true; break; }
+          }
+        }
+        for (int k = KC; k < nk && !dead; ++k) {           // overflow of the shared-memory list
           const int kp = kept[k];
+          if (abs(scls[kp] - my_cls) > J) continue;
           const float4 kb = sbox[kp];
-          if (gate_cls && scls[kp] != my_cls) continue;
-          if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+          if (suppresses(kb, box_area(kb), me, my_area, g.thr)) dead = true;
         }
       }
-      __syncthreads();
       {
         const unsigned bal = __ballot_sync(0xffffffffu, dead);
         if (lane == 0) s_removed[warp] = bal;
       }
-      // phase B: suppression bitmask inside the chunk (row i, bits j > i)
-      for (int w = 0; w < kChunkWords; ++w) {
-        unsigned bits = 0u;
-        if (!dead && (w * 32 + 31) > tid) {
+      // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i)
+      if (use_lists) {
+        // members of the chunk per class; each alive row only visits its class window
+#pragma unroll
+        for (int w = 0; w < kChunkWords; ++w) cmask[tid * kChunkWords + w] = 0u;
+        if (!dead) cnext[tid] = atomicExch(&chead[my_cls], tid);
+        __syncthreads();
+        if (!dead) {
+          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1); ++c2)
+            for (int j = chead[c2]; j >= 0; j = cnext[j])
+              if (j > tid && suppresses(me, my_area, cbox[j], carea[j], g.thr))
+                cmask[tid * kChunkWords + (j >> 5)] |= (1u << (j & 31));
+        }
+        __syncthreads();
+        if (!dead) chead[my_cls] = -1;                       // leave the heads clean for the next chunk
+      } else {
+        __syncthreads();
+        // balanced enumeration of the (row, word) items of the upper triangle: rows of group rb = row/32
+        // have (16 - rb) words each
+        for (int q = tid; q < kTriItems; q += kNmsThreads) {
+          int rb = 0, rem = q;
+          while (rem >= 32 * (kChunkWords - rb)) { rem -= 32 * (kChunkWords - rb); ++rb; }
+          const int per = kChunkWords - rb;
+          const int row = rb * 32 + rem / per;
+          const int w = rb + rem % per;
+          unsigned bits = 0u;
+          const bool row_dead = (s_removed[row >> 5] >> (row & 31)) & 1u;
+          if (!row_dead) {
+            const float4 rbx = cbox[row];
+            const float rar = carea[row];
+            const int rcl = ccls[row];
 #pragma unroll 4
-          for (int jb = 0; jb < 32; ++jb) {
-            const int j = w * 32 + jb;
-            if (j > tid && j < cn) {
-              if (!gate_cls || ccls[j] == my_cls) {
-                if (suppresses(me, my_area, cbox[j], carea[j], g.thr)) bits |= (1u << jb);
-              }
+            for (int jb = 0; jb < 32; ++jb) {
+              const int j = w * 32 + jb;
+              if (j > row && j < cn && abs(ccls[j] - rcl) <= J &&
+                  suppresses(rbx, rar, cbox[j], carea[j], g.thr))
+                bits |= (1u << jb);
             }
           }
+          cmask[row * kChunkWords + w] = bits;
         }
-        cmask[tid * kChunkWords + w] = bits;
+        __syncthreads();
       }
-      __syncthreads();
-      // phase C: one warp walks the chunk; lane w owns word w of the removed set
+      // ---- phase C: one warp walks the chunk; lane w owns word w of the removed set
       if (warp == 0) {
         unsigned removed = lane < kChunkWords ? s_removed[lane] : 0xffffffffu;
-        int nkept = nk;
+        int cnt = 0;
         int pos = 0;
         while (true) {
-          // next alive candidate at or after pos
           unsigned alive = (lane < kChunkWords) ? ~removed : 0u;
           const int wpos = pos >> 5;
           if (lane < wpos) alive = 0u;
@@ -340,13 +427,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           const unsigned aw = __shfl_sync(0xffffffffu, alive, wsel);
           const int i = wsel * 32 + (__ffs(aw) - 1);
           if (i >= cn) break;
-          if (lane == 0) kept[nkept] = c0 + i;
-          ++nkept;
+          if (lane == 0) ck[cnt] = i;
+          ++cnt;
           if (lane < kChunkWords) removed |= cmask[i * kChunkWords + lane];
           pos = i + 1;
           if (pos >= cn) break;
         }
-        if (lane == 0) s_nkept = nkept;
+        if (lane == 0) s_ck = cnt;
+      }
+      __syncthreads();
+      // ---- append the chunk's survivors to the kept list (parallel; list order is irrelevant)
+      {
+        const int cnt = s_ck;
+        if (tid < cnt) {
+          const int i = ck[tid];
+          const int e = nk + tid;
+          kept[e] = c0 + i;
+          if (e < KC) {
+            const int ci = ccls[i];
+            kbox[e] = cbox[i]; karea[e] = carea[i]; kcls[e] = ci;
+            if (use_lists) knext[e] = atomicExch(&khead[ci], e);
+          }
+        }
+        if (tid == 0) s_nkept = nk + cnt;
       }
       __syncthreads();
     }
@@ -420,14 +523,21 @@ static int smem_keys_cap(long long per_image) {
   const long long p = next_pow2_ll(per_image);
   return (int)(p > kMaxSmemKeys ? kMaxSmemKeys : p);
 }
+static int kept_cap_for(long long per_image) {
+  const long long budget = 200 * 1024 - kNmsFixedBytes;
+  long long cap = budget / kKeptEntryBytes;
+  if (cap > per_image) cap = per_image;
+  return (int)(cap < 1 ? 1 : cap);
+}
 static size_t nms_smem_bytes(long long per_image) {
   const size_t sort_bytes = (size_t)smem_keys_cap(per_image) * 8;
-  const size_t chunk_bytes = (size_t)kChunk * 24 + (size_t)kChunk * kChunkWords * 4;
-  return sort_bytes > chunk_bytes ? sort_bytes : chunk_bytes;
+  const size_t nms_bytes = (size_t)kNmsFixedBytes + (size_t)kept_cap_for(per_image) * kKeptEntryBytes;
+  return sort_bytes > nms_bytes ? sort_bytes : nms_bytes;
 }
 
 static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.smem_keys_cap = smem_keys_cap(g.src.per_image);
+  g.kept_cap = kept_cap_for(g.src.per_image);
   g.gkeys_stride = next_pow2_ll(g.src.per_image);
   const size_t smem = nms_smem_bytes(g.src.per_image);
   static size_t configured = 0;

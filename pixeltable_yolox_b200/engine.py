@@ -95,7 +95,7 @@ class Builder:
         self.weight_cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.n_ops = 0
         self.flops = 0.0
-        self.input_ops: List[tuple] = []
+        self.op_info: List[dict] = []    # per emitted op: name, algorithmic flops and bytes
 
     def close(self):
         if self.plan is not None:
@@ -187,7 +187,15 @@ class Builder:
                                res.view() if res is not None else None,
                                ups.view() if ups is not None else None, head_arg)
         self._emit_conv(d)
-        self.flops += 2.0 * x.B * oh * ow * sum(p.weight.shape[0] * p.weight.shape[1] for p in parts) * ksize * ksize
+        fl = 2.0 * x.B * oh * ow * sum(p.weight.shape[0] * p.weight.shape[1] for p in parts) * ksize * ksize
+        esz = w.element_size()
+        by = x.B * x.H * x.W * x.c_slots * esz + w.numel() * esz
+        by += x.B * oh * ow * (5 + head["nc"]) * 4 if head is not None else x.B * oh * ow * w.shape[0] * esz * (5 if ups is not None else 1)
+        if res is not None:
+            by += x.B * oh * ow * w.shape[0] * esz
+        self.flops += fl
+        self.op_info.append(dict(name=f"conv{ksize}x{ksize}s{stride} {x.c_slots}->{w.shape[0]} @{oh}x{ow}", flops=fl, bytes=by,
+                                 tc=self.dtype != torch.float32))
         return out
 
     def _emit_conv(self, d):
@@ -229,6 +237,8 @@ class Builder:
             ops.dwconv3x3(xv, w, bias, ov, stride, act)
         self.n_ops += 1
         self.flops += 2.0 * x.B * oh * ow * c * 9
+        self.op_info.append(dict(name=f"dwconv3x3s{stride} {c} @{oh}x{ow}", flops=2.0 * x.B * oh * ow * c * 9,
+                                 bytes=(x.B * x.H * x.W + x.B * oh * ow) * pad16(c) * w.element_size(), tc=False))
         return out
 
     def spp(self, cat: Feat, c: int) -> None:
@@ -240,6 +250,7 @@ class Builder:
         else:
             ops.spp_maxpool(v, c)
         self.n_ops += 1
+        self.op_info.append(dict(name=f"spp {c} @{v.H}x{v.W}", flops=0.0, bytes=v.B * v.H * v.W * 4 * c * cat.t.element_size(), tc=False))
 
     def focus(self, img: torch.Tensor) -> Feat:
         B, _, H, W = img.shape
@@ -251,6 +262,8 @@ class Builder:
         else:
             ops.focus_s2d(img, v)
         self.n_ops += 1
+        self.op_info.append(dict(name=f"focus {H}x{W}", flops=0.0,
+                                 bytes=img.numel() * img.element_size() + f.t.numel() * f.t.element_size(), tc=False))
         return f
 
     def postprocess(self, pred, nc, conf, nms, variant, inplace, dets, det_idx, det_count, max_det, ws):
@@ -259,6 +272,16 @@ class Builder:
                                             det_idx.data_ptr(), det_count.data_ptr(), max_det, ws.data_ptr(),
                                             ws.numel()), "plan_add_postprocess")
         self.keep += [pred, dets, det_idx, det_count, ws]
+        self.op_info.append(dict(name="postprocess", flops=0.0, bytes=pred.numel() * 4, tc=False))
+
+    def profile(self):
+        """Per-op device times (ms) of one eager pass: list of dicts (op_info + ms + kind)."""
+        n = lib().yx_plan_num_ops(self.plan)
+        ms = (C.c_float * n)()
+        kinds = (C.c_int32 * n)()
+        check(lib().yx_plan_profile(self.plan, stream_ptr(self.dev), ms, kinds, n), "plan_profile")
+        assert n == len(self.op_info), (n, len(self.op_info))
+        return [dict(info, ms=float(ms[i]), kind=int(kinds[i])) for i, info in enumerate(self.op_info)]
 
     def run(self, use_graph: bool = False) -> None:
         check(lib().yx_plan_run(self.plan, stream_ptr(self.dev), 1 if use_graph else 0), "plan_run")

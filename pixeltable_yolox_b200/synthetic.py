@@ -121,3 +121,48 @@ def simota_case(num_gt: int, seed: int = 21):
     cost = (rng.uniform(0.5, 8.0, size=(num_gt, n)) + 3.0 * -np.log(ious + 1e-8)).astype(np.float32)
     cost = (cost + np.float32(1e6) * (~geom)).astype(np.float32)
     return cost, ious
+
+
+def randomize_and_calibrate(model, images_nchw, seed: int = 0):
+    """Random-init weights give degenerate scores (all ties): randomise BN gamma/beta and
+    the cls/obj biases, then calibrate the BN running statistics on `images_nchw` (torch ops in
+    train-mode BN with momentum=None), and keep the raw box regressions within |v| <= 2.5.
+    Weight preparation only - not on the inference path. Works on CPU or CUDA."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed + 1)
+    dev = next(model.parameters()).device
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    was_training = model.training
+    with torch.no_grad():
+        for b in bns:
+            b.weight.copy_(torch.empty(b.weight.shape).uniform_(0.5, 1.5, generator=g).to(dev))
+            b.bias.copy_(torch.empty(b.bias.shape).normal_(0, 0.2, generator=g).to(dev))
+        for p in model.head.cls_preds:
+            p.bias.copy_(torch.empty(p.bias.shape).normal_(-2.0, 1.5, generator=g).to(dev))
+        for p in model.head.obj_preds:
+            # objectness prior of a trained detector: most anchors are background, so tens to a few
+            # hundred candidates per image pass conf 0.5 (N(-2,1.5) lets ~6500 of 8400 anchors through,
+            # none of which suppress each other; that regime is covered by the dense NMS stress case)
+            p.bias.copy_(torch.empty(p.bias.shape).normal_(-4.0, 0.5, generator=g).to(dev))
+        model.train()
+        for b in bns:
+            b.momentum = None
+            b.reset_running_stats()
+        x = torch.as_tensor(images_nchw).to(dev).float()
+        for _ in range(2):
+            raw = model.head._torch_raw_outputs(model.backbone._train_forward(x))
+        for b in bns:
+            b.momentum = 0.03
+            b.running_var.copy_(torch.maximum(b.running_var, 0.05 * b.running_var.mean() + 1e-4))
+        model.eval()
+        for b in bns:
+            b.eval()
+        raw = model.head._torch_raw_outputs(model.backbone._train_forward(x))
+        for k, (reg, _, _) in enumerate(raw):
+            m = reg.abs().max().item()
+            if m > 2.5:
+                model.head.reg_preds[k].weight.mul_(2.5 / m)
+                model.head.reg_preds[k].bias.mul_(2.5 / m)
+    model.train(was_training)
+    return model

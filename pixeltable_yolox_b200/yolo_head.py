@@ -97,6 +97,20 @@ class YoloxHead(_B200Block):
         self.hw = [torch.Size(v) for v in hw]
         return head_out
 
+    def _torch_raw_outputs(self, xin):
+        """Prediction-conv outputs per level through torch ops (used by the training branch and by
+        synthetic.randomize_and_calibrate; never by the eval hot path)."""
+        outs = []
+        for k, x in enumerate(xin):
+            x = self.stems[k]._train_forward(x)
+            cls_feat, reg_feat = x, x
+            for blk in self.cls_convs[k]:
+                cls_feat = blk._train_forward(cls_feat)
+            for blk in self.reg_convs[k]:
+                reg_feat = blk._train_forward(reg_feat)
+            outs.append((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)))
+        return outs
+
     # ------------------------------------------------------------------ forward
     def forward(self, xin, labels=None, imgs=None):
         if not self.training:
@@ -104,17 +118,7 @@ class YoloxHead(_B200Block):
 
             return run_head(self, xin)
         outputs, origin_preds, x_shifts, y_shifts, expanded_strides = [], [], [], [], []
-        for k, x in enumerate(xin):
-            x = self.stems[k]._train_forward(x)
-            cls_feat = x
-            for blk in self.cls_convs[k]:
-                cls_feat = blk._train_forward(cls_feat)
-            reg_feat = x
-            for blk in self.reg_convs[k]:
-                reg_feat = blk._train_forward(reg_feat)
-            cls_output = self.cls_preds[k](cls_feat)
-            reg_output = self.reg_preds[k](reg_feat)
-            obj_output = self.obj_preds[k](reg_feat)
+        for k, (reg_output, obj_output, cls_output) in enumerate(self._torch_raw_outputs(xin)):
             output = torch.cat([reg_output, obj_output, cls_output], 1)
             output, grid = self.get_output_and_grid(output, k, self.strides[k], xin[0].type())
             x_shifts.append(grid[:, :, 0])

@@ -53,7 +53,7 @@ class YoloxModule(nn.Module):
         self.backbone = backbone if backbone is not None else YoloPafpn()
         self.head = head if head is not None else YoloxHead(80)
         self._engines = {}
-        self.micro_batch = 16       # images per L2-resident pass (see engine.InferenceEngine)
+        self.micro_batch = 64       # images per pass (see engine.InferenceEngine)
         self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ engine cache
@@ -74,12 +74,14 @@ class YoloxModule(nn.Module):
         self.invalidate_engine()
         return super().load_state_dict(*args, **kwargs)
 
-    def engine_for(self, x: torch.Tensor, post: Optional[dict] = None):
+    def engine_for(self, x: torch.Tensor, post: Optional[dict] = None, slot: int = 0):
+        """The cached InferenceEngine for this input signature. `slot` selects an independent engine
+        (own staging/activation buffers) so that two batches can be in flight on two streams."""
         from .engine import InferenceEngine
 
         dev = next(self.parameters()).device
         key = (tuple(x.shape), x.dtype, dev, self.head.decode_in_inference, self.micro_batch, self.use_cuda_graph,
-               tuple(sorted(post.items())) if post else None)
+               tuple(sorted((k, v) for k, v in post.items() if v is not None)) if post else None, slot)
         eng = self._engines.get(key)
         if eng is None:
             eng = InferenceEngine(self, x.shape[0], x.shape[2], x.shape[3], x.dtype, dev,

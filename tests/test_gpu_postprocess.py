@@ -78,6 +78,31 @@ def test_ties_and_degenerate_boxes(cuda):
         _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.1, 0.5, nms_variant=variant), want)
 
 
+def test_negative_coordinates_disable_class_gating(cuda):
+    """With negative coordinates the offset trick lets boxes of adjacent classes overlap; the kernel must
+    then compare across classes exactly like torchvision does."""
+    pred = syn.dense_scene(2, anchors=3000, seed=46, clusters=30, size=320.0)
+    pred[:, :, 0:2] -= 250.0
+    for variant in ("offset", "per_class"):
+        want, _ = po.postprocess(pred.copy(), 80, 0.2, 0.5, variant=variant, return_indices=True)
+        _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.2, 0.5, nms_variant=variant), want)
+
+
+def test_single_class_dense_scene_overflows_the_shared_kept_list(cuda):
+    """Every box in one class, low overlap: thousands kept, more than the shared-memory list holds."""
+    rng = np.random.default_rng(47)
+    A = 12000
+    pred = np.zeros((1, A, 85), dtype=np.float32)
+    pred[0, :, 0:2] = rng.uniform(0, 4000, size=(A, 2))
+    pred[0, :, 2:4] = rng.uniform(10, 30, size=(A, 2))
+    pred[0, :, 4] = rng.uniform(0.5, 1.0, size=A)
+    pred[0, :, 5 + 7] = rng.uniform(0.5, 1.0, size=A)
+    for variant in ("offset", "per_class"):
+        want, _ = po.postprocess(pred.copy(), 80, 0.1, 0.3, variant=variant, return_indices=True)
+        assert len(want[0]) > 7000
+        _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.1, 0.3, nms_variant=variant), want)
+
+
 def test_empty_batch_and_no_candidates(cuda):
     assert yx.postprocess(torch.zeros(0, 100, 85, device=cuda), 80) == []
     out = yx.postprocess(torch.zeros(3, 100, 85, device=cuda), 80, 0.5, 0.65)
