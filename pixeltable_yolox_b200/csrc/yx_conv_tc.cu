@@ -48,12 +48,14 @@ struct ConvTcParams {
   unsigned tmem_cols;
   unsigned bias_bytes;   // shared-memory copy of the bias vector (out_c floats, rounded to 1 KB)
   unsigned head_bytes;   // YX_EPI_HEAD: per-warp [32][5+nc] fp32 staging for coalesced row stores
+  int epi_groups;        // 1..kMaxEpiGroups
   EpiParams epi;
 };
 
 static constexpr int kMaxStages = 8;
 static constexpr int kMaxAcc = 4;
-static constexpr int kThreads = 192;
+static constexpr int kMaxEpiGroups = 3;           // epilogue warpgroups (4 warps each); tiles alternate between them
+static constexpr int kMaxThreads = 64 + 128 * kMaxEpiGroups;
 
 struct __align__(8) TcShared {
   uint64_t full[kMaxStages];
@@ -126,7 +128,7 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* tiles = smem + 1024 + p.bias_bytes + p.head_bytes;
   // bias lives in shared memory: with ~200 KB of operand stages the L1 carve-out is ~0, so a
   // global bias load in the epilogue would be an L2 round trip per 16 columns
-  for (int i = threadIdx.x; i < p.epi.out_c; i += kThreads) sbias[i] = p.epi.bias[i];
+  for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x) sbias[i] = p.epi.bias[i];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,13 +236,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2.., in groups of 4) =====================
+    // With one epilogue warp per scheduler every dependent instruction stalls the SM sub-partition;
+    // group g drains the tiles it, it+G, ... of this CTA so that G tiles are in the epilogue at once.
     const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32)
     const int row = quarter * 32 + lane;     // accumulator row = pixel inside the tile
-    int as = 0;
-    uint32_t aphase = 0;
+    const int grp = (warp - 2) >> 2;
     const int out_hw = p.epi.out_h * p.epi.out_w;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int it = grp;; it += p.epi_groups) {
+      const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tl >= p.num_tiles) break;
+      const int t = (int)tl;
+      int as = it % p.acc_stages;
+      const uint32_t aphase = (uint32_t)((it / p.acc_stages) & 1);
       const int n_tile = t % p.n_tiles;
       const int m_tile = t / p.n_tiles;
       int b, ho, wo;
@@ -272,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- head: decode/sigmoid in registers, stage the warp's 32 rows in shared memory, then
         //      write each [5+nc] fp32 row with coalesced 128-byte stores
         const int nch = 5 + p.epi.head_nc;
-        float* wstage = shead + (size_t)(warp - 2) * 32 * nch;
+        float* wstage = shead + (size_t)(warp - 2) * 32 * nch;   // one staging slab per epilogue warp
         for (int c = 0; c < p.BN; c += 16) {
           uint32_t raw[16];
           tmem_ld_x16(taddr + (uint32_t)c, raw);
@@ -282,12 +290,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int ch = c + j;
             if (ch < nch) {
               float x = __uint_as_float(raw[j]) + tbias[ch];
+              // fast-math exp / reciprocal (~1e-6 relative): the inputs carry 16-bit activation noise
               if (ch < 2) {
                 if (p.epi.head_decode & 1) x = (x + (ch == 0 ? (float)wo : (float)ho)) * p.epi.head_stride;
               } else if (ch < 4) {
-                if (p.epi.head_decode & 1) x = expf(x) * p.epi.head_stride;
+                if (p.epi.head_decode & 1) x = __expf(x) * p.epi.head_stride;
               } else if (p.epi.head_decode & 2) {
-                x = 1.0f / (1.0f + expf(-x));
+                x = __fdividef(1.0f, 1.0f + __expf(-x));
               }
               wstage[lane * nch + ch] = x;
             }
@@ -299,15 +308,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long arow = valid ? ((long long)b * p.epi.head_anchors + p.epi.head_anchor_off +
                                         (long long)ho * p.epi.out_w + wo) : -1;
         __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-          const long long ar = __shfl_sync(0xffffffffu, arow, r);
-          if (ar < 0) continue;
-          float* dst = p.epi.head_out + ar * nch;
-          const float* src = wstage + r * nch;
-          for (int ch = lane; ch < nch; ch += 32) dst[ch] = src[ch];
+        const long long a0 = __shfl_sync(0xffffffffu, arow, 0);
+        const bool contiguous = __all_sync(0xffffffffu, arow == a0 + lane) && ((a0 * nch) & 3) == 0 && ((32 * nch) & 3) == 0;
+        if (contiguous) {
+          // the warp's 32 rows are one contiguous, 16-byte aligned block of 32*(5+nc) floats
+          float4* dst = reinterpret_cast<float4*>(p.epi.head_out + a0 * nch);
+          const float4* src = reinterpret_cast<const float4*>(wstage);
+          for (int i = lane; i < 8 * nch; i += 32) dst[i] = src[i];
+        } else {
+          for (int r = 0; r < 32; ++r) {
+            const long long ar = __shfl_sync(0xffffffffu, arow, r);
+            if (ar < 0) continue;
+            float* dst = p.epi.head_out + ar * nch;
+            const float* src = wstage + r * nch;
+            for (int ch = lane; ch < nch; ch += 32) dst[ch] = src[ch];
+          }
         }
         __syncwarp();
-        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         continue;
       }
       // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
@@ -336,7 +353,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&sh->tmem_empty[as]);
-      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -499,7 +515,15 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int num_k = d->ksize * d->ksize * p.kchunks;
   p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
-  p.head_bytes = d->epilogue == YX_EPI_HEAD ? ((4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
+  // epilogue groups: memory-bound layers (short K loops) need several tiles in the epilogue at once
+  {
+    const int num_k_total = d->ksize * d->ksize * (d->in_c / p.KC);
+    p.epi_groups = num_k_total * (p.KC / 16) * p.BN <= 4096 ? 3 : 2;   // MMA cycles per tile ~ k-steps * BN / 2
+    if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
+    if (d->epilogue == YX_EPI_HEAD && p.epi_groups > 2) p.epi_groups = 2;   // staging slabs are 10.9 KB per warp
+    if (const char* e = getenv("YX_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= kMaxEpiGroups && v <= p.acc_stages) p.epi_groups = v; }
+  }
+  p.head_bytes = d->epilogue == YX_EPI_HEAD ? (((unsigned)p.epi_groups * 4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
   const unsigned fixed_bytes = 2048u + p.bias_bytes + p.head_bytes;
   int stages = (int)((max_smem - (int)fixed_bytes) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -575,7 +599,7 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
-  conv_tc_kernel<<<L->grid, kThreads, L->smem, stream>>>(L->map_a, L->map_b, L->p);
+  conv_tc_kernel<<<L->grid, 64 + 128 * L->p.epi_groups, L->smem, stream>>>(L->map_a, L->map_b, L->p);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
