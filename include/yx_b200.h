@@ -121,6 +121,16 @@ int yx_spp_maxpool(void* buf, int64_t ld, int32_t batch, int32_t h, int32_t w, i
 int yx_focus_s2d(const void* img, int32_t img_dtype, void* out, int64_t out_ld, int32_t out_dtype,
                  int32_t batch, int32_t h, int32_t w, void* stream);
 
+/* Fused Focus + stem conv + folded BN + act on the tensor cores (network_blocks.py:186-208 + 27-52):
+ * reads the raw NCHW image (fp32 or uint8) once and writes the NHWC 16-bit stem output once.
+ * The Focus + 3x3 conv is evaluated as the equivalent 6x6 stride-2 pad-2 conv on the image:
+ *   w    : [out_c][128] in `dtype`, k = dy*18 + c*6 + dx (dy, dx in 0..5 window rows/cols, c image
+ *          channel), columns 108..127 zero; W6[o,c,2u+py,2v+px] = Wfocus[o, 3*(2*px+py)+c, u, v] * bn_scale
+ *   bias : [out_c] fp32; out: [B, h/2, w/2, out_ld] NHWC.  out_c % 16 == 0, out_c <= 128. */
+int yx_focus_conv_bn_act_fwd(const void* img, int32_t img_dtype, const void* w, const float* bias,
+                             void* out, int64_t out_ld, int32_t batch, int32_t h, int32_t wd,
+                             int32_t out_c, int32_t act, int32_t dtype, void* stream);
+
 /* Fold BN into a conv and repack it for yx_conv_bn_act_fwd (model_utils.py:33-75):
  *   src    : [o][i][kh][kw] fp32 (nn.Conv2d.weight); gamma/beta/mean/var [o] fp32 or NULL
  *            (plain conv); conv_bias [o] fp32 or NULL;
@@ -222,6 +232,9 @@ int yx_plan_add_spp(yx_plan* p, void* buf, int64_t ld, int32_t batch, int32_t h,
                     int32_t c, int32_t dtype);
 int yx_plan_add_focus(yx_plan* p, const void* img, int32_t img_dtype, void* out, int64_t out_ld,
                       int32_t out_dtype, int32_t batch, int32_t h, int32_t w);
+int yx_plan_add_focus_conv(yx_plan* p, const void* img, int32_t img_dtype, const void* w,
+                           const float* bias, void* out, int64_t out_ld, int32_t batch, int32_t h,
+                           int32_t wd, int32_t out_c, int32_t act, int32_t dtype);
 int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anchors, int32_t nc,
                             float conf_thre, double nms_thre, int32_t nms_variant,
                             int32_t inplace_xyxy, float* dets, int64_t* det_idx,
@@ -231,7 +244,7 @@ int yx_plan_num_launches(const yx_plan* p);
 int yx_plan_num_ops(const yx_plan* p);
 /* Measurement aid: runs the ops one by one (no graph) with a CUDA event between consecutive ops on
  * `stream` and returns each op's device time in milliseconds (ms[i], i < yx_plan_num_ops) and its
- * kind (0 tcgen05 conv, 1 SIMT conv, 2 depthwise, 3 SPP, 4 focus, 5 postprocess). Synchronises. */
+ * kind (0 tcgen05 conv, 1 SIMT conv, 2 depthwise, 3 SPP, 4 focus, 5 postprocess, 6 fused focus+stem conv). Synchronises. */
 int yx_plan_profile(yx_plan* p, void* stream, float* ms, int32_t* kinds, int32_t capacity);
 /* use_graph != 0: capture on first use, replay afterwards. */
 int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph);

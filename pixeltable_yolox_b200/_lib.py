@@ -56,6 +56,7 @@ SIGNATURES = {
     "yx_dwconv3x3_bn_act_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_spp_maxpool": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_focus_s2d": (C.c_int, [_P, _I32, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+    "yx_focus_conv_bn_act_fwd": (C.c_int, [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_pack_weights": (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "yx_head_decode": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "yx_postprocess_workspace_bytes": (_I64, [_I32, _I32]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "yx_plan_add_dwconv": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_spp": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_focus": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32]),
+    "yx_plan_add_focus_conv": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_postprocess": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _D, _I32, _I32, _P, _P, _P, _I32, _P, _I64]),
     "yx_plan_num_launches": (C.c_int, [_P]),
     "yx_plan_num_ops": (C.c_int, [_P]),

@@ -41,7 +41,12 @@ int simota_assign_launch(const float* pred, const float* labels, const float* xs
                          cudaStream_t s);
 int simota_matching_launch(const float* cost, const float* ious, int G, int n, long long ld, int* match_gt,
                            float* match_iou, int* num_fg, cudaStream_t s);
-size_t conv_tc_launch_size();
+struct StemLaunch;
+StemLaunch* stem_alloc();
+void stem_free(StemLaunch*);
+int stem_prepare(const void* img, int img_dtype, const void* w, const float* bias, void* out, long long out_ld,
+                 int batch, int h, int wd, int out_c, int act, int dtype, StemLaunch* L);
+int stem_launch(const StemLaunch* L, cudaStream_t stream);
 ConvTcLaunch* conv_tc_alloc();
 void conv_tc_free(ConvTcLaunch*);
 
@@ -92,11 +97,12 @@ static int require_device() {
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST };
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP_STEM };
 
 struct Op {
   OpKind kind;
   ConvTcLaunch* tc;  // OP_CONV_TC
+  StemLaunch* stem;  // OP_STEM
   yx_conv_desc conv;  // OP_CONV_SIMT
   struct { const void* in; long long in_ld; const void* w; const float* bias; void* out; long long out_ld;
            int batch, in_h, in_w, c, stride, act, dtype; } dw;
@@ -121,6 +127,7 @@ namespace yx {
 static int run_op(const Op& o, cudaStream_t s) {
   switch (o.kind) {
     case OP_CONV_TC: return conv_tc_launch(o.tc, s);
+    case OP_STEM: return stem_launch(o.stem, s);
     case OP_CONV_SIMT: return conv_simt_launch(&o.conv, s);
     case OP_DWCONV: return dwconv_launch(o.dw.in, o.dw.in_ld, o.dw.w, o.dw.bias, o.dw.out, o.dw.out_ld, o.dw.batch,
                                          o.dw.in_h, o.dw.in_w, o.dw.c, o.dw.stride, o.dw.act, o.dw.dtype, s);
@@ -208,6 +215,18 @@ int yx_focus_s2d(const void* img, int32_t img_dtype, void* out, int64_t out_ld, 
   return focus_launch(img, img_dtype, out, out_ld, out_dtype, batch, h, w, (cudaStream_t)stream);
 }
 
+int yx_focus_conv_bn_act_fwd(const void* img, int32_t img_dtype, const void* w, const float* bias, void* out,
+                             int64_t out_ld, int32_t batch, int32_t h, int32_t wd, int32_t out_c, int32_t act,
+                             int32_t dtype, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  StemLaunch* L = stem_alloc();
+  rc = stem_prepare(img, img_dtype, w, bias, out, out_ld, batch, h, wd, out_c, act, dtype, L);
+  if (rc == YX_OK) rc = stem_launch(L, (cudaStream_t)stream);
+  stem_free(L);
+  return rc;
+}
+
 int yx_pack_weights(const float* src, const float* gamma, const float* beta, const float* mean, const float* var,
                     const float* conv_bias, float eps, int32_t o, int32_t i, int32_t kh, int32_t kw, void* dst_w,
                     int32_t dst_dtype, int32_t dst_o_off, int32_t dst_i_off, int32_t dst_i_total, float* dst_b,
@@ -290,8 +309,10 @@ void yx_plan_destroy(yx_plan* p) {
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
   if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
-  for (auto& o : p->ops)
+  for (auto& o : p->ops) {
     if (o.tc) conv_tc_free(o.tc);
+    if (o.stem) stem_free(o.stem);
+  }
   delete p;
 }
 
@@ -357,6 +378,24 @@ int yx_plan_add_focus(yx_plan* p, const void* img, int32_t img_dtype, void* out,
   memset(&o, 0, sizeof(o));
   o.kind = OP_FOCUS;
   o.focus = {img, img_dtype, out, out_ld, out_dtype, batch, h, w};
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_focus_conv(yx_plan* p, const void* img, int32_t img_dtype, const void* w, const float* bias, void* out,
+                           int64_t out_ld, int32_t batch, int32_t h, int32_t wd, int32_t out_c, int32_t act,
+                           int32_t dtype) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_focus_conv: null plan");
+  int rc = require_device();
+  if (rc) return rc;
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_STEM;
+  o.stem = stem_alloc();
+  rc = stem_prepare(img, img_dtype, w, bias, out, out_ld, batch, h, wd, out_c, act, dtype, o.stem);
+  if (rc) { stem_free(o.stem); return rc; }
   p->ops.push_back(o);
   p->launches += 1;
   plan_invalidate(p);

@@ -24,7 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "yx_epilogue.cuh"
+#include "yx_tc_epilogue.cuh"
 
 namespace yx {
 
@@ -65,68 +65,6 @@ struct __align__(8) TcShared {
   uint32_t tmem_base;
 };
 
-
-__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-// SiLU with one MUFU: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32: ~2^-11 relative,
-// below the bf16/fp16 output rounding)
-__device__ __forceinline__ float silu_tanh(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-
-// 16 accumulator columns of one pixel: bias (smem) + act (+ residual) -> 16-bit, one 32-byte store
-__device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
-                                             const uint32_t* res, bool fp16, uint16_t* dst, int b, int ho, int wo,
-                                             int c0) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
-    v[j + 0] = __uint_as_float(raw[j + 0]) + bb.x;
-    v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
-    v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z;
-    v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
-  }
-  if (e.act == YX_ACT_SILU && !fp16) {
-    // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_tanh(v[j]);
-  } else if (e.act != YX_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = act_f<false>(v[j], e.act);
-  }
-  if (res) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a, c;
-      unpack16(res[j], fp16, a, c);
-      v[2 * j] += a; v[2 * j + 1] += c;
-    }
-  }
-  uint32_t w[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) w[j] = pack16(v[2 * j], v[2 * j + 1], fp16);
-  st_global_256(dst, w);
-  if (e.ups) {
-    const int uw = 2 * e.out_w;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long up = ((long long)b * 2 * e.out_h + 2 * ho + (q >> 1)) * uw + 2 * wo + (q & 1);
-      st_global_256((uint16_t*)e.ups + up * e.ups_ld + c0, w);
-    }
-  }
-}
 
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -372,7 +310,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {

@@ -1,0 +1,346 @@
+// Fused Focus + stem conv for sm_100a: space-to-depth, 3x3 conv, folded BN and SiLU in ONE kernel.
+//   reference: Focus.forward (yolox/models/network_blocks.py:186-208) followed by its BaseConv
+//   (network_blocks.py:27-52).  Focus(TL,BL,TR,BR) + 3x3 stride-1 pad-1 conv over 12 channels is the
+//   same linear map as a 6x6 stride-2 pad-2 conv over the 3 image channels:
+//       W6[o, c, 2u+py, 2v+px] = W[o, 3*(2*px+py) + c, u, v].
+// The raw NCHW image (fp32 or uint8, 0..255) is read once and the NHWC 16-bit stem output written
+// once; nothing else touches HBM (the unfused path writes and re-reads a 12-channel tensor and pays
+// nine 32-byte-row TMA gathers per pixel).
+//
+// GEMM view: M = output pixels (tile = 8 rows x 16 cols), K = 6*3*6 = 108 (zero padded to 128),
+// N = out_c.  TMA cannot build this operand (fp32/u8 source, channel-planar layout), so four
+// "builder" warps stage the tile's 20x36x3 input patch in shared memory as bf16/fp16 and write the
+// [128 x 128] K-major, 128B-swizzled A operand with ordinary 16-byte shared stores
+// (fence.proxy.async makes them visible to the tensor core).  The weights (out_c x 128) stay resident
+// in shared memory.  Roles: warps 0-3 build, warp 4 issues tcgen05.mma (TMEM accumulators, 4 stages),
+// warps 5-12 are two epilogue groups (bias + SiLU + 256-bit stores).
+#include <stdlib.h>
+#include <string.h>
+
+#include "yx_tc_epilogue.cuh"
+
+namespace yx {
+
+static constexpr int kStemStages = 3;
+static constexpr int kStemAcc = 4;
+static constexpr int kStemBuilders = 128;
+static constexpr int kStemEpiGroups = 2;
+static constexpr int kStemThreads = kStemBuilders + 32 + 128 * kStemEpiGroups;
+static constexpr int kPatchRows = 20, kPatchCols = 36, kPatchPitch = 40;   // bf16 elements
+static constexpr int kTileH = 8, kTileW = 16;
+
+struct StemParams {
+  const void* img; int img_dtype;
+  int batch, h, w;            // image size
+  int out_h, out_w;           // h/2, w/2
+  int tiles_w, tiles_h, num_tiles;
+  int BN, BNpad;              // out_c (multiple of 16) and its TMEM pitch
+  unsigned idesc, desc_hi, tmem_cols;
+  unsigned bias_bytes, b_bytes;
+  EpiParams epi;
+};
+
+struct __align__(8) StemShared {
+  uint64_t full[kStemStages];
+  uint64_t empty[kStemStages];
+  uint64_t tmem_full[kStemAcc];
+  uint64_t tmem_empty[kStemAcc];
+  uint64_t w_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <typename TI>
+__device__ __forceinline__ void load_pair(const TI* p, float& a, float& b);
+template <>
+__device__ __forceinline__ void load_pair<float>(const float* p, float& a, float& b) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  a = v.x; b = v.y;
+}
+template <>
+__device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, float& b) {
+  const uchar2 v = *reinterpret_cast<const uchar2*>(p);
+  a = (float)v.x; b = (float)v.y;
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  StemShared* sh = reinterpret_cast<StemShared*>(smem);
+  float* sbias = reinterpret_cast<float*>(smem + 1024);
+  uint32_t* patch = reinterpret_cast<uint32_t*>(smem + 1024 + p.bias_bytes);          // bf16 pairs
+  uint8_t* wsm = smem + 1024 + p.bias_bytes + 8192;                                    // [2][BN x 64] weights
+  uint8_t* astage = wsm + p.b_bytes;                                                   // [stages][2][128 x 64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool fp16 = (p.epi.dtype == YX_FP16);
+
+  for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x) sbias[i] = p.epi.bias[i];
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < kStemStages; ++i) { mbar_init(&sh->full[i], kStemBuilders); mbar_init(&sh->empty[i], 1); }
+    for (int i = 0; i < kStemAcc; ++i) { mbar_init(&sh->tmem_full[i], 1); mbar_init(&sh->tmem_empty[i], 128); }
+    mbar_init(&sh->w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(&sh->tmem_base, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp < 4) {
+    // ===================== A builders =====================
+    const int m = threadIdx.x;              // operand row = output pixel (hl, wl) of the tile
+    const int hl = m >> 4, wl = m & 15;
+    const TI* img = reinterpret_cast<const TI*>(p.img);
+    int stage = 0;
+    uint32_t phase = 0;
+    // each builder owns 9 (of 1080) 2-pixel words of the patch; the next tile's words are fetched
+    // into registers while the current tile's operand rows are being built
+    constexpr int kWordsPerThread = (3 * kPatchRows * (kPatchCols / 2) + kStemBuilders - 1) / kStemBuilders;
+    uint32_t pk[kWordsPerThread];
+    auto fetch = [&](int t) {
+      const int b = t / tiles_per_img;
+      const int r = t - b * tiles_per_img;
+      const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+      const int y0 = 2 * ty * kTileH - 2, x0 = 2 * tx * kTileW - 2;   // top-left of the input patch
+#pragma unroll
+      for (int j = 0; j < kWordsPerThread; ++j) {
+        const int i = m + j * kStemBuilders;
+        float a = 0.0f, bb = 0.0f;
+        if (i < 3 * kPatchRows * (kPatchCols / 2)) {
+          const int c = i / (kPatchRows * (kPatchCols / 2));
+          const int rr = (i / (kPatchCols / 2)) % kPatchRows;
+          const int xp = i % (kPatchCols / 2);
+          const int y = y0 + rr, x = x0 + 2 * xp;
+          if (y >= 0 && y < p.h && x >= 0 && x < p.w)       // zero outside the image = Conv2d padding
+            load_pair<TI>(img + (((long long)b * 3 + c) * p.h + y) * p.w + x, a, bb);
+        }
+        pk[j] = pack16(a, bb, fp16);
+      }
+    };
+    if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x);
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      // ---- 1. stage the 3 x 20 x 36 patch as 16-bit pairs
+      bar_sync_named(1, kStemBuilders);       // the previous tile's operand rows have been built
+#pragma unroll
+      for (int j = 0; j < kWordsPerThread; ++j) {
+        const int i = m + j * kStemBuilders;
+        if (i < 3 * kPatchRows * (kPatchCols / 2)) {
+          const int c = i / (kPatchRows * (kPatchCols / 2));
+          const int rr = (i / (kPatchCols / 2)) % kPatchRows;
+          const int xp = i % (kPatchCols / 2);
+          patch[(c * kPatchRows + rr) * (kPatchPitch / 2) + xp] = pk[j];
+        }
+      }
+      bar_sync_named(1, kStemBuilders);
+      if (t + (int)gridDim.x < p.num_tiles) fetch(t + gridDim.x);
+      // ---- 2. build operand row m: k = dy*18 + c*6 + dx  <->  patch[c][2*hl+dy][2*wl+dx]
+      mbar_wait(&sh->empty[stage], phase ^ 1);
+      uint8_t* a0 = astage + (size_t)stage * 32768 + (size_t)m * 128;
+      uint32_t wds[4];
+      int nw = 0, chunk = 0;
+#pragma unroll
+      for (int dy = 0; dy < 6; ++dy) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t* src = patch + (c * kPatchRows + 2 * hl + dy) * (kPatchPitch / 2) + wl;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            wds[nw++] = src[q];
+            if (nw == 4) {
+              uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+              nw = 0; ++chunk;
+            }
+          }
+        }
+      }
+      // 54 words written so far = 13 full chunks + 2 words; pad k = 108..127 with zeros
+      {
+        uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], 0u, 0u);
+        ++chunk;
+#pragma unroll
+        for (; chunk < 16; ++chunk) {
+          uint8_t* d2 = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
+          *reinterpret_cast<uint4*>(d2) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&sh->full[stage]);
+      if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // resident weights: two [BN x 64] K-major chunks
+      mbar_arrive_expect_tx(&sh->w_full, p.b_bytes);
+      tma_load_2d(&map_w, &sh->w_full, wsm, 0, 0);
+      tma_load_2d(&map_w, &sh->w_full, wsm + p.b_bytes / 2, 64, 0);
+      mbar_wait(&sh->w_full, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      const uint64_t hi = (uint64_t)p.desc_hi << 32;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        mbar_wait(&sh->tmem_empty[as], aphase ^ 1);
+        mbar_wait(&sh->full[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BNpad);
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          const uint32_t sa = smem_u32(astage + (size_t)stage * 32768 + (size_t)kc * 16384);
+          const uint32_t sb = smem_u32(wsm + (size_t)kc * (p.b_bytes / 2));
+          uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFF) | (1u << 16));
+          uint64_t bdesc = hi | (uint64_t)(((sb >> 4) & 0x3FFF) | (1u << 16));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            umma_f16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kc | j) != 0));
+            adesc += 2; bdesc += 2;
+          }
+        }
+        umma_commit(&sh->empty[stage]);
+        umma_commit(&sh->tmem_full[as]);
+        if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+        if (++as == kStemAcc) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int grp = (warp - 5) >> 2;
+    const int hl = row >> 4, wl = row & 15;
+    for (int it = grp;; it += kStemEpiGroups) {
+      const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tl >= p.num_tiles) break;
+      const int t = (int)tl;
+      const int as = it % kStemAcc;
+      const uint32_t aphase = (uint32_t)((it / kStemAcc) & 1);
+      const int b = t / tiles_per_img;
+      const int r = t - b * tiles_per_img;
+      const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+      const int ho = ty * kTileH + hl, wo = tx * kTileW + wl;
+      const bool valid = ho < p.out_h && wo < p.out_w;
+      mbar_wait(&sh->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
+      const long long pix = ((long long)b * p.out_h + ho) * p.out_w + wo;
+      uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld;
+      for (int c = 0; c < p.BN; c += 32) {
+        const bool two = (c + 16 < p.BN);
+        uint32_t ra[16], rb[16];
+        tmem_ld_x16(taddr + (uint32_t)c, ra);
+        if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
+        tmem_ld_wait();
+        if (valid) {
+          epi_tc_chunk(p.epi, ra, sbias + c, nullptr, fp16, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk(p.epi, rb, sbias + c + 16, nullptr, fp16, orow + c + 16, b, ho, wo, c + 16);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+struct StemLaunch {
+  CUtensorMap map_w;
+  StemParams p;
+  int grid;
+  size_t smem;
+};
+
+StemLaunch* stem_alloc() {
+  void* p = nullptr;
+  if (posix_memalign(&p, 64, sizeof(StemLaunch)) != 0) return nullptr;
+  memset(p, 0, sizeof(StemLaunch));
+  return reinterpret_cast<StemLaunch*>(p);
+}
+void stem_free(StemLaunch* p) { free(p); }
+
+int stem_prepare(const void* img, int img_dtype, const void* w, const float* bias, void* out, long long out_ld,
+                 int batch, int h, int wd, int out_c, int act, int dtype, StemLaunch* L) {
+  YX_REQUIRE(img && w && bias && out, YX_ERR_INVALID_ARG, "stem: null pointer");
+  YX_REQUIRE(img_dtype == YX_FP32 || img_dtype == YX_U8, YX_ERR_INVALID_ARG, "stem: image dtype must be fp32 or uint8");
+  YX_REQUIRE(dtype == YX_BF16 || dtype == YX_FP16, YX_ERR_INVALID_ARG, "stem: output dtype must be bf16/fp16");
+  YX_REQUIRE(batch > 0 && h > 0 && wd > 0 && h % 2 == 0 && wd % 2 == 0, YX_ERR_INVALID_ARG, "stem: H, W must be even");
+  YX_REQUIRE(out_c % 16 == 0 && out_c >= 16 && out_c <= 128, YX_ERR_UNSUPPORTED, "stem: out_c=%d (16..128, multiple of 16)", out_c);
+  YX_REQUIRE(out_ld % 16 == 0 && out_ld >= out_c && ((uintptr_t)out & 31) == 0, YX_ERR_INVALID_ARG, "stem: out misaligned");
+  YX_REQUIRE(((uintptr_t)img & 7) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0, YX_ERR_INVALID_ARG, "stem: pointer alignment");
+  EncodeTiledFn encode = get_encode_fn();
+  YX_REQUIRE(encode != nullptr, YX_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  StemParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.img = img; p.img_dtype = img_dtype; p.batch = batch; p.h = h; p.w = wd;
+  p.out_h = h / 2; p.out_w = wd / 2;
+  p.tiles_w = (p.out_w + kTileW - 1) / kTileW; p.tiles_h = (p.out_h + kTileH - 1) / kTileH;
+  p.num_tiles = batch * p.tiles_w * p.tiles_h;
+  p.BN = out_c;
+  p.BNpad = 32; while (p.BNpad < p.BN) p.BNpad <<= 1;
+  p.tmem_cols = (unsigned)(kStemAcc * p.BNpad);
+  const unsigned fmt = dtype == YX_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+  p.desc_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO = 8 rows * 128 B, version 1, SWIZZLE_128B
+  p.bias_bytes = ((unsigned)out_c * 4u + 1023u) & ~1023u;
+  p.b_bytes = 2u * (unsigned)out_c * 128u;                           // two [out_c x 64] chunks, multiples of 2 KB
+  EpiParams& e = p.epi;
+  e.out_h = p.out_h; e.out_w = p.out_w; e.out_c = out_c; e.act = act; e.dtype = dtype; e.epilogue = YX_EPI_STORE;
+  e.bias = bias; e.out = out; e.out_ld = out_ld;
+  L->smem = 2048 + p.bias_bytes + 8192 + p.b_bytes + (size_t)kStemStages * 32768;
+  const CUtensorMapDataType tdt = dtype == YX_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[2] = {128, (cuuint64_t)out_c};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {64, (cuuint32_t)out_c};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&L->map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(stem W) failed: %d", (int)r);
+  const int sms = num_sms();
+  L->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  return YX_OK;
+}
+
+int stem_launch(const StemLaunch* L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (L->p.img_dtype == YX_FP32)
+    stem_tc_kernel<float><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->p);
+  else
+    stem_tc_kernel<uint8_t><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->p);
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+}  // namespace yx

@@ -266,6 +266,52 @@ class Builder:
                                  bytes=img.numel() * img.element_size() + f.t.numel() * f.t.element_size(), tc=False))
         return f
 
+    def focus_conv(self, img: torch.Tensor, m, out: Optional[Feat] = None) -> Feat:
+        """Fused Focus + stem BaseConv `m` (3x3, stride 1) on the tensor cores (16-bit paths)."""
+        from .network_blocks import act_name
+
+        conv, bn = m.conv, m.bn
+        o = conv.weight.shape[0]
+        B, _, H, W = img.shape
+        key = (conv.weight.data_ptr(), conv.weight._version, "focus", self.dtype)
+        hit = self.weight_cache.get(key)
+        if hit is None:
+            # W6[o, c, 2u+py, 2v+px] = W[o, 3*(2*px+py)+c, u, v]; k = dy*18 + c*6 + dx; BN folded
+            # (model_utils.py:33-75). One-time weight preparation in fp32 torch ops.
+            wf = conv.weight.detach().float()
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+            w6 = torch.zeros((o, 3, 6, 6), dtype=torch.float32, device=wf.device)
+            for px in range(2):
+                for py in range(2):
+                    pidx = 2 * px + py
+                    w6[:, :, py::2, px::2] = wf[:, 3 * pidx:3 * pidx + 3]
+            w6 = w6 * scale[:, None, None, None]
+            packed = torch.zeros((pad16(o), 128), dtype=torch.float32, device=wf.device)
+            packed[:o, :108] = w6.permute(0, 2, 1, 3).reshape(o, 108)          # [o][dy][c][dx]
+            bias = torch.zeros((pad16(o),), dtype=torch.float32, device=self.dev)
+            bias[:o] = shift.to(self.dev)
+            hit = (packed.to(self.dev).to(self.dtype).contiguous(), bias)
+            self.keep += list(hit)
+            self.weight_cache[key] = hit
+        w, bias = hit
+        if out is None:
+            out = self.new_feat(B, H // 2, W // 2, [o])
+        ov = out.view()
+        args = (img.data_ptr(), dtype_code(img.dtype), w.data_ptr(), bias.data_ptr(), ov.ptr, ov.ld, B, H, W, ov.c,
+                ACT_CODES[act_name(m.act)], dtype_code(self.dtype))
+        if self.plan is not None:
+            check(lib().yx_plan_add_focus_conv(self.plan, *args), "plan_add_focus_conv")
+        else:
+            check(lib().yx_focus_conv_bn_act_fwd(*args, stream_ptr(self.dev)), "focus_conv")
+        self.n_ops += 1
+        fl = 2.0 * B * (H // 2) * (W // 2) * o * 108
+        self.flops += fl
+        self.op_info.append(dict(name=f"focus+conv3x3 3->{o} @{H // 2}x{W // 2}", flops=fl,
+                                 bytes=img.numel() * img.element_size() + B * (H // 2) * (W // 2) * ov.c * w.element_size(),
+                                 tc=True))
+        return out
+
     def postprocess(self, pred, nc, conf, nms, variant, inplace, dets, det_idx, det_count, max_det, ws):
         check(lib().yx_plan_add_postprocess(self.plan, pred.data_ptr(), pred.shape[0], pred.shape[1], nc, float(conf),
                                             float(nms), int(variant), 1 if inplace else 0, dets.data_ptr(),

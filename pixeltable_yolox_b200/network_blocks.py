@@ -203,4 +203,9 @@ class Focus(_B200Block):
         """img: NCHW fp32/uint8 image batch (raw 0..255)."""
         if img.shape[1] != 3:
             raise NotImplementedError("Focus on the B200 path expects a 3-channel image")
-        return self.conv.lower(b, b.focus(img), out=out)
+        conv = self.conv.conv
+        fused = (b.dtype != torch.float32 and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.groups == 1
+                 and conv.out_channels <= 128 and img.shape[2] % 2 == 0 and img.shape[3] % 2 == 0)
+        if fused:
+            return b.focus_conv(img, self.conv, out=out)      # one kernel: image -> stem activations
+        return self.conv.lower(b, b.focus(img), out=out)      # fp32 verification path: s2d + SIMT conv

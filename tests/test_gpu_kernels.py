@@ -107,6 +107,35 @@ def test_focus_space_to_depth(cuda, img_dtype, dtype):
     assert (out[..., 12:] == 0).all()
 
 
+@pytest.mark.parametrize("img_dtype", [torch.float32, torch.uint8])
+@pytest.mark.parametrize("dtype,cout", [(torch.bfloat16, 32), (torch.float16, 64), (torch.bfloat16, 24), (torch.bfloat16, 80)])
+def test_fused_focus_stem_matches_focus_then_conv(cuda, img_dtype, dtype, cout):
+    """The single-kernel Focus + 3x3 conv + BN + SiLU against the reference composition in torch fp32."""
+    from pixeltable_yolox_b200.engine import Builder
+    from pixeltable_yolox_b200.network_blocks import Focus
+
+    torch.manual_seed(cout)
+    blk = Focus(3, cout, ksize=3)
+    bn = blk.conv.bn
+    bn.eps = 1e-3
+    bn.running_mean.normal_(0, 20.0); bn.running_var.uniform_(500.0, 4000.0)
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.2)
+    blk.eval()
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (3, 3, 96, 160), generator=g).float()
+    with torch.no_grad():
+        want = blk._train_forward(img)                                       # [B, cout, 48, 80]
+    blk = blk.to(cuda).to(dtype)
+    b = Builder(cuda, dtype, use_plan=False)
+    got = blk.lower_image(b, img.to(img_dtype).to(cuda).contiguous()).to_nchw().float().cpu()
+    assert got.shape == want.shape
+    # the stem sums 108 products of 0..255 pixels with 16-bit weights: compare relative to the pre-activation scale
+    err = (got - want).abs() / want.abs().clamp_min(1.0)
+    tol = 4e-2 if dtype == torch.bfloat16 else 6e-3
+    assert err.max().item() <= tol, err.max().item()
+    assert err.mean().item() <= tol / 8
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 def test_spp_cascade_equals_maxpool_5_9_13(cuda, dtype):
     g = torch.Generator().manual_seed(2)
