@@ -8,12 +8,16 @@
 // nine 32-byte-row TMA gathers per pixel).
 //
 // GEMM view: M = output pixels (tile = 8 rows x 16 cols), K = 6*3*6 = 108 (zero padded to 128),
-// N = out_c.  TMA cannot build this operand (fp32/u8 source, channel-planar layout), so four
-// "builder" warps stage the tile's 20x36x3 input patch in shared memory as bf16/fp16 and write the
-// [128 x 128] K-major, 128B-swizzled A operand with ordinary 16-byte shared stores
-// (fence.proxy.async makes them visible to the tensor core).  The weights (out_c x 128) stay resident
-// in shared memory.  Roles: warps 0-3 build, warp 4 issues tcgen05.mma (TMEM accumulators, 4 stages),
-// warps 5-12 are two epilogue groups (bias + SiLU + 256-bit stores).
+// N = out_c.  TMA cannot build this operand directly (fp32/u8 source, channel-planar layout), so:
+//   warp 5      TMA-loads each tile's 3 x 20 x 36 input patch (one 4-D box of the NCHW image, zero
+//               filled outside the image = Conv2d padding) into a 4-deep ring, keeping ~35 KB of
+//               loads in flight per SM;
+//   warps 0-3   "builders": convert the patch to bf16/fp16 and write the [128 x 128] K-major,
+//               128B-swizzled A operand with 16-byte shared stores (fence.proxy.async publishes them
+//               to the tensor core);
+//   warp 4      issues tcgen05.mma against the weights (out_c x 128) resident in shared memory,
+//               accumulators in TMEM (4 stages);
+//   warps 6-13  two epilogue groups (bias + SiLU + 256-bit stores).
 #include <stdlib.h>
 #include <string.h>
 
@@ -25,8 +29,10 @@ static constexpr int kStemStages = 3;
 static constexpr int kStemAcc = 4;
 static constexpr int kStemBuilders = 128;
 static constexpr int kStemEpiGroups = 2;
-static constexpr int kStemThreads = kStemBuilders + 32 + 128 * kStemEpiGroups;
-static constexpr int kPatchRows = 20, kPatchCols = 36, kPatchPitch = 40;   // bf16 elements
+static constexpr int kStemThreads = kStemBuilders + 64 + 128 * kStemEpiGroups;   // + MMA warp + TMA warp
+static constexpr int kPatchRows = 20;
+static constexpr int kPatchStages = 4;
+static constexpr int kPatchStageBytes = 9600;      // 3*20*40 fp32 (u8: 3*20*64 = 3840), 128-byte multiple
 static constexpr int kTileH = 8, kTileW = 16;
 
 struct StemParams {
@@ -36,7 +42,8 @@ struct StemParams {
   int tiles_w, tiles_h, num_tiles;
   int BN, BNpad;              // out_c (multiple of 16) and its TMEM pitch
   unsigned idesc, desc_hi, tmem_cols;
-  unsigned bias_bytes, b_bytes;
+  unsigned bias_bytes, b_bytes, patch_tx;
+  int debug;
   EpiParams epi;
 };
 
@@ -46,6 +53,8 @@ struct __align__(8) StemShared {
   uint64_t tmem_full[kStemAcc];
   uint64_t tmem_empty[kStemAcc];
   uint64_t w_full;
+  uint64_t patch_full[kPatchStages];
+  uint64_t patch_empty[kPatchStages];
   uint32_t tmem_base;
 };
 
@@ -68,13 +77,15 @@ __device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, f
 
 template <typename TI>
 __global__ void __launch_bounds__(kStemThreads, 1)
-stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_img,
+               const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   StemShared* sh = reinterpret_cast<StemShared*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 1024);
-  uint32_t* patch = reinterpret_cast<uint32_t*>(smem + 1024 + p.bias_bytes);          // bf16 pairs
-  uint8_t* wsm = smem + 1024 + p.bias_bytes + 8192;                                    // [2][BN x 64] weights
+  uint8_t* patch = smem + 1024 + p.bias_bytes;                                         // [kPatchStages] raw patches
+  uint8_t* wsm = patch + kPatchStages * kPatchStageBytes;                              // [2][BN x 64] weights
+  wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wsm) + 1023) & ~uintptr_t(1023));
   uint8_t* astage = wsm + p.b_bytes;                                                   // [stages][2][128 x 64]
 
   const int warp = threadIdx.x >> 5;
@@ -87,6 +98,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
     for (int i = 0; i < kStemStages; ++i) { mbar_init(&sh->full[i], kStemBuilders); mbar_init(&sh->empty[i], 1); }
     for (int i = 0; i < kStemAcc; ++i) { mbar_init(&sh->tmem_full[i], 1); mbar_init(&sh->tmem_empty[i], 128); }
     mbar_init(&sh->w_full, 1);
+    for (int i = 0; i < kPatchStages; ++i) { mbar_init(&sh->patch_full[i], 1); mbar_init(&sh->patch_empty[i], kStemBuilders); }
+    tma_prefetch_desc(&map_img);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -103,49 +116,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
     // ===================== A builders =====================
     const int m = threadIdx.x;              // operand row = output pixel (hl, wl) of the tile
     const int hl = m >> 4, wl = m & 15;
-    const TI* img = reinterpret_cast<const TI*>(p.img);
     int stage = 0;
     uint32_t phase = 0;
-    // each builder owns 9 (of 1080) 2-pixel words of the patch; the next tile's words are fetched
-    // into registers while the current tile's operand rows are being built
-    constexpr int kWordsPerThread = (3 * kPatchRows * (kPatchCols / 2) + kStemBuilders - 1) / kStemBuilders;
-    uint32_t pk[kWordsPerThread];
-    auto fetch = [&](int t) {
-      const int b = t / tiles_per_img;
-      const int r = t - b * tiles_per_img;
-      const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
-      const int y0 = 2 * ty * kTileH - 2, x0 = 2 * tx * kTileW - 2;   // top-left of the input patch
-#pragma unroll
-      for (int j = 0; j < kWordsPerThread; ++j) {
-        const int i = m + j * kStemBuilders;
-        float a = 0.0f, bb = 0.0f;
-        if (i < 3 * kPatchRows * (kPatchCols / 2)) {
-          const int c = i / (kPatchRows * (kPatchCols / 2));
-          const int rr = (i / (kPatchCols / 2)) % kPatchRows;
-          const int xp = i % (kPatchCols / 2);
-          const int y = y0 + rr, x = x0 + 2 * xp;
-          if (y >= 0 && y < p.h && x >= 0 && x < p.w)       // zero outside the image = Conv2d padding
-            load_pair<TI>(img + (((long long)b * 3 + c) * p.h + y) * p.w + x, a, bb);
-        }
-        pk[j] = pack16(a, bb, fp16);
-      }
-    };
-    if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x);
+    int ps = 0;
+    uint32_t pphase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      // ---- 1. stage the 3 x 20 x 36 patch as 16-bit pairs
-      bar_sync_named(1, kStemBuilders);       // the previous tile's operand rows have been built
-#pragma unroll
-      for (int j = 0; j < kWordsPerThread; ++j) {
-        const int i = m + j * kStemBuilders;
-        if (i < 3 * kPatchRows * (kPatchCols / 2)) {
-          const int c = i / (kPatchRows * (kPatchCols / 2));
-          const int rr = (i / (kPatchCols / 2)) % kPatchRows;
-          const int xp = i % (kPatchCols / 2);
-          patch[(c * kPatchRows + rr) * (kPatchPitch / 2) + xp] = pk[j];
-        }
-      }
-      bar_sync_named(1, kStemBuilders);
-      if (t + (int)gridDim.x < p.num_tiles) fetch(t + gridDim.x);
+      // ---- 1. the tile's raw patch [3][20][pitch] (fp32: pitch 36, u8: pitch 48) arrives by TMA
+      mbar_wait(&sh->patch_full[ps], pphase);
+      const TI* pt = reinterpret_cast<const TI*>(patch + (size_t)ps * kPatchStageBytes);
+      // the box starts 16-byte aligned in global memory, kLead pixels left of the patch (TMA faults on
+      // a row start that is not a multiple of 16 bytes)
+      constexpr int kPitch = sizeof(TI) == 4 ? 40 : 64;
+      constexpr int kLead = sizeof(TI) == 4 ? 2 : 14;
       // ---- 2. build operand row m: k = dy*18 + c*6 + dx  <->  patch[c][2*hl+dy][2*wl+dx]
       mbar_wait(&sh->empty[stage], phase ^ 1);
       uint8_t* a0 = astage + (size_t)stage * 32768 + (size_t)m * 128;
@@ -155,10 +137,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
       for (int dy = 0; dy < 6; ++dy) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const uint32_t* src = patch + (c * kPatchRows + 2 * hl + dy) * (kPatchPitch / 2) + wl;
+          const TI* src = pt + (c * kPatchRows + 2 * hl + dy) * kPitch + kLead + 2 * wl;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            wds[nw++] = src[q];
+            float fa, fb;
+            load_pair<TI>(src + 2 * q, fa, fb);
+            wds[nw++] = pack16(fa, fb, fp16);
             if (nw == 4) {
               uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
               *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
@@ -178,6 +162,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
           *reinterpret_cast<uint4*>(d2) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
+      mbar_arrive(&sh->patch_empty[ps]);      // this thread is done with the raw patch
+      if (++ps == kPatchStages) { ps = 0; pphase ^= 1; }
       fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&sh->full[stage]);
       if (++stage == kStemStages) { stage = 0; phase ^= 1; }
@@ -216,11 +202,31 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const StemParams p) {
         if (++as == kStemAcc) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp == 5) {
+    // ===================== patch producer (TMA) =====================
+    if (lane == 0) {
+      int ps = 0;
+      uint32_t pphase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_img;
+        const int r = t - b * tiles_per_img;
+        const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+        mbar_wait(&sh->patch_empty[ps], pphase ^ 1);
+        if (p.debug & 1) {
+          mbar_arrive(&sh->patch_full[ps]);
+        } else {
+          mbar_arrive_expect_tx(&sh->patch_full[ps], p.patch_tx);
+          tma_load_4d(&map_img, &sh->patch_full[ps], patch + (size_t)ps * kPatchStageBytes,
+                      2 * tx * kTileW - (sizeof(TI) == 4 ? 4 : 16), 2 * ty * kTileH - 2, 0, b);
+        }
+        if (++ps == kPatchStages) { ps = 0; pphase ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue groups =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int grp = (warp - 5) >> 2;
+    const int grp = (warp - 6) >> 2;
     const int hl = row >> 4, wl = row & 15;
     for (int it = grp;; it += kStemEpiGroups) {
       const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -272,7 +278,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 
 struct StemLaunch {
-  CUtensorMap map_w;
+  CUtensorMap map_w, map_img;
   StemParams p;
   int grid;
   size_t smem;
@@ -294,7 +300,7 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
   YX_REQUIRE(batch > 0 && h > 0 && wd > 0 && h % 2 == 0 && wd % 2 == 0, YX_ERR_INVALID_ARG, "stem: H, W must be even");
   YX_REQUIRE(out_c % 16 == 0 && out_c >= 16 && out_c <= 128, YX_ERR_UNSUPPORTED, "stem: out_c=%d (16..128, multiple of 16)", out_c);
   YX_REQUIRE(out_ld % 16 == 0 && out_ld >= out_c && ((uintptr_t)out & 31) == 0, YX_ERR_INVALID_ARG, "stem: out misaligned");
-  YX_REQUIRE(((uintptr_t)img & 7) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0, YX_ERR_INVALID_ARG, "stem: pointer alignment");
+  YX_REQUIRE(((uintptr_t)img & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0, YX_ERR_INVALID_ARG, "stem: pointer alignment");
   EncodeTiledFn encode = get_encode_fn();
   YX_REQUIRE(encode != nullptr, YX_ERR_NO_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
   StemParams& p = L->p;
@@ -314,7 +320,23 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
   EpiParams& e = p.epi;
   e.out_h = p.out_h; e.out_w = p.out_w; e.out_c = out_c; e.act = act; e.dtype = dtype; e.epilogue = YX_EPI_STORE;
   e.bias = bias; e.out = out; e.out_ld = out_ld;
-  L->smem = 2048 + p.bias_bytes + 8192 + p.b_bytes + (size_t)kStemStages * 32768;
+  L->smem = 2048 + p.bias_bytes + (size_t)kPatchStages * kPatchStageBytes + 1024 + p.b_bytes + (size_t)kStemStages * 32768;
+  {
+    // the NCHW image as a 4-D tensor [W, H, 3, B]; one box = the 40 (u8: 64) x 20 x 3 window holding a tile's patch
+    const int es = img_dtype == YX_FP32 ? 4 : 1;
+    const cuuint32_t bw = img_dtype == YX_FP32 ? 40 : 64;   // patch is 36 wide; the box starts 16-byte aligned
+    YX_REQUIRE(((long long)wd * es) % 16 == 0, YX_ERR_UNSUPPORTED, "stem: image row pitch must be a multiple of 16 bytes");
+    cuuint64_t idims[4] = {(cuuint64_t)wd, (cuuint64_t)h, 3, (cuuint64_t)batch};
+    cuuint64_t istr[3] = {(cuuint64_t)wd * es, (cuuint64_t)wd * h * es, (cuuint64_t)wd * h * 3 * es};
+    cuuint32_t ibox[4] = {bw, (cuuint32_t)kPatchRows, 3, 1};
+    cuuint32_t iestr[4] = {1, 1, 1, 1};
+    CUresult ri = encode(&L->map_img, img_dtype == YX_FP32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                         const_cast<void*>(img), idims, istr, ibox, iestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YX_REQUIRE(ri == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(stem image) failed: %d", (int)ri);
+    p.patch_tx = bw * kPatchRows * 3 * es;
+    if (const char* e = getenv("YX_STEM_DEBUG")) p.debug = atoi(e);
+  }
   const CUtensorMapDataType tdt = dtype == YX_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t dims[2] = {128, (cuuint64_t)out_c};
   cuuint64_t strides[1] = {256};
@@ -336,9 +358,9 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
     attr_set = true;
   }
   if (L->p.img_dtype == YX_FP32)
-    stem_tc_kernel<float><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->p);
+    stem_tc_kernel<float><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->map_img, L->p);
   else
-    stem_tc_kernel<uint8_t><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->p);
+    stem_tc_kernel<uint8_t><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->map_img, L->p);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
