@@ -2,6 +2,7 @@
 // one YoloxModule.forward (yolox/models/yolox.py:72-92) + postprocess (utils/boxes.py:31-75),
 // enqueued from C++ in one FFI call and replayable as a CUDA graph.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -77,6 +78,15 @@ int num_sms() {
       cached = 148;
   }
   return cached;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 static int require_device() {

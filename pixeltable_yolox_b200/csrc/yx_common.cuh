@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached)
+bool pdl_enabled();  // programmatic dependent launch between consecutive plan kernels (YX_PDL=0 disables)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int dtype_size(int dt) { return dt == YX_FP32 ? 4 : (dt == YX_U8 ? 1 : 2); }
@@ -176,6 +177,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+
+// ---- programmatic dependent launch (PDL) ----
+// launch_dependents: the next kernel in the stream may start being scheduled (its prologue overlaps our
+// tail); wait: block until the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- numerics ----
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

@@ -104,6 +104,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias copy) touches only
+  // constants and overlaps the tail of the previous kernel; activations are read/written after the wait
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_k = p.ksize * p.ksize * p.kchunks;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -537,8 +541,18 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
-  conv_tc_kernel<<<L->grid, 64 + 128 * L->p.epi_groups, L->smem, stream>>>(L->map_a, L->map_b, L->p);
-  YX_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L->grid);
+  cfg.blockDim = dim3((unsigned)(64 + 128 * L->p.epi_groups));
+  cfg.dynamicSmemBytes = L->smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, L->map_a, L->map_b, L->p));
   return YX_OK;
 }
 

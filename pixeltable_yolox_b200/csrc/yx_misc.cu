@@ -122,12 +122,76 @@ __global__ void spp_kernel(T* __restrict__ buf, long long ld, int h, int w, int 
   }
 }
 
+// 16-bit fast path: one thread per pixel moves 8 channels as one 128-bit word; max is exact in
+// bf16/fp16, so the cascade runs on packed pairs (HMNMX2) straight from shared memory.
+template <typename T2>
+__device__ __forceinline__ uint4 max4(const uint4 a, const uint4 b) {
+  uint4 r;
+  const T2* pa = reinterpret_cast<const T2*>(&a);
+  const T2* pb = reinterpret_cast<const T2*>(&b);
+  T2* pr = reinterpret_cast<T2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(512) spp16_kernel(uint16_t* __restrict__ buf, long long ld, int h, int w, int c) {
+  extern __shared__ uint4 sp[];  // 2 slabs of h*w 128-bit words
+  const int hw = h * w;
+  uint4* cur = sp;
+  uint4* tmp = sp + hw;
+  const int groups = c / 8;
+  const int b = blockIdx.x / groups;
+  const int g = blockIdx.x - b * groups;
+  uint16_t* base = buf + (long long)b * hw * ld + g * 8;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) cur[i] = *reinterpret_cast<const uint4*>(base + (long long)i * ld);
+  __syncthreads();
+  for (int level = 1; level <= 3; ++level) {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // horizontal 5-max (window clipped = -inf padding)
+      const int y = i / w, x = i - y * w;
+      uint4 m = cur[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int xx = x + d;
+        if (d != 0 && xx >= 0 && xx < w) m = max4<T2>(m, cur[y * w + xx]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // vertical 5-max
+      const int y = i / w, x = i - y * w;
+      uint4 m = tmp[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int yy = y + d;
+        if (d != 0 && yy >= 0 && yy < h) m = max4<T2>(m, tmp[yy * w + x]);
+      }
+      cur[i] = m;   // each thread only overwrites its own pixel; others read tmp
+      *reinterpret_cast<uint4*>(base + (long long)i * ld + (long long)level * c) = m;
+    }
+    __syncthreads();
+  }
+}
+
 int spp_launch(void* buf, long long ld, int batch, int h, int w, int c, int dtype, cudaStream_t s) {
   YX_REQUIRE(buf, YX_ERR_INVALID_ARG, "spp: null buffer");
   YX_REQUIRE(c % 8 == 0 && ld >= 4 * (long long)c, YX_ERR_INVALID_ARG, "spp: c %% 8 != 0 or ld < 4c");
+  const unsigned grid = (unsigned)(batch * (c / 8));
+  if (dtype != YX_FP32 && (size_t)2 * h * w * 16 <= 200 * 1024 && ld % 8 == 0 && ((uintptr_t)buf & 15) == 0) {
+    const size_t sm16 = (size_t)2 * h * w * 16;
+    if (dtype == YX_BF16) {
+      if (sm16 > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp16_kernel<__nv_bfloat162>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+      spp16_kernel<__nv_bfloat162><<<grid, 512, sm16, s>>>((uint16_t*)buf, ld, h, w, c);
+    } else {
+      if (sm16 > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp16_kernel<__half2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+      spp16_kernel<__half2><<<grid, 512, sm16, s>>>((uint16_t*)buf, ld, h, w, c);
+    }
+    YX_CUDA(cudaGetLastError());
+    return YX_OK;
+  }
   const size_t smem = (size_t)3 * h * w * 8 * sizeof(float);
   YX_REQUIRE(smem <= 200 * 1024, YX_ERR_UNSUPPORTED, "spp: feature map %dx%d too large for the shared-memory slab", h, w);
-  const unsigned grid = (unsigned)(batch * (c / 8));
 #define YX_SPP(T)                                                                                   \
   do {                                                                                              \
     if (smem > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -55,48 +55,64 @@ filter_kernel(float* __restrict__ pred, int batch, int anchors, int nc, float co
   const int wi = warp_global - b * warps_per_img;
   if (b >= batch) return;
   const int nch = 5 + nc;
-  for (int a = wi; a < anchors; a += warps_per_img) {
-    float* row = pred + ((long long)b * anchors + a) * nch;
-    // arg-max over the class columns: lane handles classes lane, lane+32, ...
-    float best = -INFINITY;
-    int best_i = 0x7fffffff;
-    for (int c = lane; c < nc; c += 32) {
-      const float v = row[5 + c];
-      // torch.max semantics: first occurrence of the maximum; NaN propagates as the maximum
-      const bool take = (best_i == 0x7fffffff) || (!(best != best) && ((v != v) || v > best));
-      if (take) { best = v; best_i = c; }
+  constexpr int U = 4;   // anchors in flight per warp: the loads of all U rows are issued before any reduction
+  for (int a0 = wi * U; a0 < anchors; a0 += warps_per_img * U) {
+    float v0[U], v1[U], v2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int a = a0 + u;
+      const float* row = pred + ((long long)b * anchors + min(a, anchors - 1)) * nch;
+      v0[u] = lane < nc ? row[5 + lane] : -INFINITY;
+      v1[u] = lane + 32 < nc ? row[5 + lane + 32] : -INFINITY;
+      v2[u] = lane + 64 < nc ? row[5 + lane + 64] : -INFINITY;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-      const bool other_nan = (ov != ov), mine_nan = (best != best);
-      bool take;
-      if (oi == 0x7fffffff) take = false;
-      else if (best_i == 0x7fffffff) take = true;
-      else if (other_nan != mine_nan) take = other_nan;
-      else if (other_nan) take = oi < best_i;
-      else take = (ov > best) || (ov == best && oi < best_i);
-      if (take) { best = ov; best_i = oi; }
-    }
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    float obj = 0.f;
-    if (lane == 0) {
-      const float cx = row[0], cy = row[1], w = row[2], h = row[3];
-      obj = row[4];
-      const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-      box.x = __fsub_rn(cx, hw); box.y = __fsub_rn(cy, hh);
-      box.z = __fadd_rn(cx, hw); box.w = __fadd_rn(cy, hh);
-      const float score = __fmul_rn(obj, best);
-      if (inplace_xyxy) { row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; }
-      float4* crow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + a) * 8);
-      crow[0] = box;
-      crow[1] = make_float4(obj, best, (float)best_i, score);
-      if (score >= conf_thre) {
-        const int slot = atomicAdd(&counts[b], 1);
-        const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
-        keys[(long long)b * anchors + slot] =
-            ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)a;
+    for (int u = 0; u < U; ++u) {
+      const int a = a0 + u;
+      if (a >= anchors) break;
+      float* row = pred + ((long long)b * anchors + a) * nch;
+      // arg-max over the class columns (torch.max: first occurrence of the maximum; NaN wins)
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+      auto consider = [&](float v, int c) {
+        if (c < nc) {
+          const bool take = (best_i == 0x7fffffff) || (!(best != best) && ((v != v) || v > best));
+          if (take) { best = v; best_i = c; }
+        }
+      };
+      consider(v0[u], lane); consider(v1[u], lane + 32); consider(v2[u], lane + 64);
+      for (int c = lane + 96; c < nc; c += 32) consider(row[5 + c], c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        const bool other_nan = (ov != ov), mine_nan = (best != best);
+        bool take;
+        if (oi == 0x7fffffff) take = false;
+        else if (best_i == 0x7fffffff) take = true;
+        else if (other_nan != mine_nan) take = other_nan;
+        else if (other_nan) take = oi < best_i;
+        else take = (ov > best) || (ov == best && oi < best_i);
+        if (take) { best = ov; best_i = oi; }
+      }
+      if (lane == 0) {
+        const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+        const float obj = row[4];
+        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+        float4 box;
+        box.x = __fsub_rn(cx, hw); box.y = __fsub_rn(cy, hh);
+        box.z = __fadd_rn(cx, hw); box.w = __fadd_rn(cy, hh);
+        const float score = __fmul_rn(obj, best);
+        if (inplace_xyxy) { row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; }
+        float4* crow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + a) * 8);
+        crow[0] = box;
+        crow[1] = make_float4(obj, best, (float)best_i, score);
+        if (score >= conf_thre) {
+          const int slot = atomicAdd(&counts[b], 1);
+          const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
+          keys[(long long)b * anchors + slot] =
+              ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)a;
+        }
       }
     }
   }

@@ -9,15 +9,15 @@
 //
 // GEMM view: M = output pixels (tile = 8 rows x 16 cols), K = 6*3*6 = 108 (zero padded to 128),
 // N = out_c.  TMA cannot build this operand directly (fp32/u8 source, channel-planar layout), so:
-//   warp 5      TMA-loads each tile's 3 x 20 x 36 input patch (one 4-D box of the NCHW image, zero
+//   warp 9      TMA-loads each tile's 3 x 20 x 36 input patch (one 4-D box of the NCHW image, zero
 //               filled outside the image = Conv2d padding) into a 4-deep ring, keeping ~35 KB of
 //               loads in flight per SM;
-//   warps 0-3   "builders": convert the patch to bf16/fp16 and write the [128 x 128] K-major,
+//   warps 0-7   two groups of "builders" (alternating tiles): convert the patch to bf16/fp16 and write the [128 x 128] K-major,
 //               128B-swizzled A operand with 16-byte shared stores (fence.proxy.async publishes them
 //               to the tensor core);
-//   warp 4      issues tcgen05.mma against the weights (out_c x 128) resident in shared memory,
+//   warp 8      issues tcgen05.mma against the weights (out_c x 128) resident in shared memory,
 //               accumulators in TMEM (4 stages);
-//   warps 6-13  two epilogue groups (bias + SiLU + 256-bit stores).
+//   warps 10-17 two epilogue groups (bias + SiLU + 256-bit stores).
 #include <stdlib.h>
 #include <string.h>
 
@@ -27,9 +27,11 @@ namespace yx {
 
 static constexpr int kStemStages = 3;
 static constexpr int kStemAcc = 4;
-static constexpr int kStemBuilders = 128;
+static constexpr int kStemBuilders = 128;            // threads per builder group (one operand row each)
+static constexpr int kStemBuilderGroups = 2;         // tiles alternate between the groups
 static constexpr int kStemEpiGroups = 2;
-static constexpr int kStemThreads = kStemBuilders + 64 + 128 * kStemEpiGroups;   // + MMA warp + TMA warp
+static constexpr int kStemThreads = kStemBuilders * kStemBuilderGroups + 64 + 128 * kStemEpiGroups;   // + MMA warp + TMA warp
+static constexpr int kWarpMma = kStemBuilders * kStemBuilderGroups / 32, kWarpTma = kWarpMma + 1, kWarpEpi = kWarpMma + 2;
 static constexpr int kPatchRows = 20;
 static constexpr int kPatchStages = 4;
 static constexpr int kPatchStageBytes = 9600;      // 3*20*40 fp32 (u8: 3*20*64 = 3840), 128-byte multiple
@@ -102,7 +104,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     tma_prefetch_desc(&map_img);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kWarpMma) {
     tmem_alloc(&sh->tmem_base, p.tmem_cols);
     tmem_relinquish();
   }
@@ -110,17 +112,22 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias copy) touches only
+  // constants and overlaps the tail of the previous kernel; activations are read/written after the wait
+  pdl_launch_dependents();
+  pdl_wait();
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-  if (warp < 4) {
+  if (warp < kWarpMma) {
     // ===================== A builders =====================
-    const int m = threadIdx.x;              // operand row = output pixel (hl, wl) of the tile
+    const int m = threadIdx.x & (kStemBuilders - 1);   // operand row = output pixel (hl, wl) of the tile
     const int hl = m >> 4, wl = m & 15;
-    int stage = 0;
-    uint32_t phase = 0;
-    int ps = 0;
-    uint32_t pphase = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const int bgrp = threadIdx.x / kStemBuilders;
+    for (int it = bgrp;; it += kStemBuilderGroups) {
+      const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tl >= p.num_tiles) break;
+      const int stage = it % kStemStages, ps = it % kPatchStages;
+      const uint32_t phase = (uint32_t)((it / kStemStages) & 1), pphase = (uint32_t)((it / kPatchStages) & 1);
       // ---- 1. the tile's raw patch [3][20][pitch] (fp32: pitch 36, u8: pitch 48) arrives by TMA
       mbar_wait(&sh->patch_full[ps], pphase);
       const TI* pt = reinterpret_cast<const TI*>(patch + (size_t)ps * kPatchStageBytes);
@@ -163,12 +170,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         }
       }
       mbar_arrive(&sh->patch_empty[ps]);      // this thread is done with the raw patch
-      if (++ps == kPatchStages) { ps = 0; pphase ^= 1; }
       fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&sh->full[stage]);
-      if (++stage == kStemStages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 4) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // resident weights: two [BN x 64] K-major chunks
@@ -202,7 +207,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (++as == kStemAcc) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpTma) {
     // ===================== patch producer (TMA) =====================
     if (lane == 0) {
       int ps = 0;
@@ -226,7 +231,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // ===================== epilogue groups =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int grp = (warp - 6) >> 2;
+    const int grp = (warp - kWarpEpi) >> 2;
     const int hl = row >> 4, wl = row & 15;
     for (int it = grp;; it += kStemEpiGroups) {
       const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -262,7 +267,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -357,11 +362,21 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
     YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L->grid);
+  cfg.blockDim = dim3((unsigned)kStemThreads);
+  cfg.dynamicSmemBytes = L->smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   if (L->p.img_dtype == YX_FP32)
-    stem_tc_kernel<float><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->map_img, L->p);
+    YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, L->map_w, L->map_img, L->p));
   else
-    stem_tc_kernel<uint8_t><<<L->grid, kStemThreads, L->smem, stream>>>(L->map_w, L->map_img, L->p);
-  YX_CUDA(cudaGetLastError());
+    YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t>, L->map_w, L->map_img, L->p));
   return YX_OK;
 }
 
