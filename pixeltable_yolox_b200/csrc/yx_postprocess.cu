@@ -45,76 +45,68 @@ __device__ __forceinline__ uint32_t orderable(float f) {
 // ------------------------------------------------------------------------------------------
 // Stage 1
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static constexpr int kFilterAnchors = 128;   // anchors per CTA (one per thread)
+
+// One CTA stages 128 consecutive rows of [5+nc] floats in shared memory with coalesced (128-bit when
+// aligned) loads; then every thread owns one anchor: sequential arg-max over its row (row pitch 5+nc is
+// odd for nc = 80, so the strided shared reads are conflict free), box conversion, score, and one
+// warp-aggregated append of the passing anchors' sort keys.
+__global__ void __launch_bounds__(kFilterAnchors)
 filter_kernel(float* __restrict__ pred, int batch, int anchors, int nc, float conf_thre, int inplace_xyxy,
               float* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int warps_per_img = gridDim.x * (blockDim.x >> 5) / batch;  // grid is a multiple of batch
-  const int b = warp_global / warps_per_img;
-  const int wi = warp_global - b * warps_per_img;
-  if (b >= batch) return;
+  extern __shared__ float frows[];                        // [kFilterAnchors][5+nc]
   const int nch = 5 + nc;
-  constexpr int U = 4;   // anchors in flight per warp: the loads of all U rows are issued before any reduction
-  for (int a0 = wi * U; a0 < anchors; a0 += warps_per_img * U) {
-    float v0[U], v1[U], v2[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int a = a0 + u;
-      const float* row = pred + ((long long)b * anchors + min(a, anchors - 1)) * nch;
-      v0[u] = lane < nc ? row[5 + lane] : -INFINITY;
-      v1[u] = lane + 32 < nc ? row[5 + lane + 32] : -INFINITY;
-      v2[u] = lane + 64 < nc ? row[5 + lane + 64] : -INFINITY;
+  const int chunks = (anchors + kFilterAnchors - 1) / kFilterAnchors;
+  const int b = blockIdx.x / chunks;
+  const int a0 = (blockIdx.x - b * chunks) * kFilterAnchors;
+  const int na = min(kFilterAnchors, anchors - a0);
+  const int tid = threadIdx.x, lane = tid & 31;
+  float* g = pred + ((long long)b * anchors + a0) * nch;
+  const int total = na * nch;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* s4 = reinterpret_cast<float4*>(frows);
+    for (int i = tid; i < total / 4; i += kFilterAnchors) s4[i] = g4[i];
+    for (int i = (total & ~3) + tid; i < total; i += kFilterAnchors) frows[i] = g[i];
+  } else {
+    for (int i = tid; i < total; i += kFilterAnchors) frows[i] = g[i];
+  }
+  __syncthreads();
+  bool pass = false;
+  unsigned long long key = 0;
+  if (tid < na) {
+    const float* row = frows + tid * nch;
+    // torch.max(dim): first occurrence of the maximum; a NaN wins and the first NaN is reported
+    float best = row[5];
+    int best_i = 0;
+    for (int c = 1; c < nc; ++c) {
+      const float v = row[5 + c];
+      if (!(best != best) && (v > best || v != v)) { best = v; best_i = c; }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int a = a0 + u;
-      if (a >= anchors) break;
-      float* row = pred + ((long long)b * anchors + a) * nch;
-      // arg-max over the class columns (torch.max: first occurrence of the maximum; NaN wins)
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
-      auto consider = [&](float v, int c) {
-        if (c < nc) {
-          const bool take = (best_i == 0x7fffffff) || (!(best != best) && ((v != v) || v > best));
-          if (take) { best = v; best_i = c; }
-        }
-      };
-      consider(v0[u], lane); consider(v1[u], lane + 32); consider(v2[u], lane + 64);
-      for (int c = lane + 96; c < nc; c += 32) consider(row[5 + c], c);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        const bool other_nan = (ov != ov), mine_nan = (best != best);
-        bool take;
-        if (oi == 0x7fffffff) take = false;
-        else if (best_i == 0x7fffffff) take = true;
-        else if (other_nan != mine_nan) take = other_nan;
-        else if (other_nan) take = oi < best_i;
-        else take = (ov > best) || (ov == best && oi < best_i);
-        if (take) { best = ov; best_i = oi; }
-      }
-      if (lane == 0) {
-        const float cx = row[0], cy = row[1], w = row[2], h = row[3];
-        const float obj = row[4];
-        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-        float4 box;
-        box.x = __fsub_rn(cx, hw); box.y = __fsub_rn(cy, hh);
-        box.z = __fadd_rn(cx, hw); box.w = __fadd_rn(cy, hh);
-        const float score = __fmul_rn(obj, best);
-        if (inplace_xyxy) { row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; }
-        float4* crow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + a) * 8);
-        crow[0] = box;
-        crow[1] = make_float4(obj, best, (float)best_i, score);
-        if (score >= conf_thre) {
-          const int slot = atomicAdd(&counts[b], 1);
-          const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
-          keys[(long long)b * anchors + slot] =
-              ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)a;
-        }
-      }
+    const float cx = row[0], cy = row[1], w = row[2], h = row[3], obj = row[4];
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    float4 box;
+    box.x = __fsub_rn(cx, hw); box.y = __fsub_rn(cy, hh);
+    box.z = __fadd_rn(cx, hw); box.w = __fadd_rn(cy, hh);
+    const float score = __fmul_rn(obj, best);
+    const int a = a0 + tid;
+    if (inplace_xyxy) {
+      float* grow = g + (long long)tid * nch;
+      grow[0] = box.x; grow[1] = box.y; grow[2] = box.z; grow[3] = box.w;
     }
+    float4* crow = reinterpret_cast<float4*>(cand + ((long long)b * anchors + a) * 8);
+    crow[0] = box;
+    crow[1] = make_float4(obj, best, (float)best_i, score);
+    pass = score >= conf_thre;
+    const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
+    key = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)a;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, pass);
+  if (bal) {
+    int base = 0;
+    if (lane == (__ffs(bal) - 1)) base = atomicAdd(&counts[b], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (pass) keys[(long long)b * anchors + base + __popc(bal & ((1u << lane) - 1))] = key;
   }
 }
 
@@ -569,11 +561,16 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
 int filter_launch(float* pred, int batch, int anchors, int nc, float conf_thre, int inplace_xyxy, const PostWs& w,
                   cudaStream_t s) {
   YX_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * 4, s));
-  // 8 warps per block; blocks per image chosen so that each warp handles ~8 anchors
-  int blocks_per_img = (anchors + 63) / 64;
-  if (blocks_per_img < 1) blocks_per_img = 1;
-  filter_kernel<<<batch * blocks_per_img, 256, 0, s>>>(pred, batch, anchors, nc, conf_thre, inplace_xyxy, w.cand,
-                                                       w.keys, w.counts);
+  const int chunks = (anchors + kFilterAnchors - 1) / kFilterAnchors;
+  const size_t smem = (size_t)kFilterAnchors * (5 + nc) * sizeof(float);
+  YX_REQUIRE(smem <= 200 * 1024, YX_ERR_UNSUPPORTED, "postprocess: %d classes exceed the shared-memory row staging", nc);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    YX_CUDA(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  filter_kernel<<<batch * chunks, kFilterAnchors, smem, s>>>(pred, batch, anchors, nc, conf_thre, inplace_xyxy, w.cand,
+                                                             w.keys, w.counts);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
