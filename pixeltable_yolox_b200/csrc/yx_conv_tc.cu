@@ -49,10 +49,22 @@ struct ConvTcParams {
   unsigned bias_bytes;   // shared-memory copy of the bias vector (out_c floats, rounded to 1 KB)
   unsigned head_bytes;   // YX_EPI_HEAD: per-warp [32][5+nc] fp32 staging for coalesced row stores
   int epi_groups;        // 1..kMaxEpiGroups
+  // ---- halo mode (3x3 stride 1): one TMA halo tile per channel chunk, the 9 taps are row-shifted
+  //      UMMA descriptors into it; weights resident in smem or shared by G consecutive M tiles
+  int halo;
+  int pitch;             // accumulator rows per tile row (= tw + 2 in halo mode, = tw otherwise)
+  int G;                 // M tiles per weight stage
+  int m_tiles;           // real M tiles; m_tiles_pad = ceil(m_tiles / G) * G
+  int a_slots;           // halo ring depth
+  unsigned a_slot_bytes, a_tx_bytes, row_bytes;
+  int b_resident;        // all 9*kchunks weight tiles stay in smem (n_tiles == 1)
+  unsigned b_tile_bytes, b_tx_bytes, b_region_bytes;
+  int base_off;          // 1: set the descriptor base-offset field from the shifted start address
   EpiParams epi;
 };
 
-static constexpr int kMaxStages = 8;
+static constexpr int kMaxStages = 12;
+static constexpr int kMaxASlots = 8;
 static constexpr int kMaxAcc = 4;
 static constexpr int kMaxEpiGroups = 3;           // epilogue warpgroups (4 warps each); tiles alternate between them
 static constexpr int kMaxThreads = 64 + 128 * kMaxEpiGroups;
@@ -62,8 +74,48 @@ struct __align__(8) TcShared {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[kMaxAcc];
   uint64_t tmem_empty[kMaxAcc];
+  uint64_t afull[kMaxASlots];
+  uint64_t aempty[kMaxASlots];
+  uint64_t bres_full;
   uint32_t tmem_base;
 };
+
+
+// ---- halo-mode MMA issue helpers (run by the one elected lane of the MMA warp) ----
+// resident weights, one M tile: 9 taps x KS k-steps, descriptors advance by compile-time constants
+template <int KS>
+__device__ __forceinline__ void halo_issue_res(uint64_t ad, uint32_t dt, uint64_t bd, uint32_t btile16, uint32_t idesc,
+                                               uint32_t acc0, uint32_t rb16, uint32_t prb16) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint64_t a = ad + (uint64_t)((uint32_t)(tap / 3) * prb16 + (uint32_t)(tap % 3) * rb16);
+    const uint64_t b = bd + (uint64_t)((uint32_t)tap * btile16);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) umma_f16(dt, a + 2 * j, b + 2 * j, idesc, (tap | j) ? 1u : acc0);
+  }
+}
+// streamed weights (ring of `n_bs` stages), one or two M tiles sharing every weight stage
+template <int KS, bool TWO>
+__device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint64_t ad1, uint32_t dt0, uint32_t dt1,
+                                                uint64_t bd0, uint32_t btile16, uint32_t idesc, uint32_t acc0,
+                                                uint32_t rb16, uint32_t prb16, int& sb, uint32_t& pb, int n_bs) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    mbar_wait(&sh->full[sb], pb);
+    tc_fence_after();
+    const uint64_t sh16 = (uint64_t)((uint32_t)(tap / 3) * prb16 + (uint32_t)(tap % 3) * rb16);
+    const uint64_t b = bd0 + (uint64_t)((uint32_t)sb * btile16);
+    const uint32_t accf = tap ? 1u : acc0;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) umma_f16(dt0, ad0 + sh16 + 2 * j, b + 2 * j, idesc, j ? 1u : accf);
+    if (TWO) {
+#pragma unroll
+      for (int j = 0; j < KS; ++j) umma_f16(dt1, ad1 + sh16 + 2 * j, b + 2 * j, idesc, j ? 1u : accf);
+    }
+    umma_commit(&sh->empty[sb]);
+    if (++sb == n_bs) { sb = 0; pb ^= 1; }
+  }
+}
 
 
 __global__ void __launch_bounds__(kMaxThreads, 1)
@@ -94,6 +146,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&sh->tmem_full[i], 1);
       mbar_init(&sh->tmem_empty[i], 128);
     }
+    for (int i = 0; i < p.a_slots; ++i) {
+      mbar_init(&sh->afull[i], 1);
+      mbar_init(&sh->aempty[i], 1);
+    }
+    mbar_init(&sh->bres_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -111,8 +168,137 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int num_k = p.ksize * p.ksize * p.kchunks;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // halo mode: the CTA owns the contiguous unit range [t_begin, t_end) of the order
+  //   t = (mblock * n_tiles + n_tile) * G + i,   m_tile = mblock * G + i
+  // so that up to G consecutive units share one weight tile; all three roles walk it identically
+  const long long T_units = (long long)p.num_tiles;
+  const int t_begin = (int)(T_units * blockIdx.x / gridDim.x);
+  const int t_end = (int)(T_units * (blockIdx.x + 1) / gridDim.x);
+  uint8_t* const bregion = tiles;                       // weight ring or resident weights
+  uint8_t* const aregion = tiles + p.b_region_bytes;    // halo ring
 
-  if (warp == 0) {
+  if (p.halo && warp == 0) {
+    // ===================== TMA producer (halo mode) =====================
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_arrive_expect_tx(&sh->bres_full, p.b_tx_bytes * 9u * (unsigned)p.kchunks);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int c = 0; c < p.kchunks; ++c)
+            tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)(c * 9 + tap) * p.b_tile_bytes,
+                        tap * p.in_c + c * p.KC, 0);
+      }
+      int ca = 0, sb = 0;
+      uint32_t pb = 0;
+      for (int t = t_begin; t < t_end;) {
+        const int i0 = t % p.G;
+        const int u = t / p.G;
+        const int n_tile = u % p.n_tiles;
+        const int mblock = u / p.n_tiles;
+        int g = p.G - i0;
+        if (g > t_end - t) g = t_end - t;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int i = 0; i < g; ++i, ++ca) {
+            const int m_tile = mblock * p.G + i0 + i;
+            const int b = m_tile / tiles_per_img;          // >= batch for padding tiles: TMA zero-fills
+            const int r = m_tile - b * tiles_per_img;
+            const int ty = r / p.tiles_w;
+            const int tx = r - ty * p.tiles_w;
+            const int slot = ca % p.a_slots;
+            mbar_wait(&sh->aempty[slot], (uint32_t)(((ca / p.a_slots) & 1) ^ 1));
+            mbar_arrive_expect_tx(&sh->afull[slot], p.a_tx_bytes);
+            tma_load_4d(&map_a, &sh->afull[slot], aregion + (size_t)slot * p.a_slot_bytes, c * p.KC,
+                        tx * p.tw - 1, ty * p.th - 1, b);
+          }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&sh->empty[sb], pb ^ 1);
+              mbar_arrive_expect_tx(&sh->full[sb], p.b_tx_bytes);
+              tma_load_2d(&map_b, &sh->full[sb], bregion + (size_t)sb * p.b_tile_bytes, tap * p.in_c + c * p.KC,
+                          n_tile * p.BN);
+              if (++sb == p.stages) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+        t += g;
+      }
+    }
+  } else if (p.halo && warp == 1) {
+    // ===================== MMA issuer (halo mode) =====================
+    // The whole warp walks the (warp-uniform) loop and one elected lane issues: a divergent single-thread
+    // loop costs ~5 cycles per scalar instruction, which is more than a 128xNx16 MMA for N <= 64.
+    const uint32_t rb16 = p.row_bytes >> 4;
+    const uint32_t prb16 = (uint32_t)p.pitch * rb16;
+    const uint32_t a0 = smem_u32(aregion) >> 4, aslot16 = p.a_slot_bytes >> 4;
+    const uint32_t b0 = smem_u32(bregion) >> 4, btile16 = p.b_tile_bytes >> 4;
+    const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);   // LBO = 1 in the low word
+    const uint32_t idesc = p.idesc;
+    const int ksteps = p.KC >> 4;
+    const int G = p.G, n_acc = p.acc_stages, n_as = p.a_slots, n_bs = p.stages, kch = p.kchunks;
+    const bool ring = !p.b_resident;
+    int sa = 0, sb = 0, as = 0, i0 = t_begin % G;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    if (!ring) mbar_wait(&sh->bres_full, 0);
+    for (int t = t_begin; t < t_end;) {
+      int g = G - i0;
+      if (g > t_end - t) g = t_end - t;
+      i0 = 0;
+      uint32_t dt0, dt1 = 0;
+      const int st0 = as;
+      mbar_wait(&sh->tmem_empty[as], pacc ^ 1);
+      dt0 = tmem_base + (uint32_t)(as * p.BNpad);
+      if (++as == n_acc) { as = 0; pacc ^= 1; }
+      const int st1 = as;
+      if (g > 1) {
+        mbar_wait(&sh->tmem_empty[as], pacc ^ 1);
+        dt1 = tmem_base + (uint32_t)(as * p.BNpad);
+        if (++as == n_acc) { as = 0; pacc ^= 1; }
+      }
+      tc_fence_after();
+      uint32_t bres = b0;
+      for (int c = 0; c < kch; ++c) {
+        const int sl0 = sa;
+        mbar_wait(&sh->afull[sa], pa);
+        const uint32_t al0 = a0 + (uint32_t)sa * aslot16;
+        if (++sa == n_as) { sa = 0; pa ^= 1; }
+        const int sl1 = sa;
+        uint32_t al1 = 0;
+        if (g > 1) {
+          mbar_wait(&sh->afull[sa], pa);
+          al1 = a0 + (uint32_t)sa * aslot16;
+          if (++sa == n_as) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one_sync()) {
+          // one straight-line block per chunk: descriptors advance by constants, no branches between MMAs
+          const uint64_t ad0 = dhi | (uint64_t)al0, ad1 = dhi | (uint64_t)al1;
+          const uint32_t acc0 = (uint32_t)(c != 0);
+          if (ring) {
+#define YX_RING(KS, TWO) halo_issue_ring<KS, TWO>(sh, ad0, ad1, dt0, dt1, dhi | (uint64_t)b0, btile16, idesc, acc0, rb16, prb16, sb, pb, n_bs)
+            if (g > 1) {
+              if (ksteps == 4) YX_RING(4, true); else if (ksteps == 2) YX_RING(2, true); else YX_RING(1, true);
+            } else {
+              if (ksteps == 4) YX_RING(4, false); else if (ksteps == 2) YX_RING(2, false); else YX_RING(1, false);
+            }
+#undef YX_RING
+          } else {
+            const uint64_t bd = dhi | (uint64_t)bres;
+            if (ksteps == 4) halo_issue_res<4>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
+            else if (ksteps == 2) halo_issue_res<2>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
+            else halo_issue_res<1>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
+          }
+          umma_commit(&sh->aempty[sl0]);
+          if (g > 1) umma_commit(&sh->aempty[sl1]);
+        }
+        __syncwarp();
+        bres += 9u * btile16;
+      }
+      if (elect_one_sync()) {
+        umma_commit(&sh->tmem_full[st0]);
+        if (g > 1) umma_commit(&sh->tmem_full[st1]);
+      }
+      __syncwarp();
+      t += g;
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -186,13 +372,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int grp = (warp - 2) >> 2;
     const int out_hw = p.epi.out_h * p.epi.out_w;
     for (int it = grp;; it += p.epi_groups) {
-      const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tl >= p.num_tiles) break;
-      const int t = (int)tl;
+      int n_tile, m_tile;
+      if (p.halo) {
+        const int t = t_begin + it;
+        if (t >= t_end) break;
+        const int u = t / p.G;
+        n_tile = u % p.n_tiles;
+        m_tile = (u / p.n_tiles) * p.G + (t % p.G);
+      } else {
+        const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
+        if (tl >= p.num_tiles) break;
+        n_tile = (int)(tl % p.n_tiles);
+        m_tile = (int)(tl / p.n_tiles);
+      }
       int as = it % p.acc_stages;
       const uint32_t aphase = (uint32_t)((it / p.acc_stages) & 1);
-      const int n_tile = t % p.n_tiles;
-      const int m_tile = t / p.n_tiles;
       int b, ho, wo;
       bool valid;
       if (p.flat) {
@@ -208,11 +402,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int r = m_tile - b * tiles_per_img;
         const int ty = r / p.tiles_w;
         const int tx = r - ty * p.tiles_w;
-        const int hl = row / p.tw;
-        const int wl = row - hl * p.tw;
+        const int hl = row / p.pitch;
+        const int wl = row - hl * p.pitch;
         ho = ty * p.th + hl;
         wo = tx * p.tw + wl;
-        valid = (hl < p.th) && (ho < p.epi.out_h) && (wo < p.epi.out_w);
+        valid = (hl < p.th) && (wl < p.tw) && (ho < p.epi.out_h) && (wo < p.epi.out_w) && (b < p.batch);
       }
       mbar_wait(&sh->tmem_full[as], aphase);
       tc_fence_after();
@@ -422,6 +616,81 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);  // power of two >= 32 by construction
 
   p.flat = (d->ksize == 1 && d->stride == 1) ? 1 : 0;
+  p.halo = (d->ksize == 3 && d->stride == 1) ? 1 : 0;
+  if (const char* e = getenv("YX_HALO")) { if (e[0] == '0') p.halo = 0; }
+  const unsigned row_bytes = (unsigned)p.KC * 2;             // 128 / 64 / 32 = swizzle span
+  p.row_bytes = row_bytes;
+  p.G = 1; p.a_slots = 0; p.b_region_bytes = 0;
+  int dev = 0, max_smem = 0;
+  YX_CUDA(cudaGetDevice(&dev));
+  YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
+
+  if (p.halo) {
+    // N tile <= 128 so that two accumulator pairs fit TMEM (G = 2 M tiles per weight stage)
+    p.BN = largest_divisor_tile(d->out_c, 128);
+    p.n_tiles = d->out_c / p.BN;
+    p.BNpad = 32;
+    while (p.BNpad < p.BN) p.BNpad <<= 1;
+    p.acc_stages = 512 / p.BNpad;
+    if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
+    p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);
+    // spatial tile: th rows of (tw + 2) accumulator rows each (2 halo columns per row are discarded)
+    long long best_cost = -1; int btw = 1, bth = 1;
+    for (int tw = 1; tw <= d->out_w && tw + 2 <= 128; ++tw) {
+      int th = 128 / (tw + 2);
+      if (th > d->out_h) th = d->out_h;
+      if (th < 1 || th + 2 > 256) continue;
+      const long long tiles = ceil_div64(d->out_w, tw) * ceil_div64(d->out_h, th);
+      const long long cost = tiles * 4096 + (long long)(th + 2) * (tw + 2);   // fewest tiles, then least halo traffic
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; btw = tw; bth = th; }
+    }
+    p.tw = btw; p.th = bth; p.pitch = btw + 2;
+    p.tiles_w = (int)ceil_div64(d->out_w, p.tw);
+    p.tiles_h = (int)ceil_div64(d->out_h, p.th);
+    p.m_tiles = d->batch * p.tiles_w * p.tiles_h;
+    // rows touched by the last tap of accumulator row 127, rounded to the swizzle atom
+    const unsigned slot_rows = 127u + 2u * (unsigned)p.pitch + 3u;
+    p.a_slot_bytes = (slot_rows * row_bytes + 1023u) & ~1023u;
+    p.a_tx_bytes = (unsigned)((p.th + 2) * p.pitch) * row_bytes;
+    p.b_tile_bytes = ((unsigned)p.BN * row_bytes + 1023u) & ~1023u;
+    p.b_tx_bytes = (unsigned)p.BN * row_bytes;
+    p.epi_groups = 2;
+    if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
+    if (const char* e = getenv("YX_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= kMaxEpiGroups && v <= p.acc_stages) p.epi_groups = v; }
+    p.head_bytes = 0;
+    YX_REQUIRE(d->epilogue == YX_EPI_STORE, YX_ERR_UNSUPPORTED, "conv_tc: 3x3 head epilogue is not supported");
+    const unsigned fixed_bytes = 2048u + p.bias_bytes;
+    const long long avail = (long long)max_smem - fixed_bytes;
+    const long long b_all = 9ll * p.kchunks * p.b_tile_bytes;
+    p.b_resident = (p.n_tiles == 1 && avail - b_all >= 3ll * p.a_slot_bytes) ? 1 : 0;
+    if (const char* e = getenv("YX_HALO_BRES")) { if (e[0] == '0') p.b_resident = 0; }
+    if (p.b_resident) {
+      p.G = 1;
+      p.b_region_bytes = (unsigned)b_all;
+      p.stages = 1;
+      p.a_slots = (int)((avail - b_all) / p.a_slot_bytes);
+    } else {
+      p.G = p.acc_stages >= 4 ? 2 : 1;
+      if (const char* e = getenv("YX_HALO_G")) { int v = atoi(e); if (v >= 1 && v <= 2 && 2 * v <= p.acc_stages) p.G = v; }
+      p.a_slots = 2 * p.G;
+      long long rest = avail - (long long)p.a_slots * p.a_slot_bytes;
+      YX_REQUIRE(rest >= 2ll * p.b_tile_bytes, YX_ERR_UNSUPPORTED, "conv_tc(halo): shared memory too small");
+      p.stages = (int)(rest / p.b_tile_bytes);
+      if (p.stages > kMaxStages) p.stages = kMaxStages;
+      p.b_region_bytes = (unsigned)p.stages * p.b_tile_bytes;
+      // leftover shared memory deepens the halo ring
+      rest = avail - p.b_region_bytes;
+      p.a_slots = (int)(rest / p.a_slot_bytes);
+    }
+    if (p.a_slots > kMaxASlots) p.a_slots = kMaxASlots;
+    YX_REQUIRE(p.a_slots >= p.G, YX_ERR_UNSUPPORTED, "conv_tc(halo): halo ring does not fit shared memory");
+    const int m_pad = (int)ceil_div64(p.m_tiles, p.G) * p.G;
+    p.num_tiles = m_pad * p.n_tiles;
+    p.base_off = 0;
+    if (const char* e = getenv("YX_HALO_BASEOFF")) p.base_off = atoi(e);
+    L->smem = fixed_bytes + p.b_region_bytes + (size_t)p.a_slots * p.a_slot_bytes;
+  } else {
   if (p.flat) {
     p.tw = 128; p.th = 1;
     p.tiles_w = (int)ceil_div64(p.M, 128); p.tiles_h = 1;
@@ -445,18 +714,14 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
     p.tiles_h = (int)ceil_div64(d->out_h, p.th);
     p.num_tiles = d->batch * p.tiles_w * p.tiles_h * p.n_tiles;
   }
+  p.pitch = p.tw;
+  p.m_tiles = p.num_tiles / p.n_tiles;
 
-  const unsigned row_bytes = (unsigned)p.KC * 2;             // 128 / 64 / 32 = swizzle span
   const unsigned a_bytes = 128u * row_bytes;
   const unsigned b_bytes = (unsigned)p.BN * row_bytes;
   p.a_stage_bytes = (a_bytes + 1023u) & ~1023u;
   p.stage_bytes = p.a_stage_bytes + ((b_bytes + 1023u) & ~1023u);
   p.tx_bytes = (unsigned)(p.tw * p.th) * row_bytes + b_bytes;  // bytes TMA actually delivers
-  int dev = 0, max_smem = 0;
-  YX_CUDA(cudaGetDevice(&dev));
-  YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int num_k = d->ksize * d->ksize * p.kchunks;
-  p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
   // epilogue groups: memory-bound layers (short K loops) need several tiles in the epilogue at once
   {
     const int num_k_total = d->ksize * d->ksize * (d->in_c / p.KC);
@@ -468,11 +733,11 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   p.head_bytes = d->epilogue == YX_EPI_HEAD ? (((unsigned)p.epi_groups * 4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
   const unsigned fixed_bytes = 2048u + p.bias_bytes + p.head_bytes;
   int stages = (int)((max_smem - (int)fixed_bytes) / p.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > 8) stages = 8;
   YX_REQUIRE(stages >= 2, YX_ERR_UNSUPPORTED, "conv_tc: stage of %u bytes does not fit shared memory", p.stage_bytes);
-  (void)num_k;
   p.stages = stages;
   L->smem = fixed_bytes + (size_t)stages * p.stage_bytes;
+  }
 
   // UMMA shared-memory descriptor, upper word: SBO = 8 rows * row_bytes, version 1, layout type
   const unsigned layout = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);  // SW128 / SW64 / SW32
@@ -500,6 +765,7 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
       strides[1] = strides[0] * (cuuint64_t)d->in_w;
       strides[2] = strides[1] * (cuuint64_t)d->in_h;
       box[0] = (cuuint32_t)p.KC; box[1] = (cuuint32_t)(p.tw * d->stride); box[2] = (cuuint32_t)(p.th * d->stride); box[3] = 1;
+      if (p.halo) { box[1] = (cuuint32_t)p.pitch; box[2] = (cuuint32_t)(p.th + 2); }
       estr[0] = 1; estr[1] = (cuuint32_t)d->stride; estr[2] = (cuuint32_t)d->stride; estr[3] = 1;
     }
     CUresult r = encode(&L->map_a, tdt, 4, const_cast<void*>(d->in), dims, strides, box, estr,
@@ -521,6 +787,10 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   }
   const int sms = num_sms();
   L->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (p.halo) {
+    const int groups = p.num_tiles / p.G;     // never split a weight-sharing group when there is less than one per SM
+    L->grid = groups < sms ? groups : sms;
+  }
   return YX_OK;
 }
 
