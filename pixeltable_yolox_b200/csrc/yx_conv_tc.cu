@@ -60,6 +60,17 @@ struct ConvTcParams {
   int b_resident;        // all 9*kchunks weight tiles stay in smem (n_tiles == 1)
   unsigned b_tile_bytes, b_tx_bytes, b_region_bytes;
   int base_off;          // 1: set the descriptor base-offset field from the shifted start address
+  // ---- halo == 2 (3x3 stride 2): input viewed as [2C, W/2, H, B] (x parity folded into the channels), one
+  //      halo tile per (channel chunk, y parity) "plane kind"; each kind runs a short list of MMA ops
+  int s2_kinds, s2_cchunks;
+  struct S2Kind {
+    int ch_off;            // channel coordinate of the plane in the folded view (+ cc * 64)
+    int row_off;           // first input row = 2 * y0 + row_off
+    int nops;
+    unsigned a_off16[4];   // (row shift * row_bytes + byte offset inside the row) >> 4
+    int bk[4];             // K coordinate of the weight box (+ cc * 64)
+    int ks[4];             // k-steps (16 channels each)
+  } s2[4];
   EpiParams epi;
 };
 
@@ -177,7 +188,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* const bregion = tiles;                       // weight ring or resident weights
   uint8_t* const aregion = tiles + p.b_region_bytes;    // halo ring
 
-  if (p.halo && warp == 0) {
+  if (p.halo == 2 && warp == 0) {
+    // ===================== TMA producer (stride-2 planes) =====================
+    if (lane == 0) {
+      if (p.b_resident) {
+        int nb = 0;
+        for (int cc = 0; cc < p.s2_cchunks; ++cc)
+          for (int k = 0; k < p.s2_kinds; ++k) nb += p.s2[k].nops;
+        mbar_arrive_expect_tx(&sh->bres_full, p.b_tx_bytes * (unsigned)nb);
+        nb = 0;
+        for (int cc = 0; cc < p.s2_cchunks; ++cc)
+          for (int k = 0; k < p.s2_kinds; ++k)
+            for (int o = 0; o < p.s2[k].nops; ++o, ++nb)
+              tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)nb * p.b_tile_bytes, p.s2[k].bk[o] + cc * 64, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n_tile = t % p.n_tiles;
+        const int m_tile = t / p.n_tiles;
+        const int b = m_tile / tiles_per_img;
+        const int r = m_tile - b * tiles_per_img;
+        const int ty = r / p.tiles_w;
+        const int tx = r - ty * p.tiles_w;
+        for (int cc = 0; cc < p.s2_cchunks; ++cc) {
+          for (int k = 0; k < p.s2_kinds; ++k) {
+            mbar_wait(&sh->aempty[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&sh->afull[sa], p.a_tx_bytes);
+            tma_load_4d(&map_a, &sh->afull[sa], aregion + (size_t)sa * p.a_slot_bytes, p.s2[k].ch_off + cc * 64,
+                        tx * p.tw - 1, 2 * ty * p.th + p.s2[k].row_off, b);
+            if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+            if (!p.b_resident) {
+              for (int o = 0; o < p.s2[k].nops; ++o) {
+                mbar_wait(&sh->empty[sb], pb ^ 1);
+                mbar_arrive_expect_tx(&sh->full[sb], p.b_tx_bytes);
+                tma_load_2d(&map_b, &sh->full[sb], bregion + (size_t)sb * p.b_tile_bytes, p.s2[k].bk[o] + cc * 64,
+                            n_tile * p.BN);
+                if (++sb == p.stages) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (p.halo == 2 && warp == 1) {
+    // ===================== MMA issuer (stride-2 planes) =====================
+    const uint32_t a0 = smem_u32(aregion) >> 4, aslot16 = p.a_slot_bytes >> 4;
+    const uint32_t b0 = smem_u32(bregion) >> 4, btile16 = p.b_tile_bytes >> 4;
+    const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
+    const uint32_t idesc = p.idesc;
+    const int n_acc = p.acc_stages, n_as = p.a_slots, n_bs = p.stages;
+    const bool ring = !p.b_resident;
+    int sa = 0, sb = 0, as = 0;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    if (!ring) mbar_wait(&sh->bres_full, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&sh->tmem_empty[as], pacc ^ 1);
+      tc_fence_after();
+      const uint32_t dt = tmem_base + (uint32_t)(as * p.BNpad);
+      uint32_t bres = b0;
+      uint32_t accf = 0;
+      for (int cc = 0; cc < p.s2_cchunks; ++cc) {
+        for (int k = 0; k < p.s2_kinds; ++k) {
+          mbar_wait(&sh->afull[sa], pa);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t abase = a0 + (uint32_t)sa * aslot16;
+            const int nops = p.s2[k].nops;
+            for (int o = 0; o < nops; ++o) {
+              uint32_t bl;
+              if (ring) {
+                mbar_wait(&sh->full[sb], pb);
+                tc_fence_after();
+                bl = b0 + (uint32_t)sb * btile16;
+              } else {
+                bl = bres;
+                bres += btile16;
+              }
+              const uint64_t ad = dhi | (uint64_t)(abase + p.s2[k].a_off16[o]), bd = dhi | (uint64_t)bl;
+              const int ks = p.s2[k].ks[o];
+              umma_f16(dt, ad, bd, idesc, accf);
+              accf = 1;
+              if (ks > 1) umma_f16(dt, ad + 2, bd + 2, idesc, 1u);
+              if (ks > 2) { umma_f16(dt, ad + 4, bd + 4, idesc, 1u); umma_f16(dt, ad + 6, bd + 6, idesc, 1u); }
+              if (ring) {
+                umma_commit(&sh->empty[sb]);
+                if (++sb == n_bs) { sb = 0; pb ^= 1; }
+              }
+            }
+            umma_commit(&sh->aempty[sa]);
+          }
+          __syncwarp();
+          accf = 1;
+          if (++sa == n_as) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (elect_one_sync()) umma_commit(&sh->tmem_full[as]);
+      __syncwarp();
+      if (++as == n_acc) { as = 0; pacc ^= 1; }
+    }
+  } else if (p.halo && warp == 0) {
     // ===================== TMA producer (halo mode) =====================
     if (lane == 0) {
       if (p.b_resident) {
@@ -582,7 +692,7 @@ static int largest_divisor_tile(int n, int cap) {
   return 16;
 }
 
-int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
+static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool allow_s2) {
   int rc = validate_conv_geometry(d);
   if (rc) return rc;
   YX_REQUIRE(d->dtype == YX_BF16 || d->dtype == YX_FP16, YX_ERR_INVALID_ARG, "conv_tc: dtype must be bf16/fp16");
@@ -617,7 +727,12 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
 
   p.flat = (d->ksize == 1 && d->stride == 1) ? 1 : 0;
   p.halo = (d->ksize == 3 && d->stride == 1) ? 1 : 0;
+  // stride 2: the x parity folds into the channel dimension only when pixel pairs are contiguous
+  if (allow_s2 && d->ksize == 3 && d->stride == 2 && d->in_ld == d->in_c && d->in_w % 2 == 0 && (d->in_c == 32 || d->in_c % 64 == 0))
+    p.halo = 2;
   if (const char* e = getenv("YX_HALO")) { if (e[0] == '0') p.halo = 0; }
+  if (const char* e = getenv("YX_HALO_S2")) { if (e[0] == '0' && p.halo == 2) p.halo = 0; }
+  if (p.halo == 2) { p.KC = 64; p.kchunks = 2 * d->in_c / 64; }
   const unsigned row_bytes = (unsigned)p.KC * 2;             // 128 / 64 / 32 = swizzle span
   p.row_bytes = row_bytes;
   p.G = 1; p.a_slots = 0; p.b_region_bytes = 0;
@@ -637,22 +752,23 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
     p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);
     // spatial tile: th rows of (tw + 2) accumulator rows each (2 halo columns per row are discarded)
     long long best_cost = -1; int btw = 1, bth = 1;
-    for (int tw = 1; tw <= d->out_w && tw + 2 <= 128; ++tw) {
-      int th = 128 / (tw + 2);
+    const int hx = p.halo == 2 ? 1 : 2;     // halo columns / rows per tile
+    for (int tw = 1; tw <= d->out_w && tw + hx <= 128; ++tw) {
+      int th = 128 / (tw + hx);
       if (th > d->out_h) th = d->out_h;
-      if (th < 1 || th + 2 > 256) continue;
+      if (th < 1 || (th + hx) * d->stride > 256) continue;
       const long long tiles = ceil_div64(d->out_w, tw) * ceil_div64(d->out_h, th);
-      const long long cost = tiles * 4096 + (long long)(th + 2) * (tw + 2);   // fewest tiles, then least halo traffic
+      const long long cost = tiles * 4096 + (long long)(th + hx) * (tw + hx);   // fewest tiles, then least halo traffic
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; btw = tw; bth = th; }
     }
-    p.tw = btw; p.th = bth; p.pitch = btw + 2;
+    p.tw = btw; p.th = bth; p.pitch = btw + hx;
     p.tiles_w = (int)ceil_div64(d->out_w, p.tw);
     p.tiles_h = (int)ceil_div64(d->out_h, p.th);
     p.m_tiles = d->batch * p.tiles_w * p.tiles_h;
     // rows touched by the last tap of accumulator row 127, rounded to the swizzle atom
-    const unsigned slot_rows = 127u + 2u * (unsigned)p.pitch + 3u;
+    const unsigned slot_rows = p.halo == 2 ? 127u + (unsigned)p.pitch + 2u : 127u + 2u * (unsigned)p.pitch + 3u;
     p.a_slot_bytes = (slot_rows * row_bytes + 1023u) & ~1023u;
-    p.a_tx_bytes = (unsigned)((p.th + 2) * p.pitch) * row_bytes;
+    p.a_tx_bytes = (unsigned)((p.th + hx) * p.pitch) * row_bytes;
     p.b_tile_bytes = ((unsigned)p.BN * row_bytes + 1023u) & ~1023u;
     p.b_tx_bytes = (unsigned)p.BN * row_bytes;
     p.epi_groups = 2;
@@ -662,17 +778,45 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
     YX_REQUIRE(d->epilogue == YX_EPI_STORE, YX_ERR_UNSUPPORTED, "conv_tc: 3x3 head epilogue is not supported");
     const unsigned fixed_bytes = 2048u + p.bias_bytes;
     const long long avail = (long long)max_smem - fixed_bytes;
-    const long long b_all = 9ll * p.kchunks * p.b_tile_bytes;
+    long long n_btiles = 9ll * p.kchunks;
+    if (p.halo == 2) {
+      // op tables; a_off16 = (row shift * row_bytes + byte offset in the row) / 16, P = pitch
+      const unsigned rb16 = row_bytes >> 4, P = (unsigned)p.pitch;
+      const int C = d->in_c;
+      auto tapk = [&](int r, int sx) { return (r * 3 + sx) * C; };
+      memset(p.s2, 0, sizeof(p.s2));
+      if (C == 32) {
+        // one mixed chunk per row: [x-even 32 ch | x-odd 32 ch]; taps (r,1),(r,2) are one K = 64 GEMM at column
+        // x, tap (r,0) is a K = 32 GEMM on the x-odd half of column x-1
+        p.s2_kinds = 2; p.s2_cchunks = 1;
+        p.s2[0] = {0, -1, 4, {1u * rb16, 0u * rb16 + 4u, (P + 1u) * rb16, P * rb16 + 4u},
+                   {tapk(0, 1), tapk(0, 0), tapk(2, 1), tapk(2, 0)}, {4, 2, 4, 2}};
+        p.s2[1] = {0, 0, 2, {1u * rb16, 0u * rb16 + 4u, 0, 0}, {tapk(1, 1), tapk(1, 0), 0, 0}, {4, 2, 0, 0}};
+      } else {
+        p.s2_kinds = 4; p.s2_cchunks = C / 64;
+        p.s2[0] = {0, -1, 2, {1u * rb16, (P + 1u) * rb16, 0, 0}, {tapk(0, 1), tapk(2, 1), 0, 0}, {4, 4, 0, 0}};
+        p.s2[1] = {0, 0, 1, {1u * rb16, 0, 0, 0}, {tapk(1, 1), 0, 0, 0}, {4, 0, 0, 0}};
+        p.s2[2] = {C, -1, 4, {0u, 1u * rb16, P * rb16, (P + 1u) * rb16},
+                   {tapk(0, 0), tapk(0, 2), tapk(2, 0), tapk(2, 2)}, {4, 4, 4, 4}};
+        p.s2[3] = {C, 0, 2, {0u, 1u * rb16, 0, 0}, {tapk(1, 0), tapk(1, 2), 0, 0}, {4, 4, 0, 0}};
+      }
+      n_btiles = 0;
+      for (int k = 0; k < p.s2_kinds; ++k) n_btiles += p.s2[k].nops;
+      n_btiles *= p.s2_cchunks;
+    }
+    const long long b_all = n_btiles * p.b_tile_bytes;
     p.b_resident = (p.n_tiles == 1 && avail - b_all >= 3ll * p.a_slot_bytes) ? 1 : 0;
     if (const char* e = getenv("YX_HALO_BRES")) { if (e[0] == '0') p.b_resident = 0; }
+    // stride-2 planes only pay off with resident weights (streamed weights are not shared between M tiles there)
+    if (p.halo == 2 && !p.b_resident && !getenv("YX_HALO_BRES")) return conv_tc_prepare_mode(d, L, false);
     if (p.b_resident) {
       p.G = 1;
       p.b_region_bytes = (unsigned)b_all;
       p.stages = 1;
       p.a_slots = (int)((avail - b_all) / p.a_slot_bytes);
     } else {
-      p.G = p.acc_stages >= 4 ? 2 : 1;
-      if (const char* e = getenv("YX_HALO_G")) { int v = atoi(e); if (v >= 1 && v <= 2 && 2 * v <= p.acc_stages) p.G = v; }
+      p.G = (p.acc_stages >= 4 && p.halo == 1) ? 2 : 1;
+      if (p.halo == 1) if (const char* e = getenv("YX_HALO_G")) { int v = atoi(e); if (v >= 1 && v <= 2 && 2 * v <= p.acc_stages) p.G = v; }
       p.a_slots = 2 * p.G;
       long long rest = avail - (long long)p.a_slots * p.a_slot_bytes;
       YX_REQUIRE(rest >= 2ll * p.b_tile_bytes, YX_ERR_UNSUPPORTED, "conv_tc(halo): shared memory too small");
@@ -765,8 +909,14 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
       strides[1] = strides[0] * (cuuint64_t)d->in_w;
       strides[2] = strides[1] * (cuuint64_t)d->in_h;
       box[0] = (cuuint32_t)p.KC; box[1] = (cuuint32_t)(p.tw * d->stride); box[2] = (cuuint32_t)(p.th * d->stride); box[3] = 1;
-      if (p.halo) { box[1] = (cuuint32_t)p.pitch; box[2] = (cuuint32_t)(p.th + 2); }
       estr[0] = 1; estr[1] = (cuuint32_t)d->stride; estr[2] = (cuuint32_t)d->stride; estr[3] = 1;
+      if (p.halo == 1) { box[1] = (cuuint32_t)p.pitch; box[2] = (cuuint32_t)(p.th + 2); }
+      if (p.halo == 2) {
+        dims[0] = (cuuint64_t)(2 * d->in_c); dims[1] = (cuuint64_t)(d->in_w / 2);
+        strides[0] = (cuuint64_t)d->in_ld * 4;
+        box[0] = 64; box[1] = (cuuint32_t)p.pitch; box[2] = (cuuint32_t)((p.th + 1) * 2);
+        estr[1] = 1;
+      }
     }
     CUresult r = encode(&L->map_a, tdt, 4, const_cast<void*>(d->in), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -793,6 +943,8 @@ int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) {
   }
   return YX_OK;
 }
+
+int conv_tc_prepare(const yx_conv_desc* d, ConvTcLaunch* L) { return conv_tc_prepare_mode(d, L, true); }
 
 ConvTcLaunch* conv_tc_alloc() {
   void* p = nullptr;

@@ -21,7 +21,12 @@ CASES = [
     (2, 20, 20, 256, 256, 3, 1), (5, 40, 40, 64, 64, 3, 1), (2, 160, 160, 32, 32, 3, 1), (7, 23, 61, 128, 128, 3, 1),
 ]
 MODE = sys.argv[1] if len(sys.argv) > 1 else "00"
-for base in (MODE[0],) if MODE != "time" else ():
+if MODE.startswith("s2"):
+    CASES = [(2, 16, 16, 64, 64, 3, 2), (2, 40, 40, 32, 64, 3, 2), (1, 80, 80, 128, 128, 3, 2), (2, 20, 20, 256, 512, 3, 2),
+             (3, 160, 160, 64, 128, 3, 2), (2, 320, 320, 32, 64, 3, 2), (5, 26, 38, 128, 256, 3, 2), (1, 7, 10, 64, 32, 3, 2),
+             (2, 13, 14, 32, 48, 3, 2), (1, 64, 48, 16, 32, 3, 2)]
+    MODE = "0" + MODE[2]
+for base in (MODE[0],) if not MODE.startswith("time") else ():
     os.environ["YX_HALO_BASEOFF"] = base
     for bres in (MODE[1],):
         os.environ["YX_HALO_BRES"] = bres
@@ -33,6 +38,29 @@ for base in (MODE[0],) if MODE != "time" else ():
                 err = repr(e)[:200]
             print(f"baseoff={base} bres={bres} {case} err={err}", flush=True)
 os.environ.pop("YX_HALO_BRES", None)
+if MODE == "time2":
+    B = 64
+    for sh in ["32:64:320", "64:128:160", "128:256:80", "256:512:40", "128:128:80", "256:256:40"]:
+        cin, cout, hw = (int(v) for v in sh.split(":"))
+        x = torch.randn(B, hw, hw, cin, device=dev).to(torch.bfloat16)
+        w = (torch.randn(cout, 9, cin, device=dev) / (9 * cin) ** 0.5).to(torch.bfloat16)
+        bias = torch.zeros(cout, device=dev)
+        o = torch.empty(B, hw // 2, hw // 2, cout, device=dev, dtype=torch.bfloat16)
+        res = {}
+        for halo in ("0", "1"):
+            os.environ["YX_HALO_S2"] = halo
+            for _ in range(3):
+                ops.conv_bn_act(View(x), w, bias, View(o), 3, 2, 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.conv_bn_act(View(x), w, bias, View(o), 3, 2, 1)
+            e1.record(); torch.cuda.synchronize()
+            res[halo] = e0.elapsed_time(e1) * 1e3 / 5
+        fl = 2.0 * B * (hw // 2) ** 2 * cin * 9 * cout
+        by = 2.0 * B * (hw * hw * cin + (hw // 2) ** 2 * cout)
+        print(f"{sh:14s} old {res['0']:7.1f} us  planes {res['1']:7.1f} us  ({fl / res['1'] / 1e6:7.1f} TFLOP/s, {by / res['1'] / 1e3:7.1f} GB/s)", flush=True)
 if MODE == "time":
     os.environ["YX_HALO_BASEOFF"] = sys.argv[2] if len(sys.argv) > 2 else "0"
     B = 64
