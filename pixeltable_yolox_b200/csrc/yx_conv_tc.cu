@@ -51,7 +51,8 @@ struct ConvTcParams {
   int epi_groups;        // 1..kMaxEpiGroups
   // ---- halo mode (3x3 stride 1): one TMA halo tile per channel chunk, the 9 taps are row-shifted
   //      UMMA descriptors into it; weights resident in smem or shared by G consecutive M tiles
-  int halo;
+  int halo;              // 1: taps x shifted descriptors (3x3 s1 with taps = 9, 1x1 with taps = 1); 2: stride-2 planes
+  int taps;
   int pitch;             // accumulator rows per tile row (= tw + 2 in halo mode, = tw otherwise)
   int G;                 // M tiles per weight stage
   int m_tiles;           // real M tiles; m_tiles_pad = ceil(m_tiles / G) * G
@@ -60,6 +61,7 @@ struct ConvTcParams {
   int b_resident;        // all 9*kchunks weight tiles stay in smem (n_tiles == 1)
   unsigned b_tile_bytes, b_tx_bytes, b_region_bytes;
   int base_off;          // 1: set the descriptor base-offset field from the shifted start address
+  unsigned mul_tpi, mul_tw, mul_ntiles, mul_ohw, mul_ow;   // floor(2^32 / d) + 1 for tiles_per_img, tiles_w, n_tiles, out_h*out_w, out_w
   // ---- halo == 2 (3x3 stride 2): input viewed as [2C, W/2, H, B] (x parity folded into the channels), one
   //      halo tile per (channel chunk, y parity) "plane kind"; each kind runs a short list of MMA ops
   int s2_kinds, s2_cchunks;
@@ -92,13 +94,33 @@ struct __align__(8) TcShared {
 };
 
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// n / d for 0 <= n < 2^31 with mul = floor(2^32 / d) + 1 (d >= 2); the estimate is never low and at most 1 high
+__device__ __forceinline__ int fast_div(int n, unsigned mul, int d) {
+  if (d == 1) return n;
+  int q = (int)__umulhi((unsigned)n, mul);
+  if ((long long)q * d > n) --q;
+  return q;
+}
+static inline unsigned fast_div_mul(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d) + 1u; }
+
 // ---- halo-mode MMA issue helpers (run by the one elected lane of the MMA warp) ----
 // resident weights, one M tile: 9 taps x KS k-steps, descriptors advance by compile-time constants
-template <int KS>
+template <int KS, int TAPS>
 __device__ __forceinline__ void halo_issue_res(uint64_t ad, uint32_t dt, uint64_t bd, uint32_t btile16, uint32_t idesc,
                                                uint32_t acc0, uint32_t rb16, uint32_t prb16) {
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
+  for (int tap = 0; tap < TAPS; ++tap) {
     const uint64_t a = ad + (uint64_t)((uint32_t)(tap / 3) * prb16 + (uint32_t)(tap % 3) * rb16);
     const uint64_t b = bd + (uint64_t)((uint32_t)tap * btile16);
 #pragma unroll
@@ -106,12 +128,12 @@ __device__ __forceinline__ void halo_issue_res(uint64_t ad, uint32_t dt, uint64_
   }
 }
 // streamed weights (ring of `n_bs` stages), one or two M tiles sharing every weight stage
-template <int KS, bool TWO>
+template <int KS, bool TWO, int TAPS>
 __device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint64_t ad1, uint32_t dt0, uint32_t dt1,
                                                 uint64_t bd0, uint32_t btile16, uint32_t idesc, uint32_t acc0,
                                                 uint32_t rb16, uint32_t prb16, int& sb, uint32_t& pb, int n_bs) {
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
+  for (int tap = 0; tap < TAPS; ++tap) {
     mbar_wait(&sh->full[sb], pb);
     tc_fence_after();
     const uint64_t sh16 = (uint64_t)((uint32_t)(tap / 3) * prb16 + (uint32_t)(tap % 3) * rb16);
@@ -141,7 +163,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* tiles = smem + 1024 + p.bias_bytes + p.head_bytes;
   // bias lives in shared memory: with ~200 KB of operand stages the L1 carve-out is ~0, so a
   // global bias load in the epilogue would be an L2 round trip per 16 columns
-  for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x) sbias[i] = p.epi.bias[i];
+  {
+    const float bscale = (epi_half_bias(p.epi) && p.epi.epilogue == YX_EPI_STORE) ? 0.5f : 1.0f;
+    // head: the sigmoid channels (obj, classes) stage -log2e * bias (see the head epilogue)
+    const float hscale = (p.epi.epilogue == YX_EPI_HEAD && (p.epi.head_decode & 2)) ? -1.4426950408889634f : 1.0f;
+    for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x)
+      sbias[i] = p.epi.bias[i] * (p.epi.epilogue == YX_EPI_HEAD ? (i >= 4 ? hscale : 1.0f) : bscale);
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,10 +319,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer (halo mode) =====================
     if (lane == 0) {
       if (p.b_resident) {
-        mbar_arrive_expect_tx(&sh->bres_full, p.b_tx_bytes * 9u * (unsigned)p.kchunks);
-        for (int tap = 0; tap < 9; ++tap)
+        mbar_arrive_expect_tx(&sh->bres_full, p.b_tx_bytes * (unsigned)(p.taps * p.kchunks));
+        for (int tap = 0; tap < p.taps; ++tap)
           for (int c = 0; c < p.kchunks; ++c)
-            tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)(c * 9 + tap) * p.b_tile_bytes,
+            tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)(c * p.taps + tap) * p.b_tile_bytes,
                         tap * p.in_c + c * p.KC, 0);
       }
       int ca = 0, sb = 0;
@@ -316,11 +344,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int slot = ca % p.a_slots;
             mbar_wait(&sh->aempty[slot], (uint32_t)(((ca / p.a_slots) & 1) ^ 1));
             mbar_arrive_expect_tx(&sh->afull[slot], p.a_tx_bytes);
-            tma_load_4d(&map_a, &sh->afull[slot], aregion + (size_t)slot * p.a_slot_bytes, c * p.KC,
-                        tx * p.tw - 1, ty * p.th - 1, b);
+            if (p.flat)
+              tma_load_4d(&map_a, &sh->afull[slot], aregion + (size_t)slot * p.a_slot_bytes, c * p.KC, m_tile * 128, 0, 0);
+            else
+              tma_load_4d(&map_a, &sh->afull[slot], aregion + (size_t)slot * p.a_slot_bytes, c * p.KC,
+                          tx * p.tw - 1, ty * p.th - 1, b);
           }
           if (!p.b_resident) {
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < p.taps; ++tap) {
               mbar_wait(&sh->empty[sb], pb ^ 1);
               mbar_arrive_expect_tx(&sh->full[sb], p.b_tx_bytes);
               tma_load_2d(&map_b, &sh->full[sb], bregion + (size_t)sb * p.b_tile_bytes, tap * p.in_c + c * p.KC,
@@ -343,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);   // LBO = 1 in the low word
     const uint32_t idesc = p.idesc;
     const int ksteps = p.KC >> 4;
-    const int G = p.G, n_acc = p.acc_stages, n_as = p.a_slots, n_bs = p.stages, kch = p.kchunks;
+    const int G = p.G, n_acc = p.acc_stages, n_as = p.a_slots, n_bs = p.stages, kch = p.kchunks, taps = p.taps;
     const bool ring = !p.b_resident;
     int sa = 0, sb = 0, as = 0, i0 = t_begin % G;
     uint32_t pa = 0, pb = 0, pacc = 0;
@@ -382,24 +413,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t ad0 = dhi | (uint64_t)al0, ad1 = dhi | (uint64_t)al1;
           const uint32_t acc0 = (uint32_t)(c != 0);
           if (ring) {
-#define YX_RING(KS, TWO) halo_issue_ring<KS, TWO>(sh, ad0, ad1, dt0, dt1, dhi | (uint64_t)b0, btile16, idesc, acc0, rb16, prb16, sb, pb, n_bs)
-            if (g > 1) {
-              if (ksteps == 4) YX_RING(4, true); else if (ksteps == 2) YX_RING(2, true); else YX_RING(1, true);
-            } else {
-              if (ksteps == 4) YX_RING(4, false); else if (ksteps == 2) YX_RING(2, false); else YX_RING(1, false);
-            }
+#define YX_RING(KS, TWO, TAPS) halo_issue_ring<KS, TWO, TAPS>(sh, ad0, ad1, dt0, dt1, dhi | (uint64_t)b0, btile16, idesc, acc0, rb16, prb16, sb, pb, n_bs)
+#define YX_RING_T(TWO, TAPS) do { if (ksteps == 4) YX_RING(4, TWO, TAPS); else if (ksteps == 2) YX_RING(2, TWO, TAPS); else YX_RING(1, TWO, TAPS); } while (0)
+            if (taps == 9) { if (g > 1) YX_RING_T(true, 9); else YX_RING_T(false, 9); }
+            else { if (g > 1) YX_RING_T(true, 1); else YX_RING_T(false, 1); }
+#undef YX_RING_T
 #undef YX_RING
           } else {
             const uint64_t bd = dhi | (uint64_t)bres;
-            if (ksteps == 4) halo_issue_res<4>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
-            else if (ksteps == 2) halo_issue_res<2>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
-            else halo_issue_res<1>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16);
+#define YX_RES(KS, TAPS) halo_issue_res<KS, TAPS>(ad0, dt0, bd, btile16, idesc, acc0, rb16, prb16)
+            if (taps == 9) { if (ksteps == 4) YX_RES(4, 9); else if (ksteps == 2) YX_RES(2, 9); else YX_RES(1, 9); }
+            else { if (ksteps == 4) YX_RES(4, 1); else if (ksteps == 2) YX_RES(2, 1); else YX_RES(1, 1); }
+#undef YX_RES
           }
           umma_commit(&sh->aempty[sl0]);
           if (g > 1) umma_commit(&sh->aempty[sl1]);
         }
         __syncwarp();
-        bres += 9u * btile16;
+        bres += (uint32_t)taps * btile16;
       }
       if (elect_one_sync()) {
         umma_commit(&sh->tmem_full[st0]);
@@ -481,42 +512,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = quarter * 32 + lane;     // accumulator row = pixel inside the tile
     const int grp = (warp - 2) >> 2;
     const int out_hw = p.epi.out_h * p.epi.out_w;
+    // everything that does not depend on the tile is decoded once; per tile there is no integer division
+    int hl0 = 0, wl0 = 0;
+    if (!p.flat) { hl0 = row / p.pitch; wl0 = row - hl0 * p.pitch; }
+    const bool row_ok = p.flat || (hl0 < p.th && wl0 < p.tw);
+    const bool need_coords = p.flat && (p.epi.ups != nullptr || p.epi.epilogue == YX_EPI_HEAD);
+    int as = grp % p.acc_stages;
+    uint32_t aphase = (uint32_t)((grp / p.acc_stages) & 1);
     for (int it = grp;; it += p.epi_groups) {
       int n_tile, m_tile;
       if (p.halo) {
         const int t = t_begin + it;
         if (t >= t_end) break;
-        const int u = t / p.G;
-        n_tile = u % p.n_tiles;
-        m_tile = (u / p.n_tiles) * p.G + (t % p.G);
+        const int u = p.G == 2 ? (t >> 1) : t;
+        const int mb = fast_div(u, p.mul_ntiles, p.n_tiles);
+        n_tile = u - mb * p.n_tiles;
+        m_tile = p.G == 2 ? (mb * 2 + (t & 1)) : mb;
       } else {
         const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
         if (tl >= p.num_tiles) break;
-        n_tile = (int)(tl % p.n_tiles);
-        m_tile = (int)(tl / p.n_tiles);
+        m_tile = fast_div((int)tl, p.mul_ntiles, p.n_tiles);
+        n_tile = (int)tl - m_tile * p.n_tiles;
       }
-      int as = it % p.acc_stages;
-      const uint32_t aphase = (uint32_t)((it / p.acc_stages) & 1);
-      int b, ho, wo;
+      int b = 0, ho = 0, wo = 0;
+      long long pix;
       bool valid;
       if (p.flat) {
         const long long m = (long long)m_tile * 128 + row;
         valid = m < p.M;
-        const long long mm = valid ? m : 0;
-        b = (int)(mm / out_hw);
-        const int r = (int)(mm - (long long)b * out_hw);
-        ho = r / p.epi.out_w;
-        wo = r - ho * p.epi.out_w;
+        pix = valid ? m : 0;
+        if (need_coords) {
+          b = fast_div((int)pix, p.mul_ohw, out_hw);
+          const int r = (int)pix - b * out_hw;
+          ho = fast_div(r, p.mul_ow, p.epi.out_w);
+          wo = r - ho * p.epi.out_w;
+        }
       } else {
-        b = m_tile / tiles_per_img;
+        b = fast_div(m_tile, p.mul_tpi, tiles_per_img);
         const int r = m_tile - b * tiles_per_img;
-        const int ty = r / p.tiles_w;
+        const int ty = fast_div(r, p.mul_tw, p.tiles_w);
         const int tx = r - ty * p.tiles_w;
-        const int hl = row / p.pitch;
-        const int wl = row - hl * p.pitch;
-        ho = ty * p.th + hl;
-        wo = tx * p.tw + wl;
-        valid = (hl < p.th) && (wl < p.tw) && (ho < p.epi.out_h) && (wo < p.epi.out_w) && (b < p.batch);
+        ho = ty * p.th + hl0;
+        wo = tx * p.tw + wl0;
+        valid = row_ok && (ho < p.epi.out_h) && (wo < p.epi.out_w) && (b < p.batch);
+        pix = ((long long)b * p.epi.out_h + ho) * p.epi.out_w + wo;
       }
       mbar_wait(&sh->tmem_full[as], aphase);
       tc_fence_after();
@@ -527,24 +566,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         //      write each [5+nc] fp32 row with coalesced 128-byte stores
         const int nch = 5 + p.epi.head_nc;
         float* wstage = shead + (size_t)(warp - 2) * 32 * nch;   // one staging slab per epilogue warp
-        for (int c = 0; c < p.BN; c += 16) {
+        // sigmoid(x) = 1 / (1 + 2^(-x*log2e)): the staged bias of the sigmoid channels is pre-multiplied by
+        // -log2e, so each element is FFMA + EX2 + FADD + RCP (ex2/rcp.approx: ~1e-7 relative) + one shared store
+        const bool dec_box = (p.epi.head_decode & 1) != 0, dec_sig = (p.epi.head_decode & 2) != 0;
+        const float sgn = dec_sig ? -1.4426950408889634f : 1.0f;
+        float* wrow = wstage + lane * nch;
+        {
+          // channels 0..15: box (cx, cy, w, h) then obj / first classes
           uint32_t raw[16];
-          tmem_ld_x16(taddr + (uint32_t)c, raw);
+          tmem_ld_x16(taddr, raw);
+          tmem_ld_wait();
+          float x0 = __uint_as_float(raw[0]) + tbias[0], x1 = __uint_as_float(raw[1]) + tbias[1];
+          float x2 = __uint_as_float(raw[2]) + tbias[2], x3 = __uint_as_float(raw[3]) + tbias[3];
+          if (dec_box) {
+            x0 = (x0 + (float)wo) * p.epi.head_stride;
+            x1 = (x1 + (float)ho) * p.epi.head_stride;
+            x2 = __expf(x2) * p.epi.head_stride;
+            x3 = __expf(x3) * p.epi.head_stride;
+          }
+          wrow[0] = x0; wrow[1] = x1; wrow[2] = x2; wrow[3] = x3;
+#pragma unroll
+          for (int j = 4; j < 16; ++j) {
+            if (j < nch) {
+              float v = fmaf(__uint_as_float(raw[j]), sgn, tbias[j]);
+              if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
+              wrow[j] = v;
+            }
+          }
+        }
+        for (int c = 16; c < p.BN; c += 32) {
+          const bool two = (c + 16 < p.BN);
+          uint32_t ra[16], rb[16];
+          tmem_ld_x16(taddr + (uint32_t)c, ra);
+          if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ch = c + j;
-            if (ch < nch) {
-              float x = __uint_as_float(raw[j]) + tbias[ch];
-              // fast-math exp / reciprocal (~1e-6 relative): the inputs carry 16-bit activation noise
-              if (ch < 2) {
-                if (p.epi.head_decode & 1) x = (x + (ch == 0 ? (float)wo : (float)ho)) * p.epi.head_stride;
-              } else if (ch < 4) {
-                if (p.epi.head_decode & 1) x = __expf(x) * p.epi.head_stride;
-              } else if (p.epi.head_decode & 2) {
-                x = __fdividef(1.0f, 1.0f + __expf(-x));
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !two) break;
+            const int cc = c + 16 * half;
+            if (cc >= nch) break;
+            const uint32_t(&r)[16] = half ? rb : ra;
+            if (cc + 16 <= nch) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float v = fmaf(__uint_as_float(r[j]), sgn, tbias[cc + j]);
+                if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
+                wrow[cc + j] = v;
               }
-              wstage[lane * nch + ch] = x;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (cc + j < nch) {
+                  float v = fmaf(__uint_as_float(r[j]), sgn, tbias[cc + j]);
+                  if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
+                  wrow[cc + j] = v;
+                }
+              }
             }
           }
         }
@@ -571,12 +648,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         __syncwarp();
+        as += p.epi_groups;
+        while (as >= p.acc_stages) { as -= p.acc_stages; aphase ^= 1; }
         continue;
       }
       // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
       //      wait, one 256-bit store per thread per 16 columns (a full 32-byte sector)
       const bool fp16 = (p.epi.dtype == YX_FP16);
-      const long long pix = ((long long)b * p.epi.out_h + ho) * p.epi.out_w + wo;
       uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld + n_tile * p.BN;
       const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld + n_tile * p.BN : nullptr;
       for (int c = 0; c < p.BN; c += 32) {
@@ -599,6 +677,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&sh->tmem_empty[as]);
+      as += p.epi_groups;
+      while (as >= p.acc_stages) { as -= p.acc_stages; aphase ^= 1; }
     }
   }
 
@@ -692,7 +772,7 @@ static int largest_divisor_tile(int n, int cap) {
   return 16;
 }
 
-static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool allow_s2) {
+static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool allow_s2, bool allow_flat = true) {
   int rc = validate_conv_geometry(d);
   if (rc) return rc;
   YX_REQUIRE(d->dtype == YX_BF16 || d->dtype == YX_FP16, YX_ERR_INVALID_ARG, "conv_tc: dtype must be bf16/fp16");
@@ -727,6 +807,8 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
 
   p.flat = (d->ksize == 1 && d->stride == 1) ? 1 : 0;
   p.halo = (d->ksize == 3 && d->stride == 1) ? 1 : 0;
+  p.taps = p.flat ? 1 : 9;
+  if (p.flat && allow_flat) { p.halo = 1; if (const char* e = getenv("YX_HALO_FLAT")) { if (e[0] == '0') p.halo = 0; } }
   // stride 2: the x parity folds into the channel dimension only when pixel pairs are contiguous
   if (allow_s2 && d->ksize == 3 && d->stride == 2 && d->in_ld == d->in_c && d->in_w % 2 == 0 && (d->in_c == 32 || d->in_c % 64 == 0))
     p.halo = 2;
@@ -742,43 +824,42 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
   p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
 
   if (p.halo) {
-    // N tile <= 128 so that two accumulator pairs fit TMEM (G = 2 M tiles per weight stage)
-    p.BN = largest_divisor_tile(d->out_c, 128);
-    p.n_tiles = d->out_c / p.BN;
-    p.BNpad = 32;
-    while (p.BNpad < p.BN) p.BNpad <<= 1;
-    p.acc_stages = 512 / p.BNpad;
-    if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
-    p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);
-    // spatial tile: th rows of (tw + 2) accumulator rows each (2 halo columns per row are discarded)
-    long long best_cost = -1; int btw = 1, bth = 1;
     const int hx = p.halo == 2 ? 1 : 2;     // halo columns / rows per tile
-    for (int tw = 1; tw <= d->out_w && tw + hx <= 128; ++tw) {
-      int th = 128 / (tw + hx);
-      if (th > d->out_h) th = d->out_h;
-      if (th < 1 || (th + hx) * d->stride > 256) continue;
-      const long long tiles = ceil_div64(d->out_w, tw) * ceil_div64(d->out_h, th);
-      const long long cost = tiles * 4096 + (long long)(th + hx) * (tw + hx);   // fewest tiles, then least halo traffic
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; btw = tw; bth = th; }
+    if (p.flat) {
+      p.tw = 128; p.th = 1; p.pitch = 128;
+      p.tiles_w = (int)ceil_div64(p.M, 128); p.tiles_h = 1;
+      p.m_tiles = p.tiles_w;
+      p.a_slot_bytes = (128u * row_bytes + 1023u) & ~1023u;
+      p.a_tx_bytes = 128u * row_bytes;
+    } else {
+      // spatial tile: th rows of (tw + hx) accumulator rows each (the halo columns of every row are discarded)
+      long long best_cost = -1; int btw = 1, bth = 1;
+      for (int tw = 1; tw <= d->out_w && tw + hx <= 128; ++tw) {
+        int th = 128 / (tw + hx);
+        if (th > d->out_h) th = d->out_h;
+        if (th < 1 || (th + hx) * d->stride > 256) continue;
+        const long long tiles = ceil_div64(d->out_w, tw) * ceil_div64(d->out_h, th);
+        const long long cost = tiles * 4096 + (long long)(th + hx) * (tw + hx);   // fewest tiles, then least halo traffic
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; btw = tw; bth = th; }
+      }
+      p.tw = btw; p.th = bth; p.pitch = btw + hx;
+      p.tiles_w = (int)ceil_div64(d->out_w, p.tw);
+      p.tiles_h = (int)ceil_div64(d->out_h, p.th);
+      p.m_tiles = d->batch * p.tiles_w * p.tiles_h;
+      // rows touched by the last tap of accumulator row 127, rounded to the swizzle atom
+      const unsigned slot_rows = p.halo == 2 ? 127u + (unsigned)p.pitch + 2u : 127u + 2u * (unsigned)p.pitch + 3u;
+      p.a_slot_bytes = (slot_rows * row_bytes + 1023u) & ~1023u;
+      p.a_tx_bytes = (unsigned)((p.th + hx) * p.pitch) * row_bytes;
     }
-    p.tw = btw; p.th = bth; p.pitch = btw + hx;
-    p.tiles_w = (int)ceil_div64(d->out_w, p.tw);
-    p.tiles_h = (int)ceil_div64(d->out_h, p.th);
-    p.m_tiles = d->batch * p.tiles_w * p.tiles_h;
-    // rows touched by the last tap of accumulator row 127, rounded to the swizzle atom
-    const unsigned slot_rows = p.halo == 2 ? 127u + (unsigned)p.pitch + 2u : 127u + 2u * (unsigned)p.pitch + 3u;
-    p.a_slot_bytes = (slot_rows * row_bytes + 1023u) & ~1023u;
-    p.a_tx_bytes = (unsigned)((p.th + hx) * p.pitch) * row_bytes;
-    p.b_tile_bytes = ((unsigned)p.BN * row_bytes + 1023u) & ~1023u;
-    p.b_tx_bytes = (unsigned)p.BN * row_bytes;
-    p.epi_groups = 2;
-    if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
-    if (const char* e = getenv("YX_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= kMaxEpiGroups && v <= p.acc_stages) p.epi_groups = v; }
-    p.head_bytes = 0;
-    YX_REQUIRE(d->epilogue == YX_EPI_STORE, YX_ERR_UNSUPPORTED, "conv_tc: 3x3 head epilogue is not supported");
-    const unsigned fixed_bytes = 2048u + p.bias_bytes;
+    // short K loops are epilogue-bound: three tiles in the epilogue at once (MMA cycles per tile ~ k-steps * N / 2)
+    p.epi_groups = (p.taps * p.kchunks * (p.KC / 16) * d->out_c <= 4096 && d->out_c <= 128) ? 3 : 2;
+    if (d->epilogue == YX_EPI_HEAD) p.epi_groups = 2;                            // staging slabs are 10.9 KB per warp
+    if (const char* e = getenv("YX_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= kMaxEpiGroups) p.epi_groups = v; }
+    YX_REQUIRE(d->epilogue == YX_EPI_STORE || p.flat, YX_ERR_UNSUPPORTED, "conv_tc: the head epilogue needs a 1x1 conv");
+    p.head_bytes = d->epilogue == YX_EPI_HEAD ? (((unsigned)p.epi_groups * 4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
+    const unsigned fixed_bytes = 2048u + p.bias_bytes + p.head_bytes;
     const long long avail = (long long)max_smem - fixed_bytes;
-    long long n_btiles = 9ll * p.kchunks;
+    long long n_btiles = (long long)p.taps * p.kchunks;
     if (p.halo == 2) {
       // op tables; a_off16 = (row shift * row_bytes + byte offset in the row) / 16, P = pitch
       const unsigned rb16 = row_bytes >> 4, P = (unsigned)p.pitch;
@@ -804,11 +885,29 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
       for (int k = 0; k < p.s2_kinds; ++k) n_btiles += p.s2[k].nops;
       n_btiles *= p.s2_cchunks;
     }
-    const long long b_all = n_btiles * p.b_tile_bytes;
-    p.b_resident = (p.n_tiles == 1 && avail - b_all >= 3ll * p.a_slot_bytes) ? 1 : 0;
-    if (const char* e = getenv("YX_HALO_BRES")) { if (e[0] == '0') p.b_resident = 0; }
+    // N tile: the whole out_c (<= 256) when its weights can stay resident next to >= 3 halo slots, otherwise
+    // <= 128 so that two accumulator pairs fit TMEM and two M tiles share every streamed weight stage
+    long long b_all = 0;
+    for (int cap = 256; cap >= 128; cap -= 128) {
+      p.BN = largest_divisor_tile(d->out_c, cap);
+      p.n_tiles = d->out_c / p.BN;
+      p.BNpad = 32;
+      while (p.BNpad < p.BN) p.BNpad <<= 1;
+      p.acc_stages = 512 / p.BNpad;
+      if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
+      p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);
+      p.b_tile_bytes = ((unsigned)p.BN * row_bytes + 1023u) & ~1023u;
+      p.b_tx_bytes = (unsigned)p.BN * row_bytes;
+      b_all = n_btiles * p.b_tile_bytes;
+      p.b_resident = (p.n_tiles == 1 && avail - b_all >= 3ll * p.a_slot_bytes) ? 1 : 0;
+      if (const char* e = getenv("YX_HALO_BRES")) { if (e[0] == '0') p.b_resident = 0; }
+      if (p.b_resident) break;
+    }
+    if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
     // stride-2 planes only pay off with resident weights (streamed weights are not shared between M tiles there)
     if (p.halo == 2 && !p.b_resident && !getenv("YX_HALO_BRES")) return conv_tc_prepare_mode(d, L, false);
+    // 1x1 with weights too large to stay resident: the per-tap ring with N up to 256 streams fewer bytes
+    if (p.flat && !p.b_resident && !getenv("YX_HALO_BRES")) return conv_tc_prepare_mode(d, L, allow_s2, false);
     if (p.b_resident) {
       p.G = 1;
       p.b_region_bytes = (unsigned)b_all;
@@ -935,6 +1034,11 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
+  p.mul_tpi = fast_div_mul(p.tiles_w * p.tiles_h);
+  p.mul_tw = fast_div_mul(p.tiles_w);
+  p.mul_ntiles = fast_div_mul(p.n_tiles);
+  p.mul_ohw = fast_div_mul(d->out_h * d->out_w);
+  p.mul_ow = fast_div_mul(d->out_w);
   const int sms = num_sms();
   L->grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (p.halo) {

@@ -94,7 +94,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const bool fp16 = (p.epi.dtype == YX_FP16);
 
-  for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x) sbias[i] = p.epi.bias[i];
+  {
+    const float bscale = epi_half_bias(p.epi) ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x) sbias[i] = p.epi.bias[i] * bscale;
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < kStemStages; ++i) { mbar_init(&sh->full[i], kStemBuilders); mbar_init(&sh->empty[i], 1); }

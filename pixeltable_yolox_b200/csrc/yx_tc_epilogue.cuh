@@ -25,23 +25,41 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-// 16 accumulator columns of one pixel: bias (smem) + act (+ residual) -> 16-bit, one 32-byte store
+// true when the kernel stages 0.5 * bias in shared memory (SiLU written as h + h * tanh(h), h = x / 2)
+__device__ __forceinline__ bool epi_half_bias(const EpiParams& e) { return e.act == YX_ACT_SILU && e.dtype == YX_BF16; }
+
+// 16 accumulator columns of one pixel: bias (smem) + act (+ residual) -> 16-bit, one 32-byte store.
+// `bias` holds 0.5 * bias when epi_half_bias(e).
 __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
                                              const uint32_t* res, bool fp16, uint16_t* dst, int b, int ho, int wo,
                                              int c0) {
   float v[16];
+  if (e.act == YX_ACT_SILU && !fp16) {
+    // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible.
+    // 3 instructions per element: h = fma(acc, 0.5, bias/2); t = tanh(h); y = fma(h, t, h)
 #pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
-    v[j + 0] = __uint_as_float(raw[j + 0]) + bb.x;
-    v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
-    v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z;
-    v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
+    for (int j = 0; j < 16; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+      const float hb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float h = fmaf(__uint_as_float(raw[j + q]), 0.5f, hb[q]);
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        v[j + q] = fmaf(h, t, h);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+      v[j + 0] = __uint_as_float(raw[j + 0]) + bb.x;
+      v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
+      v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z;
+      v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
+    }
   }
   if (e.act == YX_ACT_SILU && !fp16) {
-    // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_tanh(v[j]);
   } else if (e.act != YX_ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = act_f<false>(v[j], e.act);
