@@ -20,6 +20,7 @@
 // intrinsics so that nvcc cannot contract multiplies and adds into FMAs):
 //   inter = max(0, min(x2) - max(x1)) * max(0, min(y2) - max(y1));
 //   suppressed iff inter / (area_i + area_j - inter) > thr.
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 
@@ -54,7 +55,8 @@ static constexpr int kFilterAnchors = 128;   // anchors per CTA (one per thread)
 __global__ void __launch_bounds__(kFilterAnchors)
 filter_kernel(float* __restrict__ pred, int batch, int anchors, int nc, float conf_thre, int inplace_xyxy,
               float* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ counts) {
-  extern __shared__ float frows[];                        // [kFilterAnchors][5+nc]
+  extern __shared__ __align__(128) float frows[];         // [kFilterAnchors][5+nc]
+  __shared__ uint64_t fbar;
   const int nch = 5 + nc;
   const int chunks = (anchors + kFilterAnchors - 1) / kFilterAnchors;
   const int b = blockIdx.x / chunks;
@@ -63,7 +65,19 @@ filter_kernel(float* __restrict__ pred, int batch, int anchors, int nc, float co
   const int tid = threadIdx.x, lane = tid & 31;
   float* g = pred + ((long long)b * anchors + a0) * nch;
   const int total = na * nch;
-  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+  if (tid == 0) { mbar_init(&fbar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (total & 3) == 0) {
+    // one bulk copy (TMA, no register staging) brings the CTA's rows in; 5 CTAs per SM keep ~200 KB in flight
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&fbar, (uint32_t)total * 4u);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(frows)),
+                   "l"(g), "r"((uint32_t)total * 4u), "r"(smem_u32(&fbar))
+                   : "memory");
+    }
+    mbar_wait(&fbar, 0);
+  } else if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
     const float4* g4 = reinterpret_cast<const float4*>(g);
     float4* s4 = reinterpret_cast<float4*>(frows);
     for (int i = tid; i < total / 4; i += kFilterAnchors) s4[i] = g4[i];
@@ -184,6 +198,7 @@ struct NmsArgs {
   // outputs
   int* keep; int* keep_count;      // yx_batched_nms
   float* dets; long long* det_idx; int* det_count; int max_det;  // yx_postprocess (from cand rows)
+  int debug;                       // YX_NMS_DEBUG: thread 0 prints per-phase cycle counts
 };
 
 __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
@@ -192,6 +207,8 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
+  // disjoint boxes: 0 / x is 0 (or NaN for 0 / 0), never > thr for thr >= 0 -- skip the IEEE division
+  if (inter == 0.0f && thr >= 0.0f) return false;
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   return ovr > thr;
 }
@@ -219,6 +236,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   int* kept = g.kept_pos + base;
 
   if (tid == 0) s_nkept = 0;
+  long long tk[8];
+  tk[0] = clock64();
   // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA) / 4000 (CPU)
   int variant = g.variant;
   if (variant == 3) variant = (4LL * n > 100000) ? 1 : 0;
@@ -256,6 +275,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
     }
 
+    tk[1] = clock64();
     // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
     float mx = -INFINITY, mn = INFINITY;
     int cmax = 0, cmin = 0;
@@ -300,6 +320,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     }
     __syncthreads();
 
+    tk[2] = clock64();
     // ---------------- greedy NMS, chunk by chunk ----------------
     // Which pairs can interact?  per-class variant: equal classes only.  Offset variant: class c lives in
     // [c*s + min, c*s + max] with s = max+1, so classes a < b can only overlap when (b-a)*s < max-min+1,
@@ -376,29 +397,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         const unsigned bal = __ballot_sync(0xffffffffu, dead);
         if (lane == 0) s_removed[warp] = bal;
       }
+      if (c0 == 0) tk[3] = clock64();
       // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i)
-      if (use_lists) {
-        // members of the chunk per class; each alive row only visits its class window
-#pragma unroll
-        for (int w = 0; w < kChunkWords; ++w) cmask[tid * kChunkWords + w] = 0u;
-        if (!dead) cnext[tid] = atomicExch(&chead[my_cls], tid);
-        __syncthreads();
-        if (!dead) {
-          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1); ++c2)
-            for (int j = chead[c2]; j >= 0; j = cnext[j])
-              if (j > tid && suppresses(me, my_area, cbox[j], carea[j], g.thr))
-                cmask[tid * kChunkWords + (j >> 5)] |= (1u << (j & 31));
-        }
-        __syncthreads();
-        if (!dead) chead[my_cls] = -1;                       // leave the heads clean for the next chunk
-      } else {
+      {
         __syncthreads();
         // balanced enumeration of the (row, word) items of the upper triangle: rows of group rb = row/32
         // have (16 - rb) words each
-        for (int q = tid; q < kTriItems; q += kNmsThreads) {
+        // (the class gate costs ~5 instructions per pair, the IoU only runs inside the class window; walking
+        // per-class lists instead degenerates to divergent pointer chasing when a few classes dominate)
+        const int nw = (cn + 31) >> 5;
+        const int items = 32 * (nw * (nw + 1) / 2);
+        for (int q = tid; q < items; q += kNmsThreads) {
           int rb = 0, rem = q;
-          while (rem >= 32 * (kChunkWords - rb)) { rem -= 32 * (kChunkWords - rb); ++rb; }
-          const int per = kChunkWords - rb;
+          while (rem >= 32 * (nw - rb)) { rem -= 32 * (nw - rb); ++rb; }
+          const int per = nw - rb;
           const int row = rb * 32 + rem / per;
           const int w = rb + rem % per;
           unsigned bits = 0u;
@@ -419,31 +431,42 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         }
         __syncthreads();
       }
-      // ---- phase C: one warp walks the chunk; lane w owns word w of the removed set
+      if (c0 == 0) tk[4] = clock64();
+      // ---- phase C: one warp walks the chunk word by word (32 candidates); lane l owns word l of the removed
+      //      set. Inside a word the greedy order is resolved on the 32x32 diagonal block held in registers;
+      //      the kept rows are then OR-ed into the later words with one warp reduction per word.
       if (warp == 0) {
         unsigned removed = lane < kChunkWords ? s_removed[lane] : 0xffffffffu;
         int cnt = 0;
-        int pos = 0;
-        while (true) {
-          unsigned alive = (lane < kChunkWords) ? ~removed : 0u;
-          const int wpos = pos >> 5;
-          if (lane < wpos) alive = 0u;
-          else if (lane == wpos) alive &= (0xffffffffu << (pos & 31));
-          const unsigned has = __ballot_sync(0xffffffffu, alive != 0u);
-          if (has == 0u) break;
-          const int wsel = __ffs(has) - 1;
-          const unsigned aw = __shfl_sync(0xffffffffu, alive, wsel);
-          const int i = wsel * 32 + (__ffs(aw) - 1);
-          if (i >= cn) break;
-          if (lane == 0) ck[cnt] = i;
-          ++cnt;
-          if (lane < kChunkWords) removed |= cmask[i * kChunkWords + lane];
-          pos = i + 1;
-          if (pos >= cn) break;
+        const int nwords = (cn + 31) >> 5;
+        for (int w = 0; w < nwords; ++w) {
+          unsigned a = ~__shfl_sync(0xffffffffu, removed, w);          // alive candidates of word w
+          if (a == 0u) continue;
+          const unsigned dj = cmask[(w * 32 + lane) * kChunkWords + w];  // row (w*32 + lane), bits of the same word
+          unsigned keptw = a;
+          // common case: no alive box of the word suppresses another alive box of the word
+          if (__any_sync(0xffffffffu, ((a >> lane) & 1u) && (dj & a) != 0u)) {
+            // 32 fixed steps: the shuffles do not depend on the chain, each step is a test + and-not
+            keptw = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const unsigned di = __shfl_sync(0xffffffffu, dj, i);
+              if ((a >> i) & 1u) { keptw |= 1u << i; a &= ~di; }
+            }
+          }
+          const bool mine = (keptw >> lane) & 1u;
+          if (mine) ck[cnt + __popc(keptw & ((1u << lane) - 1u))] = w * 32 + lane;
+          cnt += __popc(keptw);
+          // rows of the kept boxes OR-ed into the later words: lane i contributes its row, one warp reduction per word
+          for (int l = w + 1; l < nwords; ++l) {
+            const unsigned r = __reduce_or_sync(0xffffffffu, mine ? cmask[(w * 32 + lane) * kChunkWords + l] : 0u);
+            if (lane == l) removed |= r;
+          }
         }
         if (lane == 0) s_ck = cnt;
       }
       __syncthreads();
+      if (c0 == 0) tk[5] = clock64();
       // ---- append the chunk's survivors to the kept list (parallel; list order is irrelevant)
       {
         const int cnt = s_ck;
@@ -466,6 +489,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
 
   // ---------------- outputs ----------------
   const int nk = s_nkept;
+  tk[6] = clock64();
   if (g.keep) {
     for (int k = tid; k < nk; k += kNmsThreads) g.keep[base + k] = sidx[kept[k]];
     if (tid == 0) g.keep_count[b] = nk;
@@ -482,6 +506,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     }
     if (tid == 0) g.det_count[b] = nk;  // true number kept; rows beyond max_det are dropped
   }
+  if (g.debug && tid == 0 && n > 0)
+    printf("nms b=%d n=%d kept=%d sort=%lld gather=%lld A=%lld B=%lld C=%lld rest=%lld out=%lld\n", b, n, nk, tk[1] - tk[0],
+           tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], clock64() - tk[6]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -547,6 +574,7 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.smem_keys_cap = smem_keys_cap(g.src.per_image);
   g.kept_cap = kept_cap_for(g.src.per_image);
   g.gkeys_stride = next_pow2_ll(g.src.per_image);
+  g.debug = getenv("YX_NMS_DEBUG") ? 1 : 0;
   const size_t smem = nms_smem_bytes(g.src.per_image);
   static size_t configured = 0;
   if (smem > configured) {
