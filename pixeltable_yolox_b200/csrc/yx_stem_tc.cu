@@ -143,21 +143,24 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       uint8_t* a0 = astage + (size_t)stage * 32768 + (size_t)m * 128;
       uint32_t wds[4];
       int nw = 0, chunk = 0;
+      // two batches of 27 independent shared loads (3 dy x 3 c x 3 pairs) so that the load latency is paid
+      // twice per row instead of once per pair
 #pragma unroll
-      for (int dy = 0; dy < 6; ++dy) {
+      for (int half = 0; half < 2; ++half) {
+        float fa[27], fb[27];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int i = 0; i < 27; ++i) {
+          const int dy = half * 3 + i / 9, c = (i % 9) / 3, q = i % 3;
           const TI* src = pt + (c * kPatchRows + 2 * hl + dy) * kPitch + kLead + 2 * wl;
+          load_pair<TI>(src + 2 * q, fa[i], fb[i]);
+        }
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            float fa, fb;
-            load_pair<TI>(src + 2 * q, fa, fb);
-            wds[nw++] = pack16(fa, fb, fp16);
-            if (nw == 4) {
-              uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-              nw = 0; ++chunk;
-            }
+        for (int i = 0; i < 27; ++i) {
+          wds[nw++] = pack16(fa[i], fb[i], fp16);
+          if (nw == 4) {
+            uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            nw = 0; ++chunk;
           }
         }
       }
