@@ -309,8 +309,16 @@ def run_ours(args):
             for p in prof:
                 print(f"# {p['name']:44s} {p['ms']*1e3:9.1f} us  {p['flops']/max(p['ms'],1e-9)/1e9:8.1f} TFLOP/s  "
                       f"{p['bytes']/max(p['ms'],1e-9)/1e6:8.1f} GB/s", file=sys.stderr)
+        traffic, traffic_src = None, None
+        tfiles = sorted((ROOT / "profiles").glob("*_traffic.json"))
+        if tfiles:                                   # DRAM bytes per launch of the same kernel from the committed ncu pass
+            tj = json.loads(tfiles[-1].read_text())
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), f"profiles/{tfiles[-1].name}"
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+                "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": tc_flops / max(len(tc), 1),
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "launches": len(tc), "avg_launch_us": 1e3 * tc_ms / max(len(tc), 1), "share_of_step": tc_ms / all_ms,
                 "whole_step_frac_of_peak": GFLOP_PER_IMAGE.get(args.model, 0) * 1e9 * (value / world) / (pk["tf_sustained"] * 1e12)}
