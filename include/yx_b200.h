@@ -99,6 +99,29 @@ typedef struct yx_conv_desc {
 
 /* tcgen05/TMEM/TMA implicit GEMM for bf16/fp16; routes YX_FP32 to the SIMT kernel. */
 int yx_conv_bn_act_fwd(const yx_conv_desc* d, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Fused Bottleneck: y = [x +] act(bn2(conv3x3(act(bn1(conv1x1(x))))))  in one kernel
+ *   replaces Bottleneck.forward (yolox/models/network_blocks.py:77-99: conv1 1x1, conv2 3x3,
+ *   `y + x` when use_add) with hidden == in == out channels (CspLayer passes expansion = 1.0,
+ *   network_blocks.py:169-172). The hidden tensor stays in shared memory / TMEM.
+ *   x   : NHWC slice, c channels, per-pixel stride x_ld;  out: NHWC slice (out_ld), MUST NOT alias x
+ *   w1  : [c][1][c], w2: [c][9][c] packed like yx_conv_desc.w (BN folded); bias1/bias2 fp32 [c]
+ * Constraints: c in {16, 32, 64}; dtype bf16/fp16; x_ld, out_ld multiples of 16; x/out 32-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yx_bneck_desc {
+  int32_t batch, h, w, c;
+  int32_t dtype;    /* YX_BF16 | YX_FP16 */
+  int32_t act;      /* yx_act of both convs */
+  int32_t use_add;  /* 1: shortcut (network_blocks.py:97-98) */
+  const void* x;    int64_t x_ld;
+  const void* w1;   const float* bias1;
+  const void* w2;   const float* bias2;
+  void* out;        int64_t out_ld;
+} yx_bneck_desc;
+int yx_bottleneck_fwd(const yx_bneck_desc* d, void* stream);
+/* 1 when yx_bottleneck_fwd supports this shape (callers fall back to two yx_conv_bn_act_fwd). */
+int yx_bottleneck_supported(const yx_bneck_desc* d);
+
 /* CUDA-core (FFMA, fp32 accumulate in K order) implementation of the same contract for every
  * dtype: the fp32 verification mode and the on-device cross-check of the tensor-core kernel. */
 int yx_conv_bn_act_fwd_simt(const yx_conv_desc* d, void* stream);
@@ -225,6 +248,7 @@ typedef struct yx_plan yx_plan;
 yx_plan* yx_plan_create(void);
 void yx_plan_destroy(yx_plan* p);
 int yx_plan_add_conv(yx_plan* p, const yx_conv_desc* d);
+int yx_plan_add_bottleneck(yx_plan* p, const yx_bneck_desc* d);
 int yx_plan_add_dwconv(yx_plan* p, const void* in, int64_t in_ld, const void* w, const float* bias,
                        void* out, int64_t out_ld, int32_t batch, int32_t in_h, int32_t in_w,
                        int32_t c, int32_t stride, int32_t act, int32_t dtype);

@@ -43,6 +43,19 @@ class ConvDesc(C.Structure):
     ]
 
 
+class BneckDesc(C.Structure):
+    """Mirror of ``yx_bneck_desc`` (include/yx_b200.h)."""
+
+    _fields_ = [
+        ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("dtype", C.c_int32), ("act", C.c_int32), ("use_add", C.c_int32),
+        ("x", C.c_void_p), ("x_ld", C.c_int64),
+        ("w1", C.c_void_p), ("bias1", C.c_void_p),
+        ("w2", C.c_void_p), ("bias2", C.c_void_p),
+        ("out", C.c_void_p), ("out_ld", C.c_int64),
+    ]
+
+
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); mirrors include/yx_b200.h one to one
@@ -53,6 +66,8 @@ SIGNATURES = {
     "yx_device_check": (C.c_int, [C.c_int]),
     "yx_conv_bn_act_fwd": (C.c_int, [C.POINTER(ConvDesc), _P]),
     "yx_conv_bn_act_fwd_simt": (C.c_int, [C.POINTER(ConvDesc), _P]),
+    "yx_bottleneck_fwd": (C.c_int, [C.POINTER(BneckDesc), _P]),
+    "yx_bottleneck_supported": (C.c_int, [C.POINTER(BneckDesc)]),
     "yx_dwconv3x3_bn_act_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_spp_maxpool": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_focus_s2d": (C.c_int, [_P, _I32, _P, _I64, _I32, _I32, _I32, _I32, _P]),
@@ -70,6 +85,7 @@ SIGNATURES = {
     "yx_plan_create": (_P, []),
     "yx_plan_destroy": (None, [_P]),
     "yx_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),
+    "yx_plan_add_bottleneck": (C.c_int, [_P, C.POINTER(BneckDesc)]),
     "yx_plan_add_dwconv": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_spp": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_focus": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32]),

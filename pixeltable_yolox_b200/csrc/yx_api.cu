@@ -50,6 +50,12 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
 int stem_launch(const StemLaunch* L, cudaStream_t stream);
 ConvTcLaunch* conv_tc_alloc();
 void conv_tc_free(ConvTcLaunch*);
+struct BneckLaunch;
+BneckLaunch* bneck_alloc();
+void bneck_free(BneckLaunch*);
+bool bneck_supported(const yx_bneck_desc* d);
+int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L);
+int bneck_launch(const BneckLaunch* L, cudaStream_t stream);
 
 // ---- error plumbing ----
 static thread_local char g_err[512] = "";
@@ -107,12 +113,13 @@ static int require_device() {
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP_STEM };
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP_STEM, OP_BNECK };
 
 struct Op {
   OpKind kind;
   ConvTcLaunch* tc;  // OP_CONV_TC
   StemLaunch* stem;  // OP_STEM
+  BneckLaunch* bneck;  // OP_BNECK
   yx_conv_desc conv;  // OP_CONV_SIMT
   struct { const void* in; long long in_ld; const void* w; const float* bias; void* out; long long out_ld;
            int batch, in_h, in_w, c, stride, act, dtype; } dw;
@@ -138,6 +145,7 @@ static int run_op(const Op& o, cudaStream_t s) {
   switch (o.kind) {
     case OP_CONV_TC: return conv_tc_launch(o.tc, s);
     case OP_STEM: return stem_launch(o.stem, s);
+    case OP_BNECK: return bneck_launch(o.bneck, s);
     case OP_CONV_SIMT: return conv_simt_launch(&o.conv, s);
     case OP_DWCONV: return dwconv_launch(o.dw.in, o.dw.in_ld, o.dw.w, o.dw.bias, o.dw.out, o.dw.out_ld, o.dw.batch,
                                          o.dw.in_h, o.dw.in_w, o.dw.c, o.dw.stride, o.dw.act, o.dw.dtype, s);
@@ -195,6 +203,18 @@ int yx_conv_bn_act_fwd(const yx_conv_desc* d, void* stream) {
   rc = conv_tc_prepare(d, L);
   if (rc == YX_OK) rc = conv_tc_launch(L, (cudaStream_t)stream);
   conv_tc_free(L);
+  return rc;
+}
+
+int yx_bottleneck_supported(const yx_bneck_desc* d) { return bneck_supported(d) ? 1 : 0; }
+
+int yx_bottleneck_fwd(const yx_bneck_desc* d, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  BneckLaunch* L = bneck_alloc();
+  rc = bneck_prepare(d, L);
+  if (rc == YX_OK) rc = bneck_launch(L, (cudaStream_t)stream);
+  bneck_free(L);
   return rc;
 }
 
@@ -322,6 +342,7 @@ void yx_plan_destroy(yx_plan* p) {
   for (auto& o : p->ops) {
     if (o.tc) conv_tc_free(o.tc);
     if (o.stem) stem_free(o.stem);
+    if (o.bneck) bneck_free(o.bneck);
   }
   delete p;
 }
@@ -349,6 +370,22 @@ int yx_plan_add_conv(yx_plan* p, const yx_conv_desc* d) {
     rc = conv_tc_prepare(d, o.tc);
     if (rc) { conv_tc_free(o.tc); return rc; }
   }
+  p->ops.push_back(o);
+  p->launches += 1;
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_bottleneck(yx_plan* p, const yx_bneck_desc* d) {
+  YX_REQUIRE(p && d, YX_ERR_INVALID_ARG, "plan_add_bottleneck: null");
+  int rc = require_device();
+  if (rc) return rc;
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_BNECK;
+  o.bneck = bneck_alloc();
+  rc = bneck_prepare(d, o.bneck);
+  if (rc) { bneck_free(o.bneck); return rc; }
   p->ops.push_back(o);
   p->launches += 1;
   plan_invalidate(p);

@@ -105,15 +105,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// n / d for 0 <= n < 2^31 with mul = floor(2^32 / d) + 1 (d >= 2); the estimate is never low and at most 1 high
-__device__ __forceinline__ int fast_div(int n, unsigned mul, int d) {
-  if (d == 1) return n;
-  int q = (int)__umulhi((unsigned)n, mul);
-  if ((long long)q * d > n) --q;
-  return q;
-}
-static inline unsigned fast_div_mul(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d) + 1u; }
-
 // ---- halo-mode MMA issue helpers (run by the one elected lane of the MMA warp) ----
 // resident weights, one M tile: 9 taps x KS k-steps, descriptors advance by compile-time constants
 template <int KS, int TAPS>

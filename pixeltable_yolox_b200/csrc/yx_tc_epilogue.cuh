@@ -6,6 +6,15 @@
 
 namespace yx {
 
+// n / d for 0 <= n < 2^31 with mul = floor(2^32 / d) + 1 (d >= 2); the estimate is never low and at most 1 high
+__device__ __forceinline__ int fast_div(int n, unsigned mul, int d) {
+  if (d == 1) return n;
+  int q = (int)__umulhi((unsigned)n, mul);
+  if ((long long)q * d > n) --q;
+  return q;
+}
+inline unsigned fast_div_mul(int d) { return d <= 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)d) + 1u; }
+
 __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])

@@ -198,6 +198,58 @@ class Builder:
                                  tc=self.dtype != torch.float32))
         return out
 
+    def probe_feat(self, like: Feat, c: int) -> Feat:
+        """A shape-only Feat (no storage of its own) for asking capability questions before allocating."""
+        return Feat(like.t, like.c_off, [c])
+
+    def bottleneck_fusable(self, x: Feat, m) -> bool:
+        """True when Bottleneck `m` can run as the single fused kernel (yx_bottleneck_fwd)."""
+        import os
+
+        from .network_blocks import BaseConv
+
+        if os.environ.get("YX_FUSE_BNECK", "1") == "0" or self.dtype == torch.float32:
+            return False
+        c1, c2 = m.conv1, m.conv2
+        if not isinstance(c2, BaseConv) or c2.conv.groups != 1 or c2.conv.kernel_size != (3, 3) or c2.conv.stride != (1, 1):
+            return False
+        c = c1.conv.in_channels
+        if not (c1.conv.out_channels == c and c2.conv.in_channels == c and c2.conv.out_channels == c):
+            return False
+        if type(c1.act) is not type(c2.act) or len(x.segs) != 1 or x.segs[0] != c:
+            return False
+        return c in (16, 32, 64)
+
+    def bottleneck(self, x: Feat, m, out: Feat) -> Feat:
+        """Fused Bottleneck (1x1 -> 3x3 -> optional shortcut) as one launch; `out` must not alias `x`."""
+        from ._lib import BneckDesc
+        from .network_blocks import act_name
+
+        w1, b1, _ = self._pack([self.part(m.conv1)], x, 1, None)
+        hid = Feat(x.t, x.c_off, list(x.segs))               # same channel structure as the hidden tensor
+        w2, b2, _ = self._pack([self.part(m.conv2)], hid, 3, None)
+        c = x.segs[0]
+        xv, ov = x.view(), out.view()
+        d = BneckDesc()
+        d.batch, d.h, d.w, d.c = x.B, x.H, x.W, c
+        d.dtype = dtype_code(self.dtype)
+        d.act = ACT_CODES[act_name(m.conv1.act)]
+        d.use_add = 1 if m.use_add else 0
+        d.x, d.x_ld = xv.ptr, xv.ld
+        d.w1, d.bias1, d.w2, d.bias2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+        d.out, d.out_ld = ov.ptr, ov.ld
+        if self.plan is not None:
+            check(lib().yx_plan_add_bottleneck(self.plan, C.byref(d)), "plan_add_bottleneck")
+        else:
+            check(lib().yx_bottleneck_fwd(C.byref(d), stream_ptr(self.dev)), "bottleneck")
+        self.n_ops += 1
+        fl = 2.0 * x.B * x.H * x.W * c * c * 10
+        esz = w1.element_size()
+        self.flops += fl
+        self.op_info.append(dict(name=f"bottleneck {c} @{x.H}x{x.W}", flops=fl,
+                                 bytes=2 * x.B * x.H * x.W * c * esz + (w1.numel() + w2.numel()) * esz, tc=True))
+        return out
+
     def _emit_conv(self, d):
         if self.plan is not None:
             check(lib().yx_plan_add_conv(self.plan, C.byref(d)), "plan_add_conv")

@@ -106,6 +106,11 @@ class Bottleneck(_B200Block):
         return y + x if self.use_add else y
 
     def lower(self, b, x, out=None):
+        if b.bottleneck_fusable(x, self) and (out is None or out.t is not x.t or out.c_off != x.c_off):
+            # one kernel: the hidden tensor never leaves the SM (yx_bottleneck_fwd); cannot run in place
+            if out is None:
+                out = b.new_feat(x.B, x.H, x.W, [self.conv2.conv.out_channels])
+            return b.bottleneck(x, self, out)
         # the residual is added in the epilogue of conv2; writing in place over x is safe because
         # conv2 reads only conv1's output and each thread reads x[p] before it writes out[p]
         t = self.conv1.lower(b, x)
@@ -180,6 +185,27 @@ class CspLayer(_B200Block):
         # buffer [x_1 | x_2]; the bottleneck chain then updates the x_1 half in place, so the
         # torch.cat of the reference (network_blocks.py:182) never happens.
         hidden = self.conv1.conv.out_channels
+        if len(self.m) > 0 and all(b.bottleneck_fusable(b.probe_feat(x, hidden), blk) for blk in self.m):
+            # fused bottlenecks cannot run in place: buffer [y | x_2 | x_1]; the stacked GEMM writes
+            # [x_2 | x_1], the chain ping-pongs x_1 -> tmp -> ... and its last link writes y; conv3 reads
+            # [y | x_2] (the torch.cat of network_blocks.py:182 in the reference's channel order)
+            buf = b.new_feat(x.B, x.H, x.W, [hidden, hidden, hidden])
+            from .engine import Feat
+
+            b.conv(x, [b.part(self.conv2), b.part(self.conv1)], out=Feat(buf.t, buf.seg_off(1), [hidden, hidden]),
+                   act=act_name(self.conv1.act), ksize=1, stride=1)
+            cur, tmp = buf.seg(2), None
+            for i, blk in enumerate(self.m):
+                if i == len(self.m) - 1:
+                    dst = buf.seg(0)
+                elif cur.c_off == buf.seg_off(2) and cur.t is buf.t:
+                    tmp = tmp or b.new_feat(x.B, x.H, x.W, [hidden])
+                    dst = tmp
+                else:
+                    dst = buf.seg(2)
+                blk.lower(b, cur, out=dst)
+                cur = dst
+            return self.conv3.lower(b, Feat(buf.t, 0, [hidden, hidden]), out=out)
         cat = b.conv(x, [b.part(self.conv1), b.part(self.conv2)], act=act_name(self.conv1.act), ksize=1, stride=1)
         x1 = cat.seg(0)
         for blk in self.m:

@@ -302,3 +302,20 @@ def simota_matching_device(cost: torch.Tensor, ious: torch.Tensor):
     check(lib().yx_simota_matching(cost.data_ptr(), ious.data_ptr(), G, n, n, mg.data_ptr(), mi.data_ptr(),
                                    nf.data_ptr(), stream_ptr(dev)), "simota_matching")
     return mg, mi, nf
+
+
+def bottleneck_fwd(x: View, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, out: View,
+                   act: int, use_add: bool) -> None:
+    """Fused Bottleneck (network_blocks.py:77-99): out = [x +] act(conv3x3(act(conv1x1(x)))); w1 [c,1,c], w2 [c,9,c]."""
+    from ._lib import BneckDesc
+
+    require_cuda(x.t, "bottleneck_fwd")
+    d = BneckDesc()
+    d.batch, d.h, d.w, d.c = x.B, x.H, x.W, x.c
+    d.dtype = dtype_code(x.t.dtype)
+    d.act = act
+    d.use_add = 1 if use_add else 0
+    d.x, d.x_ld = x.ptr, x.ld
+    d.w1, d.bias1, d.w2, d.bias2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    d.out, d.out_ld = out.ptr, out.ld
+    check(lib().yx_bottleneck_fwd(C.byref(d), stream_ptr(x.t.device)), "bottleneck_fwd")

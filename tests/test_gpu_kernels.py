@@ -75,6 +75,61 @@ def test_conv_tcgen05_fusions(cuda, k, s):
         assert err <= 1.5e-2, (act, err)
 
 
+def _bneck_case(dev, B, H, W, c, dtype, use_add, act, in_off=0, out_off=0, seed=0):
+    """Fused Bottleneck against torch: fp32 math with the hidden tensor rounded to the 16-bit dtype, exactly
+    what the reference's two 16-bit BaseConvs do (network_blocks.py:77-99)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, H, W, c + 2 * in_off, generator=g).to(dev).to(dtype)
+    w1 = (torch.randn(c, 1, c, generator=g) / c ** 0.5).to(dev).to(dtype)
+    w2 = (torch.randn(c, 9, c, generator=g) / (9 * c) ** 0.5).to(dev).to(dtype)
+    b1 = torch.randn(c, generator=g).to(dev)
+    b2 = torch.randn(c, generator=g).to(dev)
+    o = torch.full((B, H, W, c + 2 * out_off), 7.0, device=dev, dtype=dtype)
+    xin, ov = View(x, in_off, c), View(o, out_off, c)
+    ops.bottleneck_fwd(xin, w1, b1, w2, b2, ov, _lib.ACT_CODES[act], use_add)
+    f = {"silu": F.silu, "relu": F.relu, "lrelu": lambda t: F.leaky_relu(t, 0.1)}[act]
+    xf = xin.torch().float().permute(0, 3, 1, 2)
+    h = f(F.conv2d(xf, w1.float().reshape(c, 1, 1, c).permute(0, 3, 1, 2), b1)).to(dtype).float()
+    y = f(F.conv2d(h, w2.float().reshape(c, 3, 3, c).permute(0, 3, 1, 2), b2, 1, 1))
+    if use_add:
+        y = y + xf
+    y = y.permute(0, 2, 3, 1)
+    got = ov.torch().float()
+    if out_off:
+        assert (o[..., :out_off] == 7).all() and (o[..., out_off + c:] == 7).all(), "wrote outside the channel slice"
+    return ((got - y).abs() / y.abs().clamp_min(1.0)).max().item()
+
+
+BNECK_CASES = [(2, 16, 16, 64), (1, 80, 80, 64), (3, 40, 40, 32), (1, 160, 160, 32), (2, 13, 21, 16), (1, 5, 3, 64),
+               (5, 23, 61, 32), (2, 80, 80, 16)]
+
+
+@pytest.mark.parametrize("case", BNECK_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fused_bottleneck_vs_torch(cuda, case, dtype):
+    # tolerance: one 16-bit rounding of the output plus hidden values that round differently at a tie
+    # (tanh.approx SiLU vs torch's exp form) propagated through the 3x3 conv
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    for use_add in (True, False):
+        err = _bneck_case(cuda, *case, dtype, use_add, "silu")
+        assert err <= tol, (use_add, err)
+
+
+def test_fused_bottleneck_slices_and_acts(cuda):
+    for act in ("silu", "relu", "lrelu"):
+        err = _bneck_case(cuda, 2, 24, 40, 32, torch.bfloat16, True, act, in_off=32, out_off=16)
+        assert err <= 2e-2, (act, err)
+
+
+def test_fused_bottleneck_rejects_in_place(cuda):
+    x = torch.zeros(1, 8, 8, 64, device=cuda, dtype=torch.bfloat16)
+    w1 = torch.zeros(64, 1, 64, device=cuda, dtype=torch.bfloat16)
+    w2 = torch.zeros(64, 9, 64, device=cuda, dtype=torch.bfloat16)
+    b = torch.zeros(64, device=cuda)
+    with pytest.raises(RuntimeError, match="alias"):
+        ops.bottleneck_fwd(View(x), w1, b, w2, b, View(x), 1, True)
+
+
 @pytest.mark.parametrize("case", TC_CASES[::3])
 def test_conv_simt_fp32_vs_torch(cuda, case):
     err = _conv_case(cuda, *case, torch.float32, True, True, 16, 16, "silu", simt=True)
