@@ -25,7 +25,7 @@
 namespace yx {
 
 static constexpr int kBnX = 6;          // max X halo slots
-static constexpr int kBnThreads = 64 + 128 + 128;
+static constexpr int kBnThreads = 64 + 256 + 256;   // TMA + MMA warps, 8 epilogue-1 warps (4 per GEMM1 tile), 8 epilogue-2 warps
 
 struct BneckParams {
   int C, Cpad;               // channels (= N = K), TMEM column pitch
@@ -39,9 +39,14 @@ struct BneckParams {
   unsigned desc_hi, idesc, tmem_cols, bias_bytes, swz_mask;
   unsigned mul_tpi, mul_tw;
   int act1;
+  int trace;
   const float* bias1;
   EpiParams epi;             // second conv: bias2, act, out, res (= x when the block has a shortcut)
 };
+
+// YX_BNECK_TRACE=1: CTA 0 records clock64() at the hand-off points of its first tiles (diagnostic)
+__device__ long long g_bneck_trace[4][16][4];
+#define BN_TRACE(role, it, k) do { if (p.trace && blockIdx.x == 0 && (it) < 16 && (threadIdx.x & 31) == 0 && ((role) != 1 || warp == 2) && ((role) != 2 || warp == 10 || warp == 14)) g_bneck_trace[role][it][k] = clock64(); } while (0)
 
 struct __align__(8) BneckShared {
   uint64_t xfull[kBnX], xempty[kBnX];
@@ -52,11 +57,14 @@ struct __align__(8) BneckShared {
   uint32_t tmem_base;
 };
 
+template <bool FP16, int KS>
 __global__ void __launch_bounds__(kBnThreads, 1)
 bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                 const __grid_constant__ CUtensorMap map_w2, const BneckParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space known to the
+  // compiler: LDS/STS instead of generic loads for every bias / staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   BneckShared* sh = reinterpret_cast<BneckShared*>(smem);
   float* sbias1 = reinterpret_cast<float*>(smem + 1024);
   float* sbias2 = sbias1 + p.bias_bytes / 4;
@@ -66,7 +74,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   uint8_t* w2s = w1s + p.w_tile_bytes;                            // [9][C x C]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool fp16 = (p.epi.dtype == YX_FP16);
+  constexpr bool fp16 = FP16;
+  constexpr int C = 16 * KS;                            // channels: loops over them unroll completely
   {
     const bool half1 = (p.act1 == YX_ACT_SILU && !fp16);
     const float s1 = half1 ? 0.5f : 1.0f, s2 = epi_half_bias(p.epi) ? 0.5f : 1.0f;
@@ -76,8 +85,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
     for (int i = 0; i < p.nx; ++i) { mbar_init(&sh->xfull[i], 1); mbar_init(&sh->xempty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sh->a1full[i], 1); mbar_init(&sh->a1empty[i], 128);
-      mbar_init(&sh->hfull[i], 128); mbar_init(&sh->hempty[i], 1);
+      mbar_init(&sh->a1full[i], 1); mbar_init(&sh->a1empty[i], 256);
+      mbar_init(&sh->hfull[i], 256); mbar_init(&sh->hempty[i], 1);
       mbar_init(&sh->a2full[i], 1); mbar_init(&sh->a2empty[i], 128);
     }
     mbar_init(&sh->wfull, 1);
@@ -112,6 +121,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int ty = fast_div(r, p.mul_tw, p.tiles_w);
         const int tx = r - ty * p.tiles_w;
         mbar_wait(&sh->xempty[sx], px ^ 1);
+        BN_TRACE(3, t - t_begin, 0);
         mbar_arrive_expect_tx(&sh->xfull[sx], p.x_tx_bytes);
         tma_load_4d(&map_x, &sh->xfull[sx], xs + (size_t)sx * p.x_slot_bytes, 0, tx * p.tw - 1, ty * p.th - 1, b);
         if (++sx == p.nx) { sx = 0; px ^= 1; }
@@ -126,7 +136,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint64_t w1d = dhi | (uint64_t)(smem_u32(w1s) >> 4);
     const uint32_t w2_16 = smem_u32(w2s) >> 4, wt16 = p.w_tile_bytes >> 4;
     const uint32_t idesc = p.idesc;
-    const int ks = p.ksteps;
+    constexpr int ks = KS;
     mbar_wait(&sh->wfull, 0);
     int sx = 0;
     uint32_t px = 0;
@@ -134,7 +144,9 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     auto gemm1 = [&](int k) {
       const int st = k & 1;
       mbar_wait(&sh->xfull[sx], px);
+      BN_TRACE(3, k, 1);
       mbar_wait(&sh->a1empty[st], (uint32_t)(((k >> 1) & 1) ^ 1));
+      BN_TRACE(3, k, 2);
       tc_fence_after();
       if (elect_one_sync()) {
         const uint64_t xd = dhi | (uint64_t)(x16 + (uint32_t)sx * xslot16);
@@ -142,6 +154,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const uint64_t a = xd + (uint64_t)(mt * 128) * rb16;
+#pragma unroll
           for (int j = 0; j < ks; ++j) umma_f16(d0 + (uint32_t)(mt * p.Cpad), a + 2 * j, w1d + 2 * j, idesc, (uint32_t)(j != 0));
         }
         umma_commit(&sh->a1full[st]);
@@ -153,10 +166,13 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (n_my > 0) gemm1(0);
     for (int it = 0; it < n_my; ++it) {
       if (it + 1 < n_my) gemm1(it + 1);
+      BN_TRACE(0, it, 0);
       const int st = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       mbar_wait(&sh->hfull[st], ph);
+      BN_TRACE(0, it, 1);
       mbar_wait(&sh->a2empty[st], ph ^ 1);
+      BN_TRACE(0, it, 2);
       tc_fence_after();
       if (elect_one_sync()) {
         const uint64_t hd = dhi | (uint64_t)(h16 + (uint32_t)st * hslot16);
@@ -165,20 +181,28 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int tap = 0; tap < 9; ++tap) {
           const uint64_t a = hd + (uint64_t)((uint32_t)(tap / 3) * prb16 + (uint32_t)(tap % 3) * rb16);
           const uint64_t b = dhi | (uint64_t)(w2_16 + (uint32_t)tap * wt16);
+#pragma unroll
           for (int j = 0; j < ks; ++j) umma_f16(d2, a + 2 * j, b + 2 * j, idesc, (uint32_t)((tap | j) != 0));
         }
         umma_commit(&sh->a2full[st]);
         umma_commit(&sh->hempty[st]);
       }
       __syncwarp();
+      BN_TRACE(0, it, 3);
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ===================== epilogue 1: h = act(acc1 + b1) -> swizzled shared operand =====================
+    // warps 2..5 own GEMM1 tile 0 (halo rows 0..127), warps 6..9 tile 1 (rows 128..)
     const int quarter = warp & 3;
     const int t128 = quarter * 32 + lane;                 // TMEM lane = row inside the 128-row MMA tile
-    int yy[2], xx[2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) { const int q = mt * 128 + t128; yy[mt] = q / p.pitch; xx[mt] = q - yy[mt] * p.pitch; }
+    const int mt = (warp - 2) >> 2;
+    const int q = mt * 128 + t128;
+    const int yy = q / p.pitch, xx = q - yy * p.pitch;
+    const bool warp_live = mt * 128 + quarter * 32 < p.halo_rows + 2;   // (warp-uniform) rows some tap of a real output reads
+    const bool stored = q < p.halo_rows + 2;
+    const uint32_t rowoff = (uint32_t)q * (uint32_t)(C * 2);
+    // canonical K-major layout: the 16-byte chunk index is XOR-ed with address bits [7, 7 + log2(mask + 1)) of the row
+    const uint32_t xr = (rowoff >> 7) & (C == 64 ? 7u : (C == 32 ? 3u : 1u));
     const bool silu_tanh1 = (p.act1 == YX_ACT_SILU && !fp16);
     for (int it = 0; it < n_my; ++it) {
       const int t = t_begin + it;
@@ -188,57 +212,71 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int tx = r - ty * p.tiles_w;
       const int st = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      BN_TRACE(1, it, 0);
       mbar_wait(&sh->a1full[st], ph);
+      BN_TRACE(1, it, 1);
       mbar_wait(&sh->hempty[st], ph ^ 1);
+      BN_TRACE(1, it, 2);
       tc_fence_after();
       uint8_t* hslot = hs + (size_t)st * p.h_slot_bytes;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int q = mt * 128 + t128;
-        if (mt * 128 + quarter * 32 >= p.halo_rows + 2) continue;   // (warp-uniform) rows no tap of a real output reads
-        const bool stored = q < p.halo_rows + 2;
-        const int iy = ty * p.th - 1 + yy[mt], ix = tx * p.tw - 1 + xx[mt];
+      if (warp_live) {
+        const int iy = ty * p.th - 1 + yy, ix = tx * p.tw - 1 + xx;
         const bool inside = (q < p.halo_rows) && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && b < p.batch;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc1_col + (uint32_t)((st * 2 + mt) * p.Cpad);
-        const uint32_t rowoff = (uint32_t)q * p.row_bytes;
-        for (int c = 0; c < p.C; c += 16) {
-          uint32_t raw[16];
-          tmem_ld_x16(taddr + (uint32_t)c, raw);
-          tmem_ld_wait();
+        // 16 hidden channels of this thread's halo pixel: bias + act -> two swizzled 16-byte chunks
+        auto emit = [&](const uint32_t (&raw)[16], int c) {
           uint32_t w[8];
           if (inside) {
             float v[16];
             if (silu_tanh1) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float h = fmaf(__uint_as_float(raw[j]), 0.5f, sbias1[c + j]);
-                float tt;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(tt) : "f"(h));
-                v[j] = fmaf(h, tt, h);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(sbias1 + c + j);
+                const float hb[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float h = fmaf(__uint_as_float(raw[j + u]), 0.5f, hb[u]);
+                  float tt;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(tt) : "f"(h));
+                  v[j + u] = fmaf(h, tt, h);
+                }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = act_f<false>(__uint_as_float(raw[j]) + sbias1[c + j], p.act1);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack16(v[2 * j], v[2 * j + 1], fp16);
+            for (int j = 0; j < 8; ++j) w[j] = pack16_t<FP16>(v[2 * j], v[2 * j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) w[j] = 0u;
           }
-          // canonical K-major layout: 16-byte chunk index XOR-ed with address bits [7, 7 + log2(mask+1))
 #pragma unroll
           for (int hch = 0; hch < 2; ++hch) {
+            // chunk index inside the row: (c/8 + hch); rows of 32/64 bytes share a 128-byte line with their neighbours,
+            // so the XOR acts on the full in-line chunk position
             const uint32_t a = rowoff + (uint32_t)(c * 2 + hch * 16);
-            const uint32_t phys = a ^ (((a >> 7) & p.swz_mask) << 4);
+            const uint32_t phys = (a & ~0x70u) | ((((a >> 4) & 7u) ^ xr) << 4);
             if (stored) *reinterpret_cast<uint4*>(hslot + phys) = make_uint4(w[4 * hch], w[4 * hch + 1], w[4 * hch + 2], w[4 * hch + 3]);
           }
+        };
+#pragma unroll
+        for (int c = 0; c < C; c += 32) {
+          constexpr bool kTwoAlways = (C % 32 == 0);
+          const bool two = kTwoAlways || (c + 16 < C);
+          uint32_t ra[16], rb[16];
+          tmem_ld_x16(taddr + (uint32_t)c, ra);
+          if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
+          tmem_ld_wait();
+          emit(ra, c);
+          if (two) emit(rb, c + 16);
         }
       }
       tc_fence_before();
       mbar_arrive(&sh->a1empty[st]);
       fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&sh->hfull[st]);
+      BN_TRACE(1, it, 3);
     }
   } else {
     // ===================== epilogue 2: y = act(acc2 + b2) (+ x) =====================
@@ -246,7 +284,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int row = quarter * 32 + lane;
     const int hl0 = row / p.pitch, wl0 = row - hl0 * p.pitch;
     const bool row_ok = hl0 < p.th && wl0 < p.tw;
-    for (int it = 0; it < n_my; ++it) {
+    const int grp = (warp - 10) >> 2;                     // tiles alternate between the two groups; group g owns acc2 stage g
+    for (int it = grp; it < n_my; it += 2) {
       const int t = t_begin + it;
       const int b = fast_div(t, p.mul_tpi, tiles_per_img);
       const int r = t - b * tiles_per_img;
@@ -256,13 +295,16 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const bool valid = row_ok && ho < p.H && wo < p.W && b < p.batch;
       const long long pix = ((long long)b * p.H + ho) * p.W + wo;
       const int st = it & 1;
+      BN_TRACE(2, it, 0);
       mbar_wait(&sh->a2full[st], (uint32_t)((it >> 1) & 1));
+      BN_TRACE(2, it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2_col + (uint32_t)(st * p.Cpad);
       uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld;
       const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld : nullptr;
-      for (int c = 0; c < p.C; c += 32) {
-        const bool two = (c + 16 < p.C);
+#pragma unroll
+      for (int c = 0; c < C; c += 32) {
+        const bool two = (C % 32 == 0) || (c + 16 < C);
         uint32_t ra[16], rb[16];
         tmem_ld_x16(taddr + (uint32_t)c, ra);
         if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
@@ -273,12 +315,13 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, fp16, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, fp16, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();
       mbar_arrive(&sh->a2empty[st]);
+      BN_TRACE(2, it, 2);
     }
   }
 
@@ -383,6 +426,7 @@ int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
   const unsigned fmt = d->dtype == YX_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(d->c >> 3) << 17) | ((128u >> 4) << 24);
   p.act1 = d->act; p.bias1 = d->bias1;
+  p.trace = getenv("YX_BNECK_TRACE") ? 1 : 0;
   EpiParams& e = p.epi;
   e.out_h = d->h; e.out_w = d->w; e.out_c = d->c; e.act = d->act; e.dtype = d->dtype; e.epilogue = YX_EPI_STORE;
   e.bias = d->bias2; e.out = d->out; e.out_ld = d->out_ld;
@@ -428,7 +472,9 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));
     YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define YX_BN_ATTR(F, K) YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+    YX_BN_ATTR(false, 1); YX_BN_ATTR(false, 2); YX_BN_ATTR(false, 4); YX_BN_ATTR(true, 1); YX_BN_ATTR(true, 2); YX_BN_ATTR(true, 4);
+#undef YX_BN_ATTR
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -442,7 +488,25 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel, L->map_x, L->map_w1, L->map_w2, L->p));
+  const bool h16 = L->p.epi.dtype == YX_FP16;
+#define YX_BN_GO(F, K) YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K>, L->map_x, L->map_w1, L->map_w2, L->p))
+  if (L->p.ksteps == 4) { if (h16) YX_BN_GO(true, 4); else YX_BN_GO(false, 4); }
+  else if (L->p.ksteps == 2) { if (h16) YX_BN_GO(true, 2); else YX_BN_GO(false, 2); }
+  else { if (h16) YX_BN_GO(true, 1); else YX_BN_GO(false, 1); }
+#undef YX_BN_GO
+  if (L->p.trace) {
+    long long h[4][16][4];
+    YX_CUDA(cudaStreamSynchronize(stream));
+    YX_CUDA(cudaMemcpyFromSymbol(h, g_bneck_trace, sizeof(h)));
+    const long long t0 = h[3][0][0];
+    const char* names[4] = {"mma : g1(next) issued | hfull seen | a2empty seen | g2 issued", "epi1: start | a1full seen | hempty seen | done",
+                            "epi2: start | a2full seen | done", "tma : xempty seen | (mma) xfull seen | (mma) a1empty seen"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "%s\n", names[r]);
+      for (int i = 0; i < 12; ++i)
+        fprintf(stderr, "  tile %2d: %8lld %8lld %8lld %8lld\n", i, h[r][i][0] - t0, h[r][i][1] - t0, h[r][i][2] - t0, h[r][i][3] - t0);
+    }
+  }
   return YX_OK;
 }
 

@@ -142,12 +142,15 @@ __device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint
 }
 
 
+template <bool FP16>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // operand tiles need 1024-byte alignment for the 128-byte swizzle atom
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space known to the
+  // compiler: LDS/STS instead of generic loads for every bias / staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   TcShared* sh = reinterpret_cast<TcShared*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 1024);
   float* shead = reinterpret_cast<float*>(smem + 1024 + p.bias_bytes);
@@ -645,7 +648,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
       //      wait, one 256-bit store per thread per 16 columns (a full 32-byte sector)
-      const bool fp16 = (p.epi.dtype == YX_FP16);
       uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld + n_tile * p.BN;
       const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld + n_tile * p.BN : nullptr;
       for (int c = 0; c < p.BN; c += 32) {
@@ -660,9 +662,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk(p.epi, ra, tbias + c, rrow ? qa : nullptr, fp16, orow + c, b, ho, wo, n_tile * p.BN + c);
+          epi_tc_chunk<FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, orow + c, b, ho, wo, n_tile * p.BN + c);
           if (two)
-            epi_tc_chunk(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, fp16, orow + c + 16, b, ho, wo,
+            epi_tc_chunk<FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo,
                          n_tile * p.BN + c + 16);
         }
       }
@@ -1055,7 +1057,8 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));
     YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1069,7 +1072,10 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, L->map_a, L->map_b, L->p));
+  if (L->p.epi.dtype == YX_FP16)
+    YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, L->map_a, L->map_b, L->p));
+  else
+    YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, L->map_a, L->map_b, L->p));
   return YX_OK;
 }
 

@@ -77,22 +77,24 @@ __device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, f
   a = (float)v.x; b = (float)v.y;
 }
 
-template <typename TI>
+template <typename TI, bool FP16>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_img,
                const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space known to the
+  // compiler: LDS/STS instead of generic loads for every bias / staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   StemShared* sh = reinterpret_cast<StemShared*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 1024);
   uint8_t* patch = smem + 1024 + p.bias_bytes;                                         // [kPatchStages] raw patches
   uint8_t* wsm = patch + kPatchStages * kPatchStageBytes;                              // [2][BN x 64] weights
-  wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wsm) + 1023) & ~uintptr_t(1023));
+  wsm += (1024u - (smem_u32(wsm) & 1023u)) & 1023u;
   uint8_t* astage = wsm + p.b_bytes;                                                   // [stages][2][128 x 64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool fp16 = (p.epi.dtype == YX_FP16);
+  constexpr bool fp16 = FP16;
 
   {
     const float bscale = epi_half_bias(p.epi) ? 0.5f : 1.0f;
@@ -156,7 +158,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         }
 #pragma unroll
         for (int i = 0; i < 27; ++i) {
-          wds[nw++] = pack16(fa[i], fb[i], fp16);
+          wds[nw++] = pack16_t<FP16>(fa[i], fb[i]);
           if (nw == 4) {
             uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
@@ -262,8 +264,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk(p.epi, ra, sbias + c, nullptr, fp16, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk(p.epi, rb, sbias + c + 16, nullptr, fp16, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();
@@ -364,8 +366,10 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
 int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -379,10 +383,14 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (L->p.img_dtype == YX_FP32)
-    YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float>, L->map_w, L->map_img, L->p));
-  else
-    YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t>, L->map_w, L->map_img, L->p));
+  const bool h16 = L->p.epi.dtype == YX_FP16;
+  if (L->p.img_dtype == YX_FP32) {
+    if (h16) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, true>, L->map_w, L->map_img, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, false>, L->map_w, L->map_img, L->p));
+  } else {
+    if (h16) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t, true>, L->map_w, L->map_img, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t, false>, L->map_w, L->map_img, L->p));
+  }
   return YX_OK;
 }
 

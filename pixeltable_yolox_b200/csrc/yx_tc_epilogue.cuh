@@ -39,9 +39,31 @@ __device__ __forceinline__ bool epi_half_bias(const EpiParams& e) { return e.act
 
 // 16 accumulator columns of one pixel: bias (smem) + act (+ residual) -> 16-bit, one 32-byte store.
 // `bias` holds 0.5 * bias when epi_half_bias(e).
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16_t(float a, float b) {
+  if (FP16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool FP16>
+__device__ __forceinline__ void unpack16_t(uint32_t w, float& a, float& b) {
+  if (FP16) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    a = f.x; b = f.y;
+  } else {
+    a = __uint_as_float(w << 16);            // bf16 -> fp32 is a shift
+    b = __uint_as_float(w & 0xffff0000u);
+  }
+}
+
+// FP16 is a compile-time parameter: a runtime flag costs a branch per packed pair in the hot loop
+template <bool FP16>
 __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
-                                             const uint32_t* res, bool fp16, uint16_t* dst, int b, int ho, int wo,
-                                             int c0) {
+                                             const uint32_t* res, uint16_t* dst, int b, int ho, int wo, int c0) {
+  constexpr bool fp16 = FP16;
   float v[16];
   if (e.act == YX_ACT_SILU && !fp16) {
     // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible.
@@ -77,13 +99,13 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float a, c;
-      unpack16(res[j], fp16, a, c);
+      unpack16_t<FP16>(res[j], a, c);
       v[2 * j] += a; v[2 * j + 1] += c;
     }
   }
   uint32_t w[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) w[j] = pack16(v[2 * j], v[2 * j + 1], fp16);
+  for (int j = 0; j < 8; ++j) w[j] = pack16_t<FP16>(v[2 * j], v[2 * j + 1]);
   st_global_256(dst, w);
   if (e.ups) {
     const int uw = 2 * e.out_w;
