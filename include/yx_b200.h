@@ -95,6 +95,11 @@ typedef struct yx_conv_desc {
   float* head_out;
   int32_t head_anchors, head_anchor_off, head_nc, head_decode;
   float head_stride;
+  /* optional second destination (YX_EPI_STORE): output channels >= out2_begin (a multiple of 16) are written
+   * to out2[pixel*out2_ld + (c - out2_begin)] instead of `out`; lets one stacked GEMM (CspLayer conv1 | conv2,
+   * network_blocks.py:176-177) feed two dense buffers. out2 == NULL disables it. */
+  int32_t out2_begin;
+  void* out2;       int64_t out2_ld;
 } yx_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM for bf16/fp16; routes YX_FP32 to the SIMT kernel. */

@@ -40,6 +40,8 @@ class ConvDesc(C.Structure):
         ("head_anchors", C.c_int32), ("head_anchor_off", C.c_int32), ("head_nc", C.c_int32),
         ("head_decode", C.c_int32),
         ("head_stride", C.c_float),
+        ("out2_begin", C.c_int32),
+        ("out2", C.c_void_p), ("out2_ld", C.c_int64),
     ]
 
 

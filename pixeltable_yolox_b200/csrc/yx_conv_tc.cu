@@ -649,6 +649,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
       //      wait, one 256-bit store per thread per 16 columns (a full 32-byte sector)
       uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld + n_tile * p.BN;
+      // second destination: channels >= out2_begin (the stacked CSP GEMM writes x_1 and x_2 to two dense buffers)
+      uint16_t* orow2 = p.epi.out2 ? (uint16_t*)p.epi.out2 + pix * p.epi.out2_ld + (n_tile * p.BN - p.epi.out2_begin) : nullptr;
+      const int split = orow2 ? p.epi.out2_begin - n_tile * p.BN : 0x7fffffff;
       const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld + n_tile * p.BN : nullptr;
       for (int c = 0; c < p.BN; c += 32) {
         const bool two = (c + 16 < p.BN);
@@ -662,9 +665,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, orow + c, b, ho, wo, n_tile * p.BN + c);
+          epi_tc_chunk<FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
           if (two)
-            epi_tc_chunk<FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo,
+            epi_tc_chunk<FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
                          n_tile * p.BN + c + 16);
         }
       }
@@ -722,6 +725,7 @@ int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
   e->out = d->out; e->out_ld = d->out_ld;
   e->res = d->res; e->res_ld = d->res_ld;
   e->ups = d->ups; e->ups_ld = d->ups_ld;
+  e->out2 = d->out2; e->out2_ld = d->out2_ld; e->out2_begin = d->out2_begin;
   e->head_out = d->head_out;
   e->head_anchors = d->head_anchors; e->head_anchor_off = d->head_anchor_off;
   e->head_nc = d->head_nc; e->head_decode = d->head_decode; e->head_stride = d->head_stride;
@@ -734,9 +738,14 @@ int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
     const int al = d->dtype == YX_FP32 ? 4 : 8;
     YX_REQUIRE(d->out_ld % al == 0 && ((uintptr_t)d->out & 15) == 0, YX_ERR_INVALID_ARG,
                "conv: out must be 16-byte aligned with out_ld %% %d == 0", al);
-    YX_REQUIRE(d->out_ld >= d->out_c, YX_ERR_INVALID_ARG, "conv: out_ld < out_c");
+    YX_REQUIRE(d->out_ld >= (d->out2 ? d->out2_begin : d->out_c), YX_ERR_INVALID_ARG, "conv: out_ld < out_c");
+    if (d->out2) YX_REQUIRE(d->out2_ld >= d->out_c - d->out2_begin, YX_ERR_INVALID_ARG, "conv: out2_ld too small");
     if (d->res) YX_REQUIRE(d->res_ld % al == 0 && ((uintptr_t)d->res & 15) == 0, YX_ERR_INVALID_ARG, "conv: res misaligned");
     if (d->ups) YX_REQUIRE(d->ups_ld % al == 0 && ((uintptr_t)d->ups & 15) == 0, YX_ERR_INVALID_ARG, "conv: ups misaligned");
+    if (d->out2)
+      YX_REQUIRE(d->out2_ld % 16 == 0 && ((uintptr_t)d->out2 & 31) == 0 && d->out2_begin % 16 == 0 && d->out2_begin > 0 &&
+                     d->out2_begin < d->out_c && !d->ups && !d->res,
+                 YX_ERR_INVALID_ARG, "conv: out2 needs 32-byte alignment, out2_begin %% 16 == 0 inside (0, out_c), no res/ups");
   }
   return YX_OK;
 }

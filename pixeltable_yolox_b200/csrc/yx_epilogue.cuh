@@ -16,6 +16,7 @@ struct EpiParams {
   void* out; long long out_ld;
   const void* res; long long res_ld;
   void* ups; long long ups_ld;
+  void* out2; long long out2_ld; int out2_begin;   // channels >= out2_begin go to out2 (null: disabled)
   float* head_out;
   int head_anchors, head_anchor_off, head_nc, head_decode;
   float head_stride;
@@ -78,7 +79,9 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int b, int ho, i
         v[4 * j + 0] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
       }
     }
-    float4* o = reinterpret_cast<float4*>((float*)e.out + pix * e.out_ld + c0);
+    float4* o = (e.out2 && c0 >= e.out2_begin)
+                    ? reinterpret_cast<float4*>((float*)e.out2 + pix * e.out2_ld + (c0 - e.out2_begin))
+                    : reinterpret_cast<float4*>((float*)e.out + pix * e.out_ld + c0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     if (e.ups) {
@@ -111,7 +114,9 @@ __device__ __forceinline__ void epi_store16(const EpiParams& e, int b, int ho, i
   for (int j = 0; j < 8; ++j) w[j] = pack16(v[2 * j], v[2 * j + 1], fp16);
   const uint4 o0 = make_uint4(w[0], w[1], w[2], w[3]);
   const uint4 o1 = make_uint4(w[4], w[5], w[6], w[7]);
-  uint4* o = reinterpret_cast<uint4*>((uint16_t*)e.out + pix * e.out_ld + c0);
+  uint4* o = (e.out2 && c0 >= e.out2_begin)
+                 ? reinterpret_cast<uint4*>((uint16_t*)e.out2 + pix * e.out2_ld + (c0 - e.out2_begin))
+                 : reinterpret_cast<uint4*>((uint16_t*)e.out + pix * e.out_ld + c0);
   o[0] = o0; o[1] = o1;
   if (e.ups) {
     const int uw = 2 * e.out_w;

@@ -167,7 +167,8 @@ class Builder:
     # ---------------------------------------------------------------- ops
     def conv(self, x: Feat, parts: List[Part], out: Optional[Feat] = None, res: Optional[Feat] = None,
              ups: Optional[Feat] = None, act: Optional[str] = "silu", ksize: int = 1, stride: int = 1,
-             o_total: Optional[int] = None, head: Optional[dict] = None) -> Optional[Feat]:
+             o_total: Optional[int] = None, head: Optional[dict] = None, out2: Optional[Feat] = None) -> Optional[Feat]:
+        """`out2`: second destination for the trailing output channels (those beyond out.c_slots)."""
         w, bias, out_segs = self._pack(parts, x, ksize, o_total)
         pad = (ksize - 1) // 2
         oh = (x.H + 2 * pad - ksize) // stride + 1
@@ -181,11 +182,12 @@ class Builder:
         else:
             if out is None:
                 out = self.new_feat(x.B, oh, ow, out_segs)
-            assert out.c_slots == w.shape[0], (out.segs, w.shape)
+            assert out.c_slots + (out2.c_slots if out2 is not None else 0) == w.shape[0], (out.segs, w.shape)
             out_view = out.view()
         d = ops.make_conv_desc(x.view(), w, bias, out_view, ksize, stride, ACT_CODES[act],
                                res.view() if res is not None else None,
-                               ups.view() if ups is not None else None, head_arg)
+                               ups.view() if ups is not None else None, head_arg,
+                               out2.view() if out2 is not None else None, out.c_slots if out2 is not None else 0)
         self._emit_conv(d)
         fl = 2.0 * x.B * oh * ow * sum(p.weight.shape[0] * p.weight.shape[1] for p in parts) * ksize * ksize
         esz = w.element_size()

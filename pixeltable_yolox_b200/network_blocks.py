@@ -186,26 +186,23 @@ class CspLayer(_B200Block):
         # torch.cat of the reference (network_blocks.py:182) never happens.
         hidden = self.conv1.conv.out_channels
         if len(self.m) > 0 and all(b.bottleneck_fusable(b.probe_feat(x, hidden), blk) for blk in self.m):
-            # fused bottlenecks cannot run in place: buffer [y | x_2 | x_1]; the stacked GEMM writes
-            # [x_2 | x_1], the chain ping-pongs x_1 -> tmp -> ... and its last link writes y; conv3 reads
-            # [y | x_2] (the torch.cat of network_blocks.py:182 in the reference's channel order)
-            buf = b.new_feat(x.B, x.H, x.W, [hidden, hidden, hidden])
-            from .engine import Feat
-
-            b.conv(x, [b.part(self.conv2), b.part(self.conv1)], out=Feat(buf.t, buf.seg_off(1), [hidden, hidden]),
+            # fused bottlenecks cannot run in place: the stacked GEMM writes x_1 to its own buffer and x_2 straight
+            # into the concat buffer [y | x_2] (two destinations, yx_conv_desc.out2); the chain ping-pongs
+            # x_1 -> tmp -> ... and its last link writes y, so conv3 reads one dense buffer (the torch.cat of
+            # network_blocks.py:182 in the reference's channel order) and every access stays contiguous
+            cat = b.new_feat(x.B, x.H, x.W, [hidden, hidden])
+            cur = b.new_feat(x.B, x.H, x.W, [hidden])
+            b.conv(x, [b.part(self.conv1), b.part(self.conv2)], out=cur, out2=cat.seg(1),
                    act=act_name(self.conv1.act), ksize=1, stride=1)
-            cur, tmp = buf.seg(2), None
+            spare = None
             for i, blk in enumerate(self.m):
                 if i == len(self.m) - 1:
-                    dst = buf.seg(0)
-                elif cur.c_off == buf.seg_off(2) and cur.t is buf.t:
-                    tmp = tmp or b.new_feat(x.B, x.H, x.W, [hidden])
-                    dst = tmp
+                    dst = cat.seg(0)
                 else:
-                    dst = buf.seg(2)
+                    dst = spare if spare is not None else b.new_feat(x.B, x.H, x.W, [hidden])
                 blk.lower(b, cur, out=dst)
-                cur = dst
-            return self.conv3.lower(b, Feat(buf.t, 0, [hidden, hidden]), out=out)
+                cur, spare = dst, cur
+            return self.conv3.lower(b, cat, out=out)
         cat = b.conv(x, [b.part(self.conv1), b.part(self.conv2)], act=act_name(self.conv1.act), ksize=1, stride=1)
         x1 = cat.seg(0)
         for blk in self.m:

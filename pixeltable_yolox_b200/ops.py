@@ -62,6 +62,7 @@ class View:
 def make_conv_desc(
     x: View, w: torch.Tensor, bias: torch.Tensor, out: Optional[View], ksize: int, stride: int, act: int,
     res: Optional[View] = None, ups: Optional[View] = None, head: Optional[dict] = None,
+    out2: Optional[View] = None, out2_begin: int = 0,
 ) -> ConvDesc:
     pad = (ksize - 1) // 2
     oh = (x.H + 2 * pad - ksize) // stride + 1
@@ -80,7 +81,8 @@ def make_conv_desc(
     d.w = w.data_ptr()
     d.bias = bias.data_ptr()
     if head is None:
-        assert out is not None and out.c == d.out_c and out.t.dtype == x.t.dtype
+        assert out is not None and out.t.dtype == x.t.dtype
+        assert out.c == d.out_c or (out2 is not None and out.c == out2_begin), (out.c, d.out_c, out2_begin)
         assert (out.B, out.H, out.W) == (x.B, oh, ow), ((out.B, out.H, out.W), (x.B, oh, ow))
         d.epilogue = _lib.YX_EPI_STORE
         d.out, d.out_ld = out.ptr, out.ld
@@ -90,6 +92,9 @@ def make_conv_desc(
         if ups is not None:
             assert (ups.B, ups.H, ups.W, ups.c) == (out.B, 2 * out.H, 2 * out.W, out.c)
             d.ups, d.ups_ld = ups.ptr, ups.ld
+        if out2 is not None:
+            assert (out2.B, out2.H, out2.W) == (out.B, out.H, out.W) and out2.c == w.shape[0] - out2_begin
+            d.out2, d.out2_ld, d.out2_begin = out2.ptr, out2.ld, out2_begin
     else:
         d.epilogue = _lib.YX_EPI_HEAD
         d.head_out = head["out_ptr"]
@@ -101,9 +106,10 @@ def make_conv_desc(
     return d
 
 
-def conv_bn_act(x: View, w, bias, out, ksize, stride, act, res=None, ups=None, head=None, simt=False) -> None:
+def conv_bn_act(x: View, w, bias, out, ksize, stride, act, res=None, ups=None, head=None, simt=False,
+                out2=None, out2_begin=0) -> None:
     require_cuda(x.t, "conv_bn_act")
-    d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head)
+    d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head, out2, out2_begin)
     fn = lib().yx_conv_bn_act_fwd_simt if simt else lib().yx_conv_bn_act_fwd
     check(fn(C.byref(d), stream_ptr(x.t.device)), "conv_bn_act")
 

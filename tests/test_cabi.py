@@ -38,7 +38,7 @@ def test_conv_desc_layout_matches_header():
     from pixeltable_yolox_b200._lib import ConvDesc
 
     # 12 int32, then pointer/int64 pairs ... : recompute with natural alignment
-    assert ctypes.sizeof(ConvDesc) == 12 * 4 + 8 * 2 + 8 + 8 + 8 * 2 + 8 * 2 + 8 * 2 + 8 + 4 * 4 + 4 + 4
+    assert ctypes.sizeof(ConvDesc) == 12 * 4 + 8 * 2 + 8 + 8 + 8 * 2 + 8 * 2 + 8 * 2 + 8 + 4 * 4 + 4 + 4 + 8 * 2
 
 
 def test_no_gpu_is_a_loud_error_not_a_fallback():

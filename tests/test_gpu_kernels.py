@@ -75,6 +75,23 @@ def test_conv_tcgen05_fusions(cuda, k, s):
         assert err <= 1.5e-2, (act, err)
 
 
+@pytest.mark.parametrize("k", [1, 3])
+def test_conv_two_destinations(cuda, k):
+    """yx_conv_desc.out2: the trailing output channels of one GEMM land in a second buffer (stacked CSP conv1|conv2)."""
+    g = torch.Generator().manual_seed(3)
+    B, H, W, cin, c1, c2 = 2, 20, 24, 64, 32, 48
+    x = torch.randn(B, H, W, cin, generator=g).to(cuda).to(torch.bfloat16)
+    w = (torch.randn(c1 + c2, k * k, cin, generator=g) / (k * k * cin) ** 0.5).to(cuda).to(torch.bfloat16)
+    bias = torch.randn(c1 + c2, generator=g).to(cuda)
+    whole = torch.empty(B, H, W, c1 + c2, device=cuda, dtype=torch.bfloat16)
+    ops.conv_bn_act(View(x), w, bias, View(whole), k, 1, 1)
+    o1 = torch.full((B, H, W, c1), 7.0, device=cuda, dtype=torch.bfloat16)
+    o2 = torch.full((B, H, W, 16 + c2), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.conv_bn_act(View(x), w, bias, View(o1), k, 1, 1, out2=View(o2, 16, c2), out2_begin=c1)
+    assert torch.equal(o1, whole[..., :c1]) and torch.equal(o2[..., 16:], whole[..., c1:])
+    assert (o2[..., :16] == 7).all()
+
+
 def _bneck_case(dev, B, H, W, c, dtype, use_add, act, in_off=0, out_off=0, seed=0):
     """Fused Bottleneck against torch: fp32 math with the hidden tensor rounded to the 16-bit dtype, exactly
     what the reference's two 16-bit BaseConvs do (network_blocks.py:77-99)."""
