@@ -73,8 +73,11 @@ __device__ __forceinline__ void load_pair<float>(const float* p, float& a, float
 }
 template <>
 __device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, float& b) {
-  const uchar2 v = *reinterpret_cast<const uchar2*>(p);
-  a = (float)v.x; b = (float)v.y;
+  // u8 -> fp32 without I2F (conversions issue on the quarter-rate XU pipe, 108 of them per operand row):
+  // 0x4B000000 | u is the float 2^23 + u, one FADD removes the 2^23
+  const uint32_t v = *reinterpret_cast<const uint16_t*>(p);
+  a = __uint_as_float(0x4B000000u | (v & 0xffu)) - 8388608.0f;
+  b = __uint_as_float(0x4B000000u | (v >> 8)) - 8388608.0f;
 }
 
 template <typename TI, bool FP16>
