@@ -269,6 +269,15 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
                             int32_t inplace_xyxy, float* dets, int64_t* det_idx,
                             int32_t* det_count, int32_t max_det, void* workspace,
                             int64_t workspace_bytes);
+/* Independent branches. Ops added between yx_plan_begin_lane(lane, after_op) and yx_plan_end_lane belong to side
+ * lane `lane` (1..8): in graph mode they run on their own stream, ordered only after main-lane op `after_op`
+ * (an index < yx_plan_num_ops, -1 = everything added so far). yx_plan_join_lanes makes the next main-lane op (or
+ * the end of the plan) wait for all lanes. Eager runs and yx_plan_profile execute the ops in the order they were
+ * added, which must therefore be a valid serial order. Used for the three levels of YoloxHead.forward
+ * (yolox/models/yolo_head.py:140-160: the per-level loop has no cross-level dependency). */
+int yx_plan_begin_lane(yx_plan* p, int32_t lane, int32_t after_op);
+int yx_plan_end_lane(yx_plan* p);
+int yx_plan_join_lanes(yx_plan* p);
 int yx_plan_num_launches(const yx_plan* p);
 int yx_plan_num_ops(const yx_plan* p);
 /* Measurement aid: runs the ops one by one (no graph) with a CUDA event between consecutive ops on

@@ -93,6 +93,9 @@ SIGNATURES = {
     "yx_plan_add_focus": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32]),
     "yx_plan_add_focus_conv": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_postprocess": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _D, _I32, _I32, _P, _P, _P, _I32, _P, _I64]),
+    "yx_plan_begin_lane": (C.c_int, [_P, _I32, _I32]),
+    "yx_plan_end_lane": (C.c_int, [_P]),
+    "yx_plan_join_lanes": (C.c_int, [_P]),
     "yx_plan_num_launches": (C.c_int, [_P]),
     "yx_plan_num_ops": (C.c_int, [_P]),
     "yx_plan_profile": (C.c_int, [_P, _P, _P, _P, _I32]),

@@ -117,6 +117,9 @@ enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP
 
 struct Op {
   OpKind kind;
+  int lane;        // 0 = main stream; > 0: side lane (independent branch)
+  int after;       // side lanes: index of the main-lane op whose completion the lane's first op waits for (-1: none)
+  bool join;       // before this main-lane op, main waits for every side lane
   ConvTcLaunch* tc;  // OP_CONV_TC
   StemLaunch* stem;  // OP_STEM
   BneckLaunch* bneck;  // OP_BNECK
@@ -133,6 +136,9 @@ struct Op {
 
 struct yx_plan {
   std::vector<yx::Op> ops;
+  int cur_lane = 0, cur_after = -1;
+  bool pending_join = false;
+  std::vector<cudaStream_t> lane_streams;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaStream_t capture_stream = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
@@ -339,12 +345,21 @@ void yx_plan_destroy(yx_plan* p) {
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
   if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  for (auto st : p->lane_streams) if (st) cudaStreamDestroy(st);
   for (auto& o : p->ops) {
     if (o.tc) conv_tc_free(o.tc);
     if (o.stem) stem_free(o.stem);
     if (o.bneck) bneck_free(o.bneck);
   }
   delete p;
+}
+
+static void plan_push(yx_plan* p, yx::Op& o) {
+  o.lane = p->cur_lane;
+  o.after = p->cur_lane ? p->cur_after : -1;
+  o.join = (p->cur_lane == 0) && p->pending_join;
+  if (o.join) p->pending_join = false;
+  p->ops.push_back(o);
 }
 
 static void plan_invalidate(yx_plan* p) {
@@ -370,7 +385,7 @@ int yx_plan_add_conv(yx_plan* p, const yx_conv_desc* d) {
     rc = conv_tc_prepare(d, o.tc);
     if (rc) { conv_tc_free(o.tc); return rc; }
   }
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -386,7 +401,7 @@ int yx_plan_add_bottleneck(yx_plan* p, const yx_bneck_desc* d) {
   o.bneck = bneck_alloc();
   rc = bneck_prepare(d, o.bneck);
   if (rc) { bneck_free(o.bneck); return rc; }
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -400,7 +415,7 @@ int yx_plan_add_dwconv(yx_plan* p, const void* in, int64_t in_ld, const void* w,
   memset(&o, 0, sizeof(o));
   o.kind = OP_DWCONV;
   o.dw = {in, in_ld, w, bias, out, out_ld, batch, in_h, in_w, c, stride, act, dtype};
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -412,7 +427,7 @@ int yx_plan_add_spp(yx_plan* p, void* buf, int64_t ld, int32_t batch, int32_t h,
   memset(&o, 0, sizeof(o));
   o.kind = OP_SPP;
   o.spp = {buf, ld, batch, h, w, c, dtype};
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -425,7 +440,7 @@ int yx_plan_add_focus(yx_plan* p, const void* img, int32_t img_dtype, void* out,
   memset(&o, 0, sizeof(o));
   o.kind = OP_FOCUS;
   o.focus = {img, img_dtype, out, out_ld, out_dtype, batch, h, w};
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -443,7 +458,7 @@ int yx_plan_add_focus_conv(yx_plan* p, const void* img, int32_t img_dtype, const
   o.stem = stem_alloc();
   rc = stem_prepare(img, img_dtype, w, bias, out, out_ld, batch, h, wd, out_c, act, dtype, o.stem);
   if (rc) { stem_free(o.stem); return rc; }
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 1;
   plan_invalidate(p);
   return YX_OK;
@@ -459,9 +474,33 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
   o.kind = OP_POST;
   o.post = {pred, batch, anchors, nc, conf_thre, nms_thre, nms_variant, inplace_xyxy, dets, (long long*)det_idx,
             det_count, max_det, workspace, workspace_bytes};
-  p->ops.push_back(o);
+  plan_push(p, o);
   p->launches += 2;  // filter + sort/NMS kernels (plus one memset node)
   plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_begin_lane(yx_plan* p, int32_t lane, int32_t after_op) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_begin_lane: null plan");
+  YX_REQUIRE(lane >= 1 && lane <= 8, YX_ERR_INVALID_ARG, "plan_begin_lane: lane %d (1..8)", lane);
+  YX_REQUIRE(after_op < (int)p->ops.size(), YX_ERR_INVALID_ARG, "plan_begin_lane: after_op %d is not an existing op", after_op);
+  YX_REQUIRE(after_op < 0 || p->ops[after_op].lane == 0, YX_ERR_INVALID_ARG, "plan_begin_lane: after_op must be a main-lane op");
+  p->cur_lane = lane;
+  p->cur_after = after_op;
+  return YX_OK;
+}
+
+int yx_plan_end_lane(yx_plan* p) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_end_lane: null plan");
+  p->cur_lane = 0;
+  p->cur_after = -1;
+  return YX_OK;
+}
+
+int yx_plan_join_lanes(yx_plan* p) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_join_lanes: null plan");
+  p->cur_lane = 0;
+  p->pending_join = true;     // the next main-lane op (or the end of the plan) waits for every side lane
   return YX_OK;
 }
 
@@ -516,17 +555,82 @@ int yx_plan_run(yx_plan* p, void* stream, int32_t use_graph) {
     YX_CUDA(cudaStreamSynchronize(s));
     if (!p->capture_stream) YX_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
     cudaStream_t cs = p->capture_stream;
+    // side lanes: one capture stream per lane, forked from / joined to the main stream with events, so that
+    // independent branches (the three head levels) become parallel branches of the graph
+    int max_lane = 0;
+    for (const auto& o : p->ops) if (o.lane > max_lane) max_lane = o.lane;
+    static const bool lanes_on = !(getenv("YX_LANES") && getenv("YX_LANES")[0] == '0');
+    if (!lanes_on) max_lane = 0;
+    while ((int)p->lane_streams.size() < max_lane) {
+      cudaStream_t st = nullptr;
+      YX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      p->lane_streams.push_back(st);
+    }
+    const int n_ops = (int)p->ops.size();
+    std::vector<cudaEvent_t> after_ev(n_ops, nullptr);
+    std::vector<cudaEvent_t> all_ev;
+    std::vector<char> lane_open(max_lane + 1, 0);     // lane currently holds un-joined work
+    std::vector<int> lane_after(max_lane + 1, -2);    // dependency the lane stream has already been made to wait on
+    if (max_lane > 0)
+      for (const auto& o : p->ops)
+        if (o.lane > 0 && o.after >= 0 && !after_ev[o.after]) {
+          YX_CUDA(cudaEventCreateWithFlags(&after_ev[o.after], cudaEventDisableTiming));
+          all_ev.push_back(after_ev[o.after]);
+        }
+    auto join_all = [&]() -> int {
+      for (int l = 1; l <= max_lane; ++l)
+        if (lane_open[l]) {
+          cudaEvent_t e = nullptr;
+          YX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          all_ev.push_back(e);
+          YX_CUDA(cudaEventRecord(e, p->lane_streams[l - 1]));
+          YX_CUDA(cudaStreamWaitEvent(cs, e, 0));
+          lane_open[l] = 0;
+          lane_after[l] = -2;
+        }
+      return YX_OK;
+    };
     YX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    for (const auto& o : p->ops) {
-      rc = run_op(o, cs);
-      if (rc) {
-        cudaGraph_t g = nullptr;
-        cudaStreamEndCapture(cs, &g);
-        if (g) cudaGraphDestroy(g);
-        return rc;
+    for (int i = 0; i < n_ops && rc == YX_OK; ++i) {
+      const auto& o = p->ops[i];
+      const int lane = max_lane > 0 ? o.lane : 0;
+      if (lane == 0) {
+        if (o.join && max_lane > 0) rc = join_all();
+        if (rc == YX_OK) rc = run_op(o, cs);
+        if (rc == YX_OK && after_ev[i]) {
+          cudaError_t e = cudaEventRecord(after_ev[i], cs);
+          if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord", __FILE__, __LINE__);
+        }
+      } else {
+        cudaStream_t ls = p->lane_streams[lane - 1];
+        if (!lane_open[lane] || lane_after[lane] != o.after) {
+          // fork: the lane joins the capture by waiting on a main-stream event (the op it depends on, or "now")
+          cudaEvent_t dep = o.after >= 0 ? after_ev[o.after] : nullptr;
+          if (!dep) {
+            cudaError_t e = cudaEventCreateWithFlags(&dep, cudaEventDisableTiming);
+            if (e == cudaSuccess) { all_ev.push_back(dep); e = cudaEventRecord(dep, cs); }
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord", __FILE__, __LINE__);
+          }
+          if (rc == YX_OK) {
+            cudaError_t e = cudaStreamWaitEvent(ls, dep, 0);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent", __FILE__, __LINE__);
+          }
+          lane_open[lane] = 1;
+          lane_after[lane] = o.after;
+        }
+        if (rc == YX_OK) rc = run_op(o, ls);
       }
     }
+    if (rc == YX_OK && max_lane > 0) rc = join_all();
+    if (rc) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(cs, &g);
+      if (g) cudaGraphDestroy(g);
+      for (auto e : all_ev) cudaEventDestroy(e);
+      return rc;
+    }
     YX_CUDA(cudaStreamEndCapture(cs, &p->graph));
+    for (auto e : all_ev) cudaEventDestroy(e);
     YX_CUDA(cudaGraphInstantiate(&p->exec, p->graph, 0));
   }
   YX_CUDA(cudaGraphLaunch(p->exec, s));

@@ -96,11 +96,36 @@ class Builder:
         self.n_ops = 0
         self.flops = 0.0
         self.op_info: List[dict] = []    # per emitted op: name, algorithmic flops and bytes
+        self.writer: Dict[int, int] = {}  # buffer data_ptr -> index of the last main-lane plan op that wrote it
+        self._lane = 0
 
     def close(self):
         if self.plan is not None:
             lib().yx_plan_destroy(self.plan)
             self.plan = None
+
+    # ---------------------------------------------------------------- independent branches (graph lanes)
+    def _wrote(self, feat: Optional["Feat"]) -> None:
+        if feat is not None and self.plan is not None and self._lane == 0:
+            self.writer[feat.t.data_ptr()] = lib().yx_plan_num_ops(self.plan) - 1
+
+    def begin_lane(self, lane: int, after: Optional["Feat"]) -> None:
+        """Ops emitted until end_lane() form an independent branch that only depends on the op that last wrote `after`."""
+        if self.plan is None:
+            return
+        idx = self.writer.get(after.t.data_ptr(), -1) if after is not None else -1
+        check(lib().yx_plan_begin_lane(self.plan, lane, idx), "plan_begin_lane")
+        self._lane = lane
+
+    def end_lane(self) -> None:
+        if self.plan is not None:
+            check(lib().yx_plan_end_lane(self.plan), "plan_end_lane")
+        self._lane = 0
+
+    def join_lanes(self) -> None:
+        if self.plan is not None:
+            check(lib().yx_plan_join_lanes(self.plan), "plan_join_lanes")
+        self._lane = 0
 
     # ---------------------------------------------------------------- buffers
     def new_feat(self, B, H, W, segs: Sequence[int]) -> Feat:
@@ -189,6 +214,8 @@ class Builder:
                                ups.view() if ups is not None else None, head_arg,
                                out2.view() if out2 is not None else None, out.c_slots if out2 is not None else 0)
         self._emit_conv(d)
+        self._wrote(out)
+        self._wrote(out2)
         fl = 2.0 * x.B * oh * ow * sum(p.weight.shape[0] * p.weight.shape[1] for p in parts) * ksize * ksize
         esz = w.element_size()
         by = x.B * x.H * x.W * x.c_slots * esz + w.numel() * esz
@@ -244,6 +271,7 @@ class Builder:
             check(lib().yx_plan_add_bottleneck(self.plan, C.byref(d)), "plan_add_bottleneck")
         else:
             check(lib().yx_bottleneck_fwd(C.byref(d), stream_ptr(self.dev)), "bottleneck")
+        self._wrote(out)
         self.n_ops += 1
         fl = 2.0 * x.B * x.H * x.W * c * c * 10
         esz = w1.element_size()
@@ -289,6 +317,7 @@ class Builder:
                                            x.B, x.H, x.W, xv.c, stride, act, dtype_code(self.dtype)), "plan_add_dwconv")
         else:
             ops.dwconv3x3(xv, w, bias, ov, stride, act)
+        self._wrote(out)
         self.n_ops += 1
         self.flops += 2.0 * x.B * oh * ow * c * 9
         self.op_info.append(dict(name=f"dwconv3x3s{stride} {c} @{oh}x{ow}", flops=2.0 * x.B * oh * ow * c * 9,
@@ -303,6 +332,7 @@ class Builder:
             check(lib().yx_plan_add_spp(self.plan, v.ptr, v.ld, v.B, v.H, v.W, c, dtype_code(self.dtype)), "plan_add_spp")
         else:
             ops.spp_maxpool(v, c)
+        self._wrote(cat)
         self.n_ops += 1
         self.op_info.append(dict(name=f"spp {c} @{v.H}x{v.W}", flops=0.0, bytes=v.B * v.H * v.W * 4 * c * cat.t.element_size(), tc=False))
 
@@ -358,6 +388,7 @@ class Builder:
             check(lib().yx_plan_add_focus_conv(self.plan, *args), "plan_add_focus_conv")
         else:
             check(lib().yx_focus_conv_bn_act_fwd(*args, stream_ptr(self.dev)), "focus_conv")
+        self._wrote(out)
         self.n_ops += 1
         fl = 2.0 * B * (H // 2) * (W // 2) * o * 108
         self.flops += fl
@@ -484,6 +515,7 @@ class InferenceEngine:
                     self._record = [t for t in b.keep[mark:]]
             else:
                 self._lower_reusing(img, self.pred[b0:b1])
+            b.join_lanes()                       # slices share buffers: the next one starts after every branch is done
         self.post = None
         if post is not None:
             max_det = post.get("max_det") or self.anchors

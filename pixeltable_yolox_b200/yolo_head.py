@@ -9,6 +9,8 @@ train : the network runs through PyTorch autograd; the SimOTA assignment of the 
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import torch
@@ -69,6 +71,12 @@ class YoloxHead(_B200Block):
         total = sum(f.H * f.W for f in feats)
         assert head_out.shape[1] == total and head_out.shape[2] == 5 + self.num_classes
         for k, x in enumerate(feats):
+            # the levels are independent chains (yolo_head.py:140-160): all but the last one (whose input is the final
+            # neck op anyway) run as side lanes of the graph, forked right after the op that produced their input, so
+            # the 80x80 chain overlaps the bottom-up half of the neck and the small 40x40 / 20x20 kernels
+            side = k < len(feats) - 1 and os.environ.get("YX_HEAD_LANES", "1") != "0"
+            if side:
+                b.begin_lane(k + 1, x)
             stem = self.stems[k].lower(b, x)
             hid = stem.c_real
             c0, c1 = self.cls_convs[k][0], self.cls_convs[k][1]
@@ -92,8 +100,11 @@ class YoloxHead(_B200Block):
             b.conv(t1, parts, act=None, ksize=1, stride=1, o_total=5 + self.num_classes,
                    head=dict(out=head_out, anchors=total, anchor_off=off, nc=self.num_classes, decode=decode,
                              stride=self.strides[k]))
+            if side:
+                b.end_lane()
             hw.append((x.H, x.W))
             off += x.H * x.W
+        b.join_lanes()
         self.hw = [torch.Size(v) for v in hw]
         return head_out
 

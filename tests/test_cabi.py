@@ -50,3 +50,22 @@ def test_no_gpu_is_a_loud_error_not_a_fallback():
         pytest.skip("GPU present")
     assert _lib.lib().yx_device_check(0) == -4          # YX_ERR_NO_DEVICE
     assert b"no CUDA device" in _lib.lib().yx_last_error() or _lib.lib().yx_last_error()
+
+
+def test_plan_lane_api_validates_arguments_without_a_gpu():
+    """yx_plan_begin_lane / end_lane / join_lanes are pure host bookkeeping: usable (and checked) on a GPU-less host."""
+    from pixeltable_yolox_b200 import _lib
+
+    lib = _lib.lib()
+    plan = lib.yx_plan_create()
+    try:
+        assert lib.yx_plan_begin_lane(plan, 0, -1) == -1           # lane ids are 1..8
+        assert lib.yx_plan_begin_lane(plan, 9, -1) == -1
+        assert lib.yx_plan_begin_lane(plan, 1, 0) == -1            # op 0 does not exist yet
+        assert b"not an existing op" in lib.yx_last_error()
+        assert lib.yx_plan_begin_lane(plan, 1, -1) == 0
+        assert lib.yx_plan_end_lane(plan) == 0
+        assert lib.yx_plan_join_lanes(plan) == 0
+        assert lib.yx_plan_num_ops(plan) == 0
+    finally:
+        lib.yx_plan_destroy(plan)
