@@ -25,7 +25,8 @@
 namespace yx {
 
 static constexpr int kBnX = 6;          // max X halo slots
-static constexpr int kBnThreads = 64 + 256 + 256;   // TMA + MMA warps, 8 epilogue-1 warps (4 per GEMM1 tile), 8 epilogue-2 warps
+static constexpr int kBnThreads = 64 + 256 + 256 + 32;   // TMA + GEMM2 warps, 8 epilogue-1 warps (4 per GEMM1 tile), 8 epilogue-2 warps, GEMM1 warp
+static constexpr int kWarpG1 = 18;
 
 struct BneckParams {
   int C, Cpad;               // channels (= N = K), TMEM column pitch
@@ -57,7 +58,7 @@ struct __align__(8) BneckShared {
   uint32_t tmem_base;
 };
 
-template <bool FP16, int KS>
+template <bool FP16, int KS, bool SILU>
 __global__ void __launch_bounds__(kBnThreads, 1)
 bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                 const __grid_constant__ CUtensorMap map_w2, const BneckParams p) {
@@ -97,8 +98,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_launch_dependents();      // the weights are constants: loaded before griddepcontrol.wait (see the producer)
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const long long T = p.num_tiles;
@@ -113,6 +113,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       mbar_arrive_expect_tx(&sh->wfull, p.w_tx_bytes * 10u);
       tma_load_2d(&map_w1, &sh->wfull, w1s, 0, 0);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(&map_w2, &sh->wfull, w2s + (size_t)tap * p.w_tile_bytes, tap * p.C, 0);
+      pdl_wait();
       int sx = 0;
       uint32_t px = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -128,7 +129,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== GEMM2 issuer =====================
     const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
     const uint32_t rb16 = p.row_bytes >> 4, prb16 = (uint32_t)p.pitch * rb16;
     const uint32_t x16 = smem_u32(xs) >> 4, xslot16 = p.x_slot_bytes >> 4;
@@ -140,32 +141,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     mbar_wait(&sh->wfull, 0);
     int sx = 0;
     uint32_t px = 0;
-    // GEMM1 of tile k: whole halo (two 128-row tiles) x W1
-    auto gemm1 = [&](int k) {
-      const int st = k & 1;
-      mbar_wait(&sh->xfull[sx], px);
-      BN_TRACE(3, k, 1);
-      mbar_wait(&sh->a1empty[st], (uint32_t)(((k >> 1) & 1) ^ 1));
-      BN_TRACE(3, k, 2);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t xd = dhi | (uint64_t)(x16 + (uint32_t)sx * xslot16);
-        const uint32_t d0 = tmem_base + acc1_col + (uint32_t)((st * 2) * p.Cpad);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint64_t a = xd + (uint64_t)(mt * 128) * rb16;
-#pragma unroll
-          for (int j = 0; j < ks; ++j) umma_f16(d0 + (uint32_t)(mt * p.Cpad), a + 2 * j, w1d + 2 * j, idesc, (uint32_t)(j != 0));
-        }
-        umma_commit(&sh->a1full[st]);
-        umma_commit(&sh->xempty[sx]);
-      }
-      __syncwarp();
-      if (++sx == p.nx) { sx = 0; px ^= 1; }
-    };
-    if (n_my > 0) gemm1(0);
     for (int it = 0; it < n_my; ++it) {
-      if (it + 1 < n_my) gemm1(it + 1);
       BN_TRACE(0, it, 0);
       const int st = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
@@ -190,6 +166,40 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       __syncwarp();
       BN_TRACE(0, it, 3);
     }
+  } else if (warp == kWarpG1) {
+    // ===================== GEMM1 issuer (own warp: its waits and commits never delay GEMM2) =====================
+    const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
+    const uint32_t rb16 = p.row_bytes >> 4;
+    const uint32_t x16 = smem_u32(xs) >> 4, xslot16 = p.x_slot_bytes >> 4;
+    const uint64_t w1d = dhi | (uint64_t)(smem_u32(w1s) >> 4);
+    const uint32_t idesc = p.idesc;
+    constexpr int ks = KS;
+    mbar_wait(&sh->wfull, 0);
+    int sx = 0;
+    uint32_t px = 0;
+    // GEMM1 of tile k: whole halo (two 128-row tiles) x W1
+    for (int k = 0; k < n_my; ++k) {
+      const int st = k & 1;
+      mbar_wait(&sh->xfull[sx], px);
+      BN_TRACE(3, k, 1);
+      mbar_wait(&sh->a1empty[st], (uint32_t)(((k >> 1) & 1) ^ 1));
+      BN_TRACE(3, k, 2);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t xd = dhi | (uint64_t)(x16 + (uint32_t)sx * xslot16);
+        const uint32_t d0 = tmem_base + acc1_col + (uint32_t)((st * 2) * p.Cpad);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t a = xd + (uint64_t)(mt * 128) * rb16;
+#pragma unroll
+          for (int j = 0; j < ks; ++j) umma_f16(d0 + (uint32_t)(mt * p.Cpad), a + 2 * j, w1d + 2 * j, idesc, (uint32_t)(j != 0));
+        }
+        umma_commit(&sh->a1full[st]);
+        umma_commit(&sh->xempty[sx]);
+      }
+      __syncwarp();
+      if (++sx == p.nx) { sx = 0; px ^= 1; }
+    }
   } else if (warp < 10) {
     // ===================== epilogue 1: h = act(acc1 + b1) -> swizzled shared operand =====================
     // warps 2..5 own GEMM1 tile 0 (halo rows 0..127), warps 6..9 tile 1 (rows 128..)
@@ -203,7 +213,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t rowoff = (uint32_t)q * (uint32_t)(C * 2);
     // canonical K-major layout: the 16-byte chunk index is XOR-ed with address bits [7, 7 + log2(mask + 1)) of the row
     const uint32_t xr = (rowoff >> 7) & (C == 64 ? 7u : (C == 32 ? 3u : 1u));
-    const bool silu_tanh1 = (p.act1 == YX_ACT_SILU && !fp16);
+    constexpr bool silu_tanh1 = SILU && !FP16;      // compile-time: no activation dispatch (indirect branch) per chunk
     for (int it = 0; it < n_my; ++it) {
       const int t = t_begin + it;
       const int b = fast_div(t, p.mul_tpi, tiles_per_img);
@@ -212,7 +222,6 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int tx = r - ty * p.tiles_w;
       const int st = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      BN_TRACE(1, it, 0);
       mbar_wait(&sh->a1full[st], ph);
       BN_TRACE(1, it, 1);
       mbar_wait(&sh->hempty[st], ph ^ 1);
@@ -228,7 +237,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           uint32_t w[8];
           if (inside) {
             float v[16];
-            if (silu_tanh1) {
+            if constexpr (silu_tanh1) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 const float4 bb = *reinterpret_cast<const float4*>(sbias1 + c + j);
@@ -260,18 +269,15 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (stored) *reinterpret_cast<uint4*>(hslot + phys) = make_uint4(w[4 * hch], w[4 * hch + 1], w[4 * hch + 2], w[4 * hch + 3]);
           }
         };
+        // all C/16 TMEM loads of the row are issued back to back and waited for once
+        uint32_t raw[KS][16];
 #pragma unroll
-        for (int c = 0; c < C; c += 32) {
-          constexpr bool kTwoAlways = (C % 32 == 0);
-          const bool two = kTwoAlways || (c + 16 < C);
-          uint32_t ra[16], rb[16];
-          tmem_ld_x16(taddr + (uint32_t)c, ra);
-          if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
-          tmem_ld_wait();
-          emit(ra, c);
-          if (two) emit(rb, c + 16);
-        }
+        for (int k = 0; k < KS; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * k), raw[k]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < KS; ++k) emit(raw[k], 16 * k);
       }
+      BN_TRACE(1, it, 0);
       tc_fence_before();
       mbar_arrive(&sh->a1empty[st]);
       fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
@@ -280,6 +286,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else {
     // ===================== epilogue 2: y = act(acc2 + b2) (+ x) =====================
+    pdl_wait();
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int hl0 = row / p.pitch, wl0 = row - hl0 * p.pitch;
@@ -315,8 +322,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk<FP16>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();
@@ -472,7 +479,8 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));
     YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-#define YX_BN_ATTR(F, K) YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel<F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+#define YX_BN_ATTR(F, K) YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel<F, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel<F, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     YX_BN_ATTR(false, 1); YX_BN_ATTR(false, 2); YX_BN_ATTR(false, 4); YX_BN_ATTR(true, 1); YX_BN_ATTR(true, 2); YX_BN_ATTR(true, 4);
 #undef YX_BN_ATTR
     attr_set = true;
@@ -489,7 +497,8 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool h16 = L->p.epi.dtype == YX_FP16;
-#define YX_BN_GO(F, K) YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K>, L->map_x, L->map_w1, L->map_w2, L->p))
+#define YX_BN_GO(F, K) do { if (L->p.act1 == YX_ACT_SILU) YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K, true>, L->map_x, L->map_w1, L->map_w2, L->p)); \
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K, false>, L->map_x, L->map_w1, L->map_w2, L->p)); } while (0)
   if (L->p.ksteps == 4) { if (h16) YX_BN_GO(true, 4); else YX_BN_GO(false, 4); }
   else if (L->p.ksteps == 2) { if (h16) YX_BN_GO(true, 2); else YX_BN_GO(false, 2); }
   else { if (h16) YX_BN_GO(true, 1); else YX_BN_GO(false, 1); }
@@ -499,7 +508,7 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
     YX_CUDA(cudaStreamSynchronize(stream));
     YX_CUDA(cudaMemcpyFromSymbol(h, g_bneck_trace, sizeof(h)));
     const long long t0 = h[3][0][0];
-    const char* names[4] = {"mma : g1(next) issued | hfull seen | a2empty seen | g2 issued", "epi1: start | a1full seen | hempty seen | done",
+    const char* names[4] = {"mma : g1(next) issued | hfull seen | a2empty seen | g2 issued", "epi1: stores issued | a1full seen | hempty seen | done",
                             "epi2: start | a2full seen | done", "tma : xempty seen | (mma) xfull seen | (mma) a1empty seen"};
     for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "%s\n", names[r]);

@@ -60,6 +60,7 @@ struct ConvTcParams {
   unsigned a_slot_bytes, a_tx_bytes, row_bytes;
   int b_resident;        // all 9*kchunks weight tiles stay in smem (n_tiles == 1)
   unsigned b_tile_bytes, b_tx_bytes, b_region_bytes;
+  int pdl_late;          // 1: weights are prefetched before griddepcontrol.wait
   int base_off;          // 1: set the descriptor base-offset field from the shifted start address
   unsigned mul_tpi, mul_tw, mul_ntiles, mul_ohw, mul_ow;   // floor(2^32 / d) + 1 for tiles_per_img, tiles_w, n_tiles, out_h*out_w, out_w
   // ---- halo == 2 (3x3 stride 2): input viewed as [2C, W/2, H, B] (x parity folded into the channels), one
@@ -142,7 +143,8 @@ __device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint
 }
 
 
-template <bool FP16>
+// SILU: the activation is SiLU (compile-time: the generic activation code and its per-chunk dispatch disappear)
+template <bool FP16, bool SILU>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
@@ -196,8 +198,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = sh->tmem_base;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias copy) touches only
   // constants and overlaps the tail of the previous kernel; activations are read/written after the wait
+  // resident weights are constants: their loads are issued BEFORE griddepcontrol.wait (each role waits itself,
+  // right before its first access to activations), so they overlap the previous kernel's tail as well
   pdl_launch_dependents();
-  pdl_wait();
+  if (p.pdl_late == 0) pdl_wait();   // YX_PDL_EARLY=0: every thread waits here (A/B switch)
 
   const int num_k = p.ksize * p.ksize * p.kchunks;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -224,6 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int o = 0; o < p.s2[k].nops; ++o, ++nb)
               tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)nb * p.b_tile_bytes, p.s2[k].bk[o] + cc * 64, 0);
       }
+      pdl_wait();
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -319,6 +324,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_2d(&map_b, &sh->bres_full, bregion + (size_t)(c * p.taps + tap) * p.b_tile_bytes,
                         tap * p.in_c + c * p.KC, 0);
       }
+      pdl_wait();
       int ca = 0, sb = 0;
       uint32_t pb = 0;
       for (int t = t_begin; t < t_end;) {
@@ -436,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -502,6 +509,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue (warps 2.., in groups of 4) =====================
     // With one epilogue warp per scheduler every dependent instruction stalls the SM sub-partition;
     // group g drains the tiles it, it+G, ... of this CTA so that G tiles are in the epilogue at once.
+    pdl_wait();                               // residual reads / output writes must follow the previous kernel
     const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32)
     const int row = quarter * 32 + lane;     // accumulator row = pixel inside the tile
     const int grp = (warp - 2) >> 2;
@@ -665,9 +673,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
+          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
           if (two)
-            epi_tc_chunk<FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
+            epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
                          n_tile * p.BN + c + 16);
         }
       }
@@ -1036,6 +1044,7 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
   }
+  p.pdl_late = (getenv("YX_PDL_EARLY") && getenv("YX_PDL_EARLY")[0] == '0') ? 0 : 1;
   p.mul_tpi = fast_div_mul(p.tiles_w * p.tiles_h);
   p.mul_tw = fast_div_mul(p.tiles_w);
   p.mul_ntiles = fast_div_mul(p.n_tiles);
@@ -1066,8 +1075,10 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));
     YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1081,10 +1092,14 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (L->p.epi.dtype == YX_FP16)
-    YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, L->map_a, L->map_b, L->p));
-  else
-    YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, L->map_a, L->map_b, L->p));
+  const bool silu = L->p.epi.act == YX_ACT_SILU && L->p.epi.epilogue == YX_EPI_STORE;
+  if (L->p.epi.dtype == YX_FP16) {
+    if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, L->map_a, L->map_b, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, L->map_a, L->map_b, L->p));
+  } else {
+    if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, L->map_a, L->map_b, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, L->map_a, L->map_b, L->p));
+  }
   return YX_OK;
 }
 

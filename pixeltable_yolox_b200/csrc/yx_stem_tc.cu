@@ -123,7 +123,6 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias copy) touches only
   // constants and overlaps the tail of the previous kernel; activations are read/written after the wait
   pdl_launch_dependents();
-  pdl_wait();
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp < kWarpMma) {
@@ -221,6 +220,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   } else if (warp == kWarpTma) {
     // ===================== patch producer (TMA) =====================
     if (lane == 0) {
+      pdl_wait();
       int ps = 0;
       uint32_t pphase = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -240,6 +240,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
   } else {
     // ===================== epilogue groups =====================
+    pdl_wait();
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int grp = (warp - kWarpEpi) >> 2;

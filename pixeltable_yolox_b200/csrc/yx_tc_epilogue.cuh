@@ -60,12 +60,14 @@ __device__ __forceinline__ void unpack16_t(uint32_t w, float& a, float& b) {
 }
 
 // FP16 is a compile-time parameter: a runtime flag costs a branch per packed pair in the hot loop
-template <bool FP16>
+template <bool FP16, bool SILU_ONLY = false>
 __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
                                              const uint32_t* res, uint16_t* dst, int b, int ho, int wo, int c0) {
   constexpr bool fp16 = FP16;
   float v[16];
-  if (e.act == YX_ACT_SILU && !fp16) {
+  // SILU_ONLY: the caller guarantees act == SiLU (bf16), the generic activation code is not even compiled
+  const bool silu_fast = SILU_ONLY || (e.act == YX_ACT_SILU && !fp16);
+  if (silu_fast) {
     // bf16 output (8-bit significand): the 2^-11 absolute error of tanh.approx is invisible.
     // 3 instructions per element: h = fma(acc, 0.5, bias/2); t = tanh(h); y = fma(h, t, h)
 #pragma unroll
@@ -90,8 +92,8 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
       v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
     }
   }
-  if (e.act == YX_ACT_SILU && !fp16) {
-  } else if (e.act != YX_ACT_NONE) {
+  if (silu_fast) {
+  } else if (!SILU_ONLY && e.act != YX_ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = act_f<false>(v[j], e.act);
   }
