@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, f
   b = __uint_as_float(0x4B000000u | (v >> 8)) - 8388608.0f;
 }
 
-template <typename TI, bool FP16>
+template <typename TI, bool FP16, bool SILU>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_img,
                const StemParams p) {
@@ -268,8 +268,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk<FP16>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();
@@ -370,10 +370,11 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
 int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define YX_STEM_ATTR(T, F) \
+  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+    YX_STEM_ATTR(float, false); YX_STEM_ATTR(float, true); YX_STEM_ATTR(uint8_t, false); YX_STEM_ATTR(uint8_t, true);
+#undef YX_STEM_ATTR
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -388,13 +389,15 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool h16 = L->p.epi.dtype == YX_FP16;
+  const bool silu = L->p.epi.act == YX_ACT_SILU;
+#define YX_STEM_GO(T, F) do { if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, true>, L->map_w, L->map_img, L->p)); \
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, false>, L->map_w, L->map_img, L->p)); } while (0)
   if (L->p.img_dtype == YX_FP32) {
-    if (h16) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, true>, L->map_w, L->map_img, L->p));
-    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<float, false>, L->map_w, L->map_img, L->p));
+    if (h16) YX_STEM_GO(float, true); else YX_STEM_GO(float, false);
   } else {
-    if (h16) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t, true>, L->map_w, L->map_img, L->p));
-    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<uint8_t, false>, L->map_w, L->map_img, L->p));
+    if (h16) YX_STEM_GO(uint8_t, true); else YX_STEM_GO(uint8_t, false);
   }
+#undef YX_STEM_GO
   return YX_OK;
 }
 

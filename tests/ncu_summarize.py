@@ -44,8 +44,12 @@ def launches(src, out, steps=None):
     if steps:
         lines += ["", f"{steps} forward passes captured."]
     Path(out).write_text("\n".join(lines) + "\n")
-    conv = agg.get("yx::conv_tc_kernel") or agg.get("conv_tc_kernel")
-    if conv and conv["rd"] + conv["wr"] > 0:
+    conv = {"n": 0, "ns": 0.0, "rd": 0.0, "wr": 0.0}          # every instantiation of the conv kernel template
+    for k, a in agg.items():
+        if k.split("<")[0].split("::")[-1] == "conv_tc_kernel":
+            for f in conv:
+                conv[f] += a[f]
+    if conv["n"] and conv["rd"] + conv["wr"] > 0:
         t = {"kernel": "conv_tc_kernel", "launches": conv["n"], "dram_bytes_per_launch": (conv["rd"] + conv["wr"]) / conv["n"],
              "dram_read_bytes_per_launch": conv["rd"] / conv["n"], "dram_write_bytes_per_launch": conv["wr"] / conv["n"],
              "source": Path(src).name}
