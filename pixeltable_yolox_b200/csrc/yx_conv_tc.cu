@@ -459,51 +459,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           x0 = tx * p.tw * p.stride - p.pad;
           y0 = ty * p.th * p.stride - p.pad;
         }
-        for (int kt = 0; kt < num_k; ++kt) {
-          const int tap = kt / p.kchunks;
-          const int cc = kt - tap * p.kchunks;
-          const int fr = tap / p.ksize;
-          const int fs = tap - fr * p.ksize;
-          mbar_wait(&sh->empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&sh->full[stage], p.tx_bytes);
-          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-          uint8_t* sb = sa + p.a_stage_bytes;
-          tma_load_4d(&map_a, &sh->full[stage], sa, cc * p.KC, x0 + fs, y0 + fr, b);
-          tma_load_2d(&map_b, &sh->full[stage], sb, tap * p.in_c + cc * p.KC, n_tile * p.BN);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        // taps and channel chunks as nested loops (no division per stage)
+        for (int fr = 0, kb = 0; fr < p.ksize; ++fr) {
+          for (int fs = 0; fs < p.ksize; ++fs, kb += p.in_c) {
+            for (int cc = 0; cc < p.kchunks; ++cc) {
+              mbar_wait(&sh->empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&sh->full[stage], p.tx_bytes);
+              uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+              tma_load_4d(&map_a, &sh->full[stage], sa, cc * p.KC, x0 + fs, y0 + fr, b);
+              tma_load_2d(&map_b, &sh->full[stage], sa + p.a_stage_bytes, kb + cc * p.KC, n_tile * p.BN);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      const int ksteps = p.KC / 16;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        mbar_wait(&sh->tmem_empty[as], aphase ^ 1);
+    // ===================== MMA issuer (per-tap ring) =====================
+    // warp-uniform loop, one elected lane issues; ~12 instructions + KC/16 MMAs per stage
+    const uint64_t dhi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
+    const uint32_t t16 = smem_u32(tiles) >> 4, stage16 = p.stage_bytes >> 4, boff16 = p.a_stage_bytes >> 4;
+    const uint32_t idesc = p.idesc;
+    const int ksteps = p.KC / 16, n_st = p.stages, n_acc = p.acc_stages;
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      mbar_wait(&sh->tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BNpad);
+      for (int kt = 0; kt < num_k; ++kt) {
+        mbar_wait(&sh->full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BNpad);
-        for (int kt = 0; kt < num_k; ++kt) {
-          mbar_wait(&sh->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + p.a_stage_bytes;
-          const uint64_t hi = (uint64_t)p.desc_hi << 32;
-          // lower word: start address >> 4 | LBO(=1) << 16
-          uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFF) | (1u << 16));
-          uint64_t bdesc = hi | (uint64_t)(((sb >> 4) & 0x3FFF) | (1u << 16));
-          for (int j = 0; j < ksteps; ++j) {
-            umma_f16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kt | j) != 0));
-            adesc += 2;  // +32 bytes = 16 elements along K inside the swizzled row
-            bdesc += 2;
-          }
+        if (elect_one_sync()) {
+          const uint64_t ad = dhi | (uint64_t)(t16 + (uint32_t)stage * stage16);
+          const uint64_t bd = ad + boff16;
+          const uint32_t acc0 = (uint32_t)(kt != 0);
+          umma_f16(d_tmem, ad, bd, idesc, acc0);
+          if (ksteps > 1) umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          if (ksteps > 2) { umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u); umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u); }
           umma_commit(&sh->empty[stage]);  // slot is free once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&sh->tmem_full[as]);   // accumulator complete -> epilogue
-        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == n_st) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(&sh->tmem_full[as]);   // accumulator complete -> epilogue
+      __syncwarp();
+      if (++as == n_acc) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2.., in groups of 4) =====================

@@ -160,6 +160,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         }
 #pragma unroll
         for (int i = 0; i < 27; ++i) {
+          // fp16: pixels are fed as x/256 (exact) and the host packs 256*W: BN-folded stem weights (~W/300 for raw
+          // 0..255 inputs) would otherwise fall into fp16's subnormal range and lose most of their mantissa
+          if (FP16) { fa[i] *= 0.00390625f; fb[i] *= 0.00390625f; }
           wds[nw++] = pack16_t<FP16>(fa[i], fb[i]);
           if (nw == 4) {
             uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);

@@ -375,6 +375,9 @@ class Builder:
             packed[:o, :108] = w6.permute(0, 2, 1, 3).reshape(o, 108)          # [o][dy][c][dx]
             bias = torch.zeros((pad16(o),), dtype=torch.float32, device=self.dev)
             bias[:o] = shift.to(self.dev)
+            if self.dtype == torch.float16:
+                packed = packed * 256.0      # the kernel feeds pixels as x/256 in fp16 (see yx_stem_tc.cu): keeps the
+                                             # BN-folded weights out of fp16's subnormal range
             hit = (packed.to(self.dev).to(self.dtype).contiguous(), bias)
             self.keep += list(hit)
             self.weight_cache[key] = hit
