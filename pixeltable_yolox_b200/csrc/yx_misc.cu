@@ -135,40 +135,47 @@ __device__ __forceinline__ uint4 max4(const uint4 a, const uint4 b) {
   return r;
 }
 
-template <typename T2>
+// One CTA = one image x GW groups of 8 channels (GW*16 contiguous bytes per pixel: full 32-byte sectors for GW >= 2,
+// whole 128-byte lines for GW = 8). Item i = pixel * GW + group; the 5x5 max is separable and 9 / 13 are cascades of 5.
+template <typename T2, int GW>
 __global__ void __launch_bounds__(512) spp16_kernel(uint16_t* __restrict__ buf, long long ld, int h, int w, int c) {
-  extern __shared__ uint4 sp[];  // 2 slabs of h*w 128-bit words
-  const int hw = h * w;
+  extern __shared__ uint4 sp[];  // 2 slabs of h*w*GW 128-bit words
+  const int hw = h * w, items = hw * GW;
   uint4* cur = sp;
-  uint4* tmp = sp + hw;
-  const int groups = c / 8;
-  const int b = blockIdx.x / groups;
-  const int g = blockIdx.x - b * groups;
-  uint16_t* base = buf + (long long)b * hw * ld + g * 8;
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) cur[i] = *reinterpret_cast<const uint4*>(base + (long long)i * ld);
+  uint4* tmp = sp + items;
+  const int chunks = c / (8 * GW);
+  const int b = blockIdx.x / chunks;
+  const int g = blockIdx.x - b * chunks;
+  uint16_t* base = buf + (long long)b * hw * ld + g * (8 * GW);
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int px = i / GW, gi = i - px * GW;
+    cur[i] = *reinterpret_cast<const uint4*>(base + (long long)px * ld + gi * 8);
+  }
   __syncthreads();
   for (int level = 1; level <= 3; ++level) {
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // horizontal 5-max (window clipped = -inf padding)
-      const int y = i / w, x = i - y * w;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {   // horizontal 5-max (window clipped = -inf padding)
+      const int px = i / GW;
+      const int y = px / w, x = px - y * w;
       uint4 m = cur[i];
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int xx = x + d;
-        if (d != 0 && xx >= 0 && xx < w) m = max4<T2>(m, cur[y * w + xx]);
+        if (d != 0 && xx >= 0 && xx < w) m = max4<T2>(m, cur[i + d * GW]);
       }
       tmp[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // vertical 5-max
-      const int y = i / w, x = i - y * w;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {   // vertical 5-max
+      const int px = i / GW, gi = i - px * GW;
+      const int y = px / w;
       uint4 m = tmp[i];
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int yy = y + d;
-        if (d != 0 && yy >= 0 && yy < h) m = max4<T2>(m, tmp[yy * w + x]);
+        if (d != 0 && yy >= 0 && yy < h) m = max4<T2>(m, tmp[i + d * w * GW]);
       }
-      cur[i] = m;   // each thread only overwrites its own pixel; others read tmp
-      *reinterpret_cast<uint4*>(base + (long long)i * ld + (long long)level * c) = m;
+      cur[i] = m;   // each thread only overwrites its own item; others read tmp
+      *reinterpret_cast<uint4*>(base + (long long)px * ld + (long long)level * c + gi * 8) = m;
     }
     __syncthreads();
   }
@@ -179,14 +186,20 @@ int spp_launch(void* buf, long long ld, int batch, int h, int w, int c, int dtyp
   YX_REQUIRE(c % 8 == 0 && ld >= 4 * (long long)c, YX_ERR_INVALID_ARG, "spp: c %% 8 != 0 or ld < 4c");
   const unsigned grid = (unsigned)(batch * (c / 8));
   if (dtype != YX_FP32 && (size_t)2 * h * w * 16 <= 200 * 1024 && ld % 8 == 0 && ((uintptr_t)buf & 15) == 0) {
-    const size_t sm16 = (size_t)2 * h * w * 16;
-    if (dtype == YX_BF16) {
-      if (sm16 > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp16_kernel<__nv_bfloat162>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-      spp16_kernel<__nv_bfloat162><<<grid, 512, sm16, s>>>((uint16_t*)buf, ld, h, w, c);
-    } else {
-      if (sm16 > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp16_kernel<__half2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-      spp16_kernel<__half2><<<grid, 512, sm16, s>>>((uint16_t*)buf, ld, h, w, c);
-    }
+    // widest channel group per CTA (contiguous bytes per pixel) whose two slabs fit ~100 KB, so two CTAs share an SM
+    int gw = 1;
+    while (gw < 8 && c % (16 * gw) == 0 && (size_t)2 * h * w * 16 * (2 * gw) <= 100 * 1024) gw *= 2;
+    const size_t sm16 = (size_t)2 * h * w * 16 * gw;
+    const unsigned grid16 = (unsigned)(batch * (c / (8 * gw)));
+#define YX_SPP16(T2, GW)                                                                                         \
+  do {                                                                                                           \
+    if (sm16 > 48 * 1024) YX_CUDA(cudaFuncSetAttribute(spp16_kernel<T2, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16)); \
+    spp16_kernel<T2, GW><<<grid16, 512, sm16, s>>>((uint16_t*)buf, ld, h, w, c);                                  \
+  } while (0)
+#define YX_SPP16_T(T2) do { if (gw == 8) YX_SPP16(T2, 8); else if (gw == 4) YX_SPP16(T2, 4); else if (gw == 2) YX_SPP16(T2, 2); else YX_SPP16(T2, 1); } while (0)
+    if (dtype == YX_BF16) YX_SPP16_T(__nv_bfloat162); else YX_SPP16_T(__half2);
+#undef YX_SPP16_T
+#undef YX_SPP16
     YX_CUDA(cudaGetLastError());
     return YX_OK;
   }
