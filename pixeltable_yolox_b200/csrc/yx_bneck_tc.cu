@@ -413,6 +413,10 @@ int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
     const long long cost = tiles * 4096 + (long long)(th + 2) * (tw + 2);
     if (best < 0 || cost < best) { best = cost; btw = tw; bth = th; }
   }
+  if (const char* e = getenv("YX_BN_TW")) {          // experiment: force the tile width
+    const int tw = atoi(e);
+    if (tw >= 1 && tw + 2 <= 128) { btw = tw < d->w ? tw : d->w; bth = 128 / (btw + 2); if (bth > d->h) bth = d->h; }
+  }
   p.tw = btw; p.th = bth; p.pitch = btw + 2;
   p.halo_rows = (p.th + 2) * p.pitch;
   p.tiles_w = (int)ceil_div64(d->w, p.tw); p.tiles_h = (int)ceil_div64(d->h, p.th);
