@@ -111,7 +111,7 @@ int yx_conv_bn_act_fwd(const yx_conv_desc* d, void* stream);
  *   network_blocks.py:169-172). The hidden tensor stays in shared memory / TMEM.
  *   x   : NHWC slice, c channels, per-pixel stride x_ld;  out: NHWC slice (out_ld), MUST NOT alias x
  *   w1  : [c][1][c], w2: [c][9][c] packed like yx_conv_desc.w (BN folded); bias1/bias2 fp32 [c]
- * Constraints: c in {16, 32, 64}; dtype bf16/fp16; x_ld, out_ld multiples of 16; x/out 32-byte aligned.
+ * Constraints: c in {16, 32, 64, 128}; dtype bf16/fp16; x_ld, out_ld multiples of 16; x/out 32-byte aligned.
  * ------------------------------------------------------------------------------------------ */
 typedef struct yx_bneck_desc {
   int32_t batch, h, w, c;

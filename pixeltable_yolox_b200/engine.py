@@ -247,7 +247,7 @@ class Builder:
             return False
         if type(c1.act) is not type(c2.act) or len(x.segs) != 1 or x.segs[0] != c:
             return False
-        return c in (16, 32, 64)
+        return c in (16, 32, 64, 128)
 
     def bottleneck(self, x: Feat, m, out: Feat) -> Feat:
         """Fused Bottleneck (1x1 -> 3x3 -> optional shortcut) as one launch; `out` must not alias `x`."""

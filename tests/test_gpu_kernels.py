@@ -118,7 +118,7 @@ def _bneck_case(dev, B, H, W, c, dtype, use_add, act, in_off=0, out_off=0, seed=
 
 
 BNECK_CASES = [(2, 16, 16, 64), (1, 80, 80, 64), (3, 40, 40, 32), (1, 160, 160, 32), (2, 13, 21, 16), (1, 5, 3, 64),
-               (5, 23, 61, 32), (2, 80, 80, 16)]
+               (5, 23, 61, 32), (2, 80, 80, 16), (2, 40, 40, 128), (1, 13, 21, 128), (9, 20, 20, 128), (1, 3, 5, 128)]
 
 
 @pytest.mark.parametrize("case", BNECK_CASES)
