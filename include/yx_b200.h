@@ -100,6 +100,20 @@ typedef struct yx_conv_desc {
    * network_blocks.py:176-177) feed two dense buffers. out2 == NULL disables it. */
   int32_t out2_begin;
   void* out2;       int64_t out2_ld;
+  /* YX_EPI_HEAD with head_decode == 3 on the tcgen05 path: stage 1 of yx_postprocess fused into the epilogue
+   * (the thread that decodes an anchor row still holds it in registers). When head_cand != NULL every anchor with
+   * score >= head_conf_thre writes its candidate row head_cand[(b*head_anchors + a)*8] =
+   * (x1,y1,x2,y2,obj,class_conf,class,score) (rows of the other anchors are left untouched: stage 2 never reads
+   * them) and appends its 64-bit sort key to head_keys[b*head_anchors + ...] (count in
+   * head_counts[b], which the caller zeroes first: yx_postprocess_begin) -- exactly what filter_kernel computes from
+   * the fp32 rows (boxes.py:32-50), so yx_nms_prefiltered can follow without re-reading the prediction tensor.
+   * head_xyxy != 0 additionally stores corners instead of (cx,cy,w,h) in head_out, the in-place conversion of
+   * boxes.py:32-37. The three pointers come from yx_postprocess_workspace_ptrs. */
+  float* head_cand;
+  uint64_t* head_keys;
+  int32_t* head_counts;
+  float head_conf_thre;
+  int32_t head_xyxy;
 } yx_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM for bf16/fp16; routes YX_FP32 to the SIMT kernel. */
@@ -198,6 +212,18 @@ int yx_postprocess(float* pred, int32_t batch, int32_t anchors, int32_t nc, floa
                    int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
                    int64_t workspace_bytes, void* stream);
 
+/* yx_postprocess with stage 1 (score filter) already done by the head epilogues (yx_conv_desc.head_cand):
+ *   yx_postprocess_workspace_ptrs : where the candidate rows / sort keys / per-image counters live inside a
+ *                                   workspace of yx_postprocess_workspace_bytes(batch, anchors) bytes
+ *   yx_postprocess_begin          : zeroes the per-image candidate counters (before the head GEMMs run)
+ *   yx_nms_prefiltered            : stage 2 (sort + class-aware NMS + detection rows), same outputs as yx_postprocess */
+int yx_postprocess_workspace_ptrs(void* workspace, int32_t batch, int32_t anchors, float** cand, uint64_t** keys,
+                                  int32_t** counts);
+int yx_postprocess_begin(void* workspace, int32_t batch, int32_t anchors, void* stream);
+int yx_nms_prefiltered(int32_t batch, int32_t anchors, double nms_thre, int32_t nms_variant, float* dets,
+                       int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* The two stages of yx_postprocess on their own (parity tests, SURVEY 8b export list); both use
  * a workspace of yx_postprocess_workspace_bytes(batch, anchors | n_max) bytes.
  * conf_thre is compared in fp32 (torch casts the Python scalar to the tensor dtype, boxes.py:48);
@@ -269,6 +295,12 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
                             int32_t inplace_xyxy, float* dets, int64_t* det_idx,
                             int32_t* det_count, int32_t max_det, void* workspace,
                             int64_t workspace_bytes);
+/* fused-filter variant: yx_plan_add_postprocess_begin goes before the head GEMMs (first op of the plan),
+ * yx_plan_add_nms_prefiltered after them */
+int yx_plan_add_postprocess_begin(yx_plan* p, void* workspace, int32_t batch, int32_t anchors);
+int yx_plan_add_nms_prefiltered(yx_plan* p, int32_t batch, int32_t anchors, double nms_thre, int32_t nms_variant,
+                                float* dets, int64_t* det_idx, int32_t* det_count, int32_t max_det,
+                                void* workspace, int64_t workspace_bytes);
 /* Independent branches. Ops added between yx_plan_begin_lane(lane, after_op) and yx_plan_end_lane belong to side
  * lane `lane` (1..8): in graph mode they run on their own stream, ordered only after main-lane op `after_op`
  * (an index < yx_plan_num_ops, -1 = everything added so far). yx_plan_join_lanes makes the next main-lane op (or

@@ -42,6 +42,8 @@ class ConvDesc(C.Structure):
         ("head_stride", C.c_float),
         ("out2_begin", C.c_int32),
         ("out2", C.c_void_p), ("out2_ld", C.c_int64),
+        ("head_cand", C.c_void_p), ("head_keys", C.c_void_p), ("head_counts", C.c_void_p),
+        ("head_conf_thre", C.c_float), ("head_xyxy", C.c_int32),
     ]
 
 
@@ -78,6 +80,9 @@ SIGNATURES = {
     "yx_head_decode": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "yx_postprocess_workspace_bytes": (_I64, [_I32, _I32]),
     "yx_postprocess": (C.c_int, [_P, _I32, _I32, _I32, _F, _D, _I32, _I32, _P, _P, _P, _I32, _P, _I64, _P]),
+    "yx_postprocess_workspace_ptrs": (C.c_int, [_P, _I32, _I32, _P, _P, _P]),
+    "yx_postprocess_begin": (C.c_int, [_P, _I32, _I32, _P]),
+    "yx_nms_prefiltered": (C.c_int, [_I32, _I32, _D, _I32, _P, _P, _P, _I32, _P, _I64, _P]),
     "yx_score_filter_compact": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _I64, _P]),
     "yx_batched_nms": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _D, _I32, _P, _P, _P, _I64, _P]),
     "yx_bboxes_iou": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _P]),
@@ -93,6 +98,8 @@ SIGNATURES = {
     "yx_plan_add_focus": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32]),
     "yx_plan_add_focus_conv": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32]),
     "yx_plan_add_postprocess": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _D, _I32, _I32, _P, _P, _P, _I32, _P, _I64]),
+    "yx_plan_add_postprocess_begin": (C.c_int, [_P, _P, _I32, _I32]),
+    "yx_plan_add_nms_prefiltered": (C.c_int, [_P, _I32, _I32, _D, _I32, _P, _P, _P, _I32, _P, _I64]),
     "yx_plan_begin_lane": (C.c_int, [_P, _I32, _I32]),
     "yx_plan_end_lane": (C.c_int, [_P]),
     "yx_plan_join_lanes": (C.c_int, [_P]),

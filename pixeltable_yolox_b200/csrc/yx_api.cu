@@ -30,6 +30,10 @@ long long postprocess_ws_bytes(int batch, int anchors);
 int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_thre, double nms_thre, int nms_variant,
                        int inplace_xyxy, float* dets, long long* det_idx, int* det_count, int max_det, void* ws,
                        long long ws_bytes, cudaStream_t s);
+int postprocess_ws_ptrs(void* ws, int batch, int anchors, float** cand, unsigned long long** keys, int** counts);
+int postprocess_begin_launch(void* ws, int batch, int anchors, cudaStream_t s);
+int nms_prefiltered_launch(int batch, int anchors, double nms_thre, int nms_variant, float* dets, long long* det_idx,
+                           int* det_count, int max_det, void* ws, long long ws_bytes, cudaStream_t s);
 int filter_compact_launch(const float* pred, int batch, int anchors, int nc, float conf_thre, float* cand,
                           int* cand_idx, int* cand_count, void* ws, long long ws_bytes, cudaStream_t s);
 int batched_nms_launch(const float* boxes, const float* scores, const int* cls, const int* counts, int batch,
@@ -113,7 +117,7 @@ static int require_device() {
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP_STEM, OP_BNECK };
+enum OpKind { OP_CONV_TC, OP_CONV_SIMT, OP_DWCONV, OP_SPP, OP_FOCUS, OP_POST, OP_STEM, OP_BNECK, OP_POST_BEGIN, OP_NMS };
 
 struct Op {
   OpKind kind;
@@ -161,6 +165,9 @@ static int run_op(const Op& o, cudaStream_t s) {
     case OP_POST: return postprocess_launch(o.post.pred, o.post.batch, o.post.anchors, o.post.nc, o.post.conf, o.post.nms,
                                             o.post.variant, o.post.inplace, o.post.dets, o.post.det_idx, o.post.det_count,
                                             o.post.max_det, o.post.ws, o.post.ws_bytes, s);
+    case OP_POST_BEGIN: return postprocess_begin_launch(o.post.ws, o.post.batch, o.post.anchors, s);
+    case OP_NMS: return nms_prefiltered_launch(o.post.batch, o.post.anchors, o.post.nms, o.post.variant, o.post.dets,
+                                               o.post.det_idx, o.post.det_count, o.post.max_det, o.post.ws, o.post.ws_bytes, s);
   }
   return YX_ERR_INVALID_ARG;
 }
@@ -289,6 +296,26 @@ int yx_postprocess(float* pred, int32_t batch, int32_t anchors, int32_t nc, floa
   if (rc) return rc;
   return postprocess_launch(pred, batch, anchors, nc, conf_thre, nms_thre, nms_variant, inplace_xyxy, dets,
                             (long long*)det_idx, det_count, max_det, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int yx_postprocess_workspace_ptrs(void* workspace, int32_t batch, int32_t anchors, float** cand, uint64_t** keys,
+                                  int32_t** counts) {
+  return postprocess_ws_ptrs(workspace, batch, anchors, cand, (unsigned long long**)keys, counts);
+}
+
+int yx_postprocess_begin(void* workspace, int32_t batch, int32_t anchors, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return postprocess_begin_launch(workspace, batch, anchors, (cudaStream_t)stream);
+}
+
+int yx_nms_prefiltered(int32_t batch, int32_t anchors, double nms_thre, int32_t nms_variant, float* dets,
+                       int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return nms_prefiltered_launch(batch, anchors, nms_thre, nms_variant, dets, (long long*)det_idx, det_count, max_det,
+                                workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int yx_score_filter_compact(const float* pred, int32_t batch, int32_t anchors, int32_t nc, float conf_thre,
@@ -476,6 +503,32 @@ int yx_plan_add_postprocess(yx_plan* p, float* pred, int32_t batch, int32_t anch
             det_count, max_det, workspace, workspace_bytes};
   plan_push(p, o);
   p->launches += 2;  // filter + sort/NMS kernels (plus one memset node)
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_postprocess_begin(yx_plan* p, void* workspace, int32_t batch, int32_t anchors) {
+  YX_REQUIRE(p && workspace && batch > 0 && anchors > 0, YX_ERR_INVALID_ARG, "plan_add_postprocess_begin: bad arguments");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_POST_BEGIN;
+  o.post.ws = workspace; o.post.batch = batch; o.post.anchors = anchors;
+  plan_push(p, o);            // a memset node, not a kernel launch
+  plan_invalidate(p);
+  return YX_OK;
+}
+
+int yx_plan_add_nms_prefiltered(yx_plan* p, int32_t batch, int32_t anchors, double nms_thre, int32_t nms_variant,
+                                float* dets, int64_t* det_idx, int32_t* det_count, int32_t max_det, void* workspace,
+                                int64_t workspace_bytes) {
+  YX_REQUIRE(p, YX_ERR_INVALID_ARG, "plan_add_nms_prefiltered: null plan");
+  Op o;
+  memset(&o, 0, sizeof(o));
+  o.kind = OP_NMS;
+  o.post = {nullptr, batch, anchors, 0, 0.0f, nms_thre, nms_variant, 0, dets, (long long*)det_idx, det_count, max_det,
+            workspace, workspace_bytes};
+  plan_push(p, o);
+  p->launches += 1;  // sort/NMS kernel
   plan_invalidate(p);
   return YX_OK;
 }

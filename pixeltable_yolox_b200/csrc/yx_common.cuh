@@ -91,25 +91,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// float -> uint32 whose unsigned order is the float order (sort keys of the score filter)
+__device__ __forceinline__ uint32_t orderable_f32(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 // Bounded spin: a pipeline bug must surface as a trapped launch, never as a hung GPU.
 // g_mbar_dbg (one copy per translation unit): [0] timeout seen, [1..4] block / thread / barrier smem address / parity of
 // the first one, [7] != 0: do not trap, give up the wait instead (diagnostic runs read the record back afterwards).
 static __device__ int g_mbar_dbg[8];
+// cold path, kept out of line so the waiting loops stay a handful of instructions; returns true to give up the wait
+static __device__ __noinline__ bool mbar_timed_out(uint32_t bar_smem, uint32_t parity) {
+  if (atomicCAS(&g_mbar_dbg[0], 0, 1) == 0) {
+    g_mbar_dbg[1] = (int)blockIdx.x; g_mbar_dbg[2] = (int)threadIdx.x;
+    g_mbar_dbg[3] = (int)bar_smem; g_mbar_dbg[4] = (int)parity;
+  }
+  if (g_mbar_dbg[7]) {
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == (unsigned)g_mbar_dbg[1])
+      printf("yx_b200: [no-trap] wait gave up: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar_smem, parity);
+    return true;
+  }
+  printf("yx_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+  __trap();
+  return true;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 18)) {
-      if (atomicCAS(&g_mbar_dbg[0], 0, 1) == 0) {
-        g_mbar_dbg[1] = (int)blockIdx.x; g_mbar_dbg[2] = (int)threadIdx.x;
-        g_mbar_dbg[3] = (int)smem_u32(bar); g_mbar_dbg[4] = (int)parity;
-      }
-      if (g_mbar_dbg[7]) {
-        if ((threadIdx.x & 31) == 0 && blockIdx.x == (unsigned)g_mbar_dbg[1])
-          printf("yx_b200: [no-trap] wait gave up: block %d warp %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), smem_u32(bar), parity);
-        return;
-      }
-      printf("yx_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
+      if (mbar_timed_out(smem_u32(bar), parity)) return;
     }
   }
 }

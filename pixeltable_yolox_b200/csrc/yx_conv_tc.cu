@@ -144,7 +144,9 @@ __device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint
 
 
 // SILU: the activation is SiLU (compile-time: the generic activation code and its per-chunk dispatch disappear)
-template <bool FP16, bool SILU>
+// HEAD: the YX_EPI_HEAD epilogue (decode + optional score filter) is its own instantiation, so its ~1 000 SASS
+// instructions do not sit in the instruction cache footprint / register allocation of the activation-store kernels
+template <bool FP16, bool SILU, bool HEAD>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
@@ -162,9 +164,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   {
     const float bscale = (epi_half_bias(p.epi) && p.epi.epilogue == YX_EPI_STORE) ? 0.5f : 1.0f;
     // head: the sigmoid channels (obj, classes) stage -log2e * bias (see the head epilogue)
-    const float hscale = (p.epi.epilogue == YX_EPI_HEAD && (p.epi.head_decode & 2)) ? -1.4426950408889634f : 1.0f;
+    const float hscale = (HEAD && (p.epi.head_decode & 2)) ? -1.4426950408889634f : 1.0f;
     for (int i = threadIdx.x; i < p.epi.out_c; i += blockDim.x)
-      sbias[i] = p.epi.bias[i] * (p.epi.epilogue == YX_EPI_HEAD ? (i >= 4 ? hscale : 1.0f) : bscale);
+      sbias[i] = p.epi.bias[i] * (HEAD ? (i >= 4 ? hscale : 1.0f) : bscale);
   }
 
   const int warp = threadIdx.x >> 5;
@@ -519,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int hl0 = 0, wl0 = 0;
     if (!p.flat) { hl0 = row / p.pitch; wl0 = row - hl0 * p.pitch; }
     const bool row_ok = p.flat || (hl0 < p.th && wl0 < p.tw);
-    const bool need_coords = p.flat && (p.epi.ups != nullptr || p.epi.epilogue == YX_EPI_HEAD);
+    const bool need_coords = p.flat && (p.epi.ups != nullptr || HEAD);
     int as = grp % p.acc_stages;
     uint32_t aphase = (uint32_t)((grp / p.acc_stages) & 1);
     for (int it = grp;; it += p.epi_groups) {
@@ -564,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
       const float* tbias = sbias + n_tile * p.BN;
-      if (p.epi.epilogue == YX_EPI_HEAD) {
+      if constexpr (HEAD) {
         // ---- head: decode/sigmoid in registers, stage the warp's 32 rows in shared memory, then
         //      write each [5+nc] fp32 row with coalesced 128-byte stores
         const int nch = 5 + p.epi.head_nc;
@@ -574,28 +576,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool dec_box = (p.epi.head_decode & 1) != 0, dec_sig = (p.epi.head_decode & 2) != 0;
         const float sgn = dec_sig ? -1.4426950408889634f : 1.0f;
         float* wrow = wstage + lane * nch;
+        // 16 channels at a time: the biases are read first (four LDS.128) and all 16 values are finished before the
+        // first store. Interleaving `wrow[j] = ...` with `tbias[j]` reads made every element a serial
+        // LDS -> FFMA -> EX2 -> FADD -> RCP -> STS chain (shared stores and loads may alias, so they are kept in
+        // order): ncu showed the epilogue warps ~95 % stalled on the short scoreboard at ~9 clk per instruction.
+        // fused score filter (stage 1 of yx_postprocess, filter_kernel in yx_postprocess.cu). Arg-max over the class
+        // confidences with torch.max's rule (first maximum wins; a NaN wins and the first NaN is reported): sigmoid
+        // outputs are +0..1 or the canonical NaN, so their bit patterns compared as signed integers order exactly that way
+        // and a pairwise tree that keeps the LEFT operand on ties reports the first index. Since score = obj * conf <= obj,
+        // a warp none of whose anchors has obj >= conf_thre skips the arg-max altogether (the usual case).
+        const bool filt = p.epi.head_cand != nullptr;
+        bool need = false;              // warp-uniform
+        float obj = 0.0f;
+        int best_bits = -1, best_i = 0;
+        auto sig16 = [&](const uint32_t (&r)[16], int cc, int lo) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(tbias + cc + j);
+            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sgn, bb.x);
+            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sgn, bb.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sgn, bb.z);
+            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sgn, bb.w);
+          }
+          if (dec_sig) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = ex2_approx(v[j]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = rcp_approx(1.0f + v[j]);
+          }
+          const bool full = cc + 16 <= nch;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j >= lo) wrow[cc + j] = v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j >= lo && cc + j < nch) wrow[cc + j] = v[j];
+          }
+          if (filt) {
+            if (lo) {                            // first chunk: channel 4 is the objectness
+              obj = v[4];
+              need = __any_sync(0xffffffffu, valid && !(obj < p.epi.head_conf));
+            }
+            if (need) {
+              const int first = lo ? 5 : 0;      // classes start at channel 5
+              int kb[16], ki[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                kb[j] = (j >= first && (full || cc + j < nch)) ? __float_as_int(v[j]) : -1;
+                ki[j] = j;
+              }
+#pragma unroll
+              for (int st = 1; st < 16; st <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2 * st) {
+                  const bool t = kb[j + st] > kb[j];
+                  kb[j] = t ? kb[j + st] : kb[j];
+                  ki[j] = t ? ki[j + st] : ki[j];
+                }
+              }
+              if (kb[0] > best_bits) { best_bits = kb[0]; best_i = cc - 5 + ki[0]; }
+            }
+          }
+        };
+        float x0, x1, x2, x3;
         {
           // channels 0..15: box (cx, cy, w, h) then obj / first classes
           uint32_t raw[16];
           tmem_ld_x16(taddr, raw);
           tmem_ld_wait();
-          float x0 = __uint_as_float(raw[0]) + tbias[0], x1 = __uint_as_float(raw[1]) + tbias[1];
-          float x2 = __uint_as_float(raw[2]) + tbias[2], x3 = __uint_as_float(raw[3]) + tbias[3];
+          const float4 b0 = *reinterpret_cast<const float4*>(tbias);
+          x0 = __uint_as_float(raw[0]) + b0.x; x1 = __uint_as_float(raw[1]) + b0.y;
+          x2 = __uint_as_float(raw[2]) + b0.z; x3 = __uint_as_float(raw[3]) + b0.w;
           if (dec_box) {
             x0 = (x0 + (float)wo) * p.epi.head_stride;
             x1 = (x1 + (float)ho) * p.epi.head_stride;
             x2 = __expf(x2) * p.epi.head_stride;
             x3 = __expf(x3) * p.epi.head_stride;
           }
-          wrow[0] = x0; wrow[1] = x1; wrow[2] = x2; wrow[3] = x3;
-#pragma unroll
-          for (int j = 4; j < 16; ++j) {
-            if (j < nch) {
-              float v = fmaf(__uint_as_float(raw[j]), sgn, tbias[j]);
-              if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
-              wrow[j] = v;
-            }
-          }
+          sig16(raw, 0, 4);
         }
         for (int c = 16; c < p.BN; c += 32) {
           const bool two = (c + 16 < p.BN);
@@ -603,36 +662,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_x16(taddr + (uint32_t)c, ra);
           if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
           tmem_ld_wait();
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half == 1 && !two) break;
-            const int cc = c + 16 * half;
-            if (cc >= nch) break;
-            const uint32_t(&r)[16] = half ? rb : ra;
-            if (cc + 16 <= nch) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float v = fmaf(__uint_as_float(r[j]), sgn, tbias[cc + j]);
-                if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
-                wrow[cc + j] = v;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (cc + j < nch) {
-                  float v = fmaf(__uint_as_float(r[j]), sgn, tbias[cc + j]);
-                  if (dec_sig) v = rcp_approx(1.0f + ex2_approx(v));
-                  wrow[cc + j] = v;
-                }
+          if (c < nch) sig16(ra, c, 0);
+          if (two && c + 16 < nch) sig16(rb, c + 16, 0);
+        }
+        const long long arow = valid ? ((long long)b * p.epi.head_anchors + p.epi.head_anchor_off +
+                                        (long long)ho * p.epi.out_w + wo) : -1;
+        if (filt || p.epi.head_xyxy) {
+          // boxes.py:32-37 and :44-50 in the filter kernel's arithmetic (round-to-nearest intrinsics: no FMA contraction)
+          const float hw2 = __fdiv_rn(x2, 2.0f), hh2 = __fdiv_rn(x3, 2.0f);
+          const float4 box = make_float4(__fsub_rn(x0, hw2), __fsub_rn(x1, hh2), __fadd_rn(x0, hw2), __fadd_rn(x1, hh2));
+          if (p.epi.head_xyxy) { x0 = box.x; x1 = box.y; x2 = box.z; x3 = box.w; }
+          if (filt && need) {
+            const float best = __int_as_float(best_bits);
+            const float score = __fmul_rn(obj, best);
+            const bool pass = valid && score >= p.epi.head_conf;
+            if (pass) {          // rows of anchors below the threshold are never read by the NMS stage
+              float4* crow = reinterpret_cast<float4*>(p.epi.head_cand + arow * 8);
+              crow[0] = box;
+              crow[1] = make_float4(obj, best, (float)best_i, score);
+            }
+            // a warp's rows may straddle two images (flat 1x1 tiles): aggregate per image of the first passing lane,
+            // the rare lanes of the other image append on their own
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+              const int leader = __ffs(bal) - 1;
+              const int bl = __shfl_sync(0xffffffffu, b, leader);
+              const unsigned same = __ballot_sync(0xffffffffu, pass && b == bl);
+              int base = 0;
+              if (lane == leader) base = atomicAdd(&p.epi.head_counts[bl], __popc(same));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (pass) {
+                const int a = (int)(arow - (long long)b * p.epi.head_anchors);
+                const float sc = (score == 0.0f) ? 0.0f : score;  // -0 -> +0
+                const unsigned long long key = ((unsigned long long)(~orderable_f32(sc)) << 32) | (unsigned long long)(unsigned)a;
+                const int pos = (b == bl) ? base + __popc(same & ((1u << lane) - 1)) : atomicAdd(&p.epi.head_counts[b], 1);
+                p.epi.head_keys[(long long)b * p.epi.head_anchors + pos] = key;
               }
             }
           }
         }
+        wrow[0] = x0; wrow[1] = x1; wrow[2] = x2; wrow[3] = x3;
         // accumulators are in registers/smem now: hand the TMEM stage back before the slow stores
         tc_fence_before();
         mbar_arrive(&sh->tmem_empty[as]);
-        const long long arow = valid ? ((long long)b * p.epi.head_anchors + p.epi.head_anchor_off +
-                                        (long long)ho * p.epi.out_w + wo) : -1;
         __syncwarp();
         const long long a0 = __shfl_sync(0xffffffffu, arow, 0);
         const bool contiguous = __all_sync(0xffffffffu, arow == a0 + lane) && ((a0 * nch) & 3) == 0 && ((32 * nch) & 3) == 0;
@@ -640,7 +712,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // the warp's 32 rows are one contiguous, 16-byte aligned block of 32*(5+nc) floats
           float4* dst = reinterpret_cast<float4*>(p.epi.head_out + a0 * nch);
           const float4* src = reinterpret_cast<const float4*>(wstage);
-          for (int i = lane; i < 8 * nch; i += 32) dst[i] = src[i];
+          // four 16-byte rows in flight per lane (loads first, then stores)
+          const int n4 = 8 * nch;
+          int i = lane;
+          for (; i + 96 < n4; i += 128) {
+            const float4 t0 = src[i], t1 = src[i + 32], t2 = src[i + 64], t3 = src[i + 96];
+            dst[i] = t0; dst[i + 32] = t1; dst[i + 64] = t2; dst[i + 96] = t3;
+          }
+          for (; i < n4; i += 32) dst[i] = src[i];
         } else {
           for (int r = 0; r < 32; ++r) {
             const long long ar = __shfl_sync(0xffffffffu, arow, r);
@@ -653,8 +732,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         as += p.epi_groups;
         while (as >= p.acc_stages) { as -= p.acc_stages; aphase ^= 1; }
-        continue;
-      }
+      } else {
       // ---- activation store: two 16-column TMEM loads in flight, residual prefetched before the
       //      wait, one 256-bit store per thread per 16 columns (a full 32-byte sector)
       uint16_t* orow = (uint16_t*)p.epi.out + pix * p.epi.out_ld + n_tile * p.BN;
@@ -684,6 +762,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_arrive(&sh->tmem_empty[as]);
       as += p.epi_groups;
       while (as >= p.acc_stages) { as -= p.acc_stages; aphase ^= 1; }
+      }   // !HEAD
     }
   }
 
@@ -738,9 +817,19 @@ int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
   e->head_out = d->head_out;
   e->head_anchors = d->head_anchors; e->head_anchor_off = d->head_anchor_off;
   e->head_nc = d->head_nc; e->head_decode = d->head_decode; e->head_stride = d->head_stride;
+  e->head_cand = d->head_cand; e->head_keys = (unsigned long long*)d->head_keys; e->head_counts = d->head_counts;
+  e->head_conf = d->head_conf_thre; e->head_xyxy = d->head_xyxy;
   if (d->epilogue == YX_EPI_HEAD) {
     YX_REQUIRE(d->head_out != nullptr, YX_ERR_INVALID_ARG, "conv(head): head_out is null");
     YX_REQUIRE(5 + d->head_nc <= d->out_c, YX_ERR_INVALID_ARG, "conv(head): out_c=%d < 5+nc=%d", d->out_c, 5 + d->head_nc);
+    if (d->head_cand || d->head_xyxy) {
+      YX_REQUIRE(d->dtype != YX_FP32, YX_ERR_UNSUPPORTED, "conv(head): the fused score filter exists on the tcgen05 path only");
+      YX_REQUIRE(d->head_decode == 3, YX_ERR_INVALID_ARG, "conv(head): the fused score filter needs head_decode == 3");
+      YX_REQUIRE(d->head_nc >= 1, YX_ERR_INVALID_ARG, "conv(head): the fused score filter needs at least one class");
+      if (d->head_cand)
+        YX_REQUIRE(d->head_keys && d->head_counts && ((uintptr_t)d->head_cand & 15) == 0, YX_ERR_INVALID_ARG,
+                   "conv(head): head_cand needs head_keys, head_counts and 16-byte alignment");
+    }
   } else {
     YX_REQUIRE(d->epilogue == YX_EPI_STORE, YX_ERR_INVALID_ARG, "conv: unknown epilogue %d", d->epilogue);
     YX_REQUIRE(d->out != nullptr, YX_ERR_INVALID_ARG, "conv: out is null");
@@ -1076,10 +1165,12 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));
     YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    YX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -1094,12 +1185,15 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool silu = L->p.epi.act == YX_ACT_SILU && L->p.epi.epilogue == YX_EPI_STORE;
+  const bool head = L->p.epi.epilogue == YX_EPI_HEAD;
   if (L->p.epi.dtype == YX_FP16) {
-    if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, L->map_a, L->map_b, L->p));
-    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, L->map_a, L->map_b, L->p));
+    if (head) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, L->map_a, L->map_b, L->p));
+    else if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, L->map_a, L->map_b, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false>, L->map_a, L->map_b, L->p));
   } else {
-    if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, L->map_a, L->map_b, L->p));
-    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, L->map_a, L->map_b, L->p));
+    if (head) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, L->map_a, L->map_b, L->p));
+    else if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, L->map_a, L->map_b, L->p));
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, L->map_a, L->map_b, L->p));
   }
   return YX_OK;
 }

@@ -20,6 +20,8 @@ struct EpiParams {
   float* head_out;
   int head_anchors, head_anchor_off, head_nc, head_decode;
   float head_stride;
+  float* head_cand; unsigned long long* head_keys; int* head_counts;   // fused score filter (null: off)
+  float head_conf; int head_xyxy;
 };
 
 #ifdef __CUDACC__

@@ -38,10 +38,7 @@ static constexpr int kTriItems = 32 * (kChunkWords * (kChunkWords + 1) / 2);  //
 static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassCap * 4;
 static constexpr int kKeptEntryBytes = 28;  // box 16 + area 4 + class 4 + next 4
 
-__device__ __forceinline__ uint32_t orderable(float f) {
-  uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
+__device__ __forceinline__ uint32_t orderable(float f) { return orderable_f32(f); }
 
 // ------------------------------------------------------------------------------------------
 // Stage 1
@@ -614,6 +611,46 @@ int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_t
   YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "postprocess: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
   int rc = filter_launch(pred, batch, anchors, nc, conf_thre, inplace_xyxy, w, s);
   if (rc) return rc;
+  NmsArgs g;
+  memset(&g, 0, sizeof(g));
+  g.src.boxes = w.cand; g.src.box_stride = 8;
+  g.src.scores = w.cand + 7; g.src.score_stride = 8;
+  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1;
+  g.src.per_image = anchors;
+  g.keys = w.keys; g.counts = w.counts;
+  g.thr = thr_for_strict_gt(nms_thre);
+  g.variant = nms_variant;
+  g.gkeys = w.gkeys; g.sorted_box = w.sbox; g.sorted_cls = w.scls; g.sorted_idx = w.sidx; g.kept_pos = w.kept;
+  g.dets = dets; g.det_idx = det_idx; g.det_count = det_count; g.max_det = max_det;
+  return launch_sort_nms(g, batch, s);
+}
+
+int postprocess_ws_ptrs(void* ws, int batch, int anchors, float** cand, unsigned long long** keys, int** counts) {
+  YX_REQUIRE(ws && batch > 0 && anchors > 0, YX_ERR_INVALID_ARG, "postprocess_workspace_ptrs: bad arguments");
+  YX_REQUIRE(((uintptr_t)ws & 255) == 0, YX_ERR_INVALID_ARG, "postprocess: workspace must be 256-byte aligned");
+  PostWs w = carve_ws(ws, batch, anchors);
+  if (cand) *cand = w.cand;
+  if (keys) *keys = w.keys;
+  if (counts) *counts = w.counts;
+  return YX_OK;
+}
+
+int postprocess_begin_launch(void* ws, int batch, int anchors, cudaStream_t s) {
+  YX_REQUIRE(ws && batch > 0 && anchors > 0, YX_ERR_INVALID_ARG, "postprocess_begin: bad arguments");
+  PostWs w = carve_ws(ws, batch, anchors);
+  YX_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * 4, s));
+  return YX_OK;
+}
+
+// Stage 2 only: the head epilogues (YX_EPI_HEAD with head_cand) have filled cand / keys / counts.
+int nms_prefiltered_launch(int batch, int anchors, double nms_thre, int nms_variant, float* dets, long long* det_idx,
+                           int* det_count, int max_det, void* ws, long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(dets && det_count && ws, YX_ERR_INVALID_ARG, "nms_prefiltered: null pointer");
+  YX_REQUIRE(batch > 0 && anchors > 0 && max_det > 0, YX_ERR_INVALID_ARG, "nms_prefiltered: bad sizes");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "nms_prefiltered: nms_variant must be 0..4");
+  YX_REQUIRE(((uintptr_t)ws & 255) == 0, YX_ERR_INVALID_ARG, "nms_prefiltered: workspace must be 256-byte aligned");
+  PostWs w = carve_ws(ws, batch, anchors);
+  YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "nms_prefiltered: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
   NmsArgs g;
   memset(&g, 0, sizeof(g));
   g.src.boxes = w.cand; g.src.box_stride = 8;

@@ -16,6 +16,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -203,6 +204,9 @@ class Builder:
             ho = head["out"]
             head_arg = dict(out_ptr=ho.data_ptr(), anchors=head["anchors"], anchor_off=head["anchor_off"],
                             nc=head["nc"], decode=head["decode"], stride=head["stride"])
+            for k in ("cand_ptr", "keys_ptr", "counts_ptr", "conf_thre", "xyxy"):
+                if head.get(k) is not None:
+                    head_arg[k] = head[k]
             out_view = None
         else:
             if out is None:
@@ -247,7 +251,8 @@ class Builder:
             return False
         if type(c1.act) is not type(c2.act) or len(x.segs) != 1 or x.segs[0] != c:
             return False
-        return c in (16, 32, 64, 128)
+        # c = 128 exists (bneck128_tc_kernel) but streams W2 through a 3-stage ring: 65 us vs 55 us for the unfused pair
+        return c in (16, 32, 64)
 
     def bottleneck(self, x: Feat, m, out: Feat) -> Feat:
         """Fused Bottleneck (1x1 -> 3x3 -> optional shortcut) as one launch; `out` must not alias `x`."""
@@ -408,6 +413,20 @@ class Builder:
         self.keep += [pred, dets, det_idx, det_count, ws]
         self.op_info.append(dict(name="postprocess", flops=0.0, bytes=pred.numel() * 4, tc=False))
 
+    def postprocess_begin(self, ws, batch, anchors):
+        """Fused-filter postprocess, part 1: zero the per-image candidate counters before the head GEMMs run."""
+        check(lib().yx_plan_add_postprocess_begin(self.plan, ws.data_ptr(), batch, anchors), "plan_add_postprocess_begin")
+        self.keep.append(ws)
+        self.op_info.append(dict(name="postprocess begin (memset)", flops=0.0, bytes=batch * 4, tc=False))
+
+    def nms_prefiltered(self, batch, anchors, nms, variant, dets, det_idx, det_count, max_det, ws):
+        """Fused-filter postprocess, part 2: sort + NMS over the candidates the head epilogues wrote."""
+        check(lib().yx_plan_add_nms_prefiltered(self.plan, batch, anchors, float(nms), int(variant), dets.data_ptr(),
+                                                det_idx.data_ptr(), det_count.data_ptr(), max_det, ws.data_ptr(),
+                                                ws.numel()), "plan_add_nms_prefiltered")
+        self.keep += [dets, det_idx, det_count, ws]
+        self.op_info.append(dict(name="sort+nms (filter fused in the head)", flops=0.0, bytes=batch * anchors * 32, tc=False))
+
     def profile(self):
         """Per-op device times (ms) of one eager pass: list of dicts (op_info + ms + kind)."""
         n = lib().yx_plan_num_ops(self.plan)
@@ -503,6 +522,22 @@ class InferenceEngine:
         # persistent input staging buffer: the plan's pointers are fixed at build time
         self.input = torch.empty((batch, 3, height, width), dtype=in_dtype, device=device)
         self.pred = torch.empty((batch, self.anchors, 5 + self.nc), dtype=torch.float32, device=device)
+        # postprocess in the same graph: on the 16-bit paths the score filter runs inside the decode epilogue of the
+        # prediction GEMMs (yx_conv_desc.head_cand) and only sort + NMS remain as a kernel of their own
+        self.post = None
+        self._post_fused = None
+        if post is not None:
+            max_det = post.get("max_det") or self.anchors
+            self.dets = torch.zeros((batch, max_det, 7), dtype=torch.float32, device=device)
+            self.det_idx = torch.zeros((batch, max_det), dtype=torch.int64, device=device)
+            self.det_count = torch.zeros((batch,), dtype=torch.int32, device=device)
+            self._post_ws = torch.empty((lib().yx_postprocess_workspace_bytes(batch, self.anchors),), dtype=torch.uint8,
+                                        device=device)
+            self.post = dict(post, max_det=max_det)
+            if self.dtype != torch.float32 and head.decode_in_inference and os.environ.get("YX_FUSED_FILTER", "1") != "0":
+                cand, keys, counts = ops.postprocess_ws_ptrs(self._post_ws, batch, self.anchors)
+                self._post_fused = dict(cand=cand, keys=keys, counts=counts, conf_thre=post["conf_thre"])
+                b.postprocess_begin(self._post_ws, batch, self.anchors)
         # intermediate buffers are allocated while lowering the first micro-batch and reused after
         first_keep = None
         for b0 in range(0, batch, self.mb):
@@ -512,33 +547,36 @@ class InferenceEngine:
             img = self.input[b0:b1]
             if first_keep is None or b1 - b0 != self.mb:
                 mark = len(b.keep)
-                self._lower(img, self.pred[b0:b1])
+                self._lower(img, self.pred[b0:b1], b0)
                 if first_keep is None:
                     first_keep = (mark, len(b.keep))
                     self._record = [t for t in b.keep[mark:]]
             else:
-                self._lower_reusing(img, self.pred[b0:b1])
+                self._lower_reusing(img, self.pred[b0:b1], b0)
             b.join_lanes()                       # slices share buffers: the next one starts after every branch is done
-        self.post = None
-        if post is not None:
-            max_det = post.get("max_det") or self.anchors
-            dev = device
-            self.dets = torch.zeros((batch, max_det, 7), dtype=torch.float32, device=dev)
-            self.det_idx = torch.zeros((batch, max_det), dtype=torch.int64, device=dev)
-            self.det_count = torch.zeros((batch,), dtype=torch.int32, device=dev)
-            ws = torch.empty((lib().yx_postprocess_workspace_bytes(batch, self.anchors),), dtype=torch.uint8, device=dev)
-            b.postprocess(self.pred, self.nc, post["conf_thre"], post["nms_thre"], post["nms_variant"], True,
-                          self.dets, self.det_idx, self.det_count, max_det, ws)
-            self.post = dict(post, max_det=max_det)
+        if self.post is not None:
+            if self._post_fused is not None:
+                b.nms_prefiltered(batch, self.anchors, post["nms_thre"], post["nms_variant"], self.dets, self.det_idx,
+                                  self.det_count, self.post["max_det"], self._post_ws)
+            else:
+                b.postprocess(self.pred, self.nc, post["conf_thre"], post["nms_thre"], post["nms_variant"], True,
+                              self.dets, self.det_idx, self.det_count, self.post["max_det"], self._post_ws)
         self.flops_per_image = b.flops / batch
 
     # buffer reuse across micro-batches: new_feat hands back the tensors of the first lowering
-    def _lower(self, img, pred_slice):
+    def _lower(self, img, pred_slice, b0=0):
         m = self.module
         feats = m.backbone.lower_image(self.builder, img)
-        m.head.lower(self.builder, list(feats), pred_slice)
+        post = None
+        if self._post_fused is not None:
+            f = self._post_fused
+            A = self.anchors
+            # the in-place corner conversion of postprocess (boxes.py:32-37) happens in the same epilogue
+            post = dict(cand_ptr=f["cand"] + b0 * A * 32, keys_ptr=f["keys"] + b0 * A * 8, counts_ptr=f["counts"] + b0 * 4,
+                        conf_thre=f["conf_thre"], xyxy=True)
+        m.head.lower(self.builder, list(feats), pred_slice, post=post)
 
-    def _lower_reusing(self, img, pred_slice):
+    def _lower_reusing(self, img, pred_slice, b0=0):
         b = self.builder
         pool = list(self._record)
         orig_new_feat = b.new_feat
@@ -554,7 +592,7 @@ class InferenceEngine:
 
         b.new_feat = reuse_feat
         try:
-            self._lower(img, pred_slice)
+            self._lower(img, pred_slice, b0)
         finally:
             b.new_feat = orig_new_feat
 

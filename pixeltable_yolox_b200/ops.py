@@ -103,6 +103,11 @@ def make_conv_desc(
         d.head_nc = head["nc"]
         d.head_decode = head["decode"]
         d.head_stride = float(head["stride"])
+        if head.get("cand_ptr"):
+            # fused score filter (stage 1 of postprocess) in the decode epilogue
+            d.head_cand, d.head_keys, d.head_counts = head["cand_ptr"], head["keys_ptr"], head["counts_ptr"]
+            d.head_conf_thre = float(head["conf_thre"])
+        d.head_xyxy = 1 if head.get("xyxy") else 0
     return d
 
 
@@ -221,6 +226,32 @@ def postprocess_device(pred: torch.Tensor, num_classes: int, conf_thre: float, n
     check(lib().yx_postprocess(pred.data_ptr(), B, A, num_classes, float(conf_thre), float(nms_thre), int(nms_variant),
                                1 if inplace_xyxy else 0, dets.data_ptr(), det_idx.data_ptr(), det_count.data_ptr(),
                                max_det, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "postprocess")
+    return dets, det_idx, det_count
+
+
+def postprocess_ws_ptrs(ws: torch.Tensor, batch: int, anchors: int):
+    """(cand, keys, counts) device addresses inside a postprocess workspace (yx_postprocess_workspace_ptrs)."""
+    cand, keys, counts = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    check(lib().yx_postprocess_workspace_ptrs(ws.data_ptr(), batch, anchors, C.byref(cand), C.byref(keys), C.byref(counts)),
+          "postprocess_workspace_ptrs")
+    return cand.value, keys.value, counts.value
+
+
+def postprocess_begin(ws: torch.Tensor, batch: int, anchors: int) -> None:
+    """Zero the per-image candidate counters of a postprocess workspace (before head GEMMs with a fused filter)."""
+    check(lib().yx_postprocess_begin(ws.data_ptr(), batch, anchors, stream_ptr(ws.device)), "postprocess_begin")
+
+
+def nms_prefiltered(ws: torch.Tensor, batch: int, anchors: int, nms_thre: float, nms_variant: int,
+                    max_det: Optional[int] = None):
+    """Stage 2 of postprocess over candidates written by the head epilogues; same outputs as postprocess_device."""
+    dev = ws.device
+    max_det = anchors if max_det is None else max_det
+    dets = torch.empty((batch, max_det, 7), dtype=torch.float32, device=dev)
+    det_idx = torch.empty((batch, max_det), dtype=torch.int64, device=dev)
+    det_count = torch.empty((batch,), dtype=torch.int32, device=dev)
+    check(lib().yx_nms_prefiltered(batch, anchors, float(nms_thre), int(nms_variant), dets.data_ptr(), det_idx.data_ptr(),
+                                   det_count.data_ptr(), max_det, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "nms_prefiltered")
     return dets, det_idx, det_count
 
 

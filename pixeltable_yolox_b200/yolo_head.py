@@ -63,8 +63,9 @@ class YoloxHead(_B200Block):
     def decode_flags(self) -> int:
         return 3 if self.decode_in_inference else 2
 
-    def lower(self, b, feats, head_out, decode=None):
-        """feats: 3 Feats (strides 8/16/32); head_out: fp32 tensor [B, A, 5+nc]."""
+    def lower(self, b, feats, head_out, decode=None, post=None):
+        """feats: 3 Feats (strides 8/16/32); head_out: fp32 tensor [B, A, 5+nc]. `post` (cand_ptr, keys_ptr, counts_ptr,
+        conf_thre, xyxy): run the score filter of postprocess (boxes.py:38-50) inside the decode epilogue."""
         decode = self.decode_flags() if decode is None else decode
         hw = []
         off = 0
@@ -99,7 +100,7 @@ class YoloxHead(_B200Block):
             ]
             b.conv(t1, parts, act=None, ksize=1, stride=1, o_total=5 + self.num_classes,
                    head=dict(out=head_out, anchors=total, anchor_off=off, nc=self.num_classes, decode=decode,
-                             stride=self.strides[k]))
+                             stride=self.strides[k], **(post or {})))
             if side:
                 b.end_lane()
             hw.append((x.H, x.W))

@@ -33,12 +33,29 @@ def test_library_exports_every_declared_symbol():
     assert handle.yx_strerror(-4).decode().startswith("no sm_100 device")
 
 
-def test_conv_desc_layout_matches_header():
-    """sizeof(yx_conv_desc) computed from the header's field list must equal the ctypes mirror."""
-    from pixeltable_yolox_b200._lib import ConvDesc
+def test_conv_desc_layout_matches_header(tmp_path):
+    """sizeof / field offsets of yx_conv_desc and yx_bneck_desc as gcc sees the header must equal the ctypes mirrors."""
+    import subprocess
 
-    # 12 int32, then pointer/int64 pairs ... : recompute with natural alignment
-    assert ctypes.sizeof(ConvDesc) == 12 * 4 + 8 * 2 + 8 + 8 + 8 * 2 + 8 * 2 + 8 * 2 + 8 + 4 * 4 + 4 + 4 + 8 * 2
+    from pixeltable_yolox_b200._lib import BneckDesc, ConvDesc
+
+    probes = [("yx_conv_desc", ConvDesc, ["in", "w", "bias", "out", "res", "ups", "head_out", "head_stride", "out2_begin",
+                                          "out2", "head_cand", "head_counts", "head_conf_thre", "head_xyxy"]),
+              ("yx_bneck_desc", BneckDesc, ["x", "w1", "bias2", "out", "out_ld"])]
+    lines = []
+    for cname, _, fields in probes:
+        lines.append(f'printf("%zu\\n", sizeof({cname}));')
+        lines += [f'printf("%zu\\n", offsetof({cname}, {f}));' for f in fields]
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "yx_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = []
+    for _, cls, fields in probes:
+        want.append(ctypes.sizeof(cls))
+        want += [getattr(cls, "in_" if f == "in" else f).offset for f in fields]
+    assert got == want
 
 
 def test_no_gpu_is_a_loud_error_not_a_fallback():

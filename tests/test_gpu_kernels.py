@@ -274,3 +274,46 @@ def test_bboxes_iou_bit_exact(cuda, golden_simota):
     a, b = torch.from_numpy(golden_simota["iou/a"]).to(cuda), torch.from_numpy(golden_simota["iou/b"]).to(cuda)
     assert np.array_equal(yx.bboxes_iou(a, b, True).cpu().numpy(), golden_simota["iou/xyxy"])
     assert np.array_equal(yx.bboxes_iou(a, b, False).cpu().numpy(), golden_simota["iou/cxcywh"])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("thr", [0.5, 0.05])
+def test_head_epilogue_fused_score_filter_is_bit_exact(cuda, dtype, thr):
+    """Prediction GEMM with the score filter fused into the decode epilogue (yx_conv_desc.head_cand) followed by
+    yx_nms_prefiltered == the same GEMM followed by the stand-alone yx_postprocess (filter kernel + NMS), bit for bit:
+    detections, kept anchor indices, counts and the in-place corner conversion (boxes.py:31-75). Three levels with
+    different strides write one [B, A, 5+nc] tensor; 20x20 and 10x10 make warps straddle image boundaries."""
+    g = torch.Generator().manual_seed(11)
+    B, nc, c = 3, 80, 64
+    levels = [(40, 8.0), (20, 16.0), (10, 32.0)]
+    A = sum(hw * hw for hw, _ in levels)
+    xs = [(torch.randn(B, hw, hw, c, generator=g) * 0.5).to(cuda).to(dtype) for hw, _ in levels]
+    ws_ = [(torch.randn(96, 1, c, generator=g) / c ** 0.5).to(cuda).to(dtype) for _ in levels]
+    bs = [torch.cat([torch.randn(4, generator=g) * 0.3, torch.randn(92, generator=g) - 1.0]).to(cuda) for _ in levels]
+
+    def run(post):
+        out = torch.zeros(B, A, 5 + nc, device=cuda)
+        off = 0
+        for (hw, stride), x, w, bias in zip(levels, xs, ws_, bs):
+            head = {"out_ptr": out.data_ptr(), "anchors": A, "anchor_off": off, "nc": nc, "decode": 3, "stride": stride}
+            head.update(post)
+            ops.conv_bn_act(View(x), w, bias, None, 1, 1, 0, head=head)
+            off += hw * hw
+        return out
+
+    ref_pred = run({})
+    plain = ref_pred.clone()
+    d0, i0, n0 = ops.postprocess_device(ref_pred, nc, thr, 0.65, 0, inplace_xyxy=True)
+
+    ws = torch.empty(_lib.lib().yx_postprocess_workspace_bytes(B, A), dtype=torch.uint8, device=cuda)
+    cand, keys, counts = ops.postprocess_ws_ptrs(ws, B, A)
+    ops.postprocess_begin(ws, B, A)
+    fused_pred = run({"cand_ptr": cand, "keys_ptr": keys, "counts_ptr": counts, "conf_thre": thr, "xyxy": True})
+    d1, i1, n1 = ops.nms_prefiltered(ws, B, A, 0.65, 0)
+    torch.cuda.synchronize()
+    assert int(n0.sum()) > 0 and torch.equal(n0, n1)
+    assert torch.equal(fused_pred, ref_pred)                       # corners in place, obj / cls untouched
+    assert torch.equal(fused_pred[..., 4:], plain[..., 4:])
+    for b in range(B):
+        k = int(n0[b])
+        assert torch.equal(d0[b, :k], d1[b, :k]) and torch.equal(i0[b, :k], i1[b, :k])
