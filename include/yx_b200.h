@@ -165,9 +165,10 @@ int yx_focus_s2d(const void* img, int32_t img_dtype, void* out, int64_t out_ld, 
 
 /* Fused Focus + stem conv + folded BN + act on the tensor cores (network_blocks.py:186-208 + 27-52):
  * reads the raw NCHW image (fp32 or uint8) once and writes the NHWC 16-bit stem output once.
- * The Focus + 3x3 conv is evaluated as the equivalent 6x6 stride-2 pad-2 conv on the image:
- *   w    : [out_c][128] in `dtype`, k = dy*18 + c*6 + dx (dy, dx in 0..5 window rows/cols, c image
- *          channel), columns 108..127 zero; W6[o,c,2u+py,2v+px] = Wfocus[o, 3*(2*px+py)+c, u, v] * bn_scale
+ * The 3x3 conv runs on the space-to-depth grid, one K = 16 GEMM step per filter tap:
+ *   w    : [out_c][9][16] in `dtype`: tap = 3*r + s, k = 2*(2*c + py) + px for image channel c and pixel parity
+ *          (py, px) = Wfocus[o, 3*(2*px+py)+c, r, s] * bn_scale (Focus order TL, BL, TR, BR), k = 12..15 zero.
+ *          For dtype fp16 the kernel feeds pixels as x/256: pack 256 * W.
  *   bias : [out_c] fp32; out: [B, h/2, w/2, out_ld] NHWC.  out_c % 16 == 0, out_c <= 128. */
 int yx_focus_conv_bn_act_fwd(const void* img, int32_t img_dtype, const void* w, const float* bias,
                              void* out, int64_t out_ld, int32_t batch, int32_t h, int32_t wd,

@@ -12,7 +12,7 @@ from pathlib import Path
 from typing import Optional
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libyx_b200.so"
+LIB_PATH = Path(os.environ.get("YX_B200_LIB") or PKG / "libyx_b200.so")   # YX_B200_LIB: A/B experiments with a second build
 
 YX_BF16, YX_FP16, YX_FP32, YX_U8 = 0, 1, 2, 3
 YX_ACT_NONE, YX_ACT_SILU, YX_ACT_RELU, YX_ACT_LRELU = 0, 1, 2, 3

@@ -1,23 +1,24 @@
 // Fused Focus + stem conv for sm_100a: space-to-depth, 3x3 conv, folded BN and SiLU in ONE kernel.
 //   reference: Focus.forward (yolox/models/network_blocks.py:186-208) followed by its BaseConv
-//   (network_blocks.py:27-52).  Focus(TL,BL,TR,BR) + 3x3 stride-1 pad-1 conv over 12 channels is the
-//   same linear map as a 6x6 stride-2 pad-2 conv over the 3 image channels:
-//       W6[o, c, 2u+py, 2v+px] = W[o, 3*(2*px+py) + c, u, v].
+//   (network_blocks.py:27-52).
 // The raw NCHW image (fp32 or uint8, 0..255) is read once and the NHWC 16-bit stem output written
-// once; nothing else touches HBM (the unfused path writes and re-reads a 12-channel tensor and pays
-// nine 32-byte-row TMA gathers per pixel).
+// once; nothing else touches HBM.
 //
-// GEMM view: M = output pixels (tile = 8 rows x 16 cols), K = 6*3*6 = 108 (zero padded to 128),
-// N = out_c.  TMA cannot build this operand directly (fp32/u8 source, channel-planar layout), so:
-//   warp 9      TMA-loads each tile's 3 x 20 x 36 input patch (one 4-D box of the NCHW image, zero
-//               filled outside the image = Conv2d padding) into a 4-deep ring, keeping ~35 KB of
-//               loads in flight per SM;
-//   warps 0-7   two groups of "builders" (alternating tiles): convert the patch to bf16/fp16 and write the [128 x 128] K-major,
-//               128B-swizzled A operand with 16-byte shared stores (fence.proxy.async publishes them
-//               to the tensor core);
-//   warp 8      issues tcgen05.mma against the weights (out_c x 128) resident in shared memory,
-//               accumulators in TMEM (4 stages);
+// GEMM view: the 3x3 conv runs on the space-to-depth grid (H/2 x W/2, 12 channels padded to K = 16 per tap).
+// Per tile of 7 x 16 output pixels:
+//   warp 9      TMA-loads the tile's 3 x 18 x 36 raw patch (one 4-D box of the NCHW image, zero filled outside
+//               the image = Conv2d padding) into a 4-deep ring;
+//   warps 0-7   two groups of "builders" (alternating tiles) turn it into the space-to-depth HALO tile: 9 x 18
+//               pixels x 16 channels (32-byte rows, canonical K-major SWIZZLE_32B layout). Every raw pixel is
+//               converted exactly once (the first version built the im2col operand, 9x the conversions and 32 KB
+//               of shared-memory stores per tile; ncu/roofline: shared-memory bandwidth bound at ~2x the HBM time);
+//   warp 8      issues nine tcgen05.mma per tile, one per filter tap: the A descriptor of tap (r, s) is the SAME
+//               halo tile with its start address shifted by r*18 + s rows (accumulator row m = y*18 + x; columns
+//               x >= 16 are garbage and dropped by the epilogue), B = the tap's [out_c x 16] weight tile resident
+//               in shared memory; accumulators in TMEM (4 stages);
 //   warps 10-17 two epilogue groups (bias + SiLU + 256-bit stores).
+// K order inside a tap: k = 2*(2*c + py) + px for image channel c and pixel parity (py, px), i.e. Focus channel
+// 3*(2*px + py) + c (network_blocks.py:199-207: TL, BL, TR, BR); k = 12..15 are zero.
 #include <stdlib.h>
 #include <string.h>
 
@@ -25,29 +26,39 @@
 
 namespace yx {
 
-static constexpr int kStemStages = 3;
+static constexpr int kStemStages = 4;                // halo-tile (A operand) stages
 static constexpr int kStemAcc = 4;
-static constexpr int kStemBuilders = 128;            // threads per builder group (one operand row each)
+static constexpr int kStemBuilders = 128;            // threads per builder group
 static constexpr int kStemBuilderGroups = 2;         // tiles alternate between the groups
-static constexpr int kStemEpiGroups = 2;
-static constexpr int kStemThreads = kStemBuilders * kStemBuilderGroups + 64 + 128 * kStemEpiGroups;   // + MMA warp + TMA warp
+static constexpr int kStemEpiGroups = 4;
+static constexpr int kStemThreads = kStemBuilders * kStemBuilderGroups + 64 + 128 * kStemEpiGroups + 32;   // + MMA warp + TMA warp + second MMA warp
 static constexpr int kWarpMma = kStemBuilders * kStemBuilderGroups / 32, kWarpTma = kWarpMma + 1, kWarpEpi = kWarpMma + 2;
-static constexpr int kPatchRows = 20;
+static constexpr int kWarpMma2 = kWarpEpi + 4 * kStemEpiGroups;     // tiles alternate between the two issuing warps
 static constexpr int kPatchStages = 4;
-static constexpr int kPatchStageBytes = 9600;      // 3*20*40 fp32 (u8: 3*20*64 = 3840), 128-byte multiple
-static constexpr int kTileH = 8, kTileW = 16;
+// The output tile (th x tw, accumulator row m = y * (tw + 2) + x, th * (tw + 2) <= 128) is chosen per image width
+// on the host: the raw patch arrives as 3 * (2*th + 4) TMA rows and the TMA unit's cost is per ROW (fp32 160-byte and
+// uint8 64-byte rows of the first 7 x 16 tile took the same 250 us), so wide, flat tiles (3 x 40 at 640^2: 30 rows of
+// 352 bytes per 120 pixels instead of 54 rows per 112) are what brings the kernel to the HBM roofline.
 
 struct StemParams {
   const void* img; int img_dtype;
   int batch, h, w;            // image size
   int out_h, out_w;           // h/2, w/2
   int tiles_w, tiles_h, num_tiles;
+  int tw, th, pitch, halo_pix;        // output tile, accumulator row pitch tw + 2, (th + 2) * pitch halo pixels
+  int patch_rows, patch_pitch, lead;  // raw patch: 2*th + 4 rows of patch_pitch elements; the patch starts `lead` elements in
+  unsigned patch_stage_bytes, a_stage_bytes;
+  unsigned mul_tpi, mul_tw;           // fast_div multipliers for tiles per image / tiles per row
   int BN, BNpad;              // out_c (multiple of 16) and its TMEM pitch
   unsigned idesc, desc_hi, tmem_cols;
-  unsigned bias_bytes, b_bytes, patch_tx;
+  unsigned bias_bytes, b_bytes, w_tile_bytes, patch_tx;
   int debug;
   EpiParams epi;
 };
+
+// YX_STEM_DEBUG=2: CTA 0 records clock64() at the hand-off points of tiles 16..47 (builder warp 0, MMA warp, epilogue warp 0)
+__device__ long long g_stem_trace[3][32][5];
+#define ST_TRACE(role, it, k) do { if ((p.debug & 2) && blockIdx.x == 0 && (it) >= 16 && (it) < 48 && lane == 0) g_stem_trace[role][(it) - 16][k] = clock64(); } while (0)
 
 struct __align__(8) StemShared {
   uint64_t full[kStemStages];
@@ -91,9 +102,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   StemShared* sh = reinterpret_cast<StemShared*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 1024);
   uint8_t* patch = smem + 1024 + p.bias_bytes;                                         // [kPatchStages] raw patches
-  uint8_t* wsm = patch + kPatchStages * kPatchStageBytes;                              // [2][BN x 64] weights
+  uint8_t* wsm = patch + kPatchStages * p.patch_stage_bytes;                           // [9][BN x 16] weights
   wsm += (1024u - (smem_u32(wsm) & 1023u)) & 1023u;
-  uint8_t* astage = wsm + p.b_bytes;                                                   // [stages][2][128 x 64]
+  uint8_t* astage = wsm + ((p.b_bytes + 1023u) & ~1023u);                              // [stages] s2d halo tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,10 +116,13 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_w);
-    for (int i = 0; i < kStemStages; ++i) { mbar_init(&sh->full[i], kStemBuilders); mbar_init(&sh->empty[i], 1); }
-    for (int i = 0; i < kStemAcc; ++i) { mbar_init(&sh->tmem_full[i], 1); mbar_init(&sh->tmem_empty[i], 128); }
+    // consumer-side barriers count WARPS: one elected lane arrives after __syncwarp(). A per-thread arrive is 32 serialized
+    // shared-memory operations per warp; at 3 x 4 warps per tile they were ~380 of the ~1000 shared-memory wavefronts
+    // of a tile, on the data pipe the tensor core reads its operands through (ncu: LSU + TC wavefronts at 81 %)
+    for (int i = 0; i < kStemStages; ++i) { mbar_init(&sh->full[i], kStemBuilders / 32); mbar_init(&sh->empty[i], 1); }
+    for (int i = 0; i < kStemAcc; ++i) { mbar_init(&sh->tmem_full[i], 1); mbar_init(&sh->tmem_empty[i], 4); }
     mbar_init(&sh->w_full, 1);
-    for (int i = 0; i < kPatchStages; ++i) { mbar_init(&sh->patch_full[i], 1); mbar_init(&sh->patch_empty[i], kStemBuilders); }
+    for (int i = 0; i < kPatchStages; ++i) { mbar_init(&sh->patch_full[i], 1); mbar_init(&sh->patch_empty[i], kStemBuilders / 32); }
     tma_prefetch_desc(&map_img);
     fence_barrier_init();
   }
@@ -126,98 +140,112 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp < kWarpMma) {
-    // ===================== A builders =====================
-    const int m = threadIdx.x & (kStemBuilders - 1);   // operand row = output pixel (hl, wl) of the tile
-    const int hl = m >> 4, wl = m & 15;
+    // ===================== halo-tile builders =====================
+    const int m = threadIdx.x & (kStemBuilders - 1);
     const int bgrp = threadIdx.x / kStemBuilders;
+    const int kPitch = p.patch_pitch;                       // raw patch row pitch (elements)
+    const int plane = p.patch_rows * kPitch;                // one image channel of the patch
+    // halo pixel q = Y*pitch + X of the space-to-depth grid <- raw[c][2Y + py][2X + px]; one 32-byte operand row.
+    // Everything that depends on q only is computed once (the division by the runtime pitch costs ~20 instructions).
+    int src_off[2];
+    uint32_t row0[2], row1[2];
+    bool live[2];
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int q = m + rep * kStemBuilders;
+      live[rep] = q < p.halo_pix;
+      const int Y = q / p.pitch, X = q - Y * p.pitch;
+      src_off[rep] = (2 * Y) * kPitch + p.lead + 2 * X;
+      // SWIZZLE_32B: the 16-byte chunk index of a row is XOR-ed with address bit 7 (= bit 2 of the row index)
+      const uint32_t sw = ((uint32_t)q >> 2) & 1u;
+      row0[rep] = (uint32_t)q * 32u + ((0u ^ sw) << 4);
+      row1[rep] = (uint32_t)q * 32u + ((1u ^ sw) << 4);
+    }
     for (int it = bgrp;; it += kStemBuilderGroups) {
       const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
       if (tl >= p.num_tiles) break;
       const int stage = it % kStemStages, ps = it % kPatchStages;
       const uint32_t phase = (uint32_t)((it / kStemStages) & 1), pphase = (uint32_t)((it / kPatchStages) & 1);
-      // ---- 1. the tile's raw patch [3][20][pitch] (fp32: pitch 36, u8: pitch 48) arrives by TMA
+      if (warp == 0) ST_TRACE(0, it, 0);
       mbar_wait(&sh->patch_full[ps], pphase);
-      const TI* pt = reinterpret_cast<const TI*>(patch + (size_t)ps * kPatchStageBytes);
-      // the box starts 16-byte aligned in global memory, kLead pixels left of the patch (TMA faults on
-      // a row start that is not a multiple of 16 bytes)
-      constexpr int kPitch = sizeof(TI) == 4 ? 40 : 64;
-      constexpr int kLead = sizeof(TI) == 4 ? 2 : 14;
-      // ---- 2. build operand row m: k = dy*18 + c*6 + dx  <->  patch[c][2*hl+dy][2*wl+dx]
+      if (warp == 0) ST_TRACE(0, it, 1);
+      const TI* pt = reinterpret_cast<const TI*>(patch + (size_t)ps * p.patch_stage_bytes);
       mbar_wait(&sh->empty[stage], phase ^ 1);
-      uint8_t* a0 = astage + (size_t)stage * 32768 + (size_t)m * 128;
-      uint32_t wds[4];
-      int nw = 0, chunk = 0;
-      // two batches of 27 independent shared loads (3 dy x 3 c x 3 pairs) so that the load latency is paid
-      // twice per row instead of once per pair
+      if (warp == 0) ST_TRACE(0, it, 2);
+      uint8_t* a0 = astage + (size_t)stage * p.a_stage_bytes;
+      float fa[2][6], fb[2][6];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float fa[27], fb[27];
+      for (int rep = 0; rep < 2; ++rep) {
+        if (live[rep]) {
+          const TI* src = pt + src_off[rep];
 #pragma unroll
-        for (int i = 0; i < 27; ++i) {
-          const int dy = half * 3 + i / 9, c = (i % 9) / 3, q = i % 3;
-          const TI* src = pt + (c * kPatchRows + 2 * hl + dy) * kPitch + kLead + 2 * wl;
-          load_pair<TI>(src + 2 * q, fa[i], fb[i]);
+          for (int i = 0; i < 6; ++i) load_pair<TI>(src + (i >> 1) * plane + (i & 1) * kPitch, fa[rep][i], fb[rep][i]);
         }
+      }
 #pragma unroll
-        for (int i = 0; i < 27; ++i) {
-          // fp16: pixels are fed as x/256 (exact) and the host packs 256*W: BN-folded stem weights (~W/300 for raw
-          // 0..255 inputs) would otherwise fall into fp16's subnormal range and lose most of their mantissa
-          if (FP16) { fa[i] *= 0.00390625f; fb[i] *= 0.00390625f; }
-          wds[nw++] = pack16_t<FP16>(fa[i], fb[i]);
-          if (nw == 4) {
-            uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-            nw = 0; ++chunk;
+      for (int rep = 0; rep < 2; ++rep) {
+        if (live[rep]) {
+          uint32_t wd[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            // fp16: pixels are fed as x/256 (exact) and the host packs 256*W: BN-folded stem weights (~W/300 for raw
+            // 0..255 inputs) would otherwise fall into fp16's subnormal range and lose most of their mantissa
+            if (FP16) { fa[rep][i] *= 0.00390625f; fb[rep][i] *= 0.00390625f; }
+            wd[i] = pack16_t<FP16>(fa[rep][i], fb[rep][i]);
           }
+          *reinterpret_cast<uint4*>(a0 + row0[rep]) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          *reinterpret_cast<uint4*>(a0 + row1[rep]) = make_uint4(wd[4], wd[5], 0u, 0u);
         }
       }
-      // 54 words written so far = 13 full chunks + 2 words; pad k = 108..127 with zeros
-      {
-        uint8_t* dst = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], 0u, 0u);
-        ++chunk;
-#pragma unroll
-        for (; chunk < 16; ++chunk) {
-          uint8_t* d2 = a0 + (size_t)(chunk >> 3) * 16384 + (((chunk & 7) ^ (m & 7)) << 4);
-          *reinterpret_cast<uint4*>(d2) = make_uint4(0u, 0u, 0u, 0u);
-        }
+      if (warp == 0) ST_TRACE(0, it, 3);
+      fence_proxy_async();                    // this thread's generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sh->patch_empty[ps]);    // the warp is done with the raw patch
+        mbar_arrive(&sh->full[stage]);
       }
-      mbar_arrive(&sh->patch_empty[ps]);      // this thread is done with the raw patch
-      fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(&sh->full[stage]);
+      if (warp == 0) ST_TRACE(0, it, 4);
     }
-  } else if (warp == kWarpMma) {
-    // ===================== MMA issuer =====================
+  } else if (warp == kWarpMma || warp == kWarpMma2) {
+    // ===================== MMA issuers =====================
+    // A [128 x 16] x [16 x 32] MMA is bound by the tensor core's shared-memory read of A (128 rows x 32 B at ~64 B/clk =
+    // 64 clk, the math needs 16) and the issuing thread stays in tcgen05.mma for about that long, so its barrier waits
+    // (~150 clk each even when the phase is already complete) were dead time of the tensor pipe: a clock64 trace
+    // (YX_STEM_DEBUG=2) showed 780 clk of issue + 420 clk of waits per tile. Two warps issue alternate tiles.
+    const int g = warp == kWarpMma ? 0 : 1;
     if (lane == 0) {
-      // resident weights: two [BN x 64] K-major chunks
-      mbar_arrive_expect_tx(&sh->w_full, p.b_bytes);
-      tma_load_2d(&map_w, &sh->w_full, wsm, 0, 0);
-      tma_load_2d(&map_w, &sh->w_full, wsm + p.b_bytes / 2, 64, 0);
+      if (g == 0) {
+        // resident weights: nine [BN x 16] K-major tiles
+        mbar_arrive_expect_tx(&sh->w_full, p.b_bytes);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(&map_w, &sh->w_full, wsm + (size_t)tap * p.w_tile_bytes, tap * 16, 0);
+      }
       mbar_wait(&sh->w_full, 0);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      const uint64_t hi = (uint64_t)p.desc_hi << 32;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const uint64_t hi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
+      const uint32_t w16 = smem_u32(wsm) >> 4, wt16 = p.w_tile_bytes >> 4;
+      const uint32_t pitch2 = (uint32_t)p.pitch * 2u;
+      for (int mit = g;; mit += 2) {
+        const long long tl = (long long)blockIdx.x + (long long)mit * gridDim.x;
+        if (tl >= p.num_tiles) break;
+        const int stage = mit % kStemStages, as = mit % kStemAcc;
+        const uint32_t phase = (uint32_t)((mit / kStemStages) & 1), aphase = (uint32_t)((mit / kStemAcc) & 1);
+        ST_TRACE(1, mit, 0);
         mbar_wait(&sh->tmem_empty[as], aphase ^ 1);
+        ST_TRACE(1, mit, 1);
         mbar_wait(&sh->full[stage], phase);
+        ST_TRACE(1, mit, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BNpad);
+        const uint32_t a16 = smem_u32(astage + (size_t)stage * p.a_stage_bytes) >> 4;
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-          const uint32_t sa = smem_u32(astage + (size_t)stage * 32768 + (size_t)kc * 16384);
-          const uint32_t sb = smem_u32(wsm + (size_t)kc * (p.b_bytes / 2));
-          uint64_t adesc = hi | (uint64_t)(((sa >> 4) & 0x3FFF) | (1u << 16));
-          uint64_t bdesc = hi | (uint64_t)(((sb >> 4) & 0x3FFF) | (1u << 16));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            umma_f16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kc | j) != 0));
-            adesc += 2; bdesc += 2;
-          }
+        for (int tap = 0; tap < 9; ++tap) {
+          // tap (r, s): halo rows shifted by r*pitch + s (32-byte rows = 2 units of 16 bytes)
+          const uint64_t adesc = hi | (uint64_t)(a16 + (uint32_t)(tap / 3) * pitch2 + (uint32_t)((tap % 3) * 2));
+          const uint64_t bdesc = hi | (uint64_t)(w16 + (uint32_t)tap * wt16);
+          umma_f16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)(tap != 0));
         }
         umma_commit(&sh->empty[stage]);
         umma_commit(&sh->tmem_full[as]);
-        if (++stage == kStemStages) { stage = 0; phase ^= 1; }
-        if (++as == kStemAcc) { as = 0; aphase ^= 1; }
+        ST_TRACE(1, mit, 3);
       }
     }
   } else if (warp == kWarpTma) {
@@ -235,8 +263,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           mbar_arrive(&sh->patch_full[ps]);
         } else {
           mbar_arrive_expect_tx(&sh->patch_full[ps], p.patch_tx);
-          tma_load_4d(&map_img, &sh->patch_full[ps], patch + (size_t)ps * kPatchStageBytes,
-                      2 * tx * kTileW - (sizeof(TI) == 4 ? 4 : 16), 2 * ty * kTileH - 2, 0, b);
+          tma_load_4d(&map_img, &sh->patch_full[ps], patch + (size_t)ps * p.patch_stage_bytes,
+                      2 * tx * p.tw - 2 - p.lead, 2 * ty * p.th - 2, 0, b);
         }
         if (++ps == kPatchStages) { ps = 0; pphase ^= 1; }
       }
@@ -247,19 +275,22 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int grp = (warp - kWarpEpi) >> 2;
-    const int hl = row >> 4, wl = row & 15;
+    const int hl = row / p.pitch, wl = row - hl * p.pitch;
+    const bool row_ok = hl < p.th && wl < p.tw;
     for (int it = grp;; it += kStemEpiGroups) {
       const long long tl = (long long)blockIdx.x + (long long)it * gridDim.x;
       if (tl >= p.num_tiles) break;
       const int t = (int)tl;
       const int as = it % kStemAcc;
       const uint32_t aphase = (uint32_t)((it / kStemAcc) & 1);
-      const int b = t / tiles_per_img;
+      const int b = fast_div(t, p.mul_tpi, tiles_per_img);
       const int r = t - b * tiles_per_img;
-      const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
-      const int ho = ty * kTileH + hl, wo = tx * kTileW + wl;
-      const bool valid = ho < p.out_h && wo < p.out_w;
+      const int ty = fast_div(r, p.mul_tw, p.tiles_w), tx = r - ty * p.tiles_w;
+      const int ho = ty * p.th + hl, wo = tx * p.tw + wl;
+      const bool valid = row_ok && ho < p.out_h && wo < p.out_w;
+      if (warp == kWarpEpi) ST_TRACE(2, it, 0);
       mbar_wait(&sh->tmem_full[as], aphase);
+      if (warp == kWarpEpi) ST_TRACE(2, it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
       const long long pix = ((long long)b * p.out_h + ho) * p.out_w + wo;
@@ -270,13 +301,17 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tmem_ld_x16(taddr + (uint32_t)c, ra);
         if (two) tmem_ld_x16(taddr + (uint32_t)(c + 16), rb);
         tmem_ld_wait();
+        if (warp == kWarpEpi && c == 0) ST_TRACE(2, it, 2);
         if (valid) {
           epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
           if (two) epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
+      if (warp == kWarpEpi) ST_TRACE(2, it, 3);
       tc_fence_before();
-      mbar_arrive(&sh->tmem_empty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty[as]);
+      if (warp == kWarpEpi) ST_TRACE(2, it, 4);
     }
   }
 
@@ -327,43 +362,76 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
   memset(&p, 0, sizeof(p));
   p.img = img; p.img_dtype = img_dtype; p.batch = batch; p.h = h; p.w = wd;
   p.out_h = h / 2; p.out_w = wd / 2;
-  p.tiles_w = (p.out_w + kTileW - 1) / kTileW; p.tiles_h = (p.out_h + kTileH - 1) / kTileH;
+  {
+    // tile choice: fewest TMA rows per image (3 * (2*th + 4) per tile), th >= 3 bounds the vertical re-read of the patch
+    // rows; the box must start 16-byte aligned for every tile: 2*tw*es % 16 == 0
+    const int es0 = img_dtype == YX_FP32 ? 4 : 1;
+    long long best = -1;
+    for (int tw = 8; tw <= 40; ++tw) {
+      if ((2 * tw * es0) % 16) continue;
+      const int th = 128 / (tw + 2);
+      if (th < 3 && tw > 8) continue;
+      const long long tiles = (long long)((p.out_w + tw - 1) / tw) * ((p.out_h + th - 1) / th);
+      const long long cost = tiles * 3 * (2 * th + 4);
+      if (best < 0 || cost < best) { best = cost; p.tw = tw; p.th = th; }
+    }
+    if (const char* e = getenv("YX_STEM_TILE")) {          // experiments: "tw"
+      const int tw = atoi(e);
+      if (tw >= 8 && tw <= 126 && (2 * tw * es0) % 16 == 0) { p.tw = tw; p.th = 128 / (tw + 2); }
+    }
+  }
+  p.pitch = p.tw + 2; p.halo_pix = (p.th + 2) * p.pitch;
+  YX_REQUIRE(p.halo_pix <= 2 * kStemBuilders, YX_ERR_UNSUPPORTED, "stem: halo of %d pixels exceeds the builder groups", p.halo_pix);
+  p.patch_rows = 2 * p.th + 4;
+  p.tiles_w = (p.out_w + p.tw - 1) / p.tw; p.tiles_h = (p.out_h + p.th - 1) / p.th;
   p.num_tiles = batch * p.tiles_w * p.tiles_h;
+  p.mul_tpi = fast_div_mul(p.tiles_w * p.tiles_h); p.mul_tw = fast_div_mul(p.tiles_w);
   p.BN = out_c;
   p.BNpad = 32; while (p.BNpad < p.BN) p.BNpad <<= 1;
   p.tmem_cols = (unsigned)(kStemAcc * p.BNpad);
   const unsigned fmt = dtype == YX_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-  p.desc_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO = 8 rows * 128 B, version 1, SWIZZLE_128B
+  p.desc_hi = ((256u >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);    // SBO = 8 rows * 32 B, version 1, SWIZZLE_32B
   p.bias_bytes = ((unsigned)out_c * 4u + 1023u) & ~1023u;
-  p.b_bytes = 2u * (unsigned)out_c * 128u;                           // two [out_c x 64] chunks, multiples of 2 KB
+  p.w_tile_bytes = (unsigned)out_c * 32u;                            // one tap: [out_c x 16], a multiple of 512 B
+  p.b_bytes = 9u * p.w_tile_bytes;
   EpiParams& e = p.epi;
   e.out_h = p.out_h; e.out_w = p.out_w; e.out_c = out_c; e.act = act; e.dtype = dtype; e.epilogue = YX_EPI_STORE;
   e.bias = bias; e.out = out; e.out_ld = out_ld;
-  L->smem = 2048 + p.bias_bytes + (size_t)kPatchStages * kPatchStageBytes + 1024 + p.b_bytes + (size_t)kStemStages * 32768;
   {
-    // the NCHW image as a 4-D tensor [W, H, 3, B]; one box = the 40 (u8: 64) x 20 x 3 window holding a tile's patch
+    const int es0 = img_dtype == YX_FP32 ? 4 : 1;
+    p.lead = 16 / es0 - 2;                                          // (2 + lead) * es == 16: 16-byte aligned box start
+    const int per16 = 16 / es0;
+    p.patch_pitch = (p.lead + 2 * p.tw + 4 + per16 - 1) / per16 * per16;   // box width: a multiple of 16 bytes
+    YX_REQUIRE(p.patch_pitch <= 256, YX_ERR_UNSUPPORTED, "stem: TMA box of %d elements", p.patch_pitch);
+    p.patch_stage_bytes = ((unsigned)(3 * p.patch_rows * p.patch_pitch * es0) + 127u) & ~127u;
+    p.a_stage_bytes = ((unsigned)(128 + 2 * p.pitch + 2) * 32u + 1023u) & ~1023u;   // rows addressed by the nine shifted taps
+  }
+  L->smem = 2048 + p.bias_bytes + (size_t)kPatchStages * p.patch_stage_bytes + 1024 + ((p.b_bytes + 1023u) & ~1023u) +
+            (size_t)kStemStages * p.a_stage_bytes;
+  {
+    // the NCHW image as a 4-D tensor [W, H, 3, B]; one box = the 40 (u8: 64) x 18 x 3 window holding a tile's patch
     const int es = img_dtype == YX_FP32 ? 4 : 1;
-    const cuuint32_t bw = img_dtype == YX_FP32 ? 40 : 64;   // patch is 36 wide; the box starts 16-byte aligned
+    const cuuint32_t bw = (cuuint32_t)p.patch_pitch;        // the box starts 16-byte aligned, `lead` pixels left of the patch
     YX_REQUIRE(((long long)wd * es) % 16 == 0, YX_ERR_UNSUPPORTED, "stem: image row pitch must be a multiple of 16 bytes");
     cuuint64_t idims[4] = {(cuuint64_t)wd, (cuuint64_t)h, 3, (cuuint64_t)batch};
     cuuint64_t istr[3] = {(cuuint64_t)wd * es, (cuuint64_t)wd * h * es, (cuuint64_t)wd * h * 3 * es};
-    cuuint32_t ibox[4] = {bw, (cuuint32_t)kPatchRows, 3, 1};
+    cuuint32_t ibox[4] = {bw, (cuuint32_t)p.patch_rows, 3, 1};
     cuuint32_t iestr[4] = {1, 1, 1, 1};
     CUresult ri = encode(&L->map_img, img_dtype == YX_FP32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
                          const_cast<void*>(img), idims, istr, ibox, iestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YX_REQUIRE(ri == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(stem image) failed: %d", (int)ri);
-    p.patch_tx = bw * kPatchRows * 3 * es;
+    p.patch_tx = bw * (cuuint32_t)p.patch_rows * 3 * es;
     if (const char* e = getenv("YX_STEM_DEBUG")) p.debug = atoi(e);
   }
   const CUtensorMapDataType tdt = dtype == YX_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  cuuint64_t dims[2] = {128, (cuuint64_t)out_c};
-  cuuint64_t strides[1] = {256};
-  cuuint32_t box[2] = {64, (cuuint32_t)out_c};
+  cuuint64_t dims[2] = {144, (cuuint64_t)out_c};
+  cuuint64_t strides[1] = {288};
+  cuuint32_t box[2] = {16, (cuuint32_t)out_c};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(&L->map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(stem W) failed: %d", (int)r);
   const int sms = num_sms();
   L->grid = p.num_tiles < sms ? p.num_tiles : sms;
@@ -401,6 +469,21 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
     if (h16) YX_STEM_GO(uint8_t, true); else YX_STEM_GO(uint8_t, false);
   }
 #undef YX_STEM_GO
+  if (L->p.debug & 2) {
+    static long long tr[3][32][5];
+    cudaStreamSynchronize(stream);
+    if (cudaMemcpyFromSymbol(tr, g_stem_trace, sizeof(tr)) == cudaSuccess) {
+      const char* names[3] = {"builder", "mma", "epilogue"};
+      const long long t0 = tr[1][0][0];
+      for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 32; ++i) {
+          if (tr[r][i][0] == 0) continue;
+          fprintf(stderr, "stem trace %-8s it=%2d:", names[r], i + 16);
+          for (int k = 0; k < 5; ++k) fprintf(stderr, " %7lld", tr[r][i][k] ? tr[r][i][k] - t0 : -1);
+          fprintf(stderr, "\n");
+        }
+    }
+  }
   return YX_OK;
 }
 

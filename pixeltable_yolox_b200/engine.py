@@ -365,19 +365,19 @@ class Builder:
         key = (conv.weight.data_ptr(), conv.weight._version, "focus", self.dtype)
         hit = self.weight_cache.get(key)
         if hit is None:
-            # W6[o, c, 2u+py, 2v+px] = W[o, 3*(2*px+py)+c, u, v]; k = dy*18 + c*6 + dx; BN folded
-            # (model_utils.py:33-75). One-time weight preparation in fp32 torch ops.
+            # per filter tap (r, s) of the 3x3 conv on the space-to-depth grid: k = 2*(2*c + py) + px holds Focus channel
+            # 3*(2*px + py) + c (network_blocks.py:199-207), k = 12..15 zero; BN folded (model_utils.py:33-75).
+            # One-time weight preparation in fp32 torch ops.
             wf = conv.weight.detach().float()
             scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
             shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
-            w6 = torch.zeros((o, 3, 6, 6), dtype=torch.float32, device=wf.device)
-            for px in range(2):
+            wf = wf * scale[:, None, None, None]
+            packed = torch.zeros((pad16(o), 9, 16), dtype=torch.float32, device=wf.device)
+            for c in range(3):
                 for py in range(2):
-                    pidx = 2 * px + py
-                    w6[:, :, py::2, px::2] = wf[:, 3 * pidx:3 * pidx + 3]
-            w6 = w6 * scale[:, None, None, None]
-            packed = torch.zeros((pad16(o), 128), dtype=torch.float32, device=wf.device)
-            packed[:o, :108] = w6.permute(0, 2, 1, 3).reshape(o, 108)          # [o][dy][c][dx]
+                    for px in range(2):
+                        packed[:o, :, 2 * (2 * c + py) + px] = wf[:, 3 * (2 * px + py) + c].reshape(o, 9)
+            packed = packed.reshape(pad16(o), 144)
             bias = torch.zeros((pad16(o),), dtype=torch.float32, device=self.dev)
             bias[:o] = shift.to(self.dev)
             if self.dtype == torch.float16:
