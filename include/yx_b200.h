@@ -271,6 +271,24 @@ int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Head losses, forward and gradient in one pass (YoloxHead.get_losses, yolox/models/yolo_head.py:354-418;
+ * IOUloss, yolox/models/losses.py:7-51; BCEWithLogits on objectness of every anchor and on the classes of
+ * the foreground anchors with target one_hot(matched class) * matched IoU; L1 on the raw regression outputs).
+ *   pred / labels / fg_mask / matched_* : as for yx_simota_assign (its outputs are this call's inputs)
+ *   origin   : [B, A, 4] fp32 raw regression outputs or NULL (use_l1 off); x_shift/y_shift/stride: [A]
+ *   giou     : 0 = loss_type "iou" (1 - iou^2), 1 = "giou"
+ *   sums     : [4] fp64 = sum of the iou / obj / cls / l1 terms, NOT divided by num_fg
+ *   grad     : [B, A, 5+nc] fp32 = d(reg_weight*iou_sum + obj_sum + cls_sum)/d pred
+ *   grad_origin : [B, A, 4] fp32 = d(l1_sum)/d origin (when origin != NULL)
+ * The caller divides by max(num_fg, 1) (yolo_head.py:382). No host synchronisation.
+ * ------------------------------------------------------------------------------------------ */
+int yx_head_losses(const float* pred, const float* labels, int32_t max_gt, const uint8_t* fg_mask,
+                   const int32_t* matched_gt, const float* matched_iou, const int32_t* matched_cls,
+                   const float* origin, const float* x_shift, const float* y_shift, const float* stride,
+                   int32_t batch, int32_t anchors, int32_t nc, int32_t giou, float reg_weight, double* sums,
+                   float* grad, float* grad_origin, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Plan: the native runtime.  A plan is an ordered list of the launches of one forward pass
  * (YoloxModule.forward eval branch, yolox/models/yolox.py:72-92) over pre-allocated buffers.
  * Tensor maps are encoded once at add time; yx_plan_run enqueues every launch on `stream`

@@ -89,6 +89,7 @@ SIGNATURES = {
     "yx_simota_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "yx_simota_assign": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "yx_simota_matching": (C.c_int, [_P, _P, _I32, _I32, _I64, _P, _P, _P, _P]),
+    "yx_head_losses": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P]),
     "yx_plan_create": (_P, []),
     "yx_plan_destroy": (None, [_P]),
     "yx_plan_add_conv": (C.c_int, [_P, C.POINTER(ConvDesc)]),

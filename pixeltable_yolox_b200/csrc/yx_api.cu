@@ -30,6 +30,10 @@ long long postprocess_ws_bytes(int batch, int anchors);
 int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_thre, double nms_thre, int nms_variant,
                        int inplace_xyxy, float* dets, long long* det_idx, int* det_count, int max_det, void* ws,
                        long long ws_bytes, cudaStream_t s);
+int head_loss_launch(const float* pred, const float* labels, int max_gt, const unsigned char* fg_mask, const int* matched_gt,
+                     const float* matched_iou, const int* matched_cls, const float* origin, const float* x_shift,
+                     const float* y_shift, const float* stride, int batch, int anchors, int nc, int giou, float reg_weight,
+                     double* sums, float* grad, float* grad_origin, cudaStream_t s);
 int postprocess_ws_ptrs(void* ws, int batch, int anchors, float** cand, unsigned long long** keys, int** counts);
 int postprocess_begin_launch(void* ws, int batch, int anchors, cudaStream_t s);
 int nms_prefiltered_launch(int batch, int anchors, double nms_thre, int nms_variant, float* dets, long long* det_idx,
@@ -362,6 +366,17 @@ int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int
   int rc = require_device();
   if (rc) return rc;
   return simota_matching_launch(cost, ious, num_gt, n, ld, match_gt, match_iou, num_fg, (cudaStream_t)stream);
+}
+
+int yx_head_losses(const float* pred, const float* labels, int32_t max_gt, const uint8_t* fg_mask,
+                   const int32_t* matched_gt, const float* matched_iou, const int32_t* matched_cls,
+                   const float* origin, const float* x_shift, const float* y_shift, const float* stride,
+                   int32_t batch, int32_t anchors, int32_t nc, int32_t giou, float reg_weight, double* sums,
+                   float* grad, float* grad_origin, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return head_loss_launch(pred, labels, max_gt, fg_mask, matched_gt, matched_iou, matched_cls, origin, x_shift, y_shift,
+                          stride, batch, anchors, nc, giou, reg_weight, sums, grad, grad_origin, (cudaStream_t)stream);
 }
 
 // ---- plan ----

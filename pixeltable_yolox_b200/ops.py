@@ -327,6 +327,35 @@ def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tens
     return out
 
 
+def head_losses(pred: torch.Tensor, labels: torch.Tensor, asg: dict, origin: Optional[torch.Tensor] = None,
+                x_shifts: Optional[torch.Tensor] = None, y_shifts: Optional[torch.Tensor] = None,
+                strides: Optional[torch.Tensor] = None, giou: bool = False, reg_weight: float = 5.0):
+    """Loss sums and gradients of YoloxHead.get_losses in one kernel (yx_head_losses).
+    pred [B,A,5+nc] fp32 (training-branch outputs), labels [B,G,5], asg = simota_assign(...) outputs.
+    Returns (sums [4] fp64: iou/obj/cls/l1, un-normalised; grad [B,A,5+nc]; grad_origin [B,A,4] or None)."""
+    require_cuda(pred, "head_losses")
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    B, A, nch = pred.shape
+    dev = pred.device
+    labels = labels.contiguous().float()
+    sums = torch.empty((4,), dtype=torch.float64, device=dev)
+    grad = torch.empty_like(pred)
+    g_or = None
+    o_ptr = xs_ptr = ys_ptr = st_ptr = go_ptr = None
+    if origin is not None:
+        origin = origin.contiguous().float()
+        xs = x_shifts.reshape(-1).contiguous().float(); ys = y_shifts.reshape(-1).contiguous().float()
+        st = strides.reshape(-1).contiguous().float()
+        assert origin.shape == (B, A, 4) and xs.numel() == A and ys.numel() == A and st.numel() == A
+        g_or = torch.empty_like(origin)
+        o_ptr, xs_ptr, ys_ptr, st_ptr, go_ptr = origin.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), g_or.data_ptr()
+    check(lib().yx_head_losses(pred.data_ptr(), labels.data_ptr(), labels.shape[1], asg["fg_mask"].data_ptr(),
+                               asg["matched_gt"].data_ptr(), asg["matched_iou"].data_ptr(), asg["matched_cls"].data_ptr(),
+                               o_ptr, xs_ptr, ys_ptr, st_ptr, B, A, nch - 5, 1 if giou else 0, float(reg_weight),
+                               sums.data_ptr(), grad.data_ptr(), go_ptr, stream_ptr(dev)), "head_losses")
+    return sums, grad, g_or
+
+
 def simota_matching_device(cost: torch.Tensor, ious: torch.Tensor):
     """simota_matching on a [G, n] cost / IoU pair. Returns (match_gt [n] int32, match_iou [n], num_fg [1])."""
     require_cuda(cost, "simota_matching")

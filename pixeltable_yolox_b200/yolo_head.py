@@ -22,6 +22,26 @@ from .losses import IouLoss
 from .network_blocks import BaseConv, DWConv, _B200Block, act_name
 
 
+class _FusedHeadLoss(torch.autograd.Function):
+    """total = reg_weight * iou_sum + obj_sum + cls_sum (+ l1_sum), un-normalised, with the gradient produced by the same
+    kernel launch that produced the value (ops.head_losses). `sums` (iou, obj, cls, l1) is returned for reporting."""
+
+    @staticmethod
+    def forward(ctx, pred, origin, labels, asg, x_shifts, y_shifts, strides, giou, reg_weight):
+        sums, grad, g_or = ops.head_losses(pred, labels, asg, origin, x_shifts, y_shifts, strides, giou, reg_weight)
+        ctx.save_for_backward(grad, g_or if g_or is not None else grad.new_empty(0))
+        ctx.has_origin = origin is not None
+        sums = sums.to(torch.float32)
+        total = reg_weight * sums[0] + sums[1] + sums[2] + sums[3]
+        ctx.mark_non_differentiable(sums)
+        return total, sums
+
+    @staticmethod
+    def backward(ctx, g_total, _g_sums):
+        grad, g_or = ctx.saved_tensors
+        return (grad * g_total, g_or * g_total if ctx.has_origin else None, None, None, None, None, None, None, None)
+
+
 class YoloxHead(_B200Block):
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
                  depthwise=False):
@@ -170,40 +190,27 @@ class YoloxHead(_B200Block):
 
     # ------------------------------------------------------------------ training: losses
     def get_losses(self, imgs, x_shifts, y_shifts, expanded_strides, labels, outputs, origin_preds, dtype):
-        bbox_preds = outputs[:, :, :4]
-        obj_preds = outputs[:, :, 4:5]
-        cls_preds = outputs[:, :, 5:]
+        """yolo_head.py:253-418 without the per-image Python loop: one SimOTA launch for the whole batch
+        (yx_simota_assign), then one launch that evaluates the IoU / objectness / class / L1 terms AND their gradients
+        w.r.t. the prediction tensor (yx_head_losses) -- no boolean-mask gathers, no one-hot tensor, no host sync.
+        Returns the reference's 6-tuple; only the total loss carries a gradient (the components are reported values)."""
         x_shifts = torch.cat(x_shifts, 1)
         y_shifts = torch.cat(y_shifts, 1)
         expanded_strides = torch.cat(expanded_strides, 1)
-        if self.use_l1:
-            origin_preds = torch.cat(origin_preds, 1)
-        B, A = outputs.shape[:2]
-
+        origin = torch.cat(origin_preds, 1) if self.use_l1 else None
+        ops.require_cuda(outputs, "get_losses")
+        pred = outputs.float().contiguous()
         with torch.no_grad():
-            asg = ops.simota_assign(outputs.detach(), labels, x_shifts, y_shifts, expanded_strides, self.num_classes)
-        fg = asg["fg_mask"].bool()                               # [B, A]
-        num_fg = asg["num_fg"].sum().clamp(min=1).to(outputs.dtype)
-        num_gts = asg["num_gt"].sum().clamp(min=1).to(outputs.dtype)
-        b_idx, a_idx = fg.nonzero(as_tuple=True)                 # image-major, anchor order (yolo_head.py:368-378)
-        g_idx = asg["matched_gt"][b_idx, a_idx].long()
-        reg_targets = labels[b_idx, g_idx, 1:5].to(outputs.dtype)
-        cls_targets = F.one_hot(asg["matched_cls"][b_idx, a_idx].long(), self.num_classes).to(outputs.dtype) \
-            * asg["matched_iou"][b_idx, a_idx].unsqueeze(-1).to(outputs.dtype)
-        obj_targets = fg.reshape(-1, 1).to(dtype)
-
-        loss_iou = self.iou_loss(bbox_preds.reshape(-1, 4)[fg.reshape(-1)], reg_targets).sum() / num_fg
-        loss_obj = self.bcewithlog_loss(obj_preds.reshape(-1, 1), obj_targets).sum() / num_fg
-        loss_cls = self.bcewithlog_loss(cls_preds.reshape(-1, self.num_classes)[fg.reshape(-1)], cls_targets).sum() / num_fg
-        if self.use_l1:
-            l1_targets = self.get_l1_target(outputs.new_zeros((b_idx.numel(), 4)), reg_targets,
-                                            expanded_strides[0][a_idx], x_shifts[0][a_idx], y_shifts[0][a_idx])
-            loss_l1 = self.l1_loss(origin_preds.reshape(-1, 4)[fg.reshape(-1)], l1_targets).sum() / num_fg
-        else:
-            loss_l1 = 0.0
+            asg = ops.simota_assign(pred.detach(), labels, x_shifts, y_shifts, expanded_strides, self.num_classes)
+        num_fg = asg["num_fg"].sum().clamp(min=1).to(torch.float32)
+        num_gts = asg["num_gt"].sum().clamp(min=1).to(torch.float32)
         reg_weight = 5.0
-        loss = reg_weight * loss_iou + loss_obj + loss_cls + loss_l1
-        return (loss, reg_weight * loss_iou, loss_obj, loss_cls, loss_l1, num_fg / num_gts)
+        total, sums = _FusedHeadLoss.apply(pred, None if origin is None else origin.float().contiguous(), labels, asg,
+                                           x_shifts, y_shifts, expanded_strides, self.iou_loss.loss_type == "giou", reg_weight)
+        loss = (total / num_fg).to(outputs.dtype)
+        parts = (sums / num_fg).to(outputs.dtype)
+        loss_l1 = parts[3] if self.use_l1 else 0.0
+        return (loss, reg_weight * parts[0], parts[1], parts[2], loss_l1, num_fg / num_gts)
 
     def get_l1_target(self, l1_target, gt, stride, x_shifts, y_shifts, eps=1e-8):
         l1_target[:, 0] = gt[:, 0] / stride - x_shifts

@@ -143,7 +143,70 @@ def gen_network():
     print("network.npz", len(out))
 
 
+def loss_case_inputs(name):
+    """pred / labels / anchor grid / raw regression outputs of a SIMOTA_ASSIGN case (the inverse decode of pred)."""
+    from oracle.simota_oracle import anchor_grid
+
+    pred, lab, hw = cases.assign_case(name)
+    xs, ys, st = anchor_grid(hw, cases.STRIDES)
+    origin = np.stack([pred[..., 0] / st - xs, pred[..., 1] / st - ys, np.log(pred[..., 2] / st), np.log(pred[..., 3] / st)],
+                      -1).astype(np.float32)
+    return pred, lab, xs, ys, st, origin
+
+
+def gen_losses():
+    """YoloxHead.get_losses of the unmodified reference (values + autograd gradients) on the SimOTA assign cases,
+    with the assignment it used (captured from its own get_assignments) so the loss path can be checked on its own."""
+    out = {}
+    for name in cases.SIMOTA_ASSIGN_CASES:
+        pred, lab, xs, ys, st, origin = loss_case_inputs(name)
+        B, A, _ = pred.shape
+        for l1 in (False, True):
+            head = ref["YoloxHead"](80)
+            head.use_l1 = l1
+            cap = []
+            orig = head.get_assignments
+
+            def wrapped(*a, **k):
+                r = orig(*a, **k)
+                cap.append((a[0], r))
+                return r
+
+            head.get_assignments = wrapped
+            tp = torch.from_numpy(pred).clone().requires_grad_(True)
+            to = torch.from_numpy(origin).clone().requires_grad_(True)
+            res = head.get_losses(None, [torch.from_numpy(xs)[None]], [torch.from_numpy(ys)[None]],
+                                  [torch.from_numpy(st)[None]], torch.from_numpy(lab), tp, [to], torch.float32)
+            res[0].backward()
+            key = f"{name}/l1_{int(l1)}"
+            out[key + "/losses"] = np.array([float(v) for v in res], dtype=np.float64)
+            g = tp.grad.numpy()
+            fg = np.zeros((B, A), dtype=bool); mg = np.full((B, A), -1, dtype=np.int32)
+            mi = np.zeros((B, A), dtype=np.float32); mc = np.zeros((B, A), dtype=np.int32)
+            for b, (gcls, fgm, pious, minds, num_fg) in cap:
+                fgn = fgm.numpy()
+                fg[b] = fgn; mg[b, fgn] = minds.numpy(); mi[b, fgn] = pious.numpy(); mc[b, fgn] = gcls.numpy().astype(np.int32)
+            nz = g.copy(); nz[..., 4] = 0; nz[fg] = 0
+            assert not nz.any(), "reference gradient outside the foreground rows / objectness column"
+            if not l1:
+                out[f"{name}/fg"], out[f"{name}/matched_gt"] = fg, mg
+                out[f"{name}/matched_iou"], out[f"{name}/matched_cls"] = mi, mc
+                out[f"{name}/in_sha"] = np.array(cases.checksum(pred) + cases.checksum(lab) + cases.checksum(origin))
+            out[key + "/grad_obj"] = g[..., 4].copy()
+            out[key + "/grad_fg"] = g[fg].copy()
+            if l1:
+                out[key + "/grad_origin_fg"] = to.grad.numpy()[fg].copy()
+    np.savez_compressed(OUT / "losses.npz", **out)
+    print("losses.npz", len(out))
+
+
 if __name__ == "__main__":
-    gen_postprocess()
-    gen_simota()
-    gen_network()
+    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses"]
+    if "postprocess" in which:
+        gen_postprocess()
+    if "simota" in which:
+        gen_simota()
+    if "network" in which:
+        gen_network()
+    if "losses" in which:
+        gen_losses()
