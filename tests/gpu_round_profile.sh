@@ -5,7 +5,9 @@
 tag=${1:-r1x}
 timeout 400 python bench.py --profile-ops > gpurun_out/bench_$tag.json 2> gpurun_out/ops_$tag.txt
 tail -c 300 gpurun_out/bench_$tag.json
-timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+# -k: this repo's kernels only (bench.py first calibrates BN statistics with torch ops, hundreds of cudnn/ATen launches)
+timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k 'regex:conv_tc|bneck|stem_tc|spp|dwconv|filter_kernel|sort_nms|conv_simt|focus' -c 400 --csv \
   --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof_conv3x3_$tag \
   python tests/gpu_prof_conv.py 64 128:256:3:1:80 > gpurun_out/ncu_c_$tag.log 2>&1
