@@ -34,7 +34,14 @@ static constexpr int kStemEpiGroups = 4;
 static constexpr int kStemThreads = kStemBuilders * kStemBuilderGroups + 64 + 128 * kStemEpiGroups + 32;   // + MMA warp + TMA warp + second MMA warp
 static constexpr int kWarpMma = kStemBuilders * kStemBuilderGroups / 32, kWarpTma = kWarpMma + 1, kWarpEpi = kWarpMma + 2;
 static constexpr int kWarpMma2 = kWarpEpi + 4 * kStemEpiGroups;     // tiles alternate between the two issuing warps
+// A parity wait can only tell "this phase" from "the previous one": every waiter must stay within one phase of its
+// barrier. That holds when all uses of a ring slot belong to ONE group of warps working through its tiles in order, i.e.
+// when the group count divides the slot count (three epilogue groups on four accumulator slots let a group reach tile
+// t + 8 of a slot whose tile t + 4 was still in flight with the other issuing warp: wrong accumulators, then a deadlock).
+static_assert(kStemAcc % kStemEpiGroups == 0 && kStemStages % kStemBuilderGroups == 0 && kStemStages % 2 == 0 &&
+              kStemAcc % 2 == 0, "ring slots must map to one warp group each (mbarrier parity aliasing)");
 static constexpr int kPatchStages = 4;
+static_assert(kPatchStages % kStemBuilderGroups == 0, "patch ring slots must map to one builder group each");
 // The output tile (th x tw, accumulator row m = y * (tw + 2) + x, th * (tw + 2) <= 128) is chosen per image width
 // on the host: the raw patch arrives as 3 * (2*th + 4) TMA rows and the TMA unit's cost is per ROW (fp32 160-byte and
 // uint8 64-byte rows of the first 7 x 16 tile took the same 250 us), so wide, flat tiles (3 x 40 at 640^2: 30 rows of
