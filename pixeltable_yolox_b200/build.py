@@ -45,17 +45,18 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    stamp = OBJ_DIR / "stamp.txt"
-    digest = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == digest:
-        return LIB
+def build_lib(force: bool = False, verbose: bool = False, extra_flags=(), lib: Path = LIB, obj_dir: Path = OBJ_DIR) -> Path:
+    """`extra_flags` / `lib` / `obj_dir`: an experiment build next to the product library (select it with YX_B200_LIB)."""
+    stamp = obj_dir / "stamp.txt"
+    digest = _digest() + " ".join(extra_flags)
+    if not force and lib.exists() and stamp.exists() and stamp.read_text().strip() == digest:
+        return lib
     nvcc = _nvcc()
-    OBJ_DIR.mkdir(exist_ok=True)
+    obj_dir.mkdir(exist_ok=True)
 
     def compile_one(src: str) -> Path:
-        obj = OBJ_DIR / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        obj = obj_dir / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,15 +68,20 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static",
+    cmd = [nvcc, "-shared", "-o", str(lib), *map(str, objs), "-cudart", "static",
            "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    path = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--exp" in sys.argv:
+        # python -m pixeltable_yolox_b200.build --exp -DYX_CONV_TRACE ...  ->  libyx_b200_exp.so (run with YX_B200_LIB=<path>)
+        flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+        path = build_lib(force=True, extra_flags=flags, lib=PKG / "libyx_b200_exp.so", obj_dir=PKG / "build_exp")
+    else:
+        path = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -144,6 +144,19 @@ __device__ __forceinline__ void halo_issue_ring(TcShared* sh, uint64_t ad0, uint
 
 
 // SILU: the activation is SiLU (compile-time: the generic activation code and its per-chunk dispatch disappear)
+// -DYX_CONV_TRACE (experiment builds only, see build.py --exp): CTA 0 records %globaltimer at the hand-off points of its
+// first and last tile; conv_tc_launch prints them. Compiled out of the product library (the hot loops are sensitive to
+// any extra code: see DESIGN 4.4/4.5).
+#ifdef YX_CONV_TRACE
+__device__ unsigned long long g_conv_trace[16];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CT(k) do { if (blockIdx.x == 0) g_conv_trace[k] = gtimer(); } while (0)
+#define CT_ONCE(k, flag) do { if (blockIdx.x == 0 && !(flag)) { g_conv_trace[k] = gtimer(); flag = true; } } while (0)
+#else
+#define CT(k) do { } while (0)
+#define CT_ONCE(k, flag) do { } while (0)
+#endif
+
 // HEAD: the YX_EPI_HEAD epilogue (decode + optional score filter) is its own instantiation, so its ~1 000 SASS
 // instructions do not sit in the instruction cache footprint / register allocation of the activation-store kernels
 template <bool FP16, bool SILU, bool HEAD>
@@ -151,6 +164,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) CT(0);
   // operand tiles need 1024-byte alignment for the 128-byte swizzle atom
   // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space known to the
   // compiler: LDS/STS instead of generic loads for every bias / staging access
@@ -198,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  if (threadIdx.x == 0) CT(1);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias copy) touches only
   // constants and overlaps the tail of the previous kernel; activations are read/written after the wait
   // resident weights are constants: their loads are issued BEFORE griddepcontrol.wait (each role waits itself,
@@ -327,8 +342,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tap * p.in_c + c * p.KC, 0);
       }
       pdl_wait();
+      CT(2);
       int ca = 0, sb = 0;
       uint32_t pb = 0;
+      [[maybe_unused]] bool tr3 = false;
       for (int t = t_begin; t < t_end;) {
         const int i0 = t % p.G;
         const int u = t / p.G;
@@ -351,6 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             else
               tma_load_4d(&map_a, &sh->afull[slot], aregion + (size_t)slot * p.a_slot_bytes, c * p.KC,
                           tx * p.tw - 1, ty * p.th - 1, b);
+            CT_ONCE(3, tr3);
           }
           if (!p.b_resident) {
             for (int tap = 0; tap < p.taps; ++tap) {
@@ -381,6 +399,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int sa = 0, sb = 0, as = 0, i0 = t_begin % G;
     uint32_t pa = 0, pb = 0, pacc = 0;
     if (!ring) mbar_wait(&sh->bres_full, 0);
+    if (lane == 0) CT(4);
+    [[maybe_unused]] bool tr5 = false, tr6 = false;
     for (int t = t_begin; t < t_end;) {
       int g = G - i0;
       if (g > t_end - t) g = t_end - t;
@@ -401,6 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c = 0; c < kch; ++c) {
         const int sl0 = sa;
         mbar_wait(&sh->afull[sa], pa);
+        if (lane == 0) CT_ONCE(5, tr5);
         const uint32_t al0 = a0 + (uint32_t)sa * aslot16;
         if (++sa == n_as) { sa = 0; pa ^= 1; }
         const int sl1 = sa;
@@ -439,6 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (g > 1) umma_commit(&sh->tmem_full[st1]);
       }
       __syncwarp();
+      if (lane == 0) CT_ONCE(6, tr6);
       t += g;
     }
   } else if (warp == 0) {
@@ -524,6 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool need_coords = p.flat && (p.epi.ups != nullptr || HEAD);
     int as = grp % p.acc_stages;
     uint32_t aphase = (uint32_t)((grp / p.acc_stages) & 1);
+    [[maybe_unused]] bool tr7 = false, tr8 = false;
     for (int it = grp;; it += p.epi_groups) {
       int n_tile, m_tile;
       if (p.halo) {
@@ -563,6 +586,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         pix = ((long long)b * p.epi.out_h + ho) * p.epi.out_w + wo;
       }
       mbar_wait(&sh->tmem_full[as], aphase);
+      if (warp == 2 && lane == 0) CT_ONCE(7, tr7);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BNpad);
       const float* tbias = sbias + n_tile * p.BN;
@@ -760,6 +784,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&sh->tmem_empty[as]);
+      if (warp == 2 && lane == 0) { CT_ONCE(8, tr8); CT(9); }
       as += p.epi_groups;
       while (as >= p.acc_stages) { as -= p.acc_stages; aphase ^= 1; }
       }   // !HEAD
@@ -768,6 +793,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) CT(10);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1185,6 +1211,9 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool silu = L->p.epi.act == YX_ACT_SILU && L->p.epi.epilogue == YX_EPI_STORE;
+#ifdef YX_CONV_TRACE
+  { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_conv_trace, z, sizeof(z)); }
+#endif
   const bool head = L->p.epi.epilogue == YX_EPI_HEAD;
   if (L->p.epi.dtype == YX_FP16) {
     if (head) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, L->map_a, L->map_b, L->p));
@@ -1195,6 +1224,17 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
     else if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, L->map_a, L->map_b, L->p));
     else YX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, L->map_a, L->map_b, L->p));
   }
+#ifdef YX_CONV_TRACE
+  {
+    unsigned long long z[16];
+    cudaStreamSynchronize(stream);
+    if (cudaMemcpyFromSymbol(z, g_conv_trace, sizeof(z)) == cudaSuccess) {
+      fprintf(stderr, "conv trace (ns from CTA 0 entry): setup %lld | producer: pdl %lld first A issued %lld | mma: weights %lld first A %lld first tile committed %lld | epilogue: first acc %lld first tile stored %lld last tile stored %lld | exit %lld\n",
+              (long long)(z[1] - z[0]), (long long)(z[2] - z[0]), (long long)(z[3] - z[0]), (long long)(z[4] - z[0]), (long long)(z[5] - z[0]),
+              (long long)(z[6] - z[0]), (long long)(z[7] - z[0]), (long long)(z[8] - z[0]), (long long)(z[9] - z[0]), (long long)(z[10] - z[0]));
+    }
+  }
+#endif
   return YX_OK;
 }
 
