@@ -250,6 +250,15 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                   v[j + u] = fmaf(h, tt, h);
                 }
               }
+            } else if constexpr (SILU && FP16) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(sbias1 + c + j);
+                v[j + 0] = silu_exp(__uint_as_float(raw[j + 0]) + bb.x);
+                v[j + 1] = silu_exp(__uint_as_float(raw[j + 1]) + bb.y);
+                v[j + 2] = silu_exp(__uint_as_float(raw[j + 2]) + bb.z);
+                v[j + 3] = silu_exp(__uint_as_float(raw[j + 3]) + bb.w);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = act_f<false>(__uint_as_float(raw[j]) + sbias1[c + j], p.act1);
@@ -322,8 +331,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16, SILU>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16, SILU>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();
@@ -558,6 +567,8 @@ bneck128_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     float tt;
                     asm("tanh.approx.f32 %0, %1;" : "=f"(tt) : "f"(h));
                     v[j + u] = fmaf(h, tt, h);
+                  } else if constexpr (SILU && FP16) {
+                    v[j + u] = silu_exp(__uint_as_float(raw[g][j + u]) + hb[u]);
                   } else {
                     v[j + u] = act_f<false>(__uint_as_float(raw[g][j + u]) + hb[u], p.act1);
                   }
@@ -613,8 +624,8 @@ bneck128_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (rrow && valid) { ld_global_256(rrow + c, qa); ld_global_256(rrow + c + 16, qb); }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16, silu_tanh>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
-          epi_tc_chunk<FP16, silu_tanh>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16, SILU>(p.epi, ra, sbias2 + c, rrow ? qa : nullptr, orow + c, b, ho, wo, c);
+          epi_tc_chunk<FP16, SILU>(p.epi, rb, sbias2 + c + 16, rrow ? qb : nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       tc_fence_before();

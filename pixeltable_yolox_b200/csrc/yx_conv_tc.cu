@@ -776,9 +776,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
+          epi_tc_chunk<FP16, SILU>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
           if (two)
-            epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
+            epi_tc_chunk<FP16, SILU>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
                          n_tile * p.BN + c + 16);
         }
       }

@@ -310,8 +310,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tmem_ld_wait();
         if (warp == kWarpEpi && c == 0) ST_TRACE(2, it, 2);
         if (valid) {
-          epi_tc_chunk<FP16, SILU && !FP16>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
-          if (two) epi_tc_chunk<FP16, SILU && !FP16>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
+          epi_tc_chunk<FP16, SILU>(p.epi, ra, sbias + c, nullptr, orow + c, b, ho, wo, c);
+          if (two) epi_tc_chunk<FP16, SILU>(p.epi, rb, sbias + c + 16, nullptr, orow + c + 16, b, ho, wo, c + 16);
         }
       }
       if (warp == kWarpEpi) ST_TRACE(2, it, 3);
