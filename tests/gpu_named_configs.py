@@ -24,6 +24,8 @@ for name in names:
     model.load_state_dict(sd)
     ref = yo.forward({k: v.to(dev) for k, v in sd.items()}, x.to(dev)).cpu().numpy()       # fp32 torch, same graph
     for dt in (torch.bfloat16, torch.float16):
+        model = model.float()
+        model.load_state_dict(sd)            # nn.Module.to is in place: reload, or fp16 would inherit bf16-rounded weights
         m = model.to(dev).to(dt).eval()
         out = m(x.to(dev)).float().cpu().numpy()
         sdd = {k: (v.to(dev).to(dt) if v.is_floating_point() else v.to(dev)) for k, v in sd.items()}
