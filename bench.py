@@ -106,6 +106,31 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Multi-rank runs: keep this rank's threads (and therefore its pinned host buffers, first touch) on the NUMA node the
+    GPU hangs off, so that eight ranks' H2D streams do not cross the socket interconnect. Best effort: returns the node
+    or None (single rank, sysfs not visible, or the container's cpuset has no CPU of that node)."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        avail = os.sched_getaffinity(0) & cpus
+        if not avail:
+            return None
+        os.sched_setaffinity(0, avail)
+        return node
+    except Exception:
+        return None
+
+
 def build_model(args, device):
     import torch
 
@@ -206,6 +231,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("YX_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -342,7 +368,8 @@ def run_ours(args):
                        "candidates_per_image_mean": cand_mean},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "input": "pinned host uint8 [B,3,H,W] pixels, converted on device by the stem kernel; "
-                             "double-buffered over 2 streams", "detections_kept_last_step": kept_u8},
+                             "double-buffered over 2 streams", "detections_kept_last_step": kept_u8,
+                    "numa_node_rank0": numa},
             "e2e_fp32_input": {"value": e2e_fp32, "unit": "images/s", "h2d_bytes_per_step": h2d_fp32,
                                "d2h_bytes_per_step": d2h,
                                "input": "pinned host fp32 [B,3,H,W] (the reference processor's dtype), same pixels"},
