@@ -47,7 +47,7 @@ def _digest() -> str:
 
 def build_lib(force: bool = False, verbose: bool = False, extra_flags=(), lib: Path = LIB, obj_dir: Path = OBJ_DIR) -> Path:
     """`extra_flags` / `lib` / `obj_dir`: an experiment build next to the product library (select it with YX_B200_LIB)."""
-    stamp = obj_dir / "stamp.txt"
+    stamp = lib.with_suffix(".stamp")          # next to the library, so it travels with it (gpurun snapshots, copies)
     digest = _digest() + " ".join(extra_flags)
     if not force and lib.exists() and stamp.exists() and stamp.read_text().strip() == digest:
         return lib
