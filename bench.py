@@ -254,8 +254,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- value: inputs resident in HBM ----------------
+    # Two engines (own plan, own activation buffers) alternate, each with its batch already in its input buffer: no
+    # staging copy inside the timed region, and every step reads a 315 MB input the previous step did not touch.
+    for i in range(2):
+        eng[i].input.copy_(dev_in[i])
     for i in range(args.warmup):
-        eng[0].forward(dev_in[i % 2])
+        eng[i % 2].forward(eng[i % 2].input)
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -263,7 +267,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        eng[0].forward(dev_in[i % 2])
+        eng[i % 2].forward(eng[i % 2].input)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -274,9 +278,10 @@ def run_ours(args):
         ms = float(t.item())
     barrier()
     value = world * B * args.steps / (ms / 1e3)
-    kept = int(eng[0].det_count.clamp(max=args.max_det).sum().item())
-    kept_true_mean = float(eng[0].det_count.float().mean().item())
-    scores = eng[0].pred[..., 4] * eng[0].pred[..., 5:].max(-1).values
+    last = eng[(args.steps - 1) % 2]
+    kept = int(last.det_count.clamp(max=args.max_det).sum().item())
+    kept_true_mean = float(last.det_count.float().mean().item())
+    scores = last.pred[..., 4] * last.pred[..., 5:].max(-1).values
     cand_mean = float((scores >= args.conf).float().sum(1).mean().item())
 
     # ---------------- e2e: host buffers in, detections out, every step ----------------
@@ -363,7 +368,7 @@ def run_ours(args):
                        "per_gpu_batch": B, "global_batch": B * world, "micro_batch": args.micro_batch,
                        "conf_thre": args.conf, "nms_thre": args.nms, "nms_variant": "auto (torchvision CUDA rule)",
                        "weights": "random init, BN calibrated (synthetic.randomize_and_calibrate)",
-                       "l2": "two alternating input batches of 315 MB each (> 126 MB L2)",
+                       "l2": "two alternating engines, each with its own 315 MB input batch resident in its input buffer (> 126 MB L2)",
                        "detections_kept_last_step": kept, "kept_per_image_mean": kept_true_mean,
                        "candidates_per_image_mean": cand_mean},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -601,11 +601,13 @@ class InferenceEngine:
         return self.builder.launches
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: [B,3,H,W] on any device (a host tensor is copied H2D here). Returns the engine's
-        own prediction buffer [B, A, 5+nc] fp32 (valid until the next call)."""
+        """x: [B,3,H,W] on any device (a host tensor is copied H2D here, a device tensor D2D into the persistent input
+        buffer the plan's tensor maps point at; pass `engine.input` itself to run on what is already there). Returns
+        the engine's own prediction buffer [B, A, 5+nc] fp32 (valid until the next call)."""
         if tuple(x.shape) != tuple(self.input.shape):
             raise ValueError(f"engine built for {tuple(self.input.shape)}, got {tuple(x.shape)}")
-        self.input.copy_(x, non_blocking=True)
+        if x.data_ptr() != self.input.data_ptr():        # a caller that fills `engine.input` itself skips the staging copy
+            self.input.copy_(x, non_blocking=True)
         self.builder.run(self.use_graph)
         return self.pred
 
