@@ -787,7 +787,8 @@ int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
 }
 
 int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));

@@ -12,6 +12,15 @@
 
 namespace yx {
 
+// Function attributes (opt-in shared memory) belong to a device: launch helpers cache "already configured" per device,
+// so one process may drive several GPUs (each with its own module / engine).
+static constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side error plumbing (thread-local message, never throws)
 // ------------------------------------------------------------------------------------------

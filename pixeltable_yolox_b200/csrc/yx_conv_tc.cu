@@ -1186,7 +1186,8 @@ ConvTcLaunch* conv_tc_alloc() {
 void conv_tc_free(ConvTcLaunch* p) { free(p); }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     int dev = 0, max_smem = 0;
     YX_CUDA(cudaGetDevice(&dev));

@@ -205,7 +205,9 @@ int head_loss_launch(const float* pred, const float* labels, int max_gt, const u
              "head_losses: origin / grad_origin must be 16-byte aligned");
   const size_t smem = (size_t)kLossAnchors * (5 + nc) * sizeof(float);
   YX_REQUIRE(smem <= 200 * 1024, YX_ERR_UNSUPPORTED, "head_losses: %d classes exceed the shared-memory row staging", nc);
-  static size_t configured = 48 * 1024;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device_slot()];
+  if (configured == 0) configured = 48 * 1024;
   if (smem > configured) {
     YX_CUDA(cudaFuncSetAttribute(head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -573,7 +573,8 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.gkeys_stride = next_pow2_ll(g.src.per_image);
   g.debug = getenv("YX_NMS_DEBUG") ? 1 : 0;
   const size_t smem = nms_smem_bytes(g.src.per_image);
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     YX_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -589,7 +590,9 @@ int filter_launch(float* pred, int batch, int anchors, int nc, float conf_thre, 
   const int chunks = (anchors + kFilterAnchors - 1) / kFilterAnchors;
   const size_t smem = (size_t)kFilterAnchors * (5 + nc) * sizeof(float);
   YX_REQUIRE(smem <= 200 * 1024, YX_ERR_UNSUPPORTED, "postprocess: %d classes exceed the shared-memory row staging", nc);
-  static size_t configured = 48 * 1024;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device_slot()];
+  if (configured == 0) configured = 48 * 1024;
   if (smem > configured) {
     YX_CUDA(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

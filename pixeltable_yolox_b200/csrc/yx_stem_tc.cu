@@ -446,7 +446,8 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
 }
 
 int stem_launch(const StemLaunch* L, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
 #define YX_STEM_ATTR(T, F) \
   YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
