@@ -169,6 +169,12 @@ def cpu_reference_rate(args, sd, images_np, seconds_cap=25.0):
     return done / t_used, threads, done
 
 
+def workload_name(args) -> str:
+    """The same string in both arms (ours / --impl reference): the BASELINE.json configuration being measured."""
+    return (f"{args.model} {args.size}x{args.size} batch-{args.batch}/GPU {args.dtype} inference (fwd+decode+NMS), "
+            "config[1] of BASELINE.json")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     import torch
@@ -207,8 +213,8 @@ def run_reference(args):
         "metric": "images_per_second", "impl": "reference", "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} {args.size}x{args.size} fwd+decode+NMS, CPU sample of {per_step} images/step",
-                   "conf_thre": args.conf, "nms_thre": args.nms},
+        "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "conf_thre": args.conf, "nms_thre": args.nms,
+                   "reference_arm": f"CPU fp32, bounded sample of {per_step} images per step of that workload"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} steps x {per_step} images, oracle/ torch-CPU fp32 forward + numpy/C NMS"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -364,7 +370,7 @@ def run_ours(args):
             "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": vs, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{args.model} {S}x{S} batch-{B}/GPU {args.dtype} inference (fwd+decode+NMS), config[1] of BASELINE.json",
+            "config": {"workload": workload_name(args),
                        "per_gpu_batch": B, "global_batch": B * world, "micro_batch": args.micro_batch,
                        "conf_thre": args.conf, "nms_thre": args.nms, "nms_variant": "auto (torchvision CUDA rule)",
                        "weights": "random init, BN calibrated (synthetic.randomize_and_calibrate)",
