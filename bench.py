@@ -71,6 +71,8 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.rows = []
+        self.stamps = []          # host arrival time of each row
+        self.window = None        # (t0, t1) of the timed region; rows outside it are dropped when enough fall inside
         self.proc = None
 
     def start(self):
@@ -88,6 +90,16 @@ class ClockSampler:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
                 self.rows.append(parts)
+                self.stamps.append(time.perf_counter())
+
+    def mark(self, t0: float, t1: float):
+        self.window = (t0, t1)
+
+    def wait_first(self, timeout: float = 1.0):
+        """Block until nvidia-smi has produced its first row (it needs ~100-300 ms to start)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
 
     def stop(self):
         if self.proc is None:
@@ -98,6 +110,10 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        if self.window is not None:
+            inside = [r for r, t in zip(self.rows, self.stamps) if self.window[0] <= t <= self.window[1] + 0.03]
+            if inside:
+                self.rows = inside
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -264,19 +280,23 @@ def run_ours(args):
     # staging copy inside the timed region, and every step reads a 315 MB input the previous step did not touch.
     for i in range(2):
         eng[i].input.copy_(dev_in[i])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()            # before the warm-up: nvidia-smi needs ~100-300 ms before its first row
+        clocks.wait_first()
     for i in range(args.warmup):
         eng[i % 2].forward(eng[i % 2].input)
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         eng[i % 2].forward(eng[i % 2].input)
     e1.record()
     torch.cuda.synchronize()
+    w1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
+    clocks.mark(w0, w1)           # keep the rows sampled while the timed steps ran
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
