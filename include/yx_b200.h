@@ -204,7 +204,10 @@ int yx_head_decode(float* pred, int32_t batch, int32_t anchors, int32_t nc, cons
  *               1 = per-class ("vanilla", torchvision CPU path above 4000 coordinates),
  *               2 = class-agnostic (boxes.py:55-60),
  *               3 / 4 = what torchvision itself picks per image on CUDA / on CPU:
- *               the offset trick unless 4*n_candidates > 100000 (CUDA) / 4000 (CPU), else per-class.
+ *               the offset trick unless 4*n_candidates > 100000 (CUDA, torchvision >= 0.19; 0.26 is installed and
+ *               generated the goldens) / 4000 (CPU), else per-class.
+ *               5 = the CUDA rule of torchvision 0.17.2, the version the reference pins (poetry.lock:2084-2085):
+ *               per-class above 20000 coordinates.
  *   workspace : yx_postprocess_workspace_bytes(B, A) bytes of device scratch.
  * ------------------------------------------------------------------------------------------ */
 int64_t yx_postprocess_workspace_bytes(int32_t batch, int32_t anchors);
@@ -255,15 +258,23 @@ int yx_bboxes_iou(const float* a, int32_t n, const float* b, int32_t m, int32_t 
  * outputs (dense over anchors):
  *   fg_mask [B, A] uint8, matched_gt [B, A] int32 (-1 when not foreground),
  *   matched_iou [B, A] fp32, matched_cls [B, A] int32, num_fg [B] int32, num_gt [B] int32.
- *   workspace: yx_simota_workspace_bytes(B, A, max_gt) bytes.
+ *   status [B] int32 (may be NULL): 0, or YX_SIMOTA_CAPACITY (more in-centre anchors than 9*levels*max_gt: the
+ *   anchor grid is not one unit-spaced grid per stride level; the surplus was dropped), or YX_SIMOTA_BAD_CLASS (a label
+ *   class outside [0, nc): F.one_hot raises in the reference; clamped here). Written by the kernel, no host sync.
+ *   levels: number of distinct strides in stride_per_anchor (3 for every named config).
+ *   max_gt: label rows per image, 1..512 (the reference pads to 120, data_augment.py:200-208).
+ *   workspace: yx_simota_workspace_bytes(B, A, max_gt, levels) bytes.
+ * One thread-block cluster per image (up to 8 CTAs): see csrc/yx_simota.cu.
  * ------------------------------------------------------------------------------------------ */
-int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt);
+#define YX_SIMOTA_CAPACITY 1
+#define YX_SIMOTA_BAD_CLASS 2
+int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt, int32_t levels);
 int yx_simota_assign(const float* pred, const float* labels, const float* x_shift,
                      const float* y_shift, const float* stride_per_anchor, int32_t batch,
-                     int32_t anchors, int32_t nc, int32_t max_gt, uint8_t* fg_mask,
+                     int32_t anchors, int32_t nc, int32_t max_gt, int32_t levels, uint8_t* fg_mask,
                      int32_t* matched_gt, float* matched_iou, int32_t* matched_cls,
-                     int32_t* num_fg, int32_t* num_gt, void* workspace, int64_t workspace_bytes,
-                     void* stream);
+                     int32_t* num_fg, int32_t* num_gt, int32_t* status, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 /* simota_matching alone (yolo_head.py:542-574) on a given cost / IoU matrix [G, n] fp32
  * (row stride ld): match_gt [n] int32 (-1 = not matched), match_iou [n] fp32, num_fg[1]. */
 int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int32_t n,

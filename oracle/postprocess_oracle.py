@@ -48,7 +48,9 @@ def batched_nms(boxes, scores, idxs, thr, variant="auto_cpu"):
         return batched_nms_offset(boxes, scores, idxs, thr)
     if variant == "per_class":
         return batched_nms_per_class(boxes, scores, idxs, thr)
-    limit = 4000 if variant == "auto_cpu" else 100000          # torchvision/ops/boxes.py batched_nms
+    # torchvision/ops/boxes.py batched_nms: 4000 on CPU; on CUDA 100000 (torchvision >= 0.19, 0.26 installed) or
+    # 20000 (torchvision 0.17.2, the reference's pin: "auto_tv017")
+    limit = {"auto_cpu": 4000, "auto_tv017": 20000}.get(variant, 100000)
     if boxes.size > limit:
         return batched_nms_per_class(boxes, scores, idxs, thr)
     return batched_nms_offset(boxes, scores, idxs, thr)

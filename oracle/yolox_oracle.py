@@ -136,7 +136,9 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, act: str = "silu", dec
 # ------------------------------------------------------------------------------------------------
 def seeded_state_dict(template: Dict[str, torch.Tensor], seed: int, image_hw: Tuple[int, int] = (64, 64),
                       calib_batch: int = 8, act: str = "silu", big_boxes: bool = False,
-                      calib_x: torch.Tensor = None) -> Dict[str, torch.Tensor]:
+                      calib_x: torch.Tensor = None, device=None) -> Dict[str, torch.Tensor]:
+    """`device`: run the BN calibration forwards there (weight preparation only; the named configs at 640^2 take minutes
+    on CPU). The returned state_dict is always on the CPU."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for k, v in template.items():
@@ -169,6 +171,9 @@ def seeded_state_dict(template: Dict[str, torch.Tensor], seed: int, image_hw: Tu
     x = torch.from_numpy(images(calib_batch, image_hw[0], image_hw[1], seed=seed + 100))
     if calib_x is not None:      # include the evaluation images: tiny maps give too few BN samples otherwise
         x = torch.cat([calib_x.float(), x], 0)
+    if device is not None:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        x = x.to(device)
     _calibrate(sd, x, ACTS[act])
     # keep the raw box regressions in a sane range (|v| <= 2.5) so that exp(wh) stays well conditioned
     with torch.no_grad():
@@ -181,7 +186,7 @@ def seeded_state_dict(template: Dict[str, torch.Tensor], seed: int, image_hw: Tu
             if m > 2.5:
                 sd[f"head.reg_preds.{k}.weight"] = sd[f"head.reg_preds.{k}.weight"] * (2.5 / m)
                 sd[f"head.reg_preds.{k}.bias"] = sd[f"head.reg_preds.{k}.bias"] * (2.5 / m)
-    return sd
+    return {k: v.cpu() for k, v in sd.items()} if device is not None else sd
 
 
 @torch.no_grad()

@@ -86,8 +86,8 @@ SIGNATURES = {
     "yx_score_filter_compact": (C.c_int, [_P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _I64, _P]),
     "yx_batched_nms": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _D, _I32, _P, _P, _P, _I64, _P]),
     "yx_bboxes_iou": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _P]),
-    "yx_simota_workspace_bytes": (_I64, [_I32, _I32, _I32]),
-    "yx_simota_assign": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "yx_simota_workspace_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "yx_simota_assign": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "yx_simota_matching": (C.c_int, [_P, _P, _I32, _I32, _I64, _P, _P, _P, _P]),
     "yx_head_losses": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P]),
     "yx_plan_create": (_P, []),

@@ -13,7 +13,8 @@ __all__ = ["postprocess", "bboxes_iou", "NMS_VARIANTS"]
 NMS_VARIANTS = {
     "offset": _lib.NMS_OFFSET,        # torchvision _batched_nms_coordinate_trick
     "per_class": _lib.NMS_PER_CLASS,  # torchvision _batched_nms_vanilla
-    "auto": 3,                        # what torchvision picks on CUDA (<= 100000 coordinates -> offset)
+    "auto": 3,                        # what the installed torchvision (>= 0.19) picks on CUDA (<= 100000 coordinates -> offset)
+    "auto_tv017": 5,                  # what torchvision 0.17.2 (the reference's pin) picks on CUDA (<= 20000 coordinates -> offset)
     "auto_cpu": 4,                    # what torchvision picks on CPU  (<= 4000 coordinates -> offset)
 }
 

@@ -43,11 +43,11 @@ int filter_compact_launch(const float* pred, int batch, int anchors, int nc, flo
 int batched_nms_launch(const float* boxes, const float* scores, const int* cls, const int* counts, int batch,
                        int n_max, double nms_thre, int nms_variant, int* keep, int* keep_count, void* ws,
                        long long ws_bytes, cudaStream_t s);
-long long simota_ws_bytes(int batch, int anchors, int max_gt);
+long long simota_ws_bytes(int batch, int anchors, int max_gt, int levels);
 int simota_assign_launch(const float* pred, const float* labels, const float* xs, const float* ys, const float* st,
-                         int batch, int anchors, int nc, int max_gt, unsigned char* fg_mask, int* matched_gt,
-                         float* matched_iou, int* matched_cls, int* num_fg, int* num_gt, void* ws, long long ws_bytes,
-                         cudaStream_t s);
+                         int batch, int anchors, int nc, int max_gt, int levels, unsigned char* fg_mask, int* matched_gt,
+                         float* matched_iou, int* matched_cls, int* num_fg, int* num_gt, int* status, void* ws,
+                         long long ws_bytes, cudaStream_t s);
 int simota_matching_launch(const float* cost, const float* ious, int G, int n, long long ld, int* match_gt,
                            float* match_iou, int* num_fg, cudaStream_t s);
 struct StemLaunch;
@@ -82,7 +82,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 int num_sms() {
-  static int cached = 0;
+  static int cached_dev[kMaxDevices] = {};     // per device: one process may drive several GPUs
+  int& cached = cached_dev[current_device_slot()];
   if (!cached) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&
@@ -104,7 +105,8 @@ bool pdl_enabled() {
 }
 
 static int require_device() {
-  static int ok = 0;
+  static int ok_dev[kMaxDevices] = {};         // checked once per device, not once per process
+  int& ok = ok_dev[current_device_slot()];
   if (ok) return YX_OK;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -346,19 +348,20 @@ int yx_bboxes_iou(const float* a, int32_t n, const float* b, int32_t m, int32_t 
   return iou_launch(a, n, b, m, xyxy, out, (cudaStream_t)stream);
 }
 
-int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt) {
-  return simota_ws_bytes(batch, anchors, max_gt);
+int64_t yx_simota_workspace_bytes(int32_t batch, int32_t anchors, int32_t max_gt, int32_t levels) {
+  return simota_ws_bytes(batch, anchors, max_gt, levels);
 }
 
 int yx_simota_assign(const float* pred, const float* labels, const float* x_shift, const float* y_shift,
                      const float* stride_per_anchor, int32_t batch, int32_t anchors, int32_t nc, int32_t max_gt,
-                     uint8_t* fg_mask, int32_t* matched_gt, float* matched_iou, int32_t* matched_cls, int32_t* num_fg,
-                     int32_t* num_gt, void* workspace, int64_t workspace_bytes, void* stream) {
+                     int32_t levels, uint8_t* fg_mask, int32_t* matched_gt, float* matched_iou, int32_t* matched_cls,
+                     int32_t* num_fg, int32_t* num_gt, int32_t* status, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
   int rc = require_device();
   if (rc) return rc;
-  return simota_assign_launch(pred, labels, x_shift, y_shift, stride_per_anchor, batch, anchors, nc, max_gt, fg_mask,
-                              matched_gt, matched_iou, matched_cls, num_fg, num_gt, workspace, workspace_bytes,
-                              (cudaStream_t)stream);
+  return simota_assign_launch(pred, labels, x_shift, y_shift, stride_per_anchor, batch, anchors, nc, max_gt, levels,
+                              fg_mask, matched_gt, matched_iou, matched_cls, num_fg, num_gt, status, workspace,
+                              workspace_bytes, (cudaStream_t)stream);
 }
 
 int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int32_t n, int64_t ld,

@@ -235,10 +235,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   if (tid == 0) s_nkept = 0;
   long long tk[8];
   tk[0] = clock64();
-  // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA) / 4000 (CPU)
+  // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA, torchvision >= 0.19; the installed
+  // 0.26 the goldens were generated with) / 4000 (CPU) / 20000 (CUDA, torchvision 0.17.2 = the reference's poetry.lock pin)
   int variant = g.variant;
   if (variant == 3) variant = (4LL * n > 100000) ? 1 : 0;
   if (variant == 4) variant = (4LL * n > 4000) ? 1 : 0;
+  if (variant == 5) variant = (4LL * n > 20000) ? 1 : 0;     // torchvision 0.17.2 (the reference's pin) on CUDA
 
   if (n > 0) {
     // ---------------- sort ----------------
@@ -608,7 +610,7 @@ int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_t
                        long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(pred && dets && det_count && ws, YX_ERR_INVALID_ARG, "postprocess: null pointer");
   YX_REQUIRE(batch > 0 && anchors > 0 && nc > 0 && max_det > 0, YX_ERR_INVALID_ARG, "postprocess: bad sizes");
-  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "postprocess: nms_variant must be 0..4");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 5, YX_ERR_INVALID_ARG, "postprocess: nms_variant must be 0..5");
   YX_REQUIRE(((uintptr_t)ws & 255) == 0, YX_ERR_INVALID_ARG, "postprocess: workspace must be 256-byte aligned");
   PostWs w = carve_ws(ws, batch, anchors);
   YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "postprocess: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
@@ -650,7 +652,7 @@ int nms_prefiltered_launch(int batch, int anchors, double nms_thre, int nms_vari
                            int* det_count, int max_det, void* ws, long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(dets && det_count && ws, YX_ERR_INVALID_ARG, "nms_prefiltered: null pointer");
   YX_REQUIRE(batch > 0 && anchors > 0 && max_det > 0, YX_ERR_INVALID_ARG, "nms_prefiltered: bad sizes");
-  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "nms_prefiltered: nms_variant must be 0..4");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 5, YX_ERR_INVALID_ARG, "nms_prefiltered: nms_variant must be 0..5");
   YX_REQUIRE(((uintptr_t)ws & 255) == 0, YX_ERR_INVALID_ARG, "nms_prefiltered: workspace must be 256-byte aligned");
   PostWs w = carve_ws(ws, batch, anchors);
   YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "nms_prefiltered: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
@@ -686,7 +688,7 @@ int batched_nms_launch(const float* boxes, const float* scores, const int* cls, 
                        long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(boxes && scores && cls && counts && keep && keep_count && ws, YX_ERR_INVALID_ARG, "nms: null pointer");
   YX_REQUIRE(batch > 0 && n_max > 0, YX_ERR_INVALID_ARG, "nms: bad sizes");
-  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 4, YX_ERR_INVALID_ARG, "nms: nms_variant must be 0..4");
+  YX_REQUIRE(nms_variant >= 0 && nms_variant <= 5, YX_ERR_INVALID_ARG, "nms: nms_variant must be 0..5");
   PostWs w = carve_ws(ws, batch, n_max);
   YX_REQUIRE((long long)w.total <= ws_bytes, YX_ERR_CAPACITY, "nms: workspace %lld < %lld bytes", ws_bytes, (long long)w.total);
   NmsArgs g;

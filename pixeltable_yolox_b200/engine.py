@@ -105,6 +105,12 @@ class Builder:
             lib().yx_plan_destroy(self.plan)
             self.plan = None
 
+    def __deepcopy__(self, memo):
+        raise TypeError("Builder owns a native plan (raw pointers into its buffers) and cannot be copied; build a new one")
+
+    def __reduce__(self):
+        raise TypeError("Builder owns a native plan (raw pointers into its buffers) and cannot be pickled")
+
     # ---------------------------------------------------------------- independent branches (graph lanes)
     def _wrote(self, feat: Optional["Feat"]) -> None:
         if feat is not None and self.plan is not None and self._lane == 0:
@@ -613,3 +619,10 @@ class InferenceEngine:
 
     def close(self):
         self.builder.close()
+
+    def __deepcopy__(self, memo):
+        raise TypeError("InferenceEngine is bound to one module's weights and buffers and cannot be copied "
+                        "(YoloxModule drops its engine cache on deepcopy / pickle)")
+
+    def __reduce__(self):
+        raise TypeError("InferenceEngine cannot be pickled (YoloxModule drops its engine cache on deepcopy / pickle)")

@@ -15,6 +15,20 @@ from . import _lib
 from ._lib import ConvDesc, check, dtype_code, lib, require_cuda, stream_ptr
 
 
+def same_device(dev: torch.device, what: str, **tensors) -> None:
+    """Every tensor whose raw pointer crosses the C-ABI must live on `dev`: a CPU tensor or a tensor of another GPU
+    would be an illegal-address fault (sticky CUDA error) instead of the reference's clean device-mismatch error."""
+    for name, t in tensors.items():
+        if t is not None and t.device != dev:
+            raise RuntimeError(f"{what}: `{name}` is on {t.device} but the call runs on {dev}; move it there first "
+                               "(the B200 path has no CPU fallback and no implicit peer access)")
+
+
+def on_device(dev: torch.device):
+    """Make `dev` the current CUDA device for the FFI call (the library launches on the current device)."""
+    return torch.cuda.device(dev)
+
+
 @dataclass
 class View:
     """A channel slice [c_off, c_off + c) of an NHWC buffer ``t`` of shape [B, H, W, Ctot]."""
@@ -115,8 +129,11 @@ def conv_bn_act(x: View, w, bias, out, ksize, stride, act, res=None, ups=None, h
                 out2=None, out2_begin=0) -> None:
     require_cuda(x.t, "conv_bn_act")
     d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head, out2, out2_begin)
+    same_device(x.t.device, "conv_bn_act", w=w, bias=bias, out=None if out is None else out.t,
+                res=None if res is None else res.t, ups=None if ups is None else ups.t, out2=None if out2 is None else out2.t)
     fn = lib().yx_conv_bn_act_fwd_simt if simt else lib().yx_conv_bn_act_fwd
-    check(fn(C.byref(d), stream_ptr(x.t.device)), "conv_bn_act")
+    with on_device(x.t.device):
+        check(fn(C.byref(d), stream_ptr(x.t.device)), "conv_bn_act")
 
 
 def pack_weights(
@@ -223,9 +240,10 @@ def postprocess_device(pred: torch.Tensor, num_classes: int, conf_thre: float, n
         return dets, det_idx, det_count
     nbytes = lib().yx_postprocess_workspace_bytes(B, A)
     ws = _workspace(dev, nbytes, "post")
-    check(lib().yx_postprocess(pred.data_ptr(), B, A, num_classes, float(conf_thre), float(nms_thre), int(nms_variant),
-                               1 if inplace_xyxy else 0, dets.data_ptr(), det_idx.data_ptr(), det_count.data_ptr(),
-                               max_det, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "postprocess")
+    with on_device(dev):
+        check(lib().yx_postprocess(pred.data_ptr(), B, A, num_classes, float(conf_thre), float(nms_thre), int(nms_variant),
+                                   1 if inplace_xyxy else 0, dets.data_ptr(), det_idx.data_ptr(), det_count.data_ptr(),
+                                   max_det, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "postprocess")
     return dets, det_idx, det_count
 
 
@@ -276,23 +294,27 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, cls: torch.Tensor, co
     require_cuda(boxes, "batched_nms")
     B, n, _ = boxes.shape
     dev = boxes.device
+    same_device(dev, "batched_nms", scores=scores, cls=cls, counts=counts)
     boxes = boxes.contiguous().float(); scores = scores.contiguous().float()
     cls = cls.contiguous().to(torch.int32); counts = counts.contiguous().to(torch.int32)
     keep = torch.full((B, n), -1, dtype=torch.int32, device=dev)
     keep_count = torch.zeros((B,), dtype=torch.int32, device=dev)
     ws = _workspace(dev, lib().yx_postprocess_workspace_bytes(B, n), "post")
-    check(lib().yx_batched_nms(boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), counts.data_ptr(), B, n,
-                               float(nms_thre), int(nms_variant), keep.data_ptr(), keep_count.data_ptr(),
-                               ws.data_ptr(), ws.numel(), stream_ptr(dev)), "batched_nms")
+    with on_device(dev):
+        check(lib().yx_batched_nms(boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), counts.data_ptr(), B, n,
+                                   float(nms_thre), int(nms_variant), keep.data_ptr(), keep_count.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), stream_ptr(dev)), "batched_nms")
     return keep, keep_count
 
 
 def bboxes_iou_device(a: torch.Tensor, b: torch.Tensor, xyxy: bool) -> torch.Tensor:
     require_cuda(a, "bboxes_iou")
+    same_device(a.device, "bboxes_iou", bboxes_b=b)
     a = a.contiguous().float(); b = b.contiguous().float()
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
-    check(lib().yx_bboxes_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], 1 if xyxy else 0, out.data_ptr(),
-                              stream_ptr(a.device)), "bboxes_iou")
+    with on_device(a.device):
+        check(lib().yx_bboxes_iou(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], 1 if xyxy else 0, out.data_ptr(),
+                                  stream_ptr(a.device)), "bboxes_iou")
     return out
 
 
@@ -303,6 +325,7 @@ def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tens
                   strides: torch.Tensor, num_classes: int):
     """Batched get_assignments. Returns dict of dense per-anchor tensors (see include/yx_b200.h)."""
     require_cuda(pred, "simota_assign")
+    same_device(pred.device, "simota_assign", labels=labels, x_shifts=x_shifts, y_shifts=y_shifts, strides=strides)
     pred = pred.contiguous().float(); labels = labels.contiguous().float()
     B, A, nch = pred.shape
     assert nch == 5 + num_classes and labels.shape[0] == B and labels.shape[2] == 5
@@ -318,12 +341,22 @@ def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tens
         "matched_cls": torch.empty((B, A), dtype=torch.int32, device=dev),
         "num_fg": torch.empty((B,), dtype=torch.int32, device=dev),
         "num_gt": torch.empty((B,), dtype=torch.int32, device=dev),
+        # 0 | YX_SIMOTA_CAPACITY (1) | YX_SIMOTA_BAD_CLASS (2), written by the kernel (no host sync here; callers that
+        # already synchronise, e.g. YoloxHead.get_assignments, raise on it)
+        "status": torch.zeros((B,), dtype=torch.int32, device=dev),
     }
-    ws = _workspace(dev, lib().yx_simota_workspace_bytes(B, A, max_gt), "simota")
-    check(lib().yx_simota_assign(pred.data_ptr(), labels.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), B, A,
-                                 num_classes, max_gt, out["fg_mask"].data_ptr(), out["matched_gt"].data_ptr(),
-                                 out["matched_iou"].data_ptr(), out["matched_cls"].data_ptr(), out["num_fg"].data_ptr(),
-                                 out["num_gt"].data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "simota_assign")
+    if B == 0 or max_gt == 0:
+        # the reference accepts any padding length, including none: every anchor is background
+        out["fg_mask"].zero_(); out["matched_gt"].fill_(-1); out["matched_iou"].zero_(); out["matched_cls"].fill_(-1)
+        out["num_fg"].zero_(); out["num_gt"].zero_()
+        return out
+    levels = int(torch.unique(st).numel()) if A > 0 else 1
+    ws = _workspace(dev, lib().yx_simota_workspace_bytes(B, A, max_gt, levels), "simota")
+    with on_device(dev):
+        check(lib().yx_simota_assign(pred.data_ptr(), labels.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), B, A,
+                                     num_classes, max_gt, levels, out["fg_mask"].data_ptr(), out["matched_gt"].data_ptr(),
+                                     out["matched_iou"].data_ptr(), out["matched_cls"].data_ptr(), out["num_fg"].data_ptr(),
+                                     out["num_gt"].data_ptr(), out["status"].data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "simota_assign")
     return out
 
 
@@ -337,6 +370,8 @@ def head_losses(pred: torch.Tensor, labels: torch.Tensor, asg: dict, origin: Opt
     assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
     B, A, nch = pred.shape
     dev = pred.device
+    same_device(dev, "head_losses", labels=labels, origin=origin, x_shifts=x_shifts, y_shifts=y_shifts, strides=strides,
+                **{f"asg[{k}]": v for k, v in asg.items() if k in ("fg_mask", "matched_gt", "matched_iou", "matched_cls")})
     labels = labels.contiguous().float()
     sums = torch.empty((4,), dtype=torch.float64, device=dev)
     grad = torch.empty_like(pred)
@@ -349,16 +384,18 @@ def head_losses(pred: torch.Tensor, labels: torch.Tensor, asg: dict, origin: Opt
         assert origin.shape == (B, A, 4) and xs.numel() == A and ys.numel() == A and st.numel() == A
         g_or = torch.empty_like(origin)
         o_ptr, xs_ptr, ys_ptr, st_ptr, go_ptr = origin.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), g_or.data_ptr()
-    check(lib().yx_head_losses(pred.data_ptr(), labels.data_ptr(), labels.shape[1], asg["fg_mask"].data_ptr(),
-                               asg["matched_gt"].data_ptr(), asg["matched_iou"].data_ptr(), asg["matched_cls"].data_ptr(),
-                               o_ptr, xs_ptr, ys_ptr, st_ptr, B, A, nch - 5, 1 if giou else 0, float(reg_weight),
-                               sums.data_ptr(), grad.data_ptr(), go_ptr, stream_ptr(dev)), "head_losses")
+    with on_device(dev):
+        check(lib().yx_head_losses(pred.data_ptr(), labels.data_ptr(), labels.shape[1], asg["fg_mask"].data_ptr(),
+                                   asg["matched_gt"].data_ptr(), asg["matched_iou"].data_ptr(), asg["matched_cls"].data_ptr(),
+                                   o_ptr, xs_ptr, ys_ptr, st_ptr, B, A, nch - 5, 1 if giou else 0, float(reg_weight),
+                                   sums.data_ptr(), grad.data_ptr(), go_ptr, stream_ptr(dev)), "head_losses")
     return sums, grad, g_or
 
 
 def simota_matching_device(cost: torch.Tensor, ious: torch.Tensor):
     """simota_matching on a [G, n] cost / IoU pair. Returns (match_gt [n] int32, match_iou [n], num_fg [1])."""
     require_cuda(cost, "simota_matching")
+    same_device(cost.device, "simota_matching", ious=ious)
     cost = cost.contiguous().float(); ious = ious.contiguous().float()
     G, n = cost.shape
     dev = cost.device

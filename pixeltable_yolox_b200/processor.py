@@ -54,6 +54,16 @@ class YoloxProcessor:
     def postprocess(self, images: Iterable, tensor: torch.Tensor, threshold: float = 0.5) -> list:
         outputs = boxes.postprocess(tensor, self.config.num_classes, threshold, self.config.nmsthre,
                                     class_agnostic=False, nms_variant=self.nms_variant)
+        return self._format(images, outputs)
+
+    def format_detections(self, images: Iterable, dets: torch.Tensor, counts: torch.Tensor) -> list:
+        """Detections of YoloxModule.detect() ([B, max_det, 7] rows + per-image counts) in the reference's result
+        format (processor.py:46-59): one device->host copy for the whole batch."""
+        n = counts.cpu().tolist()
+        rows = dets[:, :max(max(n), 1)].cpu() if len(n) else dets.cpu()
+        return self._format(images, [rows[i, :k] if k > 0 else None for i, k in enumerate(n)])
+
+    def _format(self, images: Iterable, outputs) -> list:
         results = []
         for i, image in enumerate(images):
             ratio = min(self.config.test_size[0] / image.height, self.config.test_size[1] / image.width)

@@ -236,6 +236,12 @@ class YoloxHead(_B200Block):
         lab = torch.zeros((1, pad, 5), dtype=torch.float32, device=pred.device)
         lab[0, :num_gt] = labels
         asg = ops.simota_assign(pred, lab, x_shifts, y_shifts, expanded_strides, self.num_classes)
+        status = int(asg["status"][0].item())          # this reference-shaped entry point synchronises anyway (num_fg below)
+        if status == 2:
+            raise RuntimeError("get_assignments: class values must be smaller than num_classes and non-negative")
+        if status == 1:
+            raise RuntimeError("get_assignments: more in-centre anchors than 9 per stride level and GT "
+                               "(the anchor grid is not one unit-spaced grid per level)")
         fg_mask = asg["fg_mask"][0].bool()
         matched_gt_inds = asg["matched_gt"][0][fg_mask].long()
         gt_matched_classes = gt_classes[matched_gt_inds]

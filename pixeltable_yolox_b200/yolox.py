@@ -40,8 +40,15 @@ class Yolox:
         images = [im if isinstance(im, Image.Image) else Image.open(im) for im in inputs]
         tensor = self.processor(images)
         dev = next(self.module.parameters()).device
-        output = self.module(tensor.to(dev))
-        return self.processor.postprocess(images, output, threshold=threshold)
+        if self.module.training or not self.module.head.decode_in_inference:
+            output = self.module(tensor.to(dev))
+            return self.processor.postprocess(images, output, threshold=threshold)
+        # eval: forward + decode + score filter + NMS as ONE captured graph (detect()); identical rows to
+        # module(tensor) followed by processor.postprocess (tests/test_gpu_named_configs.py), without the
+        # [B, A, 5+nc] prediction tensor ever leaving the engine
+        dets, _, counts = self.module.detect(tensor.to(dev), conf_thre=threshold, nms_thre=self.processor.config.nmsthre,
+                                             nms_variant=self.processor.nms_variant)
+        return self.processor.format_detections(images, dets, counts)
 
 
 class YoloxModule(nn.Module):
@@ -53,14 +60,45 @@ class YoloxModule(nn.Module):
         self.backbone = backbone if backbone is not None else YoloPafpn()
         self.head = head if head is not None else YoloxHead(80)
         self._engines = {}
+        self._fingerprint = None
         self.micro_batch = 64       # images per pass (see engine.InferenceEngine)
         self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ engine cache
+    # An engine holds raw pointers (native plan, packed weights, activation buffers): it belongs to exactly one module
+    # object and is never copied or pickled with it. Contract: weights are BN-folded and packed when an engine is built;
+    # every eval call compares a fingerprint of all parameters and buffers (storage pointer + in-place version counter,
+    # BN eps, head strides / class count) and rebuilds when it changed, so load_state_dict on a sub-module,
+    # initialize_biases(), param.data.copy_() or .half() are all picked up. Not detected: writes that bypass the
+    # version counter (raw CUDA kernels, .data_ptr() writes from outside torch); call invalidate_engine() after those.
     def invalidate_engine(self):
         for e in self._engines.values():
             e.close()
         self._engines = {}
+        self._fingerprint = None
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        import copy
+
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_engines" else (None if k == "_fingerprint" else copy.deepcopy(v, memo))
+        return new
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engines"] = {}
+        state["_fingerprint"] = None
+        return state
+
+    def _weights_fingerprint(self):
+        fp = [(t.data_ptr(), t._version) for t in self.parameters()]
+        fp += [(t.data_ptr(), t._version) for t in self.buffers()]
+        fp += [m.eps for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+        fp += [tuple(self.head.strides), self.head.num_classes]
+        return fp
 
     def train(self, mode: bool = True):
         self.invalidate_engine()
@@ -80,6 +118,11 @@ class YoloxModule(nn.Module):
         from .engine import InferenceEngine
 
         dev = next(self.parameters()).device
+        fp = self._weights_fingerprint()
+        if fp != self._fingerprint:
+            if self._engines:
+                self.invalidate_engine()
+            self._fingerprint = fp
         key = (tuple(x.shape), x.dtype, dev, self.head.decode_in_inference, self.micro_batch, self.use_cuda_graph,
                tuple(sorted((k, v) for k, v in post.items() if v is not None)) if post else None, slot)
         eng = self._engines.get(key)

@@ -173,3 +173,35 @@ def test_training_step_runs_and_backpropagates(cuda):
     out["total_loss"].backward()
     g = model.head.cls_preds[0].weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_engine_cache_survives_deepcopy_and_weight_changes(cuda):
+    """The engine (native plan + packed weights) belongs to one module object: a deep copy / pickle gets none of it and
+    builds its own; any weight change while in eval (sub-module load_state_dict, in-place copy_, initialize_biases) is
+    picked up by the parameter fingerprint instead of silently serving the old packed weights."""
+    import copy
+    import io
+
+    model, sd, x = _build("w25_d33_64")
+    model = model.to(cuda).bfloat16().eval()
+    xd = x.to(cuda)
+    base = model(xd).clone()
+    twin = copy.deepcopy(model)
+    assert twin._engines == {} and len(model._engines) == 1
+    assert torch.equal(twin(xd), base) and torch.equal(model(xd), base)
+    with torch.no_grad():                                    # change the twin only
+        twin.head.cls_preds[0].bias.add_(1.0)
+    changed = twin(xd)
+    assert not torch.equal(changed, base) and torch.equal(model(xd), base)
+    twin.invalidate_engine()                                 # frees the twin's plan only
+    assert torch.equal(model(xd), base)
+    buf = io.BytesIO(); torch.save(model, buf); buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    assert loaded._engines == {} and torch.equal(loaded(xd), base)
+    # sub-module load_state_dict and initialize_biases while in eval
+    model.head.load_state_dict(twin.head.state_dict())
+    assert torch.equal(model(xd), changed)
+    model.head.initialize_biases(0.5)
+    assert not torch.equal(model(xd), changed)
+    with pytest.raises(TypeError):
+        copy.deepcopy(next(iter(model._engines.values())))

@@ -54,6 +54,19 @@ def test_auto_variant_follows_torchvision_cuda_rule(cuda):
     _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.3, 0.65), want)
 
 
+def test_auto_tv017_variant_follows_the_pinned_torchvision_rule(cuda):
+    """torchvision 0.17.2 (poetry.lock pin of the reference) switches to per-class NMS above 20 000 box coordinates on
+    CUDA; the installed 0.26 (which generated the goldens) above 100 000. Image 0 has > 5 000 candidates, image 1 fewer."""
+    pred = syn.dense_scene(2, anchors=8400, seed=43)
+    pred[1, 3000:, 4] = 0.0                                     # < 5 000 candidates -> offset trick under both rules
+    per_class, _ = po.postprocess(pred.copy(), 80, 0.05, 0.65, variant="per_class", return_indices=True)
+    offset, _ = po.postprocess(pred.copy(), 80, 0.05, 0.65, variant="offset", return_indices=True)
+    oracle, _ = po.postprocess(pred.copy(), 80, 0.05, 0.65, variant="auto_tv017", return_indices=True)
+    got = yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.05, 0.65, nms_variant="auto_tv017")
+    _check_lists(got, [per_class[0], offset[1]])
+    _check_lists(got, oracle)
+
+
 def test_large_anchor_count_takes_global_sort_path(cuda):
     """A > 16384 candidates: keys no longer fit shared memory."""
     pred = syn.dense_scene(1, anchors=20000, seed=42, clusters=150, size=1280.0)

@@ -91,3 +91,54 @@ def test_get_assignments_reference_signature(cuda):
     assert minds.dtype == torch.int64
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         head.get_assignments(b, G, None, None, None, None, None, None, None, None, mode="cpu")
+
+
+def _assign(cuda, pred, lab, xs, ys, st):
+    d = lambda a: torch.from_numpy(a).to(cuda)
+    return ops.simota_assign(d(pred), d(lab), d(xs), d(ys), d(st), 80)
+
+
+@pytest.mark.parametrize("batch", [1, 8, 40, 300])
+def test_simota_assign_cluster_sizes_agree(cuda, batch):
+    """The cluster size (8 / 4 / 2 / 1 CTAs per image) follows the batch; every image must get the assignment the
+    oracle computes whatever the split of anchors, candidate tiles and GT rows over the CTAs."""
+    hw = [(40, 40), (20, 20), (10, 10)]
+    counts = [(7 * i) % 31 for i in range(batch)]
+    lab = syn.labels(batch, max_gt=40, seed=61, size=320.0, counts=counts)
+    pred = syn.train_head_output(batch, hw, cases.STRIDES, lab, seed=62)
+    xs, ys, st = so.anchor_grid(hw, cases.STRIDES)
+    out = _assign(cuda, pred, lab, xs, ys, st)
+    fg = out["fg_mask"].cpu().numpy().astype(bool); mgt = out["matched_gt"].cpu().numpy()
+    assert out["num_gt"].cpu().tolist() == counts and not out["status"].any()
+    assert out["num_fg"].cpu().tolist() == fg.sum(1).tolist()
+    for b in range(0, batch, max(1, batch // 8)):
+        o_fg, o_mgt, o_iou, _ = so.get_assignments(pred[b], lab[b][:counts[b]], 80, st, xs, ys)
+        assert (o_fg == fg[b]).mean() >= 0.999
+        both = o_fg & fg[b]
+        assert (o_mgt[both] == mgt[b][both]).mean() >= 0.995 if both.any() else True
+        cls = out["matched_cls"][b].cpu().numpy()
+        assert (cls[fg[b]] == lab[b][mgt[b][fg[b]], 0].astype(np.int32)).all() and (cls[~fg[b]] == -1).all()
+
+
+def test_simota_assign_label_padding_and_levels(cuda):
+    """Any padding length (the reference pads to 120 but accepts every length, also none), more than 128 label rows,
+    a four-level head; bad class ids are flagged instead of read out of bounds."""
+    hw = [(40, 40), (20, 20), (10, 10), (5, 5)]
+    strides = (8, 16, 32, 64)
+    xs, ys, st = so.anchor_grid(hw, strides)
+    lab = syn.labels(2, max_gt=200, seed=71, size=320.0, counts=[150, 9])
+    pred = syn.train_head_output(2, hw, strides, lab, seed=72)
+    out = _assign(cuda, pred, lab, xs, ys, st)
+    assert out["num_gt"].cpu().tolist() == [150, 9] and not out["status"].any()
+    for b, G in enumerate([150, 9]):
+        o_fg, o_mgt, _, _ = so.get_assignments(pred[b], lab[b][:G], 80, st, xs, ys)
+        assert (o_fg == out["fg_mask"][b].cpu().numpy().astype(bool)).mean() >= 0.998
+    # no label rows at all: everything is background, no launch
+    empty = ops.simota_assign(torch.from_numpy(pred).to(cuda), torch.zeros((2, 0, 5), device=cuda), torch.from_numpy(xs).to(cuda),
+                              torch.from_numpy(ys).to(cuda), torch.from_numpy(st).to(cuda), 80)
+    assert not empty["fg_mask"].any() and not empty["num_fg"].any()
+    bad = lab.copy(); bad[1, 3, 0] = 80.0
+    assert _assign(cuda, pred, bad, xs, ys, st)["status"].cpu().tolist() == [0, 2]
+    with pytest.raises(RuntimeError, match="is on cpu"):
+        ops.simota_assign(torch.from_numpy(pred).to(cuda), torch.from_numpy(lab), torch.from_numpy(xs).to(cuda),
+                          torch.from_numpy(ys).to(cuda), torch.from_numpy(st).to(cuda), 80)

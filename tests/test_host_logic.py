@@ -106,3 +106,20 @@ def test_two_rank_batch_sharding_gloo():
         p.join(timeout=60)
     for rank, counts, total in res:
         assert counts == [i * i for i in range(13)] and total == 13
+
+
+def test_set_match_comparator():
+    """The IoU >= 0.99 one-to-one comparator of the north_star gate (used by tests/test_gpu_named_configs.py)."""
+    from test_gpu_named_configs import match_sets
+
+    a = np.array([[10, 10, 110, 110, .9, .9, 3], [200, 200, 300, 320, .8, .9, 5], [10, 10, 110, 110, .7, .9, 4]], dtype=np.float32)
+    b = a.copy()
+    assert match_sets([a], [b]) == 3
+    b[0, :4] += 0.2                          # IoU ~0.992: still a match; 2 px shift is not
+    assert match_sets([a], [b]) == 3
+    b[1, :4] += 2.0
+    assert match_sets([a], [b]) == 2
+    b[2, 6] = 7                              # label differs
+    assert match_sets([a], [b]) == 1
+    assert match_sets([a, None], [b, a]) == 1 and match_sets([a], [None]) == 0
+    assert match_sets([a], [np.concatenate([a, a])]) == 3          # one-to-one: duplicates do not count twice

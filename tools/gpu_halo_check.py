@@ -1,6 +1,6 @@
 """GPU diagnostic (not a pytest): halo-mode 3x3 convs against torch for both UMMA base-offset
 conventions, then timings of the yolox_s 3x3 shapes with halo on/off.
-usage: python tests/gpu_halo_check.py <baseoff><bres> | time [baseoff]"""
+usage: python tools/gpu_halo_check.py <baseoff><bres> | time [baseoff]"""
 import os
 import sys
 from pathlib import Path

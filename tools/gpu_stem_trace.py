@@ -1,4 +1,4 @@
-"""YX_STEM_DEBUG=2 trace of the stem kernel (one eager launch). usage: YX_STEM_DEBUG=2 python tests/gpu_stem_trace.py"""
+"""YX_STEM_DEBUG=2 trace of the stem kernel (one eager launch). usage: YX_STEM_DEBUG=2 python tools/gpu_stem_trace.py"""
 import sys
 from pathlib import Path
 

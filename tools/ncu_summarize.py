@@ -1,9 +1,9 @@
 """Turn ncu CSV dumps into the committed summaries under profiles/.
 
-  python tests/ncu_summarize.py launches <launches.csv> <out.md> [steps]
+  python tools/ncu_summarize.py launches <launches.csv> <out.md> [steps]
       per-kernel launch count / total / share from `ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --csv`
       (+ profiles/<stem>_traffic.json with the conv kernel's average DRAM bytes per launch when present)
-  python tests/ncu_summarize.py full <raw.csv> <out.md>
+  python tools/ncu_summarize.py full <raw.csv> <out.md>
       key metrics of one `ncu --set full` capture (`ncu -i rep --page raw --csv`)
 """
 import collections

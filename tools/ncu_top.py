@@ -1,5 +1,5 @@
 """Read an `ncu --page source --csv` dump and print the instructions with the most stall samples.
-usage: ncu -i rep --page source --csv > src.csv; python tests/ncu_top.py src.csv [N]"""
+usage: ncu -i rep --page source --csv > src.csv; python tools/ncu_top.py src.csv [N]"""
 import csv
 import sys
 
