@@ -13,8 +13,16 @@ per GPU (weak scaling: the batch is sharded by image, no data-path collective).
               (e2e_fp32_input: the same with the fp32 host tensor the reference's processor produces)
   roofline  : the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs / its device
               time, measured live with CUDA events around every launch of an eager pass
-  cpu_baseline / --impl reference : the CPU restatement of the reference path (oracle/, torch CPU ops +
-              numpy/C NMS) on the host cores, on a bounded sample of the same workload
+  cpu_baseline : the CPU restatement of the reference path (oracle/, torch CPU ops + numpy/C NMS) on the host cores,
+              on a bounded sample of the same workload (rank 0, N = 1 only)
+  --impl reference : the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.py) on the host cores:
+              YoloxModule.forward + yolox.utils.postprocess, fp32, all threads (falls back to the oracle port if
+              baseline/_ref is missing)
+  extra     : conf 0.01 leg (the evaluator's threshold), dense NMS stress (config 5), per-family HBM rooflines, the
+              same-box torch GPU reference (unmodified reference module in bf16 on cuDNN + torchvision NMS)
+  --train   : config 4, one training step (fwd-train + SimOTA + losses + backward + gradient all-reduce + SGD)
+  --global-batch G : strong scaling, G images per step split over the ranks (config 3: --model yolox_l --dtype fp16
+              --global-batch 512)
 """
 from __future__ import annotations
 
@@ -51,6 +59,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=16)
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op table of the eager pass")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: images per step over ALL ranks")
+    ap.add_argument("--train", action="store_true", help="config 4: training step (8 images per rank by default)")
+    ap.add_argument("--train-batch", type=int, default=8, help="--train: images per rank")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (conf 0.01, config 5, torch GPU reference)")
     return ap.parse_args()
 
 
@@ -187,12 +199,57 @@ def cpu_reference_rate(args, sd, images_np, seconds_cap=25.0):
 
 def workload_name(args) -> str:
     """The same string in both arms (ours / --impl reference): the BASELINE.json configuration being measured."""
+    if args.train:
+        return (f"{args.model} {args.size}x{args.size} training step, {args.train_batch} images/GPU (fwd-train + SimOTA + losses + "
+                "backward + gradient all-reduce + SGD), config[3] of BASELINE.json")
+    if args.global_batch:
+        return (f"{args.model} {args.size}x{args.size} global batch-{args.global_batch} {args.dtype} inference (fwd+decode+NMS) "
+                "sharded by image over the ranks, config[2] of BASELINE.json")
     return (f"{args.model} {args.size}x{args.size} batch-{args.batch}/GPU {args.dtype} inference (fwd+decode+NMS), "
             "config[1] of BASELINE.json")
 
 
+def reference_modules():
+    """The unmodified reference from baseline/_ref (baseline/install_ref.py), or None. pycocotools is the one import this
+    image cannot satisfy (yolox/data/datasets/coco.py:7, dataset / evaluator only): stubbed, never called on the path."""
+    import types
+
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "yolox").is_dir():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    for name, attrs in {"pycocotools": [], "pycocotools.coco": ["COCO"], "pycocotools.cocoeval": ["COCOeval"],
+                        "pycocotools.mask": []}.items():
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            for a in attrs:
+                setattr(mod, a, type(a, (), {}))
+            sys.modules[name] = mod
+    try:
+        from yolox.config import YoloxConfig
+        from yolox.utils import postprocess
+    except Exception as e:                      # noqa: BLE001 - report, never crash the bench
+        print(f"# reference import failed: {e!r}", file=sys.stderr)
+        return None
+    return dict(YoloxConfig=YoloxConfig, postprocess=postprocess)
+
+
+def reference_model(ref, name: str, sd, device, dtype=None):
+    """A fresh instance of the reference's own module for a named config, carrying OUR arm's weights."""
+    cfg = ref["YoloxConfig"].get_named_config(name)
+    cfg.model = None                             # get_model() caches the module on the singleton config (config.py:168-172)
+    m = cfg.get_model()
+    m.load_state_dict(sd)
+    m = m.to(device)
+    if dtype is not None:
+        m = m.to(dtype)
+    return m.eval()
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    import numpy as np
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -200,42 +257,248 @@ def run_reference(args):
         return
     from pixeltable_yolox_b200 import synthetic as syn
 
-    _, model = build_model(args, torch.device("cpu"))
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    per_step = max(1, min(args.cpu_images, 8))
-    imgs = syn.images(per_step, args.size, args.size, seed=7)
-    import numpy as np
-
-    from oracle import postprocess_oracle as po
-    from oracle import yolox_oracle as yo
-
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    x = torch.from_numpy(imgs)
+    if args.train:
+        return run_reference_train(args, threads)
+    _, model = build_model(args, torch.device("cpu"))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = reference_modules()
+    B = args.batch if not args.global_batch else args.global_batch
+    if ref is not None:
+        kind = "reference"
+        how = "unmodified reference (baseline/_ref): YoloxModule.forward + yolox.utils.postprocess, CPU fp32"
+        rmodel = reference_model(ref, args.model, sd, torch.device("cpu"))
 
-    def step():
-        out = yo.forward(sd, x).numpy()
-        po.postprocess(np.ascontiguousarray(out), 80, args.conf, args.nms, variant="auto_cpu")
+        def step(x):
+            with torch.no_grad():
+                out = rmodel(x)
+            ref["postprocess"](out, rmodel.head.num_classes, args.conf, args.nms, class_agnostic=False)
+    else:
+        from oracle import postprocess_oracle as po
+        from oracle import yolox_oracle as yo
 
-    for _ in range(min(args.warmup, 2)):
-        step()
-    steps = min(args.steps, 10)
+        kind = "port"
+        how = "oracle/ torch-CPU fp32 forward + numpy/C NMS (baseline/_ref missing)"
+
+        def step(x):
+            out = yo.forward(sd, x).numpy()
+            po.postprocess(np.ascontiguousarray(out), 80, args.conf, args.nms, variant="auto_cpu")
+
+    probe = torch.from_numpy(syn.images(4, args.size, args.size, seed=7))
+    step(probe)                                   # thread pool / allocator warm-up
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    step(probe)
+    rate = 4 / (time.perf_counter() - t0)
+    warm = min(args.warmup, 3)
+    # bounded sample: at most 16 images per step (the CPU path is at its best rate in small batches: at 64 the activations
+    # fall out of the host caches) and the whole run (warm-up + steps) within ~150 s of CPU work
+    per_step = int(max(2, min(B, 16, rate * 150.0 / (args.steps + warm))))
+    x = torch.from_numpy(syn.images(per_step, args.size, args.size, seed=7))
+    for _ in range(warm):
+        step(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(x)
     dt = time.perf_counter() - t0
-    value = per_step * steps / dt
+    value = per_step * args.steps / dt
+    sample = (f"{args.steps} steps x {per_step} images" + ("" if per_step == B else f" (bounded sample of the {B}-image step)") +
+              f", {how}")
     line = {
         "metric": "images_per_second", "impl": "reference", "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "conf_thre": args.conf, "nms_thre": args.nms,
-                   "reference_arm": f"CPU fp32, bounded sample of {per_step} images per step of that workload"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps x {per_step} images, oracle/ torch-CPU fp32 forward + numpy/C NMS"},
+                   "reference_arm": f"host CPU fp32, {per_step} images per step"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def timed_us(fn, n: int = 10, warm: int = 3) -> float:
+    """Mean device time of fn() in microseconds (CUDA events on the current stream, synchronised on both sides)."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / n
+
+
+def parity_check(model, engine, args) -> dict:
+    """Outside the timed region: the detections of the LAST timed step (fused graph: score filter in the head epilogues +
+    sort/NMS kernel) must equal YoloxModule.forward + postprocess (the reference-shaped two-call API) on the same input,
+    row for row and bit for bit."""
+    import torch
+
+    import pixeltable_yolox_b200 as yx
+
+    pred = model(engine.input)                                       # separate engine without postprocess: cxcywh rows
+    want = yx.postprocess(pred, model.head.num_classes, args.conf, args.nms, nms_variant="auto")
+    cnt = engine.det_count.cpu().tolist()
+    ok, rows = True, 0
+    for b, w in enumerate(want):
+        n = min(cnt[b], args.max_det)
+        if w is None:
+            ok = ok and cnt[b] == 0
+            continue
+        ok = ok and cnt[b] == w.shape[0] and torch.equal(engine.dets[b, :n], w[:n])
+        rows += n
+    key = next(k for k, e in model._engines.items() if e.post is None and k[0] == tuple(engine.input.shape))
+    model._engines.pop(key).close()
+    return {"parity_checked": bool(ok), "parity_rows": rows,
+            "parity_how": "last timed step's detections == YoloxModule.forward + postprocess on the same batch (torch.equal per image)"}
+
+
+def extra_conf_leg(args, model, dev_in, conf: float, steps: int) -> dict:
+    """The same step at another score threshold (0.01 = the evaluator's test_conf, yolox/config.py:115)."""
+    import torch
+
+    from pixeltable_yolox_b200.boxes import NMS_VARIANTS
+
+    post = dict(conf_thre=conf, nms_thre=args.nms, nms_variant=NMS_VARIANTS["auto"], max_det=args.max_det)
+    eng = [model.engine_for(dev_in[0], post, slot=10 + i) for i in range(2)]
+    for i in range(2):
+        eng[i].input.copy_(dev_in[i])
+    for i in range(4):
+        eng[i % 2].forward(eng[i % 2].input)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng[i % 2].forward(eng[i % 2].input)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    last = eng[(steps - 1) % 2]
+    scores = last.pred[..., 4] * last.pred[..., 5:].max(-1).values
+    out = {"conf_thre": conf, "value": args.batch / (ms / 1e3), "unit": "images/s (one GPU, inputs resident)", "ms_per_step": ms,
+           "steps": steps, "candidates_per_image_mean": float((scores >= conf).float().sum(1).mean().item()),
+           "kept_per_image_mean": float(last.det_count.float().mean().item())}
+    for k in [k for k, e in model._engines.items() if e in eng]:
+        model._engines.pop(k).close()
+    return out
+
+
+def extra_config5(args, dev, pk, ref) -> dict:
+    """BASELINE.json config 5: dense-scene NMS stress on a synthetic decoded head tensor [64, 8400, 85],
+    thr 0.001 / 0.25 / 0.5, nms 0.65: filter_kernel and sort_nms_kernel device times, GB/s against the bytes they must
+    move, and the reference's postprocess (torchvision CUDA batched_nms, per-image Python loop) on the same tensor."""
+    import torch
+
+    from pixeltable_yolox_b200 import ops
+    from pixeltable_yolox_b200 import synthetic as syn
+    from pixeltable_yolox_b200.boxes import NMS_VARIANTS
+
+    B, A, nc = 64, 8400, 80
+    pred = torch.from_numpy(syn.dense_scene(B, anchors=A, seed=13)).to(dev)
+    ws = ops._workspace(dev, ops.lib().yx_postprocess_workspace_bytes(B, A), "post")
+    rows = []
+    for thr in (0.001, 0.25, 0.5):
+        _, _, cnt = ops.postprocess_device(pred.clone(), nc, thr, 0.65, NMS_VARIANTS["auto"], inplace_xyxy=True)
+        work = pred.clone()
+        t_total = timed_us(lambda: ops.postprocess_device(work, nc, thr, 0.65, NMS_VARIANTS["auto"], inplace_xyxy=False))
+        t_nms = timed_us(lambda: ops.nms_prefiltered(ws, B, A, 0.65, NMS_VARIANTS["auto"]))     # candidates of the last filter pass
+        t_filter = max(t_total - t_nms, 1e-3)
+        scores = pred[..., 4] * pred[..., 5:].max(-1).values
+        n_cand = int((scores >= thr).sum().item())
+        kept = int(cnt.sum().item())
+        filter_bytes = B * A * ((5 + nc) * 4 + 32) + n_cand * 8           # rows read, candidate rows + keys written
+        nms_bytes = n_cand * (32 + 8) + kept * (28 + 8)                   # candidate rows + keys read, detections written
+        row = {"conf_thre": thr, "candidates_per_image": n_cand / B, "kept_per_image": kept / B,
+               "postprocess_us": t_total, "filter_us": t_filter, "sort_nms_us": t_nms, "us_per_image": t_total / B,
+               "filter_GBps": filter_bytes / t_filter / 1e3, "filter_frac_of_hbm_peak": filter_bytes / t_filter / 1e3 / pk["hbm"],
+               "sort_nms_GBps_minimal_bytes": nms_bytes / t_nms / 1e3,
+               "sort_nms_frac_of_hbm_peak": nms_bytes / t_nms / 1e3 / pk["hbm"]}
+        if ref is not None:
+            try:
+                def ref_post():
+                    ref["postprocess"](pred.clone(), nc, thr, 0.65, class_agnostic=False)
+                ref_post(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    ref_post()
+                torch.cuda.synchronize()
+                row["reference_postprocess_us_same_gpu"] = (time.perf_counter() - t0) / 3 * 1e6
+            except Exception as e:                    # noqa: BLE001
+                row["reference_postprocess_us_same_gpu"] = f"failed: {e!r}"
+        rows.append(row)
+    return {"workload": "synthetic dense scenes [64, 8400, 85] fp32 (synthetic.dense_scene seed 13), nms 0.65, config[4] of BASELINE.json",
+            "hbm_peak_GBps": pk["hbm"], "rows": rows,
+            "note": "sort_nms is latency-bound (one CTA per image; the n^2/64 suppression mask never leaves shared memory): "
+                    "its GB/s is quoted against the minimal bytes (candidates in, detections out)"}
+
+
+def extra_hbm_families(prof, pk) -> dict:
+    """Per-family achieved GB/s of the HBM-bound launches of the step (algorithmic bytes / device time of the eager
+    per-op pass), against the measured copy bandwidth."""
+    fam = {}
+    for q in prof:
+        name = q["name"]
+        if name.startswith("conv1x1") and "->96 " in name:
+            key = "head prediction GEMM (decode + score filter epilogue)"
+        elif name.startswith("conv1x1"):
+            key = "conv1x1 @" + name.split("@")[1]
+        elif name.startswith(("spp", "dwconv", "focus", "bottleneck", "sort+nms", "conv3x3s2")):
+            key = name.split(" ")[0] + (" @" + name.split("@")[1] if "@" in name else "")
+        else:
+            continue
+        f = fam.setdefault(key, dict(launches=0, us=0.0, bytes=0.0))
+        f["launches"] += 1; f["us"] += q["ms"] * 1e3; f["bytes"] += q["bytes"]
+    out = {}
+    for k, f in fam.items():
+        gbps = f["bytes"] / max(f["us"], 1e-9) / 1e3
+        out[k] = {"launches": f["launches"], "us": round(f["us"], 1), "GBps": round(gbps, 1), "frac_of_hbm_peak": round(gbps / pk["hbm"], 3)}
+    return out
+
+
+def extra_torch_gpu(args, sd_cpu, dev_in, ref, dtype) -> dict:
+    """The reference on the same box: its unmodified YoloxModule in the bench dtype on cuDNN (torch eager, cudnn.benchmark,
+    both memory formats tried) + its own postprocess (torchvision CUDA batched_nms) on the same resident inputs."""
+    import torch
+
+    if ref is None:
+        return {"unavailable": "baseline/_ref missing (python baseline/install_ref.py)"}
+    dev = dev_in[0].device
+    torch.backends.cudnn.benchmark = True
+    best = None
+    for fmt_name, fmt in (("contiguous", torch.contiguous_format), ("channels_last", torch.channels_last)):
+        try:
+            m = reference_model(ref, args.model, sd_cpu, dev, dtype).to(memory_format=fmt)
+            xs = [d.to(dtype).contiguous(memory_format=fmt) for d in dev_in]
+
+            def step(i):
+                with torch.no_grad():
+                    out = m(xs[i % 2])
+                return ref["postprocess"](out.float(), m.head.num_classes, args.conf, args.nms, class_agnostic=False)
+
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
+            n = 10
+            t0 = time.perf_counter()
+            for i in range(n):
+                step(i)
+            torch.cuda.synchronize()
+            rate = n * xs[0].shape[0] / (time.perf_counter() - t0)
+            if best is None or rate > best["value"]:
+                best = {"value": rate, "unit": "images/s (one GPU, inputs resident)", "memory_format": fmt_name, "steps": n}
+            del m, xs
+            torch.cuda.empty_cache()
+        except Exception as e:                        # noqa: BLE001
+            print(f"# torch_gpu leg ({fmt_name}) failed: {e!r}", file=sys.stderr)
+    if best is None:
+        return {"unavailable": "the reference module failed on this GPU (see stderr)"}
+    best["what"] = (f"unmodified reference YoloxModule ({args.dtype}, cuDNN, torch eager) + yolox.utils.postprocess "
+                    "(torchvision.ops.batched_nms on CUDA), same weights and inputs; informational")
+    return best
 
 
 def run_ours(args):
@@ -245,6 +508,7 @@ def run_ours(args):
 
     from pixeltable_yolox_b200 import synthetic as syn
     from pixeltable_yolox_b200.boxes import NMS_VARIANTS
+    from pixeltable_yolox_b200.sharding import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,14 +520,23 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("YX_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.train:
+        return run_train(args, world, rank, dev)
 
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     cfg, model = build_model(args, dev)
     sd_cpu = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model = model.to(dtype).eval()
     model.micro_batch = args.micro_batch
-    B, S = args.batch, args.size
-    # two distinct synthetic batches per rank, alternated, each 315 MB fp32 (> 126 MB L2)
+    S = args.size
+    if args.global_batch:                      # strong scaling: this rank's contiguous slice of the global batch
+        lo, hi = shard_range(args.global_batch, rank, world)
+        B = hi - lo
+        total_images = args.global_batch
+    else:
+        B = args.batch
+        total_images = B * world
+    # two distinct synthetic batches per rank, alternated, each > 126 MB L2 (315 MB fp32 at batch 64)
     host = [torch.from_numpy(syn.images(B, S, S, seed=7 + 100 * rank + i)).pin_memory() for i in range(2)]
     dev_in = [h.to(dev) for h in host]
     post = dict(conf_thre=args.conf, nms_thre=args.nms, nms_variant=NMS_VARIANTS["auto"], max_det=args.max_det)
@@ -277,13 +550,12 @@ def run_ours(args):
 
     # ---------------- value: inputs resident in HBM ----------------
     # Two engines (own plan, own activation buffers) alternate, each with its batch already in its input buffer: no
-    # staging copy inside the timed region, and every step reads a 315 MB input the previous step did not touch.
+    # staging copy inside the timed region, and every step reads an input batch the previous step did not touch.
     for i in range(2):
         eng[i].input.copy_(dev_in[i])
     clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()            # before the warm-up: nvidia-smi needs ~100-300 ms before its first row
-        clocks.wait_first()
+    clocks.start()                # before the warm-up: nvidia-smi needs ~100-300 ms before its first row
+    clocks.wait_first()
     for i in range(args.warmup):
         eng[i % 2].forward(eng[i % 2].input)
     barrier()
@@ -297,18 +569,24 @@ def run_ours(args):
     w1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     clocks.mark(w0, w1)           # keep the rows sampled while the timed steps ran
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
+    per_rank_ms, per_rank_clk = [ms / args.steps], [clk]
     if world > 1:
         t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(v.item()) / args.steps for v in allt]
+        ms = max(float(v.item()) for v in allt)
+        per_rank_clk = [None] * world
+        dist.all_gather_object(per_rank_clk, clk)
     barrier()
-    value = world * B * args.steps / (ms / 1e3)
+    value = total_images * args.steps / (ms / 1e3)
     last = eng[(args.steps - 1) % 2]
     kept = int(last.det_count.clamp(max=args.max_det).sum().item())
     kept_true_mean = float(last.det_count.float().mean().item())
     scores = last.pred[..., 4] * last.pred[..., 5:].max(-1).values
     cand_mean = float((scores >= args.conf).float().sum(1).mean().item())
+    parity = parity_check(model, last, args) if rank == 0 else None
 
     # ---------------- e2e: host buffers in, detections out, every step ----------------
     # Headline: uint8 pixels (what decoders / YoloxProcessor(dtype=torch.uint8) produce; exactly the values the
@@ -340,7 +618,7 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        return world * B * args.steps / dt
+        return total_images * args.steps / dt
 
     host_u8 = [h.to(torch.uint8).pin_memory() for h in host]
     eng_u8 = [model.engine_for(host_u8[0], post, slot=i) for i in range(2)]
@@ -379,22 +657,39 @@ def run_ours(args):
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "launches": len(tc), "avg_launch_us": 1e3 * tc_ms / max(len(tc), 1), "share_of_step": tc_ms / all_ms,
                 "whole_step_frac_of_peak": GFLOP_PER_IMAGE.get(args.model, 0) * 1e9 * (value / world) / (pk["tf_sustained"] * 1e12)}
+        extra = {"hbm_bound_families": extra_hbm_families(prof, pk)}
         cpu = None
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_extras:
+            ref = reference_modules()
+            try:
+                extra["thr001"] = extra_conf_leg(args, model, dev_in, 0.01, min(args.steps, 20))
+            except Exception as e:                    # noqa: BLE001 - an extra leg never takes the headline down
+                extra["thr001"] = {"failed": repr(e)}
+            try:
+                extra["config5"] = extra_config5(args, dev, pk, ref)
+            except Exception as e:                    # noqa: BLE001
+                extra["config5"] = {"failed": repr(e)}
+            try:
+                extra["torch_gpu"] = extra_torch_gpu(args, sd_cpu, dev_in, ref, dtype)
+            except Exception as e:                    # noqa: BLE001
+                extra["torch_gpu"] = {"failed": repr(e)}
+        if world == 1 and not args.no_cpu_baseline:   # N = 1 only: seven other ranks would spin in a barrier meanwhile
             imgs = host[0][:args.cpu_images].numpy()
             rate, threads, n = cpu_reference_rate(args, sd_cpu, imgs)
             cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                    "sample": f"{n} of the step's images, oracle/ torch-CPU fp32 forward + numpy/C NMS"}
         vs = None
+        in_mb = dev_in[0].numel() * dev_in[0].element_size() / 1e6
         line = {
             "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": vs, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args),
-                       "per_gpu_batch": B, "global_batch": B * world, "micro_batch": args.micro_batch,
+                       "per_gpu_batch": B, "global_batch": total_images, "micro_batch": args.micro_batch,
                        "conf_thre": args.conf, "nms_thre": args.nms, "nms_variant": "auto (torchvision CUDA rule)",
                        "weights": "random init, BN calibrated (synthetic.randomize_and_calibrate)",
-                       "l2": "two alternating engines, each with its own 315 MB input batch resident in its input buffer (> 126 MB L2)",
+                       "l2": f"two alternating engines, each with its own {in_mb:.0f} MB input batch resident in its input buffer (> 126 MB L2)",
                        "detections_kept_last_step": kept, "kept_per_image_mean": kept_true_mean,
                        "candidates_per_image_mean": cand_mean},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -407,11 +702,254 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "per_rank": {"ms_per_step": per_rank_ms, "clocks": per_rank_clk},
+            "extra": extra,
+        }
+        line.update(parity)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# config 4: training step
+# ------------------------------------------------------------------------------------------------------------------
+def train_batch(args, rank: int, B: int):
+    """Images as config 2; labels [B, 120, 5] per SURVEY 8d config 4: G ~ randint(0, 50) per image with one G = 0 and one
+    G = 120 image on rank 0, cls ~ randint(80), centres inside the image, w,h ~ U(8, 208), zero padded."""
+    import torch
+
+    from pixeltable_yolox_b200 import synthetic as syn
+
+    import numpy as np
+
+    rng = np.random.default_rng(3 + rank)
+    counts = [int(rng.integers(0, 50)) for _ in range(B)]
+    if rank == 0 and B >= 2:
+        counts[0], counts[1] = 0, 120
+    x = torch.from_numpy(syn.images(B, args.size, args.size, seed=7 + 100 * rank))
+    lab = torch.from_numpy(syn.labels(B, max_gt=120, seed=3 + rank, size=float(args.size), counts=counts))
+    return x, lab, counts
+
+
+def sgd_for(model):
+    """The reference's optimizer (yolox/config.py:307-333): SGD momentum 0.9 nesterov; BN weights and biases without
+    weight decay, conv / linear weights with 5e-4."""
+    import torch
+    import torch.nn as nn
+
+    pg0, pg1, pg2 = [], [], []
+    for _, v in model.named_modules():
+        if hasattr(v, "bias") and isinstance(v.bias, nn.Parameter):
+            pg2.append(v.bias)
+        if isinstance(v, nn.BatchNorm2d) or "bn" in type(v).__name__.lower():
+            pg0.append(v.weight)
+        elif hasattr(v, "weight") and isinstance(v.weight, nn.Parameter):
+            pg1.append(v.weight)
+    opt = torch.optim.SGD(pg0, lr=1e-3, momentum=0.9, nesterov=True)
+    opt.add_param_group({"params": pg1, "weight_decay": 5e-4})
+    opt.add_param_group({"params": pg2})
+    return opt
+
+
+def time_train_steps(model, opt, x, lab, steps, warm, amp_dtype, world, dev, host=None):
+    """ms per step (device events, max over ranks) and the phase split of the last step. `host`: (pinned images, pinned
+    labels) -> every step uploads them and reads the loss back (the e2e leg)."""
+    import torch
+    import torch.distributed as dist
+
+    def one(i, ev=None):
+        if host is not None:
+            x.copy_(host[0], non_blocking=True); lab.copy_(host[1], non_blocking=True)
+        if ev: ev[0].record()
+        with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+            out = model(x, lab)
+        loss = out["total_loss"]
+        if ev: ev[1].record()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if ev: ev[2].record()
+        opt.step()
+        if ev: ev[3].record()
+        return float(loss.item()) if host is not None else loss
+
+    for i in range(warm):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e0.record()
+    for i in range(steps):
+        loss = one(i, ev if i == steps - 1 else None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    phases = {"forward_incl_assignment_and_losses_ms": ev[0].elapsed_time(ev[1]), "backward_incl_allreduce_ms": ev[1].elapsed_time(ev[2]),
+              "optimizer_ms": ev[2].elapsed_time(ev[3])}
+    return ms / steps, phases, float(loss) if not isinstance(loss, float) else loss
+
+
+def run_train(args, world, rank, dev):
+    import torch
+    import torch.distributed as dist
+
+    from pixeltable_yolox_b200 import ops
+
+    B = args.train_batch
+    amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None}[args.dtype]
+    cfg, model = build_model(args, dev)
+    sd_cpu = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    model.train()
+    n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
+    opt = sgd_for(model)
+    xh, labh, counts = train_batch(args, rank, B)
+    xh, labh = xh.pin_memory(), labh.pin_memory()
+    x, lab = xh.to(dev), labh.to(dev)
+    clocks = ClockSampler(dev.index)
+    clocks.start(); clocks.wait_first()
+    w0 = time.perf_counter()
+    ms, phases, loss = time_train_steps(net, opt, x, lab, args.steps, args.warmup, amp_dtype, world, dev)
+    clocks.mark(w0 + 0.0, time.perf_counter())
+    clk = clocks.stop()
+    ms_e2e, _, loss_e2e = time_train_steps(net, opt, x, lab, args.steps, 2, amp_dtype, world, dev, host=(xh, labh))
+
+    # ---- our kernels of the step, stand-alone on this rank's head output shape
+    model.eval()        # BN statistics are irrelevant here: only shapes and value ranges of the head output matter
+    with torch.no_grad():
+        from pixeltable_yolox_b200 import synthetic as syn
+        from oracle.simota_oracle import anchor_grid          # anchor grid helper only (test infrastructure, not timed)
+    hw = [(args.size // s, args.size // s) for s in (8, 16, 32)]
+    import numpy as np
+
+    xs, ys, st = (torch.from_numpy(a).to(dev) for a in anchor_grid(hw, (8, 16, 32)))
+    pred = torch.from_numpy(syn.train_head_output(B, hw, (8, 16, 32), labh.numpy(), seed=4 + rank)).to(dev)
+    asg = ops.simota_assign(pred, lab, xs, ys, st, 80, levels=3)
+
+    def graph_us(fn):
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return timed_us(g.replay, 20)
+
+    t_simota = graph_us(lambda: ops.simota_assign(pred, lab, xs, ys, st, 80, levels=3))
+    t_loss = graph_us(lambda: ops.head_losses(pred, lab, asg))
+    # ---- the gradient all-reduce alone (one flat fp32 buffer of every gradient)
+    t_ar = None
+    if world > 1:
+        flat = torch.zeros(n_grad, dtype=torch.float32, device=dev)
+        t_ar = timed_us(lambda: dist.all_reduce(flat), 20)
+        tt = torch.tensor([t_ar], device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t_ar = float(tt.item())
+
+    # ---- the reference-shaped torch-only step on the same box (unmodified reference module, same optimizer / AMP / DDP)
+    ref_line = None
+    ref = reference_modules()
+    if ref is not None and not args.no_extras:
+        try:
+            rmodel = reference_model(ref, args.model, sd_cpu, dev).train()
+            rnet = rmodel
+            if world > 1:
+                rnet = torch.nn.parallel.DistributedDataParallel(rmodel, device_ids=[dev.index], broadcast_buffers=False)
+            ropt = sgd_for(rmodel)
+            try:
+                rms, rph, rloss = time_train_steps(rnet, ropt, x, lab, min(args.steps, 10), 2, amp_dtype, world, dev)
+                ramp = args.dtype
+            except Exception as e:                    # noqa: BLE001 - e.g. an op of the reference without a bf16 kernel
+                print(f"# reference train step under autocast({args.dtype}) failed: {e!r}; timing it in fp32", file=sys.stderr)
+                rms, rph, rloss = time_train_steps(rnet, ropt, x, lab, min(args.steps, 10), 2, None, world, dev)
+                ramp = "fp32"
+            ref_line = {"ms_per_step": rms, "images_per_second": world * B / (rms / 1e3), "phases_last_step": rph, "amp": ramp,
+                        "loss_last_step": rloss,
+                        "what": "unmodified reference YoloxModule.forward(train) (per-image get_assignments loop) + backward + SGD, "
+                                "torch eager / cuDNN, same inputs, labels, optimizer and DDP"}
+        except Exception as e:                        # noqa: BLE001
+            ref_line = {"failed": repr(e)}
+    if rank == 0:
+        pk = peaks()
+        A = sum(h * w for h, w in hw)
+        sim_bytes = B * A * 85 * 4
+        cpu = None
+        line = {
+            "metric": "images_per_second", "value": world * B / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
+                       "labels": f"[{B}, 120, 5] per rank, GT counts on rank 0 {counts}", "amp": args.dtype,
+                       "optimizer": "SGD momentum 0.9 nesterov, wd 5e-4 on conv weights (yolox/config.py:307-333)",
+                       "network_fwd_bwd": "torch autograd / cuDNN (SURVEY 8f rank 2 not built: no dgrad / wgrad tcgen05 kernels)",
+                       "ours_in_step": "yx_simota_assign (whole batch, one cluster launch, no host sync) + yx_head_losses "
+                                       "(losses and d/d(pred) in one pass)",
+                       "collective": (f"gradient all-reduce: torch DDP buckets (25 MB) -> ncclAllReduce over NVLink/NVSwitch, "
+                                      f"{n_grad * 4 / 1e6:.1f} MB fp32 per step" if world > 1 else "none (one rank)"),
+                       "loss_last_step": loss},
+            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": xh.numel() * 4 + labh.numel() * 4, "d2h_bytes_per_step": 4,
+                    "input": "pinned host fp32 images + labels uploaded every step, loss read back every step", "loss_last_step": loss_e2e},
+            "gpu_launches": 2 * args.steps, "launches_per_step": 2,
+            "phases_last_step": phases,
+            "kernels": {"simota_assign_us": t_simota, "simota_GBps_of_prediction_tensor": sim_bytes / t_simota / 1e3,
+                        "head_losses_us": t_loss, "head_losses_GBps": 2 * sim_bytes / t_loss / 1e3,
+                        "allreduce_us_standalone": t_ar, "allreduce_share_of_step": (t_ar / 1e3 / ms) if t_ar else None,
+                        "allreduce_busbw_GBps": (2 * (world - 1) / world * n_grad * 4 / t_ar / 1e3) if t_ar else None},
+            "roofline": {"bound": "hbm", "kernel": "head_loss_kernel (losses + gradients, the HBM-bound kernel of ours in the step)",
+                         "achieved": 2 * sim_bytes / t_loss / 1e3, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": 2 * sim_bytes / t_loss / 1e3 / pk["hbm"], "traffic": None,
+                         "peak_source": pk["source"] + " HBM copy bandwidth"},
+            "reference_same_box": ref_line, "cpu_baseline": cpu, "clocks": clk,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_reference_train(args, threads):
+    """--impl reference --train: the unmodified reference's training step on the host cores (fp32), bounded."""
+    import torch
+
+    ref = reference_modules()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing (python baseline/install_ref.py)"}), flush=True)
+        return
+    _, model = build_model(args, torch.device("cpu"))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rmodel = reference_model(ref, args.model, sd, torch.device("cpu")).train()
+    opt = sgd_for(rmodel)
+    B = min(args.train_batch, 4)
+    x, lab, _ = train_batch(args, 0, B)
+
+    def step():
+        out = rmodel(x, lab)
+        opt.zero_grad(set_to_none=True)
+        out["total_loss"].backward()
+        opt.step()
+
+    step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    line = {"metric": "images_per_second", "impl": "reference", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "per_gpu_batch": args.train_batch,
+                       "reference_arm": f"host CPU fp32, {B} images per step"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "reference",
+                             "sample": f"{steps} steps x {B} images, unmodified reference training step (baseline/_ref), CPU fp32"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -24,6 +24,12 @@
 
 namespace yx {
 
+#ifdef YX_EXP_BNECK128
+static constexpr bool kHasBneck128 = true;
+#else
+static constexpr bool kHasBneck128 = false;
+#endif
+
 static constexpr int kBnX = 6;          // max X halo slots
 static constexpr int kBnThreads = 64 + 256 + 256 + 32;   // TMA + GEMM2 warps, 8 epilogue-1 warps (4 per GEMM1 tile), 8 epilogue-2 warps, GEMM1 warp
 static constexpr int kWarpG1 = 18;
@@ -349,6 +355,7 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
+#ifdef YX_EXP_BNECK128   // negative result: only in experiment builds (python -m pixeltable_yolox_b200.build --exp -DYX_EXP_BNECK128)
 // ------------------------------------------------------------------------------------------
 // C = 128: two 64-channel chunks, W2 (288 KB) cannot stay resident. Same five steps as above with
 //   * X: one slot of two chunk tiles; H: two slots of two chunk tiles; TMEM: acc1 (2 x 128 columns, single)
@@ -640,6 +647,7 @@ bneck128_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tmem_dealloc(tmem_base, 512);
   }
 }
+#endif  // YX_EXP_BNECK128
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -666,12 +674,12 @@ BneckLaunch* bneck_alloc() {
 void bneck_free(BneckLaunch* p) { free(p); }
 
 bool bneck_supported(const yx_bneck_desc* d) {
-  return d && (d->c == 16 || d->c == 32 || d->c == 64 || d->c == 128) && (d->dtype == YX_BF16 || d->dtype == YX_FP16);
+  return d && (d->c == 16 || d->c == 32 || d->c == 64 || (kHasBneck128 && d->c == 128)) && (d->dtype == YX_BF16 || d->dtype == YX_FP16);
 }
 
 int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
   YX_REQUIRE(d != nullptr, YX_ERR_INVALID_ARG, "bottleneck: null descriptor");
-  YX_REQUIRE(d->c == 16 || d->c == 32 || d->c == 64 || d->c == 128, YX_ERR_UNSUPPORTED, "bottleneck: c=%d (fused kernel: 16, 32, 64 or 128)", d->c);
+  YX_REQUIRE(d->c == 16 || d->c == 32 || d->c == 64 || (kHasBneck128 && d->c == 128), YX_ERR_UNSUPPORTED, "bottleneck: c=%d (fused kernel: 16, 32 or 64)", d->c);
   YX_REQUIRE(d->dtype == YX_BF16 || d->dtype == YX_FP16, YX_ERR_INVALID_ARG, "bottleneck: dtype must be bf16/fp16");
   YX_REQUIRE(d->batch > 0 && d->h > 0 && d->w > 0, YX_ERR_INVALID_ARG, "bottleneck: empty input");
   YX_REQUIRE(d->x && d->w1 && d->w2 && d->bias1 && d->bias2 && d->out, YX_ERR_INVALID_ARG, "bottleneck: null pointer");
@@ -751,7 +759,7 @@ int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
   const long long fixed = 2048 + 2 * (long long)p.bias_bytes + 2 * (long long)p.h_slot_bytes + 10 * (long long)p.w_tile_bytes;
   if (big) {
     p.nx = 1;
-    L->smem = 2048 + 2 * (size_t)p.bias_bytes + 6 * (size_t)p.x_slot_bytes + (size_t)kB2Stages * 16384;
+    L->smem = 2048 + 2 * (size_t)p.bias_bytes + 6 * (size_t)p.x_slot_bytes + 3 * 16384;
     YX_REQUIRE((long long)L->smem <= max_smem, YX_ERR_UNSUPPORTED, "bottleneck(128): needs %zu bytes of shared memory", L->smem);
   } else {
     p.nx = (int)((max_smem - fixed) / p.x_slot_bytes);
@@ -797,15 +805,17 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
   YX_CUDA(cudaFuncSetAttribute(bneck_tc_kernel<F, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     YX_BN_ATTR(false, 1); YX_BN_ATTR(false, 2); YX_BN_ATTR(false, 4); YX_BN_ATTR(true, 1); YX_BN_ATTR(true, 2); YX_BN_ATTR(true, 4);
 #undef YX_BN_ATTR
+#ifdef YX_EXP_BNECK128
 #define YX_B2_ATTR(F, S) YX_CUDA(cudaFuncSetAttribute(bneck128_tc_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     YX_B2_ATTR(false, false); YX_B2_ATTR(false, true); YX_B2_ATTR(true, false); YX_B2_ATTR(true, true);
 #undef YX_B2_ATTR
+#endif
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)L->grid);
-  cfg.blockDim = dim3((unsigned)(L->p.C == 128 ? kB2Threads : kBnThreads));
+  cfg.blockDim = dim3((unsigned)(L->p.C == 128 ? 64 + 256 + 256 + 32 : kBnThreads));
   cfg.dynamicSmemBytes = L->smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -814,6 +824,7 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool h16 = L->p.epi.dtype == YX_FP16;
+#ifdef YX_EXP_BNECK128
   if (L->p.C == 128) {
     const bool silu = L->p.act1 == YX_ACT_SILU;
     if (L->p.trace) { int z[8] = {0, 0, 0, 0, 0, 0, 0, 1}; YX_CUDA(cudaMemcpyToSymbol(g_mbar_dbg, z, sizeof(z))); }
@@ -830,6 +841,7 @@ int bneck_launch(const BneckLaunch* L, cudaStream_t stream) {
     }
     return YX_OK;
   }
+#endif
 #define YX_BN_GO(F, K) do { if (L->p.act1 == YX_ACT_SILU) YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K, true>, L->map_x, L->map_w1, L->map_w2, L->p)); \
     else YX_CUDA(cudaLaunchKernelEx(&cfg, bneck_tc_kernel<F, K, false>, L->map_x, L->map_w1, L->map_w2, L->p)); } while (0)
   if (L->p.ksteps == 4) { if (h16) YX_BN_GO(true, 4); else YX_BN_GO(false, 4); }

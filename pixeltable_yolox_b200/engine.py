@@ -544,21 +544,13 @@ class InferenceEngine:
                 cand, keys, counts = ops.postprocess_ws_ptrs(self._post_ws, batch, self.anchors)
                 self._post_fused = dict(cand=cand, keys=keys, counts=counts, conf_thre=post["conf_thre"])
                 b.postprocess_begin(self._post_ws, batch, self.anchors)
-        # intermediate buffers are allocated while lowering the first micro-batch and reused after
-        first_keep = None
+        # intermediate buffers are allocated while lowering the first micro-batch (every Builder.new_feat call is recorded as
+        # a slot: call index -> (shape, tensor)) and handed back, slot by slot, to the later micro-batches of the same size
+        self._slots = None
         for b0 in range(0, batch, self.mb):
             b1 = min(batch, b0 + self.mb)
-            if b1 - b0 != self.mb:
-                self._replay_alloc = None       # ragged tail: allocate fresh (smaller) buffers
-            img = self.input[b0:b1]
-            if first_keep is None or b1 - b0 != self.mb:
-                mark = len(b.keep)
-                self._lower(img, self.pred[b0:b1], b0)
-                if first_keep is None:
-                    first_keep = (mark, len(b.keep))
-                    self._record = [t for t in b.keep[mark:]]
-            else:
-                self._lower_reusing(img, self.pred[b0:b1], b0)
+            self._lower_slice(self.input[b0:b1], self.pred[b0:b1], b0, record=self._slots is None and b1 - b0 == self.mb,
+                              replay=self._slots is not None and b1 - b0 == self.mb)
             b.join_lanes()                       # slices share buffers: the next one starts after every branch is done
         if self.post is not None:
             if self._post_fused is not None:
@@ -582,25 +574,40 @@ class InferenceEngine:
                         conf_thre=f["conf_thre"], xyxy=True)
         m.head.lower(self.builder, list(feats), pred_slice, post=post)
 
-    def _lower_reusing(self, img, pred_slice, b0=0):
+    def _lower_slice(self, img, pred_slice, b0, record: bool, replay: bool):
+        """Lower one micro-batch. record: remember every buffer new_feat allocates, in call order. replay: the lowering
+        makes the same new_feat calls in the same order (same modules, same shapes), so call k gets slot k back; a
+        shape mismatch or a different number of calls is an error, never a silent mix-up. A ragged tail allocates its own."""
         b = self.builder
-        pool = list(self._record)
+        if not (record or replay):
+            return self._lower(img, pred_slice, b0)
         orig_new_feat = b.new_feat
+        slots = [] if record else self._slots
+        cursor = [0]
 
-        def reuse_feat(B, H, W, segs):
-            slots = sum(pad16(s) for s in segs)
-            while pool:
-                t = pool.pop(0)
-                if t.dim() == 4:
-                    assert tuple(t.shape) == (B, H, W, slots), (tuple(t.shape), (B, H, W, slots))
-                    return Feat(t, 0, list(segs))
-            raise RuntimeError("buffer replay ran out of tensors")
+        def slotted_new_feat(B, H, W, segs):
+            shape = (B, H, W, sum(pad16(s) for s in segs))
+            if record:
+                f = orig_new_feat(B, H, W, segs)
+                slots.append((shape, f.t))
+                return f
+            if cursor[0] >= len(slots):
+                raise RuntimeError(f"buffer replay: micro-batch asks for buffer #{cursor[0]} but the first one allocated {len(slots)}")
+            want, t = slots[cursor[0]]
+            if want != shape:
+                raise RuntimeError(f"buffer replay: slot {cursor[0]} was allocated as {want}, now requested as {shape}")
+            cursor[0] += 1
+            return Feat(t, 0, list(segs))
 
-        b.new_feat = reuse_feat
+        b.new_feat = slotted_new_feat
         try:
             self._lower(img, pred_slice, b0)
         finally:
             b.new_feat = orig_new_feat
+        if record:
+            self._slots = slots
+        elif cursor[0] != len(slots):
+            raise RuntimeError(f"buffer replay: micro-batch used {cursor[0]} of {len(slots)} recorded buffers")
 
     @property
     def launches(self) -> int:

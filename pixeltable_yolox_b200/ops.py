@@ -321,8 +321,22 @@ def bboxes_iou_device(a: torch.Tensor, b: torch.Tensor, xyxy: bool) -> torch.Ten
 # ---------------------------------------------------------------------------------------------
 # SimOTA
 # ---------------------------------------------------------------------------------------------
+_LEVELS_CACHE: dict = {}
+
+
+def _stride_levels(st: torch.Tensor) -> int:
+    """Number of distinct strides in the per-anchor stride vector (one device sync, cached per tensor)."""
+    key = (st.data_ptr(), st.numel(), st._version, st.device)
+    n = _LEVELS_CACHE.get(key)
+    if n is None:
+        if len(_LEVELS_CACHE) > 64:
+            _LEVELS_CACHE.clear()
+        n = _LEVELS_CACHE[key] = int(torch.unique(st).numel()) if st.numel() else 1
+    return n
+
+
 def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tensor, y_shifts: torch.Tensor,
-                  strides: torch.Tensor, num_classes: int):
+                  strides: torch.Tensor, num_classes: int, levels: Optional[int] = None):
     """Batched get_assignments. Returns dict of dense per-anchor tensors (see include/yx_b200.h)."""
     require_cuda(pred, "simota_assign")
     same_device(pred.device, "simota_assign", labels=labels, x_shifts=x_shifts, y_shifts=y_shifts, strides=strides)
@@ -350,7 +364,8 @@ def simota_assign(pred: torch.Tensor, labels: torch.Tensor, x_shifts: torch.Tens
         out["fg_mask"].zero_(); out["matched_gt"].fill_(-1); out["matched_iou"].zero_(); out["matched_cls"].fill_(-1)
         out["num_fg"].zero_(); out["num_gt"].zero_()
         return out
-    levels = int(torch.unique(st).numel()) if A > 0 else 1
+    if levels is None:
+        levels = _stride_levels(st)
     ws = _workspace(dev, lib().yx_simota_workspace_bytes(B, A, max_gt, levels), "simota")
     with on_device(dev):
         check(lib().yx_simota_assign(pred.data_ptr(), labels.data_ptr(), xs.data_ptr(), ys.data_ptr(), st.data_ptr(), B, A,

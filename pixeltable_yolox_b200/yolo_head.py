@@ -201,7 +201,8 @@ class YoloxHead(_B200Block):
         ops.require_cuda(outputs, "get_losses")
         pred = outputs.float().contiguous()
         with torch.no_grad():
-            asg = ops.simota_assign(pred.detach(), labels, x_shifts, y_shifts, expanded_strides, self.num_classes)
+            asg = ops.simota_assign(pred.detach(), labels, x_shifts, y_shifts, expanded_strides, self.num_classes,
+                                    levels=len(set(self.strides)))
         num_fg = asg["num_fg"].sum().clamp(min=1).to(torch.float32)
         num_gts = asg["num_gt"].sum().clamp(min=1).to(torch.float32)
         reg_weight = 5.0

@@ -37,8 +37,20 @@ def timed(fn, n=20):
     return e0.elapsed_time(e1) * 1e3 / n
 
 
-asg = ops.simota_assign(pred, lab, xs, ys, st, nc)
-t_asg = timed(lambda: ops.simota_assign(pred, lab, xs, ys, st, nc))
+def device_time(fn, n=20):
+    """Device time of one call: captured in a CUDA graph once, replayed n times (no Python / allocator time)."""
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return timed(g.replay, n)
+
+
+asg = ops.simota_assign(pred, lab, xs, ys, st, nc, levels=3)
+t_asg = timed(lambda: ops.simota_assign(pred, lab, xs, ys, st, nc, levels=3))
+t_asg_dev = device_time(lambda: ops.simota_assign(pred, lab, xs, ys, st, nc, levels=3))
+print(f"simota_assign: {t_asg_dev:.1f} us on the device (graph replay), {t_asg:.1f} us per Python call; "
+      f"{pred.numel() * 4 / t_asg_dev / 1e3:.0f} GB/s of the prediction tensor")
 t_loss = timed(lambda: ops.head_losses(pred, lab, asg))
 nbytes = 2 * pred.numel() * 4
 print(f"B={B} A={A}: simota_assign {t_asg:.1f} us, head_losses {t_loss:.1f} us = {nbytes / t_loss / 1e3:.0f} GB/s "
