@@ -36,7 +36,8 @@ static constexpr int kChunkBytes = kChunk * 24 + kChunk * kChunkWords * 4;
 static constexpr int kClassCap = 1024;      // class ids below this get a linked list of kept boxes
 static constexpr int kTriItems = 32 * (kChunkWords * (kChunkWords + 1) / 2);  // (row, word) items of the upper triangle
 static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassCap * 4;
-static constexpr int kKeptEntryBytes = 28;  // box 16 + area 4 + class 4 + next 4
+static constexpr int kKeptEntryBytes = 20;  // box 16 + (class | next << 10) 4; the area is recomputed (3 flops)
+static constexpr int kNmsSmemBudget = 225 * 1024;   // dynamic shared memory: 8 652 kept entries, i.e. every anchor of a 640^2 image
 
 __device__ __forceinline__ uint32_t orderable(float f) { return orderable_f32(f); }
 
@@ -196,6 +197,7 @@ struct NmsArgs {
   int* keep; int* keep_count;      // yx_batched_nms
   float* dets; long long* det_idx; int* det_count; int max_det;  // yx_postprocess (from cand rows)
   int debug;                       // YX_NMS_DEBUG: thread 0 prints per-phase cycle counts
+  int no_small;                    // YX_NMS_NO_SMALL: never take the single-warp path (tests compare the two paths)
 };
 
 __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b, float thr) {
@@ -211,6 +213,85 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
 }
 __device__ __forceinline__ float box_area(const float4 b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// n <= 32 candidates (the common case at the default thresholds: ~20 per image): one warp does the whole image in
+// registers -- key sort by 15 shuffle compare-exchanges, 32 x 32 suppression bits with the same arithmetic as the chunked
+// path, the fixed 32-step greedy resolution -- and writes the outputs; no shared memory, no block barriers.
+__device__ __forceinline__ void nms_small_warp(const NmsArgs& g, int b, int n, int variant, long long base) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned long long k = ~0ull;
+  if (lane < n) {
+    if (g.keys) k = g.keys[base + lane];
+    else {
+      float sc = g.src.scores[(base + lane) * g.src.score_stride];
+      if (sc == 0.0f) sc = 0.0f;
+      k = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)lane;
+    }
+  }
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(full, k, stride);
+      const bool keep_min = (((lane & stride) == 0) == ((lane & size) == 0));
+      k = keep_min ? (k < o ? k : o) : (k > o ? k : o);
+    }
+  }
+  const bool valid = lane < n;
+  const int idx = valid ? (int)(unsigned)(k & 0xffffffffull) : 0;
+  float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  int c = 0;
+  float mx = -INFINITY;
+  if (valid) {
+    const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
+    bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+    if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+    else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+    mx = fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(full, mx, o));
+  if (variant == 0) {
+    const float off = __fmul_rn((float)c, __fadd_rn(mx, 1.0f));
+    bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
+    bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+  }
+  const float area = box_area(bx);
+  unsigned row = 0u;                                   // bit j: this lane's box suppresses the later box j
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float4 ob;
+    ob.x = __shfl_sync(full, bx.x, j); ob.y = __shfl_sync(full, bx.y, j);
+    ob.z = __shfl_sync(full, bx.z, j); ob.w = __shfl_sync(full, bx.w, j);
+    const float oa = __shfl_sync(full, area, j);
+    const int oc = __shfl_sync(full, c, j);
+    if (valid && j > lane && j < n && (variant != 1 || oc == c) && suppresses(bx, area, ob, oa, g.thr)) row |= 1u << j;
+  }
+  unsigned alive = n >= 32 ? full : ((1u << n) - 1u), keptw = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const unsigned di = __shfl_sync(full, row, i);
+    if ((alive >> i) & 1u) { keptw |= 1u << i; alive &= ~di; }
+  }
+  const int nk = __popc(keptw);
+  const bool mine = (keptw >> lane) & 1u;
+  const int pos = __popc(keptw & ((1u << lane) - 1u));
+  if (g.keep) {
+    if (mine) g.keep[base + pos] = idx;
+    if (lane == 0) g.keep_count[b] = nk;
+  }
+  if (g.dets) {
+    if (mine && pos < g.max_det) {
+      const float4* crow = reinterpret_cast<const float4*>(g.src.boxes + (base + idx) * 8);
+      const float4 r0 = crow[0], r1 = crow[1];
+      float* d = g.dets + ((long long)b * g.max_det + pos) * 7;
+      d[0] = r0.x; d[1] = r0.y; d[2] = r0.z; d[3] = r0.w; d[4] = r1.x; d[5] = r1.y; d[6] = r1.z;
+      if (g.det_idx) g.det_idx[(long long)b * g.max_det + pos] = idx;
+    }
+    if (lane == 0) g.det_count[b] = nk;
+  }
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs g) {
@@ -242,6 +323,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   if (variant == 4) variant = (4LL * n > 4000) ? 1 : 0;
   if (variant == 5) variant = (4LL * n > 20000) ? 1 : 0;     // torchvision 0.17.2 (the reference's pin) on CUDA
 
+  if (n > 0 && n <= 32 && !g.no_small) {
+    if (warp == 0) nms_small_warp(g, b, n, variant, base);
+    return;
+  }
   if (n > 0) {
     // ---------------- sort ----------------
     int P = 1;
@@ -342,9 +427,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     uint8_t* kbase = reinterpret_cast<uint8_t*>(khead + kClassCap);
     const int KC = g.kept_cap;
     float4* kbox = reinterpret_cast<float4*>(kbase);                          // [KC]
-    float* karea = reinterpret_cast<float*>(kbase + (size_t)KC * 16);         // [KC]
-    int* kcls = reinterpret_cast<int*>(kbase + (size_t)KC * 20);              // [KC]
-    int* knext = reinterpret_cast<int*>(kbase + (size_t)KC * 24);             // [KC]
+    int* kmeta = reinterpret_cast<int*>(kbase + (size_t)KC * 16);             // [KC] class, or class | (next + 1) << 10 with lists
 
     int J = 0x3fffffff;                                   // class window; "infinite" = ungated
     if (variant == 1) J = 0;
@@ -377,12 +460,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         const int nks = min(nk, KC);
         if (use_lists) {
           for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2)
-            for (int k = khead[c2]; k >= 0; k = knext[k])
-              if (suppresses(kbox[k], karea[k], me, my_area, g.thr)) { dead = true; break; }
+            for (int k = khead[c2]; k >= 0; k = (kmeta[k] >> 10) - 1) {
+              const float4 kb = kbox[k];
+              if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+            }
         } else {
           for (int k = 0; k < nks; ++k) {
-            if (abs(kcls[k] - my_cls) > J) continue;
-            if (suppresses(kbox[k], karea[k], me, my_area, g.thr)) { dead = true; break; }
+            if (abs(kmeta[k] - my_cls) > J) continue;
+            const float4 kb = kbox[k];
+            if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
           }
         }
         for (int k = KC; k < nk && !dead; ++k) {           // overflow of the shared-memory list
@@ -475,8 +561,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           kept[e] = c0 + i;
           if (e < KC) {
             const int ci = ccls[i];
-            kbox[e] = cbox[i]; karea[e] = carea[i]; kcls[e] = ci;
-            if (use_lists) knext[e] = atomicExch(&khead[ci], e);
+            kbox[e] = cbox[i];
+            kmeta[e] = use_lists ? (ci | ((atomicExch(&khead[ci], e) + 1) << 10)) : ci;
           }
         }
         if (tid == 0) s_nkept = nk + cnt;
@@ -558,7 +644,7 @@ static int smem_keys_cap(long long per_image) {
   return (int)(p > kMaxSmemKeys ? kMaxSmemKeys : p);
 }
 static int kept_cap_for(long long per_image) {
-  const long long budget = 200 * 1024 - kNmsFixedBytes;
+  const long long budget = kNmsSmemBudget - kNmsFixedBytes;
   long long cap = budget / kKeptEntryBytes;
   if (cap > per_image) cap = per_image;
   return (int)(cap < 1 ? 1 : cap);
@@ -574,6 +660,7 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.kept_cap = kept_cap_for(g.src.per_image);
   g.gkeys_stride = next_pow2_ll(g.src.per_image);
   g.debug = getenv("YX_NMS_DEBUG") ? 1 : 0;
+  g.no_small = getenv("YX_NMS_NO_SMALL") ? 1 : 0;
   const size_t smem = nms_smem_bytes(g.src.per_image);
   static size_t configured_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[current_device_slot()];

@@ -47,15 +47,24 @@ __device__ __forceinline__ void warp_top10(const float* __restrict__ row, int n,
   float lv[10]; int li[10];
 #pragma unroll
   for (int r = 0; r < 10; ++r) { lv[r] = worst; li[r] = kNone; }
-  for (int i = lane; i < n; i += 32) {
-    const float v = row[i];
-    if (before<DESC>(v, i, lv[9], li[9])) {
-      lv[9] = v; li[9] = i;
+  // eight loads in flight per lane: the rows were written by other SMs (L2 round trips), and the insertion branch below
+  // would otherwise serialise one round trip per element
+  for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+    float v8[8];
 #pragma unroll
-      for (int r = 9; r > 0; --r) {
-        if (before<DESC>(lv[r], li[r], lv[r - 1], li[r - 1])) {
-          const float fv = lv[r]; lv[r] = lv[r - 1]; lv[r - 1] = fv;
-          const int fi = li[r]; li[r] = li[r - 1]; li[r - 1] = fi;
+    for (int u = 0; u < 8; ++u) v8[u] = (i0 + 32 * u < n) ? row[i0 + 32 * u] : worst;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + 32 * u;
+      const float v = v8[u];
+      if (i < n && before<DESC>(v, i, lv[9], li[9])) {
+        lv[9] = v; li[9] = i;
+#pragma unroll
+        for (int r = 9; r > 0; --r) {
+          if (before<DESC>(lv[r], li[r], lv[r - 1], li[r - 1])) {
+            const float fv = lv[r]; lv[r] = lv[r - 1]; lv[r - 1] = fv;
+            const int fi = li[r]; li[r] = li[r - 1]; li[r - 1] = fi;
+          }
         }
       }
     }
@@ -192,12 +201,15 @@ __device__ __forceinline__ bool in_centre(float gx, float gy, float xc, float yc
 }
 
 // dynamic shared memory: s_gt [max_gt*5] float | ballots [chunk/32] u32 | tile_c [max_gt][32] float | tile_i [max_gt][32]
+//                        | s_gc [max_gt*5] | s_tab [16 warps][nc][2]
 __global__ void __launch_bounds__(kSimThreads) simota_assign_kernel(const SimotaArgs a) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   float* s_gt = reinterpret_cast<float*>(sim_smem);                 // cls, cx, cy, w, h
   uint32_t* s_bal = reinterpret_cast<uint32_t*>(s_gt + a.max_gt * 5);
   float* tile_c = reinterpret_cast<float*>(s_bal + a.chunk / 32);
   float* tile_i = tile_c + a.max_gt * kSimTile;
+  float* s_gc = tile_i + a.max_gt * kSimTile;            // [max_gt][5] GT corners + area
+  float* s_tab = s_gc + a.max_gt * 5;                    // [kSimWarps][nc][2] per-class log terms of a warp's candidate
   __shared__ int s_G, s_cnt, s_bad;
   __shared__ int warp_sums[kSimWarps];
   const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
@@ -299,49 +311,89 @@ __global__ void __launch_bounds__(kSimThreads) simota_assign_kernel(const Simota
   int* cnt = a.cnt + (long long)b * a.ncap;
   int* m_gt = a.m_gt + (long long)b * a.ncap;
   const int tiles = (n + kSimTile - 1) / kSimTile;
+  // per-GT corners, computed once (x / 2 == x * 0.5 exactly): lo = c - wh/2, hi = c + wh/2, area = w * h
+  for (int g = tid; g < G; g += kSimThreads) {
+    const float gx = s_gt[g * 5 + 1], gy = s_gt[g * 5 + 2], gw = s_gt[g * 5 + 3], gh = s_gt[g * 5 + 4];
+    float* q = s_gc + g * 5;
+    q[0] = __fsub_rn(gx, __fmul_rn(gw, 0.5f)); q[1] = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
+    q[2] = __fadd_rn(gx, __fmul_rn(gw, 0.5f)); q[3] = __fadd_rn(gy, __fmul_rn(gh, 0.5f));
+    q[4] = __fmul_rn(gw, gh);
+  }
+  __syncthreads();
+  // many GTs: the two class-dependent log terms of a candidate are tabulated per class once (80 pairs of logs) instead of
+  // being recomputed per (GT, candidate) pair -- the same expressions on the same inputs, so the costs are bit-identical
+  const bool tabulate = G > 48;
+  float* tab = s_tab + warp * 2 * a.nc;
   for (int t = rank; t < tiles; t += CL) {
     const int i0 = t * kSimTile;
-    for (int j = warp; j < kSimTile; j += kSimWarps) {
-      const int i = i0 + j;
-      if (i >= n) break;                                  // warp-uniform
-      const int an = cand[i];
+    // the warp's two candidates (j = warp, warp + 16): anchor indices, then both rows' loads, are issued before any math
+    // so that the two dependent L2 / HBM round trips per candidate overlap
+    constexpr int kPer = kSimTile / kSimWarps;
+    int an2[kPer]; float obj2[kPer]; float4 box2[kPer]; float cls2[kPer][4];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) an2[u] = (i0 + warp + u * kSimWarps < n) ? cand[i0 + warp + u * kSimWarps] : -1;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      if (an2[u] < 0) continue;
+      const float* row = pred + (long long)an2[u] * nch;
+      obj2[u] = row[4];
+      box2[u] = make_float4(row[0], row[1], row[2], row[3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cls2[u][q] = (lane + 32 * q < a.nc) ? row[5 + lane + 32 * q] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int j = warp + u * kSimWarps;
+      const int an = an2[u];
+      if (an < 0) continue;                               // warp-uniform
       const float* row = pred + (long long)an * nch;
       // S_i = sum_c -max(log(1 - p_ic), -100)   (binary_cross_entropy clamps log at -100)
-      const float so = 1.0f / (1.0f + expf(-row[4]));
+      const float so = 1.0f / (1.0f + expf(-obj2[u]));
       float acc = 0.0f;
-      for (int c = lane; c < a.nc; c += 32) {
-        const float sc = 1.0f / (1.0f + expf(-row[5 + c]));
+      for (int c = lane, q = 0; c < a.nc; c += 32, ++q) {
+        const float lg = q < 4 ? cls2[u][q < 4 ? q : 0] : row[5 + c];
+        const float sc = 1.0f / (1.0f + expf(-lg));
         const float p = sqrtf(sc * so);
-        acc += -fmaxf(logf(1.0f - p), -100.0f);
+        const float l1 = fmaxf(logf(1.0f - p), -100.0f);
+        acc += -l1;
+        if (tabulate) { tab[2 * c] = l1; tab[2 * c + 1] = fmaxf(logf(p), -100.0f); }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const float S = acc;
-      const float px = row[0], py = row[1], pw = row[2], ph = row[3];
+      const float px = box2[u].x, py = box2[u].y, pw = box2[u].z, ph = box2[u].w;
+      const float plx = __fsub_rn(px, __fmul_rn(pw, 0.5f)), ply = __fsub_rn(py, __fmul_rn(ph, 0.5f));
+      const float phx = __fadd_rn(px, __fmul_rn(pw, 0.5f)), phy = __fadd_rn(py, __fmul_rn(ph, 0.5f));
+      const float parea = __fmul_rn(pw, ph);
       const float s = a.st[an];
       const float xc = __fmul_rn(__fadd_rn(a.xs[an], 0.5f), s);
       const float yc = __fmul_rn(__fadd_rn(a.ys[an], 0.5f), s);
+      __syncwarp();
       for (int g = lane; g < G; g += 32) {
-        const float gx = s_gt[g * 5 + 1], gy = s_gt[g * 5 + 2], gw = s_gt[g * 5 + 3], gh = s_gt[g * 5 + 4];
+        const float* q = s_gc + g * 5;
         // bboxes_iou(gt, pred, xyxy=False)  (boxes.py:88-101)
-        const float tlx = fmaxf(__fsub_rn(gx, __fdiv_rn(gw, 2.0f)), __fsub_rn(px, __fdiv_rn(pw, 2.0f)));
-        const float tly = fmaxf(__fsub_rn(gy, __fdiv_rn(gh, 2.0f)), __fsub_rn(py, __fdiv_rn(ph, 2.0f)));
-        const float brx = fminf(__fadd_rn(gx, __fdiv_rn(gw, 2.0f)), __fadd_rn(px, __fdiv_rn(pw, 2.0f)));
-        const float bry = fminf(__fadd_rn(gy, __fdiv_rn(gh, 2.0f)), __fadd_rn(py, __fdiv_rn(ph, 2.0f)));
+        const float tlx = fmaxf(q[0], plx), tly = fmaxf(q[1], ply);
+        const float brx = fminf(q[2], phx), bry = fminf(q[3], phy);
         const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
         const float area_i = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);
-        const float v_iou = __fdiv_rn(area_i, __fsub_rn(__fadd_rn(__fmul_rn(gw, gh), __fmul_rn(pw, ph)), area_i));
+        const float v_iou = __fdiv_rn(area_i, __fsub_rn(__fadd_rn(q[4], parea), area_i));
         // class cost; a class id outside [0, nc) (F.one_hot raises in the reference) is flagged and clamped
         int gc = (int)s_gt[g * 5 + 0];
         if (gc < 0 || gc >= a.nc) { s_bad = 1; gc = gc < 0 ? 0 : a.nc - 1; }
-        const float sc = 1.0f / (1.0f + expf(-row[5 + gc]));
-        const float p = sqrtf(sc * so);
-        const float cls_cost = S + fmaxf(logf(1.0f - p), -100.0f) - fmaxf(logf(p), -100.0f);
-        const float pen = in_centre(gx, gy, xc, yc, s) ? 0.0f : 1.0e6f;
+        float l1, lp;
+        if (tabulate) { l1 = tab[2 * gc]; lp = tab[2 * gc + 1]; }
+        else {
+          const float sc = 1.0f / (1.0f + expf(-row[5 + gc]));
+          const float p = sqrtf(sc * so);
+          l1 = fmaxf(logf(1.0f - p), -100.0f); lp = fmaxf(logf(p), -100.0f);
+        }
+        const float cls_cost = S + l1 - lp;
+        const float pen = in_centre(s_gt[g * 5 + 1], s_gt[g * 5 + 2], xc, yc, s) ? 0.0f : 1.0e6f;
         const float iou_loss = -logf(v_iou + 1e-8f);
         tile_c[g * kSimTile + j] = __fadd_rn(__fadd_rn(cls_cost, __fmul_rn(3.0f, iou_loss)), pen);
         tile_i[g * kSimTile + j] = v_iou;
       }
+      __syncwarp();
     }
     __syncthreads();
     const int valid = min(kSimTile, n - i0);
@@ -426,7 +478,8 @@ int simota_assign_launch(const float* pred, const float* labels, const float* xs
   a.iou = reinterpret_cast<float*>(p + off); off += a256((size_t)batch * max_gt * a.ncap * 4);
   a.cnt = reinterpret_cast<int*>(p + off); off += a256((size_t)batch * a.ncap * 4);
   a.m_gt = reinterpret_cast<int*>(p + off); off += a256((size_t)batch * a.ncap * 4);
-  const size_t smem = (size_t)max_gt * 5 * 4 + (size_t)(a.chunk / 32) * 4 + 2 * (size_t)max_gt * kSimTile * 4;
+  const size_t smem = 2 * (size_t)max_gt * 5 * 4 + (size_t)(a.chunk / 32) * 4 + 2 * (size_t)max_gt * kSimTile * 4 +
+                      (size_t)kSimWarps * nc * 8;
   YX_REQUIRE(smem <= 200 * 1024, YX_ERR_UNSUPPORTED, "simota: %zu bytes of shared memory needed (anchors=%d, max_gt=%d)", smem, anchors, max_gt);
   static size_t configured_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[current_device_slot()];

@@ -172,3 +172,42 @@ def test_processor_postprocess_matches_oracle(cuda):
         assert r["labels"] == [int(v) for v in w[:, 6]]
         np.testing.assert_allclose(np.array(r["bboxes"], dtype=np.float32), w[:, :4] / np.float32(ratio), rtol=1e-6)
         np.testing.assert_allclose(r["scores"], [float(a) * float(b) for a, b in zip(w[:, 4], w[:, 5])], rtol=0)
+
+
+@pytest.mark.parametrize("variant", ["offset", "per_class", "auto"])
+def test_single_warp_path_equals_chunked_path_and_oracle(cuda, variant, monkeypatch):
+    """n <= 32 candidates take the single-warp path (registers only); the chunked shared-memory path on the same input
+    (YX_NMS_NO_SMALL) and the oracle must keep the same rows: ties, zero-area boxes, negative coordinates, n = 1 / 32."""
+    rng = np.random.default_rng(9)
+    for n_img, A in ((3, 32), (2, 24), (2, 1), (1, 40)):
+        pred = np.zeros((n_img, A, 85), dtype=np.float32)
+        pred[:, :, 0:2] = rng.uniform(-5, 120, (n_img, A, 2))
+        pred[:, :, 2:4] = rng.uniform(10, 60, (n_img, A, 2))
+        pred[:, :, 4] = np.round(rng.uniform(0.3, 1.0, (n_img, A)), 1)            # many tied scores
+        cls = rng.integers(0, 4, (n_img, A))
+        np.put_along_axis(pred[:, :, 5:], cls[..., None], 0.9, axis=2)
+        pred[0, :3, 2:4] = 0.0                                                    # zero-area boxes
+        if A > 8:
+            pred[0, 5:8] = pred[0, 4]                                             # exact duplicates
+        want, _ = po.postprocess(pred.copy(), 80, 0.2, 0.5, variant="offset" if variant == "auto" else variant, return_indices=True)
+        got = yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.2, 0.5, nms_variant=variant)
+        _check_lists(got, want)
+        monkeypatch.setenv("YX_NMS_NO_SMALL", "1")
+        _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.2, 0.5, nms_variant=variant), want)
+        monkeypatch.delenv("YX_NMS_NO_SMALL")
+
+
+def test_every_anchor_kept_stays_in_shared_memory(cuda):
+    """8 400 disjoint boxes (nothing suppresses anything; what conf 0.01 gives on random weights): the kept list of a
+    640^2 image fits the shared-memory list, all rows come back in score order."""
+    A = 8400
+    pred = np.zeros((2, A, 85), dtype=np.float32)
+    gx, gy = np.meshgrid(np.arange(100), np.arange(84))
+    pred[:, :, 0] = (gx.reshape(-1) * 6.0 + 3.0)[None]; pred[:, :, 1] = (gy.reshape(-1) * 6.0 + 3.0)[None]
+    pred[:, :, 2:4] = 5.0
+    rng = np.random.default_rng(10)
+    pred[:, :, 4] = rng.uniform(0.5, 1.0, (2, A))
+    np.put_along_axis(pred[:, :, 5:], rng.integers(0, 80, (2, A))[..., None], 0.9, axis=2)
+    want, _ = po.postprocess(pred.copy(), 80, 0.01, 0.65, variant="offset", return_indices=True)
+    assert all(len(w) == A for w in want)
+    _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.01, 0.65, nms_variant="offset"), want)
