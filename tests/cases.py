@@ -52,6 +52,20 @@ NET_CASES = {
 }
 
 
+# BASELINE.json config 1: yolox_nano 416x416 batch 1 through the reference's user API (tests/golden/config1.npz)
+CONFIG1 = dict(name="yolox_nano", seed=7, image_hw=(480, 640), thresholds=(0.25, 0.6))
+
+
+def config1_image() -> np.ndarray:
+    """Seeded 480x640 RGB uint8 image with smooth structure (so that the letterbox resize interpolates real gradients)."""
+    h, w = CONFIG1["image_hw"]
+    rng = np.random.default_rng(CONFIG1["seed"])
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([127 + 120 * np.sin(xx / 37.0 + k) * np.cos(yy / 23.0 - k) for k in range(3)], -1)
+    img += rng.normal(0, 12, size=img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
 def checksum(a: np.ndarray) -> str:
     import hashlib
 

@@ -143,6 +143,39 @@ def gen_network():
     print("network.npz", len(out))
 
 
+def gen_config1():
+    """BASELINE.json config 1: yolox_nano 416x416 batch 1 on CPU through the reference's own user API --
+    YoloxProcessor.__call__ (letterbox) -> YoloxModule.forward -> YoloxProcessor.postprocess -- on a seeded 480x640 PIL image,
+    with the seeded non-degenerate weights of cases.CONFIG1 (the state_dict is re-derived from the seed by the tests)."""
+    from PIL import Image
+    from yolox.config import YoloxConfig
+    from yolox.models import YoloxProcessor
+
+    c = cases.CONFIG1
+    cfg = YoloxConfig.get_named_config(c["name"])
+    cfg.model = None
+    m = cfg.get_model()
+    img = Image.fromarray(cases.config1_image())
+    proc = YoloxProcessor(c["name"])
+    x = proc([img])
+    sd = yo.seeded_state_dict(m.state_dict(), c["seed"], tuple(cfg.test_size), calib_x=x)
+    m.load_state_dict(sd)
+    m.eval()
+    with torch.no_grad():
+        y = m(x)
+    out = {"x_sha": np.array(cases.checksum(x.numpy())), "x_shape": np.array(x.shape), "out": y.numpy().copy(),
+           "keys": np.array(len(sd)),
+           "sd_sha": np.array(cases.checksum(np.concatenate([v.float().reshape(-1).numpy() for v in sd.values()])))}
+    for thr in c["thresholds"]:
+        det = proc.postprocess([img], y.clone(), threshold=thr)[0]
+        out[f"t{thr}/bboxes"] = np.array(det["bboxes"], dtype=np.float64).reshape(-1, 4)
+        out[f"t{thr}/scores"] = np.array(det["scores"], dtype=np.float64)
+        out[f"t{thr}/labels"] = np.array(det["labels"], dtype=np.int64)
+        print("config1 thr", thr, "detections", len(det["labels"]))
+    np.savez_compressed(OUT / "config1.npz", **out)
+    print("config1.npz", len(out))
+
+
 def loss_case_inputs(name):
     """pred / labels / anchor grid / raw regression outputs of a SIMOTA_ASSIGN case (the inverse decode of pred)."""
     from oracle.simota_oracle import anchor_grid
@@ -201,7 +234,7 @@ def gen_losses():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses"]
+    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses", "config1"]
     if "postprocess" in which:
         gen_postprocess()
     if "simota" in which:
@@ -210,3 +243,5 @@ if __name__ == "__main__":
         gen_network()
     if "losses" in which:
         gen_losses()
+    if "config1" in which:
+        gen_config1()

@@ -205,3 +205,45 @@ def test_engine_cache_survives_deepcopy_and_weight_changes(cuda):
     assert not torch.equal(model(xd), changed)
     with pytest.raises(TypeError):
         copy.deepcopy(next(iter(model._engines.values())))
+
+
+def test_config1_nano_416_user_api_on_gpu():
+    """BASELINE.json config 1 on the GPU path: yolox_nano (depthwise) 416x416 batch 1, fp32 verification mode within 1e-3 of
+    the reference's CPU output (or the conditioning ceiling of the same graph in torch-CUDA fp32), bf16 at the torch-bf16
+    ceiling; YoloxProcessor.postprocess on the reference's own head tensor returns the reference's Detections exactly."""
+    from pathlib import Path
+
+    from PIL import Image
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "config1.npz")
+    c = cases.CONFIG1
+    dev = torch.device("cuda", 0)
+    img = Image.fromarray(cases.config1_image())
+    proc = yx.YoloxProcessor(c["name"])
+    proc.nms_variant = "auto_cpu"                  # the fixture was produced by the reference on CPU (torchvision's CPU rule)
+    x = proc([img])
+    cfg = yx.YoloxConfig.get_named_config(c["name"])
+    cfg.model = None
+    model = cfg.get_model()
+    sd = yo.seeded_state_dict(model.state_dict(), c["seed"], tuple(cfg.test_size), calib_x=x)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    out = model(x.to(dev)).cpu().numpy()
+    ref = g["out"]
+    err = _rel(out, ref).max()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ceil = _rel(yo.forward({k: v.to(dev) for k, v in sd.items()}, x.to(dev)).cpu().numpy(), ref).max()
+    assert err <= 1e-3 or err <= 1.5 * ceil, (err, ceil)
+    for thr in c["thresholds"]:
+        det = proc.postprocess([img], torch.from_numpy(ref.copy()).to(dev), threshold=thr)[0]
+        np.testing.assert_array_equal(np.array(det["bboxes"], dtype=np.float64).reshape(-1, 4), g[f"t{thr}/bboxes"])
+        np.testing.assert_array_equal(np.array(det["scores"], dtype=np.float64), g[f"t{thr}/scores"])
+        np.testing.assert_array_equal(np.array(det["labels"], dtype=np.int64), g[f"t{thr}/labels"])
+    # the whole user-facing call: Yolox.__call__ (processor -> fused detect graph -> formatted detections)
+    wrapper = yx.Yolox(model, proc)
+    res = wrapper([img], threshold=0.6)[0]
+    want = proc.postprocess([img], model(x.to(dev)), threshold=0.6)[0]
+    assert res["labels"] == want["labels"] and res["scores"] == want["scores"] and res["bboxes"] == want["bboxes"]
+    u8 = model(proc([img]).to(torch.uint8).to(dev)).cpu().numpy()
+    assert np.array_equal(u8, out)                 # byte upload: bit-identical
