@@ -300,6 +300,58 @@ int yx_head_losses(const float* pred, const float* labels, int32_t max_gt, const
                    float* grad, float* grad_origin, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training branch of YoloxHead.forward for ONE level (yolox/models/yolo_head.py:161-201, get_output_and_grid :213-231):
+ * reg [B,4,h,w], obj [B,1,h,w], cls [B,nc,h,w] contiguous NCHW conv outputs (dtype: YX_FP32 / YX_BF16 / YX_FP16) ->
+ * rows [anchor_off, anchor_off + h*w) of out [B, anchors, 5+nc] fp32: xy = (xy + grid) * stride, wh = exp(wh) * stride,
+ * raw obj / cls logits; origin (may be NULL): [B, anchors, 4] fp32 raw regression rows (`origin_preds`, :190-200).
+ * _bwd: grad_out [B, anchors, 5+nc] fp32 (+ grad_origin or NULL) and the forward's `out` -> gradients of reg / obj / cls
+ * in their own layout and dtype.
+ * ------------------------------------------------------------------------------------------ */
+int yx_head_train_decode(const void* reg, const void* obj, const void* cls, int32_t dtype, int32_t batch, int32_t nc,
+                         int32_t h, int32_t w, float stride, int32_t anchors, int32_t anchor_off, float* out,
+                         float* origin, void* stream);
+int yx_head_train_decode_bwd(const float* grad_out, const float* out, const float* grad_origin, int32_t dtype,
+                             int32_t batch, int32_t nc, int32_t h, int32_t w, float stride, int32_t anchors,
+                             int32_t anchor_off, void* grad_reg, void* grad_obj, void* grad_cls, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step + EMA update of every tensor in one launch: torch.optim.SGD(momentum, nesterov, per-group weight decay)
+ * as built by yolox/config.py:307-333, and ModelEMA.update (yolox/utils/ema.py:46-58).
+ *   table  : device int64 [n_tensors, 6] rows = param ptr | grad ptr (0: EMA only, e.g. BN running statistics) |
+ *            momentum-buffer ptr | ema ptr (0: none) | numel | weight decay (fp32 bits in the low word); fp32 tensors
+ *   chunks : device int32 [n_chunks, 2] rows = (tensor index, first element); one CTA per chunk of chunk_elems elements
+ *   first_step != 0: momentum buffers are initialised with the gradient (torch's first step)
+ *   ema_decay d and ema_rest = (float)(1.0 - d) with d = decay * (1 - exp(-updates / 2000)) evaluated by the caller.
+ * ------------------------------------------------------------------------------------------ */
+int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float lr,
+                    float momentum, int32_t nesterov, int32_t first_step, float ema_decay, float ema_rest,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Test-time preprocessing on the device (`preproc`, yolox/data/data_augment.py:140-156; YoloxProcessor.__call__,
+ * yolox/models/processor.py:30-37): aspect-preserving cv2.resize(INTER_LINEAR) of each decoded HWC uint8 image into the
+ * top-left corner of a 114-grey H x W canvas, HWC -> CHW. Bit-exact with OpenCV's 8-bit fixed-point bilinear.
+ *   images : device array of `batch` yx_letterbox_image records; out: [batch, channels, H, W] YX_U8 or YX_FP32 (0..255)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yx_letterbox_image {
+  const uint8_t* src;   /* device pointer, HWC uint8 */
+  int32_t h, w;         /* source height / width */
+  int64_t pitch;        /* bytes per source row */
+} yx_letterbox_image;
+int yx_letterbox_u8(const yx_letterbox_image* images, int32_t batch, int32_t channels, int32_t H, int32_t W,
+                    void* out, int32_t out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluator result rows (CocoEvaluator.convert_to_coco_format, yolox/evaluators/coco_evaluator.py:205-251) from the
+ * detections of yx_postprocess / yx_nms_prefiltered: for image b and kept row k < min(det_count[b], max_det):
+ * bbox = xyxy / scale[b] -> (x, y, w, h); score = obj * class_conf; category = class_ids[cls] (class_ids may be NULL);
+ * rows of all images compacted in image order. Outputs sized batch * max_det rows; total[0] = number written.
+ * ------------------------------------------------------------------------------------------ */
+int yx_coco_rows(const float* dets, const int32_t* det_count, int32_t batch, int32_t max_det, const float* scale,
+                 const int64_t* image_ids, const int32_t* class_ids, int32_t n_class_ids, float* bbox, float* score,
+                 int32_t* category, int64_t* image_id, int32_t* total, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Plan: the native runtime.  A plan is an ordered list of the launches of one forward pass
  * (YoloxModule.forward eval branch, yolox/models/yolox.py:72-92) over pre-allocated buffers.
  * Tensor maps are encoded once at add time; yx_plan_run enqueues every launch on `stream`

@@ -50,6 +50,17 @@ int simota_assign_launch(const float* pred, const float* labels, const float* xs
                          long long ws_bytes, cudaStream_t s);
 int simota_matching_launch(const float* cost, const float* ious, int G, int n, long long ld, int* match_gt,
                            float* match_iou, int* num_fg, cudaStream_t s);
+int head_train_decode_launch(const void* reg, const void* obj, const void* cls, int dtype, int batch, int nc, int h, int w,
+                             float stride, int anchors, int anchor_off, float* out, float* origin, cudaStream_t s);
+int head_train_decode_bwd_launch(const float* gout, const float* out, const float* gorigin, int dtype, int batch, int nc, int h,
+                                 int w, float stride, int anchors, int anchor_off, void* greg, void* gobj, void* gcls,
+                                 cudaStream_t s);
+int sgd_ema_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, float lr, float momentum,
+                   int nesterov, int first_step, float ema_decay, float ema_rest, cudaStream_t s);
+int letterbox_launch(const void* images_dev, int batch, int channels, int H, int W, void* out, int out_dtype, cudaStream_t s);
+int coco_rows_launch(const float* dets, const int* det_count, int batch, int max_det, const float* scale,
+                     const long long* image_ids, const int* class_ids, int n_class_ids, float* bbox, float* score,
+                     int* category, long long* image_id, int* total, cudaStream_t s);
 struct StemLaunch;
 StemLaunch* stem_alloc();
 void stem_free(StemLaunch*);
@@ -369,6 +380,50 @@ int yx_simota_matching(const float* cost, const float* ious, int32_t num_gt, int
   int rc = require_device();
   if (rc) return rc;
   return simota_matching_launch(cost, ious, num_gt, n, ld, match_gt, match_iou, num_fg, (cudaStream_t)stream);
+}
+
+int yx_head_train_decode(const void* reg, const void* obj, const void* cls, int32_t dtype, int32_t batch, int32_t nc,
+                         int32_t h, int32_t w, float stride, int32_t anchors, int32_t anchor_off, float* out,
+                         float* origin, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return head_train_decode_launch(reg, obj, cls, dtype, batch, nc, h, w, stride, anchors, anchor_off, out, origin,
+                                  (cudaStream_t)stream);
+}
+
+int yx_head_train_decode_bwd(const float* grad_out, const float* out, const float* grad_origin, int32_t dtype,
+                             int32_t batch, int32_t nc, int32_t h, int32_t w, float stride, int32_t anchors,
+                             int32_t anchor_off, void* grad_reg, void* grad_obj, void* grad_cls, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return head_train_decode_bwd_launch(grad_out, out, grad_origin, dtype, batch, nc, h, w, stride, anchors, anchor_off,
+                                      grad_reg, grad_obj, grad_cls, (cudaStream_t)stream);
+}
+
+int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float lr,
+                    float momentum, int32_t nesterov, int32_t first_step, float ema_decay, float ema_rest,
+                    void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return sgd_ema_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, lr, momentum, nesterov,
+                        first_step, ema_decay, ema_rest, (cudaStream_t)stream);
+}
+
+int yx_letterbox_u8(const yx_letterbox_image* images, int32_t batch, int32_t channels, int32_t H, int32_t W, void* out,
+                    int32_t out_dtype, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return letterbox_launch(images, batch, channels, H, W, out, out_dtype, (cudaStream_t)stream);
+}
+
+int yx_coco_rows(const float* dets, const int32_t* det_count, int32_t batch, int32_t max_det, const float* scale,
+                 const int64_t* image_ids, const int32_t* class_ids, int32_t n_class_ids, float* bbox, float* score,
+                 int32_t* category, int64_t* image_id, int32_t* total, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return coco_rows_launch(dets, det_count, batch, max_det, scale, reinterpret_cast<const long long*>(image_ids), class_ids,
+                          n_class_ids, bbox, score, category, reinterpret_cast<long long*>(image_id), total,
+                          (cudaStream_t)stream);
 }
 
 int yx_head_losses(const float* pred, const float* labels, int32_t max_gt, const uint8_t* fg_mask,

@@ -437,3 +437,112 @@ def bottleneck_fwd(x: View, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor
     d.w1, d.bias1, d.w2, d.bias2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
     d.out, d.out_ld = out.ptr, out.ld
     check(lib().yx_bottleneck_fwd(C.byref(d), stream_ptr(x.t.device)), "bottleneck_fwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# training branch rows, optimizer + EMA, preprocessing, evaluator rows
+# ---------------------------------------------------------------------------------------------
+def head_train_decode(reg: torch.Tensor, obj: torch.Tensor, cls: torch.Tensor, stride: float, out: torch.Tensor,
+                      anchor_off: int, origin: Optional[torch.Tensor] = None) -> None:
+    """One level of the training branch (yolo_head.py:161-201, 213-231): NCHW conv outputs -> decoded fp32 rows
+    [anchor_off, anchor_off + h*w) of `out` [B, A, 5+nc] (and the raw regression rows of `origin` [B, A, 4])."""
+    require_cuda(reg, "head_train_decode")
+    dev = reg.device
+    same_device(dev, "head_train_decode", obj=obj, cls=cls, out=out, origin=origin)
+    B, _, h, w = reg.shape
+    nc = cls.shape[1]
+    assert reg.shape[1] == 4 and obj.shape[1] == 1 and reg.dtype == obj.dtype == cls.dtype
+    assert reg.is_contiguous() and obj.is_contiguous() and cls.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    assert out.shape[0] == B and out.shape[2] == 5 + nc and (origin is None or (origin.is_contiguous() and origin.dtype == torch.float32))
+    with on_device(dev):
+        check(lib().yx_head_train_decode(reg.data_ptr(), obj.data_ptr(), cls.data_ptr(), dtype_code(reg.dtype), B, nc, h, w,
+                                         float(stride), out.shape[1], int(anchor_off), out.data_ptr(),
+                                         0 if origin is None else origin.data_ptr(), stream_ptr(dev)), "head_train_decode")
+
+
+def head_train_decode_bwd(grad_out: torch.Tensor, out: torch.Tensor, grad_origin: Optional[torch.Tensor], stride: float,
+                          anchor_off: int, g_reg: torch.Tensor, g_obj: torch.Tensor, g_cls: torch.Tensor) -> None:
+    dev = grad_out.device
+    same_device(dev, "head_train_decode_bwd", out=out, grad_origin=grad_origin, g_reg=g_reg, g_obj=g_obj, g_cls=g_cls)
+    B, _, h, w = g_reg.shape
+    assert grad_out.is_contiguous() and out.is_contiguous() and grad_out.dtype == out.dtype == torch.float32
+    with on_device(dev):
+        check(lib().yx_head_train_decode_bwd(grad_out.data_ptr(), out.data_ptr(), 0 if grad_origin is None else grad_origin.data_ptr(),
+                                             dtype_code(g_reg.dtype), B, g_cls.shape[1], h, w, float(stride), out.shape[1],
+                                             int(anchor_off), g_reg.data_ptr(), g_obj.data_ptr(), g_cls.data_ptr(),
+                                             stream_ptr(dev)), "head_train_decode_bwd")
+
+
+def sgd_ema_step(table: torch.Tensor, chunks: torch.Tensor, chunk_elems: int, lr: float, momentum: float, nesterov: bool,
+                 first_step: bool, ema_decay: float) -> None:
+    """One launch over every tensor of `table` (see include/yx_b200.h: yx_sgd_ema_step)."""
+    import numpy as np
+
+    dev = table.device
+    same_device(dev, "sgd_ema_step", chunks=chunks)
+    with on_device(dev):
+        check(lib().yx_sgd_ema_step(table.data_ptr(), chunks.data_ptr(), chunks.shape[0], int(chunk_elems), float(lr), float(momentum),
+                                    1 if nesterov else 0, 1 if first_step else 0, float(np.float32(ema_decay)),
+                                    float(np.float32(1.0 - ema_decay)), stream_ptr(dev)), "sgd_ema_step")
+
+
+def letterbox_u8(images, size, device: torch.device, dtype: torch.dtype = torch.uint8) -> torch.Tensor:
+    """`preproc` (data_augment.py:140-156) for a list of decoded HWC (or HW) uint8 numpy images, on the device: the raw bytes
+    are packed into one pinned buffer, uploaded with one copy and resized / padded / transposed by one launch. Returns
+    [B, C, H, W] uint8 or float32 (0..255)."""
+    import numpy as np
+
+    if device.type != "cuda":
+        raise RuntimeError("letterbox_u8 needs a CUDA device (the B200 path has no CPU fallback; use processor.letterbox on the host)")
+    H, W = int(size[0]), int(size[1])
+    imgs = [np.ascontiguousarray(im if im.ndim == 3 else im[..., None]) for im in images]
+    ch = imgs[0].shape[2]
+    assert all(im.dtype == np.uint8 and im.shape[2] == ch for im in imgs), "letterbox_u8: uint8 images with the same channel count"
+    offs, total = [], 0
+    for im in imgs:
+        offs.append(total)
+        total += (im.size + 255) & ~255
+    host = torch.empty(total + 24 * len(imgs), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for im, o in zip(imgs, offs):
+        hv[o:o + im.size] = im.reshape(-1)
+    raw = host.to(device, non_blocking=True)
+    base = raw.data_ptr()
+    table = np.zeros((len(imgs), 3), dtype=np.int64)            # yx_letterbox_image: ptr | (h, w) packed | pitch
+    for i, (im, o) in enumerate(zip(imgs, offs)):
+        table[i, 0] = base + o
+        table[i, 1] = int(im.shape[0]) | (int(im.shape[1]) << 32)
+        table[i, 2] = im.shape[1] * ch
+    tdev = torch.from_numpy(table).to(device)
+    out = torch.empty((len(imgs), ch, H, W), dtype=dtype, device=device)
+    with on_device(device):
+        check(lib().yx_letterbox_u8(tdev.data_ptr(), len(imgs), ch, H, W, out.data_ptr(), dtype_code(dtype), stream_ptr(device)),
+              "letterbox_u8")
+    out._yx_keepalive = (raw, tdev)      # the launch is asynchronous: keep the sources alive with the result
+    return out
+
+
+def coco_rows(dets: torch.Tensor, det_count: torch.Tensor, scale: torch.Tensor, image_ids: torch.Tensor,
+              class_ids: Optional[torch.Tensor] = None):
+    """Device half of convert_to_coco_format (coco_evaluator.py:205-251). Returns (bbox_xywh [N,4], score [N], category [N],
+    image_id [N]) as HOST tensors after one device->host copy."""
+    require_cuda(dets, "coco_rows")
+    dev = dets.device
+    B, max_det, _ = dets.shape
+    dets = dets.contiguous().float()
+    det_count = det_count.contiguous().to(torch.int32)
+    scale = scale.to(dev).contiguous().float()
+    image_ids = image_ids.to(dev).contiguous().to(torch.int64)
+    cid = None if class_ids is None else class_ids.to(dev).contiguous().to(torch.int32)
+    n = B * max_det
+    bbox = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((n,), dtype=torch.float32, device=dev)
+    cat = torch.empty((n,), dtype=torch.int32, device=dev)
+    iid = torch.empty((n,), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with on_device(dev):
+        check(lib().yx_coco_rows(dets.data_ptr(), det_count.data_ptr(), B, max_det, scale.data_ptr(), image_ids.data_ptr(),
+                                 0 if cid is None else cid.data_ptr(), 0 if cid is None else cid.numel(), bbox.data_ptr(),
+                                 score.data_ptr(), cat.data_ptr(), iid.data_ptr(), total.data_ptr(), stream_ptr(dev)), "coco_rows")
+    k = int(total.item())
+    return bbox[:k].cpu(), score[:k].cpu(), cat[:k].cpu(), iid[:k].cpu()

@@ -1,0 +1,105 @@
+"""The reference's optimizer step and EMA update (yolox/config.py:307-333: SGD momentum 0.9, nesterov, weight decay on conv /
+linear weights only; yolox/utils/ema.py:15-58: ModelEMA with decay * (1 - exp(-updates / 2000))) as ONE kernel launch over
+every parameter and buffer of the model (csrc/yx_train.cu: sgd_ema_kernel), instead of ~3 foreach launches per group plus
+two elementwise kernels per state tensor for the EMA."""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def reference_param_groups(model: nn.Module):
+    """pg0 (BN weights, no decay), pg1 (conv / linear weights, decay), pg2 (biases, no decay): config.py:316-324."""
+    pg0, pg1, pg2 = [], [], []
+    for k, v in model.named_modules():
+        if hasattr(v, "bias") and isinstance(v.bias, nn.Parameter):
+            pg2.append(v.bias)
+        if isinstance(v, nn.BatchNorm2d) or "bn" in k:
+            pg0.append(v.weight)
+        elif hasattr(v, "weight") and isinstance(v.weight, nn.Parameter):
+            pg1.append(v.weight)
+    return pg0, pg1, pg2
+
+
+class FusedSgdEma:
+    """step(): p <- SGD(p, grad) for every parameter, then ema <- d * ema + (1 - d) * value for every floating-point
+    state tensor (parameters and BN running statistics), all in one launch. `ema` is a deep copy of the model in eval
+    mode (ModelEMA.ema); pass ema=False for the optimizer alone."""
+
+    CHUNK = 16384
+
+    def __init__(self, model: nn.Module, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, nesterov: bool = True,
+                 ema: bool = True, ema_decay: float = 0.9998, updates: int = 0):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedSgdEma needs the model on a CUDA device (the B200 path has no CPU fallback)")
+        self.model, self.lr, self.momentum, self.nesterov = model, float(lr), float(momentum), bool(nesterov)
+        self.ema_decay, self.updates = float(ema_decay), int(updates)
+        self.ema = None
+        if ema:
+            self.ema = copy.deepcopy(model).eval()
+            for p in self.ema.parameters():
+                p.requires_grad_(False)
+        pg0, pg1, pg2 = reference_param_groups(model)
+        wd = {id(p): 0.0 for p in pg0 + pg2}
+        wd.update({id(p): float(weight_decay) for p in pg1})
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        missing = [p for p in self.params if id(p) not in wd]
+        if missing:
+            raise ValueError(f"{len(missing)} trainable parameters belong to no reference parameter group")
+        self.bufs = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self._wd = [wd[id(p)] for p in self.params]
+        self._steps = 0
+        self._table = None
+        self._dev = dev
+
+    def _build_table(self):
+        """(re)built when a gradient tensor was reallocated (zero_grad(set_to_none=True) gives new storage each step only
+        if the allocator hands out a different block; pointers are compared on every step, which is 460 integer reads)."""
+        rows, ema_sd = [], (dict(self.ema.state_dict()) if self.ema is not None else {})
+        names = {id(v): k for k, v in self.model.state_dict(keep_vars=True).items()}
+        seen = set()
+        for p, buf, w in zip(self.params, self.bufs, self._wd):
+            assert p.dtype == torch.float32 and p.is_contiguous() and p.grad is not None and p.grad.is_contiguous()
+            e = ema_sd.get(names.get(id(p)))
+            rows.append((p.data_ptr(), p.grad.data_ptr(), buf.data_ptr(), 0 if e is None else e.data_ptr(), p.numel(),
+                         int(np.float32(w).view(np.int32)) & 0xffffffff))
+            seen.add(names.get(id(p)))
+        if self.ema is not None:            # floating-point buffers (BN running mean / var): EMA only
+            for k, v in self.model.state_dict().items():
+                if k in seen or not v.dtype.is_floating_point:
+                    continue
+                rows.append((v.data_ptr(), 0, 0, ema_sd[k].data_ptr(), v.numel(), 0))
+        table = np.array(rows, dtype=np.int64).reshape(-1, 6)
+        chunks = [(t, e) for t, r in enumerate(rows) for e in range(0, r[4], self.CHUNK)]
+        self._table = torch.from_numpy(table).to(self._dev)
+        self._chunks = torch.from_numpy(np.array(chunks, dtype=np.int32).reshape(-1, 2)).to(self._dev)
+        self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
+
+    def zero_grad(self):
+        """Keeps the gradient storage (the pointer table stays valid): grads are zeroed in place."""
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self, lr: Optional[float] = None):
+        if lr is not None:
+            self.lr = float(lr)
+        if self._table is None or any(p.grad is None or p.grad.data_ptr() != q for p, q in zip(self.params, self._grad_ptrs)):
+            if any(p.grad is None for p in self.params):
+                raise RuntimeError("FusedSgdEma.step: a trainable parameter has no gradient")
+            self._build_table()
+        d = 0.0
+        if self.ema is not None:
+            self.updates += 1
+            d = self.ema_decay * (1 - math.exp(-self.updates / 2000))
+        ops.sgd_ema_step(self._table, self._chunks, self.CHUNK, self.lr, self.momentum, self.nesterov, self._steps == 0, d)
+        self._steps += 1

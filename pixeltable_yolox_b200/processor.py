@@ -46,8 +46,16 @@ class YoloxProcessor:
             raise ValueError("model_name_or_config must be a string or YoloxConfig")
         self.nms_variant = "auto"
         self.dtype = torch.float32      # torch.uint8: upload bytes, YoloxModule converts on the device
+        # a CUDA device: the letterbox (resize + pad + HWC->CHW) runs there too, bit-exact with cv2 (csrc/yx_preproc.cu);
+        # only the decoded image bytes cross PCIe and the returned tensor is already on the device
+        self.device = None
 
     def __call__(self, inputs: Iterable) -> torch.Tensor:
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            from . import ops
+
+            return ops.letterbox_u8([np.asarray(im) for im in inputs], self.config.test_size, torch.device(self.device),
+                                    torch.uint8 if self.dtype == torch.uint8 else torch.float32)
         npdt = np.uint8 if self.dtype == torch.uint8 else np.float32
         return torch.stack([torch.from_numpy(letterbox(np.array(im), self.config.test_size, npdt)) for im in inputs])
 

@@ -42,6 +42,36 @@ class _FusedHeadLoss(torch.autograd.Function):
         return (grad * g_total, g_or * g_total if ctx.has_origin else None, None, None, None, None, None, None, None)
 
 
+class _TrainRows(torch.autograd.Function):
+    """One level of the training branch (yolo_head.py:161-201 + get_output_and_grid :213-231) as one kernel each way:
+    (reg, obj, cls) NCHW conv outputs -> decoded fp32 rows [B, h*w, 5+nc] (+ the raw regression rows for the L1 term)."""
+
+    @staticmethod
+    def forward(ctx, reg, obj, cls, stride, want_origin):
+        B, _, h, w = reg.shape
+        reg, obj, cls = reg.contiguous(), obj.contiguous(), cls.contiguous()
+        out = torch.empty((B, h * w, 5 + cls.shape[1]), dtype=torch.float32, device=reg.device)
+        origin = torch.empty((B, h * w, 4), dtype=torch.float32, device=reg.device) if want_origin else None
+        ops.head_train_decode(reg, obj, cls, stride, out, 0, origin)
+        ctx.save_for_backward(out)
+        ctx.meta = (float(stride), tuple(reg.shape), tuple(obj.shape), tuple(cls.shape), reg.dtype, want_origin)
+        if not want_origin:
+            origin = out.new_empty(0)
+            ctx.mark_non_differentiable(origin)
+        return out, origin
+
+    @staticmethod
+    def backward(ctx, g_out, g_origin):
+        (out,) = ctx.saved_tensors
+        stride, s_reg, s_obj, s_cls, dt, want_origin = ctx.meta
+        dev = out.device
+        g_reg, g_obj, g_cls = (torch.empty(sh, dtype=dt, device=dev) for sh in (s_reg, s_obj, s_cls))
+        g_out = torch.zeros_like(out) if g_out is None else g_out.contiguous().float()
+        g_or = g_origin.contiguous().float() if (want_origin and g_origin is not None) else None
+        ops.head_train_decode_bwd(g_out, out, g_or, stride, 0, g_reg, g_obj, g_cls)
+        return g_reg, g_obj, g_cls, None, None
+
+
 class YoloxHead(_B200Block):
     def __init__(self, num_classes, width=1.0, strides=[8, 16, 32], in_channels=[256, 512, 1024], act="silu",
                  depthwise=False):
@@ -151,17 +181,26 @@ class YoloxHead(_B200Block):
             return run_head(self, xin)
         outputs, origin_preds, x_shifts, y_shifts, expanded_strides = [], [], [], [], []
         for k, (reg_output, obj_output, cls_output) in enumerate(self._torch_raw_outputs(xin)):
-            output = torch.cat([reg_output, obj_output, cls_output], 1)
-            output, grid = self.get_output_and_grid(output, k, self.strides[k], xin[0].type())
+            # cat + view + permute + decode (get_output_and_grid) and the origin_preds gather in one transposing kernel
+            # (csrc/yx_train.cu), fp32 rows out; only the (cached) grid is still built with torch
+            output, origin = _TrainRows.apply(reg_output, obj_output, cls_output, self.strides[k], self.use_l1)
+            grid = self._level_grid(k, reg_output.shape[-2], reg_output.shape[-1], xin[0].type())
             x_shifts.append(grid[:, :, 0])
             y_shifts.append(grid[:, :, 1])
             expanded_strides.append(torch.zeros(1, grid.shape[1]).fill_(self.strides[k]).type_as(xin[0]))
             if self.use_l1:
-                bsz, _, hs, ws = reg_output.shape
-                origin_preds.append(reg_output.view(bsz, 1, 4, hs, ws).permute(0, 1, 3, 4, 2).reshape(bsz, -1, 4).clone())
+                origin_preds.append(origin)
             outputs.append(output)
         return self.get_losses(imgs, x_shifts, y_shifts, expanded_strides, labels, torch.cat(outputs, 1),
                                origin_preds, dtype=xin[0].dtype)
+
+    def _level_grid(self, k, hsize, wsize, dtype):
+        grid = self.grids[k]
+        if grid.shape[2:4] != (hsize, wsize) or grid.type() != dtype:
+            yv, xv = torch.meshgrid([torch.arange(hsize), torch.arange(wsize)], indexing="ij")
+            grid = torch.stack((xv, yv), 2).view(1, 1, hsize, wsize, 2).type(dtype)
+            self.grids[k] = grid
+        return grid.view(1, -1, 2)
 
     def get_output_and_grid(self, output, k, stride, dtype):
         # yolo_head.py:213-231

@@ -66,6 +66,20 @@ def config1_image() -> np.ndarray:
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+# evaluator result path (tests/golden/coco.npz): postprocess output of a seeded case -> COCO json rows
+COCO_CASE = dict(post_case="sparse_a8400", img_size=(640, 640), seed=17)
+
+
+def coco_case_meta(n_images: int):
+    """Original image sizes, image ids and a COCO-style class-index -> category-id table (91-id space with gaps)."""
+    rng = np.random.default_rng(COCO_CASE["seed"])
+    hs = rng.integers(240, 1300, size=n_images).tolist()
+    ws = rng.integers(240, 1300, size=n_images).tolist()
+    ids = (rng.permutation(100000)[:n_images] + 1).tolist()
+    class_ids = sorted(rng.permutation(91)[:80].tolist())
+    return hs, ws, ids, class_ids
+
+
 def checksum(a: np.ndarray) -> str:
     import hashlib
 

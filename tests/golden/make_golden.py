@@ -176,6 +176,33 @@ def gen_config1():
     print("config1.npz", len(out))
 
 
+def gen_coco():
+    """CocoEvaluator.convert_to_coco_format (yolox/evaluators/coco_evaluator.py:205-251) of the unmodified reference on the
+    reference's own postprocess output of a seeded case; `self` is a stand-in carrying the two attributes the method reads."""
+    import types
+
+    from yolox.evaluators.coco_evaluator import CocoEvaluator
+
+    c = cases.COCO_CASE
+    pred, conf, nms = cases.post_case(c["post_case"])
+    res = ref["boxes"].postprocess(torch.from_numpy(pred.copy()), 80, conf, nms, class_agnostic=False)
+    hs, ws, ids, class_ids = cases.coco_case_meta(len(res))
+    me = types.SimpleNamespace(img_size=c["img_size"],
+                               dataloader=types.SimpleNamespace(dataset=types.SimpleNamespace(class_ids=class_ids)))
+    data_list, image_wise = CocoEvaluator.convert_to_coco_format(me, [None if r is None else r.clone() for r in res],
+                                                                 [torch.tensor(hs), torch.tensor(ws)], torch.tensor(ids),
+                                                                 return_outputs=True)
+    out = {"in_sha": np.array(cases.checksum(pred)), "n": np.array(len(data_list)),
+           "image_id": np.array([d["image_id"] for d in data_list], dtype=np.int64),
+           "category_id": np.array([d["category_id"] for d in data_list], dtype=np.int64),
+           "bbox": np.array([d["bbox"] for d in data_list], dtype=np.float64).reshape(-1, 4),
+           "score": np.array([d["score"] for d in data_list], dtype=np.float64),
+           "wise_ids": np.array(sorted(image_wise.keys()), dtype=np.int64),
+           "wise_first_bbox": np.array([image_wise[k]["bboxes"][0] for k in sorted(image_wise.keys())], dtype=np.float64)}
+    np.savez_compressed(OUT / "coco.npz", **out)
+    print("coco.npz", len(data_list), "rows")
+
+
 def loss_case_inputs(name):
     """pred / labels / anchor grid / raw regression outputs of a SIMOTA_ASSIGN case (the inverse decode of pred)."""
     from oracle.simota_oracle import anchor_grid
@@ -234,7 +261,7 @@ def gen_losses():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses", "config1"]
+    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses", "config1", "coco"]
     if "postprocess" in which:
         gen_postprocess()
     if "simota" in which:
@@ -245,3 +272,5 @@ if __name__ == "__main__":
         gen_losses()
     if "config1" in which:
         gen_config1()
+    if "coco" in which:
+        gen_coco()

@@ -1,0 +1,152 @@
+"""-m gpu: the kernels either side of the detection path -- device letterbox (bit-exact with cv2), evaluator result rows
+(bit-exact with the reference's convert_to_coco_format), the training-branch head rows (forward + backward) and the fused
+SGD + EMA step."""
+import copy
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+import pixeltable_yolox_b200 as yx  # noqa: E402
+from oracle import preproc_oracle as pre  # noqa: E402
+from pixeltable_yolox_b200 import ops  # noqa: E402
+from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def test_letterbox_on_device_is_bit_exact(cuda):
+    rng = np.random.default_rng(4)
+    sizes = [(1280, 1280), (480, 640), (1280, 1000), (640, 640), (3, 5), (37, 911), (701, 13), (416, 416), (832, 832)]
+    sizes += [(int(rng.integers(4, 1400)), int(rng.integers(4, 1400))) for _ in range(15)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    for S in ((640, 640), (416, 416), (320, 512)):
+        want = np.stack([pre.letterbox(im, S, np.uint8) for im in imgs])
+        got = ops.letterbox_u8(imgs, S, cuda, torch.uint8)
+        assert got.shape == (len(imgs), 3, S[0], S[1]) and got.dtype == torch.uint8
+        bad = [sizes[i] for i in range(len(imgs)) if not np.array_equal(got[i].cpu().numpy(), want[i])]
+        assert not bad, bad
+        gotf = ops.letterbox_u8(imgs[:4], S, cuda, torch.float32)
+        assert np.array_equal(gotf.cpu().numpy(), want[:4].astype(np.float32))
+    gray = [rng.integers(0, 256, (200, 300), dtype=np.uint8)]
+    assert np.array_equal(ops.letterbox_u8(gray, (416, 416), cuda)[0, 0].cpu().numpy(), pre.letterbox(gray[0], (416, 416), np.uint8))
+
+
+def test_processor_device_letterbox_equals_host_path(cuda):
+    from PIL import Image
+
+    img = Image.fromarray(cases.config1_image())
+    proc = yx.YoloxProcessor("yolox_s")
+    host = proc([img, img])
+    proc.device = cuda
+    dev = proc([img, img])
+    assert dev.is_cuda and dev.dtype == torch.float32 and torch.equal(dev.cpu(), host)
+    proc.dtype = torch.uint8
+    assert torch.equal(proc([img]).cpu().float(), host[:1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.letterbox_u8([np.zeros((4, 4, 3), np.uint8)], (32, 32), torch.device("cpu"))
+
+
+def test_coco_rows_match_reference_evaluator(cuda):
+    from pixeltable_yolox_b200.coco import convert_to_coco_format
+
+    g = np.load(GOLDEN / "coco.npz")
+    c = cases.COCO_CASE
+    pred, conf, nms = cases.post_case(c["post_case"])
+    dets, _, cnt = ops.postprocess_device(torch.from_numpy(pred).to(cuda), 80, conf, nms, yx.boxes.NMS_VARIANTS["auto_cpu"])
+    hs, ws, ids, class_ids = cases.coco_case_meta(pred.shape[0])
+    data_list, wise = convert_to_coco_format(dets, cnt, (hs, ws), ids, c["img_size"], class_ids, return_outputs=True)
+    assert len(data_list) == int(g["n"])
+    assert [d["image_id"] for d in data_list] == g["image_id"].tolist()
+    assert [d["category_id"] for d in data_list] == g["category_id"].tolist()
+    np.testing.assert_array_equal(np.array([d["bbox"] for d in data_list]), g["bbox"])
+    np.testing.assert_array_equal(np.array([d["score"] for d in data_list]), g["score"])
+    assert all(d["segmentation"] == [] for d in data_list) and sorted(wise) == g["wise_ids"].tolist()
+    # max_det smaller than the number kept: rows beyond it are dropped, the compaction stays dense
+    few, _, cnt2 = ops.postprocess_device(torch.from_numpy(pred).to(cuda), 80, conf, nms, yx.boxes.NMS_VARIANTS["auto_cpu"], max_det=2)
+    rows = convert_to_coco_format(few, cnt2, (hs, ws), ids, c["img_size"], class_ids)
+    assert len(rows) == int(cnt2.clamp(max=2).sum())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("use_l1", [False, True])
+def test_training_branch_rows_forward_and_backward(cuda, dtype, use_l1):
+    """_TrainRows (one kernel each way) against the torch ops of the reference's training branch
+    (cat -> get_output_and_grid -> origin_preds), values and gradients."""
+    from pixeltable_yolox_b200.yolo_head import _TrainRows
+
+    head = yx.YoloxHead(80)
+    g = torch.Generator().manual_seed(3)
+    B, h, w, stride = 3, 13, 21, 16
+    mk = lambda c: (torch.randn(B, c, h, w, generator=g) * 0.7).to(dtype).to(cuda)
+    reg, obj, cls = mk(4), mk(1), mk(80)
+    leaves = [t.clone().requires_grad_(True) for t in (reg, obj, cls)]
+    out, origin = _TrainRows.apply(*leaves, stride, use_l1)
+    ref_leaves = [t.clone().float().requires_grad_(True) for t in (reg, obj, cls)]
+    cat = torch.cat(ref_leaves, 1)
+    want, grid = head.get_output_and_grid(cat, 0, stride, cat.type())
+    assert out.dtype == torch.float32 and out.shape == want.shape
+    torch.testing.assert_close(out, want, rtol=2e-6, atol=1e-6)
+    go = torch.randn(out.shape, generator=g).to(cuda)
+    loss, ref_loss = (out * go).sum(), (want * go).sum()
+    if use_l1:
+        want_or = ref_leaves[0].view(B, 1, 4, h, w).permute(0, 1, 3, 4, 2).reshape(B, -1, 4)
+        assert torch.equal(origin, want_or)
+        gor = torch.randn(origin.shape, generator=g).to(cuda)
+        loss, ref_loss = loss + (origin * gor).sum(), ref_loss + (want_or * gor).sum()
+    else:
+        assert origin.numel() == 0
+    loss.backward(); ref_loss.backward()
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    for a, b in zip(leaves, ref_leaves):
+        assert a.grad.dtype == dtype and a.grad.shape == b.grad.shape
+        torch.testing.assert_close(a.grad.float(), b.grad, **tol)
+
+
+def test_fused_sgd_ema_matches_torch_sgd_and_reference_ema(cuda):
+    """FusedSgdEma (one launch) against torch.optim.SGD with the reference's parameter groups and ModelEMA.update's formula."""
+    from pixeltable_yolox_b200.optim import FusedSgdEma, reference_param_groups
+
+    torch.manual_seed(0)
+    cfg = yx.YoloxConfig("opt", depth=0.33, width=0.25)
+    model = cfg.get_model().to(cuda).train()
+    twin = copy.deepcopy(model)
+    pg0, pg1, pg2 = reference_param_groups(twin)
+    opt = torch.optim.SGD(pg0, lr=0.01, momentum=0.9, nesterov=True)
+    opt.add_param_group({"params": pg1, "weight_decay": 5e-4})
+    opt.add_param_group({"params": pg2})
+    ema = copy.deepcopy(twin).eval()
+    fused = FusedSgdEma(model, lr=0.01, momentum=0.9, weight_decay=5e-4, nesterov=True, ema=True, ema_decay=0.9998)
+    assert sum(p.numel() for p in pg0 + pg1 + pg2) == sum(p.numel() for p in twin.parameters())
+    g = torch.Generator().manual_seed(1)
+    for step in range(1, 4):
+        for p, q in zip(model.parameters(), twin.parameters()):
+            gr = torch.randn(p.shape, generator=g).to(cuda) * 0.1
+            p.grad = gr.clone() if p.grad is None else p.grad.copy_(gr)
+            q.grad = gr.clone()
+        with torch.no_grad():                          # BN running statistics move between steps as in training
+            for (k, b), (_, b2) in zip(model.named_buffers(), twin.named_buffers()):
+                if b.dtype.is_floating_point:
+                    b.add_(0.01 * step); b2.add_(0.01 * step)
+        fused.step()
+        opt.step()
+        d = 0.9998 * (1 - math.exp(-step / 2000))
+        with torch.no_grad():
+            msd = twin.state_dict()
+            for k, v in ema.state_dict().items():
+                if v.dtype.is_floating_point:
+                    v *= d
+                    v += (1.0 - d) * msd[k].detach()
+        for (k, a), (_, b) in zip(model.state_dict().items(), twin.state_dict().items()):
+            if a.dtype.is_floating_point:
+                torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-7, msg=lambda m: f"step {step} {k}: {m}")
+        for (k, a), (_, b) in zip(fused.ema.state_dict().items(), ema.state_dict().items()):
+            if a.dtype.is_floating_point:
+                torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-7, msg=lambda m: f"step {step} ema {k}: {m}")
+    assert fused.updates == 3
