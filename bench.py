@@ -753,6 +753,24 @@ def sgd_for(model):
     return opt
 
 
+class TorchSgdWithEma:
+    """The reference's own optimizer + EMA pair for the same-box reference arm: torch.optim.SGD (config.py:307-333) and the
+    reference's ModelEMA.update (yolox/utils/ema.py:46-58), called like Trainer.train_one_iter does (trainer.py:119-124)."""
+
+    def __init__(self, model, ema_cls):
+        self.opt = sgd_for(model)
+        self.model = model
+        self.ema = ema_cls(model, 0.9998) if ema_cls is not None else None
+
+    def zero_grad(self, set_to_none=True):
+        self.opt.zero_grad(set_to_none=set_to_none)
+
+    def step(self):
+        self.opt.step()
+        if self.ema is not None:
+            self.ema.update(self.model)
+
+
 def time_train_steps(model, opt, x, lab, steps, warm, amp_dtype, world, dev, host=None):
     """ms per step (device events, max over ranks) and the phase split of the last step. `host`: (pinned images, pinned
     labels) -> every step uploads them and reads the loss back (the e2e leg)."""
@@ -767,7 +785,7 @@ def time_train_steps(model, opt, x, lab, steps, warm, amp_dtype, world, dev, hos
             out = model(x, lab)
         loss = out["total_loss"]
         if ev: ev[1].record()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
         if ev: ev[2].record()
         opt.step()
@@ -811,7 +829,9 @@ def run_train(args, world, rank, dev):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
-    opt = sgd_for(model)
+    from pixeltable_yolox_b200.optim import FusedSgdEma
+
+    opt = FusedSgdEma(model, lr=1e-3, momentum=0.9, weight_decay=5e-4, nesterov=True, ema=True, ema_decay=0.9998)
     xh, labh, counts = train_batch(args, rank, B)
     xh, labh = xh.pin_memory(), labh.pin_memory()
     x, lab = xh.to(dev), labh.to(dev)
@@ -860,7 +880,11 @@ def run_train(args, world, rank, dev):
             rnet = rmodel
             if world > 1:
                 rnet = torch.nn.parallel.DistributedDataParallel(rmodel, device_ids=[dev.index], broadcast_buffers=False)
-            ropt = sgd_for(rmodel)
+            try:
+                from yolox.utils import ModelEMA
+            except Exception:                         # noqa: BLE001
+                ModelEMA = None
+            ropt = TorchSgdWithEma(rmodel, ModelEMA)
             try:
                 rms, rph, rloss = time_train_steps(rnet, ropt, x, lab, min(args.steps, 10), 2, amp_dtype, world, dev)
                 ramp = args.dtype
@@ -870,8 +894,8 @@ def run_train(args, world, rank, dev):
                 ramp = "fp32"
             ref_line = {"ms_per_step": rms, "images_per_second": world * B / (rms / 1e3), "phases_last_step": rph, "amp": ramp,
                         "loss_last_step": rloss,
-                        "what": "unmodified reference YoloxModule.forward(train) (per-image get_assignments loop) + backward + SGD, "
-                                "torch eager / cuDNN, same inputs, labels, optimizer and DDP"}
+                        "what": "unmodified reference YoloxModule.forward(train) (per-image get_assignments loop) + backward + SGD + "
+                                "ModelEMA.update, torch eager / cuDNN, same inputs, labels, optimizer and DDP"}
         except Exception as e:                        # noqa: BLE001
             ref_line = {"failed": repr(e)}
     if rank == 0:
@@ -885,17 +909,18 @@ def run_train(args, world, rank, dev):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
                        "labels": f"[{B}, 120, 5] per rank, GT counts on rank 0 {counts}", "amp": args.dtype,
-                       "optimizer": "SGD momentum 0.9 nesterov, wd 5e-4 on conv weights (yolox/config.py:307-333)",
+                       "optimizer": "SGD momentum 0.9 nesterov, wd 5e-4 on conv weights (yolox/config.py:307-333) + ModelEMA update "
+                                    "(yolox/utils/ema.py:46-58), both arms; ours: one fused launch (yx_sgd_ema_step)",
                        "network_fwd_bwd": "torch autograd / cuDNN (SURVEY 8f rank 2 not built: no dgrad / wgrad tcgen05 kernels)",
-                       "ours_in_step": "yx_simota_assign (whole batch, one cluster launch, no host sync) + yx_head_losses "
-                                       "(losses and d/d(pred) in one pass)",
+                       "ours_in_step": "yx_head_train_decode fwd/bwd (3 levels), yx_simota_assign (whole batch, one cluster launch, "
+                                       "no host sync), yx_head_losses (losses and d/d(pred) in one pass), yx_sgd_ema_step",
                        "collective": (f"gradient all-reduce: torch DDP buckets (25 MB) -> ncclAllReduce over NVLink/NVSwitch, "
                                       f"{n_grad * 4 / 1e6:.1f} MB fp32 per step" if world > 1 else "none (one rank)"),
                        "loss_last_step": loss},
             "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "images/s",
                     "h2d_bytes_per_step": xh.numel() * 4 + labh.numel() * 4, "d2h_bytes_per_step": 4,
                     "input": "pinned host fp32 images + labels uploaded every step, loss read back every step", "loss_last_step": loss_e2e},
-            "gpu_launches": 2 * args.steps, "launches_per_step": 2,
+            "gpu_launches": 9 * args.steps, "launches_per_step": 9,
             "phases_last_step": phases,
             "kernels": {"simota_assign_us": t_simota, "simota_GBps_of_prediction_tensor": sim_bytes / t_simota / 1e3,
                         "head_losses_us": t_loss, "head_losses_GBps": 2 * sim_bytes / t_loss / 1e3,
