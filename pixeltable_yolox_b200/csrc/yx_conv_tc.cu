@@ -891,6 +891,21 @@ int validate_conv_geometry(const yx_conv_desc* d) {
   return YX_OK;
 }
 
+// CTAs per SM for this layer. Measured on the yolox_s step (B = 64, tools/gpu_ctas_experiment.sh, us per launch, 1 -> 2 CTAs):
+// two co-resident CTAs pay off where a tile is a handful of MMAs followed by a long epilogue and the single CTA's pipeline
+// is latency-bound -- the stride-2 plane layers with few input channels (32->64 @160: 142 -> 117, 64->128 @80: 78 -> 74) and
+// the 3x3 layers on the 20x20 maps (256->256: 43 -> 39, 128->256: 29 -> 27). They lose where one CTA already keeps the
+// tensor pipe busy (head 3x3 @80x80: 178 -> 203, 3x3 128->128 @40x40: 37 -> 41) or where halving the shared memory evicts the
+// resident weights (1x1 1024->512: 31 -> 37). YX_CTAS_PER_SM=1|2 forces a setting, YX_CTAS_MAXPIX=<pixels> selects by map size.
+static int conv_ctas_per_sm(const yx_conv_desc* d) {
+  if (d->epilogue == YX_EPI_HEAD) return 1;                   // the head staging slabs need the shared memory
+  if (const char* e = getenv("YX_CTAS_PER_SM")) { const int v = atoi(e); if (v == 1 || v == 2) return v; }
+  if (const char* e = getenv("YX_CTAS_MAXPIX")) return (long long)d->out_h * d->out_w <= atoll(e) ? 2 : 1;
+  if (d->ksize == 3 && d->stride == 2 && d->in_c <= 64) return 2;
+  if (d->ksize == 3 && d->stride == 1 && d->out_h * d->out_w <= 400 && d->in_c >= 128) return 2;
+  return 1;
+}
+
 static int largest_divisor_tile(int n, int cap) {
   // largest multiple-of-16 divisor of n that is <= cap
   for (int t = cap - cap % 16; t >= 16; t -= 16)
@@ -927,7 +942,14 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
   p.n_tiles = d->out_c / p.BN;
   p.BNpad = 32;
   while (p.BNpad < p.BN) p.BNpad <<= 1;
-  p.acc_stages = 512 / p.BNpad;
+  // Two co-resident CTAs per SM for the small layers (few tiles per SM: the kernel is fill / drain latency, not throughput):
+  // each CTA takes half the shared memory and half of TMEM and one epilogue warpgroup (192 threads x ~120 registers), so that
+  // one CTA's loads and MMAs overlap the other's epilogue and, with programmatic dependent launch, the next kernel's
+  // prologue (barriers, TMEM, resident weights) starts in the slot a finished CTA frees while its neighbour still drains.
+  int ctas = conv_ctas_per_sm(d);
+  const int tmem_budget = 512 / ctas;
+  p.acc_stages = tmem_budget / p.BNpad;
+  if (p.acc_stages < 1) { ctas = 1; p.acc_stages = 512 / p.BNpad; }
   if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
   p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);  // power of two >= 32 by construction
 
@@ -947,6 +969,7 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
   int dev = 0, max_smem = 0;
   YX_CUDA(cudaGetDevice(&dev));
   YX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (ctas == 2 && max_smem > 112 * 1024) max_smem = 112 * 1024;       // 228 KB per SM, 1 KB reserved per CTA
   p.bias_bytes = ((unsigned)d->out_c * 4u + 1023u) & ~1023u;
 
   if (p.halo) {
@@ -1019,7 +1042,8 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
       p.n_tiles = d->out_c / p.BN;
       p.BNpad = 32;
       while (p.BNpad < p.BN) p.BNpad <<= 1;
-      p.acc_stages = 512 / p.BNpad;
+      p.acc_stages = tmem_budget / p.BNpad;
+      if (p.acc_stages < 1) p.acc_stages = 1;
       if (p.acc_stages > kMaxAcc) p.acc_stages = kMaxAcc;
       p.tmem_cols = (unsigned)(p.acc_stages * p.BNpad);
       p.b_tile_bytes = ((unsigned)p.BN * row_bytes + 1023u) & ~1023u;
@@ -1030,6 +1054,7 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
       if (p.b_resident) break;
     }
     if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
+    if (ctas == 2) p.epi_groups = 1;
     // stride-2 planes only pay off with resident weights (streamed weights are not shared between M tiles there)
     if (p.halo == 2 && !p.b_resident && !getenv("YX_HALO_BRES")) return conv_tc_prepare_mode(d, L, false);
     // 1x1 with weights too large to stay resident: the per-tap ring with N up to 256 streams fewer bytes
@@ -1098,6 +1123,7 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
     if (p.epi_groups > p.acc_stages) p.epi_groups = p.acc_stages;
     if (d->epilogue == YX_EPI_HEAD && p.epi_groups > 2) p.epi_groups = 2;   // staging slabs are 10.9 KB per warp
     if (const char* e = getenv("YX_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= kMaxEpiGroups && v <= p.acc_stages) p.epi_groups = v; }
+    if (ctas == 2) p.epi_groups = 1;
   }
   p.head_bytes = d->epilogue == YX_EPI_HEAD ? (((unsigned)p.epi_groups * 4u * 32u * (unsigned)(5 + d->head_nc) * 4u + 1023u) & ~1023u) : 0u;
   const unsigned fixed_bytes = 2048u + p.bias_bytes + p.head_bytes;
@@ -1166,7 +1192,7 @@ static int conv_tc_prepare_mode(const yx_conv_desc* d, ConvTcLaunch* L, bool all
   p.mul_ntiles = fast_div_mul(p.n_tiles);
   p.mul_ohw = fast_div_mul(d->out_h * d->out_w);
   p.mul_ow = fast_div_mul(d->out_w);
-  const int sms = num_sms();
+  const int sms = num_sms() * ctas;
   L->grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (p.halo) {
     const int groups = p.num_tiles / p.G;     // never split a weight-sharing group when there is less than one per SM
