@@ -37,7 +37,7 @@ static constexpr int kWarpG1 = 18;
 struct BneckParams {
   int C, Cpad;               // channels (= N = K), TMEM column pitch
   int tw, th, pitch;         // spatial tile and accumulator row pitch (tw + 2)
-  int tiles_w, tiles_h, num_tiles;
+  int tiles_w, tiles_h, num_tiles, tiles_per_img;
   int batch, H, W;
   int ksteps;                // C / 16
   int halo_rows;             // (th + 2) * pitch
@@ -103,10 +103,14 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;
+  // Values every role needs are NOT kept in registers across the role branch: at the 96-register cap of this CTA size ptxas
+  // spilled exactly those (tmem_base, tiles per image) to local memory, and with the L1 carved out for shared memory every
+  // reload in the per-tile loops was an L2 round trip (~700 clk per tile in epilogue 1, the critical stage; clock64 trace
+  // with YX_BNECK_TRACE=1). Each role re-reads them from shared memory / the constant bank instead.
+#define tmem_base (sh->tmem_base)
+#define tiles_per_img (p.tiles_per_img)
   pdl_launch_dependents();      // the weights are constants: loaded before griddepcontrol.wait (see the producer)
 
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
   const long long T = p.num_tiles;
   const int t_begin = (int)(T * blockIdx.x / gridDim.x), t_end = (int)(T * (blockIdx.x + 1) / gridDim.x);
   const int n_my = t_end - t_begin;
@@ -284,13 +288,19 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (stored) *reinterpret_cast<uint4*>(hslot + phys) = make_uint4(w[4 * hch], w[4 * hch + 1], w[4 * hch + 2], w[4 * hch + 3]);
           }
         };
-        // all C/16 TMEM loads of the row are issued back to back and waited for once
-        uint32_t raw[KS][16];
+        // up to 32 channels (two TMEM loads) in flight at a time: with all four loads of a 64-channel row live next to the
+        // 16 activations of a chunk the kernel needs > 96 registers (the cap at 608 threads) and ptxas spills loop invariants
+        // to local memory, whose reloads are L2 round trips here (the L1 is carved out for shared memory)
+        constexpr int KH = KS >= 2 ? 2 : 1;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * k), raw[k]);
-        tmem_ld_wait();
+        for (int k0 = 0; k0 < KS; k0 += KH) {
+          uint32_t raw[KH][16];
 #pragma unroll
-        for (int k = 0; k < KS; ++k) emit(raw[k], 16 * k);
+          for (int k = 0; k < KH; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * (k0 + k)), raw[k]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < KH; ++k) emit(raw[k], 16 * (k0 + k));
+        }
       }
       BN_TRACE(1, it, 0);
       tc_fence_before();
@@ -353,6 +363,8 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#undef tmem_base
+#undef tiles_per_img
 }
 
 #ifdef YX_EXP_BNECK128   // negative result: only in experiment builds (python -m pixeltable_yolox_b200.build --exp -DYX_EXP_BNECK128)
@@ -732,6 +744,7 @@ int bneck_prepare(const yx_bneck_desc* d, BneckLaunch* L) {
   p.halo_rows = (p.th + 2) * p.pitch;
   p.tiles_w = (int)ceil_div64(d->w, p.tw); p.tiles_h = (int)ceil_div64(d->h, p.th);
   p.num_tiles = d->batch * p.tiles_w * p.tiles_h;
+  p.tiles_per_img = p.tiles_w * p.tiles_h;
   p.mul_tpi = fast_div_mul(p.tiles_w * p.tiles_h); p.mul_tw = fast_div_mul(p.tiles_w);
   // GEMM1 reads 256 rows from the slot start and GEMM2 rows up to 127 + 2*pitch + 2: 256 rows cover both
   // GEMM1's second tile reads rows 128..255 from the slot start: rows past the slot are the next slot / the H
