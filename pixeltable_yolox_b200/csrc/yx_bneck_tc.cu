@@ -234,14 +234,22 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       mbar_wait(&sh->a1full[st], ph);
       BN_TRACE(1, it, 1);
+      tc_fence_after();
+      // the first TMEM loads are issued before the wait for the hidden-tile slot: that wait (a shared-memory round trip of
+      // ~170 clk even when the phase completed long ago) overlaps their latency
+      constexpr int KH = KS >= 2 ? 2 : 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc1_col + (uint32_t)((st * 2 + mt) * p.Cpad);
+      uint32_t raw[KH][16];
+      if (warp_live) {
+#pragma unroll
+        for (int k = 0; k < KH; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * k), raw[k]);
+      }
       mbar_wait(&sh->hempty[st], ph ^ 1);
       BN_TRACE(1, it, 2);
-      tc_fence_after();
       uint8_t* hslot = hs + (size_t)st * p.h_slot_bytes;
       if (warp_live) {
         const int iy = ty * p.th - 1 + yy, ix = tx * p.tw - 1 + xx;
         const bool inside = (q < p.halo_rows) && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && b < p.batch;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc1_col + (uint32_t)((st * 2 + mt) * p.Cpad);
         // 16 hidden channels of this thread's halo pixel: bias + act -> two swizzled 16-byte chunks
         auto emit = [&](const uint32_t (&raw)[16], int c) {
           uint32_t w[8];
@@ -291,12 +299,12 @@ bneck_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // up to 32 channels (two TMEM loads) in flight at a time: with all four loads of a 64-channel row live next to the
         // 16 activations of a chunk the kernel needs > 96 registers (the cap at 608 threads) and ptxas spills loop invariants
         // to local memory, whose reloads are L2 round trips here (the L1 is carved out for shared memory)
-        constexpr int KH = KS >= 2 ? 2 : 1;
 #pragma unroll
         for (int k0 = 0; k0 < KS; k0 += KH) {
-          uint32_t raw[KH][16];
+          if (k0) {
 #pragma unroll
-          for (int k = 0; k < KH; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * (k0 + k)), raw[k]);
+            for (int k = 0; k < KH; ++k) tmem_ld_x16(taddr + (uint32_t)(16 * (k0 + k)), raw[k]);
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < KH; ++k) emit(raw[k], 16 * (k0 + k));
