@@ -77,6 +77,21 @@ def full(src, out):
             if w in hdr:
                 i = hdr.index(w)
                 lines.append(f"| {w} | {r[i]} | {units[i]} |")
+        # warp-state breakdown: sampled stall reasons (smsp__pcsamp_warps_issue_stalled_*), share of all samples
+        samp = {}
+        for i, h in enumerate(hdr):
+            if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+                try:
+                    samp[h[len("smsp__pcsamp_warps_issue_stalled_"):]] = float(r[i].replace(",", ""))
+                except ValueError:
+                    pass
+        tot = sum(samp.values())
+        if tot > 0:
+            lines += ["", "warp stall samples (all warps of the kernel; producer / MMA / epilogue roles pooled):", "",
+                      "| stall reason | samples | share |", "|---|---:|---:|"]
+            for k, v in sorted(samp.items(), key=lambda kv: -kv[1]):
+                if v > 0:
+                    lines.append(f"| {k} | {int(v)} | {100 * v / tot:.1f}% |")
         lines.append("")
     Path(out).write_text("\n".join(lines) + "\n")
     print("\n".join(lines))
