@@ -26,22 +26,32 @@
 
 namespace yx {
 
-static constexpr int kStemStages = 4;                // halo-tile (A operand) stages
-static constexpr int kStemAcc = 4;
 static constexpr int kStemBuilders = 128;            // threads per builder group
-static constexpr int kStemBuilderGroups = 2;         // tiles alternate between the groups
-static constexpr int kStemEpiGroups = 4;
-static constexpr int kStemThreads = kStemBuilders * kStemBuilderGroups + 64 + 128 * kStemEpiGroups + 32;   // + MMA warp + TMA warp + second MMA warp
-static constexpr int kWarpMma = kStemBuilders * kStemBuilderGroups / 32, kWarpTma = kWarpMma + 1, kWarpEpi = kWarpMma + 2;
-static constexpr int kWarpMma2 = kWarpEpi + 4 * kStemEpiGroups;     // tiles alternate between the two issuing warps
-// A parity wait can only tell "this phase" from "the previous one": every waiter must stay within one phase of its
-// barrier. That holds when all uses of a ring slot belong to ONE group of warps working through its tiles in order, i.e.
-// when the group count divides the slot count (three epilogue groups on four accumulator slots let a group reach tile
-// t + 8 of a slot whose tile t + 4 was still in flight with the other issuing warp: wrong accumulators, then a deadlock).
-static_assert(kStemAcc % kStemEpiGroups == 0 && kStemStages % kStemBuilderGroups == 0 && kStemStages % 2 == 0 &&
-              kStemAcc % 2 == 0, "ring slots must map to one warp group each (mbarrier parity aliasing)");
-static constexpr int kPatchStages = 4;
-static_assert(kPatchStages % kStemBuilderGroups == 0, "patch ring slots must map to one builder group each");
+static constexpr int kStemMaxRing = 4;               // barrier arrays are sized for the largest variant
+// Variant V: 0 = one CTA per SM (two builder groups, two issuing warps, four epilogue groups, 4-deep rings);
+//            1 = two co-resident CTAs per SM with half of everything each (one builder group, one issuing warp, two
+//                epilogue groups, 2-deep rings); 2 = like 1 with ONE epilogue group (320 threads: no register squeeze).
+// The single-CTA kernel is bound by the hand-off latency of its TMA -> builder -> MMA -> epilogue pipeline (~1 000 clk per
+// 120-pixel tile with no unit saturated, section 4.4 of DESIGN.md); two independent pipelines per SM overlap that latency.
+template <int V> struct StemCfg {
+  static constexpr int kBuilderGroups = V == 0 ? 2 : 1;       // tiles alternate between the groups
+  static constexpr int kMmaWarps = V == 0 ? 2 : 1;            // tiles alternate between the issuing warps
+  static constexpr int kEpiGroups = V == 0 ? 4 : (V == 1 ? 2 : 1);
+  static constexpr int kStages = V == 0 ? 4 : 2;              // halo-tile (A operand) stages
+  static constexpr int kAcc = V == 0 ? 4 : 2;
+  static constexpr int kPatchStages = V == 0 ? 4 : 2;
+  static constexpr int kWarpMma = kStemBuilders * kBuilderGroups / 32, kWarpTma = kWarpMma + 1, kWarpEpi = kWarpMma + 2;
+  static constexpr int kWarpMma2 = kWarpEpi + 4 * kEpiGroups;
+  static constexpr int kThreads = kStemBuilders * kBuilderGroups + 64 + 128 * kEpiGroups + (kMmaWarps == 2 ? 32 : 0);
+  static constexpr int kCtasPerSm = V == 0 ? 1 : 2;
+  // A parity wait can only tell "this phase" from "the previous one": every waiter must stay within one phase of its
+  // barrier. That holds when all uses of a ring slot belong to ONE group of warps working through its tiles in order, i.e.
+  // when the group count divides the slot count (three epilogue groups on four accumulator slots let a group reach tile
+  // t + 8 of a slot whose tile t + 4 was still in flight with the other issuing warp: wrong accumulators, then a deadlock).
+  static_assert(kAcc % kEpiGroups == 0 && kStages % kBuilderGroups == 0 && kStages % kMmaWarps == 0 && kAcc % kMmaWarps == 0 &&
+                kPatchStages % kBuilderGroups == 0, "ring slots must map to one warp group each (mbarrier parity aliasing)");
+  static_assert(kStages <= kStemMaxRing && kAcc <= kStemMaxRing && kPatchStages <= kStemMaxRing, "ring depth");
+};
 // The output tile (th x tw, accumulator row m = y * (tw + 2) + x, th * (tw + 2) <= 128) is chosen per image width
 // on the host: the raw patch arrives as 3 * (2*th + 4) TMA rows and the TMA unit's cost is per ROW (fp32 160-byte and
 // uint8 64-byte rows of the first 7 x 16 tile took the same 250 us), so wide, flat tiles (3 x 40 at 640^2: 30 rows of
@@ -68,13 +78,13 @@ __device__ long long g_stem_trace[3][32][5];
 #define ST_TRACE(role, it, k) do { if ((p.debug & 2) && blockIdx.x == 0 && (it) >= 16 && (it) < 48 && lane == 0) g_stem_trace[role][(it) - 16][k] = clock64(); } while (0)
 
 struct __align__(8) StemShared {
-  uint64_t full[kStemStages];
-  uint64_t empty[kStemStages];
-  uint64_t tmem_full[kStemAcc];
-  uint64_t tmem_empty[kStemAcc];
+  uint64_t full[kStemMaxRing];
+  uint64_t empty[kStemMaxRing];
+  uint64_t tmem_full[kStemMaxRing];
+  uint64_t tmem_empty[kStemMaxRing];
   uint64_t w_full;
-  uint64_t patch_full[kPatchStages];
-  uint64_t patch_empty[kPatchStages];
+  uint64_t patch_full[kStemMaxRing];
+  uint64_t patch_empty[kStemMaxRing];
   uint32_t tmem_base;
 };
 
@@ -98,10 +108,14 @@ __device__ __forceinline__ void load_pair<uint8_t>(const uint8_t* p, float& a, f
   b = __uint_as_float(0x4B000000u | (v >> 8)) - 8388608.0f;
 }
 
-template <typename TI, bool FP16, bool SILU>
-__global__ void __launch_bounds__(kStemThreads, 1)
+template <typename TI, bool FP16, bool SILU, int V>
+__global__ void __launch_bounds__(StemCfg<V>::kThreads, StemCfg<V>::kCtasPerSm)
 stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_img,
                const StemParams p) {
+  using Cfg = StemCfg<V>;
+  constexpr int kStemStages = Cfg::kStages, kStemAcc = Cfg::kAcc, kPatchStages = Cfg::kPatchStages;
+  constexpr int kStemBuilderGroups = Cfg::kBuilderGroups, kStemEpiGroups = Cfg::kEpiGroups, kMmaWarps = Cfg::kMmaWarps;
+  constexpr int kWarpMma = Cfg::kWarpMma, kWarpTma = Cfg::kWarpTma, kWarpEpi = Cfg::kWarpEpi, kWarpMma2 = Cfg::kWarpMma2;
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space known to the
   // compiler: LDS/STS instead of generic loads for every bias / staging access
@@ -213,7 +227,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
       if (warp == 0) ST_TRACE(0, it, 4);
     }
-  } else if (warp == kWarpMma || warp == kWarpMma2) {
+  } else if (warp == kWarpMma || (kMmaWarps == 2 && warp == kWarpMma2)) {
     // ===================== MMA issuers =====================
     // A [128 x 16] x [16 x 32] MMA is bound by the tensor core's shared-memory read of A (128 rows x 32 B at ~64 B/clk =
     // 64 clk, the math needs 16) and the issuing thread stays in tcgen05.mma for about that long, so its barrier waits
@@ -230,7 +244,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const uint64_t hi = ((uint64_t)p.desc_hi << 32) | (1u << 16);
       const uint32_t w16 = smem_u32(wsm) >> 4, wt16 = p.w_tile_bytes >> 4;
       const uint32_t pitch2 = (uint32_t)p.pitch * 2u;
-      for (int mit = g;; mit += 2) {
+      for (int mit = g;; mit += kMmaWarps) {
         const long long tl = (long long)blockIdx.x + (long long)mit * gridDim.x;
         if (tl >= p.num_tiles) break;
         const int stage = mit % kStemStages, as = mit % kStemAcc;
@@ -344,7 +358,18 @@ struct StemLaunch {
   StemParams p;
   int grid;
   size_t smem;
+  int variant;            // StemCfg<V>
 };
+
+// ring depths / thread counts of the variants for the host side (same numbers as StemCfg<V>)
+// Default: two co-resident CTAs (variant 1) when they fit. Measured at 64 x 640^2 (tools/gpu_time_stem.py): 210 -> 202 us
+// (fp32 image), 214 -> 201 us (uint8); variant 2 (one epilogue group per CTA) 216 us. The gain is small because the kernel
+// is not latency-bound after all: ncu (profiles/r2_stem.md) has the L1 data pipe saturated -- LSU wavefronts 68 % (shared
+// loads of the builders and epilogues 39 %, stores 9 %) + tensor-core operand reads 34 % of the same pipe.
+static int stem_variant() {
+  if (const char* e = getenv("YX_STEM_V")) { const int v = atoi(e); if (v >= 0 && v <= 2) return v; }
+  return 1;
+}
 
 StemLaunch* stem_alloc() {
   void* p = nullptr;
@@ -395,7 +420,22 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
   p.mul_tpi = fast_div_mul(p.tiles_w * p.tiles_h); p.mul_tw = fast_div_mul(p.tiles_w);
   p.BN = out_c;
   p.BNpad = 32; while (p.BNpad < p.BN) p.BNpad <<= 1;
-  p.tmem_cols = (unsigned)(kStemAcc * p.BNpad);
+  int V = stem_variant();
+  {
+    // two CTAs per SM need <= 112 KB each; otherwise fall back to the single-CTA variant
+    const unsigned es1 = img_dtype == YX_FP32 ? 4u : 1u;
+    const unsigned per16 = 16u / es1, lead1 = per16 - 2u;
+    const unsigned pitch1 = (lead1 + 2u * (unsigned)p.tw + 4u + per16 - 1u) / per16 * per16;
+    const size_t patch1 = ((size_t)(3 * p.patch_rows) * pitch1 * es1 + 127u) & ~(size_t)127u;
+    const size_t a1 = ((size_t)(128 + 2 * p.pitch + 2) * 32u + 1023u) & ~(size_t)1023u;
+    const size_t need = 2048 + ((size_t)out_c * 4u + 1023u) / 1024u * 1024u + 2 * patch1 + 1024 + (((size_t)out_c * 32u * 9u + 1023u) & ~(size_t)1023u) + 2 * a1;
+    if (V != 0 && need > 112 * 1024) V = 0;
+  }
+  L->variant = V;
+  const int n_acc = V == 0 ? StemCfg<0>::kAcc : StemCfg<1>::kAcc;
+  const int n_stages = V == 0 ? StemCfg<0>::kStages : StemCfg<1>::kStages;
+  const int n_patch = V == 0 ? StemCfg<0>::kPatchStages : StemCfg<1>::kPatchStages;
+  p.tmem_cols = (unsigned)(n_acc * p.BNpad);
   const unsigned fmt = dtype == YX_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
   p.desc_hi = ((256u >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);    // SBO = 8 rows * 32 B, version 1, SWIZZLE_32B
@@ -414,8 +454,9 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
     p.patch_stage_bytes = ((unsigned)(3 * p.patch_rows * p.patch_pitch * es0) + 127u) & ~127u;
     p.a_stage_bytes = ((unsigned)(128 + 2 * p.pitch + 2) * 32u + 1023u) & ~1023u;   // rows addressed by the nine shifted taps
   }
-  L->smem = 2048 + p.bias_bytes + (size_t)kPatchStages * p.patch_stage_bytes + 1024 + ((p.b_bytes + 1023u) & ~1023u) +
-            (size_t)kStemStages * p.a_stage_bytes;
+  L->smem = 2048 + p.bias_bytes + (size_t)n_patch * p.patch_stage_bytes + 1024 + ((p.b_bytes + 1023u) & ~1023u) +
+            (size_t)n_stages * p.a_stage_bytes;
+  YX_REQUIRE(V == 0 || L->smem <= 112 * 1024, YX_ERR_UNSUPPORTED, "stem: %zu bytes of shared memory do not allow two CTAs per SM", L->smem);
   {
     // the NCHW image as a 4-D tensor [W, H, 3, B]; one box = the 40 (u8: 64) x 18 x 3 window holding a tile's patch
     const int es = img_dtype == YX_FP32 ? 4 : 1;
@@ -440,7 +481,7 @@ int stem_prepare(const void* img, int img_dtype, const void* w, const float* bia
   CUresult r = encode(&L->map_w, tdt, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   YX_REQUIRE(r == CUDA_SUCCESS, YX_ERR_CUDA, "cuTensorMapEncodeTiled(stem W) failed: %d", (int)r);
-  const int sms = num_sms();
+  const int sms = num_sms() * (V == 0 ? 1 : 2);
   L->grid = p.num_tiles < sms ? p.num_tiles : sms;
   return YX_OK;
 }
@@ -449,17 +490,20 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   static bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-#define YX_STEM_ATTR(T, F) \
-  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+#define YX_STEM_ATTR1(T, F, V) \
+  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, V == 0 ? 200 * 1024 : 112 * 1024)); \
+  YX_CUDA(cudaFuncSetAttribute(stem_tc_kernel<T, F, false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, V == 0 ? 200 * 1024 : 112 * 1024))
+#define YX_STEM_ATTR(T, F) YX_STEM_ATTR1(T, F, 0); YX_STEM_ATTR1(T, F, 1); YX_STEM_ATTR1(T, F, 2)
     YX_STEM_ATTR(float, false); YX_STEM_ATTR(float, true); YX_STEM_ATTR(uint8_t, false); YX_STEM_ATTR(uint8_t, true);
 #undef YX_STEM_ATTR
+#undef YX_STEM_ATTR1
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)L->grid);
-  cfg.blockDim = dim3((unsigned)kStemThreads);
+  const int V = L->variant;
+  cfg.blockDim = dim3((unsigned)(V == 0 ? StemCfg<0>::kThreads : (V == 1 ? StemCfg<1>::kThreads : StemCfg<2>::kThreads)));
   cfg.dynamicSmemBytes = L->smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -469,14 +513,16 @@ int stem_launch(const StemLaunch* L, cudaStream_t stream) {
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   const bool h16 = L->p.epi.dtype == YX_FP16;
   const bool silu = L->p.epi.act == YX_ACT_SILU;
-#define YX_STEM_GO(T, F) do { if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, true>, L->map_w, L->map_img, L->p)); \
-    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, false>, L->map_w, L->map_img, L->p)); } while (0)
+#define YX_STEM_GO1(T, F, V) do { if (silu) YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, true, V>, L->map_w, L->map_img, L->p)); \
+    else YX_CUDA(cudaLaunchKernelEx(&cfg, stem_tc_kernel<T, F, false, V>, L->map_w, L->map_img, L->p)); } while (0)
+#define YX_STEM_GO(T, F) do { if (V == 0) YX_STEM_GO1(T, F, 0); else if (V == 1) YX_STEM_GO1(T, F, 1); else YX_STEM_GO1(T, F, 2); } while (0)
   if (L->p.img_dtype == YX_FP32) {
     if (h16) YX_STEM_GO(float, true); else YX_STEM_GO(float, false);
   } else {
     if (h16) YX_STEM_GO(uint8_t, true); else YX_STEM_GO(uint8_t, false);
   }
 #undef YX_STEM_GO
+#undef YX_STEM_GO1
   if (L->p.debug & 2) {
     static long long tr[3][32][5];
     cudaStreamSynchronize(stream);
