@@ -28,6 +28,23 @@ from ._lib import ACT_CODES, check, dtype_code, lib, stream_ptr
 from .ops import View
 
 
+def _on_device_of(get_device):
+    """Run the wrapped function with the tensor's / engine's CUDA device current: the library launches on the current device
+    and a module on cuda:1 must not launch on cuda:0 with cuda:1 pointers (advisor finding, round 1)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            dev = get_device(*args, **kwargs)
+            if dev is not None and torch.device(dev).type == "cuda":
+                with torch.cuda.device(dev):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+        return wrapper
+    return deco
+
+
 def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
@@ -465,6 +482,7 @@ def _check_dtype(dt: torch.dtype) -> None:
 
 
 @torch.no_grad()
+@_on_device_of(lambda block, x: x.device)
 def run_block(block: nn.Module, x: torch.Tensor):
     """Eval forward of a single block through eager C-ABI launches."""
     from .darknet import CspDarknet
@@ -485,6 +503,7 @@ def run_block(block: nn.Module, x: torch.Tensor):
 
 
 @torch.no_grad()
+@_on_device_of(lambda head, xin: xin[0].device)
 def run_head(head: nn.Module, xin: Sequence[torch.Tensor]) -> torch.Tensor:
     dt = _module_dtype(head, xin[0])
     _check_dtype(dt)
@@ -505,6 +524,7 @@ class InferenceEngine:
     share every intermediate buffer, so a micro-batch's activations stay resident in the 126 MB L2
     between producer and consumer layers."""
 
+    @_on_device_of(lambda self, module, batch, height, width, in_dtype, device, *a, **k: device)
     def __init__(self, module: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype,
                  device: torch.device, micro_batch: Optional[int] = None, use_graph: bool = True,
                  post: Optional[dict] = None):
@@ -613,6 +633,7 @@ class InferenceEngine:
     def launches(self) -> int:
         return self.builder.launches
 
+    @_on_device_of(lambda self, x: self.input.device)
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: [B,3,H,W] on any device (a host tensor is copied H2D here, a device tensor D2D into the persistent input
         buffer the plan's tensor maps point at; pass `engine.input` itself to run on what is already there). Returns

@@ -247,3 +247,31 @@ def test_config1_nano_416_user_api_on_gpu():
     assert res["labels"] == want["labels"] and res["scores"] == want["scores"] and res["bboxes"] == want["bboxes"]
     u8 = model(proc([img]).to(torch.uint8).to(dev)).cpu().numpy()
     assert np.array_equal(u8, out)                 # byte upload: bit-identical
+
+
+def test_module_on_a_non_current_device(cuda):
+    """One process may drive several GPUs: a module on cuda:1 while cuda:0 is the current device must launch on cuda:1
+    (library caches are per device, every entry point makes the tensors' device current). Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model, sd, x = _build("w25_d33_64")
+    d0, d1 = torch.device("cuda", 0), torch.device("cuda", 1)
+    torch.cuda.set_device(0)
+    m0 = model.to(d0).bfloat16().eval()
+    want = m0(x.to(d0)).cpu()
+    import copy
+
+    m1 = copy.deepcopy(m0).to(d1)
+    assert torch.cuda.current_device() == 0
+    got = m1(x.to(d1))
+    assert got.device == d1 and torch.equal(got.cpu(), want)
+    dets, _, cnt = m1.detect(x.to(d1), conf_thre=0.05)
+    dets0, _, cnt0 = m0.detect(x.to(d0), conf_thre=0.05)
+    assert torch.equal(cnt.cpu(), cnt0.cpu()) and torch.equal(dets.cpu(), dets0.cpu())
+    pred = torch.from_numpy(syn.dense_scene(1, anchors=2100, seed=3, clusters=20, size=320.0))
+    a = yx.postprocess(pred.clone().to(d1), 80, 0.25, 0.65)
+    b = yx.postprocess(pred.clone().to(d0), 80, 0.25, 0.65)
+    assert torch.equal(a[0].cpu(), b[0].cpu())
+    with pytest.raises(RuntimeError, match="is on"):
+        ops = __import__("pixeltable_yolox_b200.ops", fromlist=["ops"])
+        ops.bboxes_iou_device(torch.zeros(2, 4, device=d0), torch.zeros(2, 4, device=d1), True)
