@@ -346,14 +346,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       keys[i] = k;
     }
     __syncthreads();
+    // Bitonic network; four independent pairs are loaded before the first compare so that the shared-memory latency of a
+    // stage overlaps (a register-blocked variant for the strides < 32 measured slower: 569k vs 330k clk at P = 16 384)
     for (int size = 2; size <= P; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = tid; i < (P >> 1); i += kNmsThreads) {
-          const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-          const int hi = lo | stride;
-          const bool up = ((lo & size) == 0);
-          const unsigned long long a = keys[lo], c = keys[hi];
-          if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+        for (int i0 = tid; i0 < (P >> 1); i0 += 4 * kNmsThreads) {
+          unsigned long long a[4], c[4];
+          int lo[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kNmsThreads;
+            lo[u] = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+            if (i < (P >> 1)) { a[u] = keys[lo[u]]; c[u] = keys[lo[u] | stride]; }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kNmsThreads;
+            if (i < (P >> 1) && ((a[u] > c[u]) == ((lo[u] & size) == 0))) { keys[lo[u]] = c[u]; keys[lo[u] | stride] = a[u]; }
+          }
         }
         __syncthreads();
       }
