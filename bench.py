@@ -846,6 +846,57 @@ def time_train_steps(model, opt, x, lab, steps, warm, amp_dtype, world, dev, hos
     return ms / steps, phases, float(loss) if not isinstance(loss, float) else loss
 
 
+def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev):
+    """The whole training step -- forward, SimOTA assignment, losses, backward (+ DDP all-reduce), SGD + EMA -- captured ONCE
+    as a CUDA graph and replayed: possible because nothing in our step synchronises with the host (the reference's
+    get_assignments reads device scalars per image and per GT, yolo_head.py:269-351,549-564, and cannot be captured).
+    The learning rate and the EMA ramp reach the captured optimizer launch through a 12-byte device buffer."""
+    import torch
+    import torch.distributed as dist
+
+    def eager():
+        with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+            out = model(x, lab)
+        opt.zero_grad()
+        out["total_loss"].backward()
+        opt.step()
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(11 if world > 1 else 3):        # DDP needs 11 warm-up iterations before capture (torch docs)
+            eager()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+            out = model(x, lab)
+        loss = out["total_loss"]
+        opt.zero_grad()
+        loss.backward()
+        opt.step_captured()
+    for _ in range(3):
+        opt.set_hyper()
+        g.replay()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        opt.set_hyper()
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, float(loss.item())
+
+
 def run_train(args, world, rank, dev):
     import torch
     import torch.distributed as dist
@@ -874,6 +925,17 @@ def run_train(args, world, rank, dev):
     clocks.mark(w0 + 0.0, time.perf_counter())
     clk = clocks.stop()
     ms_e2e, _, loss_e2e = time_train_steps(net, opt, x, lab, args.steps, 2, amp_dtype, world, dev, host=(xh, labh))
+
+    # ---- the same step as one CUDA graph (our step has no host synchronisation; the reference's cannot be captured)
+    graph_line = None
+    try:
+        gms, gloss = time_train_graph(net, opt, x, lab, args.steps, amp_dtype, world, dev)
+        graph_line = {"ms_per_step": gms, "images_per_second": world * B / (gms / 1e3), "loss_last_step": gloss,
+                      "what": "forward + SimOTA + losses + backward" + (" + DDP all-reduce" if world > 1 else "") +
+                              " + SGD/EMA captured once with torch.cuda.graph and replayed; lr / EMA decay via a device buffer"}
+    except Exception as e:                            # noqa: BLE001
+        graph_line = {"failed": repr(e)[:300]}
+        torch.cuda.synchronize()
 
     # ---- our kernels of the step, stand-alone on this rank's head output shape
     model.eval()        # BN statistics are irrelevant here: only shapes and value ranges of the head output matter
@@ -953,7 +1015,7 @@ def run_train(args, world, rank, dev):
                     "h2d_bytes_per_step": xh.numel() * 4 + labh.numel() * 4, "d2h_bytes_per_step": 4,
                     "input": "pinned host fp32 images + labels uploaded every step, loss read back every step", "loss_last_step": loss_e2e},
             "gpu_launches": 9 * args.steps, "launches_per_step": 9,
-            "phases_last_step": phases,
+            "phases_last_step": phases, "cuda_graph_step": graph_line,
             "kernels": {"simota_assign_us": t_simota, "simota_GBps_of_prediction_tensor": sim_bytes / t_simota / 1e3,
                         "head_losses_us": t_loss, "head_losses_GBps": 2 * sim_bytes / t_loss / 1e3,
                         "allreduce_us_standalone": t_ar, "allreduce_share_of_step": (t_ar / 1e3 / ms) if t_ar else None,

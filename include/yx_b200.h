@@ -322,10 +322,12 @@ int yx_head_train_decode_bwd(const float* grad_out, const float* out, const floa
  *   chunks : device int32 [n_chunks, 2] rows = (tensor index, first element); one CTA per chunk of chunk_elems elements
  *   first_step != 0: momentum buffers are initialised with the gradient (torch's first step)
  *   ema_decay d and ema_rest = (float)(1.0 - d) with d = decay * (1 - exp(-updates / 2000)) evaluated by the caller.
+ *   hyper (device fp32[3], may be NULL): {lr, ema_decay, ema_rest} read by the kernel INSTEAD of the arguments, so that a
+ *   CUDA graph holding this launch follows the schedule (the caller updates the three floats before each replay).
  * ------------------------------------------------------------------------------------------ */
 int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float lr,
                     float momentum, int32_t nesterov, int32_t first_step, float ema_decay, float ema_rest,
-                    void* stream);
+                    const float* hyper, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test-time preprocessing on the device (`preproc`, yolox/data/data_augment.py:140-156; YoloxProcessor.__call__,

@@ -56,7 +56,7 @@ int head_train_decode_bwd_launch(const float* gout, const float* out, const floa
                                  int w, float stride, int anchors, int anchor_off, void* greg, void* gobj, void* gcls,
                                  cudaStream_t s);
 int sgd_ema_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, float lr, float momentum,
-                   int nesterov, int first_step, float ema_decay, float ema_rest, cudaStream_t s);
+                   int nesterov, int first_step, float ema_decay, float ema_rest, const float* hyper, cudaStream_t s);
 int letterbox_launch(const void* images_dev, int batch, int channels, int H, int W, void* out, int out_dtype, cudaStream_t s);
 int coco_rows_launch(const float* dets, const int* det_count, int batch, int max_det, const float* scale,
                      const long long* image_ids, const int* class_ids, int n_class_ids, float* bbox, float* score,
@@ -402,11 +402,11 @@ int yx_head_train_decode_bwd(const float* grad_out, const float* out, const floa
 
 int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float lr,
                     float momentum, int32_t nesterov, int32_t first_step, float ema_decay, float ema_rest,
-                    void* stream) {
+                    const float* hyper, void* stream) {
   int rc = require_device();
   if (rc) return rc;
   return sgd_ema_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, lr, momentum, nesterov,
-                        first_step, ema_decay, ema_rest, (cudaStream_t)stream);
+                        first_step, ema_decay, ema_rest, hyper, (cudaStream_t)stream);
 }
 
 int yx_letterbox_u8(const yx_letterbox_image* images, int32_t batch, int32_t channels, int32_t H, int32_t W, void* out,

@@ -72,6 +72,11 @@ __device__ __forceinline__ void unpack16_t(uint32_t w, float& a, float& b) {
 }
 
 // FP16 is a compile-time parameter: a runtime flag costs a branch per packed pair in the hot loop
+#ifdef YX_EPI_NOBIAS   // experiment builds only: how much of an epilogue is the shared-memory read of the bias?
+#define YX_BIAS4(ptr) make_float4(0.f, 0.f, 0.f, 0.f)
+#else
+#define YX_BIAS4(ptr) (*reinterpret_cast<const float4*>(ptr))
+#endif
 template <bool FP16, bool SILU_ONLY = false>
 __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t (&raw)[16], const float* bias,
                                              const uint32_t* res, uint16_t* dst, int b, int ho, int wo, int c0) {
@@ -83,7 +88,7 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
   if (SILU_ONLY && fp16) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+      const float4 bb = YX_BIAS4(bias + j);
       v[j + 0] = silu_exp(__uint_as_float(raw[j + 0]) + bb.x);
       v[j + 1] = silu_exp(__uint_as_float(raw[j + 1]) + bb.y);
       v[j + 2] = silu_exp(__uint_as_float(raw[j + 2]) + bb.z);
@@ -94,7 +99,7 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
     // 3 instructions per element: h = fma(acc, 0.5, bias/2); t = tanh(h); y = fma(h, t, h)
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+      const float4 bb = YX_BIAS4(bias + j);
       const float hb[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -107,7 +112,7 @@ __device__ __forceinline__ void epi_tc_chunk(const EpiParams& e, const uint32_t 
   } else {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+      const float4 bb = YX_BIAS4(bias + j);
       v[j + 0] = __uint_as_float(raw[j + 0]) + bb.x;
       v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
       v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z;

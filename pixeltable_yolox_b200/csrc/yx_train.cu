@@ -128,7 +128,10 @@ static constexpr int kSgdThreads = 256;
 
 __global__ void __launch_bounds__(kSgdThreads)
 sgd_ema_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int chunk_elems, float lr, float momentum,
-               int nesterov, int first_step, float ema_decay, float ema_rest) {
+               int nesterov, int first_step, float ema_decay, float ema_rest, const float* __restrict__ hyper) {
+  // hyper (device, may be null): {lr, ema_decay, 1 - ema_decay} read at run time, so that a CUDA graph that captured this
+  // launch follows the learning-rate schedule and the EMA ramp without being re-captured
+  if (hyper) { lr = hyper[0]; ema_decay = hyper[1]; ema_rest = hyper[2]; }
   const int t = chunks[2 * blockIdx.x], e0 = chunks[2 * blockIdx.x + 1];
   const long long* row = table + (long long)t * 6;
   float* p = reinterpret_cast<float*>(row[0]);
@@ -159,11 +162,11 @@ sgd_ema_kernel(const long long* __restrict__ table, const int* __restrict__ chun
 }
 
 int sgd_ema_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, float lr, float momentum,
-                   int nesterov, int first_step, float ema_decay, float ema_rest, cudaStream_t s) {
+                   int nesterov, int first_step, float ema_decay, float ema_rest, const float* hyper, cudaStream_t s) {
   YX_REQUIRE(table && chunks, YX_ERR_INVALID_ARG, "sgd_ema: null table");
   YX_REQUIRE(n_chunks >= 0 && chunk_elems > 0, YX_ERR_INVALID_ARG, "sgd_ema: bad chunking");
   if (n_chunks == 0) return YX_OK;
-  sgd_ema_kernel<<<n_chunks, kSgdThreads, 0, s>>>(table, chunks, chunk_elems, lr, momentum, nesterov, first_step, ema_decay, ema_rest);
+  sgd_ema_kernel<<<n_chunks, kSgdThreads, 0, s>>>(table, chunks, chunk_elems, lr, momentum, nesterov, first_step, ema_decay, ema_rest, hyper);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

@@ -474,8 +474,9 @@ def head_train_decode_bwd(grad_out: torch.Tensor, out: torch.Tensor, grad_origin
 
 
 def sgd_ema_step(table: torch.Tensor, chunks: torch.Tensor, chunk_elems: int, lr: float, momentum: float, nesterov: bool,
-                 first_step: bool, ema_decay: float) -> None:
-    """One launch over every tensor of `table` (see include/yx_b200.h: yx_sgd_ema_step)."""
+                 first_step: bool, ema_decay: float, hyper: Optional[torch.Tensor] = None) -> None:
+    """One launch over every tensor of `table` (see include/yx_b200.h: yx_sgd_ema_step). `hyper`: device fp32[3]
+    {lr, ema_decay, 1 - ema_decay} read by the kernel instead of the arguments (CUDA-graph replay)."""
     import numpy as np
 
     dev = table.device
@@ -483,7 +484,8 @@ def sgd_ema_step(table: torch.Tensor, chunks: torch.Tensor, chunk_elems: int, lr
     with on_device(dev):
         check(lib().yx_sgd_ema_step(table.data_ptr(), chunks.data_ptr(), chunks.shape[0], int(chunk_elems), float(lr), float(momentum),
                                     1 if nesterov else 0, 1 if first_step else 0, float(np.float32(ema_decay)),
-                                    float(np.float32(1.0 - ema_decay)), stream_ptr(dev)), "sgd_ema_step")
+                                    float(np.float32(1.0 - ema_decay)), 0 if hyper is None else hyper.data_ptr(), stream_ptr(dev)),
+              "sgd_ema_step")
 
 
 def letterbox_u8(images, size, device: torch.device, dtype: torch.dtype = torch.uint8) -> torch.Tensor:

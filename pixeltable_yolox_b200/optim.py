@@ -59,6 +59,10 @@ class FusedSgdEma:
         self._steps = 0
         self._table = None
         self._dev = dev
+        # CUDA-graph mode: the captured launch reads {lr, d, 1 - d} from this device buffer; set_hyper() refreshes it from a
+        # pinned host mirror before every replay (no host sync)
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory()
 
     def _build_table(self):
         """(re)built when a gradient tensor was reallocated (zero_grad(set_to_none=True) gives new storage each step only
@@ -88,6 +92,28 @@ class FusedSgdEma:
         grads = [p.grad for p in self.params if p.grad is not None]
         if grads:
             torch._foreach_zero_(grads)          # a handful of multi-tensor launches instead of one per parameter
+
+    def set_hyper(self, lr: Optional[float] = None):
+        """Advance the EMA ramp by one update and publish {lr, d, 1 - d} to the device buffer a captured step() reads.
+        Call once before each graph replay (the replay itself runs the optimizer + EMA launch)."""
+        if lr is not None:
+            self.lr = float(lr)
+        d = 0.0
+        if self.ema is not None:
+            self.updates += 1
+            d = self.ema_decay * (1 - math.exp(-self.updates / 2000))
+        self._hyper_host[0] = self.lr
+        self._hyper_host[1] = float(np.float32(d))
+        self._hyper_host[2] = float(np.float32(1.0 - d))
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        self._steps += 1
+
+    @torch.no_grad()
+    def step_captured(self):
+        """The launch to record inside torch.cuda.graph(): hyper-parameters come from `self.hyper` at run time."""
+        if self._table is None:
+            raise RuntimeError("FusedSgdEma.step_captured: run at least one eager step() first (pointer table, momentum init)")
+        ops.sgd_ema_step(self._table, self._chunks, self.CHUNK, self.lr, self.momentum, self.nesterov, False, 0.0, self.hyper)
 
     @torch.no_grad()
     def step(self, lr: Optional[float] = None):

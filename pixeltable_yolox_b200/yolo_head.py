@@ -187,12 +187,22 @@ class YoloxHead(_B200Block):
             grid = self._level_grid(k, reg_output.shape[-2], reg_output.shape[-1], xin[0].type())
             x_shifts.append(grid[:, :, 0])
             y_shifts.append(grid[:, :, 1])
-            expanded_strides.append(torch.zeros(1, grid.shape[1]).fill_(self.strides[k]).type_as(xin[0]))
+            expanded_strides.append(self._level_strides(k, grid.shape[1], xin[0]))
             if self.use_l1:
                 origin_preds.append(origin)
             outputs.append(output)
         return self.get_losses(imgs, x_shifts, y_shifts, expanded_strides, labels, torch.cat(outputs, 1),
                                origin_preds, dtype=xin[0].dtype)
+
+    def _level_strides(self, k, n, like):
+        """[1, n] tensor filled with the level's stride (yolo_head.py:175-179), built once per level / size / dtype: the
+        reference builds it on the host every step (an H2D copy per level, which also breaks CUDA-graph capture)."""
+        cache = self.__dict__.setdefault("_stride_cache", {})
+        key = (k, n, like.dtype, like.device)
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = torch.full((1, n), float(self.strides[k]), dtype=like.dtype, device=like.device)
+        return t
 
     def _level_grid(self, k, hsize, wsize, dtype):
         grid = self.grids[k]
