@@ -854,9 +854,22 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev):
     import torch
     import torch.distributed as dist
 
+    if world > 1:
+        # a copy of the module WITHOUT the DDP wrapper: DDP's gradient hooks live on the parameters themselves and launch on
+        # streams of their own during backward, which a stream capture rejects (cudaErrorStreamCaptureImplicit)
+        import copy
+
+        from pixeltable_yolox_b200.optim import FusedSgdEma
+
+        raw = copy.deepcopy(model.module).train()
+        opt = FusedSgdEma(raw, lr=opt.lr, momentum=opt.momentum, weight_decay=5e-4, nesterov=opt.nesterov, ema=True,
+                          ema_decay=opt.ema_decay)
+    else:
+        raw = model
+
     def eager():
         with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
-            out = model(x, lab)
+            out = raw(x, lab)
         opt.zero_grad()
         out["total_loss"].backward()
         opt.step()
@@ -864,29 +877,48 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev):
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for _ in range(11 if world > 1 else 3):        # DDP needs 11 warm-up iterations before capture (torch docs)
+        for _ in range(3):
             eager()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    # With several ranks the step is TWO graphs around one eager ncclAllReduce of the flattened gradients:
+    # graph 1 = forward + assignment + losses + backward + flatten, graph 2 = average + scatter + SGD/EMA
+    params = [q for q in raw.parameters() if q.requires_grad]
+    g, g2, flat = torch.cuda.CUDAGraph(), None, None
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
         with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
-            out = model(x, lab)
+            out = raw(x, lab)
         loss = out["total_loss"]
         opt.zero_grad()
         loss.backward()
-        opt.step_captured()
-    for _ in range(3):
+        if world > 1:
+            grads = [q.grad for q in params]
+            flat = torch.cat([t.reshape(-1) for t in grads])
+        else:
+            opt.step_captured()
+    if world > 1:
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+            flat.div_(world)
+            torch._foreach_copy_(grads, [v.view_as(t) for v, t in zip(flat.split([t.numel() for t in grads]), grads)])
+            opt.step_captured()
+
+    def replay():
         opt.set_hyper()
         g.replay()
+        if world > 1:
+            dist.all_reduce(flat)
+            g2.replay()
+
+    for _ in range(3):
+        replay()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        opt.set_hyper()
-        g.replay()
+        replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -931,11 +963,20 @@ def run_train(args, world, rank, dev):
     try:
         gms, gloss = time_train_graph(net, opt, x, lab, args.steps, amp_dtype, world, dev)
         graph_line = {"ms_per_step": gms, "images_per_second": world * B / (gms / 1e3), "loss_last_step": gloss,
-                      "what": "forward + SimOTA + losses + backward" + (" + DDP all-reduce" if world > 1 else "") +
-                              " + SGD/EMA captured once with torch.cuda.graph and replayed; lr / EMA decay via a device buffer"}
+                      "what": ("forward + SimOTA + losses + backward + SGD/EMA captured once with torch.cuda.graph and replayed"
+                               if world == 1 else
+                               "two captured graphs (forward + SimOTA + losses + backward + gradient flatten | average + scatter + "
+                               "SGD/EMA) around one eager ncclAllReduce of the flattened gradients, on a copy of the module "
+                               "without the DDP wrapper") + "; lr / EMA decay reach the captured optimizer launch via a device buffer"}
     except Exception as e:                            # noqa: BLE001
+        import traceback
+
         graph_line = {"failed": repr(e)[:300]}
-        torch.cuda.synchronize()
+        print("# cuda-graph training step failed:\n" + traceback.format_exc(), file=sys.stderr)
+        try:
+            torch.cuda.synchronize()
+        except Exception:                             # noqa: BLE001
+            pass
 
     # ---- our kernels of the step, stand-alone on this rank's head output shape
     model.eval()        # BN statistics are irrelevant here: only shapes and value ranges of the head output matter

@@ -150,3 +150,61 @@ def test_fused_sgd_ema_matches_torch_sgd_and_reference_ema(cuda):
             if a.dtype.is_floating_point:
                 torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-7, msg=lambda m: f"step {step} ema {k}: {m}")
     assert fused.updates == 3
+
+
+def test_training_step_as_cuda_graph_matches_eager(cuda):
+    """The whole training step (forward, SimOTA, losses, backward, fused SGD + EMA) captured once and replayed gives the
+    loss, parameters and EMA the eager step gives FROM THE SAME STATE (two models drift apart on random weights: the SimOTA
+    costs are near-tied, so 1e-7 differences from cuDNN's atomics flip assignments). Nothing in the step synchronises with
+    the host; the learning rate / EMA ramp reach the captured optimizer launch through FusedSgdEma.hyper."""
+    from pixeltable_yolox_b200.optim import FusedSgdEma
+
+    torch.manual_seed(0)
+    cfg = yx.YoloxConfig("graph", depth=0.33, width=0.25)
+    m = cfg.get_model().to(cuda).train()
+    x = torch.from_numpy(syn.images(2, 128, 128, seed=3)).to(cuda)
+    lab = torch.from_numpy(syn.labels(2, max_gt=8, seed=5, size=128.0, counts=[3, 5])).to(cuda)
+    opt = FusedSgdEma(m, lr=0.01, ema=True)
+
+    def eager(lr):
+        out = m(x, lab)
+        opt.zero_grad()
+        out["total_loss"].backward()
+        opt.step(lr)
+        return out["total_loss"].detach().clone()
+
+    def snapshot():
+        return ([v.clone() for v in m.state_dict().values()], [b.clone() for b in opt.bufs],
+                [v.clone() for v in opt.ema.state_dict().values()], opt.updates)
+
+    def restore(s):
+        with torch.no_grad():
+            for dst, src in zip(m.state_dict().values(), s[0]): dst.copy_(src)
+            for dst, src in zip(opt.bufs, s[1]): dst.copy_(src)
+            for dst, src in zip(opt.ema.state_dict().values(), s[2]): dst.copy_(src)
+        opt.updates = s[3]
+
+    for _ in range(2):                                   # momentum buffers, pointer table, workspaces
+        eager(0.01)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = m(x, lab)
+        loss_g = out["total_loss"]
+        opt.zero_grad()
+        loss_g.backward()
+        opt.step_captured()
+    for lr in (0.02, 0.005):
+        before = snapshot()
+        want_loss = eager(lr)
+        want = snapshot()
+        restore(before)
+        opt.set_hyper(lr)
+        g.replay()
+        got = snapshot()
+        torch.testing.assert_close(loss_g.detach(), want_loss, rtol=1e-5, atol=1e-6)
+        assert got[3] == want[3]
+        for part in range(3):
+            for i, (a, b) in enumerate(zip(got[part], want[part])):
+                if a.dtype.is_floating_point:
+                    torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-4, msg=lambda t: f"part {part} tensor {i}: {t}")   # cuDNN wgrad atomics
