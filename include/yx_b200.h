@@ -330,6 +330,26 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
                     const float* hyper, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d + activation of a BaseConv (yolox/models/network_blocks.py:27-52 with the BN in train mode;
+ * eps / momentum as set by yolox/config.py:165-176), forward and backward, on the conv output x [N, C, H*W] (contiguous
+ * NCHW; YX_FP32 / YX_BF16 / YX_FP16), statistics and affine parameters in fp32.
+ *   fwd: batch mean / biased variance per channel -> save_mean, save_invstd [C]; running_mean / running_var (may be NULL)
+ *        updated with `momentum` and the UNBIASED variance like F.batch_norm; y = act(x_hat * gamma + beta), same dtype as x.
+ *   bwd: dy = gradient w.r.t. y -> dx (dtype of x), dgamma, dbeta [C] fp32. x_hat and the pre-activation are recomputed
+ *        from x and the saved statistics, nothing else is kept from the forward.
+ *   act: YX_ACT_SILU / YX_ACT_RELU / YX_ACT_LRELU / YX_ACT_NONE.  workspace: yx_bn_act_workspace_bytes(N, C, H*W).
+ * ------------------------------------------------------------------------------------------ */
+int64_t yx_bn_act_workspace_bytes(int32_t n, int32_t c, int32_t hw);
+int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t n, int32_t c, int32_t hw, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                        const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                        int32_t act, void* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test-time preprocessing on the device (`preproc`, yolox/data/data_augment.py:140-156; YoloxProcessor.__call__,
  * yolox/models/processor.py:30-37): aspect-preserving cv2.resize(INTER_LINEAR) of each decoded HWC uint8 image into the
  * top-left corner of a 114-grey H x W canvas, HWC -> CHW. Bit-exact with OpenCV's 8-bit fixed-point bilinear.

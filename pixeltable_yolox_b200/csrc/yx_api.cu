@@ -61,6 +61,13 @@ int letterbox_launch(const void* images_dev, int batch, int channels, int H, int
 int coco_rows_launch(const float* dets, const int* det_count, int batch, int max_det, const float* scale,
                      const long long* image_ids, const int* class_ids, int n_class_ids, float* bbox, float* score,
                      int* category, long long* image_id, int* total, cudaStream_t s);
+long long bn_act_ws_bytes(int n, int c, int hw);
+int bn_act_train_fwd_launch(const void* x, int dtype, int n, int c, int hw, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, int act, void* y, float* save_mean,
+                            float* save_invstd, void* ws, long long ws_bytes, cudaStream_t s);
+int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int n, int c, int hw, const float* gamma, const float* beta,
+                            const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
+                            void* ws, long long ws_bytes, cudaStream_t s);
 struct StemLaunch;
 StemLaunch* stem_alloc();
 void stem_free(StemLaunch*);
@@ -407,6 +414,28 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
   if (rc) return rc;
   return sgd_ema_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, lr, momentum, nesterov,
                         first_step, ema_decay, ema_rest, hyper, (cudaStream_t)stream);
+}
+
+int64_t yx_bn_act_workspace_bytes(int32_t n, int32_t c, int32_t hw) { return bn_act_ws_bytes(n, c, hw); }
+
+int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t n, int32_t c, int32_t hw, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return bn_act_train_fwd_launch(x, dtype, n, c, hw, gamma, beta, eps, momentum, running_mean, running_var, act, y, save_mean,
+                                 save_invstd, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                        const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                        int32_t act, void* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return bn_act_train_bwd_launch(x, dy, dtype, n, c, hw, gamma, beta, save_mean, save_invstd, act, dx, dgamma, dbeta, workspace,
+                                 workspace_bytes, (cudaStream_t)stream);
 }
 
 int yx_letterbox_u8(const yx_letterbox_image* images, int32_t batch, int32_t channels, int32_t H, int32_t W, void* out,

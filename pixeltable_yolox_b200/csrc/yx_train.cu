@@ -171,4 +171,244 @@ int sgd_ema_launch(const long long* table, const int* chunks, int n_chunks, int 
   return YX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 3. Training-mode BatchNorm + activation, forward and backward (the BN + SiLU of every BaseConv in the training step:
+//    yolox/models/network_blocks.py:27-52 with nn.BatchNorm2d in train mode, eps / momentum from yolox/config.py:165-176)
+// ------------------------------------------------------------------------------------------
+// torch runs four to six kernels per layer and direction (collect statistics, transform, silu; silu_backward,
+// batch_norm_backward); at 8 images per GPU they were 52 % of the step's GPU time (8.7 of 16.8 ms, tools/gpu_prof_train.py).
+// Here: x is the conv output [N, C, H*W] (NCHW, bf16 / fp16 / fp32), statistics in fp32.
+//   forward : bn_stats (partial sum / sum of squares per (channel, slab chunk)) -> bn_finalize (mean, 1/std, running
+//             statistics with torch's unbiased variance) -> bn_act_apply (y = act(x_hat * gamma + beta))
+//   backward: bn_act_bwd_reduce (dz = dy * act'(z); sum dz, sum dz * x_hat) -> finalize (dgamma, dbeta) ->
+//             bn_act_bwd_apply (dx = gamma / std * (dz - dbeta / M - x_hat * dgamma / M))
+// z and x_hat are recomputed from x, never stored. 16-byte loads when H*W is a multiple of 8 (every map of the named configs).
+static constexpr int kBnThreads = 256;
+static constexpr int kBnChunk = 8192;        // elements of one (n, c) slab per CTA
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(w[j] << 16); v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec8<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j])); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec8<float> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+__device__ __forceinline__ float2 block_sum2(float a, float b) {
+  __shared__ float sa[kBnThreads / 32], sb[kBnThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < kBnThreads / 32 ? sa[lane] : 0.0f; b = lane < kBnThreads / 32 ? sb[lane] : 0.0f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  }
+  return make_float2(a, b);       // valid in thread 0
+}
+
+// act: YX_ACT_SILU / RELU / LRELU / NONE. value and derivative at z.
+__device__ __forceinline__ float bn_act(float z, int act) {
+  if (act == YX_ACT_SILU) return z / (1.0f + __expf(-z));
+  if (act == YX_ACT_RELU) return fmaxf(z, 0.0f);
+  if (act == YX_ACT_LRELU) return z > 0.0f ? z : 0.1f * z;
+  return z;
+}
+__device__ __forceinline__ float bn_act_grad(float z, int act) {
+  if (act == YX_ACT_SILU) { const float s = 1.0f / (1.0f + __expf(-z)); return s * (1.0f + z * (1.0f - s)); }
+  if (act == YX_ACT_RELU) return z > 0.0f ? 1.0f : 0.0f;
+  if (act == YX_ACT_LRELU) return z > 0.0f ? 1.0f : 0.1f;
+  return 1.0f;
+}
+
+// grid (chunks, C, N): CTA (k, c, n) covers elements [k * kBnChunk, ...) of slab (n, c). part: [C][N * chunks][2]
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kBnThreads)
+bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int C, int HW, int act, float* __restrict__ part) {
+  const int c = blockIdx.y, n = blockIdx.z, k = blockIdx.x;
+  const long long base = ((long long)n * C + c) * HW;
+  const int lo = k * kBnChunk, hi = min(HW, lo + kBnChunk);
+  float s0 = 0.0f, s1 = 0.0f;
+  float mu = 0.0f, a = 1.0f, b = 0.0f, is = 1.0f;
+  if (BWD) { mu = mean[c]; is = invstd[c]; a = gamma[c]; b = beta[c]; }
+  auto one = [&](float xv, float dv) {
+    if (BWD) {
+      const float xh = (xv - mu) * is;
+      const float dz = dv * bn_act_grad(fmaf(xh, a, b), act);
+      s0 += dz; s1 = fmaf(dz, xh, s1);
+    } else {
+      s0 += xv; s1 = fmaf(xv, xv, s1);
+    }
+  };
+  if ((HW & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!BWD || (reinterpret_cast<uintptr_t>(dy) & 15) == 0)) {
+    for (int i = lo + threadIdx.x * 8; i < hi; i += kBnThreads * 8) {
+      float xv[8], dv[8];
+      Vec8<T>::load(x + base + i, xv);
+      if (BWD) Vec8<T>::load(dy + base + i, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) one(xv[j], BWD ? dv[j] : 0.0f);
+    }
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += kBnThreads) one(Cvt<T>::to_f(x[base + i]), BWD ? Cvt<T>::to_f(dy[base + i]) : 0.0f);
+  }
+  const float2 r = block_sum2(s0, s1);
+  if (threadIdx.x == 0) {
+    const long long p = ((long long)c * gridDim.z * gridDim.x + (long long)n * gridDim.x + k) * 2;
+    part[p] = r.x; part[p + 1] = r.y;
+  }
+}
+
+// one thread per channel. FWD: mean / invstd + running statistics; BWD: dbeta (sum dz), dgamma (sum dz * x_hat)
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int C, int S, double M, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ out0, float* __restrict__ out1, int bwd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int s = 0; s < S; ++s) { a += (double)part[((long long)c * S + s) * 2]; b += (double)part[((long long)c * S + s) * 2 + 1]; }
+  if (bwd) { out0[c] = (float)a; out1[c] = (float)b; return; }
+  const double mean = a / M;
+  double var = b / M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  out0[c] = (float)mean;
+  out1[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {                                  // F.batch_norm: running_var takes the unbiased estimate
+    const double unbiased = M > 1.0 ? var * M / (M - 1.0) : var;
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+  }
+}
+
+// FWD: y = act(x_hat * gamma + beta).  BWD: dx = gamma * invstd * (dz - dbeta / M - x_hat * dgamma / M)
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dbeta,
+                const float* __restrict__ dgamma, float inv_m, int C, int HW, int act, T* __restrict__ out) {
+  const int c = blockIdx.y, n = blockIdx.z, k = blockIdx.x;
+  const long long base = ((long long)n * C + c) * HW;
+  const int lo = k * kBnChunk, hi = min(HW, lo + kBnChunk);
+  const float mu = mean[c], is = invstd[c], g = gamma[c], b = beta[c];
+  float k0 = 0.0f, k1 = 0.0f, gi = 0.0f;
+  if (BWD) { k0 = dbeta[c] * inv_m; k1 = dgamma[c] * inv_m; gi = g * is; }
+  auto one = [&](float xv, float dv) -> float {
+    const float xh = (xv - mu) * is;
+    const float z = fmaf(xh, g, b);
+    if (!BWD) return bn_act(z, act);
+    const float dz = dv * bn_act_grad(z, act);
+    return gi * (dz - k0 - xh * k1);
+  };
+  const bool vec = (HW & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (!BWD || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  if (vec) {
+    for (int i = lo + threadIdx.x * 8; i < hi; i += kBnThreads * 8) {
+      float xv[8], dv[8], r[8];
+      Vec8<T>::load(x + base + i, xv);
+      if (BWD) Vec8<T>::load(dy + base + i, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = one(xv[j], BWD ? dv[j] : 0.0f);
+      Vec8<T>::store(out + base + i, r);
+    }
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += kBnThreads)
+      out[base + i] = Cvt<T>::from_f(one(Cvt<T>::to_f(x[base + i]), BWD ? Cvt<T>::to_f(dy[base + i]) : 0.0f));
+  }
+}
+
+long long bn_act_ws_bytes(int n, int c, int hw) {
+  if (n <= 0 || c <= 0 || hw <= 0) return 256;
+  const long long chunks = (hw + kBnChunk - 1) / kBnChunk;
+  return (((long long)c * n * chunks * 2 * 4) + 255) & ~255LL;
+}
+
+static int bn_check(int dtype, int n, int c, int hw, int act) {
+  YX_REQUIRE(dtype == YX_FP32 || dtype == YX_BF16 || dtype == YX_FP16, YX_ERR_INVALID_ARG, "bn_act: dtype %d", dtype);
+  YX_REQUIRE(n > 0 && c > 0 && hw > 0 && n <= 65535 && c <= 65535, YX_ERR_INVALID_ARG, "bn_act: bad sizes");
+  YX_REQUIRE(act == YX_ACT_SILU || act == YX_ACT_RELU || act == YX_ACT_LRELU || act == YX_ACT_NONE, YX_ERR_INVALID_ARG, "bn_act: act %d", act);
+  return YX_OK;
+}
+
+int bn_act_train_fwd_launch(const void* x, int dtype, int n, int c, int hw, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, int act, void* y, float* save_mean,
+                            float* save_invstd, void* ws, long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, YX_ERR_INVALID_ARG, "bn_act_fwd: null pointer");
+  int rc = bn_check(dtype, n, c, hw, act);
+  if (rc) return rc;
+  YX_REQUIRE(bn_act_ws_bytes(n, c, hw) <= ws_bytes, YX_ERR_CAPACITY, "bn_act_fwd: workspace too small");
+  const int chunks = (hw + kBnChunk - 1) / kBnChunk;
+  const dim3 grid((unsigned)chunks, (unsigned)c, (unsigned)n);
+  float* part = reinterpret_cast<float*>(ws);
+#define YX_GO(T) bn_reduce_kernel<T, false><<<grid, kBnThreads, 0, s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, c, hw, act, part)
+  if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
+#undef YX_GO
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(part, c, n * chunks, (double)n * hw, eps, momentum, running_mean, running_var,
+                                                     save_mean, save_invstd, 0);
+#define YX_GO(T) bn_apply_kernel<T, false><<<grid, kBnThreads, 0, s>>>((const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, c, hw, act, (T*)y)
+  if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
+#undef YX_GO
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int n, int c, int hw, const float* gamma, const float* beta,
+                            const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
+                            void* ws, long long ws_bytes, cudaStream_t s) {
+  YX_REQUIRE(x && dy && gamma && beta && save_mean && save_invstd && dx && dgamma && dbeta && ws, YX_ERR_INVALID_ARG, "bn_act_bwd: null pointer");
+  int rc = bn_check(dtype, n, c, hw, act);
+  if (rc) return rc;
+  YX_REQUIRE(bn_act_ws_bytes(n, c, hw) <= ws_bytes, YX_ERR_CAPACITY, "bn_act_bwd: workspace too small");
+  const int chunks = (hw + kBnChunk - 1) / kBnChunk;
+  const dim3 grid((unsigned)chunks, (unsigned)c, (unsigned)n);
+  float* part = reinterpret_cast<float*>(ws);
+#define YX_GO(T) bn_reduce_kernel<T, true><<<grid, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, c, hw, act, part)
+  if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
+#undef YX_GO
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(part, c, n * chunks, (double)n * hw, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1);
+  const float inv_m = (float)(1.0 / ((double)n * hw));
+#define YX_GO(T) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, c, hw, act, (T*)dx)
+  if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
+#undef YX_GO
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
 }  // namespace yx

@@ -11,6 +11,8 @@ Execution model
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -33,6 +35,33 @@ def act_name(module: nn.Module) -> str:
     if isinstance(module, nn.ReLU):
         return "relu"
     raise AttributeError(f"Unsupported activation module {type(module).__name__}")
+
+
+class _FusedBnAct(torch.autograd.Function):
+    """Training-mode BatchNorm2d + activation of a BaseConv as three launches each way (csrc/yx_train.cu: statistics,
+    finalize, apply) instead of torch's collect-statistics / transform / activation and activation-backward /
+    batch_norm_backward kernels, which were 52 % of the training step's GPU time at 8 images per GPU
+    (tools/gpu_prof_train.py). Running statistics are updated in place like F.batch_norm."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act):
+        from . import ops
+        from ._lib import ACT_CODES
+
+        x = x.contiguous()
+        code = ACT_CODES[act]
+        y, mean, invstd = ops.bn_act_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, code)
+        ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        ctx.act = code
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_act_train_bwd(x, dy.contiguous().to(x.dtype), gamma, beta, mean, invstd, ctx.act)
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 class _B200Block(nn.Module):
@@ -63,7 +92,17 @@ class BaseConv(_B200Block):
         self.act = get_activation(act, inplace=True)
 
     def _train_forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        y = self.conv(x)
+        bn = self.bn
+        if (y.is_cuda and bn.training and bn.momentum is not None and bn.track_running_stats and bn.affine
+                and bn.weight.dtype == torch.float32 and y.dim() == 4 and y.dtype in (torch.float32, torch.bfloat16, torch.float16)
+                and os.environ.get("YX_FUSED_BN", "1") != "0"):
+            # nn.BatchNorm2d.forward in train mode: batch statistics, running statistics updated with `momentum`
+            # (num_batches_tracked counts the calls), then the activation -- one fused pass each way
+            bn.num_batches_tracked.add_(1)
+            return _FusedBnAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                                     act_name(self.act))
+        return self.act(bn(y))
 
     def fuseforward(self, x):
         return self.act(self.conv(x))

@@ -548,3 +548,45 @@ def coco_rows(dets: torch.Tensor, det_count: torch.Tensor, scale: torch.Tensor, 
                                  score.data_ptr(), cat.data_ptr(), iid.data_ptr(), total.data_ptr(), stream_ptr(dev)), "coco_rows")
     k = int(total.item())
     return bbox[:k].cpu(), score[:k].cpu(), cat[:k].cpu(), iid[:k].cpu()
+
+
+def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
+                     running_var: Optional[torch.Tensor], eps: float, momentum: float, act: int):
+    """Training-mode BatchNorm2d + activation on a conv output x [N, C, H, W] (contiguous NCHW). Returns
+    (y, save_mean, save_invstd); running statistics are updated in place like F.batch_norm."""
+    require_cuda(x, "bn_act_train_fwd")
+    dev = x.device
+    same_device(dev, "bn_act_train_fwd", gamma=gamma, beta=beta, running_mean=running_mean, running_var=running_var)
+    assert x.dim() == 4 and x.is_contiguous() and gamma.dtype == beta.dtype == torch.float32
+    N, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    invstd = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    nbytes = lib().yx_bn_act_workspace_bytes(N, Cc, H * W)
+    ws = _workspace(dev, nbytes, "bn")
+    with on_device(dev):
+        check(lib().yx_bn_act_train_fwd(x.data_ptr(), dtype_code(x.dtype), N, Cc, H * W, gamma.data_ptr(), beta.data_ptr(),
+                                        float(eps), float(momentum), 0 if running_mean is None else running_mean.data_ptr(),
+                                        0 if running_var is None else running_var.data_ptr(), int(act), y.data_ptr(),
+                                        mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+              "bn_act_train_fwd")
+    return y, mean, invstd
+
+
+def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean: torch.Tensor,
+                     invstd: torch.Tensor, act: int):
+    """Backward of bn_act_train_fwd: (dx in x's dtype, dgamma, dbeta fp32)."""
+    dev = x.device
+    same_device(dev, "bn_act_train_bwd", dy=dy, gamma=gamma, beta=beta, mean=mean, invstd=invstd)
+    assert x.is_contiguous() and dy.is_contiguous() and dy.dtype == x.dtype and dy.shape == x.shape
+    N, Cc, H, W = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib().yx_bn_act_workspace_bytes(N, Cc, H * W), "bn")
+    with on_device(dev):
+        check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), N, Cc, H * W, gamma.data_ptr(),
+                                        beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(act), dx.data_ptr(),
+                                        dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+              "bn_act_train_bwd")
+    return dx, dgamma, dbeta

@@ -211,3 +211,39 @@ def test_training_step_as_cuda_graph_matches_eager(cuda):
                 if a.dtype.is_floating_point:
                     torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-4, msg=lambda t: f"part {part} tensor {i}: {t}")
     torch.backends.cudnn.deterministic, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("act", ["silu", "relu", "lrelu"])
+@pytest.mark.parametrize("shape", [(3, 48, 20, 20), (2, 32, 37, 29), (8, 16, 80, 80)])
+def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape):
+    """Training-mode BatchNorm2d + activation (one fused pass each way) against nn.BatchNorm2d + the activation module in
+    torch: output, running statistics, and the gradients w.r.t. input, gamma and beta."""
+    from pixeltable_yolox_b200.network_blocks import _FusedBnAct, get_activation
+
+    g = torch.Generator().manual_seed(4)
+    N, Cc, H, W = shape
+    x0 = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(dtype).to(cuda)
+    bn = torch.nn.BatchNorm2d(Cc, eps=1e-3, momentum=0.03).to(cuda).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(Cc, generator=g) + 0.5); bn.bias.copy_(torch.randn(Cc, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(Cc, generator=g) * 0.1); bn.running_var.copy_(torch.rand(Cc, generator=g) + 0.5)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    x = x0.clone().requires_grad_(True)
+    y = _FusedBnAct.apply(x, gam, bet, rm, rv, bn.eps, bn.momentum, act)
+    go = torch.randn(shape, generator=g).to(dtype).to(cuda)
+    y.backward(go)
+    # reference in fp32 on the same (already rounded) input
+    xr = x0.float().clone().requires_grad_(True)
+    yr = get_activation(act, inplace=False)(bn(xr))
+    yr.backward(go.float())
+    tol = dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    assert y.dtype == dtype
+    torch.testing.assert_close(y.float(), yr, **tol)
+    torch.testing.assert_close(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(x.grad.float(), xr.grad, **tol)
+    gt = dict(rtol=1e-4, atol=1e-3) if dtype == torch.float32 else dict(rtol=2e-2, atol=5e-2 * (N * H * W) ** 0.5 / 10)
+    torch.testing.assert_close(gam.grad, bn.weight.grad, **gt)
+    torch.testing.assert_close(bet.grad, bn.bias.grad, **gt)
