@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: images per step over ALL ranks")
     ap.add_argument("--train", action="store_true", help="config 4: training step (8 images per rank by default)")
     ap.add_argument("--train-batch", type=int, default=8, help="--train: images per rank")
+    ap.add_argument("--train-format", default="channels_last", choices=["channels_last", "contiguous"],
+                    help="--train: memory format of the module and its input in our arm (cuDNN's 16-bit kernels are NHWC; "
+                         "our BatchNorm + activation kernels take both)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (conf 0.01, config 5, torch GPU reference)")
     return ap.parse_args()
 
@@ -956,6 +959,8 @@ def run_train(args, world, rank, dev):
     cfg, model = build_model(args, dev)
     sd_cpu = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
     model.train()
+    if args.train_format == "channels_last":
+        model = model.to(memory_format=torch.channels_last)
     n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
     net = model
     if world > 1:
@@ -966,6 +971,8 @@ def run_train(args, world, rank, dev):
     xh, labh, counts = train_batch(args, rank, B)
     xh, labh = xh.pin_memory(), labh.pin_memory()
     x, lab = xh.to(dev), labh.to(dev)
+    if args.train_format == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
     clocks = ClockSampler(dev.index)
     clocks.start(); clocks.wait_first()
     w0 = time.perf_counter()
@@ -1066,6 +1073,7 @@ def run_train(args, world, rank, dev):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
                        "labels": f"[{B}, 120, 5] per rank, GT counts on rank 0 {counts}", "amp": args.dtype,
+                       "memory_format": args.train_format,
                        "optimizer": "SGD momentum 0.9 nesterov, wd 5e-4 on conv weights (yolox/config.py:307-333) + ModelEMA update "
                                     "(yolox/utils/ema.py:46-58), both arms; ours: one fused launch (yx_sgd_ema_step)",
                        "network_fwd_bwd": "convolutions: torch autograd / cuDNN (no dgrad / wgrad tcgen05 kernels yet); BatchNorm + "

@@ -48,7 +48,8 @@ class _FusedBnAct(torch.autograd.Function):
         from . import ops
         from ._lib import ACT_CODES
 
-        x = x.contiguous()
+        if not ops._is_channels_last(x):
+            x = x.contiguous()
         code = ACT_CODES[act]
         y, mean, invstd = ops.bn_act_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, code)
         ctx.save_for_backward(x, gamma, beta, mean, invstd)
@@ -60,7 +61,10 @@ class _FusedBnAct(torch.autograd.Function):
         from . import ops
 
         x, gamma, beta, mean, invstd = ctx.saved_tensors
-        dx, dgamma, dbeta = ops.bn_act_train_bwd(x, dy.contiguous().to(x.dtype), gamma, beta, mean, invstd, ctx.act)
+        dy = dy.to(x.dtype)
+        if dy.stride() != x.stride():                       # same memory format as x (NCHW or channels_last)
+            dy = dy.contiguous(memory_format=torch.channels_last) if ops._is_channels_last(x) else dy.contiguous()
+        dx, dgamma, dbeta = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act)
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
@@ -92,7 +96,9 @@ class BaseConv(_B200Block):
         self.act = get_activation(act, inplace=True)
 
     def _train_forward(self, x):
-        y = self.conv(x)
+        from .train_conv import conv2d
+
+        y = conv2d(x, self.conv)             # tcgen05 forward / dgrad / wgrad under 16-bit autocast, else torch
         bn = self.bn
         if (y.is_cuda and bn.training and bn.momentum is not None and bn.track_running_stats and bn.affine
                 and bn.weight.dtype == torch.float32 and y.dim() == 4 and y.dtype in (torch.float32, torch.bfloat16, torch.float16)

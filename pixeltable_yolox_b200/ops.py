@@ -550,6 +550,12 @@ def coco_rows(dets: torch.Tensor, det_count: torch.Tensor, scale: torch.Tensor, 
     return bbox[:k].cpu(), score[:k].cpu(), cat[:k].cpu(), iid[:k].cpu()
 
 
+def _is_channels_last(x: torch.Tensor) -> bool:
+    """Dense NHWC memory (torch.channels_last) that is not also plain NCHW-contiguous, with a channel count the 16-byte
+    channel vectors of the channels-last kernels can take."""
+    return (x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0)
+
+
 def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
                      running_var: Optional[torch.Tensor], eps: float, momentum: float, act: int):
     """Training-mode BatchNorm2d + activation on a conv output x [N, C, H, W] (contiguous NCHW). Returns
@@ -557,15 +563,16 @@ def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, r
     require_cuda(x, "bn_act_train_fwd")
     dev = x.device
     same_device(dev, "bn_act_train_fwd", gamma=gamma, beta=beta, running_mean=running_mean, running_var=running_var)
-    assert x.dim() == 4 and x.is_contiguous() and gamma.dtype == beta.dtype == torch.float32
+    cl = _is_channels_last(x)
+    assert x.dim() == 4 and (cl or x.is_contiguous()) and gamma.dtype == beta.dtype == torch.float32
     N, Cc, H, W = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x)                  # preserves the memory format
     mean = torch.empty((Cc,), dtype=torch.float32, device=dev)
     invstd = torch.empty((Cc,), dtype=torch.float32, device=dev)
     nbytes = lib().yx_bn_act_workspace_bytes(N, Cc, H * W)
     ws = _workspace(dev, nbytes, "bn")
     with on_device(dev):
-        check(lib().yx_bn_act_train_fwd(x.data_ptr(), dtype_code(x.dtype), N, Cc, H * W, gamma.data_ptr(), beta.data_ptr(),
+        check(lib().yx_bn_act_train_fwd(x.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(), beta.data_ptr(),
                                         float(eps), float(momentum), 0 if running_mean is None else running_mean.data_ptr(),
                                         0 if running_var is None else running_var.data_ptr(), int(act), y.data_ptr(),
                                         mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
@@ -578,15 +585,83 @@ def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, bet
     """Backward of bn_act_train_fwd: (dx in x's dtype, dgamma, dbeta fp32)."""
     dev = x.device
     same_device(dev, "bn_act_train_bwd", dy=dy, gamma=gamma, beta=beta, mean=mean, invstd=invstd)
-    assert x.is_contiguous() and dy.is_contiguous() and dy.dtype == x.dtype and dy.shape == x.shape
+    cl = _is_channels_last(x)
+    assert dy.dtype == x.dtype and dy.shape == x.shape and dy.stride() == x.stride(), "dy must have x's dtype and memory format"
     N, Cc, H, W = x.shape
     dx = torch.empty_like(x)
     dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
     dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
     ws = _workspace(dev, lib().yx_bn_act_workspace_bytes(N, Cc, H * W), "bn")
     with on_device(dev):
-        check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), N, Cc, H * W, gamma.data_ptr(),
+        check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(),
                                         beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(act), dx.data_ptr(),
                                         dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
               "bn_act_train_bwd")
     return dx, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------ training conv stack
+def _nhwc(t: torch.Tensor) -> View:
+    """[B, C, H, W] tensor in dense channels_last memory -> the NHWC View the conv kernels take."""
+    assert t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last), "expected dense channels_last memory"
+    return View(t.permute(0, 2, 3, 1))
+
+
+def _weight_strides(w: torch.Tensor):
+    """(stride_o, stride_i, stride_tap) of an nn.Conv2d weight [o, i, kh, kw], tap = kw_count * kh + kw; holds for
+    NCHW-contiguous and channels_last weights alike."""
+    o, i, kh, kw = w.shape
+    so, si, sh, sw = w.stride()
+    if kh * kw > 1:
+        assert sh == kw * sw, "conv weight: the filter taps are not linearly strided"
+    return so, si, sw
+
+
+def pack_train_weights(weight: torch.Tensor, dtype: torch.dtype, o_pad: int, i_pad: int, want_dgrad: bool):
+    """fp32 conv weight -> (w_fwd [o_pad, taps, i_pad], w_dgrad [i_pad, taps, o_pad] or None) in `dtype`, one launch."""
+    require_cuda(weight, "pack_train_weights")
+    dev = weight.device
+    assert weight.dtype == torch.float32 and weight.dim() == 4
+    o, i, kh, kw = weight.shape
+    taps = kh * kw
+    wf = torch.empty((o_pad, taps, i_pad), dtype=dtype, device=dev)
+    wd = torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev) if want_dgrad else None
+    so, si, st = _weight_strides(weight)
+    with on_device(dev):
+        check(lib().yx_pack_train_weights(weight.data_ptr(), so, si, st, o, i, taps, o_pad, i_pad, wf.data_ptr(),
+                                          0 if wd is None else wd.data_ptr(), dtype_code(dtype), stream_ptr(dev)),
+              "pack_train_weights")
+    return wf, wd
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksize: int, stride: int) -> torch.Tensor:
+    """dW of y = conv(x, W): x [B, Ci_pad, H, W], dy [B, Co_pad, OH, OW], both 16-bit dense channels_last with channel
+    counts padded to multiples of 16; returns fp32 dW with weight_like's shape [o, i, k, k] and strides."""
+    require_cuda(x, "conv_wgrad")
+    dev = x.device
+    same_device(dev, "conv_wgrad", dy=dy, weight=weight_like)
+    xv, dv = _nhwc(x), _nhwc(dy)
+    assert x.dtype == dy.dtype and x.dtype in (torch.bfloat16, torch.float16)
+    o, i = weight_like.shape[0], weight_like.shape[1]
+    assert i <= xv.c and o <= dv.c and xv.B == dv.B
+    dw = torch.empty_strided(weight_like.shape, weight_like.stride(), dtype=torch.float32, device=dev)
+    so, si, st = _weight_strides(dw)
+    args = (xv.B, xv.H, xv.W, xv.c, dv.H, dv.W, dv.c, ksize, stride)
+    nbytes = lib().yx_conv_wgrad_workspace_bytes(*args)
+    if nbytes < 0:
+        check(-1, "conv_wgrad (workspace query)")
+    ws = _workspace(dev, nbytes, "wgrad")
+    with on_device(dev):
+        check(lib().yx_conv_wgrad(xv.ptr, xv.ld, dv.ptr, dv.ld, dtype_code(x.dtype), *args, i, o, dw.data_ptr(), so, si, st,
+                                  ws.data_ptr(), ws.numel(), stream_ptr(dev)), "conv_wgrad")
+    return dw
+
+
+def dilate2(dy: torch.Tensor, zh: int, zw: int) -> torch.Tensor:
+    """Zero-stuffed copy of dy [B, C, OH, OW] (channels_last): z [B, C, zh, zw] with z[..., 2*oy, 2*ox] = dy[..., oy, ox]."""
+    require_cuda(dy, "dilate2")
+    dv = _nhwc(dy)
+    z = torch.empty((dv.B, dv.c, zh, zw), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+    with on_device(dy.device):
+        check(lib().yx_dilate2(dv.ptr, z.data_ptr(), dv.B, dv.H, dv.W, zh, zw, dv.c, stream_ptr(dy.device)), "dilate2")
+    return z

@@ -54,7 +54,7 @@ class FusedSgdEma:
         missing = [p for p in self.params if id(p) not in wd]
         if missing:
             raise ValueError(f"{len(missing)} trainable parameters belong to no reference parameter group")
-        self.bufs = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.bufs = [torch.zeros_like(p) for p in self.params]      # same strides as the parameter (NCHW or channels_last)
         self._wd = [wd[id(p)] for p in self.params]
         self._steps = 0
         self._table = None
@@ -71,8 +71,15 @@ class FusedSgdEma:
         names = {id(v): k for k, v in self.model.state_dict(keep_vars=True).items()}
         seen = set()
         for p, buf, w in zip(self.params, self.bufs, self._wd):
-            assert p.dtype == torch.float32 and p.is_contiguous() and p.grad is not None and p.grad.is_contiguous()
             e = ema_sd.get(names.get(id(p)))
+            # the kernel walks every tensor as flat memory: dense storage, and one element order for the parameter, its
+            # gradient, its momentum buffer and its EMA copy (all NCHW, or all channels_last)
+            assert p.dtype == torch.float32 and p.grad is not None
+            assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameter storage is not dense"
+            order = [st for st, n in zip(p.stride(), p.shape) if n > 1]          # strides of size-1 dims carry no order
+            for other in (p.grad, buf, e):
+                assert other is None or [st for st, n in zip(other.stride(), other.shape) if n > 1] == order, \
+                    "parameter / gradient / momentum / EMA memory formats differ"
             rows.append((p.data_ptr(), p.grad.data_ptr(), buf.data_ptr(), 0 if e is None else e.data_ptr(), p.numel(),
                          int(np.float32(w).view(np.int32)) & 0xffffffff))
             seen.add(names.get(id(p)))

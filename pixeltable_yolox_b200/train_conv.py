@@ -1,0 +1,114 @@
+"""Dense convolution of the training step on the tensor cores, forward and backward.
+
+Replaces what torch autograd dispatches to cuDNN for `BaseConv.conv` (yolox/models/network_blocks.py:27-52) and the
+prediction convs (yolox/models/yolo_head.py:94-120) inside `Trainer.train_one_iter` (yolox/core/trainer.py:96-129):
+
+  forward  y  = conv(x, W) (+ bias)     csrc/yx_conv_tc.cu, the inference implicit GEMM with unfolded weights, no activation
+  dgrad    dx = conv(dy, rot180(W)^T)   the same kernel (stride 2: on the zero-stuffed dy, csrc/yx_wgrad_tc.cu: dilate2)
+  wgrad    dW = sum_p dy[p] (x) x[p+t]  csrc/yx_wgrad_tc.cu (tcgen05, both operands MN-major straight from NHWC)
+
+Activations stay 16-bit channels_last (NHWC) between layers, which is the layout every kernel of this package uses; the
+fp32 master weights are packed to 16-bit operands once per step and per layer (one launch for the forward and the dgrad
+operand). Numerics match torch.autocast: 16-bit operands, fp32 accumulation, fp32 weight gradients.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import YX_ACT_NONE
+
+_zero_bias = {}
+
+
+def _zeros(dev: torch.device, n: int) -> torch.Tensor:
+    t = _zero_bias.get((dev, n))
+    if t is None:
+        t = _zero_bias[(dev, n)] = torch.zeros(n, dtype=torch.float32, device=dev)
+    return t
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def _pad_channels(t: torch.Tensor, c_pad: int) -> torch.Tensor:
+    """[B, C, H, W] -> dense channels_last [B, c_pad, H, W], extra channels zero."""
+    if t.shape[1] == c_pad:
+        return t.contiguous(memory_format=torch.channels_last)
+    out = torch.empty((t.shape[0], c_pad, t.shape[2], t.shape[3]), dtype=t.dtype, device=t.device,
+                      memory_format=torch.channels_last)
+    out[:, :t.shape[1]] = t
+    out[:, t.shape[1]:] = 0
+    return out
+
+
+def usable(x: torch.Tensor, conv: torch.nn.Conv2d) -> Optional[torch.dtype]:
+    """The 16-bit compute dtype when this conv can run on the tcgen05 training path, else None (torch / cuDNN runs it):
+    CUDA, dense (groups == 1) 1x1 stride 1 or 3x3 stride 1 / 2 with `same` padding, under 16-bit autocast or on 16-bit input."""
+    if os.environ.get("YX_TRAIN_CONV", "1") == "0" or not x.is_cuda or x.dim() != 4:
+        return None
+    k, s = conv.kernel_size, conv.stride
+    if conv.groups != 1 or k[0] != k[1] or s[0] != s[1] or conv.dilation != (1, 1) or conv.padding_mode != "zeros":
+        return None
+    if (k[0], s[0]) not in ((1, 1), (3, 1), (3, 2)) or conv.padding != ((k[0] - 1) // 2,) * 2:
+        return None
+    if conv.weight.dtype != torch.float32:
+        return None
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+    else:
+        dt = x.dtype
+    return dt if dt in (torch.bfloat16, torch.float16) else None
+
+
+class _ConvTc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, dtype):
+        o, i, k, _ = weight.shape
+        o_pad, i_pad = _pad16(o), _pad16(i)
+        B, _, H, W = x.shape
+        pad = (k - 1) // 2
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        xh = _pad_channels(x.detach().to(dtype), i_pad)
+        wf, wd = ops.pack_train_weights(weight.detach(), dtype, o_pad, i_pad, want_dgrad=ctx.needs_input_grad[0])
+        if bias is None:
+            b = _zeros(x.device, o_pad)
+        elif o_pad == o:
+            b = bias.detach().float().contiguous()
+        else:
+            b = torch.zeros(o_pad, dtype=torch.float32, device=x.device)
+            b[:o] = bias.detach()
+        y = torch.empty((B, o_pad, OH, OW), dtype=dtype, device=x.device, memory_format=torch.channels_last)
+        ops.conv_bn_act(ops._nhwc(xh), wf, b, ops._nhwc(y), k, stride, YX_ACT_NONE)
+        ctx.save_for_backward(xh, wd, weight)
+        ctx.geom = (o, i, k, stride, o_pad, i_pad, H, W, x.dtype, bias is not None)
+        return y if o_pad == o else y[:, :o]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, wd, weight = ctx.saved_tensors
+        o, i, k, stride, o_pad, i_pad, H, W, x_dtype, has_bias = ctx.geom
+        dyh = _pad_channels(dy.to(xh.dtype), o_pad)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
+        if ctx.needs_input_grad[0]:
+            src = dyh if stride == 1 else ops.dilate2(dyh, H, W)
+            dxp = torch.empty((xh.shape[0], i_pad, H, W), dtype=xh.dtype, device=xh.device, memory_format=torch.channels_last)
+            ops.conv_bn_act(ops._nhwc(src), wd, _zeros(xh.device, i_pad), ops._nhwc(dxp), k, 1, YX_ACT_NONE)
+            dx = (dxp if i_pad == i else dxp[:, :i]).to(x_dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum((0, 2, 3))
+        return dx, dw, db, None, None
+
+
+def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """`conv(x)` in the training step: tcgen05 forward / dgrad / wgrad when `usable`, else the module's own forward."""
+    dt = usable(x, conv)
+    if dt is None:
+        return conv(x)
+    return _ConvTc.apply(x, conv.weight, conv.bias, conv.stride[0], dt)

@@ -162,6 +162,8 @@ class YoloxHead(_B200Block):
     def _torch_raw_outputs(self, xin):
         """Prediction-conv outputs per level through torch ops (used by the training branch and by
         synthetic.randomize_and_calibrate; never by the eval hot path)."""
+        from .train_conv import conv2d
+
         outs = []
         for k, x in enumerate(xin):
             x = self.stems[k]._train_forward(x)
@@ -170,7 +172,7 @@ class YoloxHead(_B200Block):
                 cls_feat = blk._train_forward(cls_feat)
             for blk in self.reg_convs[k]:
                 reg_feat = blk._train_forward(reg_feat)
-            outs.append((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)))
+            outs.append((conv2d(reg_feat, self.reg_preds[k]), conv2d(reg_feat, self.obj_preds[k]), conv2d(cls_feat, self.cls_preds[k])))
         return outs
 
     # ------------------------------------------------------------------ forward

@@ -1,0 +1,171 @@
+"""-m gpu: the training conv stack on the tensor cores: forward / dgrad through the implicit-GEMM conv kernel
+with per-step packed weights, wgrad through the MN-major tcgen05 kernel, against torch's fp32 convolution gradients on the
+same 16-bit-rounded operands (so the comparison isolates the kernels' arithmetic: 16-bit products, fp32 accumulation)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import pixeltable_yolox_b200 as yx  # noqa: E402
+from pixeltable_yolox_b200 import ops, train_conv  # noqa: E402
+from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
+
+# (batch, in_c, out_c, H, W, ksize, stride)
+WGRAD_SHAPES = [
+    (2, 16, 32, 20, 20, 3, 1),       # 32-byte channel rows (SW32) for x, 64-byte rows for dy
+    (2, 64, 128, 24, 24, 3, 2),      # stride 2 (TMA elementStrides), nine slices of 64 columns -> two groups
+    (1, 128, 128, 40, 40, 3, 1),     # 3 groups x 3 slices of 128 columns, 128-byte rows both sides
+    (2, 256, 96, 12, 12, 1, 1),      # out_c = 96: 32-channel boxes, the fourth M block stays zero
+    (2, 512, 256, 10, 10, 1, 1),     # two M tiles, four input-channel tiles
+    (3, 32, 64, 33, 29, 3, 2),       # odd sizes: overhanging pixel tiles (zero fill on both operands)
+    (2, 16, 16, 7, 5, 3, 1),         # map smaller than one pixel tile
+    (2, 80, 48, 16, 16, 3, 1),       # channel counts that are multiples of 16 only
+    (8, 128, 256, 20, 20, 3, 1),     # pixel dimension split over many CTAs
+    (2, 1024, 512, 5, 5, 1, 1),      # SPP conv2 shape: eight input-channel tiles, four M tiles
+    (2, 32, 64, 80, 80, 3, 2),       # dark2 stride-2 conv
+]
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_conv_wgrad_matches_torch_fp32(cuda, shape, dtype):
+    B, ci, co, H, W, k, s = shape
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    pad = (k - 1) // 2
+    OH, OW = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    x = _cl((torch.randn(B, ci, H, W, generator=g) * 0.7 + 0.1).to(dtype).to(cuda))
+    dy = _cl((torch.randn(B, co, OH, OW, generator=g) * 0.5).to(dtype).to(cuda))
+    want = torch.nn.grad.conv2d_weight(x.float(), (co, ci, k, k), dy.float(), stride=s, padding=pad)
+    scale = float(want.abs().max())
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        like = torch.empty(co, ci, k, k, device=cuda).contiguous(memory_format=fmt)
+        got = ops.conv_wgrad(x, dy, like, k, s)
+        assert got.shape == want.shape and got.stride() == like.stride() and got.dtype == torch.float32
+        # fp32 accumulation in a different order than torch's: ~1e-6 relative to the largest sums
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_wgrad_is_deterministic(cuda):
+    g = torch.Generator().manual_seed(3)
+    x = _cl(torch.randn(4, 128, 40, 40, generator=g).bfloat16().to(cuda))
+    dy = _cl(torch.randn(4, 128, 40, 40, generator=g).bfloat16().to(cuda))
+    like = torch.empty(128, 128, 3, 3, device=cuda)
+    a = ops.conv_wgrad(x, dy, like, 3, 1)
+    b = ops.conv_wgrad(x, dy, like, 3, 1)
+    assert torch.equal(a, b)
+
+
+def test_dilate2_exact(cuda):
+    dy = _cl(torch.randn(2, 16, 5, 7).bfloat16().to(cuda))
+    for zh, zw in ((10, 14), (9, 13)):
+        z = ops.dilate2(dy, zh, zw)
+        want = torch.zeros(2, 16, zh, zw, dtype=torch.bfloat16, device=cuda)
+        want[:, :, ::2, ::2] = dy
+        assert torch.equal(z, want)
+
+
+# (batch, in_c, out_c, H, W, ksize, stride, bias)
+CONV_CASES = [
+    (2, 64, 64, 20, 20, 3, 1, False),
+    (2, 32, 64, 40, 40, 3, 2, False),
+    (2, 128, 64, 16, 16, 1, 1, False),
+    (2, 12, 32, 32, 32, 3, 1, False),     # stem: 12 input channels, padded to 16
+    (2, 64, 4, 20, 20, 1, 1, True),       # reg_preds
+    (2, 64, 1, 20, 20, 1, 1, True),       # obj_preds
+    (2, 64, 80, 20, 20, 1, 1, True),      # cls_preds
+    (2, 256, 512, 10, 10, 3, 2, False),
+    (1, 64, 64, 37, 29, 3, 2, False),     # odd input size
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_train_conv_forward_backward_matches_torch(cuda, case, dtype, channels_last):
+    B, ci, co, H, W, k, s, bias = case
+    torch.manual_seed(ci * 7 + co)
+    conv = torch.nn.Conv2d(ci, co, k, s, (k - 1) // 2, bias=bias).to(cuda)
+    if channels_last:
+        conv = conv.to(memory_format=torch.channels_last)
+    x = (torch.randn(B, ci, H, W, device=cuda) * 0.8).to(dtype)
+    if channels_last:
+        x = _cl(x)
+    x.requires_grad_(True)
+    assert train_conv.usable(x, conv) == dtype
+    y = train_conv.conv2d(x, conv)
+    go = (torch.randn(y.shape, device=cuda) * 0.3).to(dtype)
+    y.backward(go)
+    # reference: fp32 convolution of the same rounded operands
+    xr = x.detach().float().requires_grad_(True)
+    wr = conv.weight.detach().to(dtype).float().requires_grad_(True)
+    br = conv.bias.detach().clone().requires_grad_(True) if bias else None
+    yr = F.conv2d(xr, wr, br, s, (k - 1) // 2)
+    yr.backward(go.float())
+    tol = dict(rtol=1.6e-2, atol=1.6e-2) if dtype == torch.bfloat16 else dict(rtol=2e-3, atol=2e-3)
+    assert y.dtype == dtype and y.shape == yr.shape and x.grad.dtype == dtype
+    torch.testing.assert_close(y.float(), yr, **tol)
+    torch.testing.assert_close(x.grad.float(), xr.grad, **tol)
+    # the weight gradient sees dy and x exactly as the reference does; the reference's dW is w.r.t. the rounded weight,
+    # which is the same linear map
+    assert conv.weight.grad.dtype == torch.float32 and conv.weight.grad.stride() == conv.weight.stride()
+    torch.testing.assert_close(conv.weight.grad, wr.grad, rtol=1e-4, atol=2e-5 * float(wr.grad.abs().max()))
+    if bias:
+        torch.testing.assert_close(conv.bias.grad, br.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_train_conv_under_autocast_matches_cudnn_path(cuda, monkeypatch):
+    """One BaseConv (conv + training BatchNorm + SiLU) under bf16 autocast: tcgen05 training path vs torch's conv."""
+    from pixeltable_yolox_b200.network_blocks import BaseConv
+
+    torch.manual_seed(1)
+    blk = BaseConv(64, 128, 3, 2).to(cuda).train()
+    x = torch.randn(4, 64, 40, 40, device=cuda)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YX_TRAIN_CONV", flag)
+        blk.zero_grad()
+        blk.bn.running_mean.zero_(); blk.bn.running_var.fill_(1.0)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = blk(xi)
+        y.float().square().mean().backward()
+        outs.append((y.float(), xi.grad.clone(), blk.conv.weight.grad.clone(), blk.bn.weight.grad.clone(), blk.bn.running_var.clone()))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-2 * float(b.abs().max()))
+
+
+def test_training_step_tcgen05_convs_track_the_fp32_step_like_cudnn_does(cuda, monkeypatch):
+    """Whole training forward + backward of a small YOLOX: bf16 autocast with the conv stack on our kernels and on torch's
+    convs, each against the fp32 step. On random weights SimOTA's costs are near-tied, so 16-bit rounding flips individual
+    assignments and the two 16-bit gradients differ from each other as much as each differs from fp32: the gate is that ours
+    is as close to the fp32 loss / gradient as the torch 16-bit step is (its distance is the ceiling), not element-wise."""
+    torch.manual_seed(0)
+    cfg = yx.YoloxConfig("trainconv", depth=0.33, width=0.25)
+    m = cfg.get_model().to(cuda).train()
+    x = torch.from_numpy(syn.images(2, 128, 128, seed=3)).to(cuda)
+    lab = torch.from_numpy(syn.labels(2, max_gt=8, seed=5, size=128.0, counts=[3, 5])).to(cuda)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    res = {}
+    for name, flag, amp in (("fp32", "0", False), ("ours", "1", True), ("torch16", "0", True)):
+        monkeypatch.setenv("YX_TRAIN_CONV", flag)
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out = m(x, lab)
+        out["total_loss"].backward()
+        res[name] = (float(out["total_loss"].detach()), torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+
+    def cos(a, b):
+        return float(torch.dot(a, b) / (a.norm() * b.norm()))
+
+    l32, g32 = res["fp32"]
+    c_ours, c_t16 = cos(res["ours"][1], g32), cos(res["torch16"][1], g32)
+    e_ours, e_t16 = abs(res["ours"][0] - l32) / abs(l32), abs(res["torch16"][0] - l32) / abs(l32)
+    print(f"loss fp32 {l32:.4f} ours {res['ours'][0]:.4f} torch16 {res['torch16'][0]:.4f}; gradient cosine vs fp32: ours {c_ours:.4f} torch16 {c_t16:.4f}")
+    assert e_ours <= max(2.0 * e_t16, 0.02), (e_ours, e_t16)
+    assert c_ours >= c_t16 - 0.03, (c_ours, c_t16)

@@ -215,8 +215,9 @@ def test_training_step_as_cuda_graph_matches_eager(cuda):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("act", ["silu", "relu", "lrelu"])
-@pytest.mark.parametrize("shape", [(3, 48, 20, 20), (2, 32, 37, 29), (8, 16, 80, 80)])
-def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape):
+@pytest.mark.parametrize("shape", [(3, 48, 20, 20), (2, 32, 37, 29), (8, 16, 80, 80), (2, 1280, 5, 7)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape, channels_last):
     """Training-mode BatchNorm2d + activation (one fused pass each way) against nn.BatchNorm2d + the activation module in
     torch: output, running statistics, and the gradients w.r.t. input, gamma and beta."""
     from pixeltable_yolox_b200.network_blocks import _FusedBnAct, get_activation
@@ -224,6 +225,8 @@ def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape):
     g = torch.Generator().manual_seed(4)
     N, Cc, H, W = shape
     x0 = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(dtype).to(cuda)
+    if channels_last:
+        x0 = x0.contiguous(memory_format=torch.channels_last)
     bn = torch.nn.BatchNorm2d(Cc, eps=1e-3, momentum=0.03).to(cuda).train()
     with torch.no_grad():
         bn.weight.copy_(torch.rand(Cc, generator=g) + 0.5); bn.bias.copy_(torch.randn(Cc, generator=g) * 0.2)
@@ -239,7 +242,7 @@ def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape):
     yr = get_activation(act, inplace=False)(bn(xr))
     yr.backward(go.float())
     tol = dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
-    assert y.dtype == dtype
+    assert y.dtype == dtype and y.stride() == x0.stride() and x.grad.stride() == x0.stride()
     torch.testing.assert_close(y.float(), yr, **tol)
     torch.testing.assert_close(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rv, bn.running_var, rtol=1e-5, atol=1e-6)

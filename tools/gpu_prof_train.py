@@ -11,14 +11,20 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 from pixeltable_yolox_b200.optim import FusedSgdEma  # noqa: E402
 
-sys.argv = [sys.argv[0], "--train"]
+fmt = sys.argv[1] if len(sys.argv) > 1 else "channels_last"
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+sys.argv = [sys.argv[0], "--train", "--train-format", fmt]
 args = bench.parse()
 dev = torch.device("cuda", 0)
 cfg, model = bench.build_model(args, dev)
 model.train()
+if fmt == "channels_last":
+    model = model.to(memory_format=torch.channels_last)
 opt = FusedSgdEma(model, lr=1e-3)
 x, lab, _ = bench.train_batch(args, 0, 8)
 x, lab = x.to(dev), lab.to(dev)
+if fmt == "channels_last":
+    x = x.contiguous(memory_format=torch.channels_last)
 
 
 def step():
@@ -51,5 +57,5 @@ for r in rows:
     g[0] += r.device_time_total; g[1] += r.count
 for k, (t, n) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
     print(f"  {k:44s} {t / 3 / 1e3:7.2f} ms  {100 * t / tot:5.1f}%  {n // 3} launches")
-for r in sorted(rows, key=lambda r: -r.device_time_total)[:14]:
+for r in sorted(rows, key=lambda r: -r.device_time_total)[:top]:
     print(f"    {r.key[:90]:90s} {r.device_time_total / 3 / 1e3:7.3f} ms x{r.count // 3}")
