@@ -866,7 +866,7 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
 
         raw = copy.deepcopy(model.module).train()
         opt = FusedSgdEma(raw, lr=opt.lr, momentum=opt.momentum, weight_decay=5e-4, nesterov=opt.nesterov, ema=True,
-                          ema_decay=opt.ema_decay)
+                          ema_decay=opt.ema_decay, direct_grads=True)
     else:
         raw = model
 
@@ -895,15 +895,13 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
         opt.zero_grad()
         loss.backward()
         if world > 1:
-            grads = [q.grad for q in params]
-            flat = torch.cat([t.reshape(-1) for t in grads])
+            flat = opt.flat_grad                   # every .grad is a view into it: the all-reduce needs no flatten / scatter
         else:
             opt.step_captured()
     if world > 1:
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, capture_error_mode="thread_local"):
             flat.div_(world)
-            torch._foreach_copy_(grads, [v.view_as(t) for v, t in zip(flat.split([t.numel() for t in grads]), grads)])
             opt.step_captured()
 
     def replay():
@@ -967,7 +965,9 @@ def run_train(args, world, rank, dev):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
     from pixeltable_yolox_b200.optim import FusedSgdEma
 
-    opt = FusedSgdEma(model, lr=1e-3, momentum=0.9, weight_decay=5e-4, nesterov=True, ema=True, ema_decay=0.9998)
+    # one rank: no DDP wrapper, so the backward kernels may add weight gradients straight into one flat .grad buffer
+    opt = FusedSgdEma(model, lr=1e-3, momentum=0.9, weight_decay=5e-4, nesterov=True, ema=True, ema_decay=0.9998,
+                      direct_grads=(world == 1))
     xh, labh, counts = train_batch(args, rank, B)
     xh, labh = xh.pin_memory(), labh.pin_memory()
     x, lab = xh.to(dev), labh.to(dev)
@@ -989,8 +989,8 @@ def run_train(args, world, rank, dev):
                       "e2e_ms_per_step": gms_host, "e2e_images_per_second": world * B / (gms_host / 1e3), "e2e_loss_last_step": gloss_host,
                       "what": ("forward + SimOTA + losses + backward + SGD/EMA captured once with torch.cuda.graph and replayed"
                                if world == 1 else
-                               "two captured graphs (forward + SimOTA + losses + backward + gradient flatten | average + scatter + "
-                               "SGD/EMA) around one eager ncclAllReduce of the flattened gradients, on a copy of the module "
+                               "two captured graphs (forward + SimOTA + losses + backward | average + SGD/EMA) around one eager "
+                               "ncclAllReduce of the flat gradient buffer every .grad is a view of, on a copy of the module "
                                "without the DDP wrapper") + "; lr / EMA decay reach the captured optimizer launch via a device buffer"}
     except Exception as e:                            # noqa: BLE001
         import traceback
@@ -1076,9 +1076,11 @@ def run_train(args, world, rank, dev):
                        "memory_format": args.train_format,
                        "optimizer": "SGD momentum 0.9 nesterov, wd 5e-4 on conv weights (yolox/config.py:307-333) + ModelEMA update "
                                     "(yolox/utils/ema.py:46-58), both arms; ours: one fused launch (yx_sgd_ema_step)",
-                       "network_fwd_bwd": "convolutions: torch autograd / cuDNN (no dgrad / wgrad tcgen05 kernels yet); BatchNorm + "
-                                          "activation forward / backward: ours",
-                       "ours_in_step": "yx_bn_act_train_fwd/bwd (training-mode BatchNorm + SiLU of all 74 BaseConv), yx_head_train_decode "
+                       "network_fwd_bwd": ("convolutions: torch autograd / cuDNN (YX_TRAIN_CONV=0)" if os.environ.get("YX_TRAIN_CONV", "1") == "0" or amp_dtype is None
+                                           else "convolutions: ours -- forward and dgrad through the tcgen05 implicit-GEMM conv kernel with "
+                                                "per-step packed weights, wgrad through the MN-major tcgen05 kernel (yx_conv_wgrad); no cuDNN "
+                                                "call in the step") + "; BatchNorm + activation forward / backward, SPP pools: ours",
+                       "ours_in_step": "yx_conv_bn_act_fwd (forward + dgrad), yx_conv_wgrad, yx_pack_train_weights, yx_bn_act_train_fwd/bwd (training-mode BatchNorm + SiLU of all 74 BaseConv), yx_head_train_decode "
                                        "fwd/bwd (3 levels), yx_simota_assign (whole batch, one cluster launch, no host sync), "
                                        "yx_head_losses (losses and d/d(pred) in one pass), yx_sgd_ema_step",
                        "collective": (f"gradient all-reduce: torch DDP buckets (25 MB) -> ncclAllReduce over NVLink/NVSwitch, "

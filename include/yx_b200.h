@@ -338,19 +338,21 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
  *   bwd: dy = gradient w.r.t. y -> dx (dtype of x), dgamma, dbeta [C] fp32. x_hat and the pre-activation are recomputed
  *        from x and the saved statistics, nothing else is kept from the forward.
  *   channels_last != 0: x / y / dy / dx are [N*H*W][C] (torch.channels_last, C % 8 == 0), else [N][C][H*W].
+ *   acc_dgamma / acc_dbeta (may be NULL): fp32 [C] buffers the backward ALSO adds dgamma / dbeta to (the parameters' .grad).
+ *   num_batches_tracked (may be NULL): nn.BatchNorm2d's int64 call counter, incremented by the forward.
  *   act: YX_ACT_SILU / YX_ACT_RELU / YX_ACT_LRELU / YX_ACT_NONE.  workspace: yx_bn_act_workspace_bytes(N, C, H*W).
  * ------------------------------------------------------------------------------------------ */
 int64_t yx_bn_act_workspace_bytes(int32_t n, int32_t c, int32_t hw);
 int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t channels_last, int32_t n, int32_t c, int32_t hw,
                         const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                        int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
+                        int64_t* num_batches_tracked, int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
                         int64_t workspace_bytes, void* stream);
 int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t channels_last, int32_t n, int32_t c,
                         int32_t hw,
                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                        int32_t act, void* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
-                        void* stream);
+                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training conv stack on the tensor cores: what torch autograd / cuDNN computes for BaseConv.conv and the prediction
@@ -366,7 +368,8 @@ int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t ch
  *             dimension split over CTAs and reduced in a fixed order. dw: fp32, element (o, i, tap) at
  *             o*dw_stride_o + i*dw_stride_i + tap*dw_stride_tap (tap = 3*kh + kw), so NCHW-contiguous and channels_last
  *             weight gradients are both written in place; only o < out_c_real, i < in_c_real are written (x / dy carry
- *             channel counts padded to multiples of 16: in_c, out_c).
+ *             channel counts padded to multiples of 16: in_c, out_c). accumulate != 0: dw += (gradient accumulation straight
+ *             into the parameter's .grad, what autograd's AccumulateGrad would do with one more launch per parameter).
  *   yx_pack_train_weights: fp32 weight (same stride convention) -> w_fwd [o_pad][taps][i_pad] and
  *             w_dgrad [i_pad][taps][o_pad] in `dtype` (either may be NULL), zero padded.
  * x, dy: NHWC, 16-bit, per-pixel strides x_ld / dy_ld (multiples of 8), 16-byte aligned. ksize 1 | 3, stride 1 | 2.
@@ -376,10 +379,17 @@ int64_t yx_conv_wgrad_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w,
 int yx_conv_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, int32_t dtype, int32_t batch, int32_t in_h,
                   int32_t in_w, int32_t in_c, int32_t out_h, int32_t out_w, int32_t out_c, int32_t ksize, int32_t stride,
                   int32_t in_c_real, int32_t out_c_real, float* dw, int64_t dw_stride_o, int64_t dw_stride_i, int64_t dw_stride_tap,
-                  void* workspace, int64_t workspace_bytes, void* stream);
+                  int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, int64_t stride_tap, int32_t o, int32_t i, int32_t taps,
                           int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t dtype, void* stream);
 int yx_dilate2(const void* dy, void* z, int32_t batch, int32_t oh, int32_t ow, int32_t zh, int32_t zw, int32_t c, void* stream);
+
+/* Backward of the SPP pools (SPPBottleneck, network_blocks.py:120-142; forward = yx_spp_maxpool on the concat buffer):
+ * cat: NHWC buffer whose channels [0, c) hold the pools' input x (pixel stride ld); dout: NHWC gradient of the 4c-channel
+ * concat (pixel stride dout_ld); dx32: dense fp32 [B, h, w, c] that the CALLER pre-loads with dout[..., :c] (the identity
+ * segment); the gradient of every pooled value is added at the first maximum of its window (torch's tie rule). */
+int yx_spp_maxpool_bwd(const void* cat, int64_t ld, const void* dout, int64_t dout_ld, float* dx32, int32_t batch, int32_t h,
+                       int32_t w, int32_t c, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test-time preprocessing on the device (`preproc`, yolox/data/data_augment.py:140-156; YoloxProcessor.__call__,

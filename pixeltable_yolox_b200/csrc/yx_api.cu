@@ -63,18 +63,20 @@ int coco_rows_launch(const float* dets, const int* det_count, int batch, int max
                      int* category, long long* image_id, int* total, cudaStream_t s);
 long long bn_act_ws_bytes(int n, int c, int hw);
 int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta, float eps,
-                            float momentum, float* running_mean, float* running_var, int act, void* y, float* save_mean,
+                            float momentum, float* running_mean, float* running_var, long long* nbt, int act, void* y, float* save_mean,
                             float* save_invstd, void* ws, long long ws_bytes, cudaStream_t s);
 int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta,
                             const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
-                            void* ws, long long ws_bytes, cudaStream_t s);
+                            float* acc_dgamma, float* acc_dbeta, void* ws, long long ws_bytes, cudaStream_t s);
 long long wgrad_ws_bytes(int batch, int in_h, int in_w, int in_c, int out_h, int out_w, int out_c, int ksize, int stride);
 int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld, int dtype, int batch, int in_h, int in_w, int in_c,
                  int out_h, int out_w, int out_c, int ksize, int stride, int in_c_real, int out_c_real, float* dw, long long dw_so,
-                 long long dw_si, long long dw_st, void* ws, long long ws_bytes, cudaStream_t stream);
+                 long long dw_si, long long dw_st, int accumulate, void* ws, long long ws_bytes, cudaStream_t stream);
 int pack_train_weights_launch(const float* w, long long so, long long si, long long st, int o, int i, int taps, int o_pad, int i_pad,
                               void* wf, void* wd, int dtype, cudaStream_t stream);
 int dilate2_launch(const void* dy, void* z, int batch, int oh, int ow, int zh, int zw, int c, cudaStream_t stream);
+int spp_bwd_launch(const void* cat, long long ld, const void* dout, long long dld, float* dx32, int batch, int h, int w, int c,
+                   int dtype, cudaStream_t s);
 struct StemLaunch;
 StemLaunch* stem_alloc();
 void stem_free(StemLaunch*);
@@ -118,6 +120,15 @@ int num_sms() {
       cached = 148;
   }
   return cached;
+}
+
+bool train_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YX_TRAIN_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
 }
 
 bool pdl_enabled() {
@@ -427,21 +438,23 @@ int64_t yx_bn_act_workspace_bytes(int32_t n, int32_t c, int32_t hw) { return bn_
 
 int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t channels_last, int32_t n, int32_t c, int32_t hw, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                        int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
+                        int64_t* num_batches_tracked, int32_t act, void* y, float* save_mean, float* save_invstd, void* workspace,
                         int64_t workspace_bytes, void* stream) {
   int rc = require_device();
   if (rc) return rc;
-  return bn_act_train_fwd_launch(x, dtype, channels_last, n, c, hw, gamma, beta, eps, momentum, running_mean, running_var, act, y, save_mean,
+  return bn_act_train_fwd_launch(x, dtype, channels_last, n, c, hw, gamma, beta, eps, momentum, running_mean, running_var,
+                                 reinterpret_cast<long long*>(num_batches_tracked), act, y, save_mean,
                                  save_invstd, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t channels_last, int32_t n, int32_t c, int32_t hw,
                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                        int32_t act, void* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
-                        void* stream) {
+                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
   int rc = require_device();
   if (rc) return rc;
-  return bn_act_train_bwd_launch(x, dy, dtype, channels_last, n, c, hw, gamma, beta, save_mean, save_invstd, act, dx, dgamma, dbeta, workspace,
+  return bn_act_train_bwd_launch(x, dy, dtype, channels_last, n, c, hw, gamma, beta, save_mean, save_invstd, act, dx, dgamma, dbeta,
+                                 acc_dgamma, acc_dbeta, workspace,
                                  workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -454,11 +467,11 @@ int64_t yx_conv_wgrad_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w,
 int yx_conv_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, int32_t dtype, int32_t batch, int32_t in_h,
                   int32_t in_w, int32_t in_c, int32_t out_h, int32_t out_w, int32_t out_c, int32_t ksize, int32_t stride,
                   int32_t in_c_real, int32_t out_c_real, float* dw, int64_t dw_stride_o, int64_t dw_stride_i, int64_t dw_stride_tap,
-                  void* workspace, int64_t workspace_bytes, void* stream) {
+                  int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = require_device();
   if (rc) return rc;
   return wgrad_launch(x, x_ld, dy, dy_ld, dtype, batch, in_h, in_w, in_c, out_h, out_w, out_c, ksize, stride, in_c_real, out_c_real,
-                      dw, dw_stride_o, dw_stride_i, dw_stride_tap, workspace, workspace_bytes, (cudaStream_t)stream);
+                      dw, dw_stride_o, dw_stride_i, dw_stride_tap, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, int64_t stride_tap, int32_t o, int32_t i, int32_t taps,
@@ -466,6 +479,13 @@ int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, in
   int rc = require_device();
   if (rc) return rc;
   return pack_train_weights_launch(w, stride_o, stride_i, stride_tap, o, i, taps, o_pad, i_pad, w_fwd, w_dgrad, dtype, (cudaStream_t)stream);
+}
+
+int yx_spp_maxpool_bwd(const void* cat, int64_t ld, const void* dout, int64_t dout_ld, float* dx32, int32_t batch, int32_t h,
+                       int32_t w, int32_t c, int32_t dtype, void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return spp_bwd_launch(cat, ld, dout, dout_ld, dx32, batch, h, w, c, dtype, (cudaStream_t)stream);
 }
 
 int yx_dilate2(const void* dy, void* z, int32_t batch, int32_t oh, int32_t ow, int32_t zh, int32_t zw, int32_t c, void* stream) {

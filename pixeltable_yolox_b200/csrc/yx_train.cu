@@ -9,6 +9,7 @@
 //  2. sgd_ema: the reference's optimizer step and EMA update as ONE multi-tensor launch over every parameter and buffer:
 //     torch.optim.SGD(momentum, nesterov=True, per-group weight decay) as configured in yolox/config.py:307-333, and
 //     ModelEMA.update (yolox/utils/ema.py:46-58): ema = d * ema + (1 - d) * value for every floating-point state tensor.
+#include <stdlib.h>
 #include <string.h>
 
 #include "yx_common.cuh"
@@ -264,6 +265,8 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int C, int HW, int act, float* __restrict__ part) {
+  pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
+  pdl_launch_dependents();
   const int c = blockIdx.y, n = blockIdx.z, k = blockIdx.x;
   const long long base = ((long long)n * C + c) * HW;
   const int lo = k * kBnChunk, hi = min(HW, lo + kBnChunk);
@@ -302,16 +305,25 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
 // FWD: mean / invstd + running statistics; BWD: dbeta (sum dz), dgamma (sum dz * x_hat)
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int C, int S, double M, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ out0, float* __restrict__ out1, int bwd) {
+                                   float* __restrict__ out0, float* __restrict__ out1, int bwd, long long* __restrict__ nbt,
+                                   float* __restrict__ acc0, float* __restrict__ acc1) {
+  pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
+  pdl_launch_dependents();
   const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
+  if (nbt && c == 0 && lane == 0) *nbt += 1;           // nn.BatchNorm2d.num_batches_tracked
   const float2* p2 = reinterpret_cast<const float2*>(part) + (long long)c * S;
   double a = 0.0, b = 0.0;
   for (int s = lane; s < S; s += 32) { const float2 v = p2[s]; a += (double)v.x; b += (double)v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
   if (lane) return;
-  if (bwd) { out0[c] = (float)a; out1[c] = (float)b; return; }
+  if (bwd) {
+    out0[c] = (float)a; out1[c] = (float)b;
+    if (acc0) acc0[c] += (float)a;                       // gradient accumulation into the parameters' .grad (dbeta, dgamma)
+    if (acc1) acc1[c] += (float)b;
+    return;
+  }
   const double mean = a / M;
   double var = b / M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -330,6 +342,8 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dbeta,
                 const float* __restrict__ dgamma, float inv_m, int C, int HW, int act, T* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
+  pdl_launch_dependents();
   const int c = blockIdx.y, n = blockIdx.z, k = blockIdx.x;
   const long long base = ((long long)n * C + c) * HW;
   const int lo = k * kBnChunk, hi = min(HW, lo + kBnChunk);
@@ -360,42 +374,63 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* 
   }
 }
 
-// ---- channels-last variants: x is [M = N*H*W][C] with C contiguous (torch.channels_last, what cuDNN's bf16 kernels use
-// natively: with NCHW tensors 1.9 ms of a 8.7 ms step were cuDNN's own nchw<->nhwc conversion kernels). A thread owns 8
-// consecutive channels (one 16-byte load per row) and strides over the rows of its CTA's slab; the threads of a column are
-// reduced through shared memory. Requires C % 8 == 0.
-template <typename T, bool BWD>
+// ---- channels-last: x is [M = N*H*W][C] with C contiguous (torch.channels_last, the layout of every kernel of this package and
+// of cuDNN's 16-bit kernels: with NCHW tensors 1.9 ms of a 8.7 ms step were cuDNN's own nchw<->nhwc conversion kernels). A
+// thread owns 8 consecutive channels (one 16-byte load per row) and strides over the rows of its CTA's slab; the threads of a
+// column are reduced through shared memory. Requires C % 8 == 0.
+// (A single cooperative launch per direction -- statistics, grid barrier, finalize spread over the grid, grid barrier, apply from
+// L2 -- measured SLOWER than three launches: 16 vs 11 us on a 0.8 MB tensor, 81 vs 50 us on 52 MB; the sense-reversing barrier
+// with its fences costs more than the launch it saves. Kept out of the build.)
+__device__ __forceinline__ void bn_ld8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// partial sums of every channel over the CTA's row slab; U rows in flight per thread. part: [C][S] float2
+template <typename T, bool BWD, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int C, int rows_per_cta, int act,
                       float* __restrict__ part) {
+  pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
+  pdl_launch_dependents();
   __shared__ float red[kBnThreads][17];
+  const int S = gridDim.x;
   const int cg = C >> 3;
   const int tpr = cg < kBnThreads ? cg : kBnThreads;          // threads per row
   const int rpi = kBnThreads / tpr;                            // rows per iteration
   const int col = threadIdx.x % tpr, row0 = threadIdx.x / tpr;
   const long long m_lo = (long long)blockIdx.x * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
-  const int S = gridDim.x;
+  const bool active = row0 < rpi;
   for (int cc = col; cc < cg; cc += tpr) {
     float s0[8], s1[8], mu[8], is[8], a[8], b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s0[j] = 0.0f; s1[j] = 0.0f;
-      if (BWD) { mu[j] = mean[cc * 8 + j]; is[j] = invstd[cc * 8 + j]; a[j] = gamma[cc * 8 + j]; b[j] = beta[cc * 8 + j]; }
-    }
-    if (row0 < rpi) {
-      for (long long m = m_lo + row0; m < m_hi; m += rpi) {
-        float xv[8], dv[8];
-        Vec8<T>::load(x + m * C + cc * 8, xv);
-        if (BWD) Vec8<T>::load(dy + m * C + cc * 8, dv);
+    for (int j = 0; j < 8; ++j) { s0[j] = 0.0f; s1[j] = 0.0f; }
+    if (BWD) { bn_ld8(mean + cc * 8, mu); bn_ld8(invstd + cc * 8, is); bn_ld8(gamma + cc * 8, a); bn_ld8(beta + cc * 8, b); }
+    if (active) {
+      for (long long m = m_lo + row0; m < m_hi; m += (long long)U * rpi) {
+        float xv[U][8], dv[U][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (BWD) {
-            const float xh = (xv[j] - mu[j]) * is[j];
-            const float dz = dv[j] * bn_act_grad(fmaf(xh, a[j], b[j]), act);
-            s0[j] += dz; s1[j] = fmaf(dz, xh, s1[j]);
-          } else {
-            s0[j] += xv[j]; s1[j] = fmaf(xv[j], xv[j], s1[j]);
+        for (int u = 0; u < U; ++u) {
+          const long long mm = m + (long long)u * rpi;
+          if (mm < m_hi) {
+            Vec8<T>::load(x + mm * C + cc * 8, xv[u]);
+            if (BWD) Vec8<T>::load(dy + mm * C + cc * 8, dv[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (m + (long long)u * rpi < m_hi) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (BWD) {
+                const float xh = (xv[u][j] - mu[j]) * is[j];
+                const float dz = dv[u][j] * bn_act_grad(fmaf(xh, a[j], b[j]), act);
+                s0[j] += dz; s1[j] = fmaf(dz, xh, s1[j]);
+              } else {
+                s0[j] += xv[u][j]; s1[j] = fmaf(xv[u][j], xv[u][j], s1[j]);
+              }
+            }
           }
         }
       }
@@ -404,24 +439,25 @@ bn_reduce_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const f
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s0[j]; red[threadIdx.x][8 + j] = s1[j]; }
     __syncthreads();
-    // the tpr threads of row 0 own one column each; each sums its column over the rpi row-threads
-    if (row0 == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t0 = 0.0f, t1 = 0.0f;
-        for (int r = 0; r < rpi; ++r) { t0 += red[r * tpr + col][j]; t1 += red[r * tpr + col][8 + j]; }
-        const long long pidx = ((long long)(cc * 8 + j) * S + blockIdx.x) * 2;
-        part[pidx] = t0; part[pidx + 1] = t1;
-      }
+    // column sums: thread t < 16 * tpr... every (column, value) pair gets its own thread when there are enough
+    for (int t = threadIdx.x; t < tpr * 16; t += kBnThreads) {
+      const int cl = t >> 4, j = t & 15;
+      float acc = 0.0f;
+      for (int r = 0; r < rpi; ++r) acc += red[r * tpr + cl][j];
+      // j < 8: sum 0 of channel (cc0 + cl) * 8 + j; j >= 8: sum 1 of channel ... + j - 8, where cc0 = cc - col
+      part[((long long)((cc - col + cl) * 8 + (j & 7)) * S + blockIdx.x) * 2 + (j >> 3)] = acc;
     }
   }
 }
 
-template <typename T, bool BWD>
+// FWD: y = act(x_hat * gamma + beta).  BWD: dx = gamma * invstd * (dz - dbeta / M - x_hat * dgamma / M)
+template <typename T, bool BWD, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dbeta,
                      const float* __restrict__ dgamma, float inv_m, long long M, int C, int rows_per_cta, int act, T* __restrict__ out) {
+  pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
+  pdl_launch_dependents();
   const int cg = C >> 3;
   const int tpr = cg < kBnThreads ? cg : kBnThreads;
   const int rpi = kBnThreads / tpr;
@@ -430,32 +466,46 @@ bn_apply_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const fl
   if (row0 >= rpi) return;
   for (int cc = col; cc < cg; cc += tpr) {
     float mu[8], is[8], g[8], b[8], k0[8], k1[8];
+    bn_ld8(mean + cc * 8, mu); bn_ld8(invstd + cc * 8, is); bn_ld8(gamma + cc * 8, g); bn_ld8(beta + cc * 8, b);
+    if (BWD) {
+      bn_ld8(dbeta + cc * 8, k0); bn_ld8(dgamma + cc * 8, k1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cc * 8 + j;
-      mu[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma[c]; b[j] = beta[c];
-      if (BWD) { k0[j] = dbeta[c] * inv_m; k1[j] = dgamma[c] * inv_m; }
+      for (int j = 0; j < 8; ++j) { k0[j] *= inv_m; k1[j] *= inv_m; }
     }
-    for (long long m = m_lo + row0; m < m_hi; m += rpi) {
-      float xv[8], dv[8], r[8];
-      Vec8<T>::load(x + m * C + cc * 8, xv);
-      if (BWD) Vec8<T>::load(dy + m * C + cc * 8, dv);
+    for (long long m = m_lo + row0; m < m_hi; m += (long long)U * rpi) {
+      float xv[U][8], dv[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (xv[j] - mu[j]) * is[j];
-        const float z = fmaf(xh, g[j], b[j]);
-        if (!BWD) r[j] = bn_act(z, act);
-        else r[j] = g[j] * is[j] * (dv[j] * bn_act_grad(z, act) - k0[j] - xh * k1[j]);
+      for (int u = 0; u < U; ++u) {
+        const long long mm = m + (long long)u * rpi;
+        if (mm < m_hi) {
+          Vec8<T>::load(x + mm * C + cc * 8, xv[u]);
+          if (BWD) Vec8<T>::load(dy + mm * C + cc * 8, dv[u]);
+        }
       }
-      Vec8<T>::store(out + m * C + cc * 8, r);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long mm = m + (long long)u * rpi;
+        if (mm < m_hi) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[u][j] - mu[j]) * is[j];
+            const float z = fmaf(xh, g[j], b[j]);
+            if (!BWD) r[j] = bn_act(z, act);
+            else r[j] = g[j] * is[j] * (dv[u][j] * bn_act_grad(z, act) - k0[j] - xh * k1[j]);
+          }
+          Vec8<T>::store(out + mm * C + cc * 8, r);
+        }
+      }
     }
   }
 }
 
-// row slabs of the channels-last kernels: enough CTAs for four waves, at least 32 rows each
-static int bn_nhwc_slabs(long long M, int* rows_per_cta) {
-  long long s = (M + 31) / 32;
-  const long long cap = 4LL * num_sms();
+// row slabs of the channels-last kernels: at least `min_rows` rows per CTA, at most `waves` CTAs per SM
+static int bn_nhwc_slabs(long long M, int min_rows, int waves, int* rows_per_cta) {
+  long long s = (M + min_rows - 1) / min_rows;
+  long long cap = (long long)waves * num_sms();
+  if (cap > 1024) cap = 1024;                           // bn_act_ws_bytes reserves 1024 slabs per channel
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   *rows_per_cta = (int)((M + s - 1) / s);
@@ -466,7 +516,7 @@ long long bn_act_ws_bytes(int n, int c, int hw) {
   if (n <= 0 || c <= 0 || hw <= 0) return 256;
   const long long chunks = (hw + kBnChunk - 1) / kBnChunk;
   long long parts = (long long)n * chunks;
-  const long long nhwc_parts = 4LL * 256;                    // bn_nhwc_slabs never exceeds 4 x the SM count (<= 256 SMs)
+  const long long nhwc_parts = 1024;                         // the fused channels_last kernel never uses more CTAs
   if (parts < nhwc_parts) parts = nhwc_parts;
   return (((long long)c * parts * 2 * 4) + 255) & ~255LL;
 }
@@ -479,7 +529,7 @@ static int bn_check(int dtype, int n, int c, int hw, int act) {
 }
 
 int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta, float eps,
-                            float momentum, float* running_mean, float* running_var, int act, void* y, float* save_mean,
+                            float momentum, float* running_mean, float* running_var, long long* nbt, int act, void* y, float* save_mean,
                             float* save_invstd, void* ws, long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, YX_ERR_INVALID_ARG, "bn_act_fwd: null pointer");
   int rc = bn_check(dtype, n, c, hw, act);
@@ -491,13 +541,13 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
     YX_REQUIRE(c % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, YX_ERR_INVALID_ARG,
                "bn_act_fwd(channels_last): C %% 8 == 0 and 16-byte aligned tensors required");
     const long long M = (long long)n * hw;
-    int rows = 0;
-    const int S = bn_nhwc_slabs(M, &rows);
-#define YX_GO(T) bn_reduce_nhwc_kernel<T, false><<<S, kBnThreads, 0, s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, M, c, rows, act, part)
+    int rows = 0, rows2 = 0;
+    const int S = bn_nhwc_slabs(M, 64, 4, &rows), S2 = bn_nhwc_slabs(M, 32, 6, &rows2);
+#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, false, 4>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, M, c, rows, act, part)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
-    bn_finalize_kernel<<<(c + 3) / 4, 128, 0, s>>>(part, c, S, (double)M, eps, momentum, running_mean, running_var, save_mean, save_invstd, 0);
-#define YX_GO(T) bn_apply_nhwc_kernel<T, false><<<S, kBnThreads, 0, s>>>((const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, M, c, rows, act, (T*)y)
+    launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, S, (double)M, eps, momentum, running_mean, running_var, save_mean, save_invstd, 0, nbt, (float*)nullptr, (float*)nullptr);
+#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, false, 4>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, M, c, rows2, act, (T*)y)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     YX_CUDA(cudaGetLastError());
@@ -505,12 +555,12 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
   }
   const int chunks = (hw + kBnChunk - 1) / kBnChunk;
   const dim3 grid((unsigned)chunks, (unsigned)c, (unsigned)n);
-#define YX_GO(T) bn_reduce_kernel<T, false><<<grid, kBnThreads, 0, s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, c, hw, act, part)
+#define YX_GO(T) launch_pdl(bn_reduce_kernel<T, false>, dim3(grid), dim3(kBnThreads), 0, s, (const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, c, hw, act, part)
   if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
-  bn_finalize_kernel<<<(c + 3) / 4, 128, 0, s>>>(part, c, n * chunks, (double)n * hw, eps, momentum, running_mean, running_var,
-                                                     save_mean, save_invstd, 0);
-#define YX_GO(T) bn_apply_kernel<T, false><<<grid, kBnThreads, 0, s>>>((const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, c, hw, act, (T*)y)
+  launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, n * chunks, (double)n * hw, eps, momentum, running_mean, running_var,
+                                                     save_mean, save_invstd, 0, nbt, (float*)nullptr, (float*)nullptr);
+#define YX_GO(T) launch_pdl(bn_apply_kernel<T, false>, dim3(grid), dim3(kBnThreads), 0, s, (const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, c, hw, act, (T*)y)
   if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
   YX_CUDA(cudaGetLastError());
@@ -519,7 +569,7 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
 
 int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta,
                             const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
-                            void* ws, long long ws_bytes, cudaStream_t s) {
+                            float* acc_dgamma, float* acc_dbeta, void* ws, long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(x && dy && gamma && beta && save_mean && save_invstd && dx && dgamma && dbeta && ws, YX_ERR_INVALID_ARG, "bn_act_bwd: null pointer");
   int rc = bn_check(dtype, n, c, hw, act);
   if (rc) return rc;
@@ -530,14 +580,14 @@ int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, 
     YX_REQUIRE(c % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, YX_ERR_INVALID_ARG,
                "bn_act_bwd(channels_last): C %% 8 == 0 and 16-byte aligned tensors required");
     const long long M = (long long)n * hw;
-    int rows = 0;
-    const int S = bn_nhwc_slabs(M, &rows);
-#define YX_GO(T) bn_reduce_nhwc_kernel<T, true><<<S, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, M, c, rows, act, part)
+    int rows = 0, rows2 = 0;
+    const int S = bn_nhwc_slabs(M, 64, 4, &rows), S2 = bn_nhwc_slabs(M, 32, 6, &rows2);
+#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, true, 2>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, M, c, rows, act, part)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
-    bn_finalize_kernel<<<(c + 3) / 4, 128, 0, s>>>(part, c, S, (double)M, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1);
+    launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, S, (double)M, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1, (long long*)nullptr, acc_dbeta, acc_dgamma);
     const float inv_m = (float)(1.0 / (double)M);
-#define YX_GO(T) bn_apply_nhwc_kernel<T, true><<<S, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, M, c, rows, act, (T*)dx)
+#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, true, 2>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, M, c, rows2, act, (T*)dx)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     YX_CUDA(cudaGetLastError());
@@ -545,14 +595,85 @@ int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, 
   }
   const int chunks = (hw + kBnChunk - 1) / kBnChunk;
   const dim3 grid((unsigned)chunks, (unsigned)c, (unsigned)n);
-#define YX_GO(T) bn_reduce_kernel<T, true><<<grid, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, c, hw, act, part)
+#define YX_GO(T) launch_pdl(bn_reduce_kernel<T, true>, dim3(grid), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, c, hw, act, part)
   if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
-  bn_finalize_kernel<<<(c + 3) / 4, 128, 0, s>>>(part, c, n * chunks, (double)n * hw, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1);
+  launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, n * chunks, (double)n * hw, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1, (long long*)nullptr, acc_dbeta, acc_dgamma);
   const float inv_m = (float)(1.0 / ((double)n * hw));
-#define YX_GO(T) bn_apply_kernel<T, true><<<grid, kBnThreads, 0, s>>>((const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, c, hw, act, (T*)dx)
+#define YX_GO(T) launch_pdl(bn_apply_kernel<T, true>, dim3(grid), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, c, hw, act, (T*)dx)
   if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
+  YX_CUDA(cudaGetLastError());
+  return YX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// SPP max pools, backward (SPPBottleneck, network_blocks.py:120-142: cat[x, m5(x), m9(x), m13(x)]): the gradient of every
+// pooled value goes to the FIRST maximum of its window in row-major order (torch's max_pool2d: `val > max` while scanning).
+// One thread per (pixel, 8 channels) scans the 13x13 window once and tracks the first maximum of the three nested windows;
+// the three gradients are added to dx32 (fp32, pre-loaded with the gradient of the identity segment) with atomics.
+//   cat  : NHWC buffer whose channels [0, c) hold x (pixel stride ld)      dout : NHWC gradient of the 4c-channel cat
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void spp_bwd_kernel(const T* __restrict__ cat, long long ld, const T* __restrict__ dout, long long dld,
+                               float* __restrict__ dx32, int batch, int h, int w, int c) {
+  const int c8 = c >> 3;
+  const long long total = (long long)batch * h * w * c8;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(e % c8);
+    long long r = e / c8;
+    const int x0 = (int)(r % w); r /= w;
+    const int y0 = (int)(r % h);
+    const int b = (int)(r / h);
+    float best[3][8];
+    int arg[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[k][j] = -INFINITY; arg[k][j] = -1; }
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = y0 + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int xx = x0 + dx;
+        if (xx < 0 || xx >= w) continue;
+        float v[8];
+        Vec8<T>::load(cat + (((long long)b * h + yy) * w + xx) * ld + cc * 8, v);
+        const int pos = yy * w + xx;
+        const int rad = max(abs(dy), abs(dx));             // inside the 5x5 / 9x9 / 13x13 window when rad <= 2 / 4 / 6
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (rad <= 2 * k + 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (v[j] > best[k][j] || arg[k][j] < 0) { best[k][j] = v[j]; arg[k][j] = pos; }
+          }
+        }
+      }
+    }
+    const long long pix = ((long long)b * h + y0) * w + x0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float g[8];
+      Vec8<T>::load(dout + pix * dld + (long long)(k + 1) * c + cc * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (g[j] != 0.0f) atomicAdd(dx32 + ((long long)b * h * w + arg[k][j]) * c + cc * 8 + j, g[j]);
+    }
+  }
+}
+
+int spp_bwd_launch(const void* cat, long long ld, const void* dout, long long dld, float* dx32, int batch, int h, int w, int c,
+                   int dtype, cudaStream_t s) {
+  YX_REQUIRE(cat && dout && dx32, YX_ERR_INVALID_ARG, "spp_bwd: null pointer");
+  YX_REQUIRE(c % 8 == 0 && ld >= c && dld >= 4LL * c && ld % 8 == 0 && dld % 8 == 0 && batch > 0 && h > 0 && w > 0, YX_ERR_INVALID_ARG, "spp_bwd: shape");
+  YX_REQUIRE(((uintptr_t)cat & 15) == 0 && ((uintptr_t)dout & 15) == 0, YX_ERR_INVALID_ARG, "spp_bwd: 16-byte alignment");
+  const long long total = (long long)batch * h * w * (c / 8);
+  const int grid = (int)((total + 127) / 128 < 16384 ? (total + 127) / 128 : 16384);
+  if (dtype == YX_BF16) spp_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)cat, ld, (const __nv_bfloat16*)dout, dld, dx32, batch, h, w, c);
+  else if (dtype == YX_FP16) spp_bwd_kernel<__half><<<grid, 128, 0, s>>>((const __half*)cat, ld, (const __half*)dout, dld, dx32, batch, h, w, c);
+  else if (dtype == YX_FP32) spp_bwd_kernel<float><<<grid, 128, 0, s>>>((const float*)cat, ld, (const float*)dout, dld, dx32, batch, h, w, c);
+  else YX_REQUIRE(false, YX_ERR_INVALID_ARG, "spp_bwd: dtype %d", dtype);
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

@@ -105,6 +105,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     }
     fence_proxy_async();
   }
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail;
+  // from here on the kernel reads x / dy and (much later) overwrites the partial buffer the previous reduction read
+  pdl_wait();
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,7 +193,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // sum of the per-split partials in split order -> dW with the weight tensor's own strides (fp32)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int ksplit, long long split_stride, long long row_stride,
                                     int N, int taps, int out_c, int in_c, int out_c_real, int in_c_real, float* __restrict__ dw,
-                                    long long so, long long si, long long st) {
+                                    long long so, long long si, long long st, int accumulate) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)out_c * taps * in_c;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e % in_c);
@@ -201,7 +207,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
     const float* src = partial + (long long)o * row_stride + (long long)(n_tile * taps + t) * N + n;
     float acc = 0.f;
     for (int sp = 0; sp < ksplit; ++sp) acc += src[(long long)sp * split_stride];
-    dw[(long long)o * so + (long long)i * si + (long long)t * st] = acc;
+    float* d = dw + (long long)o * so + (long long)i * si + (long long)t * st;
+    *d = accumulate ? *d + acc : acc;
   }
 }
 
@@ -211,6 +218,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
 template <typename T>
 __global__ void pack_train_weights_kernel(const float* __restrict__ w, long long so, long long si, long long st, int o, int i,
                                           int taps, int o_pad, int i_pad, T* __restrict__ wf, T* __restrict__ wd) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)o_pad * taps * i_pad;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ii = (int)(e % i_pad);
@@ -226,6 +235,8 @@ __global__ void pack_train_weights_kernel(const float* __restrict__ w, long long
 
 // z[b, 2*oy, 2*ox, :] = dy[b, oy, ox, :], every other pixel of z [b, zh, zw, c] zero (16-byte vectors)
 __global__ void dilate2_kernel(const uint4* __restrict__ dy, uint4* __restrict__ z, int batch, int oh, int ow, int zh, int zw, int c8) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = (long long)batch * zh * zw * c8;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(e % c8);
@@ -268,7 +279,12 @@ static int wgrad_plan(int batch, int in_h, int in_w, int in_c, int out_h, int ou
   p.n_blocks = p.N / p.ci_box;
   p.Ncol = (p.N + 31) & ~31;
   p.slices = p.n_tiles * p.taps;
-  const int sg_max = 512 / p.Ncol < p.slices ? 512 / p.Ncol : p.slices;
+  // slices per CTA: measured on the yolox_s layers (tools/gpu_wgrad_sweep.py), about 128 accumulator columns per CTA is best
+  // (N = 128: one slice, 36.6 -> 20.8 us for 256->256 3x3 @20x20; N = 64: two; N = 32: four): more CTAs on the (o, i, tap)
+  // space and a shorter epilogue per CTA beat the saved re-loads of the dy tile; N = 16 keeps all nine taps together
+  int sg_max = p.N <= 16 ? 512 / p.Ncol : (128 / p.N > 1 ? 128 / p.N : 1);
+  if (sg_max > p.slices) sg_max = p.slices;
+  if (const char* e = getenv("YX_WGRAD_SG")) { const int v = atoi(e); if (v >= 1 && v < sg_max) sg_max = v; }
   p.n_groups = (p.slices + sg_max - 1) / sg_max;
   p.SG = (p.slices + p.n_groups - 1) / p.n_groups;
   p.n_groups = (p.slices + p.SG - 1) / p.SG;
@@ -280,6 +296,7 @@ static int wgrad_plan(int batch, int in_h, int in_w, int in_c, int out_h, int ou
   const unsigned bpp = 256u + (unsigned)(p.SG * p.N) * 2u;   // bytes per pixel of one stage: 128 A channels + SG * N B channels
   int kp_max = (budget / 3) / (int)bpp / 16 * 16;
   if (kp_max > 128) kp_max = 128;
+  if (const char* e = getenv("YX_WGRAD_KP")) { const int v = atoi(e); if (v >= 16 && v < kp_max) kp_max = v / 16 * 16; }
   if (kp_max < 16) kp_max = 16;
   long long best = -1;
   for (int tw = 1; tw <= 128; ++tw) {
@@ -311,6 +328,7 @@ static int wgrad_plan(int batch, int in_h, int in_w, int in_c, int out_h, int ou
   if (ks < 1) ks = 1;
   if (ks > p.PT) ks = p.PT;
   if (p.PT >= 8 && ks > p.PT / 4) ks = p.PT / 4;          // at least four pixel tiles per CTA: the pipeline needs something to overlap
+  if (const char* e = getenv("YX_WGRAD_KSPLIT")) { const int v = atoi(e); if (v >= 1) ks = v < p.PT ? v : p.PT; }
   p.tiles_per_split = (p.PT + ks - 1) / ks;
   p.ksplit = (p.PT + p.tiles_per_split - 1) / p.tiles_per_split;
   p.row_stride = (long long)p.slices * p.N;
@@ -331,7 +349,7 @@ static CUtensorMapSwizzle swizzle_of(unsigned rb) {
 
 int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld, int dtype, int batch, int in_h, int in_w, int in_c,
                  int out_h, int out_w, int out_c, int ksize, int stride, int in_c_real, int out_c_real, float* dw, long long dw_so,
-                 long long dw_si, long long dw_st, void* ws, long long ws_bytes, cudaStream_t stream) {
+                 long long dw_si, long long dw_st, int accumulate, void* ws, long long ws_bytes, cudaStream_t stream) {
   YX_REQUIRE(dtype == YX_BF16 || dtype == YX_FP16, YX_ERR_UNSUPPORTED, "wgrad: 16-bit activations only");
   YX_REQUIRE(x && dy && dw && ws, YX_ERR_INVALID_ARG, "wgrad: null pointer");
   YX_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0, YX_ERR_INVALID_ARG,
@@ -389,14 +407,12 @@ int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld,
     attr_set = true;
   }
   const int grid = p.m_tiles * p.n_groups * p.ksplit;
-  wgrad_tc_kernel<<<grid, 192, L->smem, stream>>>(L->map_dy, L->map_x, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(192), L->smem, stream, L->map_dy, L->map_x, p);
   if (e == cudaSuccess) {
     const long long total = (long long)out_c * p.taps * in_c;
     const int rgrid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.partial, p.ksplit, p.split_stride, p.row_stride, p.N, p.taps, out_c, in_c,
-                                                   out_c_real, in_c_real, dw, dw_so, dw_si, dw_st);
-    e = cudaGetLastError();
+    e = launch_pdl(wgrad_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, (const float*)p.partial, p.ksplit, p.split_stride, p.row_stride,
+                   p.N, p.taps, out_c, in_c, out_c_real, in_c_real, dw, dw_so, dw_si, dw_st, accumulate);
   }
   free(L);
   if (e != cudaSuccess) return cuda_fail(e, "wgrad launch", __FILE__, __LINE__);
@@ -411,12 +427,11 @@ int pack_train_weights_launch(const float* w, long long so, long long si, long l
   const long long total = (long long)o_pad * taps * i_pad;
   const int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
   if (dtype == YX_BF16)
-    pack_train_weights_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, so, si, st, o, i, taps, o_pad, i_pad,
-                                                                        reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd));
+    YX_CUDA(launch_pdl(pack_train_weights_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, w, so, si, st, o, i, taps, o_pad, i_pad,
+                       reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd)));
   else
-    pack_train_weights_kernel<__half><<<grid, 256, 0, stream>>>(w, so, si, st, o, i, taps, o_pad, i_pad, reinterpret_cast<__half*>(wf),
-                                                                reinterpret_cast<__half*>(wd));
-  YX_CUDA(cudaGetLastError());
+    YX_CUDA(launch_pdl(pack_train_weights_kernel<__half>, dim3(grid), dim3(256), 0, stream, w, so, si, st, o, i, taps, o_pad, i_pad,
+                       reinterpret_cast<__half*>(wf), reinterpret_cast<__half*>(wd)));
   return YX_OK;
 }
 
@@ -424,8 +439,8 @@ int dilate2_launch(const void* dy, void* z, int batch, int oh, int ow, int zh, i
   YX_REQUIRE(dy && z && c % 8 == 0 && batch > 0 && oh > 0 && ow > 0 && zh >= 2 * oh - 1 && zw >= 2 * ow - 1, YX_ERR_INVALID_ARG, "dilate2: shape");
   const long long total = (long long)batch * zh * zw * (c / 8);
   const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-  dilate2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(z), batch, oh, ow, zh, zw, c / 8);
-  YX_CUDA(cudaGetLastError());
+  YX_CUDA(launch_pdl(dilate2_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(z), batch, oh, ow,
+                     zh, zw, c / 8));
   return YX_OK;
 }
 

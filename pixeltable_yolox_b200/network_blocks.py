@@ -44,14 +44,14 @@ class _FusedBnAct(torch.autograd.Function):
     (tools/gpu_prof_train.py). Running statistics are updated in place like F.batch_norm."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act, num_batches_tracked=None):
         from . import ops
         from ._lib import ACT_CODES
 
         if not ops._is_channels_last(x):
             x = x.contiguous()
         code = ACT_CODES[act]
-        y, mean, invstd = ops.bn_act_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, code)
+        y, mean, invstd = ops.bn_act_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum, code, num_batches_tracked)
         ctx.save_for_backward(x, gamma, beta, mean, invstd)
         ctx.act = code
         return y
@@ -64,8 +64,38 @@ class _FusedBnAct(torch.autograd.Function):
         dy = dy.to(x.dtype)
         if dy.stride() != x.stride():                       # same memory format as x (NCHW or channels_last)
             dy = dy.contiguous(memory_format=torch.channels_last) if ops._is_channels_last(x) else dy.contiguous()
+        from .train_conv import direct_grads
+
+        if direct_grads() and gamma.grad is not None and beta.grad is not None:
+            # gradient accumulation into .grad inside the finalize launch (see train_conv.set_direct_grads)
+            dx, _, _ = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act, gamma.grad, beta.grad)
+            return dx, None, None, None, None, None, None, None, None
         dx, dgamma, dbeta = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act)
-        return dx, dgamma, dbeta, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+class _SppCat(torch.autograd.Function):
+    """cat[x, maxpool5(x), maxpool9(x), maxpool13(x)] of SPPBottleneck (network_blocks.py:137-139) on a channels_last 16-bit
+    tensor: forward = the inference pool kernel on the concat buffer, backward = one scatter kernel (torch's channels_last
+    max-pool kernels took 1.2 ms of the 8-image training step for these three 20x20 maps)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import ops
+
+        B, c, H, W = x.shape
+        cat = torch.empty((B, 4 * c, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        cat[:, :c] = x
+        ops.spp_maxpool(ops._nhwc(cat), c)
+        ctx.save_for_backward(cat)
+        return cat
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+
+        (cat,) = ctx.saved_tensors
+        return ops.spp_maxpool_bwd(cat, dout.to(cat.dtype).contiguous(memory_format=torch.channels_last))
 
 
 class _B200Block(nn.Module):
@@ -105,9 +135,9 @@ class BaseConv(_B200Block):
                 and os.environ.get("YX_FUSED_BN", "1") != "0"):
             # nn.BatchNorm2d.forward in train mode: batch statistics, running statistics updated with `momentum`
             # (num_batches_tracked counts the calls), then the activation -- one fused pass each way
-            bn.num_batches_tracked.add_(1)
+            # (num_batches_tracked counts the calls: incremented by the kernel)
             return _FusedBnAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
-                                     act_name(self.act))
+                                     act_name(self.act), bn.num_batches_tracked)
         return self.act(bn(y))
 
     def fuseforward(self, x):
@@ -191,7 +221,13 @@ class SPPBottleneck(_B200Block):
 
     def _train_forward(self, x):
         x = self.conv1._train_forward(x)
-        x = torch.cat([x] + [m(x) for m in self.m], dim=1)
+        from . import ops
+
+        if (x.is_cuda and tuple(m.kernel_size for m in self.m) == (5, 9, 13) and x.dtype in (torch.bfloat16, torch.float16)
+                and ops._is_channels_last(x) and os.environ.get("YX_TRAIN_SPP", "1") != "0"):
+            x = _SppCat.apply(x)
+        else:
+            x = torch.cat([x] + [m(x) for m in self.m], dim=1)
         return self.conv2._train_forward(x)
 
     def lower(self, b, x, out=None):

@@ -557,12 +557,15 @@ def _is_channels_last(x: torch.Tensor) -> bool:
 
 
 def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
-                     running_var: Optional[torch.Tensor], eps: float, momentum: float, act: int):
+                     running_var: Optional[torch.Tensor], eps: float, momentum: float, act: int,
+                     num_batches_tracked: Optional[torch.Tensor] = None):
     """Training-mode BatchNorm2d + activation on a conv output x [N, C, H, W] (contiguous NCHW). Returns
     (y, save_mean, save_invstd); running statistics are updated in place like F.batch_norm."""
     require_cuda(x, "bn_act_train_fwd")
     dev = x.device
-    same_device(dev, "bn_act_train_fwd", gamma=gamma, beta=beta, running_mean=running_mean, running_var=running_var)
+    same_device(dev, "bn_act_train_fwd", gamma=gamma, beta=beta, running_mean=running_mean, running_var=running_var,
+                num_batches_tracked=num_batches_tracked)
+    assert num_batches_tracked is None or (num_batches_tracked.dtype == torch.int64 and num_batches_tracked.numel() == 1)
     cl = _is_channels_last(x)
     assert x.dim() == 4 and (cl or x.is_contiguous()) and gamma.dtype == beta.dtype == torch.float32
     N, Cc, H, W = x.shape
@@ -574,17 +577,23 @@ def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, r
     with on_device(dev):
         check(lib().yx_bn_act_train_fwd(x.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(), beta.data_ptr(),
                                         float(eps), float(momentum), 0 if running_mean is None else running_mean.data_ptr(),
-                                        0 if running_var is None else running_var.data_ptr(), int(act), y.data_ptr(),
+                                        0 if running_var is None else running_var.data_ptr(),
+                                        0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), int(act), y.data_ptr(),
                                         mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
               "bn_act_train_fwd")
     return y, mean, invstd
 
 
 def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean: torch.Tensor,
-                     invstd: torch.Tensor, act: int):
-    """Backward of bn_act_train_fwd: (dx in x's dtype, dgamma, dbeta fp32)."""
+                     invstd: torch.Tensor, act: int, acc_dgamma: Optional[torch.Tensor] = None,
+                     acc_dbeta: Optional[torch.Tensor] = None):
+    """Backward of bn_act_train_fwd: (dx in x's dtype, dgamma, dbeta fp32). acc_dgamma / acc_dbeta: contiguous fp32 [C]
+    tensors (the parameters' .grad) that dgamma / dbeta are also added to, in the same launch."""
     dev = x.device
-    same_device(dev, "bn_act_train_bwd", dy=dy, gamma=gamma, beta=beta, mean=mean, invstd=invstd)
+    same_device(dev, "bn_act_train_bwd", dy=dy, gamma=gamma, beta=beta, mean=mean, invstd=invstd, acc_dgamma=acc_dgamma,
+                acc_dbeta=acc_dbeta)
+    for t in (acc_dgamma, acc_dbeta):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x.shape[1])
     cl = _is_channels_last(x)
     assert dy.dtype == x.dtype and dy.shape == x.shape and dy.stride() == x.stride(), "dy must have x's dtype and memory format"
     N, Cc, H, W = x.shape
@@ -595,7 +604,8 @@ def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, bet
     with on_device(dev):
         check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(),
                                         beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(act), dx.data_ptr(),
-                                        dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+                                        dgamma.data_ptr(), dbeta.data_ptr(), 0 if acc_dgamma is None else acc_dgamma.data_ptr(),
+                                        0 if acc_dbeta is None else acc_dbeta.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
               "bn_act_train_bwd")
     return dx, dgamma, dbeta
 
@@ -634,9 +644,11 @@ def pack_train_weights(weight: torch.Tensor, dtype: torch.dtype, o_pad: int, i_p
     return wf, wd
 
 
-def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksize: int, stride: int) -> torch.Tensor:
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksize: int, stride: int,
+               accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dW of y = conv(x, W): x [B, Ci_pad, H, W], dy [B, Co_pad, OH, OW], both 16-bit dense channels_last with channel
-    counts padded to multiples of 16; returns fp32 dW with weight_like's shape [o, i, k, k] and strides."""
+    counts padded to multiples of 16; returns fp32 dW with weight_like's shape [o, i, k, k] and strides.
+    accumulate_into: an fp32 tensor of the weight's shape (its .grad): dW is ADDED to it in place and returned."""
     require_cuda(x, "conv_wgrad")
     dev = x.device
     same_device(dev, "conv_wgrad", dy=dy, weight=weight_like)
@@ -644,7 +656,11 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksi
     assert x.dtype == dy.dtype and x.dtype in (torch.bfloat16, torch.float16)
     o, i = weight_like.shape[0], weight_like.shape[1]
     assert i <= xv.c and o <= dv.c and xv.B == dv.B
-    dw = torch.empty_strided(weight_like.shape, weight_like.stride(), dtype=torch.float32, device=dev)
+    if accumulate_into is not None:
+        dw = accumulate_into
+        assert dw.dtype == torch.float32 and dw.shape == weight_like.shape and dw.device == dev
+    else:
+        dw = torch.empty_strided(weight_like.shape, weight_like.stride(), dtype=torch.float32, device=dev)
     so, si, st = _weight_strides(dw)
     args = (xv.B, xv.H, xv.W, xv.c, dv.H, dv.W, dv.c, ksize, stride)
     nbytes = lib().yx_conv_wgrad_workspace_bytes(*args)
@@ -653,7 +669,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksi
     ws = _workspace(dev, nbytes, "wgrad")
     with on_device(dev):
         check(lib().yx_conv_wgrad(xv.ptr, xv.ld, dv.ptr, dv.ld, dtype_code(x.dtype), *args, i, o, dw.data_ptr(), so, si, st,
-                                  ws.data_ptr(), ws.numel(), stream_ptr(dev)), "conv_wgrad")
+                                  0 if accumulate_into is None else 1, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "conv_wgrad")
     return dw
 
 
@@ -665,3 +681,18 @@ def dilate2(dy: torch.Tensor, zh: int, zw: int) -> torch.Tensor:
     with on_device(dy.device):
         check(lib().yx_dilate2(dv.ptr, z.data_ptr(), dv.B, dv.H, dv.W, zh, zw, dv.c, stream_ptr(dy.device)), "dilate2")
     return z
+
+
+def spp_maxpool_bwd(cat: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    """Backward of cat[x, m5, m9, m13]: cat [B, 4c, H, W] (the forward's output, channels [0, c) = x) and its gradient, both
+    dense channels_last 16-bit -> dx [B, c, H, W] (channels_last, same dtype)."""
+    require_cuda(cat, "spp_maxpool_bwd")
+    same_device(cat.device, "spp_maxpool_bwd", dout=dout)
+    cv, dv = _nhwc(cat), _nhwc(dout)
+    assert cat.shape == dout.shape and cat.dtype == dout.dtype and cv.c % 4 == 0
+    c = cv.c // 4
+    dx32 = dout[:, :c].to(torch.float32, memory_format=torch.channels_last)
+    with on_device(cat.device):
+        check(lib().yx_spp_maxpool_bwd(cv.ptr, cv.ld, dv.ptr, dv.ld, dx32.data_ptr(), cv.B, cv.H, cv.W, c, dtype_code(cat.dtype),
+                                       stream_ptr(cat.device)), "spp_maxpool_bwd")
+    return dx32.to(cat.dtype)

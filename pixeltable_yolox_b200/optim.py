@@ -36,7 +36,7 @@ class FusedSgdEma:
     CHUNK = 16384
 
     def __init__(self, model: nn.Module, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, nesterov: bool = True,
-                 ema: bool = True, ema_decay: float = 0.9998, updates: int = 0):
+                 ema: bool = True, ema_decay: float = 0.9998, updates: int = 0, direct_grads: bool = False):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("FusedSgdEma needs the model on a CUDA device (the B200 path has no CPU fallback)")
@@ -55,6 +55,20 @@ class FusedSgdEma:
         if missing:
             raise ValueError(f"{len(missing)} trainable parameters belong to no reference parameter group")
         self.bufs = [torch.zeros_like(p) for p in self.params]      # same strides as the parameter (NCHW or channels_last)
+        # direct_grads: every .grad is a view into ONE flat fp32 buffer (zero_grad = one memset, a multi-GPU step all-reduces
+        # the buffer itself), and the conv / BatchNorm backward kernels add their weight gradients into it in place
+        # (train_conv.set_direct_grads). Not for modules wrapped in DistributedDataParallel.
+        self.flat_grad = None
+        if direct_grads:
+            from . import train_conv
+
+            self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+            off = 0
+            for p in self.params:
+                assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameter storage is not dense"
+                p.grad = torch.as_strided(self.flat_grad, p.shape, p.stride(), off)
+                off += p.numel()
+            train_conv.set_direct_grads(True)
         self._wd = [wd[id(p)] for p in self.params]
         self._steps = 0
         self._table = None
@@ -96,6 +110,9 @@ class FusedSgdEma:
 
     def zero_grad(self):
         """Keeps the gradient storage (the pointer table stays valid): grads are zeroed in place."""
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
+            return
         grads = [p.grad for p in self.params if p.grad is not None]
         if grads:
             torch._foreach_zero_(grads)          # a handful of multi-tensor launches instead of one per parameter

@@ -23,6 +23,21 @@ from ._lib import YX_ACT_NONE
 
 _zero_bias = {}
 
+# Direct gradient accumulation (FusedSgdEma(direct_grads=True) switches it on): the wgrad reduction and the BatchNorm backward
+# add their results straight into `param.grad` (which must exist: the optimizer owns one flat, zeroed gradient buffer) and
+# return no gradient to autograd, so AccumulateGrad's one `grad += new` launch per parameter (242 per step) disappears. Not for
+# modules wrapped in DistributedDataParallel, whose reduction hooks hang off AccumulateGrad.
+_direct_grads = False
+
+
+def set_direct_grads(on: bool) -> None:
+    global _direct_grads
+    _direct_grads = bool(on)
+
+
+def direct_grads() -> bool:
+    return _direct_grads
+
 
 def _zeros(dev: torch.device, n: int) -> torch.Tensor:
     t = _zero_bias.get((dev, n))
@@ -95,7 +110,10 @@ class _ConvTc(torch.autograd.Function):
         dyh = _pad_channels(dy.to(xh.dtype), o_pad)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
+            if _direct_grads and weight.grad is not None:
+                ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
+            else:
+                dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
         if ctx.needs_input_grad[0]:
             src = dyh if stride == 1 else ops.dilate2(dyh, H, W)
             dxp = torch.empty((xh.shape[0], i_pad, H, W), dtype=xh.dtype, device=xh.device, memory_format=torch.channels_last)

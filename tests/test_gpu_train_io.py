@@ -234,7 +234,8 @@ def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape, channels_last
     rm, rv = bn.running_mean.clone(), bn.running_var.clone()
     gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
     x = x0.clone().requires_grad_(True)
-    y = _FusedBnAct.apply(x, gam, bet, rm, rv, bn.eps, bn.momentum, act)
+    nbt = torch.full((), 5, dtype=torch.int64, device=cuda)
+    y = _FusedBnAct.apply(x, gam, bet, rm, rv, bn.eps, bn.momentum, act, nbt)
     go = torch.randn(shape, generator=g).to(dtype).to(cuda)
     y.backward(go)
     # reference in fp32 on the same (already rounded) input
@@ -243,6 +244,7 @@ def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape, channels_last
     yr.backward(go.float())
     tol = dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
     assert y.dtype == dtype and y.stride() == x0.stride() and x.grad.stride() == x0.stride()
+    assert int(nbt) == 6                       # nn.BatchNorm2d.num_batches_tracked, incremented by the forward kernel
     torch.testing.assert_close(y.float(), yr, **tol)
     torch.testing.assert_close(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rv, bn.running_var, rtol=1e-5, atol=1e-6)
