@@ -865,6 +865,10 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
         from pixeltable_yolox_b200.optim import FusedSgdEma
 
         raw = copy.deepcopy(model.module).train()
+        if amp_dtype is not None and os.environ.get("YX_TRAIN_CONV", "1") != "0":
+            from pixeltable_yolox_b200 import train_conv
+
+            train_conv.attach_packer(raw, amp_dtype)
         opt = FusedSgdEma(raw, lr=opt.lr, momentum=opt.momentum, weight_decay=5e-4, nesterov=opt.nesterov, ema=True,
                           ema_decay=opt.ema_decay, direct_grads=True)
     else:
@@ -959,6 +963,10 @@ def run_train(args, world, rank, dev):
     model.train()
     if args.train_format == "channels_last":
         model = model.to(memory_format=torch.channels_last)
+    if amp_dtype is not None and os.environ.get("YX_TRAIN_CONV", "1") != "0":
+        from pixeltable_yolox_b200 import train_conv
+
+        train_conv.attach_packer(model, amp_dtype)       # every conv weight packed to its 16-bit operands in one launch per step
     n_grad = sum(p.numel() for p in model.parameters() if p.requires_grad)
     net = model
     if world > 1:

@@ -338,6 +338,8 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
  *   bwd: dy = gradient w.r.t. y -> dx (dtype of x), dgamma, dbeta [C] fp32. x_hat and the pre-activation are recomputed
  *        from x and the saved statistics, nothing else is kept from the forward.
  *   channels_last != 0: x / y / dy / dx are [N*H*W][C] (torch.channels_last, C % 8 == 0), else [N][C][H*W].
+ *   dy_ld (channels_last only; 0 = C): per-pixel stride of dy in elements, so that a channel slice of a wider gradient
+ *   tensor (the backward of torch.cat) is read in place.
  *   acc_dgamma / acc_dbeta (may be NULL): fp32 [C] buffers the backward ALSO adds dgamma / dbeta to (the parameters' .grad).
  *   num_batches_tracked (may be NULL): nn.BatchNorm2d's int64 call counter, incremented by the forward.
  *   act: YX_ACT_SILU / YX_ACT_RELU / YX_ACT_LRELU / YX_ACT_NONE.  workspace: yx_bn_act_workspace_bytes(N, C, H*W).
@@ -351,8 +353,8 @@ int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t channels_last, int
 int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t channels_last, int32_t n, int32_t c,
                         int32_t hw,
                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, void* workspace,
-                        int64_t workspace_bytes, void* stream);
+                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, int64_t dy_ld,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training conv stack on the tensor cores: what torch autograd / cuDNN computes for BaseConv.conv and the prediction
@@ -382,6 +384,11 @@ int yx_conv_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, in
                   int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, int64_t stride_tap, int32_t o, int32_t i, int32_t taps,
                           int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t dtype, void* stream);
+/* yx_pack_train_weights for every conv of a model in one launch. table: device int64 [n, 11] rows = w ptr | stride_o |
+ * stride_i | stride_tap | o | i | taps | o_pad | i_pad | w_fwd ptr | w_dgrad ptr (0: skip); chunks: device int32 [n_chunks, 2]
+ * rows = (tensor index, first element of its [o_pad][taps][i_pad] index space), one CTA per chunk of chunk_elems elements. */
+int yx_pack_train_weights_multi(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, int32_t dtype,
+                                void* stream);
 int yx_dilate2(const void* dy, void* z, int32_t batch, int32_t oh, int32_t ow, int32_t zh, int32_t zw, int32_t c, void* stream);
 
 /* Backward of the SPP pools (SPPBottleneck, network_blocks.py:120-142; forward = yx_spp_maxpool on the concat buffer):

@@ -95,11 +95,12 @@ SIGNATURES = {
     "yx_sgd_ema_step": (C.c_int, [_P, _P, _I32, _I32, _F, _F, _I32, _I32, _F, _F, _P, _P]),
     "yx_bn_act_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "yx_bn_act_train_fwd": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P, _F, _F, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
-    "yx_bn_act_train_bwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "yx_bn_act_train_bwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "yx_conv_wgrad_workspace_bytes": (_I64, [_I32] * 9),
     "yx_conv_wgrad": (C.c_int, [_P, _I64, _P, _I64] + [_I32] * 12 + [_P, _I64, _I64, _I64, _I32, _P, _I64, _P]),
     "yx_pack_train_weights": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "yx_spp_maxpool_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "yx_pack_train_weights_multi": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
     "yx_dilate2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_letterbox_u8": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "yx_coco_rows": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),

@@ -67,7 +67,7 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
                             float* save_invstd, void* ws, long long ws_bytes, cudaStream_t s);
 int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta,
                             const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
-                            float* acc_dgamma, float* acc_dbeta, void* ws, long long ws_bytes, cudaStream_t s);
+                            float* acc_dgamma, float* acc_dbeta, long long dy_ld, void* ws, long long ws_bytes, cudaStream_t s);
 long long wgrad_ws_bytes(int batch, int in_h, int in_w, int in_c, int out_h, int out_w, int out_c, int ksize, int stride);
 int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld, int dtype, int batch, int in_h, int in_w, int in_c,
                  int out_h, int out_w, int out_c, int ksize, int stride, int in_c_real, int out_c_real, float* dw, long long dw_so,
@@ -75,6 +75,7 @@ int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld,
 int pack_train_weights_launch(const float* w, long long so, long long si, long long st, int o, int i, int taps, int o_pad, int i_pad,
                               void* wf, void* wd, int dtype, cudaStream_t stream);
 int dilate2_launch(const void* dy, void* z, int batch, int oh, int ow, int zh, int zw, int c, cudaStream_t stream);
+int pack_train_weights_multi_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, int dtype, cudaStream_t stream);
 int spp_bwd_launch(const void* cat, long long ld, const void* dout, long long dld, float* dx32, int batch, int h, int w, int c,
                    int dtype, cudaStream_t s);
 struct StemLaunch;
@@ -449,12 +450,12 @@ int yx_bn_act_train_fwd(const void* x, int32_t dtype, int32_t channels_last, int
 
 int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t channels_last, int32_t n, int32_t c, int32_t hw,
                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, void* workspace,
-                        int64_t workspace_bytes, void* stream) {
+                        int32_t act, void* dx, float* dgamma, float* dbeta, float* acc_dgamma, float* acc_dbeta, int64_t dy_ld,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = require_device();
   if (rc) return rc;
   return bn_act_train_bwd_launch(x, dy, dtype, channels_last, n, c, hw, gamma, beta, save_mean, save_invstd, act, dx, dgamma, dbeta,
-                                 acc_dgamma, acc_dbeta, workspace,
+                                 acc_dgamma, acc_dbeta, dy_ld, workspace,
                                  workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -486,6 +487,13 @@ int yx_spp_maxpool_bwd(const void* cat, int64_t ld, const void* dout, int64_t do
   int rc = require_device();
   if (rc) return rc;
   return spp_bwd_launch(cat, ld, dout, dout_ld, dx32, batch, h, w, c, dtype, (cudaStream_t)stream);
+}
+
+int yx_pack_train_weights_multi(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, int32_t dtype,
+                                void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return pack_train_weights_multi_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, dtype, (cudaStream_t)stream);
 }
 
 int yx_dilate2(const void* dy, void* z, int32_t batch, int32_t oh, int32_t ow, int32_t zh, int32_t zw, int32_t c, void* stream) {

@@ -391,7 +391,7 @@ template <typename T, bool BWD, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_reduce_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int C, int rows_per_cta, int act,
-                      float* __restrict__ part) {
+                      float* __restrict__ part, long long dy_ld) {
   pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
   pdl_launch_dependents();
   __shared__ float red[kBnThreads][17];
@@ -415,7 +415,7 @@ bn_reduce_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const f
           const long long mm = m + (long long)u * rpi;
           if (mm < m_hi) {
             Vec8<T>::load(x + mm * C + cc * 8, xv[u]);
-            if (BWD) Vec8<T>::load(dy + mm * C + cc * 8, dv[u]);
+            if (BWD) Vec8<T>::load(dy + mm * dy_ld + cc * 8, dv[u]);
           }
         }
 #pragma unroll
@@ -455,7 +455,8 @@ template <typename T, bool BWD, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dbeta,
-                     const float* __restrict__ dgamma, float inv_m, long long M, int C, int rows_per_cta, int act, T* __restrict__ out) {
+                     const float* __restrict__ dgamma, float inv_m, long long M, int C, int rows_per_cta, int act, T* __restrict__ out,
+                     long long dy_ld) {
   pdl_wait();               // programmatic dependent launch: our prologue overlapped the predecessor's tail
   pdl_launch_dependents();
   const int cg = C >> 3;
@@ -479,7 +480,7 @@ bn_apply_nhwc_kernel(const T* __restrict__ x, const T* __restrict__ dy, const fl
         const long long mm = m + (long long)u * rpi;
         if (mm < m_hi) {
           Vec8<T>::load(x + mm * C + cc * 8, xv[u]);
-          if (BWD) Vec8<T>::load(dy + mm * C + cc * 8, dv[u]);
+          if (BWD) Vec8<T>::load(dy + mm * dy_ld + cc * 8, dv[u]);
         }
       }
 #pragma unroll
@@ -543,11 +544,11 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
     const long long M = (long long)n * hw;
     int rows = 0, rows2 = 0;
     const int S = bn_nhwc_slabs(M, 64, 4, &rows), S2 = bn_nhwc_slabs(M, 32, 6, &rows2);
-#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, false, 4>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, M, c, rows, act, part)
+#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, false, 4>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, M, c, rows, act, part, (long long)c)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, S, (double)M, eps, momentum, running_mean, running_var, save_mean, save_invstd, 0, nbt, (float*)nullptr, (float*)nullptr);
-#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, false, 4>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, M, c, rows2, act, (T*)y)
+#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, false, 4>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, nullptr, save_mean, save_invstd, gamma, beta, nullptr, nullptr, 0.0f, M, c, rows2, act, (T*)y, (long long)c)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     YX_CUDA(cudaGetLastError());
@@ -569,7 +570,7 @@ int bn_act_train_fwd_launch(const void* x, int dtype, int nhwc, int n, int c, in
 
 int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, int n, int c, int hw, const float* gamma, const float* beta,
                             const float* save_mean, const float* save_invstd, int act, void* dx, float* dgamma, float* dbeta,
-                            float* acc_dgamma, float* acc_dbeta, void* ws, long long ws_bytes, cudaStream_t s) {
+                            float* acc_dgamma, float* acc_dbeta, long long dy_ld, void* ws, long long ws_bytes, cudaStream_t s) {
   YX_REQUIRE(x && dy && gamma && beta && save_mean && save_invstd && dx && dgamma && dbeta && ws, YX_ERR_INVALID_ARG, "bn_act_bwd: null pointer");
   int rc = bn_check(dtype, n, c, hw, act);
   if (rc) return rc;
@@ -579,15 +580,17 @@ int bn_act_train_bwd_launch(const void* x, const void* dy, int dtype, int nhwc, 
     YX_REQUIRE(c <= 2048, YX_ERR_UNSUPPORTED, "bn_act_bwd(channels_last): C = %d > 2048", c);
     YX_REQUIRE(c % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, YX_ERR_INVALID_ARG,
                "bn_act_bwd(channels_last): C %% 8 == 0 and 16-byte aligned tensors required");
+    if (dy_ld <= 0) dy_ld = c;
+    YX_REQUIRE(dy_ld >= c && dy_ld % 8 == 0, YX_ERR_INVALID_ARG, "bn_act_bwd(channels_last): dy pixel stride %lld", dy_ld);
     const long long M = (long long)n * hw;
     int rows = 0, rows2 = 0;
     const int S = bn_nhwc_slabs(M, 64, 4, &rows), S2 = bn_nhwc_slabs(M, 32, 6, &rows2);
-#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, true, 2>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, M, c, rows, act, part)
+#define YX_GO(T) launch_pdl(bn_reduce_nhwc_kernel<T, true, 2>, dim3(S), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, M, c, rows, act, part, dy_ld)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     launch_pdl(bn_finalize_kernel, dim3((c + 3) / 4), dim3(128), 0, s, part, c, S, (double)M, 0.0f, 0.0f, nullptr, nullptr, dbeta, dgamma, 1, (long long*)nullptr, acc_dbeta, acc_dgamma);
     const float inv_m = (float)(1.0 / (double)M);
-#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, true, 2>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, M, c, rows2, act, (T*)dx)
+#define YX_GO(T) launch_pdl(bn_apply_nhwc_kernel<T, true, 2>, dim3(S2), dim3(kBnThreads), 0, s, (const T*)x, (const T*)dy, save_mean, save_invstd, gamma, beta, dbeta, dgamma, inv_m, M, c, rows2, act, (T*)dx, dy_ld)
     if (dtype == YX_FP32) YX_GO(float); else if (dtype == YX_BF16) YX_GO(__nv_bfloat16); else YX_GO(__half);
 #undef YX_GO
     YX_CUDA(cudaGetLastError());

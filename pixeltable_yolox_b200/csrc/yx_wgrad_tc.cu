@@ -233,6 +233,33 @@ __global__ void pack_train_weights_kernel(const float* __restrict__ w, long long
   }
 }
 
+// every conv weight of the model in ONE launch (83 launches of ~4 us each otherwise): table rows (int64 x 11) =
+// src ptr | stride_o | stride_i | stride_tap | o | i | taps | o_pad | i_pad | wf ptr | wd ptr; chunks rows = (tensor, first
+// element of the [o_pad][taps][i_pad] index space); one CTA per chunk of chunk_elems elements.
+template <typename T>
+__global__ void pack_train_weights_multi_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int chunk_elems) {
+  const int t = chunks[2 * blockIdx.x];
+  const long long e0 = chunks[2 * blockIdx.x + 1];
+  const long long* r = table + (long long)t * 11;
+  const float* w = reinterpret_cast<const float*>(r[0]);
+  const long long so = r[1], si = r[2], st = r[3];
+  const int o = (int)r[4], i = (int)r[5], taps = (int)r[6], o_pad = (int)r[7], i_pad = (int)r[8];
+  T* wf = reinterpret_cast<T*>(r[9]);
+  T* wd = reinterpret_cast<T*>(r[10]);
+  const long long total = (long long)o_pad * taps * i_pad;
+  const long long e1 = e0 + chunk_elems < total ? e0 + chunk_elems : total;
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int ii = (int)(e % i_pad);
+    const long long ot = e / i_pad;
+    const int tp = (int)(ot % taps);
+    const int oo = (int)(ot / taps);
+    const float v = (oo < o && ii < i) ? w[(long long)oo * so + (long long)ii * si + (long long)tp * st] : 0.f;
+    const T h = Cvt<T>::from_f(v);
+    if (wf) wf[e] = h;
+    if (wd) wd[((long long)ii * taps + (taps - 1 - tp)) * o_pad + oo] = h;
+  }
+}
+
 // z[b, 2*oy, 2*ox, :] = dy[b, oy, ox, :], every other pixel of z [b, zh, zw, c] zero (16-byte vectors)
 __global__ void dilate2_kernel(const uint4* __restrict__ dy, uint4* __restrict__ z, int batch, int oh, int ow, int zh, int zw, int c8) {
   pdl_wait();
@@ -432,6 +459,15 @@ int pack_train_weights_launch(const float* w, long long so, long long si, long l
   else
     YX_CUDA(launch_pdl(pack_train_weights_kernel<__half>, dim3(grid), dim3(256), 0, stream, w, so, si, st, o, i, taps, o_pad, i_pad,
                        reinterpret_cast<__half*>(wf), reinterpret_cast<__half*>(wd)));
+  return YX_OK;
+}
+
+int pack_train_weights_multi_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, int dtype, cudaStream_t stream) {
+  YX_REQUIRE(table && chunks && n_chunks > 0 && chunk_elems > 0, YX_ERR_INVALID_ARG, "pack_train_weights_multi: arguments");
+  YX_REQUIRE(dtype == YX_BF16 || dtype == YX_FP16, YX_ERR_UNSUPPORTED, "pack_train_weights_multi: 16-bit destinations only");
+  if (dtype == YX_BF16) pack_train_weights_multi_kernel<__nv_bfloat16><<<n_chunks, 256, 0, stream>>>(table, chunks, chunk_elems);
+  else pack_train_weights_multi_kernel<__half><<<n_chunks, 256, 0, stream>>>(table, chunks, chunk_elems);
+  YX_CUDA(cudaGetLastError());
   return YX_OK;
 }
 

@@ -63,7 +63,12 @@ class _FusedBnAct(torch.autograd.Function):
         x, gamma, beta, mean, invstd = ctx.saved_tensors
         dy = dy.to(x.dtype)
         if dy.stride() != x.stride():                       # same memory format as x (NCHW or channels_last)
-            dy = dy.contiguous(memory_format=torch.channels_last) if ops._is_channels_last(x) else dy.contiguous()
+            _, _, H, W = x.shape
+            ld = dy.stride(3)
+            sliced = (ops._is_channels_last(x) and ld % 8 == 0 and dy.stride() == (H * W * ld, 1, W * ld, ld)
+                      and dy.data_ptr() % 16 == 0)           # channel slice of a wider NHWC gradient (backward of cat): read in place
+            if not sliced:
+                dy = dy.contiguous(memory_format=torch.channels_last) if ops._is_channels_last(x) else dy.contiguous()
         from .train_conv import direct_grads
 
         if direct_grads() and gamma.grad is not None and beta.grad is not None:

@@ -595,8 +595,14 @@ def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, bet
     for t in (acc_dgamma, acc_dbeta):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x.shape[1])
     cl = _is_channels_last(x)
-    assert dy.dtype == x.dtype and dy.shape == x.shape and dy.stride() == x.stride(), "dy must have x's dtype and memory format"
     N, Cc, H, W = x.shape
+    dy_ld = 0
+    if cl and dy.stride() != x.stride():
+        dy_ld = dy.stride(3)               # a channel slice of a wider channels_last tensor (the backward of torch.cat)
+        assert dy.stride() == (H * W * dy_ld, 1, W * dy_ld, dy_ld) and dy_ld % 8 == 0 and dy.data_ptr() % 16 == 0, "dy layout"
+    else:
+        assert dy.stride() == x.stride(), "dy must have x's memory format"
+    assert dy.dtype == x.dtype and dy.shape == x.shape
     dx = torch.empty_like(x)
     dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
     dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
@@ -605,7 +611,8 @@ def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, bet
         check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(),
                                         beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(act), dx.data_ptr(),
                                         dgamma.data_ptr(), dbeta.data_ptr(), 0 if acc_dgamma is None else acc_dgamma.data_ptr(),
-                                        0 if acc_dbeta is None else acc_dbeta.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+                                        0 if acc_dbeta is None else acc_dbeta.data_ptr(), dy_ld, ws.data_ptr(), ws.numel(),
+                                        stream_ptr(dev)),
               "bn_act_train_bwd")
     return dx, dgamma, dbeta
 

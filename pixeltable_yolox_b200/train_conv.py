@@ -39,6 +39,76 @@ def direct_grads() -> bool:
     return _direct_grads
 
 
+class WeightPacker:
+    """All conv weights of a model packed to their 16-bit forward / dgrad operands in ONE launch per step
+    (yx_pack_train_weights_multi) instead of one launch per layer. `attach(model, dtype)` makes `YoloxModule.forward` call
+    `pack()` at the start of every training forward; the packed buffers are used by the convs of THAT forward (and, through
+    the tensors saved for backward, by its backward) and by nothing else."""
+
+    CHUNK = 8192
+
+    def __init__(self, model: torch.nn.Module, dtype: torch.dtype):
+        import numpy as np
+
+        self.dtype = dtype
+        self.entries = {}
+        rows, chunks, keep = [], [], []
+        dev = None
+        for mod in model.modules():
+            if not isinstance(mod, torch.nn.Conv2d) or mod.groups != 1 or mod.weight.dtype != torch.float32 or not mod.weight.is_cuda:
+                continue
+            k, s = mod.kernel_size, mod.stride
+            if k[0] != k[1] or s[0] != s[1] or (k[0], s[0]) not in ((1, 1), (3, 1), (3, 2)):
+                continue
+            w = mod.weight
+            dev = w.device
+            o, i, taps = w.shape[0], w.shape[1], k[0] * k[0]
+            o_pad, i_pad = _pad16(o), _pad16(i)
+            wf = torch.empty((o_pad, taps, i_pad), dtype=dtype, device=dev)
+            wd = torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev)
+            so, si, st = ops._weight_strides(w)
+            t = len(rows)
+            rows.append((w.data_ptr(), so, si, st, o, i, taps, o_pad, i_pad, wf.data_ptr(), wd.data_ptr()))
+            chunks += [(t, e) for e in range(0, o_pad * taps * i_pad, self.CHUNK)]
+            self.entries[id(w)] = (w, wf, wd, w.data_ptr())
+        if not rows:
+            raise ValueError("WeightPacker: the model has no dense CUDA convolution")
+        self.device = dev
+        self.table = torch.from_numpy(np.array(rows, dtype=np.int64)).to(dev)
+        self.chunks = torch.from_numpy(np.array(chunks, dtype=np.int32)).to(dev)
+        self.active = False
+
+    def __deepcopy__(self, memo):
+        return None                  # the table holds raw pointers of THIS model's weights: a copied model gets no packer
+
+    def pack(self) -> None:
+        from ._lib import check, dtype_code, lib, stream_ptr
+
+        with ops.on_device(self.device):
+            check(lib().yx_pack_train_weights_multi(self.table.data_ptr(), self.chunks.data_ptr(), self.chunks.shape[0], self.CHUNK,
+                                                    dtype_code(self.dtype), stream_ptr(self.device)), "pack_train_weights_multi")
+        self.active = True
+
+    def lookup(self, weight: torch.Tensor, dtype: torch.dtype):
+        if not self.active or dtype != self.dtype:
+            return None
+        ent = self.entries.get(id(weight))
+        # a parameter that was reallocated since the table was built (.to(), load_state_dict(assign=True)) is not in it
+        if ent is None or ent[0] is not weight or weight.data_ptr() != ent[3]:
+            return None
+        return ent[1], ent[2]
+
+
+_packer: Optional[WeightPacker] = None
+
+
+def attach_packer(model: torch.nn.Module, dtype: torch.dtype) -> WeightPacker:
+    """Batched weight packing for `model`'s training forward (see WeightPacker). Returns the packer; detach with None."""
+    p = WeightPacker(model, dtype)
+    model.__dict__["_yx_train_packer"] = p
+    return p
+
+
 def _zeros(dev: torch.device, n: int) -> torch.Tensor:
     t = _zero_bias.get((dev, n))
     if t is None:
@@ -89,7 +159,11 @@ class _ConvTc(torch.autograd.Function):
         pad = (k - 1) // 2
         OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         xh = _pad_channels(x.detach().to(dtype), i_pad)
-        wf, wd = ops.pack_train_weights(weight.detach(), dtype, o_pad, i_pad, want_dgrad=ctx.needs_input_grad[0])
+        pre = _packer.lookup(weight, dtype) if _packer is not None else None
+        if pre is not None:
+            wf, wd = pre
+        else:
+            wf, wd = ops.pack_train_weights(weight.detach(), dtype, o_pad, i_pad, want_dgrad=ctx.needs_input_grad[0])
         if bias is None:
             b = _zeros(x.device, o_pad)
         elif o_pad == o:
@@ -122,6 +196,29 @@ class _ConvTc(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3))
         return dx, dw, db, None, None
+
+
+class packed_weights:
+    """Context of one training forward: `with packed_weights(model): ...` packs every conv weight in one launch when a
+    WeightPacker is attached to the model and makes the convs inside the block use the packed operands."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.packer = model.__dict__.get("_yx_train_packer")
+
+    def __enter__(self):
+        global _packer
+        self.prev = _packer
+        if self.packer is not None and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == self.packer.dtype:
+            self.packer.pack()
+            _packer = self.packer
+        return self
+
+    def __exit__(self, *exc):
+        global _packer
+        if self.packer is not None:
+            self.packer.active = False
+        _packer = self.prev
+        return False
 
 
 def conv2d(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:

@@ -136,8 +136,11 @@ class YoloxModule(nn.Module):
     def forward(self, x, targets=None):
         if self.training:
             assert targets is not None
-            fpn_outs = self.backbone._train_forward(x)
-            loss, iou_loss, conf_loss, cls_loss, l1_loss, num_fg = self.head(fpn_outs, targets, x)
+            from .train_conv import packed_weights
+
+            with packed_weights(self):         # one launch packs every conv weight when a WeightPacker is attached
+                fpn_outs = self.backbone._train_forward(x)
+                loss, iou_loss, conf_loss, cls_loss, l1_loss, num_fg = self.head(fpn_outs, targets, x)
             return {"total_loss": loss, "iou_loss": iou_loss, "l1_loss": l1_loss, "conf_loss": conf_loss,
                     "cls_loss": cls_loss, "num_fg": num_fg}
         p = next(self.parameters())

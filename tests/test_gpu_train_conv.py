@@ -232,3 +232,59 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(cuda):
             torch.testing.assert_close(a, 2 * b, rtol=1e-3, atol=2e-3 * float(b.abs().max()) + 1e-9)
     finally:
         train_conv.set_direct_grads(False)
+
+
+def test_batched_weight_packing_equals_per_layer_packing(cuda):
+    """WeightPacker: one launch packs every conv weight; the training forward / backward that uses the packed operands gives
+    exactly the loss and gradients of the per-layer packing (same kernels, same operands)."""
+    torch.manual_seed(0)
+    cfg = yx.YoloxConfig("packer", depth=0.33, width=0.25)
+    m = cfg.get_model().to(cuda).train().to(memory_format=torch.channels_last)
+    x = torch.from_numpy(syn.images(2, 128, 128, seed=3)).to(cuda).contiguous(memory_format=torch.channels_last)
+    lab = torch.from_numpy(syn.labels(2, max_gt=8, seed=5, size=128.0, counts=[3, 5])).to(cuda)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+
+    def run():
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x, lab)
+        out["total_loss"].backward()
+        return out["total_loss"].detach().clone(), [p.grad.clone() for p in m.parameters()]
+
+    l0, g0 = run()
+    packer = train_conv.attach_packer(m, torch.bfloat16)
+    try:
+        l1, g1 = run()
+        assert len(packer.entries) > 50 and not packer.active
+        w0 = next(iter(packer.entries.values()))
+        wf, _ = ops.pack_train_weights(w0[0].detach(), torch.bfloat16, w0[1].shape[0], w0[1].shape[2], True)
+        assert torch.equal(wf, w0[1])
+        assert torch.equal(l0, l1)
+        for a, b in zip(g1, g0):
+            torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-3 * float(b.abs().max()) + 1e-9)
+    finally:
+        m.__dict__.pop("_yx_train_packer", None)
+
+
+def test_bn_backward_reads_a_channel_slice_of_the_cat_gradient_in_place(cuda):
+    """BaseConv outputs that feed torch.cat (CspLayer, YoloPafpn): the BatchNorm backward reads its slice of the cat's gradient
+    with a pixel stride instead of a copy; same result as torch's modules."""
+    from pixeltable_yolox_b200.network_blocks import _FusedBnAct
+
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(2, 32, 20, 20, generator=g).bfloat16().to(cuda).contiguous(memory_format=torch.channels_last)
+    other = torch.randn(2, 16, 20, 20, generator=g).bfloat16().to(cuda).contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(32, eps=1e-3, momentum=0.03).to(cuda).train()
+    gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    x = x0.clone().requires_grad_(True)
+    y = _FusedBnAct.apply(x, gam, bet, bn.running_mean.clone(), bn.running_var.clone(), bn.eps, bn.momentum, "silu")
+    z = torch.cat([other, y], 1)
+    go = torch.randn(z.shape, generator=g).bfloat16().to(cuda).contiguous(memory_format=torch.channels_last)
+    z.backward(go)
+    xr = x0.float().requires_grad_(True)
+    yr = torch.nn.functional.silu(bn(xr))
+    yr.backward(go[:, 16:].float())
+    torch.testing.assert_close(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(gam.grad, bn.weight.grad, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(bet.grad, bn.bias.grad, rtol=2e-2, atol=2e-2)
