@@ -898,6 +898,7 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
         loss = out["total_loss"]
         opt.zero_grad()
         loss.backward()
+        opt.join()                                 # side-stream weight gradients rejoin the captured stream
         if world > 1:
             flat = opt.flat_grad                   # every .grad is a view into it: the all-reduce needs no flatten / scatter
         else:

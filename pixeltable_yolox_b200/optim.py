@@ -108,6 +108,12 @@ class FusedSgdEma:
         self._chunks = torch.from_numpy(np.array(chunks, dtype=np.int32).reshape(-1, 2)).to(self._dev)
         self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
 
+    def join(self):
+        if self.flat_grad is not None:
+            from . import train_conv
+
+            train_conv.join_wgrad(self._dev)       # side-stream weight gradients land before the update reads them
+
     def zero_grad(self):
         """Keeps the gradient storage (the pointer table stays valid): grads are zeroed in place."""
         if self.flat_grad is not None:
@@ -137,12 +143,14 @@ class FusedSgdEma:
         """The launch to record inside torch.cuda.graph(): hyper-parameters come from `self.hyper` at run time."""
         if self._table is None:
             raise RuntimeError("FusedSgdEma.step_captured: run at least one eager step() first (pointer table, momentum init)")
+        self.join()
         ops.sgd_ema_step(self._table, self._chunks, self.CHUNK, self.lr, self.momentum, self.nesterov, False, 0.0, self.hyper)
 
     @torch.no_grad()
     def step(self, lr: Optional[float] = None):
         if lr is not None:
             self.lr = float(lr)
+        self.join()
         if self._table is None or any(p.grad is None or p.grad.data_ptr() != q for p, q in zip(self.params, self._grad_ptrs)):
             if any(p.grad is None for p in self.params):
                 raise RuntimeError("FusedSgdEma.step: a trainable parameter has no gradient")

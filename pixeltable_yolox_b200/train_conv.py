@@ -39,6 +39,30 @@ def direct_grads() -> bool:
     return _direct_grads
 
 
+# With direct gradient accumulation the weight-gradient launches have no consumer before the optimizer step, so they run on a
+# side stream (one per device) next to the backward's critical chain  BatchNorm backward -> dgrad -> BatchNorm backward ...:
+# every kernel of an 8-image step is a fraction of a wave, so the two chains overlap (a CUDA-graph capture records the fork
+# and the join as graph branches). The wgrad inputs (saved activation, output gradient) are kept referenced until
+# `join_wgrad()` so that the caching allocator cannot hand their memory to the main stream while the side stream reads it.
+_wgrad_side = {}
+
+
+def _side(dev: torch.device):
+    ent = _wgrad_side.get(dev)
+    if ent is None:
+        ent = _wgrad_side[dev] = [torch.cuda.Stream(dev), []]
+    return ent
+
+
+def join_wgrad(dev: Optional[torch.device] = None) -> None:
+    """Make the current stream wait for the side-stream weight gradients (call before reading .grad: FusedSgdEma.step does)."""
+    for d, (stream, pending) in _wgrad_side.items():
+        if dev is None or d == dev:
+            if pending:
+                torch.cuda.current_stream(d).wait_stream(stream)
+                pending.clear()
+
+
 class WeightPacker:
     """All conv weights of a model packed to their 16-bit forward / dgrad operands in ONE launch per step
     (yx_pack_train_weights_multi) instead of one launch per layer. `attach(model, dtype)` makes `YoloxModule.forward` call
@@ -185,7 +209,14 @@ class _ConvTc(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
             if _direct_grads and weight.grad is not None:
-                ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
+                if os.environ.get("YX_WGRAD_OVERLAP", "1") != "0":
+                    stream, pending = _side(xh.device)
+                    stream.wait_event(torch.cuda.current_stream(xh.device).record_event())
+                    with torch.cuda.stream(stream):
+                        ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
+                    pending.append((xh, dyh))
+                else:
+                    ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
             else:
                 dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
         if ctx.needs_input_grad[0]:

@@ -213,6 +213,7 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(cuda):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = m(x, lab)
         out["total_loss"].backward()
+        train_conv.join_wgrad()                     # direct mode: the weight gradients run on a side stream
         return [p.grad.clone() for p in m.parameters()]
 
     want = run()

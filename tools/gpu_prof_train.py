@@ -1,5 +1,6 @@
 """Kernel-time breakdown of one training step (yolox_s, 8 images, bf16 autocast) with torch.profiler: which part of the
 torch / cuDNN side the step spends its GPU time in. usage: python tools/gpu_prof_train.py"""
+import os
 import sys
 from pathlib import Path
 
@@ -20,7 +21,11 @@ cfg, model = bench.build_model(args, dev)
 model.train()
 if fmt == "channels_last":
     model = model.to(memory_format=torch.channels_last)
-opt = FusedSgdEma(model, lr=1e-3)
+direct = os.environ.get("YX_TRAIN_CONV", "1") != "0"
+opt = FusedSgdEma(model, lr=1e-3, direct_grads=direct)
+if direct:
+    from pixeltable_yolox_b200 import train_conv
+    train_conv.attach_packer(model, torch.bfloat16)
 x, lab, _ = bench.train_batch(args, 0, 8)
 x, lab = x.to(dev), lab.to(dev)
 if fmt == "channels_last":
