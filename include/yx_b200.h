@@ -114,6 +114,11 @@ typedef struct yx_conv_desc {
   int32_t* head_counts;
   float head_conf_thre;
   int32_t head_xyxy;
+  /* YX_EPI_STORE on the tcgen05 path, depth-to-space store (0 = off): out_c == 4 * shuffle2_c, `out` is an NHWC buffer of
+   * spatial size 2*out_h x 2*out_w, and channel c of output pixel (b, y, x) is written to pixel (b, 2y + (q >> 1), 2x + (q & 1)),
+   * channel c - q * shuffle2_c, q = c / shuffle2_c. With the sub-pixel weights of yx_pack_train_weights(subpixel = 1) this
+   * makes the dgrad of a 3x3 stride-2 conv ONE stride-1 conv over dy. No res / ups / out2. */
+  int32_t shuffle2_c;
 } yx_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM for bf16/fp16; routes YX_FP32 to the SIMT kernel. */
@@ -373,7 +378,11 @@ int yx_bn_act_train_bwd(const void* x, const void* dy, int32_t dtype, int32_t ch
  *             channel counts padded to multiples of 16: in_c, out_c). accumulate != 0: dw += (gradient accumulation straight
  *             into the parameter's .grad, what autograd's AccumulateGrad would do with one more launch per parameter).
  *   yx_pack_train_weights: fp32 weight (same stride convention) -> w_fwd [o_pad][taps][i_pad] and
- *             w_dgrad [i_pad][taps][o_pad] in `dtype` (either may be NULL), zero padded.
+ *             w_dgrad [i_pad][taps][o_pad] in `dtype` (either may be NULL), zero padded. subpixel != 0 (3x3 stride-2 convs with
+ *             an even input size): w_dgrad is instead [4 * i_pad][9][o_pad], the four sub-pixel phases of the transposed conv as
+ *             one stride-1 3x3 conv over dy (phase q = 2 * (row parity) + column parity of the dx pixel; tap (r', s') reads
+ *             dy[a + r' - 1, b + s' - 1]; only the positions that carry a weight are written: zero the buffer once), to be run
+ *             with yx_conv_desc.shuffle2_c = i_pad -- no zero-stuffed copy, a quarter of the pixels.
  * x, dy: NHWC, 16-bit, per-pixel strides x_ld / dy_ld (multiples of 8), 16-byte aligned. ksize 1 | 3, stride 1 | 2.
  * ------------------------------------------------------------------------------------------ */
 int64_t yx_conv_wgrad_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, int32_t in_c, int32_t out_h, int32_t out_w,
@@ -383,9 +392,9 @@ int yx_conv_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, in
                   int32_t in_c_real, int32_t out_c_real, float* dw, int64_t dw_stride_o, int64_t dw_stride_i, int64_t dw_stride_tap,
                   int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, int64_t stride_tap, int32_t o, int32_t i, int32_t taps,
-                          int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t dtype, void* stream);
-/* yx_pack_train_weights for every conv of a model in one launch. table: device int64 [n, 11] rows = w ptr | stride_o |
- * stride_i | stride_tap | o | i | taps | o_pad | i_pad | w_fwd ptr | w_dgrad ptr (0: skip); chunks: device int32 [n_chunks, 2]
+                          int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t subpixel, int32_t dtype, void* stream);
+/* yx_pack_train_weights for every conv of a model in one launch. table: device int64 [n, 12] rows = w ptr | stride_o |
+ * stride_i | stride_tap | o | i | taps | o_pad | i_pad | w_fwd ptr | w_dgrad ptr (0: skip) | subpixel; chunks: device int32 [n_chunks, 2]
  * rows = (tensor index, first element of its [o_pad][taps][i_pad] index space), one CTA per chunk of chunk_elems elements. */
 int yx_pack_train_weights_multi(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, int32_t dtype,
                                 void* stream);

@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_ld", C.c_int64),
         ("head_cand", C.c_void_p), ("head_keys", C.c_void_p), ("head_counts", C.c_void_p),
         ("head_conf_thre", C.c_float), ("head_xyxy", C.c_int32),
+        ("shuffle2_c", C.c_int32),
     ]
 
 
@@ -98,7 +99,7 @@ SIGNATURES = {
     "yx_bn_act_train_bwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "yx_conv_wgrad_workspace_bytes": (_I64, [_I32] * 9),
     "yx_conv_wgrad": (C.c_int, [_P, _I64, _P, _I64] + [_I32] * 12 + [_P, _I64, _I64, _I64, _I32, _P, _I64, _P]),
-    "yx_pack_train_weights": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "yx_pack_train_weights": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P]),
     "yx_spp_maxpool_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "yx_pack_train_weights_multi": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
     "yx_dilate2": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -73,7 +73,7 @@ int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld,
                  int out_h, int out_w, int out_c, int ksize, int stride, int in_c_real, int out_c_real, float* dw, long long dw_so,
                  long long dw_si, long long dw_st, int accumulate, void* ws, long long ws_bytes, cudaStream_t stream);
 int pack_train_weights_launch(const float* w, long long so, long long si, long long st, int o, int i, int taps, int o_pad, int i_pad,
-                              void* wf, void* wd, int dtype, cudaStream_t stream);
+                              void* wf, void* wd, int subpixel, int dtype, cudaStream_t stream);
 int dilate2_launch(const void* dy, void* z, int batch, int oh, int ow, int zh, int zw, int c, cudaStream_t stream);
 int pack_train_weights_multi_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, int dtype, cudaStream_t stream);
 int spp_bwd_launch(const void* cat, long long ld, const void* dout, long long dld, float* dx32, int batch, int h, int w, int c,
@@ -476,10 +476,10 @@ int yx_conv_wgrad(const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, in
 }
 
 int yx_pack_train_weights(const float* w, int64_t stride_o, int64_t stride_i, int64_t stride_tap, int32_t o, int32_t i, int32_t taps,
-                          int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t dtype, void* stream) {
+                          int32_t o_pad, int32_t i_pad, void* w_fwd, void* w_dgrad, int32_t subpixel, int32_t dtype, void* stream) {
   int rc = require_device();
   if (rc) return rc;
-  return pack_train_weights_launch(w, stride_o, stride_i, stride_tap, o, i, taps, o_pad, i_pad, w_fwd, w_dgrad, dtype, (cudaStream_t)stream);
+  return pack_train_weights_launch(w, stride_o, stride_i, stride_tap, o, i, taps, o_pad, i_pad, w_fwd, w_dgrad, subpixel, dtype, (cudaStream_t)stream);
 }
 
 int yx_spp_maxpool_bwd(const void* cat, int64_t ld, const void* dout, int64_t dout_ld, float* dx32, int32_t batch, int32_t h,

@@ -543,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int hl0 = 0, wl0 = 0;
     if (!p.flat) { hl0 = row / p.pitch; wl0 = row - hl0 * p.pitch; }
     const bool row_ok = p.flat || (hl0 < p.th && wl0 < p.tw);
-    const bool need_coords = p.flat && (p.epi.ups != nullptr || HEAD);
+    const bool need_coords = (p.flat && (p.epi.ups != nullptr || HEAD)) || p.epi.shuf_c != 0;
     int as = grp % p.acc_stages;
     uint32_t aphase = (uint32_t)((grp / p.acc_stages) & 1);
     [[maybe_unused]] bool tr7 = false, tr8 = false;
@@ -764,6 +764,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint16_t* orow2 = p.epi.out2 ? (uint16_t*)p.epi.out2 + pix * p.epi.out2_ld + (n_tile * p.BN - p.epi.out2_begin) : nullptr;
       const int split = orow2 ? p.epi.out2_begin - n_tile * p.BN : 0x7fffffff;
       const uint16_t* rrow = p.epi.res ? (const uint16_t*)p.epi.res + pix * p.epi.res_ld + n_tile * p.BN : nullptr;
+      // depth-to-space store (dgrad of a stride-2 conv as one sub-pixel conv): channel block q goes to pixel (2y + q/2, 2x + q%2)
+      const int sc = p.epi.shuf_c;
+      auto dst_of = [&](int c) -> uint16_t* {
+        if (!sc) return (c >= split ? orow2 : orow) + c;
+        const int cg = n_tile * p.BN + c;
+        const int q = cg >= 2 * sc ? (cg >= 3 * sc ? 3 : 2) : (cg >= sc ? 1 : 0);
+        const long long up = ((long long)b * 2 * p.epi.out_h + 2 * ho + (q >> 1)) * (2 * p.epi.out_w) + 2 * wo + (q & 1);
+        return (uint16_t*)p.epi.out + up * p.epi.out_ld + (cg - q * sc);
+      };
       for (int c = 0; c < p.BN; c += 32) {
         const bool two = (c + 16 < p.BN);
         uint32_t ra[16], rb[16];
@@ -776,10 +785,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if (valid) {
-          epi_tc_chunk<FP16, SILU>(p.epi, ra, tbias + c, rrow ? qa : nullptr, (c >= split ? orow2 : orow) + c, b, ho, wo, n_tile * p.BN + c);
+          epi_tc_chunk<FP16, SILU>(p.epi, ra, tbias + c, rrow ? qa : nullptr, dst_of(c), b, ho, wo, n_tile * p.BN + c);
           if (two)
-            epi_tc_chunk<FP16, SILU>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, (c + 16 >= split ? orow2 : orow) + c + 16, b, ho, wo,
-                         n_tile * p.BN + c + 16);
+            epi_tc_chunk<FP16, SILU>(p.epi, rb, tbias + c + 16, rrow ? qb : nullptr, dst_of(c + 16), b, ho, wo, n_tile * p.BN + c + 16);
         }
       }
       tc_fence_before();
@@ -845,6 +853,7 @@ int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
   e->head_nc = d->head_nc; e->head_decode = d->head_decode; e->head_stride = d->head_stride;
   e->head_cand = d->head_cand; e->head_keys = (unsigned long long*)d->head_keys; e->head_counts = d->head_counts;
   e->head_conf = d->head_conf_thre; e->head_xyxy = d->head_xyxy;
+  e->shuf_c = d->shuffle2_c;
   if (d->epilogue == YX_EPI_HEAD) {
     YX_REQUIRE(d->head_out != nullptr, YX_ERR_INVALID_ARG, "conv(head): head_out is null");
     YX_REQUIRE(5 + d->head_nc <= d->out_c, YX_ERR_INVALID_ARG, "conv(head): out_c=%d < 5+nc=%d", d->out_c, 5 + d->head_nc);
@@ -862,6 +871,12 @@ int fill_epi_params(const yx_conv_desc* d, EpiParams* e) {
     const int al = d->dtype == YX_FP32 ? 4 : 8;
     YX_REQUIRE(d->out_ld % al == 0 && ((uintptr_t)d->out & 15) == 0, YX_ERR_INVALID_ARG,
                "conv: out must be 16-byte aligned with out_ld %% %d == 0", al);
+    if (d->shuffle2_c) {
+      YX_REQUIRE(d->dtype != YX_FP32, YX_ERR_UNSUPPORTED, "conv: the depth-to-space store exists on the tcgen05 path only");
+      YX_REQUIRE(d->shuffle2_c > 0 && d->shuffle2_c % 16 == 0 && d->out_c == 4 * d->shuffle2_c && d->out_ld >= d->shuffle2_c &&
+                     !d->res && !d->ups && !d->out2,
+                 YX_ERR_INVALID_ARG, "conv: shuffle2_c must be a multiple of 16 with out_c == 4 * shuffle2_c, no res / ups / out2");
+    } else
     YX_REQUIRE(d->out_ld >= (d->out2 ? d->out2_begin : d->out_c), YX_ERR_INVALID_ARG, "conv: out_ld < out_c");
     if (d->out2) YX_REQUIRE(d->out2_ld >= d->out_c - d->out2_begin, YX_ERR_INVALID_ARG, "conv: out2_ld too small");
     if (d->res) YX_REQUIRE(d->res_ld % al == 0 && ((uintptr_t)d->res & 15) == 0, YX_ERR_INVALID_ARG, "conv: res misaligned");

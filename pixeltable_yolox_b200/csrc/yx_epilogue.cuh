@@ -22,6 +22,7 @@ struct EpiParams {
   float head_stride;
   float* head_cand; unsigned long long* head_keys; int* head_counts;   // fused score filter (null: off)
   float head_conf; int head_xyxy;
+  int shuf_c;     // depth-to-space store (yx_conv_desc.shuffle2_c), tcgen05 path only
 };
 
 #ifdef __CUDACC__

@@ -212,12 +212,25 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int kspli
   }
 }
 
+// index of weight element (oo, tap = 3r + s, ii) in the dgrad operand.
+//   rotated form  [i_pad][taps][o_pad]: tap reversed.
+//   sub-pixel form [4 * i_pad][9][o_pad] (3x3 stride 2, pad 1): dx[2a + pa] = sum_oy dy[oy] W[r] with 2 oy - 1 + r = 2a + pa, i.e.
+//   pa = 0: r = 1 reads dy[a]; pa = 1: r = 2 reads dy[a], r = 0 reads dy[a + 1]. As a pad-1 3x3 conv over dy (tap r' reads
+//   dy[a + r' - 1]): r = 1 -> (pa 0, r' 1), r = 2 -> (pa 1, r' 1), r = 0 -> (pa 1, r' 2); same for columns.
+__device__ __forceinline__ long long dgrad_index(int oo, int tp, int ii, int taps, int o_pad, int i_pad, int subpixel) {
+  if (!subpixel) return ((long long)ii * taps + (taps - 1 - tp)) * o_pad + oo;
+  const int r = tp / 3, s = tp - 3 * r;
+  const int pa = r == 1 ? 0 : 1, rr = r == 0 ? 2 : 1;
+  const int pb = s == 1 ? 0 : 1, ss = s == 0 ? 2 : 1;
+  return ((long long)((pa * 2 + pb) * i_pad + ii) * 9 + (rr * 3 + ss)) * o_pad + oo;
+}
+
 // fp32 conv weight (any strides) -> 16-bit packed operands of yx_conv_bn_act_fwd:
 //   wf [o_pad][taps][i_pad]                 forward:  y = conv(x, W)
 //   wd [i_pad][taps][o_pad], tap reversed   dgrad:    dx = conv(dy or its zero-stuffed copy, W rotated by 180 degrees, o <-> i)
 template <typename T>
 __global__ void pack_train_weights_kernel(const float* __restrict__ w, long long so, long long si, long long st, int o, int i,
-                                          int taps, int o_pad, int i_pad, T* __restrict__ wf, T* __restrict__ wd) {
+                                          int taps, int o_pad, int i_pad, T* __restrict__ wf, T* __restrict__ wd, int subpixel) {
   pdl_wait();
   pdl_launch_dependents();
   const long long total = (long long)o_pad * taps * i_pad;
@@ -229,18 +242,19 @@ __global__ void pack_train_weights_kernel(const float* __restrict__ w, long long
     const float v = (oo < o && ii < i) ? w[(long long)oo * so + (long long)ii * si + (long long)t * st] : 0.f;
     const T h = Cvt<T>::from_f(v);
     if (wf) wf[e] = h;
-    if (wd) wd[((long long)ii * taps + (taps - 1 - t)) * o_pad + oo] = h;
+    if (wd) wd[dgrad_index(oo, t, ii, taps, o_pad, i_pad, subpixel)] = h;
   }
 }
 
-// every conv weight of the model in ONE launch (83 launches of ~4 us each otherwise): table rows (int64 x 11) =
-// src ptr | stride_o | stride_i | stride_tap | o | i | taps | o_pad | i_pad | wf ptr | wd ptr; chunks rows = (tensor, first
+// every conv weight of the model in ONE launch (83 launches of ~4 us each otherwise): table rows (int64 x 12) =
+// src ptr | stride_o | stride_i | stride_tap | o | i | taps | o_pad | i_pad | wf ptr | wd ptr | subpixel; chunks rows = (tensor, first
 // element of the [o_pad][taps][i_pad] index space); one CTA per chunk of chunk_elems elements.
 template <typename T>
 __global__ void pack_train_weights_multi_kernel(const long long* __restrict__ table, const int* __restrict__ chunks, int chunk_elems) {
   const int t = chunks[2 * blockIdx.x];
   const long long e0 = chunks[2 * blockIdx.x + 1];
-  const long long* r = table + (long long)t * 11;
+  const long long* r = table + (long long)t * 12;
+  const int subpixel = (int)r[11];
   const float* w = reinterpret_cast<const float*>(r[0]);
   const long long so = r[1], si = r[2], st = r[3];
   const int o = (int)r[4], i = (int)r[5], taps = (int)r[6], o_pad = (int)r[7], i_pad = (int)r[8];
@@ -256,7 +270,7 @@ __global__ void pack_train_weights_multi_kernel(const long long* __restrict__ ta
     const float v = (oo < o && ii < i) ? w[(long long)oo * so + (long long)ii * si + (long long)tp * st] : 0.f;
     const T h = Cvt<T>::from_f(v);
     if (wf) wf[e] = h;
-    if (wd) wd[((long long)ii * taps + (taps - 1 - tp)) * o_pad + oo] = h;
+    if (wd) wd[dgrad_index(oo, tp, ii, taps, o_pad, i_pad, subpixel)] = h;
   }
 }
 
@@ -447,18 +461,19 @@ int wgrad_launch(const void* x, long long x_ld, const void* dy, long long dy_ld,
 }
 
 int pack_train_weights_launch(const float* w, long long so, long long si, long long st, int o, int i, int taps, int o_pad, int i_pad,
-                              void* wf, void* wd, int dtype, cudaStream_t stream) {
+                              void* wf, void* wd, int subpixel, int dtype, cudaStream_t stream) {
   YX_REQUIRE(w && (wf || wd), YX_ERR_INVALID_ARG, "pack_train_weights: null pointer");
+  YX_REQUIRE(!subpixel || taps == 9, YX_ERR_INVALID_ARG, "pack_train_weights: the sub-pixel dgrad form is for 3x3 convs");
   YX_REQUIRE(dtype == YX_BF16 || dtype == YX_FP16, YX_ERR_UNSUPPORTED, "pack_train_weights: 16-bit destinations only");
   YX_REQUIRE(o > 0 && i > 0 && o <= o_pad && i <= i_pad && (taps == 1 || taps == 9), YX_ERR_INVALID_ARG, "pack_train_weights: shape");
   const long long total = (long long)o_pad * taps * i_pad;
   const int grid = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
   if (dtype == YX_BF16)
     YX_CUDA(launch_pdl(pack_train_weights_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, w, so, si, st, o, i, taps, o_pad, i_pad,
-                       reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd)));
+                       reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd), subpixel));
   else
     YX_CUDA(launch_pdl(pack_train_weights_kernel<__half>, dim3(grid), dim3(256), 0, stream, w, so, si, st, o, i, taps, o_pad, i_pad,
-                       reinterpret_cast<__half*>(wf), reinterpret_cast<__half*>(wd)));
+                       reinterpret_cast<__half*>(wf), reinterpret_cast<__half*>(wd), subpixel));
   return YX_OK;
 }
 

@@ -76,7 +76,7 @@ class View:
 def make_conv_desc(
     x: View, w: torch.Tensor, bias: torch.Tensor, out: Optional[View], ksize: int, stride: int, act: int,
     res: Optional[View] = None, ups: Optional[View] = None, head: Optional[dict] = None,
-    out2: Optional[View] = None, out2_begin: int = 0,
+    out2: Optional[View] = None, out2_begin: int = 0, shuffle2_c: int = 0,
 ) -> ConvDesc:
     pad = (ksize - 1) // 2
     oh = (x.H + 2 * pad - ksize) // stride + 1
@@ -96,8 +96,13 @@ def make_conv_desc(
     d.bias = bias.data_ptr()
     if head is None:
         assert out is not None and out.t.dtype == x.t.dtype
-        assert out.c == d.out_c or (out2 is not None and out.c == out2_begin), (out.c, d.out_c, out2_begin)
-        assert (out.B, out.H, out.W) == (x.B, oh, ow), ((out.B, out.H, out.W), (x.B, oh, ow))
+        if shuffle2_c:                      # depth-to-space store: out is the 2x larger map with a quarter of the channels
+            assert d.out_c == 4 * shuffle2_c and out.c == shuffle2_c and (out.B, out.H, out.W) == (x.B, 2 * oh, 2 * ow)
+            assert res is None and ups is None and out2 is None
+            d.shuffle2_c = shuffle2_c
+        else:
+            assert out.c == d.out_c or (out2 is not None and out.c == out2_begin), (out.c, d.out_c, out2_begin)
+            assert (out.B, out.H, out.W) == (x.B, oh, ow), ((out.B, out.H, out.W), (x.B, oh, ow))
         d.epilogue = _lib.YX_EPI_STORE
         d.out, d.out_ld = out.ptr, out.ld
         if res is not None:
@@ -126,9 +131,9 @@ def make_conv_desc(
 
 
 def conv_bn_act(x: View, w, bias, out, ksize, stride, act, res=None, ups=None, head=None, simt=False,
-                out2=None, out2_begin=0) -> None:
+                out2=None, out2_begin=0, shuffle2_c=0) -> None:
     require_cuda(x.t, "conv_bn_act")
-    d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head, out2, out2_begin)
+    d = make_conv_desc(x, w, bias, out, ksize, stride, act, res, ups, head, out2, out2_begin, shuffle2_c)
     same_device(x.t.device, "conv_bn_act", w=w, bias=bias, out=None if out is None else out.t,
                 res=None if res is None else res.t, ups=None if ups is None else ups.t, out2=None if out2 is None else out2.t)
     fn = lib().yx_conv_bn_act_fwd_simt if simt else lib().yx_conv_bn_act_fwd
@@ -634,19 +639,25 @@ def _weight_strides(w: torch.Tensor):
     return so, si, sw
 
 
-def pack_train_weights(weight: torch.Tensor, dtype: torch.dtype, o_pad: int, i_pad: int, want_dgrad: bool):
-    """fp32 conv weight -> (w_fwd [o_pad, taps, i_pad], w_dgrad [i_pad, taps, o_pad] or None) in `dtype`, one launch."""
+def pack_train_weights(weight: torch.Tensor, dtype: torch.dtype, o_pad: int, i_pad: int, want_dgrad: bool, subpixel: bool = False):
+    """fp32 conv weight -> (w_fwd [o_pad, taps, i_pad], w_dgrad [i_pad, taps, o_pad] or None) in `dtype`, one launch.
+    subpixel (3x3 stride-2 convs): w_dgrad is [4 * i_pad, 9, o_pad], the transposed conv as one stride-1 conv over dy whose
+    output is stored depth-to-space (conv_bn_act(..., shuffle2_c=i_pad))."""
     require_cuda(weight, "pack_train_weights")
     dev = weight.device
     assert weight.dtype == torch.float32 and weight.dim() == 4
     o, i, kh, kw = weight.shape
     taps = kh * kw
     wf = torch.empty((o_pad, taps, i_pad), dtype=dtype, device=dev)
-    wd = torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev) if want_dgrad else None
+    wd = None
+    if want_dgrad:
+        wd = (torch.zeros((4 * i_pad, 9, o_pad), dtype=dtype, device=dev) if subpixel
+              else torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev))
     so, si, st = _weight_strides(weight)
     with on_device(dev):
         check(lib().yx_pack_train_weights(weight.data_ptr(), so, si, st, o, i, taps, o_pad, i_pad, wf.data_ptr(),
-                                          0 if wd is None else wd.data_ptr(), dtype_code(dtype), stream_ptr(dev)),
+                                          0 if wd is None else wd.data_ptr(), 1 if subpixel else 0, dtype_code(dtype),
+                                          stream_ptr(dev)),
               "pack_train_weights")
     return wf, wd
 

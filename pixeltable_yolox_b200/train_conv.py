@@ -89,10 +89,12 @@ class WeightPacker:
             o, i, taps = w.shape[0], w.shape[1], k[0] * k[0]
             o_pad, i_pad = _pad16(o), _pad16(i)
             wf = torch.empty((o_pad, taps, i_pad), dtype=dtype, device=dev)
-            wd = torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev)
+            sub = s[0] == 2            # stride-2 dgrad as one sub-pixel conv: zeros of the buffer are written once, here
+            wd = (torch.zeros((4 * i_pad, 9, o_pad), dtype=dtype, device=dev) if sub
+                  else torch.empty((i_pad, taps, o_pad), dtype=dtype, device=dev))
             so, si, st = ops._weight_strides(w)
             t = len(rows)
-            rows.append((w.data_ptr(), so, si, st, o, i, taps, o_pad, i_pad, wf.data_ptr(), wd.data_ptr()))
+            rows.append((w.data_ptr(), so, si, st, o, i, taps, o_pad, i_pad, wf.data_ptr(), wd.data_ptr(), 1 if sub else 0))
             chunks += [(t, e) for e in range(0, o_pad * taps * i_pad, self.CHUNK)]
             self.entries[id(w)] = (w, wf, wd, w.data_ptr())
         if not rows:
@@ -183,11 +185,14 @@ class _ConvTc(torch.autograd.Function):
         pad = (k - 1) // 2
         OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         xh = _pad_channels(x.detach().to(dtype), i_pad)
+        # stride-2 dgrad: one sub-pixel conv over dy with a depth-to-space store when the input size is even, else the
+        # rotated weights on the zero-stuffed dy
+        sub = stride == 2 and H % 2 == 0 and W % 2 == 0 and os.environ.get("YX_DGRAD_SUBPIXEL", "1") != "0"
         pre = _packer.lookup(weight, dtype) if _packer is not None else None
-        if pre is not None:
+        if pre is not None and (stride == 1 or sub):
             wf, wd = pre
         else:
-            wf, wd = ops.pack_train_weights(weight.detach(), dtype, o_pad, i_pad, want_dgrad=ctx.needs_input_grad[0])
+            wf, wd = ops.pack_train_weights(weight.detach(), dtype, o_pad, i_pad, want_dgrad=ctx.needs_input_grad[0], subpixel=sub)
         if bias is None:
             b = _zeros(x.device, o_pad)
         elif o_pad == o:
@@ -198,13 +203,13 @@ class _ConvTc(torch.autograd.Function):
         y = torch.empty((B, o_pad, OH, OW), dtype=dtype, device=x.device, memory_format=torch.channels_last)
         ops.conv_bn_act(ops._nhwc(xh), wf, b, ops._nhwc(y), k, stride, YX_ACT_NONE)
         ctx.save_for_backward(xh, wd, weight)
-        ctx.geom = (o, i, k, stride, o_pad, i_pad, H, W, x.dtype, bias is not None)
+        ctx.geom = (o, i, k, stride, o_pad, i_pad, H, W, x.dtype, bias is not None, sub)
         return y if o_pad == o else y[:, :o]
 
     @staticmethod
     def backward(ctx, dy):
         xh, wd, weight = ctx.saved_tensors
-        o, i, k, stride, o_pad, i_pad, H, W, x_dtype, has_bias = ctx.geom
+        o, i, k, stride, o_pad, i_pad, H, W, x_dtype, has_bias, sub = ctx.geom
         dyh = _pad_channels(dy.to(xh.dtype), o_pad)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
@@ -220,9 +225,12 @@ class _ConvTc(torch.autograd.Function):
             else:
                 dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
         if ctx.needs_input_grad[0]:
-            src = dyh if stride == 1 else ops.dilate2(dyh, H, W)
             dxp = torch.empty((xh.shape[0], i_pad, H, W), dtype=xh.dtype, device=xh.device, memory_format=torch.channels_last)
-            ops.conv_bn_act(ops._nhwc(src), wd, _zeros(xh.device, i_pad), ops._nhwc(dxp), k, 1, YX_ACT_NONE)
+            if sub:
+                ops.conv_bn_act(ops._nhwc(dyh), wd, _zeros(xh.device, 4 * i_pad), ops._nhwc(dxp), 3, 1, YX_ACT_NONE, shuffle2_c=i_pad)
+            else:
+                src = dyh if stride == 1 else ops.dilate2(dyh, H, W)
+                ops.conv_bn_act(ops._nhwc(src), wd, _zeros(xh.device, i_pad), ops._nhwc(dxp), k, 1, YX_ACT_NONE)
             dx = (dxp if i_pad == i else dxp[:, :i]).to(x_dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3))

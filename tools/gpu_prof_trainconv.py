@@ -77,7 +77,11 @@ for (ci, co, H, W, k, s), cnt in shapes.items():
     if s == 1:
         t_d = timeit(lambda: ops.conv_bn_act(ops._nhwc(dy), wd, zb_i, ops._nhwc(dx), k, 1, YX_ACT_NONE))
     else:
-        t_d = timeit(lambda: ops.conv_bn_act(ops._nhwc(ops.dilate2(dy, H, W)), wd, zb_i, ops._nhwc(dx), k, 1, YX_ACT_NONE))
+        t_dil = timeit(lambda: ops.conv_bn_act(ops._nhwc(ops.dilate2(dy, H, W)), wd, zb_i, ops._nhwc(dx), k, 1, YX_ACT_NONE))
+        _, wd4 = ops.pack_train_weights(w, torch.bfloat16, cop, cip, True, subpixel=True)
+        zb4 = torch.zeros(4 * cip, device=dev)
+        t_d = timeit(lambda: ops.conv_bn_act(ops._nhwc(dy), wd4, zb4, ops._nhwc(dx), 3, 1, YX_ACT_NONE, shuffle2_c=cip))
+        print(f"      stride-2 dgrad: zero-stuffed {t_dil:.1f} us, sub-pixel conv {t_d:.1f} us")
     t_w = timeit(lambda: ops.conv_wgrad(xx, dy, w, k, s))
     wb = w.bfloat16()
     c_f = timeit(lambda: F.conv2d(xx, wb, None, s, pad))
