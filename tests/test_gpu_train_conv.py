@@ -140,40 +140,45 @@ def test_train_conv_under_autocast_matches_cudnn_path(cuda, monkeypatch):
 
 
 def test_network_forward_backward_tcgen05_convs_track_fp32_like_cudnn_does(cuda, monkeypatch):
-    """Backbone + neck + head towers + prediction convs of a small YOLOX in training mode, with a smooth loss (mean square of
+    """Backbone + neck + head towers + prediction convs of a small YOLOX in training mode with a smooth loss (mean square of
     the raw prediction maps; the detection loss goes through SimOTA, whose near-tied costs on random weights flip
-    assignments under 16-bit noise and make gradients incomparable): bf16 autocast with the conv stack on our kernels and
-    on torch's convs, each against the fp32 run. Ours must be as close to fp32 as torch's 16-bit step is."""
-    torch.manual_seed(0)
-    cfg = yx.YoloxConfig("trainconv", depth=0.33, width=0.25)
-    m = cfg.get_model().to(cuda).train()
-    x = torch.from_numpy(syn.images(2, 128, 128, seed=3)).to(cuda)
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
-    res = {}
-    for name, flag, amp in (("fp32", "0", False), ("ours", "1", True), ("torch16", "0", True)):
-        monkeypatch.setenv("YX_TRAIN_CONV", flag)
-        m.load_state_dict(sd)
-        m.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            outs = m.head._torch_raw_outputs(m.backbone(x))
-        loss = sum(t.float().square().mean() for lvl in outs for t in lvl)
-        loss.backward()
-        res[name] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).clone(),
-                     [t.detach().float() for lvl in outs for t in lvl])
+    assignments under 16-bit noise): bf16 autocast with the conv stack on our kernels and on torch's convs, each against
+    the fp32 run, over six seeds. On random weights ANY 16-bit backward is only ~0.2-0.8 aligned with the fp32 gradient
+    (chaotic: per seed either path may be ahead, tools/gpu_train_fidelity.py), so the gate is on the means: ours must be as
+    close to fp32 as torch's 16-bit step is."""
+    rows = []
+    for seed in range(6):
+        torch.manual_seed(seed)
+        m = yx.YoloxConfig("trainconv", depth=0.33, width=0.25).get_model().to(cuda).train()
+        x = torch.from_numpy(syn.images(2, 128, 128, seed=seed + 3)).to(cuda)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        res = {}
+        for name, flag, amp in (("fp32", "0", False), ("ours", "1", True), ("torch16", "0", True)):
+            monkeypatch.setenv("YX_TRAIN_CONV", flag)
+            m.load_state_dict(sd)
+            m.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                outs = m.head._torch_raw_outputs(m.backbone(x))
+            loss = sum(t.float().square().mean() for lvl in outs for t in lvl)
+            loss.backward()
+            res[name] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).clone(),
+                         [t.detach().float() for lvl in outs for t in lvl])
 
-    def cos(a, b):
-        return float(torch.dot(a, b) / (a.norm() * b.norm()))
+        def cos(a, b):
+            return float(torch.dot(a, b) / (a.norm() * b.norm()))
 
-    l32, g32, o32 = res["fp32"]
-    c_ours, c_t16 = cos(res["ours"][1], g32), cos(res["torch16"][1], g32)
-    e_ours, e_t16 = abs(res["ours"][0] - l32) / abs(l32), abs(res["torch16"][0] - l32) / abs(l32)
-    o_ours = max(float((a - b).abs().max()) for a, b in zip(res["ours"][2], o32))
-    o_t16 = max(float((a - b).abs().max()) for a, b in zip(res["torch16"][2], o32))
-    print(f"loss fp32 {l32:.5f} ours {res['ours'][0]:.5f} torch16 {res['torch16'][0]:.5f}; max |pred - fp32|: ours {o_ours:.4f} "
-          f"torch16 {o_t16:.4f}; gradient cosine vs fp32: ours {c_ours:.5f} torch16 {c_t16:.5f}")
-    assert e_ours <= 2.0 * e_t16 + 5e-3, (e_ours, e_t16)
-    assert o_ours <= 2.0 * o_t16 + 1e-3, (o_ours, o_t16)
-    assert c_ours >= c_t16 - 0.03, (c_ours, c_t16)        # (a random-init 16-bit step is only ~0.7 aligned with fp32, torch's too)
+        l32, g32, o32 = res["fp32"]
+        rows.append((cos(res["ours"][1], g32), cos(res["torch16"][1], g32),
+                     abs(res["ours"][0] - l32) / abs(l32), abs(res["torch16"][0] - l32) / abs(l32),
+                     max(float((a - b).abs().max()) for a, b in zip(res["ours"][2], o32)),
+                     max(float((a - b).abs().max()) for a, b in zip(res["torch16"][2], o32))))
+    n = len(rows)
+    c_ours, c_t16, e_ours, e_t16, o_ours, o_t16 = (sum(r[k] for r in rows) / n for k in range(6))
+    print(f"means over {n} seeds: gradient cosine vs fp32 ours {c_ours:.4f} torch16 {c_t16:.4f}; loss rel err ours {e_ours:.2e} "
+          f"torch16 {e_t16:.2e}; max |pred - fp32| ours {o_ours:.4f} torch16 {o_t16:.4f}")
+    assert e_ours <= 2.0 * e_t16 + 2e-4, (e_ours, e_t16)
+    assert o_ours <= 1.5 * o_t16 + 1e-3, (o_ours, o_t16)
+    assert c_ours >= c_t16 - 0.06, (c_ours, c_t16)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
