@@ -84,3 +84,29 @@ def checksum(a: np.ndarray) -> str:
     import hashlib
 
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# training blocks: the reference's BaseConv in train mode (conv -> BatchNorm2d with batch statistics -> SiLU), forward and the
+# autograd backward of a seeded output gradient: name -> (batch, in_c, out_c, H, W, ksize, stride, seed)
+TRAIN_BLOCK_CASES = {
+    "c3s1_16_32": (2, 16, 32, 12, 10, 3, 1, 31),
+    "c3s2_32_48": (2, 32, 48, 14, 12, 3, 2, 32),
+    "c1s1_64_16": (3, 64, 16, 7, 9, 1, 1, 33),
+    "c3s2_odd": (1, 16, 16, 9, 11, 3, 2, 34),
+}
+
+
+def train_block_inputs(name):
+    """x, conv weight, gamma, beta, output gradient of a TRAIN_BLOCK case (fp32 numpy, seeded)."""
+    import numpy as np
+
+    B, ci, co, H, W, k, s, seed = TRAIN_BLOCK_CASES[name]
+    r = np.random.default_rng(seed)
+    pad = (k - 1) // 2
+    oh, ow = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    x = r.standard_normal((B, ci, H, W)).astype(np.float32)
+    w = (r.standard_normal((co, ci, k, k)) * 0.2).astype(np.float32)
+    gamma = (r.random(co) + 0.5).astype(np.float32)
+    beta = (r.standard_normal(co) * 0.2).astype(np.float32)
+    go = r.standard_normal((B, co, oh, ow)).astype(np.float32)
+    return x, w, gamma, beta, go

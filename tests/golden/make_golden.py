@@ -260,8 +260,37 @@ def gen_losses():
     print("losses.npz", len(out))
 
 
+def gen_trainblock():
+    """The reference's BaseConv (yolox/models/network_blocks.py:27-52) in train mode on seeded inputs: forward output, the
+    BatchNorm running statistics it leaves behind, and the autograd gradients w.r.t. input, conv weight, gamma and beta
+    (what Trainer.train_one_iter's loss.backward(), core/trainer.py:104-118, computes per block). fp32 on CPU."""
+    out = {}
+    for name, (B, ci, co, H, W, k, s, seed) in cases.TRAIN_BLOCK_CASES.items():
+        x, w, gamma, beta, go = cases.train_block_inputs(name)
+        from yolox.models.network_blocks import BaseConv as RefBaseConv      # the unmodified reference module
+
+        blk = RefBaseConv(ci, co, k, s).train()
+        with torch.no_grad():
+            blk.conv.weight.copy_(torch.from_numpy(w)); blk.bn.weight.copy_(torch.from_numpy(gamma)); blk.bn.bias.copy_(torch.from_numpy(beta))
+        xt = torch.from_numpy(x).requires_grad_(True)
+        y = blk(xt)
+        y.backward(torch.from_numpy(go))
+        out[name + "_y"] = y.detach().numpy()
+        out[name + "_dx"] = xt.grad.numpy()
+        out[name + "_dw"] = blk.conv.weight.grad.numpy()
+        out[name + "_dgamma"] = blk.bn.weight.grad.numpy()
+        out[name + "_dbeta"] = blk.bn.bias.grad.numpy()
+        out[name + "_running_mean"] = blk.bn.running_mean.numpy().copy()
+        out[name + "_running_var"] = blk.bn.running_var.numpy().copy()
+        out[name + "_eps_momentum"] = np.array([blk.bn.eps, blk.bn.momentum], dtype=np.float64)
+    np.savez_compressed(OUT / "trainblock.npz", **out)
+    print("trainblock.npz", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses", "config1", "coco"]
+    which = sys.argv[1:] or ["postprocess", "simota", "network", "losses", "config1", "coco", "trainblock"]
+    if "trainblock" in which:
+        gen_trainblock()
     if "postprocess" in which:
         gen_postprocess()
     if "simota" in which:

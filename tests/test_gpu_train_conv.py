@@ -294,3 +294,44 @@ def test_bn_backward_reads_a_channel_slice_of_the_cat_gradient_in_place(cuda):
     torch.testing.assert_close(x.grad.float(), xr.grad, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(gam.grad, bn.weight.grad, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(bet.grad, bn.bias.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("name", ["c3s1_16_32", "c3s2_32_48", "c1s1_64_16", "c3s2_odd"])
+def test_train_block_matches_the_reference_baseconv_golden(cuda, name):
+    """Our BaseConv in train mode under bf16 autocast (tcgen05 forward / dgrad / wgrad + BatchNorm kernels) against the
+    UNMODIFIED reference's BaseConv forward and autograd gradients (tests/golden/trainblock.npz, fp32 CPU) and against the
+    fp64 oracle evaluated on the operands as the 16-bit path sees them (x and W rounded to bf16)."""
+    import cases
+    import numpy as np
+    from pathlib import Path
+
+    from oracle import train_oracle as to
+    from pixeltable_yolox_b200.network_blocks import BaseConv
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "trainblock.npz")
+    B, ci, co, H, W, k, s, seed = cases.TRAIN_BLOCK_CASES[name]
+    x, w, gamma, beta, go = cases.train_block_inputs(name)
+    blk = BaseConv(ci, co, k, s).to(cuda).train()
+    with torch.no_grad():
+        blk.conv.weight.copy_(torch.from_numpy(w)); blk.bn.weight.copy_(torch.from_numpy(gamma)); blk.bn.bias.copy_(torch.from_numpy(beta))
+    xt = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = blk(xt)
+    y.backward(torch.from_numpy(go).to(cuda).to(y.dtype))
+    got = dict(y=y.float(), dx=xt.grad, dw=blk.conv.weight.grad, dgamma=blk.bn.weight.grad, dbeta=blk.bn.bias.grad,
+               running_mean=blk.bn.running_mean, running_var=blk.bn.running_var)
+    assert int(blk.bn.num_batches_tracked) == 1
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    eps, mom = g[name + "_eps_momentum"]
+    orc = to.base_conv_train(rnd(x), rnd(w), gamma, beta, rnd(go), s, eps, mom)
+    for key, v in got.items():
+        ref, o = g[f"{name}_{key}"], orc[key]
+        v = v.detach().float().cpu().numpy()
+        scale = max(float(np.abs(ref).max()), 1e-6)
+        # 16-bit path vs the fp32 reference: bf16 operand + activation rounding (2^-8 relative per rounding, a few in a row)
+        assert np.abs(v - ref).max() <= 4e-2 * scale, (key, np.abs(v - ref).max() / scale)
+        # vs the oracle on the rounded operands: what is left is the rounding of the intermediate tensors
+        assert np.abs(v - o).max() <= 3e-2 * scale, (key, np.abs(v - o).max() / scale)
+        if key in ("running_mean", "running_var"):
+            # (the statistics are those of the bf16-rounded conv output: 2^-9 relative of values of order 1, times momentum)
+            assert np.abs(v - o).max() <= 2e-3 * max(scale, 0.1), key
