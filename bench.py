@@ -715,18 +715,6 @@ def run_ours(args):
                    "sample": f"{n} of the step's images, oracle/ torch-CPU fp32 forward + numpy/C NMS"}
         vs = None
         in_mb = dev_in[0].numel() * dev_in[0].element_size() / 1e6
-        from pixeltable_yolox_b200.network_blocks import BaseConv as _BaseConv
-
-        n_bn = sum(isinstance(m_, _BaseConv) for m_ in model.modules())
-        n_conv = sum(isinstance(m_, torch.nn.Conv2d) and m_.groups == 1 for m_ in model.modules())
-        ours_convs = amp_dtype is not None and os.environ.get("YX_TRAIN_CONV", "1") != "0"
-        launches_per_step = n_bn * 6 + 6 + 3 + ((4 * n_conv - 1) + 1 + 2 if ours_convs else 0)
-        launches_note = (f"ours per step: {n_bn} BaseConv x (3 BatchNorm + activation forward + 3 backward launches) + 6 head-row launches "
-                         "+ SimOTA + losses + SGD/EMA" +
-                         (f" + {n_conv} convs x (forward, dgrad, wgrad, wgrad reduce; no dgrad for the stem) + 1 weight-packing launch + "
-                          "SPP pools forward / backward" if ours_convs else "; the convolutions themselves are cuDNN (YX_TRAIN_CONV=0)"))
-        best_ms = graph_line["ms_per_step"] if graph_line and "ms_per_step" in graph_line else ms
-        train_tflops = 3 * GFLOP_PER_IMAGE.get(args.model, 0) * 1e9 * B / (best_ms / 1e3) / 1e12
         line = {
             "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -1088,6 +1076,17 @@ def run_train(args, world, rank, dev):
         A = sum(h * w for h, w in hw)
         sim_bytes = B * A * 85 * 4
         cpu = None
+        from pixeltable_yolox_b200.network_blocks import BaseConv as _BaseConv
+
+        n_bn = sum(isinstance(m_, _BaseConv) for m_ in model.modules())
+        n_conv = sum(isinstance(m_, torch.nn.Conv2d) and m_.groups == 1 for m_ in model.modules())
+        ours_convs = amp_dtype is not None and os.environ.get("YX_TRAIN_CONV", "1") != "0"
+        launches_per_step = n_bn * 6 + 6 + 3 + ((4 * n_conv - 1) + 1 + 2 if ours_convs else 0)
+        launches_note = (f"ours per step: {n_bn} BaseConv x (3 BatchNorm + activation forward + 3 backward launches) + 6 head-row launches "
+                         "+ SimOTA + losses + SGD/EMA" +
+                         (f" + {n_conv} convs x (forward, dgrad, wgrad, wgrad reduce; no dgrad for the stem) + 1 weight-packing launch + "
+                          "SPP pools forward / backward" if ours_convs else "; the convolutions themselves are cuDNN (YX_TRAIN_CONV=0)"))
+        train_tflops = 3 * GFLOP_PER_IMAGE.get(args.model, 0) * 1e9 * B / (best_ms / 1e3) / 1e12
         line = {
             "metric": "images_per_second", "value": world * B / (best_ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": best_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -335,3 +335,27 @@ def test_train_block_matches_the_reference_baseconv_golden(cuda, name):
         if key in ("running_mean", "running_var"):
             # (the statistics are those of the bf16-rounded conv output: 2^-9 relative of values of order 1, times momentum)
             assert np.abs(v - o).max() <= 2e-3 * max(scale, 0.1), key
+
+
+@pytest.mark.parametrize("name", ["yolox_nano", "yolox_tiny", "yolox_m"])
+def test_training_step_of_other_named_configs_runs_on_the_tcgen05_convs(cuda, name, monkeypatch):
+    """Widths that need channel padding (tiny: 24-channel stem), depthwise blocks that stay with torch (nano), a deeper /
+    wider network (m): the bf16 training step runs through our convs, gives finite gradients for every parameter and the loss
+    of the torch-conv step up to 16-bit noise (SimOTA flips allowed for)."""
+    torch.manual_seed(0)
+    m = yx.YoloxConfig.get_named_config(name).get_model().to(cuda).train()
+    x = torch.from_numpy(syn.images(2, 160, 160, seed=3)).to(cuda)
+    lab = torch.from_numpy(syn.labels(2, max_gt=8, seed=5, size=160.0, counts=[3, 5])).to(cuda)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    losses = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YX_TRAIN_CONV", flag)
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x, lab)
+        out["total_loss"].backward()
+        losses[flag] = float(out["total_loss"])
+        for n, p in m.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert abs(losses["1"] - losses["0"]) <= 0.05 * abs(losses["0"]), losses
