@@ -358,4 +358,38 @@ def test_training_step_of_other_named_configs_runs_on_the_tcgen05_convs(cuda, na
         losses[flag] = float(out["total_loss"])
         for n, p in m.named_parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all(), n
-    assert abs(losses["1"] - losses["0"]) <= 0.05 * abs(losses["0"]), losses
+    # the detection loss goes through SimOTA: with 8 GTs one flipped assignment moves it by several per cent
+    assert abs(losses["1"] - losses["0"]) <= 0.15 * abs(losses["0"]), losses
+
+
+@pytest.mark.parametrize("name", ["yolox_nano", "yolox_s"])
+def test_backbone_prefix_gradients_match_fp32_where_the_network_is_not_yet_chaotic(cuda, name, monkeypatch):
+    """Stem + dark2 + dark3 in training mode (depthwise + pointwise blocks for nano, dense CSP layers with shortcut adds for s):
+    a prefix shallow enough that 16-bit noise has not decorrelated the gradients, so the comparison with the fp32 run is tight
+    (cosine > 0.998 for torch's 16-bit path): ours must match it. Through dark5 both paths drop to ~0.75, through the whole
+    network to ~0.5 (tools/gpu_nano_sub.py, tools/gpu_train_fidelity.py)."""
+    def cos(a, b):
+        return float(torch.dot(a, b) / (a.norm() * b.norm()))
+
+    torch.manual_seed(0)
+    m = yx.YoloxConfig.get_named_config(name).get_model().to(cuda).train()
+    bb = m.backbone.backbone
+    x = torch.from_numpy(syn.images(2, 128, 128, seed=3)).to(cuda)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    res = {}
+    for tag, flag, amp in (("fp32", "0", False), ("ours", "1", True), ("torch16", "0", True)):
+        monkeypatch.setenv("YX_TRAIN_CONV", flag)
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            t = bb.stem._train_forward(x)
+            for blk in (bb.dark2, bb.dark3):
+                for sub in blk:
+                    t = sub._train_forward(t)
+        loss = t.float().square().mean()
+        loss.backward()
+        res[tag] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).clone())
+    c_ours, c_t16 = cos(res["ours"][1], res["fp32"][1]), cos(res["torch16"][1], res["fp32"][1])
+    print(f"{name} through dark3: gradient cosine vs fp32 ours {c_ours:.5f} torch16 {c_t16:.5f}; loss {res['fp32'][0]:.5f} / {res['ours'][0]:.5f} / {res['torch16'][0]:.5f}")
+    assert c_ours > 0.998 and c_ours >= c_t16 - 0.001, (c_ours, c_t16)
+    assert abs(res["ours"][0] - res["fp32"][0]) <= 2e-3 * abs(res["fp32"][0]), res

@@ -12,6 +12,7 @@ import pixeltable_yolox_b200 as yx  # noqa: E402
 from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
 
 seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+named = sys.argv[2] if len(sys.argv) > 2 else None
 dev = torch.device("cuda", 0)
 
 
@@ -22,7 +23,7 @@ def cos(a, b):
 rows = []
 for seed in range(seeds):
     torch.manual_seed(seed)
-    m = yx.YoloxConfig("fid", depth=0.33, width=0.25).get_model().to(dev).train()
+    m = (yx.YoloxConfig.get_named_config(named) if named else yx.YoloxConfig("fid", depth=0.33, width=0.25)).get_model().to(dev).train()
     x = torch.from_numpy(syn.images(2, 128, 128, seed=seed + 3)).to(dev)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     res = {}
@@ -34,8 +35,11 @@ for seed in range(seeds):
             outs = m.head._torch_raw_outputs(m.backbone(x))
         loss = sum(t.float().square().mean() for lvl in outs for t in lvl)
         loss.backward()
-        res[name] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).clone())
-    l32, g32 = res["fp32"]
+        res[name] = (float(loss.detach()), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).clone(),
+                     torch.cat([t.detach().float().flatten() for lvl in outs for t in lvl]))
+    l32, g32, o32 = res["fp32"]
+    print(f"   max |pred - fp32|: ours {float((res['ours'][2] - o32).abs().max()):.4f} torch16 {float((res['torch16'][2] - o32).abs().max()):.4f}; "
+          f"rms: ours {float((res['ours'][2] - o32).square().mean().sqrt()):.5f} torch16 {float((res['torch16'][2] - o32).square().mean().sqrt()):.5f}")
     rows.append((cos(res["ours"][1], g32), cos(res["torch16"][1], g32), abs(res["ours"][0] - l32) / l32, abs(res["torch16"][0] - l32) / l32))
     print(f"seed {seed}: gradient cosine vs fp32 ours {rows[-1][0]:.4f} torch16 {rows[-1][1]:.4f} | loss rel err ours {rows[-1][2]:.2e} torch16 {rows[-1][3]:.2e}", flush=True)
 n = len(rows)
