@@ -869,16 +869,37 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
             from pixeltable_yolox_b200 import train_conv
 
             train_conv.attach_packer(raw, amp_dtype)
-        opt = FusedSgdEma(raw, lr=opt.lr, momentum=opt.momentum, weight_decay=5e-4, nesterov=opt.nesterov, ema=True,
-                          ema_decay=opt.ema_decay, direct_grads=True)
+        kw = dict(lr=opt.lr, momentum=opt.momentum, weight_decay=5e-4, nesterov=opt.nesterov, ema=True, ema_decay=opt.ema_decay,
+                  direct_grads=True)
+        # the flat gradient buffer as symmetric memory (every rank maps every peer's buffer over NVLink): all-reduce + SGD +
+        # EMA run as ONE kernel of ours over those mappings and the whole step is one graph; without symmetric memory the
+        # step is two graphs around an eager ncclAllReduce. Every rank must take the same branch.
+        fused_collective = os.environ.get("YX_FUSED_ALLREDUCE", "1") != "0"
+        try:
+            opt = FusedSgdEma(raw, peer_group=dist.group.WORLD if fused_collective else None, **kw)
+        except Exception as e:                      # noqa: BLE001
+            print(f"# symmetric memory unavailable ({e!r}): NCCL all-reduce between two graphs", file=sys.stderr)
+            fused_collective = False
+            opt = FusedSgdEma(raw, **kw)
+        ok = torch.tensor([1 if fused_collective else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if fused_collective and int(ok.item()) == 0:                     # some rank fell back: all do
+            fused_collective = False
+            opt = FusedSgdEma(raw, **kw)
     else:
         raw = model
+        fused_collective = False
+    time_train_graph.fused_collective = fused_collective
 
     def eager():
         with torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
             out = raw(x, lab)
         opt.zero_grad()
         out["total_loss"].backward()
+        if world > 1:
+            opt.join()
+            dist.all_reduce(opt.flat_grad)
+            opt.flat_grad.div_(world)
         opt.step()
 
     side = torch.cuda.Stream(dev)
@@ -899,11 +920,13 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
         opt.zero_grad()
         loss.backward()
         opt.join()                                 # side-stream weight gradients rejoin the captured stream
-        if world > 1:
+        if fused_collective:
+            opt.step_allreduce_captured()          # reduce-scatter over peer memory -> all-gather fused with SGD + EMA
+        elif world > 1:
             flat = opt.flat_grad                   # every .grad is a view into it: the all-reduce needs no flatten / scatter
         else:
             opt.step_captured()
-    if world > 1:
+    if world > 1 and not fused_collective:
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, capture_error_mode="thread_local"):
             flat.div_(world)
@@ -912,7 +935,7 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
     def replay():
         opt.set_hyper()
         g.replay()
-        if world > 1:
+        if world > 1 and not fused_collective:
             dist.all_reduce(flat)
             g2.replay()
 
@@ -998,6 +1021,11 @@ def run_train(args, world, rank, dev):
                       "e2e_ms_per_step": gms_host, "e2e_images_per_second": world * B / (gms_host / 1e3), "e2e_loss_last_step": gloss_host,
                       "what": ("forward + SimOTA + losses + backward + SGD/EMA captured once with torch.cuda.graph and replayed"
                                if world == 1 else
+                               "ONE captured graph per step: forward + SimOTA + losses + backward + yx_allreduce_sgd_ema_step (gradient "
+                               "all-reduce over NVLink peer memory -- reduce-scatter in rank order, all-gather fused with the SGD + EMA "
+                               "update -- as one kernel of ours on the symmetric flat gradient buffer; no NCCL call in the step), on a "
+                               "copy of the module without the DDP wrapper"
+                               if getattr(time_train_graph, "fused_collective", False) else
                                "two captured graphs (forward + SimOTA + losses + backward | average + SGD/EMA) around one eager "
                                "ncclAllReduce of the flat gradient buffer every .grad is a view of, on a copy of the module "
                                "without the DDP wrapper") + "; lr / EMA decay reach the captured optimizer launch via a device buffer"}
@@ -1103,8 +1131,11 @@ def run_train(args, world, rank, dev):
                        "ours_in_step": "yx_conv_bn_act_fwd (forward + dgrad), yx_conv_wgrad, yx_pack_train_weights, yx_bn_act_train_fwd/bwd (training-mode BatchNorm + SiLU of all 74 BaseConv), yx_head_train_decode "
                                        "fwd/bwd (3 levels), yx_simota_assign (whole batch, one cluster launch, no host sync), "
                                        "yx_head_losses (losses and d/d(pred) in one pass), yx_sgd_ema_step",
-                       "collective": (f"gradient all-reduce: torch DDP buckets (25 MB) -> ncclAllReduce over NVLink/NVSwitch, "
-                                      f"{n_grad * 4 / 1e6:.1f} MB fp32 per step" if world > 1 else "none (one rank)"),
+                       "collective": ("none (one rank)" if world == 1 else
+                                      (f"graph step (value): yx_allreduce_sgd_ema_step, our all-reduce over NVLink 5 / NVSwitch peer memory fused with "
+                                       f"SGD + EMA, {n_grad * 4 / 1e6:.1f} MB fp32 per step, no NCCL call; " if getattr(time_train_graph, "fused_collective", False)
+                                       else f"graph step (value): one eager ncclAllReduce of the flat {n_grad * 4 / 1e6:.1f} MB fp32 gradient buffer between two graphs; ") +
+                                      "eager step: torch DDP buckets (25 MB) -> ncclAllReduce over NVLink/NVSwitch"),
                        "loss_last_step": loss},
             "e2e": {"value": world * B / (best_e2e_ms / 1e3), "unit": "images/s",
                     "h2d_bytes_per_step": xh.numel() * 4 + labh.numel() * 4, "d2h_bytes_per_step": 4,

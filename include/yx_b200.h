@@ -335,6 +335,21 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
                     const float* hyper, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gradient all-reduce + yx_sgd_ema_step as ONE kernel over NVLink peer memory: the data-parallel exchange of the training step
+ * (DDP's ncclAllReduce, yolox/core/trainer.py:169) fused with the optimizer step and the EMA update that follow it
+ * (core/trainer.py:119-124). Every rank's gradients live in one flat fp32 buffer of `flat_elems` elements allocated as symmetric
+ * memory; peer_grad_ptrs[q] (HOST array of `world` addresses) is rank q's buffer as mapped into THIS process, peer_flag_ptrs[q] a
+ * zero-initialised symmetric uint32[world] array of rank q (barrier flags). The table's grad pointers must point into the local
+ * buffer. Reduce-scatter in rank order (deterministic) -> barrier -> all-gather fused with the update; three node-wide
+ * barriers per call. `state`: local device uint32[4], zero-initialised once, owned by the kernel. hyper: device {lr, ema_decay,
+ * 1 - ema_decay} (required). Every rank must make the same sequence of calls. world <= 16.
+ * ------------------------------------------------------------------------------------------ */
+int yx_allreduce_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float momentum,
+                              int32_t nesterov, int32_t first_step, const float* hyper, const int64_t* peer_grad_ptrs,
+                              const int64_t* peer_flag_ptrs, int64_t flat_elems, int32_t rank, int32_t world, uint32_t* state,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training-mode BatchNorm2d + activation of a BaseConv (yolox/models/network_blocks.py:27-52 with the BN in train mode;
  * eps / momentum as set by yolox/config.py:165-176), forward and backward, on the conv output x [N, C, H*W] (contiguous
  * NCHW; YX_FP32 / YX_BF16 / YX_FP16), statistics and affine parameters in fp32.

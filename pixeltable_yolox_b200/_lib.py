@@ -94,6 +94,7 @@ SIGNATURES = {
     "yx_head_train_decode": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _I32, _I32, _P, _P, _P]),
     "yx_head_train_decode_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _I32, _I32, _P, _P, _P, _P]),
     "yx_sgd_ema_step": (C.c_int, [_P, _P, _I32, _I32, _F, _F, _I32, _I32, _F, _F, _P, _P]),
+    "yx_allreduce_sgd_ema_step": (C.c_int, [_P, _P, _I32, _I32, _F, _I32, _I32, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "yx_bn_act_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "yx_bn_act_train_fwd": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P, _F, _F, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "yx_bn_act_train_bwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I64, _P, _I64, _P]),

@@ -78,6 +78,9 @@ int dilate2_launch(const void* dy, void* z, int batch, int oh, int ow, int zh, i
 int pack_train_weights_multi_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, int dtype, cudaStream_t stream);
 int spp_bwd_launch(const void* cat, long long ld, const void* dout, long long dld, float* dx32, int batch, int h, int w, int c,
                    int dtype, cudaStream_t s);
+int allreduce_sgd_ema_launch(const long long* table, const int* chunks, int n_chunks, int chunk_elems, float momentum, int nesterov,
+                             int first_step, const float* hyper, const long long* peer_grad, const long long* peer_flag,
+                             long long flat_elems, int rank, int world, unsigned* state, cudaStream_t s);
 struct StemLaunch;
 StemLaunch* stem_alloc();
 void stem_free(StemLaunch*);
@@ -433,6 +436,17 @@ int yx_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunk
   if (rc) return rc;
   return sgd_ema_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, lr, momentum, nesterov,
                         first_step, ema_decay, ema_rest, hyper, (cudaStream_t)stream);
+}
+
+int yx_allreduce_sgd_ema_step(const int64_t* table, const int32_t* chunks, int32_t n_chunks, int32_t chunk_elems, float momentum,
+                              int32_t nesterov, int32_t first_step, const float* hyper, const int64_t* peer_grad_ptrs,
+                              const int64_t* peer_flag_ptrs, int64_t flat_elems, int32_t rank, int32_t world, uint32_t* state,
+                              void* stream) {
+  int rc = require_device();
+  if (rc) return rc;
+  return allreduce_sgd_ema_launch(reinterpret_cast<const long long*>(table), chunks, n_chunks, chunk_elems, momentum, nesterov, first_step,
+                                  hyper, reinterpret_cast<const long long*>(peer_grad_ptrs), reinterpret_cast<const long long*>(peer_flag_ptrs),
+                                  flat_elems, rank, world, state, (cudaStream_t)stream);
 }
 
 int64_t yx_bn_act_workspace_bytes(int32_t n, int32_t c, int32_t hw) { return bn_act_ws_bytes(n, c, hw); }

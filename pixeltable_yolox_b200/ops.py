@@ -714,3 +714,20 @@ def spp_maxpool_bwd(cat: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
         check(lib().yx_spp_maxpool_bwd(cv.ptr, cv.ld, dv.ptr, dv.ld, dx32.data_ptr(), cv.B, cv.H, cv.W, c, dtype_code(cat.dtype),
                                        stream_ptr(cat.device)), "spp_maxpool_bwd")
     return dx32.to(cat.dtype)
+
+
+def allreduce_sgd_ema_step(table: torch.Tensor, chunks: torch.Tensor, chunk_elems: int, momentum: float, nesterov: bool,
+                           first_step: bool, hyper: torch.Tensor, peer_grad_ptrs, peer_flag_ptrs, flat_elems: int, rank: int,
+                           world: int, state: torch.Tensor) -> None:
+    """Gradient all-reduce over NVLink peer memory fused with the SGD + EMA update (csrc/yx_allreduce_sgd.cu). peer_*_ptrs:
+    sequences of `world` integer addresses (this rank's mapping of every rank's symmetric buffer)."""
+    require_cuda(table, "allreduce_sgd_ema_step")
+    dev = table.device
+    same_device(dev, "allreduce_sgd_ema_step", chunks=chunks, hyper=hyper, state=state)
+    assert len(peer_grad_ptrs) == world and len(peer_flag_ptrs) == world and state.dtype == torch.int32 and state.numel() >= 4
+    pg = (C.c_int64 * world)(*[int(v) for v in peer_grad_ptrs])
+    pf = (C.c_int64 * world)(*[int(v) for v in peer_flag_ptrs])
+    with on_device(dev):
+        check(lib().yx_allreduce_sgd_ema_step(table.data_ptr(), chunks.data_ptr(), chunks.shape[0], int(chunk_elems), float(momentum),
+                                              1 if nesterov else 0, 1 if first_step else 0, hyper.data_ptr(), pg, pf, int(flat_elems),
+                                              int(rank), int(world), state.data_ptr(), stream_ptr(dev)), "allreduce_sgd_ema_step")

@@ -36,7 +36,7 @@ class FusedSgdEma:
     CHUNK = 16384
 
     def __init__(self, model: nn.Module, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4, nesterov: bool = True,
-                 ema: bool = True, ema_decay: float = 0.9998, updates: int = 0, direct_grads: bool = False):
+                 ema: bool = True, ema_decay: float = 0.9998, updates: int = 0, direct_grads: bool = False, peer_group=None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("FusedSgdEma needs the model on a CUDA device (the B200 path has no CPU fallback)")
@@ -62,7 +62,28 @@ class FusedSgdEma:
         if direct_grads:
             from . import train_conv
 
-            self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+            n_flat = sum(p.numel() for p in self.params)
+            self._peer = None
+            if peer_group is not None:
+                # the flat buffer as SYMMETRIC memory: every rank of the node maps every other rank's buffer over NVLink, and
+                # step_allreduce_captured() runs the all-reduce and the update as one kernel over those mappings
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+
+                self.flat_grad = symm.empty(n_flat, dtype=torch.float32, device=dev)
+                self.flat_grad.zero_()
+                flags = symm.empty(64, dtype=torch.int32, device=dev)
+                flags.zero_()
+                hg = symm.rendezvous(self.flat_grad, group=peer_group)
+                hf = symm.rendezvous(flags, group=peer_group)
+                self._peer = dict(grad=[int(v) for v in hg.buffer_ptrs], flag=[int(v) for v in hf.buffer_ptrs], rank=int(hg.rank),
+                                  world=int(hg.world_size), flags=flags, state=torch.zeros(4, dtype=torch.int32, device=dev),
+                                  handles=(hg, hf))
+                assert self._peer["grad"][self._peer["rank"]] == self.flat_grad.data_ptr()
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=peer_group)               # every rank's flags are zero before anyone signals
+            else:
+                self.flat_grad = torch.zeros(n_flat, dtype=torch.float32, device=dev)
             off = 0
             for p in self.params:
                 assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameter storage is not dense"
@@ -145,6 +166,19 @@ class FusedSgdEma:
             raise RuntimeError("FusedSgdEma.step_captured: run at least one eager step() first (pointer table, momentum init)")
         self.join()
         ops.sgd_ema_step(self._table, self._chunks, self.CHUNK, self.lr, self.momentum, self.nesterov, False, 0.0, self.hyper)
+
+    @torch.no_grad()
+    def step_allreduce_captured(self):
+        """Gradient all-reduce (mean over the ranks of `peer_group`) + optimizer step + EMA update as ONE launch over NVLink
+        peer memory; hyper-parameters from `self.hyper` like step_captured(). Every rank must call it the same number of times."""
+        if self._peer is None:
+            raise RuntimeError("FusedSgdEma.step_allreduce_captured needs direct_grads=True and a peer_group")
+        if self._table is None:
+            raise RuntimeError("FusedSgdEma.step_allreduce_captured: run at least one eager step() first (pointer table, momentum init)")
+        self.join()
+        P = self._peer
+        ops.allreduce_sgd_ema_step(self._table, self._chunks, self.CHUNK, self.momentum, self.nesterov, False, self.hyper,
+                                   P["grad"], P["flag"], self.flat_grad.numel(), P["rank"], P["world"], P["state"])
 
     @torch.no_grad()
     def step(self, lr: Optional[float] = None):
