@@ -252,3 +252,58 @@ def test_fused_train_bn_act_matches_torch(cuda, dtype, act, shape, channels_last
     gt = dict(rtol=1e-4, atol=1e-3) if dtype == torch.float32 else dict(rtol=2e-2, atol=5e-2 * (N * H * W) ** 0.5 / 10)
     torch.testing.assert_close(gam.grad, bn.weight.grad, **gt)
     torch.testing.assert_close(bet.grad, bn.bias.grad, **gt)
+
+
+def test_fused_allreduce_sgd_ema_kernel_on_one_rank_equals_the_plain_optimizer_launch(cuda):
+    """yx_allreduce_sgd_ema_step (gradient all-reduce over NVLink peer memory + SGD + EMA in one kernel) with a one-rank group:
+    the barriers and the reduce-scatter degenerate, the update must equal yx_sgd_ema_step bit for bit. The multi-rank check
+    (against ncclAllReduce, parameters identical across ranks) is tools/gpu_allreduce_sgd_check.py under torchrun."""
+    import os
+
+    import torch.distributed as dist
+
+    from pixeltable_yolox_b200 import train_conv
+    from pixeltable_yolox_b200.optim import FusedSgdEma
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda)
+        created = True
+    try:
+        torch.manual_seed(0)
+        m = yx.YoloxConfig("ar", depth=0.33, width=0.25).get_model().to(cuda).train()
+        try:
+            opt = FusedSgdEma(m, lr=0.01, ema=True, direct_grads=True, peer_group=dist.group.WORLD)
+        except Exception as e:                      # noqa: BLE001
+            pytest.skip(f"symmetric memory unavailable: {e!r}")
+        train_conv.set_direct_grads(False)
+        g = torch.Generator(device=cuda).manual_seed(5)
+        for _ in range(2):
+            opt.flat_grad.copy_(torch.randn(opt.flat_grad.shape, generator=g, device=cuda) * 0.1)
+            opt.step(0.01)
+
+        def snapshot():
+            return [v.clone() for v in m.state_dict().values()] + [b.clone() for b in opt.bufs] + [v.clone() for v in opt.ema.state_dict().values()]
+
+        def restore(s):
+            with torch.no_grad():
+                for dst, src in zip(list(m.state_dict().values()) + opt.bufs + list(opt.ema.state_dict().values()), s):
+                    dst.copy_(src)
+
+        for it in range(3):
+            opt.flat_grad.copy_(torch.randn(opt.flat_grad.shape, generator=g, device=cuda) * 0.1)
+            grads, before, upd = opt.flat_grad.clone(), snapshot(), opt.updates
+            opt.set_hyper(0.02); opt.step_captured()
+            want = snapshot()
+            restore(before); opt.updates = upd; opt.flat_grad.copy_(grads)
+            opt.set_hyper(0.02); opt.step_allreduce_captured()
+            torch.cuda.synchronize()
+            for a, b in zip(snapshot(), want):
+                assert torch.equal(a, b)
+            assert torch.equal(opt.flat_grad, grads)            # one rank: the reduced slice is the gradient itself
+    finally:
+        train_conv.set_direct_grads(False)
+        if created:
+            dist.destroy_process_group()
