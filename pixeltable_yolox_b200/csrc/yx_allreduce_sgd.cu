@@ -131,42 +131,98 @@ allreduce_sgd_ema_kernel(const ArSgdParams p) {
     const float wd = __int_as_float((int)(row[5] & 0xffffffffll));
     const long long e1 = min(n, (long long)e0 + p.chunk_elems);
     const long long goff = g ? (g - mine) : 0;                                       // offset of this tensor in the flat buffer
-    // U elements per thread in flight: the remote gradient loads take microseconds over NVLink, a one-element-at-a-time loop
-    // (the first version) spent 540 us on 36 MB at two ranks
-    constexpr int U = 8;
-    for (long long base = e0; base < e1; base += (long long)kArThreads * U) {
-      float gv[U], wv[U], bv[U], ev[U];
+    // U items per thread in flight: the remote gradient loads take microseconds over NVLink (a one-element-at-a-time loop, the
+    // first version, spent 540 us on 36 MB at two ranks). Tensors whose element count and flat offset are multiples of four
+    // (all but the 1-element objectness biases: FusedSgdEma pads every slot of the flat buffer to 16 bytes) move as float4.
+    constexpr int U = 4;
+    const bool vec = (n & 3) == 0 && (e0 & 3) == 0 && (goff & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(buf) |
+                      reinterpret_cast<uintptr_t>(ema)) & 15) == 0;
+    const bool mom = p.momentum != 0.0f;
+    if (vec) {
+      const long long q0 = e0 >> 2, q1 = e1 >> 2;
+      for (long long base = q0; base < q1; base += (long long)kArThreads * U) {
+        float4 gv[U], wv[U], bv[U], ev[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long i = base + (long long)u * kArThreads + threadIdx.x;
-        if (i < e1) {
-          wv[u] = w[i];
-          if (g) {
-            const long long off = goff + i;
-            const int owner = (int)(off / SL);
-            gv[u] = __ldcg(reinterpret_cast<const float*>(p.peer_grad[owner]) + off);   // L2 / NVLink, never a stale L1 line of phase 1
-            if (p.momentum != 0.0f && !p.first_step) bv[u] = buf[i];
+        for (int u = 0; u < U; ++u) {
+          const long long i = base + (long long)u * kArThreads + threadIdx.x;
+          if (i < q1) {
+            wv[u] = reinterpret_cast<const float4*>(w)[i];
+            if (g) {
+              const long long off = goff + 4 * i;
+              const int owner = (int)(off / SL);                    // SL and off are multiples of 4: a vector never straddles slices
+              gv[u] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.peer_grad[owner]) + off));
+              if (mom && !p.first_step) bv[u] = reinterpret_cast<const float4*>(buf)[i];
+            }
+            if (ema) ev[u] = reinterpret_cast<const float4*>(ema)[i];
           }
-          if (ema) ev[u] = ema[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = base + (long long)u * kArThreads + threadIdx.x;
+          if (i < q1) {
+            float v[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+            if (g) {
+              const float d4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+              const float b4[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+              float nb[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float d = d4[k];
+                if (wd != 0.0f) d = fmaf(wd, v[k], d);
+                if (mom) {
+                  nb[k] = p.first_step ? d : __fadd_rn(__fmul_rn(p.momentum, b4[k]), d);
+                  d = p.nesterov ? fmaf(p.momentum, nb[k], d) : nb[k];
+                }
+                v[k] = fmaf(-lr, d, v[k]);
+              }
+              if (mom) reinterpret_cast<float4*>(buf)[i] = make_float4(nb[0], nb[1], nb[2], nb[3]);
+              reinterpret_cast<float4*>(w)[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            if (ema) {
+              const float e4[4] = {ev[u].x, ev[u].y, ev[u].z, ev[u].w};
+              float r[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) r[k] = __fadd_rn(__fmul_rn(e4[k], ema_decay), __fmul_rn(ema_rest, v[k]));
+              reinterpret_cast<float4*>(ema)[i] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+          }
         }
       }
+    } else {
+      for (long long base = e0; base < e1; base += (long long)kArThreads * U) {
+        float gv[U], wv[U], bv[U], ev[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long i = base + (long long)u * kArThreads + threadIdx.x;
-        if (i < e1) {
-          float v = wv[u];
-          if (g) {
-            float d = gv[u];
-            if (wd != 0.0f) d = fmaf(wd, v, d);
-            if (p.momentum != 0.0f) {
-              const float nb = p.first_step ? d : __fadd_rn(__fmul_rn(p.momentum, bv[u]), d);
-              buf[i] = nb;
-              d = p.nesterov ? fmaf(p.momentum, nb, d) : nb;
+        for (int u = 0; u < U; ++u) {
+          const long long i = base + (long long)u * kArThreads + threadIdx.x;
+          if (i < e1) {
+            wv[u] = w[i];
+            if (g) {
+              const long long off = goff + i;
+              const int owner = (int)(off / SL);
+              gv[u] = __ldcg(reinterpret_cast<const float*>(p.peer_grad[owner]) + off);   // L2 / NVLink, never a stale L1 line of phase 1
+              if (mom && !p.first_step) bv[u] = buf[i];
             }
-            v = fmaf(-lr, d, v);
-            w[i] = v;
+            if (ema) ev[u] = ema[i];
           }
-          if (ema) ema[i] = __fadd_rn(__fmul_rn(ev[u], ema_decay), __fmul_rn(ema_rest, v));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = base + (long long)u * kArThreads + threadIdx.x;
+          if (i < e1) {
+            float v = wv[u];
+            if (g) {
+              float d = gv[u];
+              if (wd != 0.0f) d = fmaf(wd, v, d);
+              if (mom) {
+                const float nb = p.first_step ? d : __fadd_rn(__fmul_rn(p.momentum, bv[u]), d);
+                buf[i] = nb;
+                d = p.nesterov ? fmaf(p.momentum, nb, d) : nb;
+              }
+              v = fmaf(-lr, d, v);
+              w[i] = v;
+            }
+            if (ema) ema[i] = __fadd_rn(__fmul_rn(ev[u], ema_decay), __fmul_rn(ema_rest, v));
+          }
         }
       }
     }

@@ -62,7 +62,7 @@ class FusedSgdEma:
         if direct_grads:
             from . import train_conv
 
-            n_flat = sum(p.numel() for p in self.params)
+            n_flat = sum((p.numel() + 3) // 4 * 4 for p in self.params)      # every slot starts on a 16-byte boundary (vector loads)
             self._peer = None
             if peer_group is not None:
                 # the flat buffer as SYMMETRIC memory: every rank of the node maps every other rank's buffer over NVLink, and
@@ -88,7 +88,7 @@ class FusedSgdEma:
             for p in self.params:
                 assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameter storage is not dense"
                 p.grad = torch.as_strided(self.flat_grad, p.shape, p.stride(), off)
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
             train_conv.set_direct_grads(True)
         self._wd = [wd[id(p)] for p in self.params]
         self._steps = 0
