@@ -269,7 +269,10 @@ def test_fused_allreduce_sgd_ema_kernel_on_one_rank_equals_the_plain_optimizer_l
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29577")
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda)
+        try:
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda)
+        except Exception as e:                      # noqa: BLE001
+            pytest.skip(f"cannot create a one-rank NCCL group here: {e!r}")
         created = True
     try:
         torch.manual_seed(0)
