@@ -69,11 +69,12 @@ class _FusedBnAct(torch.autograd.Function):
                       and dy.data_ptr() % 16 == 0)           # channel slice of a wider NHWC gradient (backward of cat): read in place
             if not sliced:
                 dy = dy.contiguous(memory_format=torch.channels_last) if ops._is_channels_last(x) else dy.contiguous()
-        from .train_conv import direct_grads
+        from .train_conv import direct_target
 
-        if direct_grads() and gamma.grad is not None and beta.grad is not None:
-            # gradient accumulation into .grad inside the finalize launch (see train_conv.set_direct_grads)
-            dx, _, _ = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act, gamma.grad, beta.grad)
+        tg, tb = direct_target(gamma), direct_target(beta)
+        if tg is not None and tb is not None:
+            # gradient accumulation into .grad inside the finalize launch (see train_conv.direct_target)
+            dx, _, _ = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act, tg, tb)
             return dx, None, None, None, None, None, None, None, None
         dx, dgamma, dbeta = ops.bn_act_train_bwd(x, dy, gamma, beta, mean, invstd, ctx.act)
         return dx, dgamma, dbeta, None, None, None, None, None, None

@@ -219,13 +219,24 @@ def head_decode_(pred: torch.Tensor, hw: Sequence[Sequence[int]], strides: Seque
 _ws_cache: dict = {}
 
 
+_ws_retired = {}
+
+
 def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
     key = (dev.index, tag)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None and tag == "wgrad":
+            # weight-gradient launches may still be running on the side stream (train_conv): the outgrown buffer stays
+            # allocated until the streams are joined, so the caching allocator cannot hand it to another stream
+            _ws_retired.setdefault(dev.index, []).append(ws)
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         _ws_cache[key] = ws
     return ws
+
+
+def release_retired_workspaces(dev: torch.device) -> None:
+    _ws_retired.pop(dev.index, None)
 
 
 def postprocess_device(pred: torch.Tensor, num_classes: int, conf_thre: float, nms_thre: float, nms_variant: int,

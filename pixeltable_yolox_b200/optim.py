@@ -57,7 +57,7 @@ class FusedSgdEma:
         self.bufs = [torch.zeros_like(p) for p in self.params]      # same strides as the parameter (NCHW or channels_last)
         # direct_grads: every .grad is a view into ONE flat fp32 buffer (zero_grad = one memset, a multi-GPU step all-reduces
         # the buffer itself), and the conv / BatchNorm backward kernels add their weight gradients into it in place
-        # (train_conv.set_direct_grads). Not for modules wrapped in DistributedDataParallel.
+        # (train_conv.direct_target: opt-in per parameter). Not for modules wrapped in DistributedDataParallel.
         self.flat_grad = None
         if direct_grads:
             from . import train_conv
@@ -88,8 +88,8 @@ class FusedSgdEma:
             for p in self.params:
                 assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameter storage is not dense"
                 p.grad = torch.as_strided(self.flat_grad, p.shape, p.stride(), off)
+                p._yx_direct_grad = True              # the backward kernels may add into p.grad (train_conv.direct_target)
                 off += (p.numel() + 3) // 4 * 4
-            train_conv.set_direct_grads(True)
         self._wd = [wd[id(p)] for p in self.params]
         self._steps = 0
         self._table = None
@@ -128,6 +128,15 @@ class FusedSgdEma:
         self._table = torch.from_numpy(table).to(self._dev)
         self._chunks = torch.from_numpy(np.array(chunks, dtype=np.int32).reshape(-1, 2)).to(self._dev)
         self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
+
+    def close(self):
+        """Give the parameters back to plain autograd accumulation (direct_grads): their .grad stays a view of the flat buffer
+        until it is replaced, but the backward kernels no longer write into it."""
+        if self.flat_grad is not None:
+            self.join()
+            for p in self.params:
+                if hasattr(p, "_yx_direct_grad"):
+                    del p._yx_direct_grad
 
     def join(self):
         if self.flat_grad is not None:

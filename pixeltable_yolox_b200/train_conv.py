@@ -23,11 +23,13 @@ from ._lib import YX_ACT_NONE
 
 _zero_bias = {}
 
-# Direct gradient accumulation (FusedSgdEma(direct_grads=True) switches it on): the wgrad reduction and the BatchNorm backward
-# add their results straight into `param.grad` (which must exist: the optimizer owns one flat, zeroed gradient buffer) and
-# return no gradient to autograd, so AccumulateGrad's one `grad += new` launch per parameter (242 per step) disappears. Not for
-# modules wrapped in DistributedDataParallel, whose reduction hooks hang off AccumulateGrad.
-_direct_grads = False
+# Direct gradient accumulation: for parameters that FusedSgdEma(direct_grads=True) has marked (`param._yx_direct_grad`: their
+# .grad is a view of the optimizer's flat, zeroed gradient buffer) the wgrad reduction and the BatchNorm backward add their
+# results straight into `param.grad` and return no gradient to autograd, so AccumulateGrad's one `grad += new` launch per
+# parameter (242 per step) disappears. Opt-in per parameter, so other modules in the process are unaffected; not for modules
+# wrapped in DistributedDataParallel, whose reduction hooks hang off AccumulateGrad. set_direct_grads(False) is a global off
+# switch (scripts that fill .grad themselves).
+_direct_grads = True
 
 
 def set_direct_grads(on: bool) -> None:
@@ -37,6 +39,13 @@ def set_direct_grads(on: bool) -> None:
 
 def direct_grads() -> bool:
     return _direct_grads
+
+
+def direct_target(param: torch.Tensor) -> Optional[torch.Tensor]:
+    """The tensor a backward kernel should accumulate this parameter's gradient into, or None (return it to autograd)."""
+    if _direct_grads and getattr(param, "_yx_direct_grad", False) and param.grad is not None:
+        return param.grad
+    return None
 
 
 # With direct gradient accumulation the weight-gradient launches have no consumer before the optimizer step, so they run on a
@@ -61,6 +70,7 @@ def join_wgrad(dev: Optional[torch.device] = None) -> None:
             if pending:
                 torch.cuda.current_stream(d).wait_stream(stream)
                 pending.clear()
+                ops.release_retired_workspaces(d)
 
 
 class WeightPacker:
@@ -213,15 +223,16 @@ class _ConvTc(torch.autograd.Function):
         dyh = _pad_channels(dy.to(xh.dtype), o_pad)
         dx = dw = db = None
         if ctx.needs_input_grad[1]:
-            if _direct_grads and weight.grad is not None:
+            target = direct_target(weight)
+            if target is not None:
                 if os.environ.get("YX_WGRAD_OVERLAP", "1") != "0":
                     stream, pending = _side(xh.device)
                     stream.wait_event(torch.cuda.current_stream(xh.device).record_event())
                     with torch.cuda.stream(stream):
-                        ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
+                        ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=target)
                     pending.append((xh, dyh))
                 else:
-                    ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=weight.grad)
+                    ops.conv_wgrad(xh, dyh, weight, k, stride, accumulate_into=target)
             else:
                 dw = ops.conv_wgrad(xh, dyh, weight, k, stride)
         if ctx.needs_input_grad[0]:

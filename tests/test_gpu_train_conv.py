@@ -226,6 +226,7 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(cuda):
     want = run()
     for p in m.parameters():
         p.grad = None
+    opt = None
     try:
         opt = FusedSgdEma(m, lr=0.01, ema=False, direct_grads=True)
         assert train_conv.direct_grads() and opt.flat_grad.numel() == sum((p.numel() + 3) // 4 * 4 for p in m.parameters())
@@ -239,7 +240,8 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(cuda):
         for a, b in zip(twice, want):
             torch.testing.assert_close(a, 2 * b, rtol=1e-3, atol=2e-3 * float(b.abs().max()) + 1e-9)
     finally:
-        train_conv.set_direct_grads(False)
+        if opt is not None:
+            opt.close()
 
 
 def test_batched_weight_packing_equals_per_layer_packing(cuda):

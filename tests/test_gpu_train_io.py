@@ -281,7 +281,6 @@ def test_fused_allreduce_sgd_ema_kernel_on_one_rank_equals_the_plain_optimizer_l
             opt = FusedSgdEma(m, lr=0.01, ema=True, direct_grads=True, peer_group=dist.group.WORLD)
         except Exception as e:                      # noqa: BLE001
             pytest.skip(f"symmetric memory unavailable: {e!r}")
-        train_conv.set_direct_grads(False)
         g = torch.Generator(device=cuda).manual_seed(5)
         for _ in range(2):
             opt.flat_grad.copy_(torch.randn(opt.flat_grad.shape, generator=g, device=cuda) * 0.1)
@@ -307,6 +306,5 @@ def test_fused_allreduce_sgd_ema_kernel_on_one_rank_equals_the_plain_optimizer_l
                 assert torch.equal(a, b)
             assert torch.equal(opt.flat_grad, grads)            # one rank: the reduced slice is the gradient itself
     finally:
-        train_conv.set_direct_grads(False)
         if created:
             dist.destroy_process_group()

@@ -21,7 +21,6 @@ dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)                               # identical parameters on every rank
 model = yx.YoloxConfig.get_named_config("yolox_s").get_model().to(dev).train()
 opt = FusedSgdEma(model, lr=0.01, ema=True, direct_grads=True, peer_group=dist.group.WORLD)
-train_conv.set_direct_grads(False)                 # this script writes the gradients itself
 g = torch.Generator(device=dev).manual_seed(100 + rank)    # different gradients per rank
 
 
