@@ -261,10 +261,15 @@ class CspLayer(_B200Block):
         ])
 
     def _train_forward(self, x):
+        from .streams import Branch
+
+        br = Branch(x, 0)                    # conv2 (+ its BatchNorm) next to conv1 -> bottleneck chain, forward and backward
+        with br:
+            x_2 = self.conv2._train_forward(x)
         x_1 = self.conv1._train_forward(x)
-        x_2 = self.conv2._train_forward(x)
         for blk in self.m:
             x_1 = blk._train_forward(x_1)
+        br.join()
         return self.conv3._train_forward(torch.cat((x_1, x_2), dim=1))
 
     def lower(self, b, x, out=None):

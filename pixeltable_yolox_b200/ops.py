@@ -589,7 +589,7 @@ def bn_act_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, r
     mean = torch.empty((Cc,), dtype=torch.float32, device=dev)
     invstd = torch.empty((Cc,), dtype=torch.float32, device=dev)
     nbytes = lib().yx_bn_act_workspace_bytes(N, Cc, H * W)
-    ws = _workspace(dev, nbytes, "bn")
+    ws = _workspace(dev, nbytes, f"bn:{stream_ptr(dev)}")          # per stream: branches of the step run concurrently
     with on_device(dev):
         check(lib().yx_bn_act_train_fwd(x.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(), beta.data_ptr(),
                                         float(eps), float(momentum), 0 if running_mean is None else running_mean.data_ptr(),
@@ -622,7 +622,7 @@ def bn_act_train_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, bet
     dx = torch.empty_like(x)
     dgamma = torch.empty((Cc,), dtype=torch.float32, device=dev)
     dbeta = torch.empty((Cc,), dtype=torch.float32, device=dev)
-    ws = _workspace(dev, lib().yx_bn_act_workspace_bytes(N, Cc, H * W), "bn")
+    ws = _workspace(dev, lib().yx_bn_act_workspace_bytes(N, Cc, H * W), f"bn:{stream_ptr(dev)}")
     with on_device(dev):
         check(lib().yx_bn_act_train_bwd(x.data_ptr(), dy.data_ptr(), dtype_code(x.dtype), 1 if cl else 0, N, Cc, H * W, gamma.data_ptr(),
                                         beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(act), dx.data_ptr(),

@@ -164,15 +164,30 @@ class YoloxHead(_B200Block):
         synthetic.randomize_and_calibrate; never by the eval hot path)."""
         from .train_conv import conv2d
 
-        outs = []
+        from .streams import Branch
+
+        # the levels are independent chains and so are the two towers of a level (yolo_head.py:140-160): level k on side
+        # stream 1 + k, its reg tower on side stream 4 + k; every kernel here is a fraction of a wave at training batch sizes
+        outs, levels = [None] * len(xin), []
         for k, x in enumerate(xin):
-            x = self.stems[k]._train_forward(x)
-            cls_feat, reg_feat = x, x
-            for blk in self.cls_convs[k]:
-                cls_feat = blk._train_forward(cls_feat)
-            for blk in self.reg_convs[k]:
-                reg_feat = blk._train_forward(reg_feat)
-            outs.append((conv2d(reg_feat, self.reg_preds[k]), conv2d(reg_feat, self.obj_preds[k]), conv2d(cls_feat, self.cls_preds[k])))
+            lvl = Branch(x, 1 + k)
+            with lvl:
+                x = self.stems[k]._train_forward(x)
+                tower = Branch(x, 4 + k)
+                with tower:
+                    reg_feat = x
+                    for blk in self.reg_convs[k]:
+                        reg_feat = blk._train_forward(reg_feat)
+                    reg_out, obj_out = conv2d(reg_feat, self.reg_preds[k]), conv2d(reg_feat, self.obj_preds[k])
+                cls_feat = x
+                for blk in self.cls_convs[k]:
+                    cls_feat = blk._train_forward(cls_feat)
+                cls_out = conv2d(cls_feat, self.cls_preds[k])
+                tower.join()
+                outs[k] = (reg_out, obj_out, cls_out)
+            levels.append(lvl)
+        for lvl in levels:
+            lvl.join()
         return outs
 
     # ------------------------------------------------------------------ forward
