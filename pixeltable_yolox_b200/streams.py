@@ -30,6 +30,19 @@ def side_stream(dev: torch.device, idx: int) -> "torch.cuda.Stream":
     return s
 
 
+_ready = {}
+
+
+def mark_ready(x: torch.Tensor) -> torch.Tensor:
+    """Record "x is complete" on the current stream; a Branch created on x later forks from this point instead of from the
+    point of its creation (YoloPafpn: the stride-8 head level only needs pan_out2, not the bottom-up half of the neck)."""
+    if enabled(x):
+        import weakref
+
+        _ready[id(x)] = (weakref.ref(x), torch.cuda.current_stream(x.device).record_event())
+    return x
+
+
 def enabled(x: torch.Tensor) -> bool:
     return x.is_cuda and os.environ.get("YX_TRAIN_BRANCHES", "1") != "0"
 
@@ -43,7 +56,10 @@ class Branch:
         if self.on:
             self.dev = x.device
             self.side = side_stream(self.dev, idx)
-            self.side.wait_event(torch.cuda.current_stream(self.dev).record_event())
+            # fork point: the event `mark_ready` attached to x when it was produced (the branch then overlaps whatever the
+            # producing stream enqueued after x), else "now"
+            ev = _ready.pop(id(x), None)
+            self.side.wait_event(ev[1] if ev is not None and ev[0]() is x else torch.cuda.current_stream(self.dev).record_event())
             self.ctx = None
 
     def __enter__(self):

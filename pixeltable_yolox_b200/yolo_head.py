@@ -159,9 +159,10 @@ class YoloxHead(_B200Block):
         self.hw = [torch.Size(v) for v in hw]
         return head_out
 
-    def _torch_raw_outputs(self, xin):
+    def _torch_raw_outputs(self, xin, rows=None):
         """Prediction-conv outputs per level through torch ops (used by the training branch and by
-        synthetic.randomize_and_calibrate; never by the eval hot path)."""
+        synthetic.randomize_and_calibrate; never by the eval hot path). rows(k, reg, obj, cls): optional per-level
+        continuation that runs inside the level's branch; its result replaces the (reg, obj, cls) tuple."""
         from .train_conv import conv2d
 
         from .streams import Branch
@@ -184,7 +185,7 @@ class YoloxHead(_B200Block):
                     cls_feat = blk._train_forward(cls_feat)
                 cls_out = conv2d(cls_feat, self.cls_preds[k])
                 tower.join()
-                outs[k] = (reg_out, obj_out, cls_out)
+                outs[k] = (reg_out, obj_out, cls_out) if rows is None else rows(k, reg_out, obj_out, cls_out)
             levels.append(lvl)
         for lvl in levels:
             lvl.join()
@@ -197,11 +198,15 @@ class YoloxHead(_B200Block):
 
             return run_head(self, xin)
         outputs, origin_preds, x_shifts, y_shifts, expanded_strides = [], [], [], [], []
-        for k, (reg_output, obj_output, cls_output) in enumerate(self._torch_raw_outputs(xin)):
+
+        def rows(k, reg_output, obj_output, cls_output):
             # cat + view + permute + decode (get_output_and_grid) and the origin_preds gather in one transposing kernel
-            # (csrc/yx_train.cu), fp32 rows out; only the (cached) grid is still built with torch
-            output, origin = _TrainRows.apply(reg_output, obj_output, cls_output, self.strides[k], self.use_l1)
-            grid = self._level_grid(k, reg_output.shape[-2], reg_output.shape[-1], xin[0].type())
+            # (csrc/yx_train.cu), fp32 rows out, still inside the level's branch
+            return _TrainRows.apply(reg_output, obj_output, cls_output, self.strides[k], self.use_l1) + (reg_output.shape,)
+
+        for k, (output, origin, shape) in enumerate(self._torch_raw_outputs(xin, rows)):
+            # only the (cached) grid is still built with torch
+            grid = self._level_grid(k, shape[-2], shape[-1], xin[0].type())
             x_shifts.append(grid[:, :, 0])
             y_shifts.append(grid[:, :, 1])
             expanded_strides.append(self._level_strides(k, grid.shape[1], xin[0]))

@@ -37,9 +37,13 @@ class YoloPafpn(_B200Block):
         fpn_out0 = self.lateral_conv0._train_forward(x0)
         f_out0 = self.C3_p4._train_forward(torch.cat([self.upsample(fpn_out0), x1], 1))
         fpn_out1 = self.reduce_conv1._train_forward(f_out0)
-        pan_out2 = self.C3_p3._train_forward(torch.cat([self.upsample(fpn_out1), x2], 1))
+        from .streams import mark_ready
+
+        # the head's level chains fork from the point their input was produced: the stride-8 level (the heaviest) then runs
+        # next to the bottom-up half of the neck, like the lanes of the inference plan
+        pan_out2 = mark_ready(self.C3_p3._train_forward(torch.cat([self.upsample(fpn_out1), x2], 1)))
         p_out1 = torch.cat([self.bu_conv2._train_forward(pan_out2), fpn_out1], 1)
-        pan_out1 = self.C3_n3._train_forward(p_out1)
+        pan_out1 = mark_ready(self.C3_n3._train_forward(p_out1))
         p_out0 = torch.cat([self.bu_conv1._train_forward(pan_out1), fpn_out0], 1)
         pan_out0 = self.C3_n4._train_forward(p_out0)
         return (pan_out2, pan_out1, pan_out0)
