@@ -308,3 +308,56 @@ def test_fused_allreduce_sgd_ema_kernel_on_one_rank_equals_the_plain_optimizer_l
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_captured_training_step_with_branches_replays_bit_identically(cuda):
+    """The captured step with everything switched on (tcgen05 convs, batched weight packing, direct gradient accumulation,
+    weight gradients on their own stream, network branches on side streams): with lr = 0 the parameters never change, so
+    every replay must give the same loss and the same gradients, bit for bit -- a race between the graph's branches, or
+    memory handed to two streams at once, shows up as a replay that differs (tools/gpu_train_stress.py: 300 replays of the
+    full-size step)."""
+    from pixeltable_yolox_b200 import train_conv
+    from pixeltable_yolox_b200.optim import FusedSgdEma
+
+    torch.manual_seed(0)
+    m = yx.YoloxConfig("stress", depth=0.33, width=0.25).get_model().to(cuda).train().to(memory_format=torch.channels_last)
+    x = torch.from_numpy(syn.images(4, 160, 160, seed=3)).to(cuda).contiguous(memory_format=torch.channels_last)
+    lab = torch.from_numpy(syn.labels(4, max_gt=16, seed=5, size=160.0, counts=[3, 0, 16, 7])).to(cuda)
+    opt = FusedSgdEma(m, lr=0.0, direct_grads=True)
+    train_conv.attach_packer(m, torch.bfloat16)
+    try:
+        def eager():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = m(x, lab)
+            opt.zero_grad()
+            out["total_loss"].backward()
+            opt.step(0.0)
+            return out["total_loss"].detach().clone()
+
+        side = torch.cuda.Stream(cuda)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                l_eager = eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = m(x, lab)
+            loss = out["total_loss"]
+            opt.zero_grad()
+            loss.backward()
+            opt.join()
+            grads = opt.flat_grad.clone()
+            opt.step_captured()
+        opt.set_hyper(0.0); g.replay(); torch.cuda.synchronize()
+        l0, g0 = loss.detach().clone(), grads.clone()
+        assert torch.equal(l0, l_eager) and float(g0.abs().max()) > 0
+        for _ in range(40):
+            opt.set_hyper(0.0); g.replay(); torch.cuda.synchronize()
+            assert torch.equal(loss.detach(), l0)
+            assert torch.equal(grads, g0)
+    finally:
+        opt.close()
+        m.__dict__.pop("_yx_train_packer", None)
