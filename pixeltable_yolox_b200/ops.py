@@ -226,7 +226,7 @@ def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
     key = (dev.index, tag)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        if ws is not None and tag == "wgrad":
+        if ws is not None and tag.startswith("wgrad"):
             # weight-gradient launches may still be running on the side stream (train_conv): the outgrown buffer stays
             # allocated until the streams are joined, so the caching allocator cannot hand it to another stream
             _ws_retired.setdefault(dev.index, []).append(ws)
@@ -695,7 +695,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor, ksi
     nbytes = lib().yx_conv_wgrad_workspace_bytes(*args)
     if nbytes < 0:
         check(-1, "conv_wgrad (workspace query)")
-    ws = _workspace(dev, nbytes, "wgrad")
+    ws = _workspace(dev, nbytes, f"wgrad:{stream_ptr(dev)}")        # per stream: wgrad launches of several layers run concurrently
     with on_device(dev):
         check(lib().yx_conv_wgrad(xv.ptr, xv.ld, dv.ptr, dv.ld, dtype_code(x.dtype), *args, i, o, dw.data_ptr(), so, si, st,
                                   0 if accumulate_into is None else 1, ws.data_ptr(), ws.numel(), stream_ptr(dev)), "conv_wgrad")

@@ -56,19 +56,26 @@ def direct_target(param: torch.Tensor) -> Optional[torch.Tensor]:
 _wgrad_side = {}
 
 
+_N_WGRAD_STREAMS = max(1, int(os.environ.get("YX_WGRAD_STREAMS", "3")))
+
+
 def _side(dev: torch.device):
+    """(stream, pending list) for the next weight gradient: round robin over YX_WGRAD_STREAMS side streams (each with its own
+    partial-sum workspace, ops.conv_wgrad keys it by stream), so consecutive layers' wgrad launches overlap each other too."""
     ent = _wgrad_side.get(dev)
     if ent is None:
-        ent = _wgrad_side[dev] = [torch.cuda.Stream(dev), []]
-    return ent
+        ent = _wgrad_side[dev] = [[torch.cuda.Stream(dev) for _ in range(_N_WGRAD_STREAMS)], [], 0]
+    ent[2] = (ent[2] + 1) % len(ent[0])
+    return ent[0][ent[2]], ent[1]
 
 
 def join_wgrad(dev: Optional[torch.device] = None) -> None:
     """Make the current stream wait for the side-stream weight gradients (call before reading .grad: FusedSgdEma.step does)."""
-    for d, (stream, pending) in _wgrad_side.items():
+    for d, (streams, pending, _) in _wgrad_side.items():
         if dev is None or d == dev:
             if pending:
-                torch.cuda.current_stream(d).wait_stream(stream)
+                for stream in streams:
+                    torch.cuda.current_stream(d).wait_stream(stream)
                 pending.clear()
                 ops.release_retired_workspaces(d)
 
