@@ -4,12 +4,13 @@ Replaces what torch autograd dispatches to cuDNN for `BaseConv.conv` (yolox/mode
 prediction convs (yolox/models/yolo_head.py:94-120) inside `Trainer.train_one_iter` (yolox/core/trainer.py:96-129):
 
   forward  y  = conv(x, W) (+ bias)     csrc/yx_conv_tc.cu, the inference implicit GEMM with unfolded weights, no activation
-  dgrad    dx = conv(dy, rot180(W)^T)   the same kernel (stride 2: on the zero-stuffed dy, csrc/yx_wgrad_tc.cu: dilate2)
+  dgrad    dx = conv(dy, rot180(W)^T)   the same kernel (stride 2: the four sub-pixel phases as one conv over dy with a
+                                        depth-to-space store; odd input sizes: on the zero-stuffed dy, dilate2)
   wgrad    dW = sum_p dy[p] (x) x[p+t]  csrc/yx_wgrad_tc.cu (tcgen05, both operands MN-major straight from NHWC)
 
 Activations stay 16-bit channels_last (NHWC) between layers, which is the layout every kernel of this package uses; the
-fp32 master weights are packed to 16-bit operands once per step and per layer (one launch for the forward and the dgrad
-operand). Numerics match torch.autocast: 16-bit operands, fp32 accumulation, fp32 weight gradients.
+fp32 master weights are packed to 16-bit operands once per step (WeightPacker: one launch for all layers; without it one
+launch per layer for the forward and the dgrad operand). Numerics match torch.autocast: 16-bit operands, fp32 accumulation, fp32 weight gradients.
 """
 from __future__ import annotations
 
@@ -49,7 +50,7 @@ def direct_target(param: torch.Tensor) -> Optional[torch.Tensor]:
 
 
 # With direct gradient accumulation the weight-gradient launches have no consumer before the optimizer step, so they run on a
-# side stream (one per device) next to the backward's critical chain  BatchNorm backward -> dgrad -> BatchNorm backward ...:
+# side streams (YX_WGRAD_STREAMS per device, round robin) next to the backward's critical chain  BatchNorm backward -> dgrad -> BatchNorm backward ...:
 # every kernel of an 8-image step is a fraction of a wave, so the two chains overlap (a CUDA-graph capture records the fork
 # and the join as graph branches). The wgrad inputs (saved activation, output gradient) are kept referenced until
 # `join_wgrad()` so that the caching allocator cannot hand their memory to the main stream while the side stream reads it.
@@ -93,7 +94,7 @@ class WeightPacker:
 
         self.dtype = dtype
         self.entries = {}
-        rows, chunks, keep = [], [], []
+        rows, chunks = [], []
         dev = None
         for mod in model.modules():
             if not isinstance(mod, torch.nn.Conv2d) or mod.groups != 1 or mod.weight.dtype != torch.float32 or not mod.weight.is_cuda:
