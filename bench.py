@@ -971,19 +971,6 @@ def time_train_graph(model, opt, x, lab, steps, amp_dtype, world, dev, host=None
 
         ms_host = timed(from_host)
         loss_host = last[0]
-        # the same with the images uploaded as uint8 (the pixels are integers 0..255: exact), a quarter of the bytes, and
-        # converted on the device into the graph's input buffer
-        hu8 = host[0].to(torch.uint8).contiguous(memory_format=torch.channels_last if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous() else torch.contiguous_format).pin_memory()
-        xu8 = torch.empty_like(hu8, device=dev)
-
-        def from_host_u8():
-            xu8.copy_(hu8, non_blocking=True); lab.copy_(host[1], non_blocking=True)
-            x.copy_(xu8)
-            replay()
-            last[0] = float(loss.item())
-
-        time_train_graph.ms_host_u8 = timed(from_host_u8)
-        time_train_graph.loss_host_u8 = last[0]
     return ms_resident, loss_resident, ms_host, loss_host
 
 
@@ -1016,8 +1003,8 @@ def run_train(args, world, rank, dev):
     xh, labh, counts = train_batch(args, rank, B)
     xh, labh = xh.pin_memory(), labh.pin_memory()
     x, lab = xh.to(dev), labh.to(dev)
-    if args.train_format == "channels_last":
-        x = x.contiguous(memory_format=torch.channels_last)
+    if args.train_format == "channels_last" and os.environ.get("YX_TRAIN_CONV", "1") == "0":
+        x = x.contiguous(memory_format=torch.channels_last)      # (our Focus kernel reads the NCHW image as it arrives)
     clocks = ClockSampler(dev.index)
     clocks.start(); clocks.wait_first()
     w0 = time.perf_counter()
@@ -1032,8 +1019,6 @@ def run_train(args, world, rank, dev):
         gms, gloss, gms_host, gloss_host = time_train_graph(net, opt, x, lab, args.steps, amp_dtype, world, dev, host=(xh, labh))
         graph_line = {"ms_per_step": gms, "images_per_second": world * B / (gms / 1e3), "loss_last_step": gloss,
                       "e2e_ms_per_step": gms_host, "e2e_images_per_second": world * B / (gms_host / 1e3), "e2e_loss_last_step": gloss_host,
-                      "e2e_uint8_input_ms_per_step": getattr(time_train_graph, "ms_host_u8", None),
-                      "e2e_uint8_input_images_per_second": (world * B / (time_train_graph.ms_host_u8 / 1e3)) if getattr(time_train_graph, "ms_host_u8", None) else None,
                       "what": ("forward + SimOTA + losses + backward + SGD/EMA captured once with torch.cuda.graph and replayed"
                                if world == 1 else
                                "ONE captured graph per step: forward + SimOTA + losses + backward + yx_allreduce_sgd_ema_step (gradient "

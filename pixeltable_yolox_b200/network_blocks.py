@@ -310,6 +310,20 @@ class Focus(_B200Block):
         self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act)
 
     def _train_forward(self, x):
+        from . import ops
+        from .train_conv import usable
+
+        dt = usable(x, self.conv.conv) if x.dim() == 4 else None
+        if (dt is not None and x.shape[1] == 3 and x.is_contiguous() and x.dtype in (torch.float32, torch.uint8)
+                and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and not x.requires_grad
+                and os.environ.get("YX_TRAIN_FOCUS", "1") != "0"):
+            # the four strided slices + cat + cast + channel padding of the torch path (six launches over the largest tensor
+            # of the step) as the inference space-to-depth kernel: image -> 16-bit NHWC with the 12 Focus channels padded to 16,
+            # which is the layout the stem conv's tcgen05 kernels take (the conv pads its 12 input channels to 16 anyway)
+            B, _, H, W = x.shape
+            s2d = torch.empty((B, 16, H // 2, W // 2), dtype=dt, device=x.device, memory_format=torch.channels_last)
+            ops.focus_s2d(x, ops._nhwc(s2d))
+            return self.conv._train_forward(s2d)
         tl, tr = x[..., ::2, ::2], x[..., ::2, 1::2]
         bl, br = x[..., 1::2, ::2], x[..., 1::2, 1::2]
         return self.conv._train_forward(torch.cat((tl, bl, tr, br), dim=1))

@@ -400,3 +400,26 @@ def test_backbone_prefix_gradients_match_fp32_where_the_network_is_not_yet_chaot
     # (torch's depthwise / cuDNN backward kernels use atomics: both cosines move in the fourth decimal from run to run)
     assert c_ours > 0.996 and c_ours >= c_t16 - 0.003, (c_ours, c_t16)
     assert abs(res["ours"][0] - res["fp32"][0]) <= 3e-3 * abs(res["fp32"][0]), (res["ours"][0], res["fp32"][0])
+
+
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.uint8])
+def test_focus_training_forward_through_the_space_to_depth_kernel_equals_the_torch_slicing(cuda, in_dtype, monkeypatch):
+    """Focus in the training step (network_blocks.py:193-208): space-to-depth kernel + stem conv on 16 padded channels against
+    the four strided slices + cat of the torch path -- same conv kernel, same operands, so the outputs and the weight
+    gradients are bit-identical."""
+    from pixeltable_yolox_b200.network_blocks import Focus
+
+    torch.manual_seed(2)
+    f = Focus(3, 32, ksize=3).to(cuda).train()
+    x = torch.from_numpy(syn.images(2, 64, 96, seed=9)).to(cuda).to(in_dtype)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YX_TRAIN_FOCUS", flag)
+        f.zero_grad(set_to_none=True)
+        f.conv.bn.running_mean.zero_(); f.conv.bn.running_var.fill_(1.0)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = f(x)
+        y.float().square().mean().backward()
+        res.append((y.detach().clone(), f.conv.conv.weight.grad.clone(), f.conv.bn.weight.grad.clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
