@@ -1029,6 +1029,17 @@ def run_train(args, world, rank, dev):
                                "two captured graphs (forward + SimOTA + losses + backward | average + SGD/EMA) around one eager "
                                "ncclAllReduce of the flat gradient buffer every .grad is a view of, on a copy of the module "
                                "without the DDP wrapper") + "; lr / EMA decay reach the captured optimizer launch via a device buffer"}
+        if world == 1 and amp_dtype is not None and os.environ.get("YX_TRAIN_CONV", "1") != "0":
+            # the same graph step fed with uint8 images (the pixels are integers 0..255: exact; the Focus kernel reads them as
+            # bytes): a quarter of the upload. The reference's data path hands the trainer fp32 images, so `e2e` stays fp32.
+            try:
+                xh8 = xh.to(torch.uint8).pin_memory()
+                _, _, gms_u8, gloss_u8 = time_train_graph(net, opt, xh8.to(dev), lab, args.steps, amp_dtype, world, dev, host=(xh8, labh))
+                graph_line.update({"e2e_uint8_input_ms_per_step": gms_u8, "e2e_uint8_input_images_per_second": B / (gms_u8 / 1e3),
+                                   "e2e_uint8_input_h2d_bytes_per_step": xh8.numel() + labh.numel() * 4,
+                                   "e2e_uint8_input_loss_last_step": gloss_u8})
+            except Exception as e:                    # noqa: BLE001
+                graph_line["e2e_uint8_input_failed"] = repr(e)[:200]
     except Exception as e:                            # noqa: BLE001
         import traceback
 
