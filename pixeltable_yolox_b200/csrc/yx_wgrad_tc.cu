@@ -339,7 +339,7 @@ static int wgrad_plan(int batch, int in_h, int in_w, int in_c, int out_h, int ou
   // space and a shorter epilogue per CTA beat the saved re-loads of the dy tile; N = 16 keeps all nine taps together
   int sg_max = p.N <= 16 ? 512 / p.Ncol : (128 / p.N > 1 ? 128 / p.N : 1);
   if (sg_max > p.slices) sg_max = p.slices;
-  if (const char* e = getenv("YX_WGRAD_SG")) { const int v = atoi(e); if (v >= 1 && v < sg_max) sg_max = v; }
+  if (const char* e = getenv("YX_WGRAD_SG")) { const int v = atoi(e); if (v >= 1 && v * p.Ncol <= 512) sg_max = v < p.slices ? v : p.slices; }
   p.n_groups = (p.slices + sg_max - 1) / sg_max;
   p.SG = (p.slices + p.n_groups - 1) / p.n_groups;
   p.n_groups = (p.slices + p.SG - 1) / p.SG;

@@ -11,8 +11,8 @@ sys.path.insert(0, str(ROOT))
 from pixeltable_yolox_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
-B = 8
-LAYERS = [(256, 256, 20, 3, 1), (512, 256, 20, 1, 1), (128, 128, 40, 3, 1), (256, 128, 40, 1, 1), (128, 128, 80, 3, 1),
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+LAYERS = [(128, 128, 80, 3, 1), (256, 256, 40, 3, 1), (64, 64, 160, 3, 1), (128, 128, 40, 3, 1)] if B >= 32 else [(256, 256, 20, 3, 1), (512, 256, 20, 1, 1), (128, 128, 40, 3, 1), (256, 128, 40, 1, 1), (128, 128, 80, 3, 1),
           (64, 64, 80, 3, 1), (32, 32, 160, 3, 1), (16, 32, 320, 3, 1), (32, 64, 320, 3, 2), (128, 256, 40, 3, 2)]
 
 
@@ -38,7 +38,7 @@ for ci, co, H, k, s in LAYERS:
     w = torch.empty(co, ci, k, k, device=dev).contiguous(memory_format=torch.channels_last)
     row = []
     for sg in (0, 1, 2, 4):
-        for ks in (0, 1, 2, 4, 8, 16, 32, 64):
+        for ks in ((0, 8, 16, 32, 64, 148) if B >= 32 else (0, 1, 2, 4, 8, 16, 32, 64)):
             for kp in (0, 32):
                 for name, v in (("YX_WGRAD_SG", sg), ("YX_WGRAD_KSPLIT", ks), ("YX_WGRAD_KP", kp)):
                     if v:
