@@ -142,6 +142,45 @@ sgd_ema_kernel(const long long* __restrict__ table, const int* __restrict__ chun
   const long long n = row[4];
   const float wd = __int_as_float((int)(row[5] & 0xffffffffll));
   const long long e1 = min(n, (long long)e0 + chunk_elems);
+  // 16-byte vectors when the tensor allows it (every conv weight and BatchNorm vector of the named configs): the kernel moves
+  // eight fp32 streams, 4-byte accesses left it at 3.1 TB/s
+  const bool vec = (n & 3) == 0 && (e0 & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(buf) |
+                     reinterpret_cast<uintptr_t>(ema)) & 15) == 0;
+  if (vec) {
+    for (long long i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += kSgdThreads) {
+      const float4 pv = reinterpret_cast<const float4*>(p)[i];
+      float v[4] = {pv.x, pv.y, pv.z, pv.w};
+      if (g) {
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (momentum != 0.0f && !first_step) bq = reinterpret_cast<const float4*>(buf)[i];
+        const float d4[4] = {gv.x, gv.y, gv.z, gv.w}, b4[4] = {bq.x, bq.y, bq.z, bq.w};
+        float nb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float d = d4[k];
+          if (wd != 0.0f) d = fmaf(wd, v[k], d);
+          if (momentum != 0.0f) {
+            nb[k] = first_step ? d : __fadd_rn(__fmul_rn(momentum, b4[k]), d);
+            d = nesterov ? fmaf(momentum, nb[k], d) : nb[k];
+          }
+          v[k] = fmaf(-lr, d, v[k]);
+        }
+        if (momentum != 0.0f) reinterpret_cast<float4*>(buf)[i] = make_float4(nb[0], nb[1], nb[2], nb[3]);
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      if (ema) {
+        const float4 eq = reinterpret_cast<const float4*>(ema)[i];
+        const float e4[4] = {eq.x, eq.y, eq.z, eq.w};
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = __fadd_rn(__fmul_rn(e4[k], ema_decay), __fmul_rn(ema_rest, v[k]));
+        reinterpret_cast<float4*>(ema)[i] = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    return;
+  }
   for (long long i = e0 + threadIdx.x; i < e1; i += kSgdThreads) {
     float v = p[i];
     if (g) {
