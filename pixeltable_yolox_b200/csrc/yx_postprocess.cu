@@ -39,7 +39,28 @@ static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassC
 static constexpr int kKeptEntryBytes = 20;  // box 16 + (class | next << 10) 4; the area is recomputed (3 flops)
 static constexpr int kNmsSmemBudget = 225 * 1024;   // dynamic shared memory: 8 652 kept entries, i.e. every anchor of a 640^2 image
 
+static constexpr int kNmsMaxCluster = 8;             // CTAs of one image's thread-block cluster (sort_nms_kernel<true>)
+
 __device__ __forceinline__ uint32_t orderable(float f) { return orderable_f32(f); }
+
+__device__ __forceinline__ uint32_t nms_cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ uint32_t nms_cluster_nctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r;
+}
+// every thread of every CTA of the cluster; release / acquire at cluster scope (orders shared memory of the own CTA,
+// distributed shared memory and the global workspace before / after it); also a CTA barrier
+__device__ __forceinline__ void nms_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of the same shared-memory object in CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ T* nms_peer(T* local, int rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<unsigned long long>(local)), "r"(rank));
+  return reinterpret_cast<T*>(out);
+}
 
 // ------------------------------------------------------------------------------------------
 // Stage 1
@@ -294,14 +315,94 @@ __device__ __forceinline__ void nms_small_warp(const NmsArgs& g, int b, int n, i
   }
 }
 
+// Ascending sort of keys[0, n) (unique 64-bit keys) by all threads of the CTA: bitonic network in its all-ascending
+// form -- for every block size one "flip" step (i against i ^ (size-1)) followed by half-cleaners (i against i ^ j,
+// j = size/4 .. 1). Because every compare-exchange is ascending, the slots >= n behave like +inf padding that never
+// moves, so pairs with a partner >= n are simply not enumerated: n = 8 400 costs about half of the padded 16 384
+// network. Four independent pairs are loaded before the first compare so that the shared-memory latency of a step
+// overlaps. Ends with a CTA barrier.
+__device__ __forceinline__ void sort_keys_asc(unsigned long long* keys, const int n, const int tid) {
+  for (int lg = 1; (1 << (lg - 1)) < n; ++lg) {
+    const int size = 1 << lg, half = size >> 1;
+    {
+      const int fb = n >> lg, rem = n & (size - 1);
+      const int full = fb << (lg - 1);                       // pairs of the complete blocks
+      const int cnt = full + max(0, rem - half);             // + pairs of the last, partial block whose partner is < n
+      for (int q0 = tid; q0 < cnt; q0 += 4 * kNmsThreads) {
+        unsigned long long a[4], c[4];
+        int lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * kNmsThreads;
+          if (q < cnt) {
+            const int blk = q < full ? (q >> (lg - 1)) : fb;
+            const int t = q < full ? (q & (half - 1)) : (size - rem) + (q - full);
+            lo[u] = (blk << lg) + t; hi[u] = (blk << lg) + size - 1 - t;
+            a[u] = keys[lo[u]]; c[u] = keys[hi[u]];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + u * kNmsThreads < cnt && a[u] > c[u]) { keys[lo[u]] = c[u]; keys[hi[u]] = a[u]; }
+      }
+      __syncthreads();
+    }
+    for (int lgj = lg - 2; lgj >= 0; --lgj) {
+      const int j = 1 << lgj;
+      const int cnt = ((n >> (lgj + 1)) << lgj) + max(0, (n & (2 * j - 1)) - j);
+      for (int q0 = tid; q0 < cnt; q0 += 4 * kNmsThreads) {
+        unsigned long long a[4], c[4];
+        int lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * kNmsThreads;
+          if (q < cnt) {
+            lo[u] = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+            a[u] = keys[lo[u]]; c[u] = keys[lo[u] | j];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + u * kNmsThreads < cnt && a[u] > c[u]) { keys[lo[u]] = c[u]; keys[lo[u] | j] = a[u]; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long nms_key(const NmsArgs& g, long long base, int i) {
+  if (g.keys) return g.keys[base + i];
+  float sc = g.src.scores[(base + i) * g.src.score_stride];
+  if (sc == 0.0f) sc = 0.0f;
+  return ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)i;
+}
+
+// CL = false: one CTA per image (grid = batch). CL = true: one thread-block cluster of R = 2 / 4 / 8 CTAs per image
+// (grid = batch * R, cluster dimension R), chosen by the host when batch * R CTAs are co-resident:
+//   sort     every CTA sorts one contiguous 1/R run of the key list in its own shared memory; the final position of a
+//            key is its index in its run plus its lower bounds in the other runs (binary searches through distributed
+//            shared memory; keys are unique), and the CTA scatters box / class / index there
+//   phase A  the kept list is dealt round-robin over the CTAs (entry e lives in CTA e % R): every CTA tests the whole
+//            chunk against its share, the 512 dead bits are OR-ed through distributed shared memory
+//   phase B  the (row, word) items of the chunk's suppression mask are dealt round-robin; every CTA stores its words
+//            into the mask of CTA 0
+//   phase C  greedy scan by one warp of CTA 0, which broadcasts the chunk's survivors; every CTA appends its share
+// Three cluster barriers per chunk. The arithmetic of every IoU test and the greedy order are those of CL = false:
+// kept rows are bit-identical for every R.
+template <bool CL>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs g) {
   extern __shared__ __align__(16) uint8_t nsm[];
   __shared__ float red[kNmsThreads / 32], red_mn[kNmsThreads / 32];
   __shared__ int red_cmax[kNmsThreads / 32], red_cmin[kNmsThreads / 32];
   __shared__ int s_nkept, s_ck;
   __shared__ unsigned s_removed[kChunkWords];
+  __shared__ unsigned s_deadx[CL ? kNmsMaxCluster * kChunkWords : 1];   // [R][16] dead bits found by every CTA
+  __shared__ float s_xf[CL ? kNmsMaxCluster * 2 : 1];                   // [R] (max, min) coordinate of every run
+  __shared__ int s_xi[CL ? kNmsMaxCluster * 2 : 1];                     // [R] (max, min) class of every run
 
-  const int b = blockIdx.x;
+  const int R = CL ? (int)nms_cluster_nctarank() : 1;
+  const int rank = CL ? (int)nms_cluster_ctarank() : 0;
+  const int b = CL ? (int)(blockIdx.x / (unsigned)R) : (int)blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const long long base = (long long)b * g.src.per_image;
@@ -323,67 +424,73 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   if (variant == 4) variant = (4LL * n > 4000) ? 1 : 0;
   if (variant == 5) variant = (4LL * n > 20000) ? 1 : 0;     // torchvision 0.17.2 (the reference's pin) on CUDA
 
+  // (n is the same in every CTA of a cluster: all exits and barrier counts below are uniform over the cluster)
   if (n > 0 && n <= 32 && !g.no_small) {
-    if (warp == 0) nms_small_warp(g, b, n, variant, base);
+    if (warp == 0 && rank == 0) nms_small_warp(g, b, n, variant, base);
     return;
   }
   if (n > 0) {
-    // ---------------- sort ----------------
-    int P = 1;
-    while (P < n) P <<= 1;
-    unsigned long long* keys = (P <= g.smem_keys_cap) ? reinterpret_cast<unsigned long long*>(nsm)
-                                                      : (g.gkeys + (long long)b * g.gkeys_stride);
-    for (int i = tid; i < P; i += kNmsThreads) {
-      unsigned long long k = ~0ull;
-      if (i < n) {
-        if (g.keys) k = g.keys[base + i];
-        else {
-          float sc = g.src.scores[(base + i) * g.src.score_stride];
-          if (sc == 0.0f) sc = 0.0f;
-          k = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned long long)(unsigned)i;
-        }
-      }
-      keys[i] = k;
-    }
-    __syncthreads();
-    // Bitonic network; four independent pairs are loaded before the first compare so that the shared-memory latency of a
-    // stage overlaps (a register-blocked variant for the strides < 32 measured slower: 569k vs 330k clk at P = 16 384)
-    for (int size = 2; size <= P; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i0 = tid; i0 < (P >> 1); i0 += 4 * kNmsThreads) {
-          unsigned long long a[4], c[4];
-          int lo[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kNmsThreads;
-            lo[u] = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-            if (i < (P >> 1)) { a[u] = keys[lo[u]]; c[u] = keys[lo[u] | stride]; }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kNmsThreads;
-            if (i < (P >> 1) && ((a[u] > c[u]) == ((lo[u] & size) == 0))) { keys[lo[u]] = c[u]; keys[lo[u] | stride] = a[u]; }
-          }
-        }
-        __syncthreads();
-      }
-    }
-
-    tk[1] = clock64();
-    // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
     float mx = -INFINITY, mn = INFINITY;
     int cmax = 0, cmin = 0;
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
-      const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
-      const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
-      int c;
-      if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-      else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-      sbox[i] = bx; scls[i] = c; sidx[i] = idx;
-      mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
-      mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
-      cmax = max(cmax, c); cmin = min(cmin, c);
+    if constexpr (!CL) {
+      // ---------------- sort ----------------
+      int P = 1;
+      while (P < n) P <<= 1;
+      unsigned long long* keys = (P <= g.smem_keys_cap) ? reinterpret_cast<unsigned long long*>(nsm)
+                                                        : (g.gkeys + (long long)b * g.gkeys_stride);
+      for (int i = tid; i < n; i += kNmsThreads) keys[i] = nms_key(g, base, i);
+      __syncthreads();
+      sort_keys_asc(keys, n, tid);
+
+      tk[1] = clock64();
+      // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
+        const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
+        const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+        int c;
+        if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+        else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+        sbox[i] = bx; scls[i] = c; sidx[i] = idx;
+        mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+        mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
+        cmax = max(cmax, c); cmin = min(cmin, c);
+      }
+    } else {
+      // ---------------- sort: one run per CTA, then merge by rank ----------------
+      const int seg = (n + R - 1) / R;                      // run r = candidates [r * seg, min(n, (r + 1) * seg))
+      const int lo_r = min(n, rank * seg), m = min(n, lo_r + seg) - lo_r;
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(nsm);
+      for (int i = tid; i < m; i += kNmsThreads) keys[i] = nms_key(g, base, lo_r + i);
+      __syncthreads();
+      sort_keys_asc(keys, m, tid);
+      nms_cluster_sync();                                    // every run is final
+      tk[1] = clock64();
+      for (int i = tid; i < m; i += kNmsThreads) {
+        const unsigned long long k = keys[i];
+        int pos = i;
+        for (int rr = 0; rr < R; ++rr) {
+          if (rr == rank) continue;
+          const int lo2 = min(n, rr * seg), m2 = min(n, lo2 + seg) - lo2;
+          const unsigned long long* run = nms_peer(keys, rr);
+          int l = 0, h = m2;                                 // lower bound: keys of run rr below k
+          while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (run[mid] < k) l = mid + 1; else h = mid;
+          }
+          pos += l;
+        }
+        const int idx = (int)(unsigned)(k & 0xffffffffull);
+        const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
+        const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+        int c;
+        if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+        else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+        sbox[pos] = bx; scls[pos] = c; sidx[pos] = idx;
+        mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+        mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
+        cmax = max(cmax, c); cmin = min(cmin, c);
+      }
     }
     {
 #pragma unroll
@@ -401,10 +508,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         cmax = max(cmax, red_cmax[i]); cmin = min(cmin, red_cmin[i]);
       }
     }
+    if constexpr (CL) {
+      // all-reduce of the four extrema over the cluster (max / min are exact in any order)
+      if (tid < R) {
+        float* xf = nms_peer(s_xf, tid);
+        int* xi = nms_peer(s_xi, tid);
+        xf[rank * 2] = mx; xf[rank * 2 + 1] = mn;
+        xi[rank * 2] = cmax; xi[rank * 2 + 1] = cmin;
+      }
+      nms_cluster_sync();                                    // extrema exchanged; sorted rows visible; runs no longer read
+      for (int rr = 0; rr < R; ++rr) {
+        mx = fmaxf(mx, s_xf[rr * 2]); mn = fminf(mn, s_xf[rr * 2 + 1]);
+        cmax = max(cmax, s_xi[rr * 2]); cmin = min(cmin, s_xi[rr * 2 + 1]);
+      }
+    }
     if (variant == 0) {
       // boxes_for_nms = boxes + idxs.to(boxes) * (max_coordinate + 1)   (torchvision boxes.py)
       const float step = __fadd_rn(mx, 1.0f);
-      for (int i = tid; i < n; i += kNmsThreads) {
+      for (int i = rank * kNmsThreads + tid; i < n; i += R * kNmsThreads) {
         const float off = __fmul_rn((float)scls[i], step);
         float4 bx = sbox[i];
         bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
@@ -412,7 +533,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         sbox[i] = bx;
       }
     }
-    __syncthreads();
+    if constexpr (CL) nms_cluster_sync(); else __syncthreads();
 
     tk[2] = clock64();
     // ---------------- greedy NMS, chunk by chunk ----------------
@@ -425,7 +546,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     // shared memory (the sort buffer is dead now):
     //   chunk : box/area/class of the 512 candidates in flight, their 512x512 suppression bitmask, and a
     //           linked list of chunk members per class
-    //   kept  : boxes already kept (box, area, class) with a linked list per class
+    //   kept  : boxes already kept (box, area, class) with a linked list per class; with a cluster, this CTA's share
+    //           (global entry e = slot * R + rank)
     float4* cbox = reinterpret_cast<float4*>(nsm);                          // [kChunk]
     float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
     int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
@@ -438,6 +560,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     const int KC = g.kept_cap;
     float4* kbox = reinterpret_cast<float4*>(kbase);                          // [KC]
     int* kmeta = reinterpret_cast<int*>(kbase + (size_t)KC * 16);             // [KC] class, or class | (next + 1) << 10 with lists
+    unsigned* cmask_w = (CL && rank != 0) ? nms_peer(cmask, 0) : cmask;       // phase B stores into CTA 0's mask
 
     int J = 0x3fffffff;                                   // class window; "infinite" = ungated
     if (variant == 1) J = 0;
@@ -455,6 +578,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       const int cn = min(kChunk, n - c0);
       __syncthreads();
       const int nk = s_nkept;
+      const int nk_own = (nk + R - 1 - rank) / R;        // entries of the kept list this CTA holds
       // kNmsThreads == kChunk: thread t owns candidate c0 + t
       float4 me = make_float4(0, 0, 0, 0);
       float my_area = 0.f;
@@ -467,7 +591,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       if (tid == 0) s_ck = 0;
       // ---- phase A: against the boxes kept in earlier chunks
       if (!dead) {
-        const int nks = min(nk, KC);
+        const int nks = min(nk_own, KC);
         if (use_lists) {
           for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2)
             for (int k = khead[c2]; k >= 0; k = (kmeta[k] >> 10) - 1) {
@@ -481,8 +605,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
             if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
           }
         }
-        for (int k = KC; k < nk && !dead; ++k) {           // overflow of the shared-memory list
-          const int kp = kept[k];
+        for (int k = KC; k < nk_own && !dead; ++k) {       // overflow of the shared-memory list
+          const int kp = kept[k * R + rank];
           if (abs(scls[kp] - my_cls) > J) continue;
           const float4 kb = sbox[kp];
           if (suppresses(kb, box_area(kb), me, my_area, g.thr)) dead = true;
@@ -490,7 +614,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
       {
         const unsigned bal = __ballot_sync(0xffffffffu, dead);
-        if (lane == 0) s_removed[warp] = bal;
+        if constexpr (CL) {
+          if (lane < R) nms_peer(s_deadx, lane)[rank * kChunkWords + warp] = bal;
+          nms_cluster_sync();                              // (1) every CTA's dead bits have arrived
+          if (tid < kChunkWords) {
+            unsigned u = 0u;
+            for (int rr = 0; rr < R; ++rr) u |= s_deadx[rr * kChunkWords + tid];
+            s_removed[tid] = u;
+          }
+        } else {
+          if (lane == 0) s_removed[warp] = bal;
+        }
       }
       if (c0 == 0) tk[3] = clock64();
       // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i)
@@ -502,7 +636,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         // per-class lists instead degenerates to divergent pointer chasing when a few classes dominate)
         const int nw = (cn + 31) >> 5;
         const int items = 32 * (nw * (nw + 1) / 2);
-        for (int q = tid; q < items; q += kNmsThreads) {
+        for (int q = rank * kNmsThreads + tid; q < items; q += R * kNmsThreads) {
           int rb = 0, rem = q;
           while (rem >= 32 * (nw - rb)) { rem -= 32 * (nw - rb); ++rb; }
           const int per = nw - rb;
@@ -522,15 +656,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
                 bits |= (1u << jb);
             }
           }
-          cmask[row * kChunkWords + w] = bits;
+          cmask_w[row * kChunkWords + w] = bits;
         }
-        __syncthreads();
+        if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // (2) CTA 0 holds the whole mask
       }
       if (c0 == 0) tk[4] = clock64();
       // ---- phase C: one warp walks the chunk word by word (32 candidates); lane l owns word l of the removed
       //      set. Inside a word the greedy order is resolved on the 32x32 diagonal block held in registers;
-      //      the kept rows are then OR-ed into the later words with one warp reduction per word.
-      if (warp == 0) {
+      //      the rows of the kept boxes are then OR-ed into the later words.
+      if (warp == 0 && rank == 0) {
         unsigned removed = lane < kChunkWords ? s_removed[lane] : 0xffffffffu;
         int cnt = 0;
         const int nwords = (cn + 31) >> 5;
@@ -550,17 +684,34 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
             }
           }
           const bool mine = (keptw >> lane) & 1u;
-          if (mine) ck[cnt + __popc(keptw & ((1u << lane) - 1u))] = w * 32 + lane;
+          if (mine) {
+            const int slot = cnt + __popc(keptw & ((1u << lane) - 1u));
+            ck[slot] = w * 32 + lane;
+            if constexpr (CL)
+              for (int rr = 1; rr < R; ++rr) nms_peer(ck, rr)[slot] = w * 32 + lane;
+          }
           cnt += __popc(keptw);
-          // rows of the kept boxes OR-ed into the later words: lane i contributes its row, one warp reduction per word
-          for (int l = w + 1; l < nwords; ++l) {
-            const unsigned r = __reduce_or_sync(0xffffffffu, mine ? cmask[(w * 32 + lane) * kChunkWords + l] : 0u);
-            if (lane == l) removed |= r;
+          // rows of the kept boxes OR-ed into the later words. Few kept boxes (dense scenes: most of the word is
+          // suppressed): lane l walks the kept rows and ORs word l of each (independent loads). Many: lane i
+          // contributes its row, one warp reduction per later word. Same result either way.
+          if (__popc(keptw) < nwords - 1 - w) {
+            if (lane > w && lane < nwords) {
+              unsigned r = 0u;
+              for (unsigned mk = keptw; mk; mk &= mk - 1u) r |= cmask[(w * 32 + __ffs(mk) - 1) * kChunkWords + lane];
+              removed |= r;
+            }
+          } else {
+            for (int l = w + 1; l < nwords; ++l) {
+              const unsigned r = __reduce_or_sync(0xffffffffu, mine ? cmask[(w * 32 + lane) * kChunkWords + l] : 0u);
+              if (lane == l) removed |= r;
+            }
           }
         }
         if (lane == 0) s_ck = cnt;
+        if constexpr (CL)
+          if (lane > 0 && lane < R) *nms_peer(&s_ck, lane) = cnt;
       }
-      __syncthreads();
+      if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) every CTA knows the chunk's survivors
       if (c0 == 0) tk[5] = clock64();
       // ---- append the chunk's survivors to the kept list (parallel; list order is irrelevant)
       {
@@ -568,11 +719,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         if (tid < cnt) {
           const int i = ck[tid];
           const int e = nk + tid;
-          kept[e] = c0 + i;
-          if (e < KC) {
+          if (rank == 0) kept[e] = c0 + i;
+          const int slot = e / R;
+          if (e - slot * R == rank && slot < KC) {
             const int ci = ccls[i];
-            kbox[e] = cbox[i];
-            kmeta[e] = use_lists ? (ci | ((atomicExch(&khead[ci], e) + 1) << 10)) : ci;
+            kbox[slot] = cbox[i];
+            kmeta[slot] = use_lists ? (ci | ((atomicExch(&khead[ci], slot) + 1) << 10)) : ci;
           }
         }
         if (tid == 0) s_nkept = nk + cnt;
@@ -581,6 +733,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     }
   }
   __syncthreads();
+  if (rank != 0) return;      // no distributed-shared-memory access after the last cluster barrier
 
   // ---------------- outputs ----------------
   const int nk = s_nkept;
@@ -602,8 +755,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     if (tid == 0) g.det_count[b] = nk;  // true number kept; rows beyond max_det are dropped
   }
   if (g.debug && tid == 0 && n > 0)
-    printf("nms b=%d n=%d kept=%d sort=%lld gather=%lld A=%lld B=%lld C=%lld rest=%lld out=%lld\n", b, n, nk, tk[1] - tk[0],
-           tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], clock64() - tk[6]);
+    printf("nms b=%d R=%d n=%d kept=%d sort=%lld gather=%lld A=%lld B=%lld C=%lld rest=%lld out=%lld\n", b, R, n, nk,
+           tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], clock64() - tk[6]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -665,6 +818,37 @@ static size_t nms_smem_bytes(long long per_image) {
   return sort_bytes > nms_bytes ? sort_bytes : nms_bytes;
 }
 
+// Cluster size for the batch: the largest of 8 / 4 / 2 whose batch clusters are co-resident (one CTA per SM at this
+// shared-memory size; asked from the occupancy API once per device), 1 otherwise. Small candidate capacities and key
+// lists beyond shared memory stay on the single-CTA kernel. YX_NMS_CLUSTER=<1|2|4|8> caps it (tests compare the paths).
+static int nms_cluster_size(int batch, long long per_image, size_t smem) {
+  if (per_image <= 2 * kChunk || per_image > kMaxSmemKeys) return 1;
+  int cap = kNmsMaxCluster;
+  if (const char* e = getenv("YX_NMS_CLUSTER")) { cap = atoi(e); if (cap < 1) cap = 1; }
+  static int max_clusters_dev[kMaxDevices][4] = {};          // [device][log2 R]: co-resident clusters, 0 = not asked yet
+  static size_t asked_smem_dev[kMaxDevices] = {};
+  const int slot = current_device_slot();
+  if (asked_smem_dev[slot] != smem) { memset(max_clusters_dev[slot], 0, sizeof(max_clusters_dev[slot])); asked_smem_dev[slot] = smem; }
+  for (int lg = 3; lg >= 1; --lg) {
+    const int R = 1 << lg;
+    if (R > cap) continue;
+    int& mc = max_clusters_dev[slot][lg];
+    if (mc == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)R * 16u, 1, 1); cfg.blockDim = dim3(kNmsThreads, 1, 1); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)R; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int got = 0;
+      if (cudaOccupancyMaxActiveClusters(&got, sort_nms_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); got = 0; }
+      mc = got > 0 ? got : -1;
+    }
+    if (mc >= batch) return R;
+  }
+  return 1;
+}
+
 static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.smem_keys_cap = smem_keys_cap(g.src.per_image);
   g.kept_cap = kept_cap_for(g.src.per_image);
@@ -675,10 +859,23 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   static size_t configured_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
-    YX_CUDA(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YX_CUDA(cudaFuncSetAttribute(sort_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YX_CUDA(cudaFuncSetAttribute(sort_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  sort_nms_kernel<<<batch, kNmsThreads, smem, s>>>(g);
+  const int R = nms_cluster_size(batch, g.src.per_image, smem);
+  if (R > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * R), 1, 1); cfg.blockDim = dim3(kNmsThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)R; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    YX_CUDA(cudaLaunchKernelEx(&cfg, sort_nms_kernel<true>, (const NmsArgs)g));
+  } else {
+    sort_nms_kernel<false><<<batch, kNmsThreads, smem, s>>>(g);
+  }
   YX_CUDA(cudaGetLastError());
   return YX_OK;
 }

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 import pixeltable_yolox_b200 as yx  # noqa: E402
 from oracle import postprocess_oracle as po  # noqa: E402
-from pixeltable_yolox_b200 import ops  # noqa: E402
+from pixeltable_yolox_b200 import _lib, ops  # noqa: E402
 from pixeltable_yolox_b200 import synthetic as syn  # noqa: E402
 
 
@@ -211,3 +211,58 @@ def test_every_anchor_kept_stays_in_shared_memory(cuda):
     want, _ = po.postprocess(pred.copy(), 80, 0.01, 0.65, variant="offset", return_indices=True)
     assert all(len(w) == A for w in want)
     _check_lists(yx.postprocess(torch.from_numpy(pred).to(cuda), 80, 0.01, 0.65, nms_variant="offset"), want)
+
+
+def _cluster_scenes():
+    rng = np.random.default_rng(21)
+    scenes = {}
+    scenes["dense_8400"] = (syn.dense_scene(2, anchors=8400, seed=13), 0.001, 0.65)
+    scenes["dense_8400_thr3"] = (syn.dense_scene(3, anchors=8400, seed=15), 0.3, 0.45)
+    neg = syn.dense_scene(2, anchors=3000, seed=46, clusters=30, size=320.0)
+    neg[:, :, 0:2] -= 250.0                                                       # class window J > 0
+    scenes["negative_coords"] = (neg, 0.2, 0.5)
+    A = 12000                                                                     # one class, thousands kept: list overflow
+    one = np.zeros((1, A, 85), dtype=np.float32)
+    one[0, :, 0:2] = rng.uniform(0, 4000, size=(A, 2)); one[0, :, 2:4] = rng.uniform(10, 30, size=(A, 2))
+    one[0, :, 4] = rng.uniform(0.5, 1.0, size=A); one[0, :, 5 + 7] = rng.uniform(0.5, 1.0, size=A)
+    scenes["one_class_12000"] = (one, 0.1, 0.3)
+    A = 2500                                                                      # tied scores, duplicates, zero areas
+    tie = np.zeros((2, A, 85), dtype=np.float32)
+    tie[:, :, 0:2] = rng.uniform(-20, 600, (2, A, 2)); tie[:, :, 2:4] = rng.uniform(10, 90, (2, A, 2))
+    tie[:, :, 4] = np.round(rng.uniform(0.3, 1.0, (2, A)), 1)
+    np.put_along_axis(tie[:, :, 5:], rng.integers(0, 6, (2, A))[..., None], 0.9, axis=2)
+    tie[0, :40, 2:4] = 0.0; tie[0, 100:140] = tie[0, 99]
+    tie[1, 600:, 4] = 0.0                                                         # ragged: image 1 has 600 candidates
+    scenes["ties_2500"] = (tie, 0.2, 0.5)
+    few = syn.dense_scene(2, anchors=8400, seed=17)
+    few[0, 40:, 4] = 0.0; few[1, 33:, 4] = 0.0                                    # 33 .. 40 candidates: short runs, empty runs
+    scenes["few_of_8400"] = (few, 0.0005, 0.65)
+    return scenes
+
+
+@pytest.mark.parametrize("scene", ["dense_8400", "dense_8400_thr3", "negative_coords", "one_class_12000", "ties_2500", "few_of_8400"])
+def test_cluster_nms_equals_single_cta_and_oracle(cuda, scene, monkeypatch):
+    """sort_nms_kernel<true> (one thread-block cluster of 2 / 4 / 8 CTAs per image: split sort with a rank merge through
+    distributed shared memory, kept list / mask rows dealt over the CTAs) keeps exactly the rows of the single-CTA
+    kernel and of the oracle, for every variant."""
+    pred, conf, nms = _cluster_scenes()[scene]
+    for variant in ("offset", "per_class", "agnostic"):
+        agn = variant == "agnostic"
+        want, _ = po.postprocess(pred.copy(), 80, conf, nms, variant="offset" if agn else variant, class_agnostic=agn,
+                                 return_indices=True)
+        rows = {}
+        for R in (1, 2, 4, 8):
+            monkeypatch.setenv("YX_NMS_CLUSTER", str(R))
+            dets, idx, cnt = ops.postprocess_device(torch.from_numpy(pred).to(cuda), 80, conf, nms,
+                                                    _lib.NMS_AGNOSTIC if agn else yx.boxes.NMS_VARIANTS[variant])
+            cnt = cnt.cpu().tolist()
+            rows[R] = [(dets[b, :cnt[b]].cpu().numpy(), idx[b, :cnt[b]].cpu().numpy()) for b in range(len(cnt))]
+        monkeypatch.delenv("YX_NMS_CLUSTER")
+        for b, w in enumerate(want):
+            for R in (1, 2, 4, 8):
+                d, _ = rows[R][b]
+                if w is None:
+                    assert d.shape[0] == 0, f"{variant} R={R} image {b}"
+                else:
+                    np.testing.assert_array_equal(d, w, err_msg=f"{variant} R={R} image {b}")
+                np.testing.assert_array_equal(rows[R][b][1], rows[1][b][1], err_msg=f"{variant} R={R} image {b} (indices)")
