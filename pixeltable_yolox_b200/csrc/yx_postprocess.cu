@@ -32,7 +32,8 @@ static constexpr int kChunk = 512;
 static constexpr int kChunkWords = kChunk / 32;
 static constexpr int kNmsThreads = 512;
 static constexpr int kMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
-static constexpr int kChunkBytes = kChunk * 24 + kChunk * kChunkWords * 4;
+static constexpr int kMaskPitch = kChunkWords + 1;   // words per mask row: odd pitch, column reads are bank-conflict free
+static constexpr int kChunkBytes = kChunk * 24 + kChunk * kMaskPitch * 4;
 static constexpr int kClassCap = 1024;      // class ids below this get a linked list of kept boxes
 static constexpr int kTriItems = 32 * (kChunkWords * (kChunkWords + 1) / 2);  // (row, word) items of the upper triangle
 static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassCap * 4;
@@ -370,6 +371,13 @@ __device__ __forceinline__ void sort_keys_asc(unsigned long long* keys, const in
   }
 }
 
+__device__ __forceinline__ void nms_load_row(const NmsArgs& g, long long base, int idx, float4& bx, int& c) {
+  const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
+  bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
+  if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+  else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
+}
+
 __device__ __forceinline__ unsigned long long nms_key(const NmsArgs& g, long long base, int i) {
   if (g.keys) return g.keys[base + i];
   float sc = g.src.scores[(base + i) * g.src.score_stride];
@@ -396,6 +404,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   __shared__ int red_cmax[kNmsThreads / 32], red_cmin[kNmsThreads / 32];
   __shared__ int s_nkept, s_ck;
   __shared__ unsigned s_removed[kChunkWords];
+  __shared__ unsigned short s_alive[kChunk];    // rows of the chunk that survived phase A, ascending
+  __shared__ int s_nalive;
   __shared__ unsigned s_deadx[CL ? kNmsMaxCluster * kChunkWords : 1];   // [R][16] dead bits found by every CTA
   __shared__ float s_xf[CL ? kNmsMaxCluster * 2 : 1];                   // [R] (max, min) coordinate of every run
   __shared__ int s_xi[CL ? kNmsMaxCluster * 2 : 1];                     // [R] (max, min) class of every run
@@ -416,6 +426,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
 
   if (tid == 0) s_nkept = 0;
   long long tk[8];
+  long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0, t_prev = 0;   // YX_NMS_DEBUG: clocks per phase over all chunks
   tk[0] = clock64();
   // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA, torchvision >= 0.19; the installed
   // 0.26 the goldens were generated with) / 4000 (CPU) / 20000 (CUDA, torchvision 0.17.2 = the reference's poetry.lock pin)
@@ -430,67 +441,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     return;
   }
   if (n > 0) {
+    // ---------------- keys + extrema of the (unsorted) candidates: max coordinate for the offset trick, class window ----
+    // run of this CTA: all n candidates, or with a cluster the contiguous 1/R share [lo_r, lo_r + m)
+    const int seg = (n + R - 1) / R;
+    const int lo_r = min(n, rank * seg), m = min(n, lo_r + seg) - lo_r;
+    int P = 1;
+    while (P < m) P <<= 1;
+    unsigned long long* keys = (CL || P <= g.smem_keys_cap) ? reinterpret_cast<unsigned long long*>(nsm)
+                                                           : (g.gkeys + (long long)b * g.gkeys_stride);
     float mx = -INFINITY, mn = INFINITY;
     int cmax = 0, cmin = 0;
-    if constexpr (!CL) {
-      // ---------------- sort ----------------
-      int P = 1;
-      while (P < n) P <<= 1;
-      unsigned long long* keys = (P <= g.smem_keys_cap) ? reinterpret_cast<unsigned long long*>(nsm)
-                                                        : (g.gkeys + (long long)b * g.gkeys_stride);
-      for (int i = tid; i < n; i += kNmsThreads) keys[i] = nms_key(g, base, i);
-      __syncthreads();
-      sort_keys_asc(keys, n, tid);
-
-      tk[1] = clock64();
-      // ---------------- gather sorted candidates; max coordinate for the offset trick ----------------
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
-        const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
-        const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
-        int c;
-        if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-        else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-        sbox[i] = bx; scls[i] = c; sidx[i] = idx;
-        mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
-        mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
-        cmax = max(cmax, c); cmin = min(cmin, c);
-      }
-    } else {
-      // ---------------- sort: one run per CTA, then merge by rank ----------------
-      const int seg = (n + R - 1) / R;                      // run r = candidates [r * seg, min(n, (r + 1) * seg))
-      const int lo_r = min(n, rank * seg), m = min(n, lo_r + seg) - lo_r;
-      unsigned long long* keys = reinterpret_cast<unsigned long long*>(nsm);
-      for (int i = tid; i < m; i += kNmsThreads) keys[i] = nms_key(g, base, lo_r + i);
-      __syncthreads();
-      sort_keys_asc(keys, m, tid);
-      nms_cluster_sync();                                    // every run is final
-      tk[1] = clock64();
-      for (int i = tid; i < m; i += kNmsThreads) {
-        const unsigned long long k = keys[i];
-        int pos = i;
-        for (int rr = 0; rr < R; ++rr) {
-          if (rr == rank) continue;
-          const int lo2 = min(n, rr * seg), m2 = min(n, lo2 + seg) - lo2;
-          const unsigned long long* run = nms_peer(keys, rr);
-          int l = 0, h = m2;                                 // lower bound: keys of run rr below k
-          while (l < h) {
-            const int mid = (l + h) >> 1;
-            if (run[mid] < k) l = mid + 1; else h = mid;
-          }
-          pos += l;
-        }
-        const int idx = (int)(unsigned)(k & 0xffffffffull);
-        const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
-        const float4 bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
-        int c;
-        if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-        else c = reinterpret_cast<const int*>(g.src.cls)[(base + idx) * g.src.cls_stride];
-        sbox[pos] = bx; scls[pos] = c; sidx[pos] = idx;
-        mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
-        mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
-        cmax = max(cmax, c); cmin = min(cmin, c);
-      }
+    for (int i = tid; i < m; i += kNmsThreads) {
+      const unsigned long long k = nms_key(g, base, lo_r + i);
+      keys[i] = k;
+      float4 bx; int c;
+      nms_load_row(g, base, (int)(unsigned)(k & 0xffffffffull), bx, c);
+      mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+      mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
+      cmax = max(cmax, c); cmin = min(cmin, c);
     }
     {
 #pragma unroll
@@ -501,7 +469,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
       }
       if (lane == 0) { red[warp] = mx; red_mn[warp] = mn; red_cmax[warp] = cmax; red_cmin[warp] = cmin; }
-      __syncthreads();
+      __syncthreads();                                       // also: the keys are in place
       mx = red[0]; mn = red_mn[0]; cmax = red_cmax[0]; cmin = red_cmin[0];
       for (int i = 1; i < kNmsThreads / 32; ++i) {
         mx = fmaxf(mx, red[i]); mn = fminf(mn, red_mn[i]);
@@ -509,31 +477,76 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
     }
     if constexpr (CL) {
-      // all-reduce of the four extrema over the cluster (max / min are exact in any order)
+      // all-reduce of the four extrema over the cluster (max / min are exact in any order); lands with the barrier below
       if (tid < R) {
         float* xf = nms_peer(s_xf, tid);
         int* xi = nms_peer(s_xi, tid);
         xf[rank * 2] = mx; xf[rank * 2 + 1] = mn;
         xi[rank * 2] = cmax; xi[rank * 2 + 1] = cmin;
       }
-      nms_cluster_sync();                                    // extrema exchanged; sorted rows visible; runs no longer read
+    }
+    // ---------------- sort ----------------
+    sort_keys_asc(keys, m, tid);
+    if constexpr (CL) {
+      nms_cluster_sync();                                    // every run is final, extrema exchanged
       for (int rr = 0; rr < R; ++rr) {
         mx = fmaxf(mx, s_xf[rr * 2]); mn = fminf(mn, s_xf[rr * 2 + 1]);
         cmax = max(cmax, s_xi[rr * 2]); cmin = min(cmin, s_xi[rr * 2 + 1]);
       }
     }
-    if (variant == 0) {
-      // boxes_for_nms = boxes + idxs.to(boxes) * (max_coordinate + 1)   (torchvision boxes.py)
-      const float step = __fadd_rn(mx, 1.0f);
-      for (int i = rank * kNmsThreads + tid; i < n; i += R * kNmsThreads) {
-        const float off = __fmul_rn((float)scls[i], step);
-        float4 bx = sbox[i];
-        bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
-        bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
-        sbox[i] = bx;
+    tk[1] = clock64();
+    // ---------------- gather the sorted candidates (four rows in flight per thread) ----------------
+    // boxes_for_nms = boxes + idxs.to(boxes) * (max_coordinate + 1)   (torchvision boxes.py) for the offset variant.
+    // With a cluster the position of a key is its index in the own run plus its lower bounds in the other runs
+    // (binary searches through distributed shared memory, four keys in lock-step; the keys are unique).
+    const float step = __fadd_rn(mx, 1.0f);
+    for (int i0 = tid; i0 < m; i0 += 4 * kNmsThreads) {
+      unsigned long long k[4];
+      int pos[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kNmsThreads;
+        pos[u] = i;
+        k[u] = i < m ? keys[i] : 0ull;
       }
+      if constexpr (CL) {
+        for (int rr = 0; rr < R; ++rr) {
+          if (rr == rank) continue;
+          const int lo2 = min(n, rr * seg), m2 = min(n, lo2 + seg) - lo2;
+          const unsigned long long* run = nms_peer(keys, rr);
+          int l[4] = {0, 0, 0, 0}, h[4] = {m2, m2, m2, m2};
+          for (int st = 32 - __clz(m2); st > 0; --st) {     // an interval of m2 closes in <= floor(log2 m2) + 1 halvings
+            unsigned long long v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = l[u] < h[u] ? run[(l[u] + h[u]) >> 1] : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (l[u] < h[u]) {
+                const int mid = (l[u] + h[u]) >> 1;
+                if (v[u] < k[u]) l[u] = mid + 1; else h[u] = mid;
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pos[u] += l[u];        // keys of run rr below k
+        }
+      }
+      float4 bx[4];
+      int c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kNmsThreads < m) nms_load_row(g, base, (int)(unsigned)(k[u] & 0xffffffffull), bx[u], c[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kNmsThreads < m) {
+          if (variant == 0) {
+            const float off = __fmul_rn((float)c[u], step);
+            bx[u].x = __fadd_rn(bx[u].x, off); bx[u].y = __fadd_rn(bx[u].y, off);
+            bx[u].z = __fadd_rn(bx[u].z, off); bx[u].w = __fadd_rn(bx[u].w, off);
+          }
+          sbox[pos[u]] = bx[u]; scls[pos[u]] = c[u]; sidx[pos[u]] = (int)(unsigned)(k[u] & 0xffffffffull);
+        }
     }
-    if constexpr (CL) nms_cluster_sync(); else __syncthreads();
+    if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // sorted rows visible; runs no longer read
 
     tk[2] = clock64();
     // ---------------- greedy NMS, chunk by chunk ----------------
@@ -551,7 +564,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     float4* cbox = reinterpret_cast<float4*>(nsm);                          // [kChunk]
     float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
     int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
-    unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kChunkWords]
+    unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kMaskPitch]
     int* cnext = reinterpret_cast<int*>(nsm + kChunkBytes);                  // [kChunk]
     int* ck = cnext + kChunk;                                                // [kChunk] kept members of the chunk
     int* chead = ck + kChunk;                                                // [kClassCap]
@@ -574,6 +587,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     const bool use_lists = (J <= 4) && cmin >= 0 && cmax < kClassCap;
     for (int i = tid; i < kClassCap; i += kNmsThreads) { khead[i] = -1; chead[i] = -1; }
 
+    // row of the next chunk, loaded one chunk ahead (the global-memory latency hides behind phases B and C)
+    float4 nx_box = make_float4(0, 0, 0, 0);
+    int nx_cls = -1;
+    if (tid < n) { nx_box = sbox[tid]; nx_cls = scls[tid]; }
+    t_prev = clock64();
     for (int c0 = 0; c0 < n; c0 += kChunk) {
       const int cn = min(kChunk, n - c0);
       __syncthreads();
@@ -585,10 +603,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       int my_cls = -1;
       bool dead = (tid >= cn);
       if (!dead) {
-        me = sbox[c0 + tid]; my_cls = scls[c0 + tid]; my_area = box_area(me);
+        me = nx_box; my_cls = nx_cls; my_area = box_area(me);
       }
       cbox[tid] = me; carea[tid] = my_area; ccls[tid] = my_cls;
-      if (tid == 0) s_ck = 0;
+      if (c0 + kChunk + tid < n) { nx_box = sbox[c0 + kChunk + tid]; nx_cls = scls[c0 + kChunk + tid]; }
       // ---- phase A: against the boxes kept in earlier chunks
       if (!dead) {
         const int nks = min(nk_own, KC);
@@ -626,41 +644,58 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           if (lane == 0) s_removed[warp] = bal;
         }
       }
-      if (c0 == 0) tk[3] = clock64();
-      // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i)
+      { const long long t = clock64(); acc_a += t - t_prev; t_prev = t; }
+      // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i), for the rows AND columns that survived
+      //      phase A only: phase C never looks at a bit of a removed candidate, neither as a row nor as a column
       {
         __syncthreads();
-        // balanced enumeration of the (row, word) items of the upper triangle: rows of group rb = row/32
-        // have (16 - rb) words each
-        // (the class gate costs ~5 instructions per pair, the IoU only runs inside the class window; walking
-        // per-class lists instead degenerates to divergent pointer chasing when a few classes dominate)
         const int nw = (cn + 31) >> 5;
-        const int items = 32 * (nw * (nw + 1) / 2);
+        if (warp < nw) {                                   // warp w compacts the alive rows of word w
+          int before = 0;
+          for (int l = 0; l < warp; ++l) before += __popc(~s_removed[l]);
+          const unsigned al = ~s_removed[warp];
+          if ((al >> lane) & 1u) s_alive[before + __popc(al & ((1u << lane) - 1u))] = (unsigned short)(warp * 32 + lane);
+          if (warp == nw - 1 && lane == 0) s_nalive = before + __popc(al);
+        }
+        __syncthreads();
+        // items (alive row, word): 16 per row, the words before the row's own are skipped; with a cluster the items are
+        // dealt round-robin over the CTAs and stored into CTA 0's mask
+        const int items = s_nalive << 4;
         for (int q = rank * kNmsThreads + tid; q < items; q += R * kNmsThreads) {
-          int rb = 0, rem = q;
-          while (rem >= 32 * (nw - rb)) { rem -= 32 * (nw - rb); ++rb; }
-          const int per = nw - rb;
-          const int row = rb * 32 + rem / per;
-          const int w = rb + rem % per;
-          unsigned bits = 0u;
-          const bool row_dead = (s_removed[row >> 5] >> (row & 31)) & 1u;
-          if (!row_dead) {
-            const float4 rbx = cbox[row];
-            const float rar = carea[row];
-            const int rcl = ccls[row];
-#pragma unroll 4
+          const int row = s_alive[q >> 4];
+          const int w = q & (kChunkWords - 1);
+          if (w < (row >> 5) || w >= nw) continue;
+          const float4 rbx = cbox[row];
+          const float rar = carea[row];
+          const int rcl = ccls[row];
+          // alive columns of the word that come after the row
+          const int lo_bit = row + 1 - w * 32;
+          unsigned m = ~s_removed[w] & (lo_bit <= 0 ? 0xffffffffu : (lo_bit >= 32 ? 0u : (0xffffffffu << lo_bit)));
+          if (J != 0x3fffffff && __popc(m) > 8) {
+            // class gate first, as a bit mask (the lanes of a warp hold up to 16 different words: column jb + w of
+            // the word is read in step jb, so that the lanes hit different banks), ...
+            unsigned gate = 0u;
+#pragma unroll 8
             for (int jb = 0; jb < 32; ++jb) {
-              const int j = w * 32 + jb;
-              if (j > row && j < cn && abs(ccls[j] - rcl) <= J &&
-                  suppresses(rbx, rar, cbox[j], carea[j], g.thr))
-                bits |= (1u << jb);
+              const int jc = (jb + w) & 31;
+              if (abs(ccls[w * 32 + jc] - rcl) <= J) gate |= (1u << jc);
             }
+            m &= gate;
           }
-          cmask_w[row * kChunkWords + w] = bits;
+          // ... then the IoU of the few pairs inside the class window only (a warp runs as many steps as its
+          // fullest lane has pairs, instead of the IoU path in nearly every one of 32 steps)
+          unsigned bits = 0u;
+          while (m) {
+            const int jb = __ffs(m) - 1;
+            m &= m - 1u;
+            const int j = w * 32 + jb;
+            if (abs(ccls[j] - rcl) <= J && suppresses(rbx, rar, cbox[j], carea[j], g.thr)) bits |= (1u << jb);
+          }
+          cmask_w[row * kMaskPitch + w] = bits;
         }
         if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // (2) CTA 0 holds the whole mask
       }
-      if (c0 == 0) tk[4] = clock64();
+      { const long long t = clock64(); acc_b += t - t_prev; t_prev = t; }
       // ---- phase C: one warp walks the chunk word by word (32 candidates); lane l owns word l of the removed
       //      set. Inside a word the greedy order is resolved on the 32x32 diagonal block held in registers;
       //      the rows of the kept boxes are then OR-ed into the later words.
@@ -671,7 +706,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         for (int w = 0; w < nwords; ++w) {
           unsigned a = ~__shfl_sync(0xffffffffu, removed, w);          // alive candidates of word w
           if (a == 0u) continue;
-          const unsigned dj = cmask[(w * 32 + lane) * kChunkWords + w];  // row (w*32 + lane), bits of the same word
+          if (__popc(a) <= 6) {
+            // few alive candidates (dense scenes after phase A): hop from kept box to kept box; every lane reads the
+            // diagonal word of the kept row (broadcast) and its own later word
+            while (a) {
+              const int i = __ffs(a) - 1;
+              const unsigned* rowp = cmask + (w * 32 + i) * kMaskPitch;
+              const unsigned diag = rowp[w];
+              const unsigned r = (lane > w && lane < nwords) ? rowp[lane] : 0u;
+              if (lane == 0) ck[cnt] = w * 32 + i;
+              ++cnt;
+              a &= ~(diag | (1u << i));
+              removed |= r;
+            }
+            continue;
+          }
+          const unsigned dj = cmask[(w * 32 + lane) * kMaskPitch + w];  // row (w*32 + lane), bits of the same word
           unsigned keptw = a;
           // common case: no alive box of the word suppresses another alive box of the word
           if (__any_sync(0xffffffffu, ((a >> lane) & 1u) && (dj & a) != 0u)) {
@@ -687,8 +737,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           if (mine) {
             const int slot = cnt + __popc(keptw & ((1u << lane) - 1u));
             ck[slot] = w * 32 + lane;
-            if constexpr (CL)
-              for (int rr = 1; rr < R; ++rr) nms_peer(ck, rr)[slot] = w * 32 + lane;
           }
           cnt += __popc(keptw);
           // rows of the kept boxes OR-ed into the later words. Few kept boxes (dense scenes: most of the word is
@@ -697,27 +745,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           if (__popc(keptw) < nwords - 1 - w) {
             if (lane > w && lane < nwords) {
               unsigned r = 0u;
-              for (unsigned mk = keptw; mk; mk &= mk - 1u) r |= cmask[(w * 32 + __ffs(mk) - 1) * kChunkWords + lane];
+              for (unsigned mk = keptw; mk; mk &= mk - 1u) r |= cmask[(w * 32 + __ffs(mk) - 1) * kMaskPitch + lane];
               removed |= r;
             }
           } else {
             for (int l = w + 1; l < nwords; ++l) {
-              const unsigned r = __reduce_or_sync(0xffffffffu, mine ? cmask[(w * 32 + lane) * kChunkWords + l] : 0u);
+              const unsigned r = __reduce_or_sync(0xffffffffu, mine ? cmask[(w * 32 + lane) * kMaskPitch + l] : 0u);
               if (lane == l) removed |= r;
             }
           }
         }
         if (lane == 0) s_ck = cnt;
-        if constexpr (CL)
-          if (lane > 0 && lane < R) *nms_peer(&s_ck, lane) = cnt;
       }
-      if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) every CTA knows the chunk's survivors
-      if (c0 == 0) tk[5] = clock64();
+      if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) CTA 0 has the chunk's survivors
+      { const long long t = clock64(); acc_c += t - t_prev; t_prev = t; }
       // ---- append the chunk's survivors to the kept list (parallel; list order is irrelevant)
       {
-        const int cnt = s_ck;
+        // (the other CTAs read CTA 0's list: it is rewritten only after barrier (2) of the next chunk)
+        const int cnt = (CL && rank != 0) ? *nms_peer(&s_ck, 0) : s_ck;
         if (tid < cnt) {
-          const int i = ck[tid];
+          const int i = (CL && rank != 0) ? nms_peer(ck, 0)[tid] : ck[tid];
           const int e = nk + tid;
           if (rank == 0) kept[e] = c0 + i;
           const int slot = e / R;
@@ -730,10 +777,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         if (tid == 0) s_nkept = nk + cnt;
       }
       __syncthreads();
+      { const long long t = clock64(); acc_d += t - t_prev; t_prev = t; }
     }
+    if constexpr (CL) nms_cluster_sync();   // the other CTAs have read the last chunk's survivors from CTA 0
   }
   __syncthreads();
-  if (rank != 0) return;      // no distributed-shared-memory access after the last cluster barrier
+  if (rank != 0) return;
 
   // ---------------- outputs ----------------
   const int nk = s_nkept;
@@ -755,8 +804,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     if (tid == 0) g.det_count[b] = nk;  // true number kept; rows beyond max_det are dropped
   }
   if (g.debug && tid == 0 && n > 0)
-    printf("nms b=%d R=%d n=%d kept=%d sort=%lld gather=%lld A=%lld B=%lld C=%lld rest=%lld out=%lld\n", b, R, n, nk,
-           tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], clock64() - tk[6]);
+    printf("nms b=%d R=%d n=%d kept=%d keys+sort=%lld gather=%lld A=%lld B=%lld C=%lld append=%lld out=%lld\n", b, R, n, nk,
+           tk[1] - tk[0], tk[2] - tk[1], acc_a, acc_b, acc_c, acc_d, clock64() - tk[6]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -47,7 +47,8 @@ def all_kept(batch, classes):
 
 
 rows = []
-for batch in (64, 16, 4, 1):
+PHASES_ONLY = "--phases-only" in sys.argv
+for batch in (() if PHASES_ONLY else (64, 16, 4, 1)):
     dense = torch.from_numpy(syn.dense_scene(batch, anchors=A, seed=13)).to(dev)
     kept3 = torch.from_numpy(all_kept(batch, 3)).to(dev)
     for name, pred, thr in (("dense", dense, 0.001), ("dense", dense, 0.25), ("dense", dense, 0.5), ("all_kept_3_classes", kept3, 0.01)):
@@ -65,7 +66,7 @@ for batch in (64, 16, 4, 1):
         rows.append(row)
 for batch in (64, 1):
     dense = torch.from_numpy(syn.dense_scene(batch, anchors=A, seed=13)).to(dev)
-    for cap in ("1", None):
+    for cap in ("1", "2", None):
         if cap:
             os.environ["YX_NMS_CLUSTER"] = cap
         ops.postprocess_device(dense.clone(), 80, 0.001, 0.65, NMS_VARIANTS["auto"])
@@ -76,6 +77,6 @@ for batch in (64, 1):
         torch.cuda.synchronize()
         del os.environ["YX_NMS_DEBUG"]
         os.environ.pop("YX_NMS_CLUSTER", None)
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and not PHASES_ONLY:
     Path(sys.argv[1]).write_text(json.dumps(rows, indent=1))
 assert all(r["rows_equal"] for r in rows), "cluster kernel keeps different rows"
