@@ -197,6 +197,7 @@ struct NmsSource {
   const float* scores; int score_stride;
   const void* cls; int cls_stride; int cls_is_float;
   long long per_image;                      // candidates per image in the dense arrays
+  int cand_rows;                            // 1: boxes / scores / cls are the 8-float candidate rows of the score filter
 };
 
 struct NmsArgs {
@@ -210,6 +211,7 @@ struct NmsArgs {
   unsigned long long* gkeys;       // used when the key list does not fit shared memory
   long long gkeys_stride;          // keys per image in gkeys (next_pow2(per_image))
   int smem_keys_cap;               // number of 64-bit keys the dynamic shared memory can hold
+  int smem_bytes;                  // dynamic shared memory of the launch
   int kept_cap;                    // kept boxes that fit the shared-memory kept list
   float4* sorted_box;              // boxes as NMS sees them (offset applied for variant 0)
   int* sorted_cls;
@@ -322,8 +324,8 @@ __device__ __forceinline__ void nms_small_warp(const NmsArgs& g, int b, int n, i
 // moves, so pairs with a partner >= n are simply not enumerated: n = 8 400 costs about half of the padded 16 384
 // network. Four independent pairs are loaded before the first compare so that the shared-memory latency of a step
 // overlaps. Ends with a CTA barrier.
-__device__ __forceinline__ void sort_keys_asc(unsigned long long* keys, const int n, const int tid) {
-  for (int lg = 1; (1 << (lg - 1)) < n; ++lg) {
+__device__ __forceinline__ void sort_keys_asc(unsigned long long* keys, const int n, const int tid, const int max_lg = 31) {
+  for (int lg = 1; (1 << (lg - 1)) < n && lg <= max_lg; ++lg) {      // max_lg: stop at sorted blocks of 2^max_lg keys
     const int size = 1 << lg, half = size >> 1;
     {
       const int fb = n >> lg, rem = n & (size - 1);
@@ -371,7 +373,67 @@ __device__ __forceinline__ void sort_keys_asc(unsigned long long* keys, const in
   }
 }
 
+// Merge sort of keys[0, n) (unique keys, all below ~0) with a second buffer of n keys: blocks of 16 by the bitonic network
+// above, then log2(n / 16) merge passes. In a pass every thread produces D = 17 (n <= 4 096) or 33 consecutive outputs of
+// one pair of runs: merge-path binary search for its starting point, then a sequential two-way merge out of shared
+// memory. D is odd so that the threads of a warp, D keys apart, stream through different banks (a power of two put all 32
+// lanes on one bank: 190k clk for n = 8 400 instead of the network's 230k). A pass reads and writes every key once; the
+// 10 passes for n = 8 400 replace 95 steps of the network.
+// Returns the buffer that holds the result (keys after an even number of passes, tmp after an odd one: see
+// merge_sorted_in_tmp). Ends with a CTA barrier.
+__device__ __forceinline__ int merge_passes(int n) { return n > 16 ? (32 - __clz(n - 1)) - 4 : 0; }
+__device__ __forceinline__ bool merge_sorted_in_tmp(int n) { return merge_passes(n) & 1; }
+__device__ __forceinline__ unsigned long long* merge_sort_keys(unsigned long long* keys, unsigned long long* tmp, const int n,
+                                                               const int tid) {
+  sort_keys_asc(keys, n, tid, 4);
+  unsigned long long* src = keys;
+  unsigned long long* dst = tmp;
+  const int D = n <= 4096 ? 17 : 33;
+  for (int lgL = 4; (1 << lgL) < n; ++lgL) {
+    const int L = 1 << lgL;
+    const int ipp = (2 * L + D - 1) / D;                      // items per pair of runs (the last one is shorter)
+    const int items = ((n + 2 * L - 1) >> (lgL + 1)) * ipp;
+    for (int it = tid; it < items; it += kNmsThreads) {
+      const int pr = it / ipp;
+      const int d = (it - pr * ipp) * D;                      // first output of the item inside its pair
+      const int a0 = pr << (lgL + 1);
+      const int lenA = min(L, n - a0), b0 = a0 + lenA, lenB = min(L, n - b0);
+      const int cnt = min(D, lenA + lenB - d);
+      if (cnt <= 0) continue;                                 // the pair at the end of the list is incomplete
+      const unsigned long long* A = src + a0;
+      const unsigned long long* B = src + b0;
+      int lo = max(0, d - lenB), hi = min(d, lenA);          // merge path: how many of the first d outputs come from A
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (A[mid] < B[d - 1 - mid]) lo = mid + 1; else hi = mid;
+      }
+      int i = lo, j = d - lo;
+      unsigned long long ka = i < lenA ? A[i] : ~0ull, kb = j < lenB ? B[j] : ~0ull;
+      unsigned long long* out = dst + a0 + d;
+      for (int t = 0; t < cnt; ++t) {                         // branch-free step: one shared-memory load, no divergence
+        const bool ta = ka < kb;
+        out[t] = ta ? ka : kb;
+        i += ta ? 1 : 0; j += ta ? 0 : 1;
+        const int nx = ta ? i : j;
+        const unsigned long long* P = ta ? A : B;
+        const unsigned long long v = nx < (ta ? lenA : lenB) ? P[nx] : ~0ull;
+        ka = ta ? v : ka; kb = ta ? kb : v;
+      }
+    }
+    __syncthreads();
+    unsigned long long* sw = src; src = dst; dst = sw;
+  }
+  return src;
+}
+
 __device__ __forceinline__ void nms_load_row(const NmsArgs& g, long long base, int idx, float4& bx, int& c) {
+  if (g.src.cand_rows) {
+    // candidate rows of the score filter: 8 floats (x1, y1, x2, y2, obj, class_conf, class, score), 32-byte aligned
+    const float4* row = reinterpret_cast<const float4*>(g.src.boxes + (base + idx) * 8);
+    bx = row[0];
+    c = (int)row[1].z;
+    return;
+  }
   const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
   bx = make_float4(bp[0], bp[1], bp[2], bp[3]);
   if (g.src.cls_is_float) c = (int)reinterpret_cast<const float*>(g.src.cls)[(base + idx) * g.src.cls_stride];
@@ -427,6 +489,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   if (tid == 0) s_nkept = 0;
   long long tk[8];
   long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0, t_prev = 0;   // YX_NMS_DEBUG: clocks per phase over all chunks
+#ifdef YX_NMS_TRACE
+  long long tr[6] = {0, 0, 0, 0, 0, 0};
+#define YX_TR(k) { tr[k] += clock64() - t_prev; }
+#else
+#define YX_TR(k)
+#endif
   tk[0] = clock64();
   // torchvision.ops.batched_nms: coordinate trick unless boxes.numel() > 100000 (CUDA, torchvision >= 0.19; the installed
   // 0.26 the goldens were generated with) / 4000 (CPU) / 20000 (CUDA, torchvision 0.17.2 = the reference's poetry.lock pin)
@@ -451,14 +519,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
                                                            : (g.gkeys + (long long)b * g.gkeys_stride);
     float mx = -INFINITY, mn = INFINITY;
     int cmax = 0, cmin = 0;
-    for (int i = tid; i < m; i += kNmsThreads) {
-      const unsigned long long k = nms_key(g, base, lo_r + i);
-      keys[i] = k;
-      float4 bx; int c;
-      nms_load_row(g, base, (int)(unsigned)(k & 0xffffffffull), bx, c);
-      mx = fmaxf(mx, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
-      mn = fminf(mn, fminf(fminf(bx.x, bx.y), fminf(bx.z, bx.w)));
-      cmax = max(cmax, c); cmin = min(cmin, c);
+    for (int i0 = tid; i0 < m; i0 += 4 * kNmsThreads) {      // four keys, then their four rows, in flight per thread
+      unsigned long long k[4];
+      float4 bx[4];
+      int c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kNmsThreads < m) k[u] = nms_key(g, base, lo_r + i0 + u * kNmsThreads);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kNmsThreads < m) {
+          keys[i0 + u * kNmsThreads] = k[u];
+          nms_load_row(g, base, (int)(unsigned)(k[u] & 0xffffffffull), bx[u], c[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * kNmsThreads < m) {
+          mx = fmaxf(mx, fmaxf(fmaxf(bx[u].x, bx[u].y), fmaxf(bx[u].z, bx[u].w)));
+          mn = fminf(mn, fminf(fminf(bx[u].x, bx[u].y), fminf(bx[u].z, bx[u].w)));
+          cmax = max(cmax, c[u]); cmin = min(cmin, c[u]);
+        }
     }
     {
 #pragma unroll
@@ -486,7 +566,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
     }
     // ---------------- sort ----------------
-    sort_keys_asc(keys, m, tid);
+    // merge sort when two key buffers fit the shared memory of the launch (uniform over the cluster: decided on seg)
+    const bool use_merge = (keys == reinterpret_cast<unsigned long long*>(nsm)) && (16LL * seg <= (long long)g.smem_bytes);
+    unsigned long long* const keys0 = keys;
+    if (use_merge) keys = merge_sort_keys(keys, keys + seg, m, tid);
+    else sort_keys_asc(keys, m, tid);
     if constexpr (CL) {
       nms_cluster_sync();                                    // every run is final, extrema exchanged
       for (int rr = 0; rr < R; ++rr) {
@@ -513,7 +597,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         for (int rr = 0; rr < R; ++rr) {
           if (rr == rank) continue;
           const int lo2 = min(n, rr * seg), m2 = min(n, lo2 + seg) - lo2;
-          const unsigned long long* run = nms_peer(keys, rr);
+          const unsigned long long* run = nms_peer(keys0, rr) + ((use_merge && merge_sorted_in_tmp(m2)) ? seg : 0);
           int l[4] = {0, 0, 0, 0}, h[4] = {m2, m2, m2, m2};
           for (int st = 32 - __clz(m2); st > 0; --st) {     // an interval of m2 closes in <= floor(log2 m2) + 1 halvings
             unsigned long long v[4];
@@ -607,15 +691,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
       cbox[tid] = me; carea[tid] = my_area; ccls[tid] = my_cls;
       if (c0 + kChunk + tid < n) { nx_box = sbox[c0 + kChunk + tid]; nx_cls = scls[c0 + kChunk + tid]; }
+      YX_TR(0)
       // ---- phase A: against the boxes kept in earlier chunks
       if (!dead) {
         const int nks = min(nk_own, KC);
         if (use_lists) {
-          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2)
-            for (int k = khead[c2]; k >= 0; k = (kmeta[k] >> 10) - 1) {
-              const float4 kb = kbox[k];
+          // (the next entry of a list is loaded while the IoU of the current one is computed)
+          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2) {
+            int k = khead[c2];
+            float4 kb = make_float4(0, 0, 0, 0);
+            int meta = 0;
+            if (k >= 0) { kb = kbox[k]; meta = kmeta[k]; }
+            while (k >= 0) {
+              const int kn = (meta >> 10) - 1;
+              float4 kbn = kb;
+              int metan = 0;
+              if (kn >= 0) { kbn = kbox[kn]; metan = kmeta[kn]; }
               if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+              k = kn; kb = kbn; meta = metan;
             }
+          }
         } else {
           for (int k = 0; k < nks; ++k) {
             if (abs(kmeta[k] - my_cls) > J) continue;
@@ -630,6 +725,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           if (suppresses(kb, box_area(kb), me, my_area, g.thr)) dead = true;
         }
       }
+      YX_TR(1)
       {
         const unsigned bal = __ballot_sync(0xffffffffu, dead);
         if constexpr (CL) {
@@ -661,6 +757,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         // items (alive row, word): 16 per row, the words before the row's own are skipped; with a cluster the items are
         // dealt round-robin over the CTAs and stored into CTA 0's mask
         const int items = s_nalive << 4;
+        YX_TR(2)
         for (int q = rank * kNmsThreads + tid; q < items; q += R * kNmsThreads) {
           const int row = s_alive[q >> 4];
           const int w = q & (kChunkWords - 1);
@@ -693,6 +790,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           }
           cmask_w[row * kMaskPitch + w] = bits;
         }
+        YX_TR(3)
         if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // (2) CTA 0 holds the whole mask
       }
       { const long long t = clock64(); acc_b += t - t_prev; t_prev = t; }
@@ -756,6 +854,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           }
         }
         if (lane == 0) s_ck = cnt;
+        YX_TR(4)
       }
       if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) CTA 0 has the chunk's survivors
       { const long long t = clock64(); acc_c += t - t_prev; t_prev = t; }
@@ -806,6 +905,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   if (g.debug && tid == 0 && n > 0)
     printf("nms b=%d R=%d n=%d kept=%d keys+sort=%lld gather=%lld A=%lld B=%lld C=%lld append=%lld out=%lld\n", b, R, n, nk,
            tk[1] - tk[0], tk[2] - tk[1], acc_a, acc_b, acc_c, acc_d, clock64() - tk[6]);
+#ifdef YX_NMS_TRACE
+  if (g.debug && tid == 0 && n > 0)
+    printf("trace b=%d (since phase start) A: loaded=%lld walked=%lld | B: compacted=%lld items=%lld | C: scanned=%lld\n", b,
+           tr[0], tr[1], tr[2], tr[3], tr[4]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -905,6 +1009,7 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.debug = getenv("YX_NMS_DEBUG") ? 1 : 0;
   g.no_small = getenv("YX_NMS_NO_SMALL") ? 1 : 0;
   const size_t smem = nms_smem_bytes(g.src.per_image);
+  g.smem_bytes = (int)smem;
   static size_t configured_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
@@ -963,7 +1068,7 @@ int postprocess_launch(float* pred, int batch, int anchors, int nc, float conf_t
   memset(&g, 0, sizeof(g));
   g.src.boxes = w.cand; g.src.box_stride = 8;
   g.src.scores = w.cand + 7; g.src.score_stride = 8;
-  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1;
+  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1; g.src.cand_rows = 1;
   g.src.per_image = anchors;
   g.keys = w.keys; g.counts = w.counts;
   g.thr = thr_for_strict_gt(nms_thre);
@@ -1003,7 +1108,7 @@ int nms_prefiltered_launch(int batch, int anchors, double nms_thre, int nms_vari
   memset(&g, 0, sizeof(g));
   g.src.boxes = w.cand; g.src.box_stride = 8;
   g.src.scores = w.cand + 7; g.src.score_stride = 8;
-  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1;
+  g.src.cls = w.cand + 6; g.src.cls_stride = 8; g.src.cls_is_float = 1; g.src.cand_rows = 1;
   g.src.per_image = anchors;
   g.keys = w.keys; g.counts = w.counts;
   g.thr = thr_for_strict_gt(nms_thre);
