@@ -435,8 +435,9 @@ def extra_config5(args, dev, pk, ref) -> dict:
         rows.append(row)
     return {"workload": "synthetic dense scenes [64, 8400, 85] fp32 (synthetic.dense_scene seed 13), nms 0.65, config[4] of BASELINE.json",
             "hbm_peak_GBps": pk["hbm"], "rows": rows,
-            "note": "sort_nms is latency-bound (one CTA per image; the n^2/64 suppression mask never leaves shared memory): "
-                    "its GB/s is quoted against the minimal bytes (candidates in, detections out)"}
+            "note": "sort_nms is latency-bound (one thread-block cluster of 2 CTAs per image at batch 64, 4 / 8 at smaller batches; "
+                    "merge sort, suppression mask and kept list stay in (distributed) shared memory): its GB/s is quoted against "
+                    "the minimal bytes (candidates in, detections out)"}
 
 
 def extra_hbm_families(prof, pk) -> dict:

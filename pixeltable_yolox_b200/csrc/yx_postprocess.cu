@@ -35,8 +35,7 @@ static constexpr int kMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
 static constexpr int kMaskPitch = kChunkWords + 1;   // words per mask row: odd pitch, column reads are bank-conflict free
 static constexpr int kChunkBytes = kChunk * 24 + kChunk * kMaskPitch * 4;
 static constexpr int kClassCap = 1024;      // class ids below this get a linked list of kept boxes
-static constexpr int kTriItems = 32 * (kChunkWords * (kChunkWords + 1) / 2);  // (row, word) items of the upper triangle
-static constexpr int kNmsFixedBytes = kChunkBytes + 2 * kChunk * 4 + 2 * kClassCap * 4;
+static constexpr int kNmsFixedBytes = kChunkBytes + kChunk * 4 + 3 * kClassCap * 4;   // + survivors, list heads, two bounds per class
 static constexpr int kKeptEntryBytes = 20;  // box 16 + (class | next << 10) 4; the area is recomputed (3 flops)
 static constexpr int kNmsSmemBudget = 225 * 1024;   // dynamic shared memory: 8 652 kept entries, i.e. every anchor of a 640^2 image
 
@@ -649,11 +648,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
     int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
     unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kMaskPitch]
-    int* cnext = reinterpret_cast<int*>(nsm + kChunkBytes);                  // [kChunk]
-    int* ck = cnext + kChunk;                                                // [kChunk] kept members of the chunk
-    int* chead = ck + kChunk;                                                // [kClassCap]
-    int* khead = chead + kClassCap;                                          // [kClassCap]
-    uint8_t* kbase = reinterpret_cast<uint8_t*>(khead + kClassCap);
+    int* ck = reinterpret_cast<int*>(nsm + kChunkBytes);                     // [kChunk] kept members of the chunk
+    int* khead = ck + kChunk;                                                // [kClassCap] list heads
+    // bounds of a class's kept boxes (orderable_f32): max over the list of min(x2, y2), min over the list of max(x1, y1).
+    // A box whose min(x1, y1) is not below the first, or whose max(x2, y2) is not above the second, overlaps no entry in
+    // x or in y -- its IoU with every entry is 0 in torchvision's own arithmetic -- and skips the list. With the offset
+    // trick's class window J = 1 (any scene with a coordinate below zero) that removes the two neighbour lists.
+    unsigned* kmaxlo = reinterpret_cast<unsigned*>(khead + kClassCap);       // [kClassCap]
+    unsigned* kminhi = kmaxlo + kClassCap;                                   // [kClassCap]
+    uint8_t* kbase = reinterpret_cast<uint8_t*>(kminhi + kClassCap);
     const int KC = g.kept_cap;
     float4* kbox = reinterpret_cast<float4*>(kbase);                          // [KC]
     int* kmeta = reinterpret_cast<int*>(kbase + (size_t)KC * 16);             // [KC] class, or class | (next + 1) << 10 with lists
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       }
     }
     const bool use_lists = (J <= 4) && cmin >= 0 && cmax < kClassCap;
-    for (int i = tid; i < kClassCap; i += kNmsThreads) { khead[i] = -1; chead[i] = -1; }
+    for (int i = tid; i < kClassCap; i += kNmsThreads) { khead[i] = -1; kmaxlo[i] = 0u; kminhi[i] = 0xffffffffu; }
 
     // row of the next chunk, loaded one chunk ahead (the global-memory latency hides behind phases B and C)
     float4 nx_box = make_float4(0, 0, 0, 0);
@@ -697,7 +700,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         const int nks = min(nk_own, KC);
         if (use_lists) {
           // (the next entry of a list is loaded while the IoU of the current one is computed)
+          const unsigned my_lo = orderable(fminf(me.x, me.y)), my_hi = orderable(fmaxf(me.z, me.w));
           for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2) {
+            if (g.thr >= 0.0f && (my_lo >= kmaxlo[c2] || my_hi <= kminhi[c2])) continue;
             int k = khead[c2];
             float4 kb = make_float4(0, 0, 0, 0);
             int meta = 0;
@@ -803,7 +808,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         const int nwords = (cn + 31) >> 5;
         for (int w = 0; w < nwords; ++w) {
           unsigned a = ~__shfl_sync(0xffffffffu, removed, w);          // alive candidates of word w
-          if (a == 0u) continue;
+          if (a == 0u) continue;       // (a ballot that jumps to the next alive word measured slower: 104k vs 95k clk)
           if (__popc(a) <= 6) {
             // few alive candidates (dense scenes after phase A): hop from kept box to kept box; every lane reads the
             // diagonal word of the kept row (broadcast) and its own later word
@@ -871,6 +876,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
             const int ci = ccls[i];
             kbox[slot] = cbox[i];
             kmeta[slot] = use_lists ? (ci | ((atomicExch(&khead[ci], slot) + 1) << 10)) : ci;
+            if (use_lists) {
+              const float4 kb = cbox[i];
+              float lo = fminf(kb.z, kb.w), hi = fmaxf(kb.x, kb.y);
+              if (!(kb.x == kb.x && kb.y == kb.y && kb.z == kb.z && kb.w == kb.w)) { lo = INFINITY; hi = -INFINITY; }   // NaN: never skipped
+              atomicMax(&kmaxlo[ci], orderable(lo));
+              atomicMin(&kminhi[ci], orderable(hi));
+            }
           }
         }
         if (tid == 0) s_nkept = nk + cnt;
