@@ -34,10 +34,10 @@ static constexpr int kNmsThreads = 512;
 static constexpr int kMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
 static constexpr int kMaskPitch = kChunkWords + 1;   // words per mask row: odd pitch, column reads are bank-conflict free
 static constexpr int kChunkBytes = kChunk * 24 + kChunk * kMaskPitch * 4;
-static constexpr int kClassCap = 1024;      // class ids below this get a linked list of kept boxes
+static constexpr int kClassCap = 512;       // class ids below this get a linked list of kept boxes
 static constexpr int kNmsFixedBytes = kChunkBytes + kChunk * 4 + 3 * kClassCap * 4;   // + survivors, list heads, two bounds per class
 static constexpr int kKeptEntryBytes = 20;  // box 16 + (class | next << 10) 4; the area is recomputed (3 flops)
-static constexpr int kNmsSmemBudget = 225 * 1024;   // dynamic shared memory: 8 652 kept entries, i.e. every anchor of a 640^2 image
+static constexpr int kNmsSmemBudget = 224 * 1024;   // dynamic shared memory (+ ~3.5 KB static <= 228 KB per CTA): 8 704 kept entries, i.e. every anchor of a 640^2 image
 
 static constexpr int kNmsMaxCluster = 8;             // CTAs of one image's thread-block cluster (sort_nms_kernel<true>)
 
@@ -465,9 +465,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
   __shared__ int red_cmax[kNmsThreads / 32], red_cmin[kNmsThreads / 32];
   __shared__ int s_nkept, s_ck;
   __shared__ unsigned s_removed[kChunkWords];
-  __shared__ unsigned short s_alive[kChunk];    // rows of the chunk that survived phase A, ascending
-  __shared__ int s_nalive;
-  __shared__ unsigned s_deadx[CL ? kNmsMaxCluster * kChunkWords : 1];   // [R][16] dead bits found by every CTA
+  __shared__ unsigned short s_cpos[kChunk];     // sorted position of every batch row, relative to the batch's first group
+  __shared__ unsigned s_deadx[CL ? 2 * kNmsMaxCluster * kChunkWords : 1];   // [2][R][16] dead bits found by every CTA
   __shared__ float s_xf[CL ? kNmsMaxCluster * 2 : 1];                   // [R] (max, min) coordinate of every run
   __shared__ int s_xi[CL ? kNmsMaxCluster * 2 : 1];                     // [R] (max, min) class of every run
 
@@ -674,105 +673,134 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     const bool use_lists = (J <= 4) && cmin >= 0 && cmax < kClassCap;
     for (int i = tid; i < kClassCap; i += kNmsThreads) { khead[i] = -1; kmaxlo[i] = 0u; kminhi[i] = 0xffffffffu; }
 
-    // row of the next chunk, loaded one chunk ahead (the global-memory latency hides behind phases B and C)
-    float4 nx_box = make_float4(0, 0, 0, 0);
-    int nx_cls = -1;
-    if (tid < n) { nx_box = sbox[tid]; nx_cls = scls[tid]; }
+    // The sorted candidates are walked in groups of 512 (thread t owns candidate g0 + t). Phase A tests a group against
+    // the boxes kept so far; its survivors are appended, in order, to a BATCH of up to 512 rows. Only a batch goes through
+    // the suppression mask (phase B) and the greedy scan (phase C): in a dense scene most candidates die in phase A, so
+    // one batch collects the survivors of several groups and B / C run a few times instead of once per group. This is
+    // exact: the survivors of a later group were not tested against the keeps of the pending batch, but those keeps are
+    // rows of the same batch and suppress them through the mask. A group whose survivors do not fit the batch is tested
+    // again after the batch has been resolved (against the longer kept list).
+    float4 cur_box = make_float4(0, 0, 0, 0), nx_box = cur_box;          // rows of this group / the next (loaded ahead)
+    int cur_cls = -1, nx_cls = -1;
+    if (tid < n) { cur_box = sbox[tid]; cur_cls = scls[tid]; }
+    if (kChunk + tid < n) { nx_box = sbox[kChunk + tid]; nx_cls = scls[kChunk + tid]; }
+    int g0 = 0;                       // first candidate of the group
+    int nb = 0, cbase = 0;            // rows in the batch; sorted position of its first group (s_cpos is relative to it)
+    unsigned turn = 0;                // phase-A executions so far: parity selects the dead-bit exchange buffer
     t_prev = clock64();
-    for (int c0 = 0; c0 < n; c0 += kChunk) {
-      const int cn = min(kChunk, n - c0);
+    while (g0 < n || nb > 0) {
       __syncthreads();
       const int nk = s_nkept;
       const int nk_own = (nk + R - 1 - rank) / R;        // entries of the kept list this CTA holds
-      // kNmsThreads == kChunk: thread t owns candidate c0 + t
-      float4 me = make_float4(0, 0, 0, 0);
-      float my_area = 0.f;
-      int my_cls = -1;
-      bool dead = (tid >= cn);
-      if (!dead) {
-        me = nx_box; my_cls = nx_cls; my_area = box_area(me);
-      }
-      cbox[tid] = me; carea[tid] = my_area; ccls[tid] = my_cls;
-      if (c0 + kChunk + tid < n) { nx_box = sbox[c0 + kChunk + tid]; nx_cls = scls[c0 + kChunk + tid]; }
-      YX_TR(0)
-      // ---- phase A: against the boxes kept in earlier chunks
-      if (!dead) {
-        const int nks = min(nk_own, KC);
-        if (use_lists) {
-          // (the next entry of a list is loaded while the IoU of the current one is computed)
-          const unsigned my_lo = orderable(fminf(me.x, me.y)), my_hi = orderable(fmaxf(me.z, me.w));
-          for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2) {
-            if (g.thr >= 0.0f && (my_lo >= kmaxlo[c2] || my_hi <= kminhi[c2])) continue;
-            int k = khead[c2];
-            float4 kb = make_float4(0, 0, 0, 0);
-            int meta = 0;
-            if (k >= 0) { kb = kbox[k]; meta = kmeta[k]; }
-            while (k >= 0) {
-              const int kn = (meta >> 10) - 1;
-              float4 kbn = kb;
-              int metan = 0;
-              if (kn >= 0) { kbn = kbox[kn]; metan = kmeta[kn]; }
+      bool flush = true;
+      if (g0 < n) {
+        const int gn = min(kChunk, n - g0);
+        const float4 me = cur_box;
+        const int my_cls = cur_cls;
+        const float my_area = box_area(me);
+        bool dead = (tid >= gn);
+        YX_TR(0)
+        // ---- phase A: against the boxes kept so far
+        if (!dead) {
+          const int nks = min(nk_own, KC);
+          if (use_lists) {
+            // (the next entry of a list is loaded while the IoU of the current one is computed)
+            const unsigned my_lo = orderable(fminf(me.x, me.y)), my_hi = orderable(fmaxf(me.z, me.w));
+            for (int c2 = max(my_cls - J, 0); c2 <= min(my_cls + J, kClassCap - 1) && !dead; ++c2) {
+              if (g.thr >= 0.0f && (my_lo >= kmaxlo[c2] || my_hi <= kminhi[c2])) continue;
+              int k = khead[c2];
+              float4 kb = make_float4(0, 0, 0, 0);
+              int meta = 0;
+              if (k >= 0) { kb = kbox[k]; meta = kmeta[k]; }
+              while (k >= 0) {
+                const int kn = (meta >> 10) - 1;
+                float4 kbn = kb;
+                int metan = 0;
+                if (kn >= 0) { kbn = kbox[kn]; metan = kmeta[kn]; }
+                if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+                k = kn; kb = kbn; meta = metan;
+              }
+            }
+          } else {
+            for (int k = 0; k < nks; ++k) {
+              if (abs(kmeta[k] - my_cls) > J) continue;
+              const float4 kb = kbox[k];
               if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
-              k = kn; kb = kbn; meta = metan;
             }
           }
-        } else {
-          for (int k = 0; k < nks; ++k) {
-            if (abs(kmeta[k] - my_cls) > J) continue;
-            const float4 kb = kbox[k];
-            if (suppresses(kb, box_area(kb), me, my_area, g.thr)) { dead = true; break; }
+          for (int k = KC; k < nk_own && !dead; ++k) {       // overflow of the shared-memory list
+            const int kp = kept[k * R + rank];
+            if (abs(scls[kp] - my_cls) > J) continue;
+            const float4 kb = sbox[kp];
+            if (suppresses(kb, box_area(kb), me, my_area, g.thr)) dead = true;
           }
         }
-        for (int k = KC; k < nk_own && !dead; ++k) {       // overflow of the shared-memory list
-          const int kp = kept[k * R + rank];
-          if (abs(scls[kp] - my_cls) > J) continue;
-          const float4 kb = sbox[kp];
-          if (suppresses(kb, box_area(kb), me, my_area, g.thr)) dead = true;
-        }
-      }
-      YX_TR(1)
-      {
-        const unsigned bal = __ballot_sync(0xffffffffu, dead);
-        if constexpr (CL) {
-          if (lane < R) nms_peer(s_deadx, lane)[rank * kChunkWords + warp] = bal;
-          nms_cluster_sync();                              // (1) every CTA's dead bits have arrived
-          if (tid < kChunkWords) {
-            unsigned u = 0u;
-            for (int rr = 0; rr < R; ++rr) u |= s_deadx[rr * kChunkWords + tid];
-            s_removed[tid] = u;
+        YX_TR(1)
+        {
+          const unsigned bal = __ballot_sync(0xffffffffu, dead);
+          if constexpr (CL) {
+            // double buffered by turn: a CTA that runs ahead writes the next group's bits while this one still reads
+            unsigned* dx = s_deadx + (turn & 1u) * (kNmsMaxCluster * kChunkWords);
+            if (lane < R) nms_peer(dx, lane)[rank * kChunkWords + warp] = bal;
+            nms_cluster_sync();                              // (1) every CTA's dead bits have arrived
+            if (tid < kChunkWords) {
+              unsigned u = 0u;
+              for (int rr = 0; rr < R; ++rr) u |= dx[rr * kChunkWords + tid];
+              s_removed[tid] = u;
+            }
+          } else {
+            if (lane == 0) s_removed[warp] = bal;
           }
-        } else {
-          if (lane == 0) s_removed[warp] = bal;
+          ++turn;
         }
+        __syncthreads();
+        // survivors of the group and this thread's place among them (uniform counts: every thread reads the 16 words)
+        int surv = 0, before = 0;
+#pragma unroll
+        for (int l = 0; l < kChunkWords; ++l) {
+          const int pc = __popc(~s_removed[l]);
+          surv += pc;
+          before += l < warp ? pc : 0;
+        }
+        const bool alive = !((s_removed[warp] >> lane) & 1u);
+        { const long long t = clock64(); acc_a += t - t_prev; t_prev = t; }
+        if (nb + surv <= kChunk) {
+          if (nb == 0) cbase = g0;
+          if (alive) {
+            const int row = nb + before + __popc(~s_removed[warp] & ((1u << lane) - 1u));
+            cbox[row] = me; carea[row] = my_area; ccls[row] = my_cls;
+            s_cpos[row] = (unsigned short)(g0 + tid - cbase);
+          }
+          nb += surv;
+          g0 += kChunk;
+          cur_box = nx_box; cur_cls = nx_cls;
+          if (g0 + kChunk + tid < n) { nx_box = sbox[g0 + kChunk + tid]; nx_cls = scls[g0 + kChunk + tid]; }
+          // resolve the batch when it is nearly full, at the end of the list, or before its 16-bit positions run out
+          flush = nb >= kChunk - kChunk / 4 || g0 >= n || g0 - cbase > 60000;
+        }
+        // else: the batch is resolved first and the group tested again
       }
-      { const long long t = clock64(); acc_a += t - t_prev; t_prev = t; }
-      // ---- phase B: suppression bitmask inside the chunk (row i, bits j > i), for the rows AND columns that survived
-      //      phase A only: phase C never looks at a bit of a removed candidate, neither as a row nor as a column
+      if (!flush || nb == 0) continue;
+
+      const int cn = nb;
+      const int nw = (cn + 31) >> 5;
+      // ---- phase B: suppression bitmask inside the batch (row i, bits j > i)
       {
         __syncthreads();
-        const int nw = (cn + 31) >> 5;
-        if (warp < nw) {                                   // warp w compacts the alive rows of word w
-          int before = 0;
-          for (int l = 0; l < warp; ++l) before += __popc(~s_removed[l]);
-          const unsigned al = ~s_removed[warp];
-          if ((al >> lane) & 1u) s_alive[before + __popc(al & ((1u << lane) - 1u))] = (unsigned short)(warp * 32 + lane);
-          if (warp == nw - 1 && lane == 0) s_nalive = before + __popc(al);
-        }
-        __syncthreads();
-        // items (alive row, word): 16 per row, the words before the row's own are skipped; with a cluster the items are
+        // items (row, word): 16 per row, the words before the row's own are skipped; with a cluster the items are
         // dealt round-robin over the CTAs and stored into CTA 0's mask
-        const int items = s_nalive << 4;
+        const int items = cn << 4;
         YX_TR(2)
         for (int q = rank * kNmsThreads + tid; q < items; q += R * kNmsThreads) {
-          const int row = s_alive[q >> 4];
+          const int row = q >> 4;
           const int w = q & (kChunkWords - 1);
           if (w < (row >> 5) || w >= nw) continue;
           const float4 rbx = cbox[row];
           const float rar = carea[row];
           const int rcl = ccls[row];
-          // alive columns of the word that come after the row
-          const int lo_bit = row + 1 - w * 32;
-          unsigned m = ~s_removed[w] & (lo_bit <= 0 ? 0xffffffffu : (lo_bit >= 32 ? 0u : (0xffffffffu << lo_bit)));
+          // columns of the word that come after the row and exist
+          const int lo_bit = row + 1 - w * 32, hi_bit = cn - w * 32;
+          unsigned m = (hi_bit >= 32 ? 0xffffffffu : ((1u << hi_bit) - 1u)) & (lo_bit <= 0 ? 0xffffffffu : (lo_bit >= 32 ? 0u : (0xffffffffu << lo_bit)));
           if (J != 0x3fffffff && __popc(m) > 8) {
             // class gate first, as a bit mask (the lanes of a warp hold up to 16 different words: column jb + w of
             // the word is read in step jb, so that the lanes hit different banks), ...
@@ -799,19 +827,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // (2) CTA 0 holds the whole mask
       }
       { const long long t = clock64(); acc_b += t - t_prev; t_prev = t; }
-      // ---- phase C: one warp walks the chunk word by word (32 candidates); lane l owns word l of the removed
-      //      set. Inside a word the greedy order is resolved on the 32x32 diagonal block held in registers;
-      //      the rows of the kept boxes are then OR-ed into the later words.
+      // ---- phase C: one warp walks the batch word by word (32 rows); lane l owns word l of the removed set (at the
+      //      start: the rows past the end of the batch). Inside a word the greedy order is resolved on the 32x32 diagonal
+      //      block held in registers; the rows of the kept boxes are then OR-ed into the later words.
       if (warp == 0 && rank == 0) {
-        unsigned removed = lane < kChunkWords ? s_removed[lane] : 0xffffffffu;
+        unsigned removed = 0xffffffffu;
+        if (lane < nw) removed = (cn - lane * 32 >= 32) ? 0u : (0xffffffffu << (cn - lane * 32));
         int cnt = 0;
-        const int nwords = (cn + 31) >> 5;
+        const int nwords = nw;
         for (int w = 0; w < nwords; ++w) {
           unsigned a = ~__shfl_sync(0xffffffffu, removed, w);          // alive candidates of word w
           if (a == 0u) continue;       // (a ballot that jumps to the next alive word measured slower: 104k vs 95k clk)
           if (__popc(a) <= 6) {
-            // few alive candidates (dense scenes after phase A): hop from kept box to kept box; every lane reads the
-            // diagonal word of the kept row (broadcast) and its own later word
+            // few alive candidates: hop from kept box to kept box; every lane reads the diagonal word of the kept row
+            // (broadcast) and its own later word
             while (a) {
               const int i = __ffs(a) - 1;
               const unsigned* rowp = cmask + (w * 32 + i) * kMaskPitch;
@@ -842,9 +871,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
             ck[slot] = w * 32 + lane;
           }
           cnt += __popc(keptw);
-          // rows of the kept boxes OR-ed into the later words. Few kept boxes (dense scenes: most of the word is
-          // suppressed): lane l walks the kept rows and ORs word l of each (independent loads). Many: lane i
-          // contributes its row, one warp reduction per later word. Same result either way.
+          // rows of the kept boxes OR-ed into the later words. Few kept boxes: lane l walks the kept rows and ORs word
+          // l of each (independent loads). Many: lane i contributes its row, one warp reduction per later word. Same
+          // result either way.
           if (__popc(keptw) < nwords - 1 - w) {
             if (lane > w && lane < nwords) {
               unsigned r = 0u;
@@ -861,16 +890,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         if (lane == 0) s_ck = cnt;
         YX_TR(4)
       }
-      if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) CTA 0 has the chunk's survivors
+      if constexpr (CL) nms_cluster_sync(); else __syncthreads();     // (3) CTA 0 has the batch's survivors
       { const long long t = clock64(); acc_c += t - t_prev; t_prev = t; }
-      // ---- append the chunk's survivors to the kept list (parallel; list order is irrelevant)
+      // ---- append the batch's survivors to the kept list (parallel; list order is irrelevant)
       {
-        // (the other CTAs read CTA 0's list: it is rewritten only after barrier (2) of the next chunk)
+        // (the other CTAs read CTA 0's list: it is rewritten only after barrier (2) of the next batch)
         const int cnt = (CL && rank != 0) ? *nms_peer(&s_ck, 0) : s_ck;
         if (tid < cnt) {
           const int i = (CL && rank != 0) ? nms_peer(ck, 0)[tid] : ck[tid];
           const int e = nk + tid;
-          if (rank == 0) kept[e] = c0 + i;
+          if (rank == 0) kept[e] = cbase + (int)s_cpos[i];
           const int slot = e / R;
           if (e - slot * R == rank && slot < KC) {
             const int ci = ccls[i];
@@ -887,6 +916,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
         }
         if (tid == 0) s_nkept = nk + cnt;
       }
+      nb = 0;
       __syncthreads();
       { const long long t = clock64(); acc_d += t - t_prev; t_prev = t; }
     }
