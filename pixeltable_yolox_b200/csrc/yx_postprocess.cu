@@ -231,7 +231,17 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
   const float inter = __fmul_rn(w, h);
   // disjoint boxes: 0 / x is 0 (or NaN for 0 / 0), never > thr for thr >= 0 -- skip the IEEE division
   if (inter == 0.0f && thr >= 0.0f) return false;
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // The IEEE division only decides pairs within 2^-20 of the threshold. Rounding is monotone, so with q = inter / uni (real):
+  // inter > rn(rn(thr * uni) * (1 + 2^-20)) implies q > thr * (1 + 2^-21) >= thr + ulp(thr), hence rn(q) > thr; and
+  // inter < rn(rn(thr * uni) * (1 - 2^-20)) implies q < thr, hence rn(q) <= thr. (Ranges keep thr * uni a normal number; NaNs
+  // fail both compares and take the division.)
+  if (uni > 1e-18f && uni < 1e18f && thr > 1e-6f && thr < 1e6f) {
+    const float p = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(p, 1.00000095367431640625f)) return true;
+    if (inter < __fmul_rn(p, 0.99999904632568359375f)) return false;
+  }
+  const float ovr = __fdiv_rn(inter, uni);
   return ovr > thr;
 }
 __device__ __forceinline__ float box_area(const float4 b) {
@@ -428,9 +438,11 @@ __device__ __forceinline__ unsigned long long* merge_sort_keys(unsigned long lon
 __device__ __forceinline__ void nms_load_row(const NmsArgs& g, long long base, int idx, float4& bx, int& c) {
   if (g.src.cand_rows) {
     // candidate rows of the score filter: 8 floats (x1, y1, x2, y2, obj, class_conf, class, score), 32-byte aligned
-    const float4* row = reinterpret_cast<const float4*>(g.src.boxes + (base + idx) * 8);
-    bx = row[0];
-    c = (int)row[1].z;
+    float o, cc, cl, sc;                      // one 256-bit load (sm_100: LDG.256)
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(bx.x), "=f"(bx.y), "=f"(bx.z), "=f"(bx.w), "=f"(o), "=f"(cc), "=f"(cl), "=f"(sc)
+                 : "l"(g.src.boxes + (base + idx) * 8));
+    c = (int)cl;
     return;
   }
   const float* bp = g.src.boxes + (base + idx) * g.src.box_stride;
