@@ -677,7 +677,7 @@ def run_ours(args):
                 print(f"# {p['name']:44s} {p['ms']*1e3:9.1f} us  {p['flops']/max(p['ms'],1e-9)/1e9:8.1f} TFLOP/s  "
                       f"{p['bytes']/max(p['ms'],1e-9)/1e6:8.1f} GB/s", file=sys.stderr)
         traffic, traffic_src = None, None
-        tfiles = sorted((ROOT / "profiles").glob("*_traffic.json"))
+        tfiles = sorted(f for f in (ROOT / "profiles").glob("*_traffic.json") if "train" not in f.name)   # the inference step's own list
         if tfiles:                                   # DRAM bytes per launch of the same kernel from the committed ncu pass
             tj = json.loads(tfiles[-1].read_text())
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), f"profiles/{tfiles[-1].name}"
