@@ -9,17 +9,19 @@
 //                             obj*class_conf (one fp32 multiply), cxcywh->xyxy exactly as
 //                             boxes.py:32-37, dense candidate row + 64-bit sort key for anchors with
 //                             score >= conf_thre (warp-aggregated append).
-// Stage 2  sort_nms_kernel    one CTA per image: bitonic sort of the keys (descending score,
-//                             ascending anchor = torch's stable descending sort) in shared memory,
-//                             then greedy NMS in chunks of 512 sorted candidates: a chunk is first
-//                             tested against the boxes already kept (they sit in L1/L2), then the
-//                             512x512 suppression bitmask of the chunk is built in shared memory
-//                             and scanned by one warp that hops from kept box to kept box with
-//                             ffs. The O(n^2/64) mask never touches HBM.
+// Stage 2  sort_nms_kernel    one CTA per image, or one thread-block cluster of 2 / 4 / 8 CTAs per image:
+//                             merge sort of the keys (descending score, ascending anchor = torch's stable
+//                             descending sort) in shared memory, then greedy NMS: groups of 512 sorted
+//                             candidates are tested against the boxes already kept (phase A, per-class
+//                             lists in shared memory); the survivors of several groups form a batch whose
+//                             512x512 suppression bitmask is built in shared memory (phase B) and scanned
+//                             by one warp that hops from kept box to kept box (phase C). Keys, mask and
+//                             kept list never touch HBM. DESIGN.md 4.9 has the phase clocks.
 // IoU arithmetic follows torchvision's nms kernel operation by operation in fp32 (round-to-nearest
 // intrinsics so that nvcc cannot contract multiplies and adds into FMAs):
 //   inter = max(0, min(x2) - max(x1)) * max(0, min(y2) - max(y1));
-//   suppressed iff inter / (area_i + area_j - inter) > thr.
+//   suppressed iff inter / (area_i + area_j - inter) > thr   (the division itself only runs within 2^-20 of
+//   the threshold; outside that band a multiply decides with the same result, see suppresses()).
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
