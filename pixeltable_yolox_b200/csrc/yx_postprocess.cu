@@ -41,6 +41,7 @@ static constexpr int kNmsFixedBytes = kChunkBytes + kChunk * 4 + 3 * kClassCap *
 static constexpr int kKeptEntryBytes = 20;  // box 16 + (class | next << 10) 4; the area is recomputed (3 flops)
 static constexpr int kNmsSmemBudget = 224 * 1024;   // dynamic shared memory (+ ~3.5 KB static <= 228 KB per CTA): 8 704 kept entries, i.e. every anchor of a 640^2 image
 
+static constexpr int kFlushRows = 192;               // survivor batch: resolved once it holds this many of its 512 rows (measured sweep 128..512: flat within 3 %, profiles/r2_nms_flush_sweep.jsonl; YX_NMS_FLUSH overrides)
 static constexpr int kNmsMaxCluster = 8;             // CTAs of one image's thread-block cluster (sort_nms_kernel<true>)
 
 __device__ __forceinline__ uint32_t orderable(float f) { return orderable_f32(f); }
@@ -213,6 +214,7 @@ struct NmsArgs {
   long long gkeys_stride;          // keys per image in gkeys (next_pow2(per_image))
   int smem_keys_cap;               // number of 64-bit keys the dynamic shared memory can hold
   int smem_bytes;                  // dynamic shared memory of the launch
+  int flush_rows;                  // a batch of phase-A survivors is resolved once it holds this many rows
   int kept_cap;                    // kept boxes that fit the shared-memory kept list
   float4* sorted_box;              // boxes as NMS sees them (offset applied for variant 0)
   int* sorted_cls;
@@ -790,7 +792,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
           cur_box = nx_box; cur_cls = nx_cls;
           if (g0 + kChunk + tid < n) { nx_box = sbox[g0 + kChunk + tid]; nx_cls = scls[g0 + kChunk + tid]; }
           // resolve the batch when it is nearly full, at the end of the list, or before its 16-bit positions run out
-          flush = nb >= kChunk - kChunk / 4 || g0 >= n || g0 - cbase > 60000;
+          flush = nb >= g.flush_rows || g0 >= n || g0 - cbase > 60000;
         }
         // else: the batch is resolved first and the group tested again
       }
@@ -1064,6 +1066,8 @@ static int launch_sort_nms(NmsArgs& g, int batch, cudaStream_t s) {
   g.gkeys_stride = next_pow2_ll(g.src.per_image);
   g.debug = getenv("YX_NMS_DEBUG") ? 1 : 0;
   g.no_small = getenv("YX_NMS_NO_SMALL") ? 1 : 0;
+  g.flush_rows = kFlushRows;
+  if (const char* e = getenv("YX_NMS_FLUSH")) { const int v = atoi(e); if (v >= 32 && v <= kChunk) g.flush_rows = v; }
   const size_t smem = nms_smem_bytes(g.src.per_image);
   g.smem_bytes = (int)smem;
   static size_t configured_dev[kMaxDevices] = {};
