@@ -468,12 +468,12 @@ __device__ __forceinline__ unsigned long long nms_key(const NmsArgs& g, long lon
 //            key is its index in its run plus its lower bounds in the other runs (binary searches through distributed
 //            shared memory; keys are unique), and the CTA scatters box / class / index there
 //   phase A  the kept list is dealt round-robin over the CTAs (entry e lives in CTA e % R): every CTA tests the whole
-//            chunk against its share, the 512 dead bits are OR-ed through distributed shared memory
-//   phase B  the (row, word) items of the chunk's suppression mask are dealt round-robin; every CTA stores its words
+//            group against its share, the 512 dead bits are OR-ed through distributed shared memory
+//   phase B  the (row, word) items of the batch's suppression mask are dealt round-robin; every CTA stores its words
 //            into the mask of CTA 0
-//   phase C  greedy scan by one warp of CTA 0, which broadcasts the chunk's survivors; every CTA appends its share
-// Three cluster barriers per chunk. The arithmetic of every IoU test and the greedy order are those of CL = false:
-// kept rows are bit-identical for every R.
+//   phase C  greedy scan by one warp of CTA 0; the other CTAs read its survivor list and every CTA appends its share
+// One cluster barrier per group and two per batch. The arithmetic of every IoU test and the greedy order are those of
+// CL = false: kept rows are bit-identical for every R.
 template <bool CL>
 __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs g) {
   extern __shared__ __align__(16) uint8_t nsm[];
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
 
   if (tid == 0) s_nkept = 0;
   long long tk[8];
-  long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0, t_prev = 0;   // YX_NMS_DEBUG: clocks per phase over all chunks
+  long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0, t_prev = 0;   // YX_NMS_DEBUG: clocks per phase over all groups / batches
 #ifdef YX_NMS_TRACE
   long long tr[6] = {0, 0, 0, 0, 0, 0};
 #define YX_TR(k) { tr[k] += clock64() - t_prev; }
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     if constexpr (CL) nms_cluster_sync(); else __syncthreads();   // sorted rows visible; runs no longer read
 
     tk[2] = clock64();
-    // ---------------- greedy NMS, chunk by chunk ----------------
+    // ---------------- greedy NMS: groups of 512 candidates, batches of survivors ----------------
     // Which pairs can interact?  per-class variant: equal classes only.  Offset variant: class c lives in
     // [c*s + min, c*s + max] with s = max+1, so classes a < b can only overlap when (b-a)*s < max-min+1,
     // i.e. |a-b| <= J with J = ceil((max-min+1)/s) - 1 (J = 0 when no coordinate is negative; J = 1 for
@@ -655,15 +655,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
     // torchvision's own arithmetic, so skipping them is exact.  Class-agnostic: everything interacts.
     //
     // shared memory (the sort buffer is dead now):
-    //   chunk : box/area/class of the 512 candidates in flight, their 512x512 suppression bitmask, and a
-    //           linked list of chunk members per class
+    //   batch : box/area/class of up to 512 phase-A survivors, their 512x512 suppression bitmask, the rows kept by the scan
     //   kept  : boxes already kept (box, area, class) with a linked list per class; with a cluster, this CTA's share
     //           (global entry e = slot * R + rank)
     float4* cbox = reinterpret_cast<float4*>(nsm);                          // [kChunk]
     float* carea = reinterpret_cast<float*>(nsm + kChunk * 16);              // [kChunk]
     int* ccls = reinterpret_cast<int*>(nsm + kChunk * 20);                   // [kChunk]
     unsigned* cmask = reinterpret_cast<unsigned*>(nsm + kChunk * 24);        // [kChunk][kMaskPitch]
-    int* ck = reinterpret_cast<int*>(nsm + kChunkBytes);                     // [kChunk] kept members of the chunk
+    int* ck = reinterpret_cast<int*>(nsm + kChunkBytes);                     // [kChunk] kept rows of the batch
     int* khead = ck + kChunk;                                                // [kClassCap] list heads
     // bounds of a class's kept boxes (orderable_f32): max over the list of min(x2, y2), min over the list of max(x1, y1).
     // A box whose min(x1, y1) is not below the first, or whose max(x2, y2) is not above the second, overlaps no entry in
@@ -936,7 +935,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) sort_nms_kernel(const NmsArgs 
       __syncthreads();
       { const long long t = clock64(); acc_d += t - t_prev; t_prev = t; }
     }
-    if constexpr (CL) nms_cluster_sync();   // the other CTAs have read the last chunk's survivors from CTA 0
+    if constexpr (CL) nms_cluster_sync();   // the other CTAs have read the last batch's survivors from CTA 0
   }
   __syncthreads();
   if (rank != 0) return;
