@@ -16,3 +16,10 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:stem
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 3 -c 1 -o gpurun_out/prof_head_$tag \
   python tools/gpu_prof_head.py 64 80 > gpurun_out/ncu_h_$tag.log 2>&1
 ls -la gpurun_out/*_$tag*
+# cluster NMS (config 5 dense scene) and SimOTA: live comparison + one full capture each (profiles/r2_nms_cluster.*, r2_simota.md)
+timeout 150 python tools/gpu_nms_cluster.py gpurun_out/nms_cluster_$tag.json > gpurun_out/nms_cluster_$tag.log 2>&1
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:sort_nms -s 2 -c 1 -f -o gpurun_out/prof_nms_$tag \
+  python tools/gpu_nms_one.py > gpurun_out/ncu_n_$tag.log 2>&1
+timeout 150 ncu --set full --clock-control none -k regex:simota_assign -c 1 -f -o gpurun_out/prof_simota_$tag \
+  python -m pytest tests/test_gpu_simota.py -q -m gpu -k "test_simota_assign_vs_reference and s640" > gpurun_out/ncu_sim_$tag.log 2>&1
+for k in nms simota; do ncu -i gpurun_out/prof_${k}_$tag.ncu-rep --page raw --csv > gpurun_out/prof_${k}_${tag}_raw.csv 2>/dev/null; done
